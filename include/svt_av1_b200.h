@@ -1,0 +1,209 @@
+/*
+ * svt_av1_b200.h — C ABI of the B200 (sm_100a) hot-path library `libsvtav1_b200.so`.
+ *
+ * Scope: open-loop motion estimation (HME + full-pel SAD search), residual +
+ * forward/inverse transform + quantisation, and the in-loop filters (deblock, CDEF, restoration)
+ * of SVT-AV1 v0.8.6.  Two families of entry points:
+ *
+ *  (1) `*_cuda` drop-ins with EXACTLY the signature of the reference's RTCD function pointers
+ *      (Source/Lib/Encoder/Codec/aom_dsp_rtcd.h, Source/Lib/Common/Codec/common_dsp_rtcd.h).
+ *      They take HOST pointers, stage through a thread-local pinned buffer + stream, run the sm_100a
+ *      kernel and copy the result back.  They exist for API fidelity and parity tests; a launch per
+ *      8x8 block can never be fast.  `svt_b200_install_rtcd()` hands their addresses to the patched
+ *      `setup_rtcd_internal`.
+ *
+ *  (2) `svt_b200_*` picture-level ("batched") entries, which are where throughput comes from.  They
+ *      replace the L2 segment loops of the reference (motion_estimation_kernel, EncDec final pass,
+ *      dlf_kernel, cdef_kernel, rest_kernel).  All pointers are DEVICE pointers unless the name ends
+ *      in `_host`; `stream` is a `cudaStream_t` passed as `void*` (NULL = default stream).
+ *
+ * No torch / C++ types cross this boundary.  Every function returns 0 on success or a negative
+ * SvtB200Status; there is NO CPU fallback — a missing GPU is an error.
+ */
+#ifndef SVT_AV1_B200_H
+#define SVT_AV1_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVT_B200_API __attribute__((visibility("default")))
+
+typedef enum SvtB200Status {
+    SVT_B200_OK = 0,
+    SVT_B200_ERR_CUDA = -1, /* a CUDA runtime call failed (message via svt_b200_last_error) */
+    SVT_B200_ERR_ARG = -2, /* bad argument */
+    SVT_B200_ERR_UNSUPPORTED = -3 /* configuration outside what the kernels implement */
+} SvtB200Status;
+
+/* ---- library / device management -------------------------------------------------------------- */
+SVT_B200_API int svt_b200_version(void);
+SVT_B200_API int svt_b200_device_count(void); /* <0 on error, 0 if no GPU */
+SVT_B200_API int svt_b200_set_device(int device);
+SVT_B200_API const char *svt_b200_last_error(void); /* thread-local text of the last failure */
+/* Number of kernel launches issued by this library since load (all threads); bench.py reports it. */
+SVT_B200_API uint64_t svt_b200_launch_count(void);
+SVT_B200_API void *svt_b200_malloc(size_t bytes); /* cudaMalloc */
+SVT_B200_API void svt_b200_free(void *dptr);
+SVT_B200_API void *svt_b200_malloc_host(size_t bytes); /* pinned host memory */
+SVT_B200_API void svt_b200_free_host(void *hptr);
+SVT_B200_API int svt_b200_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+SVT_B200_API int svt_b200_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+SVT_B200_API int svt_b200_stream_sync(void *stream);
+
+/* =============================================================================================== */
+/* (1) RTCD drop-ins: motion estimation                                                            */
+/* =============================================================================================== */
+
+/* replaces svt_sad_loop_kernel  (aom_dsp_rtcd.h:597; C impl Encoder/C_DEFAULT/EbComputeSAD_C.c:57) */
+SVT_B200_API void svt_sad_loop_kernel_cuda(uint8_t *src, uint32_t src_stride, uint8_t *ref,
+                                           uint32_t ref_stride, uint32_t block_height,
+                                           uint32_t block_width, uint64_t *best_sad,
+                                           int16_t *x_search_center, int16_t *y_search_center,
+                                           uint32_t src_stride_raw, int16_t search_area_width,
+                                           int16_t search_area_height);
+
+/* replaces svt_ext_all_sad_calculation_8x8_16x16 (aom_dsp_rtcd.h:640; EbMotionEstimation.c:362) */
+SVT_B200_API void svt_ext_all_sad_calculation_8x8_16x16_cuda(
+    uint8_t *src, uint32_t src_stride, uint8_t *ref, uint32_t ref_stride, uint32_t mv,
+    uint32_t *p_best_sad_8x8, uint32_t *p_best_sad_16x16, uint32_t *p_best_mv8x8,
+    uint32_t *p_best_mv16x16, uint32_t p_eight_sad16x16[16][8], uint32_t p_eight_sad8x8[64][8],
+    uint8_t sub_sad);
+
+/* replaces svt_ext_eight_sad_calculation_32x32_64x64 (aom_dsp_rtcd.h:641; EbMotionEstimation.c:396) */
+SVT_B200_API void svt_ext_eight_sad_calculation_32x32_64x64_cuda(
+    uint32_t p_sad16x16[16][8], uint32_t *p_best_sad_32x32, uint32_t *p_best_sad_64x64,
+    uint32_t *p_best_mv32x32, uint32_t *p_best_mv64x64, uint32_t mv, uint32_t p_sad32x32[4][8]);
+
+/* replaces svt_ext_sad_calculation_8x8_16x16 (aom_dsp_rtcd.h:630; EbMotionEstimation.c:122) */
+SVT_B200_API void svt_ext_sad_calculation_8x8_16x16_cuda(
+    uint8_t *src, uint32_t src_stride, uint8_t *ref, uint32_t ref_stride, uint32_t *p_best_sad_8x8,
+    uint32_t *p_best_sad_16x16, uint32_t *p_best_mv8x8, uint32_t *p_best_mv16x16, uint32_t mv,
+    uint32_t *p_sad16x16, uint32_t *p_sad8x8, uint8_t sub_sad);
+
+/* replaces svt_ext_sad_calculation_32x32_64x64 (aom_dsp_rtcd.h:636; EbMotionEstimation.c:191) */
+SVT_B200_API void svt_ext_sad_calculation_32x32_64x64_cuda(
+    uint32_t *p_sad16x16, uint32_t *p_best_sad_32x32, uint32_t *p_best_sad_64x64,
+    uint32_t *p_best_mv32x32, uint32_t *p_best_mv64x64, uint32_t mv, uint32_t *p_sad32x32);
+
+/* replaces svt_nxm_sad_kernel (aom_dsp_rtcd.h:644; Encoder/C_DEFAULT/EbComputeSAD_C.c helper) */
+SVT_B200_API uint32_t svt_nxm_sad_kernel_cuda(const uint8_t *src, uint32_t src_stride,
+                                              const uint8_t *ref, uint32_t ref_stride,
+                                              uint32_t height, uint32_t width);
+
+/* replaces svt_initialize_buffer_32bits (aom_dsp_rtcd.h:642): fills count128*4+count32 words */
+SVT_B200_API void svt_initialize_buffer_32bits_cuda(uint32_t *pointer, uint32_t count128,
+                                                    uint32_t count32, uint32_t value);
+
+/* =============================================================================================== */
+/* (2) Picture-level open-loop ME: replaces the SB loop of motion_estimation_kernel               */
+/*     (EbMotionEstimationProcess.c:831-965) -> motion_estimate_sb (EbMotionEstimation.c:2912).    */
+/* =============================================================================================== */
+
+#define SVT_B200_ME_MAX_REFS 4 /* REF_LIST_MAX_DEPTH (EbDefinitions.h) */
+#define SVT_B200_ME_LISTS 2 /* MAX_NUM_OF_REF_PIC_LIST */
+#define SVT_B200_ME_PU 85 /* SQUARE_PU_COUNT: 1x64^2 + 4x32^2 + 16x16^2 + 64x8^2 */
+#define SVT_B200_ME_MAX_MV 7 /* MAX_PA_ME_MV   (EbMotionEstimationLcuResults.h:23) */
+#define SVT_B200_ME_MAX_CAND 23 /* MAX_PA_ME_CAND (EbMotionEstimationLcuResults.h:24) */
+
+/* Geometry of one padded 8-bit luma plane (EbPictureBufferDesc: stride_y, origin_x/y, width/height). */
+typedef struct SvtB200Plane {
+    int32_t stride;
+    int32_t origin_x;
+    int32_t origin_y;
+    int32_t width;
+    int32_t height;
+} SvtB200Plane;
+
+/* Mirror of the MeContext search parameters (EbMotionEstimationContext.h:325-400) that
+ * signal_derivation_me_kernel_oq / set_me_hme_params_oq (EbMotionEstimationProcess.c:113-420) fill,
+ * plus the per-picture fields motion_estimation_kernel copies from the PCS (:914-940). */
+typedef struct SvtB200MeParams {
+    /* geometry (source and every reference share it) */
+    SvtB200Plane full; /* input_padded_picture_ptr */
+    SvtB200Plane quarter; /* quarter_{decimated,filtered}_picture_ptr */
+    SvtB200Plane sixteenth; /* sixteenth_{decimated,filtered}_picture_ptr */
+    /* reference structure */
+    int32_t num_lists; /* num_of_list_to_search + 1: 1 (P) or 2 (B) */
+    int32_t num_refs[SVT_B200_ME_LISTS]; /* num_of_ref_pic_to_search[] (<=4, list1 <=3) */
+    int32_t ref_dist[SVT_B200_ME_LISTS][SVT_B200_ME_MAX_REFS]; /* |poc - ref poc| (get_me_reference) */
+    int32_t temporal_layer_index;
+    int32_t is_used_as_reference_flag;
+    /* HME */
+    int32_t enable_hme_flag, enable_hme_level0_flag, enable_hme_level1_flag, enable_hme_level2_flag;
+    int32_t hme_search_method; /* 0 = FULL_SAD_SEARCH, 1 = SUB_SAD_SEARCH */
+    int32_t me_search_method; /* idem for the full-pel search */
+    int32_t number_hme_search_region_in_width, number_hme_search_region_in_height; /* <=2 each */
+    int32_t hme_level0_total_search_area_width, hme_level0_total_search_area_height;
+    int32_t hme_level0_max_total_search_area_width, hme_level0_max_total_search_area_height;
+    int32_t hme_level0_search_area_in_width_array[2], hme_level0_search_area_in_height_array[2];
+    int32_t hme_level0_max_search_area_in_width_array[2], hme_level0_max_search_area_in_height_array[2];
+    int32_t hme_level1_search_area_in_width_array[2], hme_level1_search_area_in_height_array[2];
+    int32_t hme_level2_search_area_in_width_array[2], hme_level2_search_area_in_height_array[2];
+    /* full-pel ME */
+    int32_t search_area_width, search_area_height, max_me_search_width, max_me_search_height;
+    /* pruning / search-region adjustment (MeHmeRefPruneCtrls, MeSrCtrls) */
+    int32_t enable_me_hme_ref_pruning;
+    int32_t prune_ref_if_hme_sad_dev_bigger_than_th; /* 0xFFFF = off */
+    int32_t prune_ref_if_me_sad_dev_bigger_than_th; /* 0xFFFF = off */
+    int32_t enable_me_sr_adjustment;
+    int32_t reduce_me_sr_based_on_mv_length_th, stationary_hme_sad_abs_th, stationary_me_sr_divisor;
+    int32_t reduce_me_sr_based_on_hme_sad_abs_th, me_sr_divisor_for_low_hme_sad;
+    /* result shaping */
+    int32_t max_number_of_pus_per_sb; /* pcs->max_number_of_pus_per_sb: 85 (or 21 / 5) */
+    int32_t rc_dist_from_8x8; /* 1 if input_resolution <= 480p (EbMotionEstimation.c:3025) */
+} SvtB200MeParams;
+
+/* Device-side planes of one picture: the padded full-res luma and its two decimations. Pointers
+ * address element (0,0) of the PADDED buffer (EbPictureBufferDesc::buffer_y). */
+typedef struct SvtB200MePlanes {
+    const uint8_t *full;
+    const uint8_t *quarter;
+    const uint8_t *sixteenth;
+} SvtB200MePlanes;
+
+/* Per-picture outputs, all device pointers, n_sb = ceil(w/64)*ceil(h/64) superblocks in raster order.
+ *  best_sad / best_mv : [n_sb][2][4][85] — MeContext::p_sb_best_sad / p_sb_best_mv after
+ *                       integer_search_sb; index order is the reference's internal PU order
+ *                       (64x64, 4x 32x32, 16x 16x16 z-order, 64x 8x8 z-order).  MVs are packed
+ *                       (y<<16)|(x&0xffff) in quarter-pel units, as the reference stores them.
+ *  hme                : [n_sb][2][4] {int16 sc_x, int16 sc_y, uint32 do_ref, uint64 hme_sad}
+ *  me_mv              : [n_sb][85*7] {int16 x, int16 y}          (MeSbResults::me_mv_array)
+ *  me_cand            : [n_sb][85*23] uint8 bit-field             (MeSbResults::me_candidate_array;
+ *                       bits 0-1 direction, 2-3 ref_idx_l0, 4-5 ref_idx_l1, 6 ref0_list, 7 ref1_list;
+ *                       the index of the list a uni-pred candidate does NOT use is written as 0 —
+ *                       the reference leaves a stale value there that nothing reads)
+ *  total_cand         : [n_sb][85] uint8                          (total_me_candidate_index)
+ *  rc_me_distortion   : [n_sb] uint32                             (pcs->rc_me_distortion) */
+typedef struct SvtB200HmeResult {
+    int16_t sc_x, sc_y;
+    uint32_t do_ref;
+    uint64_t hme_sad;
+} SvtB200HmeResult;
+
+typedef struct SvtB200MeOutputs {
+    uint32_t *best_sad;
+    uint32_t *best_mv;
+    SvtB200HmeResult *hme;
+    int16_t *me_mv;
+    uint8_t *me_cand;
+    uint8_t *total_cand;
+    uint32_t *rc_me_distortion;
+} SvtB200MeOutputs;
+
+/* Bytes of device scratch svt_b200_me_picture needs for a picture of this geometry. */
+SVT_B200_API size_t svt_b200_me_scratch_bytes(const SvtB200MeParams *p);
+
+/* Open-loop ME of one whole picture against up to 2x4 references, all resident in HBM.
+ * refs[list][idx] are only read for idx < num_refs[list]. Asynchronous on `stream`. */
+SVT_B200_API int svt_b200_me_picture(const SvtB200MeParams *p, const SvtB200MePlanes *src,
+                                     const SvtB200MePlanes refs[SVT_B200_ME_LISTS][SVT_B200_ME_MAX_REFS],
+                                     const SvtB200MeOutputs *out, void *scratch, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVT_AV1_B200_H */

@@ -1,0 +1,46 @@
+/* oracle.h — prototypes of the CPU restatement (TEST INFRASTRUCTURE; see the header of each .c file).
+ * Built into oracle/liboracle.so by oracle/Makefile. Never linked into libsvtav1_b200.so. */
+#ifndef SVT_B200_ORACLE_H
+#define SVT_B200_ORACLE_H
+#include <stdint.h>
+#include "../include/svt_av1_b200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+#define ORC_API __attribute__((visibility("default")))
+
+/* ---- me_oracle.c ---- */
+ORC_API uint32_t orc_nxm_sad(const uint8_t *src, uint32_t src_stride, const uint8_t *ref, uint32_t ref_stride,
+                             uint32_t height, uint32_t width);
+ORC_API void orc_sad_loop_kernel(const uint8_t *src, uint32_t src_stride, const uint8_t *ref,
+                                 uint32_t ref_stride, uint32_t block_height, uint32_t block_width,
+                                 uint64_t *best_sad, int16_t *x_search_center, int16_t *y_search_center,
+                                 uint32_t src_stride_raw, int16_t search_area_width, int16_t search_area_height);
+ORC_API void orc_ext_sad_calculation_8x8_16x16(const uint8_t *src, uint32_t src_stride, const uint8_t *ref,
+                                               uint32_t ref_stride, uint32_t *p_best_sad_8x8,
+                                               uint32_t *p_best_sad_16x16, uint32_t *p_best_mv8x8,
+                                               uint32_t *p_best_mv16x16, uint32_t mv, uint32_t *p_sad16x16,
+                                               uint32_t *p_sad8x8, uint8_t sub_sad);
+ORC_API void orc_ext_sad_calculation_32x32_64x64(const uint32_t *p_sad16x16, uint32_t *p_best_sad_32x32,
+                                                 uint32_t *p_best_sad_64x64, uint32_t *p_best_mv32x32,
+                                                 uint32_t *p_best_mv64x64, uint32_t mv, uint32_t *p_sad32x32);
+ORC_API void orc_ext_all_sad_calculation_8x8_16x16(const uint8_t *src, uint32_t src_stride, const uint8_t *ref,
+                                                   uint32_t ref_stride, uint32_t mv, uint32_t *p_best_sad_8x8,
+                                                   uint32_t *p_best_sad_16x16, uint32_t *p_best_mv8x8,
+                                                   uint32_t *p_best_mv16x16, uint32_t p_eight_sad16x16[16][8],
+                                                   uint32_t p_eight_sad8x8[64][8], uint8_t sub_sad);
+ORC_API void orc_ext_eight_sad_calculation_32x32_64x64(uint32_t p_sad16x16[16][8], uint32_t *p_best_sad_32x32,
+                                                       uint32_t *p_best_sad_64x64, uint32_t *p_best_mv32x32,
+                                                       uint32_t *p_best_mv64x64, uint32_t mv,
+                                                       uint32_t p_sad32x32[4][8]);
+ORC_API void orc_me_sb(const SvtB200MeParams *p, const SvtB200MePlanes *src, const SvtB200MePlanes refs[2][4],
+                       int sb_x, int sb_y, uint32_t *best_sad, uint32_t *best_mv, SvtB200HmeResult *hme_out,
+                       int16_t *me_mv, uint8_t *me_cand, uint8_t *total_cand, uint32_t *rc_me_distortion);
+ORC_API void orc_me_picture(const SvtB200MeParams *p, const SvtB200MePlanes *src,
+                            const SvtB200MePlanes refs[2][4], uint32_t *best_sad, uint32_t *best_mv,
+                            SvtB200HmeResult *hme, int16_t *me_mv, uint8_t *me_cand, uint8_t *total_cand,
+                            uint32_t *rc_me_distortion);
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,266 @@
+/*
+ * ref_harness.c — thin C driver around the UNMODIFIED reference (svt-av1 v0.8.6) compiled into
+ * oracle/_ref/libSvtAv1EncRef.so.  TEST INFRASTRUCTURE: it lets the Python tests and bench.py call the
+ * reference's own SB-level / frame-level C routines (which take the encoder's internal structs) with plain
+ * pointers.  It includes the reference headers from /root/reference at build time (never copied) and is
+ * built by Makefile.ref into oracle/_ref/librefharness.so.
+ *
+ * Every entry sets up exactly the fields the reference routine reads, citing where the encoder itself
+ * sets them.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "EbDefinitions.h"
+#include "EbSequenceControlSet.h"
+#include "EbPictureControlSet.h"
+#include "EbPictureBufferDesc.h"
+#include "EbMotionEstimationProcess.h"
+#include "EbMotionEstimation.h"
+#include "EbMotionEstimationContext.h"
+#include "EbMotionEstimationLcuResults.h"
+#include "EbSystemResourceManager.h"
+#include "aom_dsp_rtcd.h"
+#include "common_dsp_rtcd.h"
+
+#include "../include/svt_av1_b200.h"
+
+#define REFH_API __attribute__((visibility("default")))
+
+static int g_rtcd_done = 0;
+REFH_API void refh_init(void) {
+    if (!g_rtcd_done) {
+        setup_common_rtcd_internal(0); /* CPU_FLAGS = 0 -> every pointer = the _c function */
+        setup_rtcd_internal(0);
+        g_rtcd_done = 1;
+    }
+}
+
+static void plane_desc(EbPictureBufferDesc *d, const SvtB200Plane *g, const uint8_t *buf) {
+    memset(d, 0, sizeof(*d));
+    d->buffer_y = (uint8_t *)buf;
+    d->stride_y = (uint16_t)g->stride;
+    d->origin_x = (uint16_t)g->origin_x;
+    d->origin_y = (uint16_t)g->origin_y;
+    d->width = (uint16_t)g->width;
+    d->height = (uint16_t)g->height;
+    d->max_width = (uint16_t)g->width;
+    d->max_height = (uint16_t)g->height;
+    d->bit_depth = EB_8BIT;
+}
+
+/* Derive the preset's ME/HME parameters with the reference's own signal_derivation_me_kernel_oq
+ * (EbMotionEstimationProcess.c:344) and run motion_estimate_sb (EbMotionEstimation.c:2912) over every SB
+ * of one picture, with the per-SB set-up of motion_estimation_kernel (EbMotionEstimationProcess.c:831-940).
+ * planes: src, then refs[list*4+idx]. */
+REFH_API int refh_me_picture(int width, int height, int enc_mode, int n_l0, int n_l1,
+                             const int32_t *ref_dist /*[8]*/, int temporal_layer, int is_ref,
+                             const SvtB200Plane *gfull, const SvtB200Plane *gquarter,
+                             const SvtB200Plane *gsixteenth, const SvtB200MePlanes *src,
+                             const SvtB200MePlanes *refs /*[8]*/, SvtB200MeParams *params_out,
+                             uint32_t *best_sad, uint32_t *best_mv, SvtB200HmeResult *hme, int16_t *me_mv,
+                             uint8_t *me_cand, uint8_t *total_cand, uint32_t *rc_me_distortion) {
+    refh_init();
+    SequenceControlSet *scs = calloc(1, sizeof(*scs));
+    PictureParentControlSet *pcs = calloc(1, sizeof(*pcs));
+    EbObjectWrapper scs_wrap;
+    memset(&scs_wrap, 0, sizeof(scs_wrap));
+    scs_wrap.object_ptr = scs;
+    pcs->scs_wrapper_ptr = &scs_wrap;
+
+    /* sequence-level fields read by ME (EbEncHandle.c set_param_based_on_input / copy_api_from_app) */
+    scs->static_config.use_default_me_hme = EB_TRUE;
+    scs->static_config.frame_rate = 30 << 16;
+    scs->static_config.enable_global_motion = EB_TRUE;
+    scs->static_config.unrestricted_motion_vector = EB_TRUE;
+    scs->sb_sz = 64;
+    /* derive_input_resolution (EbUtility / EbEncHandle.c) on the luma sample count */
+    {
+        uint32_t n = (uint32_t)width * (uint32_t)height;
+        scs->input_resolution = n < INPUT_SIZE_240p_TH   ? INPUT_SIZE_240p_RANGE
+            : n < INPUT_SIZE_360p_TH                     ? INPUT_SIZE_360p_RANGE
+            : n < INPUT_SIZE_480p_TH                     ? INPUT_SIZE_480p_RANGE
+            : n < INPUT_SIZE_720p_TH                     ? INPUT_SIZE_720p_RANGE
+            : n < INPUT_SIZE_1080p_TH                    ? INPUT_SIZE_1080p_RANGE
+            : n < INPUT_SIZE_4K_TH                       ? INPUT_SIZE_4K_RANGE
+                                                         : INPUT_SIZE_8K_RANGE;
+    }
+    pcs->enc_mode = (EbEncMode)enc_mode;
+    pcs->sc_content_detected = 0;
+    pcs->enable_hme_flag = 1; /* EbPictureDecisionProcess.c: hme flags on for all presets by default */
+    pcs->enable_hme_level0_flag = 1;
+    pcs->enable_hme_level1_flag = 1;
+    pcs->enable_hme_level2_flag = 1;
+    pcs->is_used_as_reference_flag = (EbBool)is_ref;
+    pcs->temporal_layer_index = (uint8_t)temporal_layer;
+    pcs->slice_type = n_l1 > 0 ? B_SLICE : P_SLICE;
+    pcs->aligned_width = (uint16_t)width;
+    pcs->aligned_height = (uint16_t)height;
+    pcs->max_number_of_pus_per_sb = SQUARE_PU_COUNT;
+    pcs->ref_list0_count_try = (uint8_t)n_l0;
+    pcs->ref_list1_count_try = (uint8_t)n_l1;
+    pcs->picture_number = 100;
+
+    const int sbs_x = (width + 63) / 64, sbs_y = (height + 63) / 64, n_sb = sbs_x * sbs_y;
+    pcs->sb_total_count = (uint16_t)n_sb;
+    pcs->rc_me_distortion = calloc(n_sb, sizeof(uint32_t));
+    MotionEstimationData med;
+    memset(&med, 0, sizeof(med));
+    med.me_results = calloc(n_sb, sizeof(MeSbResults *));
+    pcs->pa_me_data = &med;
+    for (int i = 0; i < n_sb; i++) {
+        med.me_results[i] = calloc(1, sizeof(MeSbResults));
+        me_sb_results_ctor(med.me_results[i]);
+        /* the ctor mallocs; slots of references that are not searched are never written -> define them */
+        memset(med.me_results[i]->me_mv_array, 0, sizeof(MvCandidate) * SQUARE_PU_COUNT * MAX_PA_ME_MV);
+        memset(med.me_results[i]->total_me_candidate_index, 0, SQUARE_PU_COUNT);
+    }
+
+    MotionEstimationContext_t mectx;
+    memset(&mectx, 0, sizeof(mectx));
+    MeContext *me = calloc(1, sizeof(*me));
+    me_context_ctor(me);
+    mectx.me_context_ptr = me;
+    signal_derivation_me_kernel_oq(scs, pcs, &mectx);
+
+    EbPictureBufferDesc in_full, in_q, in_s, rf[8], rq[8], rs[8];
+    plane_desc(&in_full, gfull, src->full);
+    plane_desc(&in_q, gquarter, src->quarter);
+    plane_desc(&in_s, gsixteenth, src->sixteenth);
+    for (int i = 0; i < 8; i++) {
+        plane_desc(&rf[i], gfull, refs[i].full);
+        plane_desc(&rq[i], gquarter, refs[i].quarter);
+        plane_desc(&rs[i], gsixteenth, refs[i].sixteenth);
+    }
+
+    /* export the derived parameters in the C-ABI's plain struct */
+    if (params_out) {
+        SvtB200MeParams *p = params_out;
+        memset(p, 0, sizeof(*p));
+        p->full = *gfull;
+        p->quarter = *gquarter;
+        p->sixteenth = *gsixteenth;
+        p->num_lists = n_l1 > 0 ? 2 : 1;
+        p->num_refs[0] = n_l0;
+        p->num_refs[1] = n_l1;
+        for (int i = 0; i < 8; i++) p->ref_dist[i / 4][i % 4] = ref_dist[i];
+        p->temporal_layer_index = temporal_layer;
+        p->is_used_as_reference_flag = is_ref;
+        p->enable_hme_flag = me->enable_hme_flag;
+        p->enable_hme_level0_flag = me->enable_hme_level0_flag;
+        p->enable_hme_level1_flag = me->enable_hme_level1_flag;
+        p->enable_hme_level2_flag = me->enable_hme_level2_flag;
+        p->hme_search_method = me->hme_search_method == SUB_SAD_SEARCH;
+        p->me_search_method = me->me_search_method == SUB_SAD_SEARCH;
+        p->number_hme_search_region_in_width = me->number_hme_search_region_in_width;
+        p->number_hme_search_region_in_height = me->number_hme_search_region_in_height;
+        p->hme_level0_total_search_area_width = me->hme_level0_total_search_area_width;
+        p->hme_level0_total_search_area_height = me->hme_level0_total_search_area_height;
+        p->hme_level0_max_total_search_area_width = me->hme_level0_max_total_search_area_width;
+        p->hme_level0_max_total_search_area_height = me->hme_level0_max_total_search_area_height;
+        for (int i = 0; i < 2; i++) {
+            p->hme_level0_search_area_in_width_array[i] = me->hme_level0_search_area_in_width_array[i];
+            p->hme_level0_search_area_in_height_array[i] = me->hme_level0_search_area_in_height_array[i];
+            p->hme_level0_max_search_area_in_width_array[i] = me->hme_level0_max_search_area_in_width_array[i];
+            p->hme_level0_max_search_area_in_height_array[i] = me->hme_level0_max_search_area_in_height_array[i];
+            p->hme_level1_search_area_in_width_array[i] = me->hme_level1_search_area_in_width_array[i];
+            p->hme_level1_search_area_in_height_array[i] = me->hme_level1_search_area_in_height_array[i];
+            p->hme_level2_search_area_in_width_array[i] = me->hme_level2_search_area_in_width_array[i];
+            p->hme_level2_search_area_in_height_array[i] = me->hme_level2_search_area_in_height_array[i];
+        }
+        p->search_area_width = me->search_area_width;
+        p->search_area_height = me->search_area_height;
+        p->max_me_search_width = me->max_me_search_width;
+        p->max_me_search_height = me->max_me_search_height;
+        p->enable_me_hme_ref_pruning = me->me_hme_prune_ctrls.enable_me_hme_ref_pruning;
+        p->prune_ref_if_hme_sad_dev_bigger_than_th = me->me_hme_prune_ctrls.prune_ref_if_hme_sad_dev_bigger_than_th;
+        p->prune_ref_if_me_sad_dev_bigger_than_th = me->me_hme_prune_ctrls.prune_ref_if_me_sad_dev_bigger_than_th;
+        p->enable_me_sr_adjustment = me->me_sr_adjustment_ctrls.enable_me_sr_adjustment;
+        p->reduce_me_sr_based_on_mv_length_th = me->me_sr_adjustment_ctrls.reduce_me_sr_based_on_mv_length_th;
+        p->stationary_hme_sad_abs_th = me->me_sr_adjustment_ctrls.stationary_hme_sad_abs_th;
+        p->stationary_me_sr_divisor = me->me_sr_adjustment_ctrls.stationary_me_sr_divisor;
+        p->reduce_me_sr_based_on_hme_sad_abs_th = me->me_sr_adjustment_ctrls.reduce_me_sr_based_on_hme_sad_abs_th;
+        p->me_sr_divisor_for_low_hme_sad = me->me_sr_adjustment_ctrls.me_sr_divisor_for_low_hme_sad;
+        p->max_number_of_pus_per_sb = pcs->max_number_of_pus_per_sb;
+        p->rc_dist_from_8x8 = scs->input_resolution <= INPUT_SIZE_480p_RANGE;
+        if (me->hme_decimation != TWO_DECIMATION_HME) return -3;
+    }
+
+    for (int sy = 0; sy < sbs_y; sy++)
+        for (int sx = 0; sx < sbs_x; sx++) {
+            const int sb = sy * sbs_x + sx;
+            const uint32_t ox = sx * 64, oy = sy * 64;
+            const uint32_t sb_width = (uint32_t)(width - ox) < 64 ? (uint32_t)(width - ox) : 64;
+            /* EbMotionEstimationProcess.c:847-908: load SB + decimated SBs into the context */
+            uint32_t bi = (in_full.origin_y + oy) * in_full.stride_y + in_full.origin_x + ox;
+            for (unsigned r = 0; r < 64; r++)
+                memcpy(&me->sb_buffer[r * 64], &in_full.buffer_y[bi + r * in_full.stride_y], 64);
+            me->sb_src_ptr = &in_full.buffer_y[bi];
+            me->sb_src_stride = in_full.stride_y;
+            bi = (in_q.origin_y + (oy >> 1)) * in_q.stride_y + in_q.origin_x + (ox >> 1);
+            for (unsigned r = 0; r < 32; r++)
+                memcpy(&me->quarter_sb_buffer[r * me->quarter_sb_buffer_stride],
+                       &in_q.buffer_y[bi + r * in_q.stride_y], sb_width >> 1);
+            bi = (in_s.origin_y + (oy >> 2)) * in_s.stride_y + in_s.origin_x + (ox >> 2);
+            {
+                uint8_t *fp = &in_s.buffer_y[bi], *lp = me->sixteenth_sb_buffer;
+                const int full = me->hme_search_method == FULL_SAD_SEARCH;
+                for (unsigned r = 0; r < 16; r += full ? 1 : 2) {
+                    memcpy(lp, fp, sb_width >> 2);
+                    lp += 16;
+                    fp += in_s.stride_y << (full ? 0 : 1);
+                }
+            }
+            /* :910-940 */
+            me->me_type = ME_OPEN_LOOP;
+            me->num_of_list_to_search = (pcs->slice_type == P_SLICE) ? REF_LIST_0 : REF_LIST_1;
+            me->num_of_ref_pic_to_search[0] = pcs->ref_list0_count_try;
+            me->num_of_ref_pic_to_search[1] = pcs->slice_type == B_SLICE ? pcs->ref_list1_count_try : 0;
+            me->temporal_layer_index = pcs->temporal_layer_index;
+            me->is_used_as_reference_flag = pcs->is_used_as_reference_flag;
+            for (int l = 0; l < 2; l++)
+                for (int r = 0; r < 4; r++) {
+                    me->me_ds_ref_array[l][r].picture_ptr = &rf[l * 4 + r];
+                    me->me_ds_ref_array[l][r].quarter_picture_ptr = &rq[l * 4 + r];
+                    me->me_ds_ref_array[l][r].sixteenth_picture_ptr = &rs[l * 4 + r];
+                    me->me_ds_ref_array[l][r].picture_number = pcs->picture_number - (uint64_t)ref_dist[l * 4 + r];
+                }
+            memset(me->p_sb_best_sad, 0, sizeof(me->p_sb_best_sad)); /* defined value for unsearched slots */
+            motion_estimate_sb(pcs, sb, ox, oy, me, &in_full);
+
+            for (int l = 0; l < 2; l++)
+                for (int r = 0; r < 4; r++) {
+                    memcpy(best_sad + ((size_t)(sb * 2 + l) * 4 + r) * 85, me->p_sb_best_sad[l][r], 85 * 4);
+                    memcpy(best_mv + ((size_t)(sb * 2 + l) * 4 + r) * 85, me->p_sb_best_mv[l][r], 85 * 4);
+                    SvtB200HmeResult *h = &hme[(size_t)(sb * 2 + l) * 4 + r];
+                    memset(h, 0, sizeof(*h));
+                    h->sc_x = me->hme_results[l][r].hme_sc_x;
+                    h->sc_y = me->hme_results[l][r].hme_sc_y;
+                    h->do_ref = me->hme_results[l][r].do_ref;
+                    h->hme_sad = me->hme_results[l][r].hme_sad;
+                }
+            MeSbResults *res = med.me_results[sb];
+            for (int pu = 0; pu < 85; pu++) {
+                total_cand[(size_t)sb * 85 + pu] = res->total_me_candidate_index[pu];
+                for (int c = 0; c < 23; c++) {
+                    uint8_t v = 0;
+                    if (c < res->total_me_candidate_index[pu]) {
+                        MeCandidate mc = res->me_candidate_array[pu * MAX_PA_ME_CAND + c];
+                        /* the index of the list a uni-pred candidate does not use is stale in the reference
+                         * (construct_me_candidate_array writes only ref_index[list]); nothing reads it */
+                        uint8_t i0 = mc.direction == 1 ? 0 : mc.ref_idx_l0;
+                        uint8_t i1 = mc.direction == 0 ? 0 : mc.ref_idx_l1;
+                        v = (uint8_t)(mc.direction | (i0 << 2) | (i1 << 4) | (mc.ref0_list << 6) | (mc.ref1_list << 7));
+                    }
+                    me_cand[((size_t)sb * 85 + pu) * 23 + c] = v;
+                }
+                for (int m = 0; m < 7; m++) {
+                    me_mv[(((size_t)sb * 85 + pu) * 7 + m) * 2] = res->me_mv_array[pu * MAX_PA_ME_MV + m].x_mv;
+                    me_mv[(((size_t)sb * 85 + pu) * 7 + m) * 2 + 1] = res->me_mv_array[pu * MAX_PA_ME_MV + m].y_mv;
+                }
+            }
+            rc_me_distortion[sb] = pcs->rc_me_distortion[sb];
+        }
+    return 0;
+}

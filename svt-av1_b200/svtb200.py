@@ -1,0 +1,149 @@
+"""ctypes binding of libsvtav1_b200.so (include/svt_av1_b200.h) — host-side convenience for tests and bench.py.
+
+The product is the C-ABI library; this module only mirrors its structs and loads it.  There is no CPU
+fallback: if the shared library is missing, `load()` raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvtav1_b200.so")
+
+ME_MAX_REFS, ME_LISTS, ME_PU, ME_MAX_MV, ME_MAX_CAND = 4, 2, 85, 7, 23
+
+
+class Plane(C.Structure):
+    _fields_ = [("stride", C.c_int32), ("origin_x", C.c_int32), ("origin_y", C.c_int32),
+                ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class MeParams(C.Structure):
+    _fields_ = [
+        ("full", Plane), ("quarter", Plane), ("sixteenth", Plane),
+        ("num_lists", C.c_int32), ("num_refs", C.c_int32 * 2), ("ref_dist", (C.c_int32 * 4) * 2),
+        ("temporal_layer_index", C.c_int32), ("is_used_as_reference_flag", C.c_int32),
+        ("enable_hme_flag", C.c_int32), ("enable_hme_level0_flag", C.c_int32),
+        ("enable_hme_level1_flag", C.c_int32), ("enable_hme_level2_flag", C.c_int32),
+        ("hme_search_method", C.c_int32), ("me_search_method", C.c_int32),
+        ("number_hme_search_region_in_width", C.c_int32), ("number_hme_search_region_in_height", C.c_int32),
+        ("hme_level0_total_search_area_width", C.c_int32), ("hme_level0_total_search_area_height", C.c_int32),
+        ("hme_level0_max_total_search_area_width", C.c_int32),
+        ("hme_level0_max_total_search_area_height", C.c_int32),
+        ("hme_level0_search_area_in_width_array", C.c_int32 * 2),
+        ("hme_level0_search_area_in_height_array", C.c_int32 * 2),
+        ("hme_level0_max_search_area_in_width_array", C.c_int32 * 2),
+        ("hme_level0_max_search_area_in_height_array", C.c_int32 * 2),
+        ("hme_level1_search_area_in_width_array", C.c_int32 * 2),
+        ("hme_level1_search_area_in_height_array", C.c_int32 * 2),
+        ("hme_level2_search_area_in_width_array", C.c_int32 * 2),
+        ("hme_level2_search_area_in_height_array", C.c_int32 * 2),
+        ("search_area_width", C.c_int32), ("search_area_height", C.c_int32),
+        ("max_me_search_width", C.c_int32), ("max_me_search_height", C.c_int32),
+        ("enable_me_hme_ref_pruning", C.c_int32),
+        ("prune_ref_if_hme_sad_dev_bigger_than_th", C.c_int32),
+        ("prune_ref_if_me_sad_dev_bigger_than_th", C.c_int32),
+        ("enable_me_sr_adjustment", C.c_int32),
+        ("reduce_me_sr_based_on_mv_length_th", C.c_int32), ("stationary_hme_sad_abs_th", C.c_int32),
+        ("stationary_me_sr_divisor", C.c_int32), ("reduce_me_sr_based_on_hme_sad_abs_th", C.c_int32),
+        ("me_sr_divisor_for_low_hme_sad", C.c_int32),
+        ("max_number_of_pus_per_sb", C.c_int32), ("rc_dist_from_8x8", C.c_int32),
+    ]
+
+
+class MePlanes(C.Structure):
+    _fields_ = [("full", C.c_void_p), ("quarter", C.c_void_p), ("sixteenth", C.c_void_p)]
+
+
+class HmeResult(C.Structure):
+    _fields_ = [("sc_x", C.c_int16), ("sc_y", C.c_int16), ("do_ref", C.c_uint32), ("hme_sad", C.c_uint64)]
+
+
+class MeOutputs(C.Structure):
+    _fields_ = [("best_sad", C.c_void_p), ("best_mv", C.c_void_p), ("hme", C.c_void_p),
+                ("me_mv", C.c_void_p), ("me_cand", C.c_void_p), ("total_cand", C.c_void_p),
+                ("rc_me_distortion", C.c_void_p)]
+
+
+def preset8_me_params(width, height, n_l0=1, n_l1=1, dist=((1, 2, 3, 4), (1, 2, 3, 4)), temporal_layer=1,
+                      is_ref=1):
+    """ME parameters of preset 8 (ENC_M8) at >=720p, 30 fps, as set_me_hme_params_oq /
+    signal_derivation_me_kernel_oq (EbMotionEstimationProcess.c:113-420) derive them.  tests check this table
+    against the reference's own derivation (oracle/_ref) when it is available."""
+    p = MeParams()
+    geo = me_geometry(width, height)
+    p.full, p.quarter, p.sixteenth = geo
+    p.num_lists = 2 if n_l1 > 0 else 1
+    p.num_refs[0], p.num_refs[1] = n_l0, n_l1
+    for l in range(2):
+        for r in range(4):
+            p.ref_dist[l][r] = dist[l][r]
+    p.temporal_layer_index, p.is_used_as_reference_flag = temporal_layer, is_ref
+    p.enable_hme_flag = p.enable_hme_level0_flag = p.enable_hme_level1_flag = p.enable_hme_level2_flag = 1
+    p.hme_search_method = p.me_search_method = 1
+    p.number_hme_search_region_in_width = p.number_hme_search_region_in_height = 2
+    p.hme_level0_total_search_area_width = p.hme_level0_total_search_area_height = 32
+    p.hme_level0_max_total_search_area_width = p.hme_level0_max_total_search_area_height = 164
+    for i in range(2):
+        p.hme_level0_search_area_in_width_array[i] = p.hme_level0_search_area_in_height_array[i] = 16
+        p.hme_level0_max_search_area_in_width_array[i] = p.hme_level0_max_search_area_in_height_array[i] = 82
+        p.hme_level1_search_area_in_width_array[i] = p.hme_level2_search_area_in_width_array[i] = 8
+        p.hme_level1_search_area_in_height_array[i] = p.hme_level2_search_area_in_height_array[i] = 3
+    p.search_area_width = p.search_area_height = 24  # 16 * 3/2 (low frame rate)
+    p.max_me_search_width, p.max_me_search_height = 64, 32
+    p.enable_me_hme_ref_pruning = 1
+    p.prune_ref_if_hme_sad_dev_bigger_than_th = 30
+    p.prune_ref_if_me_sad_dev_bigger_than_th = 60
+    p.enable_me_sr_adjustment = 1
+    p.reduce_me_sr_based_on_mv_length_th = 4
+    p.stationary_hme_sad_abs_th = 12000
+    p.stationary_me_sr_divisor = 8
+    p.reduce_me_sr_based_on_hme_sad_abs_th = 6000
+    p.me_sr_divisor_for_low_hme_sad = 8
+    p.max_number_of_pus_per_sb = 85
+    p.rc_dist_from_8x8 = 1 if width * height < 0xA1400 else 0
+    return p
+
+
+def me_geometry(width, height):
+    """Plane geometry the reference allocates for ME: full-res padded by sb_sz+ME_FILTER_TAP = 68, the 1/4 and
+    1/16 planes by sb_sz>>1 and sb_sz>>2 (EbEncHandle.c:971-988, 1030-1053)."""
+    def mk(w, h, pad):
+        return Plane(w + 2 * pad, pad, pad, w, h)
+    return mk(width, height, 68), mk(width >> 1, height >> 1, 32), mk(width >> 2, height >> 2, 16)
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA C-ABI library. Raises (never falls back) if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} missing: run __graft_entry__.build() (nvcc sm_100a); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    lib.svt_b200_last_error.restype = C.c_char_p
+    lib.svt_b200_launch_count.restype = C.c_uint64
+    lib.svt_b200_malloc.restype = C.c_void_p
+    lib.svt_b200_malloc.argtypes = [C.c_size_t]
+    lib.svt_b200_free.argtypes = [C.c_void_p]
+    lib.svt_b200_malloc_host.restype = C.c_void_p
+    lib.svt_b200_malloc_host.argtypes = [C.c_size_t]
+    lib.svt_b200_free_host.argtypes = [C.c_void_p]
+    lib.svt_b200_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.svt_b200_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.svt_b200_stream_sync.argtypes = [C.c_void_p]
+    lib.svt_b200_me_scratch_bytes.restype = C.c_size_t
+    lib.svt_b200_me_scratch_bytes.argtypes = [C.POINTER(MeParams)]
+    lib.svt_b200_me_picture.argtypes = [C.POINTER(MeParams), C.POINTER(MePlanes), C.POINTER(MePlanes),
+                                        C.POINTER(MeOutputs), C.c_void_p, C.c_void_p]
+    lib.svt_nxm_sad_kernel_cuda.restype = C.c_uint32
+    _lib = lib
+    return lib
+
+
+def check(rc, lib=None):
+    if rc != 0:
+        lib = lib or load()
+        raise RuntimeError(f"svt_b200 call failed rc={rc}: {lib.svt_b200_last_error().decode()}")
