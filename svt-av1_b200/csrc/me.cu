@@ -1,0 +1,1072 @@
+// me.cu — open-loop motion estimation on sm_100a.
+//
+// Replaces (reference files under Source/Lib/Encoder):
+//   svt_sad_loop_kernel_c                      C_DEFAULT/EbComputeSAD_C.c:57-96
+//   svt_ext_all_sad_calculation_8x8_16x16_c    Codec/EbMotionEstimation.c:230-390
+//   svt_ext_eight_sad_calculation_32x32_64x64_c Codec/EbMotionEstimation.c:396-455
+//   svt_ext_sad_calculation_8x8_16x16_c / _32x32_64x64_c  :122-225
+//   motion_estimate_sb and everything below it (:852-3041) for a whole picture.
+//
+// Design (B200-first, not a port of the AVX2 mpsadbw code):
+//   * one CTA per (super-block, reference picture); the 64x64 source block and the reference search
+//     window are staged once into shared memory and every candidate position is evaluated from there,
+//     so HBM traffic is the algorithmic minimum (source + window once per SB-ref);
+//   * SAD arithmetic uses the native VABSDIFF4.U8.ACC (4 abs-diffs + accumulate per lane-op); a thread
+//     owns FOUR horizontally adjacent search positions so three aligned LDS words serve all four through
+//     funnel shifts (SHF) — 4.5 issue slots per 8-pixel row-position instead of 9;
+//   * "first minimum in raster order" (the reference's strict `<` running best) is an argmin over the key
+//     (sad << 32 | raster_index): REDUX.MIN warp reductions + one shared-memory atomicMin per warp;
+//   * the data-dependent glue between the stages (search-centre choice, reference pruning, search-region
+//     shrinking, candidate list) runs on-device too, so one picture is three launches and no host sync.
+#include "common.cuh"
+
+using namespace svtb200;
+
+namespace {
+
+constexpr int kMaxSadValue = 128 * 128 * 255; // MAX_SAD_VALUE, Codec/EbMotionEstimation.h:93
+constexpr int NT_SEARCH = 256;
+
+__constant__ uint8_t c_tab16[16] = {0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15};
+__constant__ uint8_t c_inv16[16] = {0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15}; // self-inverse
+__constant__ uint8_t c_tab8[64] = {0,  1,  4,  5,  16, 17, 20, 21, 2,  3,  6,  7,  18, 19, 22, 23,
+                                   8,  9,  12, 13, 24, 25, 28, 29, 10, 11, 14, 15, 26, 27, 30, 31,
+                                   32, 33, 36, 37, 48, 49, 52, 53, 34, 35, 38, 39, 50, 51, 54, 55,
+                                   40, 41, 44, 45, 56, 57, 60, 61, 42, 43, 46, 47, 58, 59, 62, 63};
+
+// The reference's search-window clamp, statement for statement (e.g. EbMotionEstimation.c:927-975): the
+// left/top clamp moves the origin and then re-tests the corrected origin (never true), so only the
+// right/bottom clamp shrinks the size.
+__device__ __forceinline__ void clamp_window(int origin, int pad, int pic_size, int &ao, int &size) {
+    if (origin + ao < -pad) ao = -pad - origin;
+    if (origin + ao > pic_size - 1) ao = ao - ((origin + ao) - (pic_size - 1));
+    if (origin + ao + size > pic_size) size = max(1, size - ((origin + ao + size) - pic_size));
+}
+__device__ __forceinline__ int scaled_dist(int dist) { return ((dist * 5) / 8) + ((dist % 8) == 0 ? 0 : 1); }
+
+// -----------------------------------------------------------------------------------------------------
+// Block-cooperative exhaustive search of one bw x bh block over a saw x sah window (svt_sad_loop_kernel).
+// `ref` points at search position (0,0); reference row of block row r at search row ys is
+// ys*raw_stride + r*k*raw_stride.  Returns (sad << 32 | ys*saw + xs) of the first minimum, or ~0 if no
+// position exists.  smem: `smem_bytes` of scratch (uint32 aligned); s_red: NT/32 uint64.
+// -----------------------------------------------------------------------------------------------------
+template <int NT>
+__device__ uint64_t block_search(const uint8_t *__restrict__ src, int src_stride, const uint8_t *__restrict__ ref,
+                                 int raw_stride, int k, int bw, int bh, int saw, int sah, uint32_t *smem,
+                                 int smem_bytes, uint64_t *s_red) {
+    const int tid = threadIdx.x;
+    const int spw = (bw + 3) >> 2; // source words per row
+    const int wpw = ((saw - 1 + bw + 3) >> 2) + 1; // window words per row (+1: funnel reads one past)
+    const int wbytes = saw - 1 + bw;
+    uint32_t *s_src = smem;
+    uint32_t *s_win = smem + spw * bh;
+    const int budget_rows = (smem_bytes - spw * bh * 4) / (wpw * 4);
+    const int span = (bh - 1) * k + 1;
+    int chunk = budget_rows - span + 1; // search rows per pass
+    if (chunk > sah) chunk = sah;
+    if (chunk < 1) chunk = 1; // caller guarantees enough smem for one row
+    const uint32_t tail_mask = (bw & 3) ? ((1u << (8 * (bw & 3))) - 1u) : 0xffffffffu;
+
+    __syncthreads(); // previous users of smem are done
+    { // stage the source block (bytewise: arbitrary alignment)
+        uint8_t *sb = reinterpret_cast<uint8_t *>(s_src);
+        for (int i = tid; i < bh * spw * 4; i += NT) {
+            int r = i / (spw * 4), c = i - r * (spw * 4);
+            sb[i] = c < bw ? src[(size_t)r * src_stride + c] : 0;
+        }
+    }
+    uint64_t best = ~0ull;
+    for (int y0 = 0; y0 < sah; y0 += chunk) {
+        const int cr = min(chunk, sah - y0);
+        const int rows = cr - 1 + span;
+        __syncthreads();
+        {
+            uint8_t *wb = reinterpret_cast<uint8_t *>(s_win);
+            const int rb = wpw * 4;
+            for (int i = tid; i < rows * rb; i += NT) {
+                int r = i / rb, c = i - r * rb;
+                wb[i] = c < wbytes ? ref[(size_t)(y0 + r) * raw_stride + c] : 0;
+            }
+        }
+        __syncthreads();
+        for (int p = tid; p < cr * saw; p += NT) {
+            const int ysl = p / saw, xs = p - ysl * saw;
+            const int a = xs >> 2, sh = (xs & 3) * 8;
+            uint32_t sad = 0;
+            for (int r = 0; r < bh; r++) {
+                const uint32_t *wr = s_win + (ysl + r * k) * wpw + a;
+                const uint32_t *sr = s_src + r * spw;
+                uint32_t lo = wr[0];
+                for (int w = 0; w < spw; w++) {
+                    uint32_t hi = wr[w + 1];
+                    uint32_t v = __funnelshift_r(lo, hi, sh);
+                    uint32_t s = sr[w];
+                    if (w == spw - 1) {
+                        v &= tail_mask;
+                        s &= tail_mask;
+                    }
+                    sad = sad4(s, v, sad);
+                    lo = hi;
+                }
+            }
+            uint64_t key = ((uint64_t)sad << 32) | (uint32_t)((y0 + ysl) * saw + xs);
+            best = key < best ? key : best;
+        }
+    }
+    best = warp_min_u64(best);
+    __syncthreads();
+    if ((tid & 31) == 0) s_red[tid >> 5] = best;
+    __syncthreads();
+    uint64_t r = s_red[0];
+#pragma unroll
+    for (int i = 1; i < NT / 32; i++) r = s_red[i] < r ? s_red[i] : r;
+    return r;
+}
+
+// -----------------------------------------------------------------------------------------------------
+// Picture-level state passed by value to the kernels
+// -----------------------------------------------------------------------------------------------------
+struct RawHme { // one (sb, list, ref): result of the last enabled HME level, before cross-ref logic
+    int16_t x, y;
+    uint32_t valid;
+    uint64_t sad;
+};
+
+struct MeDev {
+    SvtB200MeParams p;
+    SvtB200MePlanes src;
+    SvtB200MePlanes refs[2][4];
+    SvtB200MeOutputs out;
+    RawHme *raw; // [n_sb][2][4]
+    int sbs_x, sbs_y;
+    int slot_l[8], slot_r[8], n_slots;
+};
+
+struct HmeState {
+    int16_t sc_x[2][4], sc_y[2][4];
+    uint64_t sad[2][4];
+    uint32_t do_ref[2][4];
+    uint32_t divisor[2][4];
+};
+
+// set_final_seach_centre_sb's cross-reference carry (EbMotionEstimation.c:2575-2740) +
+// hme_prune_ref_and_adjust_sr (:2779-2823). Serial, tiny; run by one thread.
+__device__ void derive_hme_state(const SvtB200MeParams &p, const RawHme *raw /*[2][4]*/, HmeState &h) {
+    for (int l = 0; l < 2; l++)
+        for (int r = 0; r < 4; r++) {
+            h.sc_x[l][r] = h.sc_y[l][r] = 0;
+            h.sad[l][r] = 0xFFFFFFFFull;
+            h.do_ref[l][r] = 1;
+            h.divisor[l][r] = 1;
+        }
+    uint64_t carry_sad = 0;
+    for (int l = 0; l < p.num_lists; l++)
+        for (int r = 0; r < p.num_refs[l]; r++) {
+            const RawHme &w = raw[l * 4 + r];
+            int16_t scx = 0, scy = 0;
+            if (w.valid) {
+                scx = w.x;
+                scy = w.y;
+                carry_sad = w.sad;
+            }
+            h.sc_x[l][r] = scx;
+            h.sc_y[l][r] = scy;
+            h.sad[l][r] = carry_sad;
+        }
+    const bool prune_ref = p.enable_hme_flag && p.enable_hme_level2_flag;
+    if (prune_ref && (p.enable_me_sr_adjustment || p.enable_me_hme_ref_pruning)) {
+        uint64_t best = h.sad[0][0];
+        for (int l = 0; l < 2; l++)
+            for (int r = 0; r < 4; r++) best = h.sad[l][r] < best ? h.sad[l][r] : best;
+        const uint32_t th = (uint32_t)p.prune_ref_if_hme_sad_dev_bigger_than_th & 0xFFFFu;
+        for (int l = 0; l < 2; l++)
+            for (int r = 0; r < 4; r++) {
+                if (p.enable_me_hme_ref_pruning && th != 0xFFFFu && (h.sad[l][r] - best) * 100 > (uint64_t)th * best)
+                    h.do_ref[l][r] = 0;
+                if (p.enable_me_sr_adjustment) {
+                    if (abs((int)h.sc_x[l][r]) <= p.reduce_me_sr_based_on_mv_length_th &&
+                        abs((int)h.sc_y[l][r]) <= p.reduce_me_sr_based_on_mv_length_th &&
+                        h.sad[l][r] < (uint64_t)p.stationary_hme_sad_abs_th)
+                        h.divisor[l][r] = p.stationary_me_sr_divisor;
+                    else if (h.sad[l][r] < (uint64_t)p.reduce_me_sr_based_on_hme_sad_abs_th)
+                        h.divisor[l][r] = p.me_sr_divisor_for_low_hme_sad;
+                }
+            }
+    }
+}
+
+constexpr int HME_SMEM_BYTES = 40 * 1024;
+
+// Kernel A: hierarchical ME, one CTA per (SB, reference). hme_level_0/1/2 (:852-1318) for the 2x2 search
+// regions, then the region choice of set_final_seach_centre_sb.
+__global__ void __launch_bounds__(NT_SEARCH) hme_kernel(const __grid_constant__ MeDev d) {
+    extern __shared__ uint32_t smem[];
+    __shared__ uint64_t s_red[NT_SEARCH / 32];
+    const SvtB200MeParams &p = d.p;
+    const int sb = blockIdx.x, slot = blockIdx.y;
+    const int l = d.slot_l[slot], r = d.slot_r[slot];
+    RawHme *out = d.raw + (size_t)sb * 8 + l * 4 + r;
+    const bool active = (p.temporal_layer_index > 0 || l == 0) && p.enable_hme_flag &&
+                        (p.enable_hme_level0_flag || p.enable_hme_level1_flag || p.enable_hme_level2_flag);
+    if (!active) {
+        if (threadIdx.x == 0) {
+            RawHme z = {0, 0, 0, 0};
+            *out = z;
+        }
+        return;
+    }
+    const int sx = sb % d.sbs_x, sy = sb / d.sbs_x;
+    const int ox = sx * 64, oy = sy * 64;
+    const int sbw = min(p.full.width - ox, 64), sbh = min(p.full.height - oy, 64);
+    const int sub = p.hme_search_method != 0;
+    const int mult = scaled_dist(p.ref_dist[l][r]) * 100;
+    const int nrw = p.number_hme_search_region_in_width, nrh = p.number_hme_search_region_in_height;
+    const SvtB200MePlanes &rp = d.refs[l][r];
+
+    uint64_t best_sad = 0;
+    int best_x = 0, best_y = 0;
+    bool first = true;
+    for (int ry = 0; ry < nrh; ry++)
+        for (int rx = 0; rx < nrw; rx++) {
+            int cx = 0, cy = 0;
+            uint64_t csad = 0;
+            if (p.enable_hme_level0_flag) { // hme_level_0, 1/16 resolution
+                const SvtB200Plane &pl = p.sixteenth;
+                const int o_x = ox >> 2, o_y = oy >> 2, bw = sbw >> 2, bh = sbh >> 2;
+                int saw = min((int)(int16_t)((((p.hme_level0_search_area_in_width_array[rx] * mult) / 100) + 15) & ~0x0F),
+                              (int)(int16_t)((p.hme_level0_max_search_area_in_width_array[rx] + 15) & ~0x0F));
+                int sah = min((int)(int16_t)((p.hme_level0_search_area_in_height_array[ry] * mult) / 100),
+                              (int)(int16_t)p.hme_level0_max_search_area_in_height_array[ry]);
+                int xdist = 0, ydist = 0;
+                for (int i = 0; i < rx; i++)
+                    xdist += min((int)(int16_t)((p.hme_level0_search_area_in_width_array[i] * mult) / 100),
+                                 (int)(int16_t)p.hme_level0_max_search_area_in_width_array[i]);
+                for (int i = 0; i < ry; i++)
+                    ydist += min((int)(int16_t)((p.hme_level0_search_area_in_height_array[i] * mult) / 100),
+                                 (int)(int16_t)p.hme_level0_max_search_area_in_height_array[i]);
+                int xo = -(int)(int16_t)(min((p.hme_level0_total_search_area_width * mult) / 100,
+                                             p.hme_level0_max_total_search_area_width) >> 1) + xdist;
+                int yo = -(int)(int16_t)(min((p.hme_level0_total_search_area_height * mult) / 100,
+                                             p.hme_level0_max_total_search_area_height) >> 1) + ydist;
+                clamp_window(o_x, pl.origin_x - 1, pl.width, xo, saw);
+                saw = saw < 16 ? saw : saw & ~0x0F;
+                clamp_window(o_y, pl.origin_y - 1, pl.height, yo, sah);
+                const uint8_t *s = d.src.sixteenth + (size_t)(pl.origin_y + o_y) * pl.stride + pl.origin_x + o_x;
+                const uint8_t *f = rp.sixteenth + (size_t)(pl.origin_y + o_y + yo) * pl.stride + pl.origin_x + o_x + xo;
+                uint64_t key = block_search<NT_SEARCH>(s, sub ? pl.stride * 2 : pl.stride, f, pl.stride, sub ? 2 : 1, bw,
+                                                       sub ? bh >> 1 : bh, saw, sah, smem, HME_SMEM_BYTES, s_red);
+                uint32_t sad = (uint32_t)(key >> 32), idx = (uint32_t)key;
+                int kx = 0, ky = 0;
+                uint64_t lsad = 0xffffff; // svt_sad_loop_kernel_c start value; centre untouched if never beaten
+                if (sad < 0xffffffu) {
+                    lsad = sad;
+                    kx = idx % saw;
+                    ky = idx / saw;
+                }
+                csad = sub ? lsad * 2 : lsad;
+                cx = (int16_t)((kx + xo) * 4);
+                cy = (int16_t)((ky + yo) * 4);
+            }
+            if (p.enable_hme_level1_flag) { // hme_level_1, 1/4 resolution
+                const SvtB200Plane &pl = p.quarter;
+                const int o_x = ox >> 1, o_y = oy >> 1, bw = sbw >> 1, bh = sbh >> 1;
+                int saw = (int16_t)((p.hme_level1_search_area_in_width_array[rx] + 7) & ~0x07);
+                int sah = p.hme_level1_search_area_in_height_array[ry];
+                int xo = -(saw >> 1) + (cx >> 1), yo = -(sah >> 1) + (cy >> 1);
+                clamp_window(o_x, pl.origin_x - 1, pl.width, xo, saw);
+                saw = saw < 8 ? saw : saw & ~0x07;
+                clamp_window(o_y, pl.origin_y - 1, pl.height, yo, sah);
+                const uint8_t *s = d.src.quarter + (size_t)(pl.origin_y + o_y) * pl.stride + pl.origin_x + o_x;
+                const uint8_t *f = rp.quarter + (size_t)(pl.origin_y + o_y + yo) * pl.stride + pl.origin_x + o_x + xo;
+                uint64_t key = block_search<NT_SEARCH>(s, sub ? pl.stride * 2 : pl.stride, f, pl.stride, sub ? 2 : 1, bw,
+                                                       sub ? bh >> 1 : bh, saw, sah, smem, HME_SMEM_BYTES, s_red);
+                uint32_t sad = (uint32_t)(key >> 32), idx = (uint32_t)key;
+                int kx = 0, ky = 0;
+                uint64_t lsad = 0xffffff;
+                if (sad < 0xffffffu) {
+                    lsad = sad;
+                    kx = idx % saw;
+                    ky = idx / saw;
+                }
+                csad = sub ? lsad * 2 : lsad;
+                cx = (int16_t)((kx + xo) * 2);
+                cy = (int16_t)((ky + yo) * 2);
+            }
+            if (p.enable_hme_level2_flag) { // hme_level_2, full resolution
+                const SvtB200Plane &pl = p.full;
+                int saw = (int16_t)((p.hme_level2_search_area_in_width_array[rx] + 7) & ~0x07);
+                int sah = p.hme_level2_search_area_in_height_array[ry];
+                int xo = -(saw >> 1) + cx, yo = -(sah >> 1) + cy;
+                clamp_window(ox, 63, pl.width, xo, saw);
+                saw = saw < 8 ? saw : saw & ~0x07;
+                clamp_window(oy, 63, pl.height, yo, sah);
+                const uint8_t *s = d.src.full + (size_t)(pl.origin_y + oy) * pl.stride + pl.origin_x + ox;
+                const uint8_t *f = rp.full + (size_t)(pl.origin_y + oy + yo) * pl.stride + pl.origin_x + ox + xo;
+                uint64_t key = block_search<NT_SEARCH>(s, sub ? pl.stride * 2 : pl.stride, f, pl.stride, sub ? 2 : 1, sbw,
+                                                       sub ? sbh >> 1 : sbh, saw, sah, smem, HME_SMEM_BYTES, s_red);
+                uint32_t sad = (uint32_t)(key >> 32), idx = (uint32_t)key;
+                int kx = 0, ky = 0;
+                uint64_t lsad = 0xffffff;
+                if (sad < 0xffffffu) {
+                    lsad = sad;
+                    kx = idx % saw;
+                    ky = idx / saw;
+                }
+                csad = sub ? lsad * 2 : lsad;
+                cx = (int16_t)(kx + xo);
+                cy = (int16_t)(ky + yo);
+            }
+            // set_final_seach_centre_sb: start from region (0,0), strict `<` over (ry outer, rx inner)
+            if (first || csad < best_sad) {
+                best_sad = csad;
+                best_x = cx;
+                best_y = cy;
+                first = false;
+            }
+        }
+    if (threadIdx.x == 0) {
+        RawHme w;
+        w.x = (int16_t)best_x;
+        w.y = (int16_t)best_y;
+        w.valid = 1;
+        w.sad = best_sad;
+        *out = w;
+    }
+}
+
+// -----------------------------------------------------------------------------------------------------
+// Kernel B: integer full-pel search (integer_search_sb :1868-2139 + open_loop_me_fullpel_search_sblock)
+// -----------------------------------------------------------------------------------------------------
+constexpr int FP_SMEM_BYTES = 96 * 1024;
+
+__global__ void __launch_bounds__(NT_SEARCH) fullpel_kernel(const __grid_constant__ MeDev d) {
+    extern __shared__ uint32_t smem[];
+    __shared__ unsigned long long s_best[85];
+    __shared__ HmeState s_h;
+    __shared__ uint32_t s_sad2[2];
+    const SvtB200MeParams &p = d.p;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int sb = blockIdx.x, slot = blockIdx.y;
+    const int l = d.slot_l[slot], r = d.slot_r[slot];
+    uint32_t *o_sad = d.out.best_sad + ((size_t)(sb * 2 + l) * 4 + r) * 85;
+    uint32_t *o_mv = d.out.best_mv + ((size_t)(sb * 2 + l) * 4 + r) * 85;
+
+    if (tid == 0) {
+        derive_hme_state(p, d.raw + (size_t)sb * 8, s_h);
+        s_sad2[0] = s_sad2[1] = 0;
+    }
+    __syncthreads();
+    if (!s_h.do_ref[l][r]) { // pruned by HME: the reference skips the search; slots are defined as 0
+        for (int i = tid; i < 85; i += NT_SEARCH) {
+            o_sad[i] = 0;
+            o_mv[i] = 0;
+        }
+        return;
+    }
+    const int sx = sb % d.sbs_x, sy = sb / d.sbs_x;
+    const int ox = sx * 64, oy = sy * 64;
+    const SvtB200Plane &fp = p.full;
+    const int pic_w = fp.width, pic_h = fp.height;
+    const int sbw = min(pic_w - ox, 64), sbh = min(pic_h - oy, 64);
+    const int sub = p.me_search_method != 0;
+    const uint8_t *srcb = d.src.full + (size_t)(fp.origin_y + oy) * fp.stride + fp.origin_x + ox;
+    const uint8_t *refb = d.refs[l][r].full + (size_t)(fp.origin_y + oy) * fp.stride + fp.origin_x + ox;
+
+    int xsc = s_h.sc_x[l][r], ysc = s_h.sc_y[l][r];
+    const int dist = scaled_dist(p.ref_dist[l][r]);
+    int saw = (int16_t)min(p.search_area_width * dist, p.max_me_search_width);
+    int sah = (int16_t)min(p.search_area_height * dist, p.max_me_search_height);
+    const int dv = (int)s_h.divisor[l][r];
+    saw = (int16_t)(((saw / dv) + 7) & ~0x07);
+    sah = (int16_t)max(1, sah / dv);
+
+    if ((xsc != 0 || ysc != 0) && p.is_used_as_reference_flag) { // check_00_center :1348-1421
+        int cx = xsc, cy = ysc;
+        if (ox + cx < -63) cx = -63 - ox;
+        if (ox + cx > fp.width - 1) cx = cx - ((ox + cx) - (fp.width - 1));
+        if (oy + cy < -63) cy = -63 - oy;
+        if (oy + cy > fp.height - 1) cy = cy - ((oy + cy) - (fp.height - 1));
+        const uint8_t *rh = refb + (ptrdiff_t)cy * fp.stride + cx;
+        uint32_t z = 0, h = 0;
+        const int rows = sbh >> 1;
+        for (int i = tid; i < rows * sbw; i += NT_SEARCH) {
+            int rr = i / sbw, c = i - rr * sbw;
+            int s = srcb[(size_t)rr * 2 * fp.stride + c];
+            z += abs(s - (int)refb[(size_t)rr * 2 * fp.stride + c]);
+            h += abs(s - (int)rh[(ptrdiff_t)rr * 2 * fp.stride + c]);
+        }
+        z = __reduce_add_sync(0xffffffffu, z);
+        h = __reduce_add_sync(0xffffffffu, h);
+        if (lane == 0) {
+            atomicAdd(&s_sad2[0], z);
+            atomicAdd(&s_sad2[1], h);
+        }
+        __syncthreads();
+        if (s_sad2[0] <= s_sad2[1]) cx = cy = 0; // (sad<<1) on both sides, zero wins ties
+        xsc = cx;
+        ysc = cy;
+    }
+    int xo = xsc - (saw >> 1), yo = ysc - (sah >> 1);
+    clamp_window(ox, 63, pic_w, xo, saw);
+    saw = saw < 8 ? saw : saw & ~0x07;
+    clamp_window(oy, 63, pic_h, yo, sah);
+
+    for (int i = tid; i < 85; i += NT_SEARCH) s_best[i] = ((unsigned long long)kMaxSadValue << 32) | 0xffffffffull;
+
+    // ---- stage the source rows that take part in the SAD (even rows only with sub-sampling) ----
+    const int nrows_src = sub ? 32 : 64;
+    uint32_t *s_src = smem; // [nrows_src][16 words]
+    uint32_t *s_win = smem + nrows_src * 16;
+    {
+        uint8_t *sbp = reinterpret_cast<uint8_t *>(s_src);
+        for (int i = tid; i < nrows_src * 64; i += NT_SEARCH) {
+            int rr = i >> 6, c = i & 63;
+            sbp[i] = srcb[(size_t)(sub ? 2 * rr : rr) * fp.stride + c];
+        }
+    }
+    const int span = sub ? 63 : 64;
+    const int wbytes = saw + 63;
+    const int wpw = ((wbytes + 3) >> 2) + 1;
+    const int budget_rows = (FP_SMEM_BYTES - nrows_src * 64) / (wpw * 4);
+    int chunk = min(sah, budget_rows - span + 1);
+    if (chunk < 1) chunk = 1;
+    const int nq = (saw + 3) >> 2; // position quads per search row
+    const int nr8 = sub ? 4 : 8; // rows summed per 8x8
+
+    for (int y0 = 0; y0 < sah; y0 += chunk) {
+        const int cr = min(chunk, sah - y0);
+        const int rows = cr - 1 + span;
+        __syncthreads();
+        {
+            uint8_t *wb = reinterpret_cast<uint8_t *>(s_win);
+            const int rb = wpw * 4;
+            const uint8_t *g = refb + (ptrdiff_t)(yo + y0) * fp.stride + xo;
+            for (int i = tid; i < rows * rb; i += NT_SEARCH) {
+                int rr = i / rb, c = i - rr * rb;
+                wb[i] = c < wbytes ? g[(ptrdiff_t)rr * fp.stride + c] : 0;
+            }
+        }
+        __syncthreads();
+        const int nquads = cr * nq;
+        for (int qb = 0; qb < nquads; qb += NT_SEARCH) { // uniform trip count: every lane joins the reductions
+            const int qi = qb + tid;
+            const bool live = qi < nquads;
+            const int ysl = live ? qi / nq : 0;
+            const int xs0 = live ? (qi - ysl * nq) * 4 : 0;
+            const uint32_t idx0 = (uint32_t)((y0 + ysl) * saw + xs0);
+            uint32_t ok[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) ok[j] = live && (xs0 + j < saw);
+            uint32_t acc32[4] = {0, 0, 0, 0}, acc64[4] = {0, 0, 0, 0};
+            for (int b = 0; b < 16; b++) { // internal (z-order) 16x16 index; 4 consecutive form one 32x32
+                const int ras = c_inv16[b];
+                const int by = ras >> 2, bx = ras & 3;
+                uint32_t s16[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const int py = by * 16 + (q >> 1) * 8, px = bx * 16 + (q & 1) * 8;
+                    uint32_t s8[4] = {0, 0, 0, 0};
+                    if (live) {
+                        const uint32_t *sp = s_src + (sub ? (py >> 1) : py) * 16 + (px >> 2);
+                        const uint32_t *wp = s_win + (ysl + py) * wpw + ((xs0 + px) >> 2);
+#pragma unroll
+                        for (int rr = 0; rr < 8; rr++) {
+                            if (rr < nr8) {
+                                const uint32_t a0 = sp[rr * 16], a1 = sp[rr * 16 + 1];
+                                const uint32_t *w = wp + (sub ? 2 * rr : rr) * wpw;
+                                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+                                s8[0] = sad4(a1, w1, sad4(a0, w0, s8[0]));
+                                s8[1] = sad4(a1, __funnelshift_r(w1, w2, 8), sad4(a0, __funnelshift_r(w0, w1, 8), s8[1]));
+                                s8[2] = sad4(a1, __funnelshift_r(w1, w2, 16), sad4(a0, __funnelshift_r(w0, w1, 16), s8[2]));
+                                s8[3] = sad4(a1, __funnelshift_r(w1, w2, 24), sad4(a0, __funnelshift_r(w0, w1, 24), s8[3]));
+                            }
+                        }
+                    }
+                    uint32_t bs = 0xffffffffu, bi = 0xffffffffu; // thread-local first minimum of its 4 positions
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t v = sub ? s8[j] << 1 : s8[j];
+                        s16[j] += v;
+                        if (ok[j] && v < bs) {
+                            bs = v;
+                            bi = idx0 + j;
+                        }
+                    }
+                    const uint32_t m = __reduce_min_sync(0xffffffffu, bs);
+                    const uint32_t mi = __reduce_min_sync(0xffffffffu, bs == m ? bi : 0xffffffffu);
+                    if (lane == 0 && m != 0xffffffffu) atomicMin(&s_best[21 + 4 * b + q], ((unsigned long long)m << 32) | mi);
+                }
+                {
+                    uint32_t bs = 0xffffffffu, bi = 0xffffffffu;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        acc32[j] += s16[j];
+                        if (ok[j] && s16[j] < bs) {
+                            bs = s16[j];
+                            bi = idx0 + j;
+                        }
+                    }
+                    const uint32_t m = __reduce_min_sync(0xffffffffu, bs);
+                    const uint32_t mi = __reduce_min_sync(0xffffffffu, bs == m ? bi : 0xffffffffu);
+                    if (lane == 0 && m != 0xffffffffu) atomicMin(&s_best[5 + b], ((unsigned long long)m << 32) | mi);
+                }
+                if ((b & 3) == 3) {
+                    uint32_t bs = 0xffffffffu, bi = 0xffffffffu;
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        acc64[j] += acc32[j];
+                        if (ok[j] && acc32[j] < bs) {
+                            bs = acc32[j];
+                            bi = idx0 + j;
+                        }
+                        acc32[j] = 0;
+                    }
+                    const uint32_t m = __reduce_min_sync(0xffffffffu, bs);
+                    const uint32_t mi = __reduce_min_sync(0xffffffffu, bs == m ? bi : 0xffffffffu);
+                    if (lane == 0 && m != 0xffffffffu) atomicMin(&s_best[1 + (b >> 2)], ((unsigned long long)m << 32) | mi);
+                }
+            }
+            {
+                uint32_t bs = 0xffffffffu, bi = 0xffffffffu;
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (ok[j] && acc64[j] < bs) {
+                        bs = acc64[j];
+                        bi = idx0 + j;
+                    }
+                const uint32_t m = __reduce_min_sync(0xffffffffu, bs);
+                const uint32_t mi = __reduce_min_sync(0xffffffffu, bs == m ? bi : 0xffffffffu);
+                if (lane == 0 && m != 0xffffffffu) atomicMin(&s_best[0], ((unsigned long long)m << 32) | mi);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 85; i += NT_SEARCH) {
+        const unsigned long long key = s_best[i];
+        const uint32_t sad = (uint32_t)(key >> 32), idx = (uint32_t)key;
+        uint32_t mv = 0;
+        if (idx != 0xffffffffu) {
+            const int ys = idx / saw, xs = idx - ys * saw;
+            // (y<<18)|(uint16)(x<<2) and the 8-point variant both equal this packing
+            mv = ((uint32_t)(uint16_t)((yo + ys) * 4) << 16) | (uint16_t)((xo + xs) * 4);
+        }
+        o_sad[i] = sad;
+        o_mv[i] = mv;
+    }
+}
+
+// -----------------------------------------------------------------------------------------------------
+// Kernel C: me_prune_ref (:2145-2199), construct_me_candidate_array (:2825-2905), MeSbResults (:2964-3040)
+// -----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(96) finalize_kernel(const __grid_constant__ MeDev d) {
+    __shared__ HmeState s_h;
+    __shared__ uint32_t s_first[85];
+    const SvtB200MeParams &p = d.p;
+    const int tid = threadIdx.x, sb = blockIdx.x;
+    const uint32_t *bsad = d.out.best_sad + (size_t)sb * 2 * 4 * 85;
+    const uint32_t *bmv = d.out.best_mv + (size_t)sb * 2 * 4 * 85;
+    if (tid == 0) {
+        derive_hme_state(p, d.raw + (size_t)sb * 8, s_h);
+        const bool prune_ref = p.enable_hme_flag && p.enable_hme_level2_flag;
+        if (prune_ref && p.enable_me_hme_ref_pruning) {
+            for (int l = 0; l < p.num_lists; l++)
+                for (int r = 0; r < p.num_refs[l]; r++) {
+                    if (!s_h.do_ref[l][r]) {
+                        s_h.sad[l][r] = (uint64_t)kMaxSadValue * 64;
+                        continue;
+                    }
+                    uint64_t s = 0;
+                    for (int i = 0; i < 64; i++) s += bsad[(l * 4 + r) * 85 + 21 + i];
+                    s_h.sad[l][r] = s;
+                }
+            uint64_t best = s_h.sad[0][0];
+            for (int l = 0; l < 2; l++)
+                for (int r = 0; r < 4; r++) best = s_h.sad[l][r] < best ? s_h.sad[l][r] : best;
+            const uint32_t th = (uint32_t)p.prune_ref_if_me_sad_dev_bigger_than_th & 0xFFFFu;
+            for (int l = 0; l < 2; l++)
+                for (int r = 0; r < 4; r++)
+                    if (th != 0xFFFFu && (s_h.sad[l][r] - best) * 100 > (uint64_t)th * best) s_h.do_ref[l][r] = 0;
+        }
+        for (int l = 0; l < 2; l++)
+            for (int r = 0; r < 4; r++) {
+                SvtB200HmeResult o;
+                o.sc_x = s_h.sc_x[l][r];
+                o.sc_y = s_h.sc_y[l][r];
+                o.do_ref = s_h.do_ref[l][r];
+                o.hme_sad = s_h.sad[l][r];
+                d.out.hme[(size_t)sb * 8 + l * 4 + r] = o;
+            }
+    }
+    __syncthreads();
+    if (tid < 85) {
+        const int pu = tid;
+        uint8_t *cand = d.out.me_cand + ((size_t)sb * 85 + pu) * 23;
+        int16_t *mv = d.out.me_mv + ((size_t)sb * 85 + pu) * 7 * 2;
+        for (int i = 0; i < 23; i++) cand[i] = 0;
+        for (int i = 0; i < 14; i++) mv[i] = 0;
+        uint32_t first = 0;
+        int n = 0;
+        if (pu < p.max_number_of_pus_per_sb) {
+            const int n_idx = pu > 20 ? c_tab8[pu - 21] + 21 : pu > 4 ? c_tab16[pu - 5] + 5 : pu;
+            for (int l = 0; l < p.num_lists; l++)
+                for (int r = 0; r < p.num_refs[l]; r++) {
+                    if (!s_h.do_ref[l][r]) continue;
+                    if (n == 0) first = bsad[(l * 4 + r) * 85 + n_idx];
+                    if (n < 23) cand[n] = (uint8_t)(l | (l == 0 ? (r << 2) : (r << 4)) | (l == 1 ? 0x80 : 0));
+                    n++;
+                }
+            if (p.num_lists > 1) {
+                for (int a = 0; a < p.num_refs[0]; a++)
+                    for (int b = 0; b < p.num_refs[1]; b++)
+                        if (s_h.do_ref[0][a] && s_h.do_ref[1][b]) {
+                            if (n < 23) cand[n] = (uint8_t)(2 | (a << 2) | (b << 4) | 0x80);
+                            n++;
+                        }
+                for (int a = 1; a < p.num_refs[0]; a++)
+                    if (s_h.do_ref[0][0] && s_h.do_ref[0][a]) {
+                        if (n < 23) cand[n] = (uint8_t)(2 | (a << 4));
+                        n++;
+                    }
+                if (p.num_refs[1] == 3 && s_h.do_ref[1][0] && s_h.do_ref[1][2]) {
+                    if (n < 23) cand[n] = (uint8_t)(2 | (2 << 4) | 0x40 | 0x80);
+                    n++;
+                }
+            }
+            for (int l = 0; l < p.num_lists; l++)
+                for (int r = 0; r < p.num_refs[l]; r++) {
+                    const uint32_t v = bmv[(l * 4 + r) * 85 + n_idx];
+                    const int s = (l ? 4 : 0) + r;
+                    mv[2 * s] = (int16_t)(v & 0xffff);
+                    mv[2 * s + 1] = (int16_t)(v >> 16);
+                }
+        }
+        d.out.total_cand[(size_t)sb * 85 + pu] = (uint8_t)min(n, 23);
+        s_first[pu] = first;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t rc = 0;
+        if (p.rc_dist_from_8x8)
+            for (int i = 0; i < 64; i++) rc += s_first[21 + i];
+        else
+            for (int i = 0; i < 16; i++) rc += s_first[5 + i];
+        d.out.rc_me_distortion[sb] = rc;
+    }
+}
+
+// -----------------------------------------------------------------------------------------------------
+// Small kernels behind the RTCD drop-ins (single block worth of work each; fidelity, not throughput)
+// -----------------------------------------------------------------------------------------------------
+struct SadLoopArgs {
+    const uint8_t *src, *ref;
+    int src_stride, raw_stride, k, bw, bh, saw, sah;
+    uint64_t *out; // [0] key
+    int smem_bytes;
+};
+__global__ void __launch_bounds__(NT_SEARCH) sad_loop_kernel(const SadLoopArgs a) {
+    extern __shared__ uint32_t smem[];
+    __shared__ uint64_t s_red[NT_SEARCH / 32];
+    uint64_t key = block_search<NT_SEARCH>(a.src, a.src_stride, a.ref, a.raw_stride, a.k, a.bw, a.bh, a.saw, a.sah,
+                                           smem, a.smem_bytes, s_red);
+    if (threadIdx.x == 0) a.out[0] = key;
+}
+
+// 8 search points x 16 16x16 blocks: thread = (block, point). Layout of io (uint32 words):
+//   [0..63] best_sad_8x8  [64..79] best_sad_16x16  [80..143] best_mv8x8  [144..159] best_mv16x16
+//   [160..287] eight_sad16x16[16][8]  [288..799] eight_sad8x8[64][8]
+__global__ void __launch_bounds__(128) ext_all_sad_kernel(const uint8_t *src, int ss, const uint8_t *ref, int rs,
+                                                          uint32_t mv, int sub, uint32_t *io) {
+    __shared__ uint32_t s8[64][8], s16[16][8];
+    const int t = threadIdx.x, i = t & 7, ras = t >> 3;
+    const int by = ras >> 2, bx = ras & 3, b = c_tab16[ras];
+    uint32_t sum = 0;
+    for (int q = 0; q < 4; q++) {
+        const uint8_t *s = src + (size_t)(16 * by + (q >> 1) * 8) * ss + 16 * bx + (q & 1) * 8;
+        const uint8_t *r = ref + (size_t)(16 * by + (q >> 1) * 8) * rs + 16 * bx + (q & 1) * 8 + i;
+        uint32_t v = 0;
+        if (sub) {
+            for (int y = 0; y < 4; y++)
+                for (int x = 0; x < 8; x++) v += abs((int)s[(size_t)2 * y * ss + x] - (int)r[(size_t)2 * y * rs + x]);
+            v <<= 1;
+        } else {
+            for (int y = 0; y < 8; y++)
+                for (int x = 0; x < 8; x++) v += abs((int)s[(size_t)y * ss + x] - (int)r[(size_t)y * rs + x]);
+        }
+        s8[4 * b + q][i] = v;
+        sum += v;
+    }
+    s16[b][i] = sum;
+    __syncthreads();
+    const int16_t mx = (int16_t)(mv & 0xffff), my = (int16_t)(mv >> 16);
+    if (t < 80) { // one thread per PU walks the 8 points in order (strict <)
+        const bool is16 = t >= 64;
+        const int pu = is16 ? t - 64 : t;
+        uint32_t *bs = io + (is16 ? 64 + pu : pu), *bm = io + (is16 ? 144 + pu : 80 + pu);
+        uint32_t cur = *bs, cmv = *bm;
+        for (int j = 0; j < 8; j++) {
+            uint32_t v = is16 ? s16[pu][j] : s8[pu][j];
+            if (v < cur) {
+                cur = v;
+                cmv = ((uint32_t)(uint16_t)my << 16) | (uint16_t)(int16_t)(mx + 4 * j);
+            }
+        }
+        *bs = cur;
+        *bm = cmv;
+    }
+    for (int j = t; j < 128; j += 128) io[160 + j] = s16[j >> 3][j & 7];
+    for (int j = t; j < 512; j += 128) io[288 + j] = s8[j >> 3][j & 7];
+}
+
+// io: [0..127] sad16x16[16][8] (in)  [128..131] best32 [132] best64 [133..136] mv32 [137] mv64 [138..169] sad32[4][8]
+__global__ void ext_eight_32_64_kernel(uint32_t mv, uint32_t *io) {
+    if (threadIdx.x != 0) return;
+    const int16_t mx = (int16_t)(mv & 0xffff), my = (int16_t)(mv >> 16);
+    for (int i = 0; i < 8; i++) {
+        uint32_t s64 = 0;
+        const uint32_t pm = ((uint32_t)(uint16_t)my << 16) | (uint16_t)(int16_t)(mx + 4 * i);
+        for (int q = 0; q < 4; q++) {
+            uint32_t s = io[(4 * q) * 8 + i] + io[(4 * q + 1) * 8 + i] + io[(4 * q + 2) * 8 + i] + io[(4 * q + 3) * 8 + i];
+            io[138 + q * 8 + i] = s;
+            if (s < io[128 + q]) {
+                io[128 + q] = s;
+                io[133 + q] = pm;
+            }
+            s64 += s;
+        }
+        if (s64 < io[132]) {
+            io[132] = s64;
+            io[137] = pm;
+        }
+    }
+}
+
+// single-point variants. io16: [0..3] best8 [4] best16 [5..8] mv8 [9] mv16 [10] sad16 [11..14] sad8
+__global__ void ext_sad_8_16_kernel(const uint8_t *src, int ss, const uint8_t *ref, int rs, uint32_t mv, int sub,
+                                    uint32_t *io) {
+    __shared__ uint32_t s8[4];
+    const int q = threadIdx.x;
+    if (q < 4) {
+        const uint8_t *s = src + (size_t)(q >> 1) * 8 * ss + (q & 1) * 8;
+        const uint8_t *r = ref + (size_t)(q >> 1) * 8 * rs + (q & 1) * 8;
+        uint32_t v = 0;
+        if (sub) {
+            for (int y = 0; y < 4; y++)
+                for (int x = 0; x < 8; x++) v += abs((int)s[(size_t)2 * y * ss + x] - (int)r[(size_t)2 * y * rs + x]);
+            v <<= 1;
+        } else {
+            for (int y = 0; y < 8; y++)
+                for (int x = 0; x < 8; x++) v += abs((int)s[(size_t)y * ss + x] - (int)r[(size_t)y * rs + x]);
+        }
+        s8[q] = v;
+        io[11 + q] = v;
+        if (v < io[q]) {
+            io[q] = v;
+            io[5 + q] = mv;
+        }
+    }
+    __syncthreads();
+    if (q == 0) {
+        uint32_t s = s8[0] + s8[1] + s8[2] + s8[3];
+        if (s < io[4]) {
+            io[4] = s;
+            io[9] = mv;
+        }
+        io[10] = s;
+    }
+}
+// io: [0..15] sad16 (in) [16..19] best32 [20] best64 [21..24] mv32 [25] mv64 [26..29] sad32
+__global__ void ext_sad_32_64_kernel(uint32_t mv, uint32_t *io) {
+    if (threadIdx.x != 0) return;
+    uint32_t s64 = 0;
+    for (int q = 0; q < 4; q++) {
+        uint32_t s = io[4 * q] + io[4 * q + 1] + io[4 * q + 2] + io[4 * q + 3];
+        io[26 + q] = s;
+        if (s < io[16 + q]) {
+            io[16 + q] = s;
+            io[21 + q] = mv;
+        }
+        s64 += s;
+    }
+    if (s64 < io[20]) {
+        io[20] = s64;
+        io[25] = mv;
+    }
+}
+
+__global__ void nxm_sad_kernel(const uint8_t *src, int ss, const uint8_t *ref, int rs, int h, int w, uint32_t *out) {
+    uint32_t v = 0;
+    for (int i = threadIdx.x; i < h * w; i += blockDim.x) {
+        int y = i / w, x = i - y * w;
+        v += abs((int)src[(size_t)y * ss + x] - (int)ref[(size_t)y * rs + x]);
+    }
+    v = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, v);
+}
+
+__global__ void fill32_kernel(uint32_t *p, int n, uint32_t v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+static bool g_attr_done = false;
+static void set_attrs() {
+    if (g_attr_done) return;
+    cudaFuncSetAttribute(hme_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HME_SMEM_BYTES);
+    cudaFuncSetAttribute(fullpel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FP_SMEM_BYTES);
+    cudaFuncSetAttribute(sad_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    g_attr_done = true;
+}
+
+// copy a w x h byte rectangle (row stride `stride`) into a tight buffer
+static void pack_rect(uint8_t *dst, const uint8_t *src, size_t stride, int w, int h) {
+    for (int y = 0; y < h; y++) memcpy(dst + (size_t)y * w, src + (size_t)y * stride, w);
+}
+
+} // namespace
+
+extern "C" {
+
+size_t svt_b200_me_scratch_bytes(const SvtB200MeParams *p) {
+    if (!p) return 0;
+    const size_t n_sb = (size_t)((p->full.width + 63) / 64) * ((p->full.height + 63) / 64);
+    return n_sb * 8 * sizeof(RawHme);
+}
+
+int svt_b200_me_picture(const SvtB200MeParams *p, const SvtB200MePlanes *src,
+                        const SvtB200MePlanes refs[SVT_B200_ME_LISTS][SVT_B200_ME_MAX_REFS],
+                        const SvtB200MeOutputs *out, void *scratch, void *stream) {
+    if (!p || !src || !refs || !out || !scratch) {
+        set_error("svt_b200_me_picture: null argument");
+        return SVT_B200_ERR_ARG;
+    }
+    if (p->num_lists < 1 || p->num_lists > 2 || p->num_refs[0] < 1 || p->num_refs[0] > 4 || p->num_refs[1] < 0 ||
+        p->num_refs[1] > 4 || p->number_hme_search_region_in_width > 2 || p->number_hme_search_region_in_height > 2 ||
+        p->number_hme_search_region_in_width < 1 || p->number_hme_search_region_in_height < 1) {
+        set_error("svt_b200_me_picture: reference structure / HME regions out of range");
+        return SVT_B200_ERR_ARG;
+    }
+    // window sizes the staging budget was sized for (every preset of v0.8.6 at non-screen content fits)
+    if (p->max_me_search_width > 256 || p->max_me_search_height > 256 ||
+        p->hme_level0_max_search_area_in_width_array[0] > 240 || p->hme_level0_max_search_area_in_height_array[0] > 240) {
+        set_error("svt_b200_me_picture: search area larger than the kernels are sized for");
+        return SVT_B200_ERR_UNSUPPORTED;
+    }
+    set_attrs();
+    MeDev d;
+    memset(&d, 0, sizeof(d));
+    d.p = *p;
+    d.src = *src;
+    memcpy(d.refs, refs, sizeof(d.refs));
+    d.out = *out;
+    d.raw = (RawHme *)scratch;
+    d.sbs_x = (p->full.width + 63) / 64;
+    d.sbs_y = (p->full.height + 63) / 64;
+    int n = 0;
+    for (int l = 0; l < p->num_lists; l++)
+        for (int r = 0; r < p->num_refs[l]; r++) {
+            d.slot_l[n] = l;
+            d.slot_r[n] = r;
+            n++;
+        }
+    d.n_slots = n;
+    const int n_sb = d.sbs_x * d.sbs_y;
+    cudaStream_t st = (cudaStream_t)stream;
+    // slots of unused references are defined as zero
+    SVTB_CUDA_TRY(cudaMemsetAsync(out->best_sad, 0, (size_t)n_sb * 8 * 85 * 4, st));
+    SVTB_CUDA_TRY(cudaMemsetAsync(out->best_mv, 0, (size_t)n_sb * 8 * 85 * 4, st));
+    SVTB_CUDA_TRY(cudaMemsetAsync(d.raw, 0, (size_t)n_sb * 8 * sizeof(RawHme), st));
+    SVTB_LAUNCH(hme_kernel, dim3(n_sb, n), NT_SEARCH, HME_SMEM_BYTES, st, d);
+    SVTB_LAUNCH(fullpel_kernel, dim3(n_sb, n), NT_SEARCH, FP_SMEM_BYTES, st, d);
+    SVTB_LAUNCH(finalize_kernel, n_sb, 96, 0, st, d);
+    SVTB_CUDA_TRY(cudaGetLastError());
+    return SVT_B200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// RTCD drop-ins (host pointers)
+// ---------------------------------------------------------------------------------------------------
+void svt_sad_loop_kernel_cuda(uint8_t *src, uint32_t src_stride, uint8_t *ref, uint32_t ref_stride,
+                              uint32_t block_height, uint32_t block_width, uint64_t *best_sad,
+                              int16_t *x_search_center, int16_t *y_search_center, uint32_t src_stride_raw,
+                              int16_t search_area_width, int16_t search_area_height) {
+    *best_sad = 0xffffff;
+    if (search_area_width <= 0 || search_area_height <= 0 || block_width == 0 || block_height == 0) return;
+    if (src_stride_raw == 0 || ref_stride % src_stride_raw != 0) {
+        fprintf(stderr, "svt_sad_loop_kernel_cuda: ref_stride must be a multiple of src_stride_raw\n");
+        abort();
+    }
+    set_attrs();
+    const int k = ref_stride / src_stride_raw;
+    const int bw = block_width, bh = block_height, saw = search_area_width, sah = search_area_height;
+    const int ww = saw - 1 + bw, wh = (sah - 1) + (bh - 1) * k + 1;
+    const size_t src_bytes = (size_t)bw * bh, win_bytes = (size_t)ww * wh;
+    const size_t off_win = (src_bytes + 15) & ~(size_t)15, off_out = (off_win + win_bytes + 15) & ~(size_t)15;
+    ThreadCtx &c = tls();
+    c.reserve(off_out + 16);
+    pack_rect(c.h, src, src_stride, bw, bh);
+    pack_rect(c.h + off_win, ref, src_stride_raw, ww, wh);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.d, c.h, off_out, cudaMemcpyHostToDevice, c.stream));
+    SadLoopArgs a;
+    a.src = c.d;
+    a.ref = c.d + off_win;
+    a.src_stride = bw;
+    a.raw_stride = ww;
+    a.k = k;
+    a.bw = bw;
+    a.bh = bh;
+    a.saw = saw;
+    a.sah = sah;
+    a.out = (uint64_t *)(c.d + off_out);
+    // enough shared memory for the source block + at least one search row, up to 200 KB
+    const size_t spw = (bw + 3) / 4, wpw = (ww + 3) / 4 + 1;
+    size_t need = spw * bh * 4 + wpw * 4 * (size_t)wh;
+    size_t min_need = spw * bh * 4 + wpw * 4 * (size_t)((bh - 1) * k + 1);
+    if (min_need > 200 * 1024) {
+        fprintf(stderr, "svt_sad_loop_kernel_cuda: block too large for shared memory\n");
+        abort();
+    }
+    if (need > 200 * 1024) need = 200 * 1024;
+    a.smem_bytes = (int)need;
+    SVTB_LAUNCH(sad_loop_kernel, 1, NT_SEARCH, need, c.stream, a);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h + off_out, c.d + off_out, 8, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_FATAL(cudaStreamSynchronize(c.stream));
+    uint64_t key;
+    memcpy(&key, c.h + off_out, 8);
+    const uint32_t sad = (uint32_t)(key >> 32), idx = (uint32_t)key;
+    if (sad < 0xffffffu) { // strict < against the 0xffffff start value
+        *best_sad = sad;
+        *x_search_center = (int16_t)(idx % saw);
+        *y_search_center = (int16_t)(idx / saw);
+    }
+}
+
+void svt_ext_all_sad_calculation_8x8_16x16_cuda(uint8_t *src, uint32_t src_stride, uint8_t *ref,
+                                                uint32_t ref_stride, uint32_t mv, uint32_t *p_best_sad_8x8,
+                                                uint32_t *p_best_sad_16x16, uint32_t *p_best_mv8x8,
+                                                uint32_t *p_best_mv16x16, uint32_t p_eight_sad16x16[16][8],
+                                                uint32_t p_eight_sad8x8[64][8], uint8_t sub_sad) {
+    ThreadCtx &c = tls();
+    const size_t off_ref = 64 * 64, off_io = off_ref + 72 * 64, total = off_io + 800 * 4;
+    c.reserve(total);
+    pack_rect(c.h, src, src_stride, 64, 64);
+    pack_rect(c.h + off_ref, ref, ref_stride, 71, 64);
+    uint32_t *io = (uint32_t *)(c.h + off_io);
+    memcpy(io, p_best_sad_8x8, 64 * 4);
+    memcpy(io + 64, p_best_sad_16x16, 16 * 4);
+    memcpy(io + 80, p_best_mv8x8, 64 * 4);
+    memcpy(io + 144, p_best_mv16x16, 16 * 4);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.d, c.h, off_io + 160 * 4, cudaMemcpyHostToDevice, c.stream));
+    SVTB_LAUNCH(ext_all_sad_kernel, 1, 128, 0, c.stream, c.d, 64, c.d + off_ref, 71, mv, (int)sub_sad,
+                (uint32_t *)(c.d + off_io));
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h + off_io, c.d + off_io, 800 * 4, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_FATAL(cudaStreamSynchronize(c.stream));
+    memcpy(p_best_sad_8x8, io, 64 * 4);
+    memcpy(p_best_sad_16x16, io + 64, 16 * 4);
+    memcpy(p_best_mv8x8, io + 80, 64 * 4);
+    memcpy(p_best_mv16x16, io + 144, 16 * 4);
+    memcpy(p_eight_sad16x16, io + 160, 128 * 4);
+    memcpy(p_eight_sad8x8, io + 288, 512 * 4);
+}
+
+void svt_ext_eight_sad_calculation_32x32_64x64_cuda(uint32_t p_sad16x16[16][8], uint32_t *p_best_sad_32x32,
+                                                    uint32_t *p_best_sad_64x64, uint32_t *p_best_mv32x32,
+                                                    uint32_t *p_best_mv64x64, uint32_t mv,
+                                                    uint32_t p_sad32x32[4][8]) {
+    ThreadCtx &c = tls();
+    c.reserve(170 * 4);
+    uint32_t *io = (uint32_t *)c.h;
+    memcpy(io, p_sad16x16, 128 * 4);
+    memcpy(io + 128, p_best_sad_32x32, 16);
+    io[132] = *p_best_sad_64x64;
+    memcpy(io + 133, p_best_mv32x32, 16);
+    io[137] = *p_best_mv64x64;
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.d, c.h, 138 * 4, cudaMemcpyHostToDevice, c.stream));
+    SVTB_LAUNCH(ext_eight_32_64_kernel, 1, 32, 0, c.stream, mv, (uint32_t *)c.d);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h, c.d, 170 * 4, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_FATAL(cudaStreamSynchronize(c.stream));
+    memcpy(p_best_sad_32x32, io + 128, 16);
+    *p_best_sad_64x64 = io[132];
+    memcpy(p_best_mv32x32, io + 133, 16);
+    *p_best_mv64x64 = io[137];
+    memcpy(p_sad32x32, io + 138, 32 * 4);
+}
+
+void svt_ext_sad_calculation_8x8_16x16_cuda(uint8_t *src, uint32_t src_stride, uint8_t *ref, uint32_t ref_stride,
+                                            uint32_t *p_best_sad_8x8, uint32_t *p_best_sad_16x16,
+                                            uint32_t *p_best_mv8x8, uint32_t *p_best_mv16x16, uint32_t mv,
+                                            uint32_t *p_sad16x16, uint32_t *p_sad8x8, uint8_t sub_sad) {
+    ThreadCtx &c = tls();
+    const size_t off_ref = 256, off_io = 512;
+    c.reserve(off_io + 64);
+    pack_rect(c.h, src, src_stride, 16, 16);
+    pack_rect(c.h + off_ref, ref, ref_stride, 16, 16);
+    uint32_t *io = (uint32_t *)(c.h + off_io);
+    memcpy(io, p_best_sad_8x8, 16);
+    io[4] = *p_best_sad_16x16;
+    memcpy(io + 5, p_best_mv8x8, 16);
+    io[9] = *p_best_mv16x16;
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.d, c.h, off_io + 40, cudaMemcpyHostToDevice, c.stream));
+    SVTB_LAUNCH(ext_sad_8_16_kernel, 1, 32, 0, c.stream, c.d, 16, c.d + off_ref, 16, mv, (int)sub_sad,
+                (uint32_t *)(c.d + off_io));
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h + off_io, c.d + off_io, 60, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_FATAL(cudaStreamSynchronize(c.stream));
+    memcpy(p_best_sad_8x8, io, 16);
+    *p_best_sad_16x16 = io[4];
+    memcpy(p_best_mv8x8, io + 5, 16);
+    *p_best_mv16x16 = io[9];
+    *p_sad16x16 = io[10];
+    memcpy(p_sad8x8, io + 11, 16);
+}
+
+void svt_ext_sad_calculation_32x32_64x64_cuda(uint32_t *p_sad16x16, uint32_t *p_best_sad_32x32,
+                                              uint32_t *p_best_sad_64x64, uint32_t *p_best_mv32x32,
+                                              uint32_t *p_best_mv64x64, uint32_t mv, uint32_t *p_sad32x32) {
+    ThreadCtx &c = tls();
+    c.reserve(128);
+    uint32_t *io = (uint32_t *)c.h;
+    memcpy(io, p_sad16x16, 64);
+    memcpy(io + 16, p_best_sad_32x32, 16);
+    io[20] = *p_best_sad_64x64;
+    memcpy(io + 21, p_best_mv32x32, 16);
+    io[25] = *p_best_mv64x64;
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.d, c.h, 26 * 4, cudaMemcpyHostToDevice, c.stream));
+    SVTB_LAUNCH(ext_sad_32_64_kernel, 1, 32, 0, c.stream, mv, (uint32_t *)c.d);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h, c.d, 30 * 4, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_FATAL(cudaStreamSynchronize(c.stream));
+    memcpy(p_best_sad_32x32, io + 16, 16);
+    *p_best_sad_64x64 = io[20];
+    memcpy(p_best_mv32x32, io + 21, 16);
+    *p_best_mv64x64 = io[25];
+    memcpy(p_sad32x32, io + 26, 16);
+}
+
+uint32_t svt_nxm_sad_kernel_cuda(const uint8_t *src, uint32_t src_stride, const uint8_t *ref, uint32_t ref_stride,
+                                 uint32_t height, uint32_t width) {
+    if (!height || !width) return 0;
+    ThreadCtx &c = tls();
+    const size_t n = (size_t)width * height, off_ref = (n + 15) & ~(size_t)15, off_out = 2 * off_ref;
+    c.reserve(off_out + 16);
+    pack_rect(c.h, src, src_stride, width, height);
+    pack_rect(c.h + off_ref, ref, ref_stride, width, height);
+    memset(c.h + off_out, 0, 4);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.d, c.h, off_out + 4, cudaMemcpyHostToDevice, c.stream));
+    SVTB_LAUNCH(nxm_sad_kernel, 1, 256, 0, c.stream, c.d, (int)width, c.d + off_ref, (int)width, (int)height,
+                (int)width, (uint32_t *)(c.d + off_out));
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h + off_out, c.d + off_out, 4, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_FATAL(cudaStreamSynchronize(c.stream));
+    uint32_t v;
+    memcpy(&v, c.h + off_out, 4);
+    return v;
+}
+
+void svt_initialize_buffer_32bits_cuda(uint32_t *pointer, uint32_t count128, uint32_t count32, uint32_t value) {
+    const int n = (int)(count128 * 4 + count32);
+    if (n <= 0) return;
+    ThreadCtx &c = tls();
+    c.reserve((size_t)n * 4);
+    SVTB_LAUNCH(fill32_kernel, (n + 255) / 256, 256, 0, c.stream, (uint32_t *)c.d, n, value);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h, c.d, (size_t)n * 4, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_FATAL(cudaStreamSynchronize(c.stream));
+    memcpy(pointer, c.h, (size_t)n * 4);
+}
+}
