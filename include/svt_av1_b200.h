@@ -203,6 +203,77 @@ SVT_B200_API int svt_b200_me_picture(const SvtB200MeParams *p, const SvtB200MePl
                                      const SvtB200MePlanes refs[SVT_B200_ME_LISTS][SVT_B200_ME_MAX_REFS],
                                      const SvtB200MeOutputs *out, void *scratch, void *stream);
 
+/* =============================================================================================== */
+/* Pictures for the EncDec / in-loop-filter entries                                                */
+/* =============================================================================================== */
+
+/* A 4:2:0 picture in HBM (or host memory for the *_host variants). Pointers address sample (0,0) of
+ * each plane (i.e. EbPictureBufferDesc::buffer_* + origin offsets); strides are in SAMPLES.
+ * bit_depth 8 -> uint8_t samples, 10 -> uint16_t samples (the reference's is_16bit pipeline). */
+typedef struct SvtB200Frame {
+    void *y, *cb, *cr;
+    int32_t stride_y, stride_c;
+    int32_t width, height; /* luma size; chroma is (width+1)>>1 x (height+1)>>1 */
+    int32_t bit_depth;
+} SvtB200Frame;
+
+/* =============================================================================================== */
+/* CDEF                                                                                            */
+/* =============================================================================================== */
+
+/* replaces svt_cdef_find_dir (common_dsp_rtcd.h:1032; C impl Common/Codec/EbCdef.c:132-197) */
+SVT_B200_API int32_t svt_cdef_find_dir_cuda(const uint16_t *img, int32_t stride, int32_t *var,
+                                            int32_t coeff_shift);
+/* replaces svt_cdef_filter_block (common_dsp_rtcd.h:1034; EbCdef.c:202-257). `in` points inside a
+ * CDEF_BSTRIDE(144)-strided uint16 tile with >=2 valid rows/columns around the block; bsize is the
+ * reference's BlockSize enum value (BLOCK_4X4=0, BLOCK_4X8=1, BLOCK_8X4=2, BLOCK_8X8=3). */
+SVT_B200_API void svt_cdef_filter_block_cuda(uint8_t *dst8, uint16_t *dst16, int32_t dstride,
+                                             const uint16_t *in, int32_t pri_strength,
+                                             int32_t sec_strength, int32_t dir, int32_t pri_damping,
+                                             int32_t sec_damping, int32_t bsize, int32_t coeff_shift);
+
+#define SVT_B200_CDEF_MAX_STRENGTHS 64 /* TOTAL_STRENGTHS (EbDefinitions.h:1675-1690) */
+
+/* Strength search of cdef_kernel: replaces cdef_seg_search / cdef_seg_search16bit
+ * (Encoder/Codec/EbCdefProcess.c:80-277, 281-475) for a whole picture. */
+typedef struct SvtB200CdefSearchParams {
+    int32_t mi_rows, mi_cols; /* Av1Common::mi_rows / mi_cols (4x4 units) */
+    int32_t pri_damping; /* 3 + (base_q_idx >> 6); sec_damping is the same */
+    int32_t n_strengths; /* nb_cdef_strengths[pick_method] */
+    /* per strength index gi: (threshold, sec_strength + (sec_strength == 3)) exactly as passed to
+     * svt_cdef_filter_fb (EbCdefProcess.c:236-252); fill with svt_b200_cdef_strength_table(). */
+    int32_t pri_strength[SVT_B200_CDEF_MAX_STRENGTHS];
+    int32_t sec_strength[SVT_B200_CDEF_MAX_STRENGTHS];
+} SvtB200CdefSearchParams;
+
+/* Host helper mirroring get_cdef_filter_strengths (EbDefinitions.h:1696-1722).
+ * pick_method: 0 full(64), 1 lvl1(32), 2 lvl2(20), 3 lvl3(10 — preset 8). Returns n_strengths. */
+SVT_B200_API int svt_b200_cdef_strength_table(int pick_method, SvtB200CdefSearchParams *p);
+
+/* recon  : deblocked reconstruction (pcs->src[] in the reference), read only
+ * source : the input picture (pcs->ref_coeff[])
+ * skip8  : device uint8 [ceil(mi_rows/2)][skip_stride]: 1 where every 4x4 of the 8x8 is `skip`
+ *          (is_8x8_block_skip, EbEncCdef.c:238); this flattens the ModeInfo grid
+ * mse    : device uint64 [2][nvfb*nhfb][64] = pcs->mse_seg (plane 0 = Y, 1 = Cb+Cr); entries of filter
+ *          blocks the reference skips (all-skip) are written as 0. */
+SVT_B200_API int svt_b200_cdef_search(const SvtB200CdefSearchParams *p, const SvtB200Frame *recon,
+                                      const SvtB200Frame *source, const uint8_t *skip8,
+                                      int32_t skip_stride, uint64_t *mse, void *stream);
+
+/* Frame apply: replaces svt_av1_cdef_frame / av1_cdef_frame16bit (EbEncCdef.c:292-660, 663-1030).
+ * fb_strength_idx : device int8 [nvfb*nhfb], mbmi.cdef_strength of each 64x64 filter block (-1: skip)
+ * y_strength/uv_strength : frm_hdr->cdef_params.cdef_y_strength / cdef_uv_strength (host arrays of 8)
+ * Reads `recon` (pre-CDEF) and writes `out` (may not alias recon: the GPU version is out-of-place,
+ * which is what the reference's line/column buffers emulate). Blocks that are not filtered are copied. */
+typedef struct SvtB200CdefApplyParams {
+    int32_t mi_rows, mi_cols;
+    int32_t damping; /* frm_hdr->cdef_params.cdef_damping */
+    int32_t y_strength[8], uv_strength[8];
+} SvtB200CdefApplyParams;
+SVT_B200_API int svt_b200_cdef_apply(const SvtB200CdefApplyParams *p, const SvtB200Frame *recon,
+                                     const SvtB200Frame *out, const uint8_t *skip8, int32_t skip_stride,
+                                     const int8_t *fb_strength_idx, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

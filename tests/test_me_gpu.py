@@ -130,7 +130,8 @@ def test_me_picture_1080p_full_size():
     again = gr.run_gpu_me(params, src, refs)
     cm.assert_me_equal(got, again, params, "idempotence")
     cm.assert_me_equal(got, cm.run_oracle_me(params, src, refs), params, "1080p gpu-vs-oracle")
-    # a picture searched against itself must find zero-SAD, zero-MV everywhere
+    # a picture searched against itself must find SAD 0 for every PU (the MV may be a non-zero tie that comes
+    # earlier in raster order on flat/periodic content, exactly as in the reference)
     refs_same = [src] * 8
     same = gr.run_gpu_me(params, src, refs_same)
-    assert (same.best_sad[:, 0, 0] == 0).all() and (same.best_mv[:, 0, 0] == 0).all()
+    assert (same.best_sad[:, 0, 0] == 0).all()
