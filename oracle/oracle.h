@@ -40,6 +40,16 @@ ORC_API void orc_me_picture(const SvtB200MeParams *p, const SvtB200MePlanes *src
                             const SvtB200MePlanes refs[2][4], uint32_t *best_sad, uint32_t *best_mv,
                             SvtB200HmeResult *hme, int16_t *me_mv, uint8_t *me_cand, uint8_t *total_cand,
                             uint32_t *rc_me_distortion);
+/* ---- cdef_oracle.c ---- */
+ORC_API int32_t orc_cdef_find_dir(const uint16_t *img, int32_t stride, int32_t *var, int32_t coeff_shift);
+ORC_API void orc_cdef_filter_block(uint8_t *dst8, uint16_t *dst16, int32_t dstride, const uint16_t *in,
+                                   int32_t pri_strength, int32_t sec_strength, int32_t dir, int32_t pri_damping,
+                                   int32_t sec_damping, int32_t bsize, int32_t coeff_shift);
+ORC_API void orc_cdef_search(const SvtB200CdefSearchParams *p, const SvtB200Frame *recon,
+                             const SvtB200Frame *source, const uint8_t *skip8, int32_t skip_stride, uint64_t *mse);
+ORC_API void orc_cdef_apply(const SvtB200CdefApplyParams *p, const SvtB200Frame *recon, const SvtB200Frame *out,
+                            const uint8_t *skip8, int32_t skip_stride, const int8_t *fb_strength_idx);
+ORC_API int orc_cdef_strength_table(int pick_method, SvtB200CdefSearchParams *p);
 #ifdef __cplusplus
 }
 #endif

@@ -264,3 +264,139 @@ REFH_API int refh_me_picture(int width, int height, int enc_mode, int n_l0, int 
         }
     return 0;
 }
+
+/* ====================================================================================================
+ * CDEF: cdef_seg_search[16bit] (EbCdefProcess.c:80,281) and svt_av1_cdef_frame / av1_cdef_frame16bit
+ * (EbEncCdef.c:292,663) on a picture described by plain pointers.
+ * ================================================================================================== */
+#include "EbCdefProcess.h"
+#include "EbEncCdef.h"
+#include "EbReferenceObject.h"
+
+void cdef_seg_search(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr, uint32_t segment_index);
+void cdef_seg_search16bit(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr, uint32_t segment_index);
+void svt_av1_cdef_frame(void *context_ptr, SequenceControlSet *scs_ptr, PictureControlSet *pCs);
+void av1_cdef_frame16bit(void *context_ptr, SequenceControlSet *scs_ptr, PictureControlSet *pCs);
+
+typedef struct {
+    SequenceControlSet *scs;
+    PictureControlSet *pcs;
+    PictureParentControlSet *ppcs;
+    Av1Common *cm;
+    ModeInfo *mi;
+    ModeInfo **grid;
+    EbPictureBufferDesc recon, input;
+    EbObjectWrapper scs_wrap;
+} FiltCtx;
+
+/* Picture state shared by the in-loop filter entries. skip8: [ceil(mi_rows/2)][skip_stride]. */
+static FiltCtx *filt_ctx_new(int mi_rows, int mi_cols, int bit_depth, const SvtB200Frame *recon,
+                             const SvtB200Frame *input, const uint8_t *skip8, int skip_stride,
+                             const int8_t *fb_strength_idx) {
+    refh_init();
+    FiltCtx *c = calloc(1, sizeof(*c));
+    c->scs = calloc(1, sizeof(SequenceControlSet));
+    c->pcs = calloc(1, sizeof(PictureControlSet));
+    c->ppcs = calloc(1, sizeof(PictureParentControlSet));
+    c->cm = calloc(1, sizeof(Av1Common));
+    c->scs_wrap.object_ptr = c->scs;
+    c->pcs->scs_wrapper_ptr = &c->scs_wrap;
+    c->pcs->parent_pcs_ptr = c->ppcs;
+    c->ppcs->scs_wrapper_ptr = &c->scs_wrap;
+    c->ppcs->av1_cm = c->cm;
+    c->scs->static_config.encoder_bit_depth = bit_depth;
+    c->scs->seq_header.color_config.mono_chrome = 0;
+    c->cm->mi_rows = mi_rows;
+    c->cm->mi_cols = mi_cols;
+    c->cm->mi_stride = mi_cols;
+    c->pcs->mi_stride = mi_cols;
+    c->ppcs->aligned_width = (uint16_t)(mi_cols * 4);
+    c->ppcs->aligned_height = (uint16_t)(mi_rows * 4);
+    c->ppcs->is_used_as_reference_flag = EB_FALSE;
+    c->mi = calloc((size_t)mi_rows * mi_cols, sizeof(ModeInfo));
+    c->grid = calloc((size_t)mi_rows * mi_cols, sizeof(ModeInfo *));
+    const int nhfb = (mi_cols + 15) / 16;
+    for (int r = 0; r < mi_rows; r++)
+        for (int q = 0; q < mi_cols; q++) {
+            ModeInfo *m = &c->mi[(size_t)r * mi_cols + q];
+            c->grid[(size_t)r * mi_cols + q] = m;
+            m->mbmi.block_mi.sb_type = BLOCK_8X8;
+            m->mbmi.block_mi.skip = skip8 ? skip8[(r >> 1) * skip_stride + (q >> 1)] : 0;
+            m->mbmi.cdef_strength = fb_strength_idx ? fb_strength_idx[(r >> 4) * nhfb + (q >> 4)] : 0;
+        }
+    c->pcs->mi_grid_base = c->grid;
+    const int hbd = bit_depth > 8;
+    EbPictureBufferDesc *d[2] = {&c->recon, &c->input};
+    const SvtB200Frame *f[2] = {recon, input};
+    for (int i = 0; i < 2; i++) {
+        if (!f[i]) continue;
+        d[i]->buffer_y = f[i]->y;
+        d[i]->buffer_cb = f[i]->cb;
+        d[i]->buffer_cr = f[i]->cr;
+        d[i]->stride_y = (uint16_t)f[i]->stride_y;
+        d[i]->stride_cb = d[i]->stride_cr = (uint16_t)f[i]->stride_c;
+        d[i]->origin_x = d[i]->origin_y = 0;
+        d[i]->width = (uint16_t)(mi_cols * 4);
+        d[i]->height = (uint16_t)(mi_rows * 4);
+        d[i]->bit_depth = hbd ? EB_10BIT : EB_8BIT;
+    }
+    c->pcs->recon_picture_ptr = &c->recon;
+    c->pcs->recon_picture16bit_ptr = &c->recon;
+    c->pcs->input_frame16bit = &c->input;
+    c->ppcs->enhanced_picture_ptr = &c->input;
+    return c;
+}
+static void filt_ctx_free(FiltCtx *c) {
+    free(c->mi);
+    free(c->grid);
+    free(c->cm);
+    free(c->ppcs);
+    free(c->pcs);
+    free(c->scs);
+    free(c);
+}
+
+REFH_API int refh_cdef_search(int mi_rows, int mi_cols, int base_q_idx, int cdef_level, const SvtB200Frame *recon,
+                              const SvtB200Frame *source, const uint8_t *skip8, int skip_stride,
+                              uint64_t *mse /*[2][nfb][64]*/) {
+    FiltCtx *c = filt_ctx_new(mi_rows, mi_cols, recon->bit_depth, recon, source, skip8, skip_stride, NULL);
+    const int nfb = ((mi_rows + 15) / 16) * ((mi_cols + 15) / 16);
+    c->ppcs->frm_hdr.quantization_params.base_q_idx = (uint8_t)base_q_idx;
+    c->ppcs->cdef_level = (int8_t)cdef_level;
+    c->pcs->cdef_segments_column_count = 1;
+    c->pcs->cdef_segments_row_count = 1;
+    c->pcs->cdef_segments_total_count = 1;
+    memset(mse, 0, sizeof(uint64_t) * 2 * nfb * 64);
+    c->pcs->mse_seg[0] = (uint64_t(*)[TOTAL_STRENGTHS])mse;
+    c->pcs->mse_seg[1] = (uint64_t(*)[TOTAL_STRENGTHS])(mse + (size_t)nfb * 64);
+    c->pcs->src[0] = recon->y;
+    c->pcs->src[1] = recon->cb;
+    c->pcs->src[2] = recon->cr;
+    c->pcs->ref_coeff[0] = source->y;
+    c->pcs->ref_coeff[1] = source->cb;
+    c->pcs->ref_coeff[2] = source->cr;
+    if (recon->bit_depth > 8)
+        cdef_seg_search16bit(c->pcs, c->scs, 0);
+    else
+        cdef_seg_search(c->pcs, c->scs, 0);
+    filt_ctx_free(c);
+    return 0;
+}
+
+/* in place on `recon` (the reference's behaviour) */
+REFH_API int refh_cdef_apply(int mi_rows, int mi_cols, int damping, const int32_t *y_strength,
+                             const int32_t *uv_strength, SvtB200Frame *recon, const uint8_t *skip8, int skip_stride,
+                             const int8_t *fb_strength_idx) {
+    FiltCtx *c = filt_ctx_new(mi_rows, mi_cols, recon->bit_depth, recon, NULL, skip8, skip_stride, fb_strength_idx);
+    c->ppcs->frm_hdr.cdef_params.cdef_damping = (uint8_t)damping;
+    for (int i = 0; i < 8; i++) {
+        c->ppcs->frm_hdr.cdef_params.cdef_y_strength[i] = y_strength[i];
+        c->ppcs->frm_hdr.cdef_params.cdef_uv_strength[i] = uv_strength[i];
+    }
+    if (recon->bit_depth > 8)
+        av1_cdef_frame16bit(NULL, c->scs, c->pcs);
+    else
+        svt_av1_cdef_frame(NULL, c->scs, c->pcs);
+    filt_ctx_free(c);
+    return 0;
+}

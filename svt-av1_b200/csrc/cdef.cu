@@ -1,0 +1,515 @@
+// cdef.cu — constrained directional enhancement filter on sm_100a.
+//
+// Replaces (reference files under Source/Lib):
+//   svt_cdef_find_dir_c, svt_cdef_filter_block_c, svt_cdef_filter_fb   Common/Codec/EbCdef.c:132-388
+//   cdef_seg_search / cdef_seg_search16bit                             Encoder/Codec/EbCdefProcess.c:80-475
+//   compute_cdef_dist_c / _8bit_c (incl. the double-precision 8x8 distortion) Encoder/Codec/EbEncCdef.c:20-220
+//   svt_av1_cdef_frame / av1_cdef_frame16bit                           Encoder/Codec/EbEncCdef.c:292-1030
+//
+// Design: one CTA per 64x64 filter block.  The deblocked reconstruction of the block (+2 sample rim, frame
+// exterior = CDEF_VERY_LARGE) is staged ONCE into shared memory as int16 and every strength of the search is
+// evaluated from that tile, so HBM traffic is recon + source once per block (2 B/sample) instead
+// of once per strength.  A thread owns one row of one 8x8 (or 4x4 chroma) block; block sums for the
+// distortion are reduced with 8-lane shuffles.  The 8x8 luma distortion keeps the reference's double formula
+// with explicit round-to-nearest intrinsics (no FMA contraction) so it is bit-identical (0 ULP).
+#include "common.cuh"
+
+using namespace svtb200;
+
+namespace {
+
+constexpr int VERY_LARGE = 16384; // CDEF_VERY_LARGE
+constexpr int TS = 72; // tile row stride (int16): 64 + 2*2 rim, padded
+constexpr int NT = 256;
+
+__constant__ int8_t c_dir[8][2][2] = {{{-1, 1}, {-2, 2}}, {{0, 1}, {-1, 2}}, {{0, 1}, {0, 2}}, {{0, 1}, {1, 2}},
+                                      {{1, 1}, {2, 2}},   {{1, 0}, {2, 1}},  {{1, 0}, {2, 0}}, {{1, 0}, {2, -1}}};
+
+__device__ __forceinline__ int msb(uint32_t n) { return 31 - __clz((int)n); }
+
+// constrain() of EbCdef.c:86-93 with the shift (max(0, damping - msb(threshold))) hoisted by the caller
+__device__ __forceinline__ int constrain_s(int diff, int threshold, int shift) {
+    const int mag = abs(diff);
+    const int lim = max(0, threshold - (mag >> shift));
+    const int v = min(mag, lim);
+    return diff < 0 ? -v : v;
+}
+__device__ __forceinline__ int adjust_strength(int strength, int var) {
+    const int i = (var >> 6) ? min(msb((uint32_t)(var >> 6)), 12) : 0;
+    return var ? (strength * (4 + i) + 8) >> 4 : 0;
+}
+
+// body of svt_cdef_filter_block_c for one sample; `in` points into an int16 tile of stride `s`
+__device__ __forceinline__ int cdef_sample(const int16_t *in, int s, int pri, int sec, int dir, int pri_damping,
+                                           int sec_damping, int coeff_shift) {
+    const int x = in[0];
+    if (pri == 0 && sec == 0) return x; // every constrain() is 0 and x lies inside [min,max]
+    const int odd = (pri >> coeff_shift) & 1;
+    const int pt0 = odd ? 3 : 4, pt1 = odd ? 3 : 2;
+    const int psh = pri ? max(0, pri_damping - msb((uint32_t)pri)) : 0;
+    const int ssh = sec ? max(0, sec_damping - msb((uint32_t)sec)) : 0;
+    int sum = 0, mx = x, mn = x;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int po = c_dir[dir][k][0] * s + c_dir[dir][k][1];
+        const int p0 = in[po], p1 = in[-po];
+        const int pt = k ? pt1 : pt0;
+        if (pri) sum += pt * constrain_s(p0 - x, pri, psh) + pt * constrain_s(p1 - x, pri, psh);
+        if (p0 != VERY_LARGE) mx = max(mx, p0);
+        if (p1 != VERY_LARGE) mx = max(mx, p1);
+        mn = min(mn, min(p0, p1));
+        const int o2 = c_dir[(dir + 2) & 7][k][0] * s + c_dir[(dir + 2) & 7][k][1];
+        const int o6 = c_dir[(dir + 6) & 7][k][0] * s + c_dir[(dir + 6) & 7][k][1];
+        const int s0 = in[o2], s1 = in[-o2], s2 = in[o6], s3 = in[-o6];
+        if (s0 != VERY_LARGE) mx = max(mx, s0);
+        if (s1 != VERY_LARGE) mx = max(mx, s1);
+        if (s2 != VERY_LARGE) mx = max(mx, s2);
+        if (s3 != VERY_LARGE) mx = max(mx, s3);
+        mn = min(mn, min(min(s0, s1), min(s2, s3)));
+        const int stp = k ? 1 : 2;
+        if (sec)
+            sum += stp * (constrain_s(s0 - x, sec, ssh) + constrain_s(s1 - x, sec, ssh) + constrain_s(s2 - x, sec, ssh) +
+                          constrain_s(s3 - x, sec, ssh));
+    }
+    const int y = x + ((8 + sum - (sum < 0)) >> 4);
+    return min(max(y, mn), mx);
+}
+
+// svt_cdef_find_dir_c on an 8x8 block of an int16 tile (serial; one thread per block)
+__device__ int find_dir(const int16_t *img, int stride, int *var, int coeff_shift) {
+    const int div_table[9] = {0, 840, 420, 280, 210, 168, 140, 120, 105};
+    int partial[8][15];
+#pragma unroll
+    for (int a = 0; a < 8; a++)
+#pragma unroll
+        for (int b = 0; b < 15; b++) partial[a][b] = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int x = (img[i * stride + j] >> coeff_shift) - 128;
+            partial[0][i + j] += x;
+            partial[1][i + j / 2] += x;
+            partial[2][i] += x;
+            partial[3][3 + i - j / 2] += x;
+            partial[4][7 + i - j] += x;
+            partial[5][3 - i / 2 + j] += x;
+            partial[6][j] += x;
+            partial[7][i / 2 + j] += x;
+        }
+    int cost[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        cost[2] += partial[2][i] * partial[2][i];
+        cost[6] += partial[6][i] * partial[6][i];
+    }
+    cost[2] *= div_table[8];
+    cost[6] *= div_table[8];
+#pragma unroll
+    for (int i = 0; i < 7; i++) {
+        cost[0] += (partial[0][i] * partial[0][i] + partial[0][14 - i] * partial[0][14 - i]) * div_table[i + 1];
+        cost[4] += (partial[4][i] * partial[4][i] + partial[4][14 - i] * partial[4][14 - i]) * div_table[i + 1];
+    }
+    cost[0] += partial[0][7] * partial[0][7] * div_table[8];
+    cost[4] += partial[4][7] * partial[4][7] * div_table[8];
+#pragma unroll
+    for (int d = 1; d < 8; d += 2) {
+#pragma unroll
+        for (int j = 0; j < 5; j++) cost[d] += partial[d][3 + j] * partial[d][3 + j];
+        cost[d] *= div_table[8];
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+            cost[d] += (partial[d][j] * partial[d][j] + partial[d][10 - j] * partial[d][10 - j]) * div_table[2 * j + 2];
+    }
+    int best_cost = 0, best_dir = 0;
+#pragma unroll
+    for (int d = 0; d < 8; d++)
+        if (cost[d] > best_cost) {
+            best_cost = cost[d];
+            best_dir = d;
+        }
+    int orth = 0;
+#pragma unroll
+    for (int d = 0; d < 8; d++)
+        if (d == ((best_dir + 4) & 7)) orth = cost[d];
+    *var = (best_cost - orth) >> 10;
+    return best_dir;
+}
+
+struct FrameDev {
+    const void *p[3];
+    int stride[3];
+    int hbd;
+};
+template <typename T>
+__device__ __forceinline__ int ldpx(const void *p, size_t off) {
+    return reinterpret_cast<const T *>(p)[off];
+}
+
+// Stage the filter block of plane `pli` (+2 rim; outside the frame = VERY_LARGE) into an int16 tile.
+template <typename T>
+__device__ void load_tile(const void *plane, int stride, int pw, int ph, int y0, int x0, int bh, int bw, int16_t *tile) {
+    const int rw = bw + 4;
+    for (int i = threadIdx.x; i < (bh + 4) * rw; i += NT) {
+        const int r = i / rw, c = i - r * rw;
+        const int yy = y0 + r - 2, xx = x0 + c - 2;
+        tile[r * TS + c] = (yy >= 0 && yy < ph && xx >= 0 && xx < pw) ? (int16_t)ldpx<T>(plane, (size_t)yy * stride + xx) : (int16_t)VERY_LARGE;
+    }
+}
+
+struct CdefSearchDev {
+    SvtB200CdefSearchParams p;
+    FrameDev recon, source;
+    const uint8_t *skip8;
+    int skip_stride;
+    uint64_t *mse;
+    int nvfb, nhfb, coeff_shift;
+};
+
+// dist_8x8_8bit_c / dist_8x8_16bit_c (EbEncCdef.c:20-33, 75-98): identical IEEE double operation sequence
+__device__ __forceinline__ unsigned long long dist8x8_from_sums(unsigned long long sum_s, unsigned long long sum_d,
+                                                                unsigned long long sum_s2, unsigned long long sum_d2,
+                                                                unsigned long long sum_sd, int coeff_shift) {
+    const unsigned long long svar = sum_s2 - ((sum_s * sum_s + 32) >> 6);
+    const unsigned long long dvar = sum_d2 - ((sum_d * sum_d + 32) >> 6);
+    const double a = __dmul_rn((double)(sum_d2 + sum_s2 - 2 * sum_sd), .5);
+    const double b = __dmul_rn(a, (double)(svar + dvar + (unsigned long long)(400 << 2 * coeff_shift)));
+    const double c = __dsqrt_rn(__dadd_rn((double)(20000 << 4 * coeff_shift), __dmul_rn((double)svar, (double)dvar)));
+    return (unsigned long long)floor(__dadd_rn(.5, __ddiv_rn(b, c)));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(NT) cdef_search_kernel(const __grid_constant__ CdefSearchDev d) {
+    __shared__ int16_t tile[68 * TS];
+    __shared__ uint8_t s_by[64], s_bx[64];
+    __shared__ int8_t s_dir[64];
+    __shared__ int s_var[64];
+    __shared__ int s_count;
+    __shared__ unsigned long long s_mse[64];
+    const int tid = threadIdx.x;
+    const int fb = blockIdx.x, fbr = fb / d.nhfb, fbc = fb - fbr * d.nhfb;
+    const SvtB200CdefSearchParams &p = d.p;
+    const int nvb = min(16, p.mi_rows - 16 * fbr), nhb = min(16, p.mi_cols - 16 * fbc);
+    const int cs = d.coeff_shift;
+    uint64_t *out_y = d.mse + ((size_t)fb) * 64;
+    uint64_t *out_c = d.mse + ((size_t)d.nvfb * d.nhfb + fb) * 64;
+    if (tid == 0) { // svt_sb_compute_cdef_list: raster list of the non-skip 8x8 blocks
+        int n = 0;
+        for (int r = 0; r < nvb; r += 2)
+            for (int c = 0; c < nhb; c += 2)
+                if (!d.skip8[(size_t)((16 * fbr + r) >> 1) * d.skip_stride + ((16 * fbc + c) >> 1)]) {
+                    s_by[n] = (uint8_t)(r >> 1);
+                    s_bx[n] = (uint8_t)(c >> 1);
+                    n++;
+                }
+        s_count = n;
+    }
+    __syncthreads();
+    const int count = s_count;
+    if (count == 0) { // svt_sb_all_skip: not searched; entries defined as 0
+        for (int i = tid; i < 64; i += NT) {
+            out_y[i] = 0;
+            out_c[i] = 0;
+        }
+        return;
+    }
+    for (int pli = 0; pli < 3; pli++) {
+        const int sh = pli ? 1 : 0, bs = 8 >> sh;
+        const int pw = (p.mi_cols * 4) >> sh, ph = (p.mi_rows * 4) >> sh;
+        const int bh = (nvb * 4) >> sh, bw = (nhb * 4) >> sh;
+        const int y0 = (fbr * 64) >> sh, x0 = (fbc * 64) >> sh;
+        __syncthreads();
+        load_tile<T>(d.recon.p[pli], d.recon.stride[pli], pw, ph, y0, x0, bh, bw, tile);
+        for (int i = tid; i < 64; i += NT) s_mse[i] = 0;
+        __syncthreads();
+        const int16_t *in = tile + 2 * TS + 2;
+        if (pli == 0) {
+            if (tid < count) {
+                int v;
+                s_dir[tid] = (int8_t)find_dir(in + 8 * s_by[tid] * TS + 8 * s_bx[tid], TS, &v, cs);
+                s_var[tid] = v;
+            }
+            __syncthreads();
+        }
+        const int damping = p.pri_damping + cs - (pli != 0);
+        const int rows_per_blk = bs; // threads per block = rows
+        const int blk_per_pass = NT / rows_per_blk;
+        const void *sp = d.source.p[pli];
+        const int sstride = d.source.stride[pli];
+        for (int gi = 0; gi < p.n_strengths; gi++) {
+            const int pri = p.pri_strength[gi] << cs, sec = p.sec_strength[gi] << cs;
+            unsigned long long acc = 0;
+            for (int b0 = 0; b0 < count; b0 += blk_per_pass) {
+                const int b = b0 + tid / rows_per_blk, row = tid % rows_per_blk;
+                const bool live = b < count;
+                unsigned int ss = 0, sd = 0, ss2 = 0, sd2 = 0, ssd = 0, se = 0;
+                if (live) {
+                    const int by = s_by[b], bx = s_bx[b];
+                    const int t = pli ? pri : adjust_strength(pri, s_var[b]);
+                    const int dir = pri ? s_dir[b] : 0;
+                    const int16_t *q = in + (by * bs + row) * TS + bx * bs;
+                    const size_t so = (size_t)(y0 + by * bs + row) * sstride + x0 + bx * bs;
+                    for (int j = 0; j < bs; j++) {
+                        const int f = cdef_sample(q + j, TS, t, sec, dir, damping, damping, cs);
+                        const int o = ldpx<T>(sp, so + j);
+                        if (pli == 0) {
+                            ss += f;
+                            sd += o;
+                            ss2 += f * f;
+                            sd2 += o * o;
+                            ssd += f * o;
+                        } else {
+                            se += (o - f) * (o - f);
+                        }
+                    }
+                }
+                if (pli == 0) { // 8 lanes = one 8x8 block
+#pragma unroll
+                    for (int o = 1; o < 8; o <<= 1) {
+                        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+                        sd += __shfl_xor_sync(0xffffffffu, sd, o);
+                        ss2 += __shfl_xor_sync(0xffffffffu, ss2, o);
+                        sd2 += __shfl_xor_sync(0xffffffffu, sd2, o);
+                        ssd += __shfl_xor_sync(0xffffffffu, ssd, o);
+                    }
+                    if (live && row == 0) acc += dist8x8_from_sums(ss, sd, ss2, sd2, ssd, cs);
+                } else {
+                    acc += se;
+                }
+            }
+            // CTA-wide sum of this strength
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if ((tid & 31) == 0 && acc) atomicAdd(&s_mse[gi], acc);
+        }
+        __syncthreads();
+        for (int gi = tid; gi < 64; gi += NT) {
+            const unsigned long long v = gi < p.n_strengths ? (s_mse[gi] >> (2 * cs)) : 0;
+            if (pli == 0)
+                out_y[gi] = v;
+            else if (pli == 1)
+                out_c[gi] = v;
+            else
+                out_c[gi] += v;
+        }
+    }
+}
+
+struct CdefApplyDev {
+    SvtB200CdefApplyParams p;
+    FrameDev recon, out;
+    const uint8_t *skip8;
+    int skip_stride;
+    const int8_t *fb_idx;
+    int nvfb, nhfb, coeff_shift;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(NT) cdef_apply_kernel(const __grid_constant__ CdefApplyDev d) {
+    __shared__ int16_t tile[68 * TS];
+    __shared__ uint8_t s_skip[64];
+    __shared__ int8_t s_dir[64];
+    __shared__ int s_var[64];
+    __shared__ int s_any;
+    const int tid = threadIdx.x;
+    const int fb = blockIdx.x, fbr = fb / d.nhfb, fbc = fb - fbr * d.nhfb;
+    const SvtB200CdefApplyParams &p = d.p;
+    const int nvb = min(16, p.mi_rows - 16 * fbr), nhb = min(16, p.mi_cols - 16 * fbc);
+    const int cs = d.coeff_shift;
+    const int idx = d.fb_idx[fb];
+    int level = 0, sec = 0, uv_level = 0, uv_sec = 0;
+    if (idx >= 0) {
+        level = p.y_strength[idx] / 4;
+        sec = p.y_strength[idx] % 4;
+        sec += sec == 3;
+        uv_level = p.uv_strength[idx] / 4;
+        uv_sec = p.uv_strength[idx] % 4;
+        uv_sec += uv_sec == 3;
+    }
+    const bool fb_on = idx >= 0 && !(level == 0 && sec == 0 && uv_level == 0 && uv_sec == 0);
+    if (tid == 0) s_any = 0;
+    __syncthreads();
+    if (tid < 64) {
+        const int by = tid >> 3, bx = tid & 7;
+        int sk = 1;
+        if (fb_on && 2 * by < nvb && 2 * bx < nhb)
+            sk = d.skip8[(size_t)((16 * fbr + 2 * by) >> 1) * d.skip_stride + ((16 * fbc + 2 * bx) >> 1)];
+        s_skip[tid] = (uint8_t)sk;
+        if (!sk) s_any = 1;
+    }
+    __syncthreads();
+    const bool filt = fb_on && s_any;
+    for (int pli = 0; pli < 3; pli++) {
+        const int sh = pli ? 1 : 0, bs = 8 >> sh;
+        const int pw = (p.mi_cols * 4) >> sh, ph = (p.mi_rows * 4) >> sh;
+        const int bh = (nvb * 4) >> sh, bw = (nhb * 4) >> sh;
+        const int y0 = (fbr * 64) >> sh, x0 = (fbc * 64) >> sh;
+        __syncthreads();
+        load_tile<T>(d.recon.p[pli], d.recon.stride[pli], pw, ph, y0, x0, bh, bw, tile);
+        __syncthreads();
+        const int16_t *in = tile + 2 * TS + 2;
+        if (pli == 0 && filt) {
+            if (tid < 64 && !s_skip[tid]) {
+                int v;
+                s_dir[tid] = (int8_t)find_dir(in + 8 * (tid >> 3) * TS + 8 * (tid & 7), TS, &v, cs);
+                s_var[tid] = v;
+            }
+            __syncthreads();
+        }
+        const int pri = (pli ? uv_level : level) << cs, s2 = (pli ? uv_sec : sec) << cs;
+        const int damping = p.damping + cs - (pli != 0);
+        T *op = reinterpret_cast<T *>(const_cast<void *>(d.out.p[pli]));
+        const int ostride = d.out.stride[pli];
+        for (int i = tid; i < bh * bw; i += NT) {
+            const int r = i / bw, c = i - r * bw;
+            const int b = (r / bs) * 8 + (c / bs);
+            int v = in[r * TS + c];
+            if (filt && !s_skip[b]) {
+                const int t = pli ? pri : adjust_strength(pri, s_var[b]);
+                v = cdef_sample(in + r * TS + c, TS, t, s2, pri ? s_dir[b] : 0, damping, damping, cs);
+            }
+            op[(size_t)(y0 + r) * ostride + x0 + c] = (T)v;
+        }
+    }
+}
+
+// drop-in kernels ----------------------------------------------------------------------------------------
+__global__ void find_dir_kernel(const uint16_t *img, int stride, int coeff_shift, int *out) {
+    if (threadIdx.x == 0) {
+        int16_t t[64];
+        for (int i = 0; i < 8; i++)
+            for (int j = 0; j < 8; j++) t[i * 8 + j] = (int16_t)img[i * stride + j];
+        int v;
+        out[0] = find_dir(t, 8, &v, coeff_shift);
+        out[1] = v;
+    }
+}
+// in: 12x12 uint16 window (2 rim) of the block, out: 8x8 ints
+__global__ void filter_block_kernel(const uint16_t *win, int pri, int sec, int dir, int pd, int sd, int rows, int cols,
+                                    int coeff_shift, uint16_t *out) {
+    __shared__ int16_t t[12 * 12];
+    for (int i = threadIdx.x; i < 144; i += blockDim.x) t[i] = (int16_t)win[i];
+    __syncthreads();
+    const int i = threadIdx.x >> 3, j = threadIdx.x & 7;
+    if (i < rows && j < cols) out[i * 8 + j] = (uint16_t)cdef_sample(t + (i + 2) * 12 + j + 2, 12, pri, sec, dir, pd, sd, coeff_shift);
+}
+
+static int frame_dev(const SvtB200Frame *f, FrameDev *o) {
+    if (!f || !f->y || !f->cb || !f->cr || (f->bit_depth != 8 && f->bit_depth != 10 && f->bit_depth != 12)) return -1;
+    o->p[0] = f->y;
+    o->p[1] = f->cb;
+    o->p[2] = f->cr;
+    o->stride[0] = f->stride_y;
+    o->stride[1] = o->stride[2] = f->stride_c;
+    o->hbd = f->bit_depth > 8;
+    return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+int svt_b200_cdef_strength_table(int pick_method, SvtB200CdefSearchParams *p) {
+    // get_cdef_filter_strengths (EbDefinitions.h:1696-1722) + `sec_strength + (sec_strength == 3)` of the callers
+    static const int n[4] = {64, 32, 20, 10};
+    static const int pri1[8] = {0, 1, 2, 3, 5, 7, 10, 13}, pri2[5] = {0, 2, 4, 8, 14}, sec3[2] = {0, 2};
+    if (!p || pick_method < 0 || pick_method > 3) return SVT_B200_ERR_ARG;
+    const int tot_sec = pick_method == 3 ? 2 : 4;
+    p->n_strengths = n[pick_method];
+    for (int gi = 0; gi < p->n_strengths; gi++) {
+        const int pi = gi / tot_sec, si = gi % tot_sec;
+        const int pri = pick_method == 0 ? pi : pick_method == 1 ? pri1[pi] : pri2[pi];
+        const int sec = pick_method == 3 ? sec3[si] : si;
+        p->pri_strength[gi] = pri;
+        p->sec_strength[gi] = sec + (sec == 3);
+    }
+    return p->n_strengths;
+}
+
+int svt_b200_cdef_search(const SvtB200CdefSearchParams *p, const SvtB200Frame *recon, const SvtB200Frame *source,
+                         const uint8_t *skip8, int32_t skip_stride, uint64_t *mse, void *stream) {
+    CdefSearchDev d;
+    if (!p || !skip8 || !mse || frame_dev(recon, &d.recon) || frame_dev(source, &d.source) ||
+        recon->bit_depth != source->bit_depth || p->n_strengths < 1 || p->n_strengths > 64) {
+        set_error("svt_b200_cdef_search: bad argument");
+        return SVT_B200_ERR_ARG;
+    }
+    d.p = *p;
+    d.skip8 = skip8;
+    d.skip_stride = skip_stride;
+    d.mse = mse;
+    d.nvfb = (p->mi_rows + 15) / 16;
+    d.nhfb = (p->mi_cols + 15) / 16;
+    d.coeff_shift = recon->bit_depth - 8;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d.recon.hbd)
+        SVTB_LAUNCH(cdef_search_kernel<uint16_t>, d.nvfb * d.nhfb, NT, 0, st, d);
+    else
+        SVTB_LAUNCH(cdef_search_kernel<uint8_t>, d.nvfb * d.nhfb, NT, 0, st, d);
+    SVTB_CUDA_TRY(cudaGetLastError());
+    return SVT_B200_OK;
+}
+
+int svt_b200_cdef_apply(const SvtB200CdefApplyParams *p, const SvtB200Frame *recon, const SvtB200Frame *out,
+                        const uint8_t *skip8, int32_t skip_stride, const int8_t *fb_strength_idx, void *stream) {
+    CdefApplyDev d;
+    if (!p || !skip8 || !fb_strength_idx || frame_dev(recon, &d.recon) || frame_dev(out, &d.out) ||
+        recon->bit_depth != out->bit_depth || recon->y == out->y) {
+        set_error("svt_b200_cdef_apply: bad argument (out must not alias recon)");
+        return SVT_B200_ERR_ARG;
+    }
+    d.p = *p;
+    d.skip8 = skip8;
+    d.skip_stride = skip_stride;
+    d.fb_idx = fb_strength_idx;
+    d.nvfb = (p->mi_rows + 15) / 16;
+    d.nhfb = (p->mi_cols + 15) / 16;
+    d.coeff_shift = recon->bit_depth - 8;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d.recon.hbd)
+        SVTB_LAUNCH(cdef_apply_kernel<uint16_t>, d.nvfb * d.nhfb, NT, 0, st, d);
+    else
+        SVTB_LAUNCH(cdef_apply_kernel<uint8_t>, d.nvfb * d.nhfb, NT, 0, st, d);
+    SVTB_CUDA_TRY(cudaGetLastError());
+    return SVT_B200_OK;
+}
+
+int32_t svt_cdef_find_dir_cuda(const uint16_t *img, int32_t stride, int32_t *var, int32_t coeff_shift) {
+    ThreadCtx &c = tls();
+    c.reserve(256);
+    uint16_t *h = (uint16_t *)c.h;
+    for (int i = 0; i < 8; i++) memcpy(h + 8 * i, img + (size_t)i * stride, 16);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.d, c.h, 128, cudaMemcpyHostToDevice, c.stream));
+    SVTB_LAUNCH(find_dir_kernel, 1, 32, 0, c.stream, (const uint16_t *)c.d, 8, coeff_shift, (int *)(c.d + 128));
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h + 128, c.d + 128, 8, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_FATAL(cudaStreamSynchronize(c.stream));
+    int r[2];
+    memcpy(r, c.h + 128, 8);
+    *var = r[1];
+    return r[0];
+}
+
+void svt_cdef_filter_block_cuda(uint8_t *dst8, uint16_t *dst16, int32_t dstride, const uint16_t *in,
+                                int32_t pri_strength, int32_t sec_strength, int32_t dir, int32_t pri_damping,
+                                int32_t sec_damping, int32_t bsize, int32_t coeff_shift) {
+    const int rows = 4 << (bsize == 3 || bsize == 1), cols = 4 << (bsize == 3 || bsize == 2);
+    ThreadCtx &c = tls();
+    c.reserve(512);
+    uint16_t *h = (uint16_t *)c.h;
+    for (int i = 0; i < 12; i++)
+        for (int j = 0; j < 12; j++) h[i * 12 + j] = (i < rows + 4 && j < cols + 4) ? in[(i - 2) * 144 + (j - 2)] : 0;
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.d, c.h, 288, cudaMemcpyHostToDevice, c.stream));
+    SVTB_LAUNCH(filter_block_kernel, 1, 64, 0, c.stream, (const uint16_t *)c.d, pri_strength, sec_strength, dir,
+                pri_damping, sec_damping, rows, cols, coeff_shift, (uint16_t *)(c.d + 288));
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h + 288, c.d + 288, 128, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_FATAL(cudaStreamSynchronize(c.stream));
+    const uint16_t *o = (const uint16_t *)(c.h + 288);
+    for (int i = 0; i < rows; i++)
+        for (int j = 0; j < cols; j++) {
+            if (dst8)
+                dst8[i * dstride + j] = (uint8_t)o[i * 8 + j];
+            else
+                dst16[i * dstride + j] = o[i * 8 + j];
+        }
+}
+}

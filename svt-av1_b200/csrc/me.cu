@@ -140,6 +140,7 @@ struct MeDev {
     RawHme *raw; // [n_sb][2][4]
     int sbs_x, sbs_y;
     int slot_l[8], slot_r[8], n_slots;
+    int fp_smem_bytes; // dynamic shared memory given to fullpel_kernel
 };
 
 struct HmeState {
@@ -197,9 +198,10 @@ __device__ void derive_hme_state(const SvtB200MeParams &p, const RawHme *raw /*[
 
 constexpr int HME_SMEM_BYTES = 40 * 1024;
 
-// Kernel A: hierarchical ME, one CTA per (SB, reference). hme_level_0/1/2 (:852-1318) for the 2x2 search
+// Kernel A (generic fallback, any window size: regions searched one after another, windows chunked through
+// shared memory): hierarchical ME, one CTA per (SB, reference). hme_level_0/1/2 (:852-1318) for the 2x2 search
 // regions, then the region choice of set_final_seach_centre_sb.
-__global__ void __launch_bounds__(NT_SEARCH) hme_kernel(const __grid_constant__ MeDev d) {
+__global__ void __launch_bounds__(NT_SEARCH) hme_kernel_generic(const __grid_constant__ MeDev d) {
     extern __shared__ uint32_t smem[];
     __shared__ uint64_t s_red[NT_SEARCH / 32];
     const SvtB200MeParams &p = d.p;
@@ -334,6 +336,222 @@ __global__ void __launch_bounds__(NT_SEARCH) hme_kernel(const __grid_constant__ 
     }
 }
 
+
+// ---- Kernel A (fast path): all 2x2 search regions of an HME level are searched concurrently ----------------
+// Per level: every region's window + the (shared) source block are staged once, then each region ("job") is
+// searched by the whole CTA with `tpp` threads per candidate position (rows interleaved) so that small search
+// areas (8x3 at levels 1/2) still use all lanes; partial SADs are combined with xor-shuffles, the per-job
+// argmin with a shared-memory 64-bit atomicMin.  Requires all windows of a level to fit in HME_FAST_SMEM.
+constexpr int HME_FAST_SMEM = 64 * 1024;
+struct HmeJob {
+    const uint8_t *ref; // search position (0,0)
+    int xo, yo, saw, sah;
+    int woff, wpw; // window offset (words) in smem, words per row
+};
+
+template <int NT>
+__device__ void hme_level_search(const uint8_t *__restrict__ src, int src_stride, int raw_stride, int k, int bw, int bh,
+                                 const HmeJob *jobs, int njobs, uint32_t *smem, unsigned long long *s_key) {
+    const int tid = threadIdx.x;
+    const int spw = (bw + 3) >> 2;
+    uint32_t *s_src = smem;
+    const uint32_t tail_mask = (bw & 3) ? ((1u << (8 * (bw & 3))) - 1u) : 0xffffffffu;
+    { // stage the source block once for all jobs
+        uint8_t *sbp = reinterpret_cast<uint8_t *>(s_src);
+        for (int i = tid; i < bh * spw * 4; i += NT) {
+            int r = i / (spw * 4), c = i - r * (spw * 4);
+            sbp[i] = c < bw ? src[(size_t)r * src_stride + c] : 0;
+        }
+    }
+    const int span = (bh - 1) * k + 1;
+    for (int j = 0; j < njobs; j++) {
+        const HmeJob jb = jobs[j];
+        uint8_t *wb = reinterpret_cast<uint8_t *>(smem + jb.woff);
+        const int rb = jb.wpw * 4, wbytes = jb.saw - 1 + bw, rows = jb.sah - 1 + span;
+        for (int i = tid; i < rows * rb; i += NT) {
+            int r = i / rb, c = i - r * rb;
+            wb[i] = c < wbytes ? jb.ref[(size_t)r * raw_stride + c] : 0;
+        }
+    }
+    __syncthreads();
+    for (int j = 0; j < njobs; j++) {
+        const HmeJob jb = jobs[j];
+        const int P = jb.saw * jb.sah;
+        int tpp = 1;
+        while (tpp * 2 * P <= NT && tpp * 2 <= 32 && tpp * 2 <= bh) tpp *= 2;
+        const int sub = tid & (tpp - 1), gpt = NT / tpp;
+        const uint32_t *s_win = smem + jb.woff;
+        unsigned long long best = ~0ull;
+        for (int g0 = 0; g0 < P; g0 += gpt) { // uniform trip count: all lanes join the shuffles
+            const int g = g0 + tid / tpp;
+            const bool live = g < P;
+            uint32_t sad = 0;
+            int ys = 0, xs = 0;
+            if (live) {
+                ys = g / jb.saw;
+                xs = g - ys * jb.saw;
+                const int a = xs >> 2, sh = (xs & 3) * 8;
+                for (int r = sub; r < bh; r += tpp) {
+                    const uint32_t *wr = s_win + (ys + r * k) * jb.wpw + a;
+                    const uint32_t *sr = s_src + r * spw;
+                    uint32_t lo = wr[0];
+                    for (int w = 0; w < spw; w++) {
+                        const uint32_t hi = wr[w + 1];
+                        uint32_t v = __funnelshift_r(lo, hi, sh), sv = sr[w];
+                        if (w == spw - 1) {
+                            v &= tail_mask;
+                            sv &= tail_mask;
+                        }
+                        sad = sad4(sv, v, sad);
+                        lo = hi;
+                    }
+                }
+            }
+            for (int o = 1; o < tpp; o <<= 1) sad += __shfl_xor_sync(0xffffffffu, sad, o);
+            if (live && sub == 0) {
+                const unsigned long long key = ((unsigned long long)sad << 32) | (uint32_t)g;
+                best = key < best ? key : best;
+            }
+        }
+        best = warp_min_u64(best);
+        if ((tid & 31) == 0 && best != ~0ull) atomicMin(&s_key[j], best);
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT_SEARCH) hme_kernel(const __grid_constant__ MeDev d) {
+    extern __shared__ uint32_t smem[];
+    __shared__ HmeJob s_jobs[4];
+    __shared__ unsigned long long s_key[4];
+    __shared__ int s_cx[4], s_cy[4];
+    __shared__ unsigned long long s_csad[4];
+    const SvtB200MeParams &p = d.p;
+    const int tid = threadIdx.x;
+    const int sb = blockIdx.x, slot = blockIdx.y;
+    const int l = d.slot_l[slot], r = d.slot_r[slot];
+    RawHme *out = d.raw + (size_t)sb * 8 + l * 4 + r;
+    const bool active = (p.temporal_layer_index > 0 || l == 0) && p.enable_hme_flag &&
+                        (p.enable_hme_level0_flag || p.enable_hme_level1_flag || p.enable_hme_level2_flag);
+    if (!active) {
+        if (tid == 0) {
+            RawHme z = {0, 0, 0, 0};
+            *out = z;
+        }
+        return;
+    }
+    const int sx = sb % d.sbs_x, sy = sb / d.sbs_x;
+    const int ox = sx * 64, oy = sy * 64;
+    const int sbw = min(p.full.width - ox, 64), sbh = min(p.full.height - oy, 64);
+    const int sub = p.hme_search_method != 0;
+    const int mult = scaled_dist(p.ref_dist[l][r]) * 100;
+    const int nrw = p.number_hme_search_region_in_width, nrh = p.number_hme_search_region_in_height;
+    const int njobs = nrw * nrh;
+    const SvtB200MePlanes &rp = d.refs[l][r];
+    if (tid < 4) {
+        s_cx[tid] = s_cy[tid] = 0;
+        s_csad[tid] = 0;
+    }
+    for (int level = 0; level < 3; level++) {
+        const bool on = level == 0 ? p.enable_hme_level0_flag : level == 1 ? p.enable_hme_level1_flag : p.enable_hme_level2_flag;
+        if (!on) continue;
+        const SvtB200Plane &pl = level == 0 ? p.sixteenth : level == 1 ? p.quarter : p.full;
+        const int shf = 2 - level;
+        const int o_x = ox >> shf, o_y = oy >> shf, bw = sbw >> shf, bh0 = sbh >> shf;
+        const int bh = sub ? bh0 >> 1 : bh0, k = sub ? 2 : 1;
+        const uint8_t *srcp = level == 0 ? d.src.sixteenth : level == 1 ? d.src.quarter : d.src.full;
+        const uint8_t *refp = level == 0 ? rp.sixteenth : level == 1 ? rp.quarter : rp.full;
+        __syncthreads(); // previous level's results (s_cx/s_cy) are final; smem free
+        if (tid < njobs) { // job geometry: the window arithmetic of hme_level_0/1/2
+            const int rx = tid % nrw, ry = tid / nrw;
+            int saw, sah, xo, yo;
+            if (level == 0) {
+                saw = min((int)(int16_t)((((p.hme_level0_search_area_in_width_array[rx] * mult) / 100) + 15) & ~0x0F),
+                          (int)(int16_t)((p.hme_level0_max_search_area_in_width_array[rx] + 15) & ~0x0F));
+                sah = min((int)(int16_t)((p.hme_level0_search_area_in_height_array[ry] * mult) / 100),
+                          (int)(int16_t)p.hme_level0_max_search_area_in_height_array[ry]);
+                int xdist = 0, ydist = 0;
+                for (int i = 0; i < rx; i++)
+                    xdist += min((int)(int16_t)((p.hme_level0_search_area_in_width_array[i] * mult) / 100),
+                                 (int)(int16_t)p.hme_level0_max_search_area_in_width_array[i]);
+                for (int i = 0; i < ry; i++)
+                    ydist += min((int)(int16_t)((p.hme_level0_search_area_in_height_array[i] * mult) / 100),
+                                 (int)(int16_t)p.hme_level0_max_search_area_in_height_array[i]);
+                xo = -(int)(int16_t)(min((p.hme_level0_total_search_area_width * mult) / 100,
+                                         p.hme_level0_max_total_search_area_width) >> 1) + xdist;
+                yo = -(int)(int16_t)(min((p.hme_level0_total_search_area_height * mult) / 100,
+                                         p.hme_level0_max_total_search_area_height) >> 1) + ydist;
+                clamp_window(o_x, pl.origin_x - 1, pl.width, xo, saw);
+                saw = saw < 16 ? saw : saw & ~0x0F;
+                clamp_window(o_y, pl.origin_y - 1, pl.height, yo, sah);
+            } else {
+                const int aw = level == 1 ? p.hme_level1_search_area_in_width_array[rx] : p.hme_level2_search_area_in_width_array[rx];
+                const int ah = level == 1 ? p.hme_level1_search_area_in_height_array[ry] : p.hme_level2_search_area_in_height_array[ry];
+                saw = (int16_t)((aw + 7) & ~0x07);
+                sah = ah;
+                const int cx = level == 1 ? (s_cx[tid] >> 1) : s_cx[tid], cy = level == 1 ? (s_cy[tid] >> 1) : s_cy[tid];
+                xo = -(saw >> 1) + cx;
+                yo = -(sah >> 1) + cy;
+                clamp_window(o_x, level == 1 ? pl.origin_x - 1 : 63, pl.width, xo, saw);
+                saw = saw < 8 ? saw : saw & ~0x07;
+                clamp_window(o_y, level == 1 ? pl.origin_y - 1 : 63, pl.height, yo, sah);
+            }
+            HmeJob jb;
+            jb.ref = refp + (size_t)(pl.origin_y + o_y + yo) * pl.stride + pl.origin_x + o_x + xo;
+            jb.xo = xo;
+            jb.yo = yo;
+            jb.saw = saw;
+            jb.sah = sah;
+            jb.wpw = ((saw - 1 + bw + 3) >> 2) + 1;
+            jb.woff = 0;
+            s_jobs[tid] = jb;
+            s_key[tid] = ~0ull;
+        }
+        __syncthreads();
+        if (tid == 0) { // window offsets (words) after the source block
+            int off = ((bw + 3) >> 2) * bh;
+            for (int j = 0; j < njobs; j++) {
+                s_jobs[j].woff = off;
+                off += s_jobs[j].wpw * (s_jobs[j].sah - 1 + (bh - 1) * k + 1);
+            }
+        }
+        __syncthreads();
+        const uint8_t *s = srcp + (size_t)(pl.origin_y + o_y) * pl.stride + pl.origin_x + o_x;
+        hme_level_search<NT_SEARCH>(s, sub ? pl.stride * 2 : pl.stride, pl.stride, k, bw, bh, s_jobs, njobs, smem, s_key);
+        if (tid < njobs) {
+            const unsigned long long key = s_key[tid];
+            const uint32_t sad = (uint32_t)(key >> 32), idx = (uint32_t)key;
+            int kx = 0, ky = 0;
+            unsigned long long lsad = 0xffffff; // svt_sad_loop_kernel_c start value
+            if (key != ~0ull && sad < 0xffffffu) {
+                lsad = sad;
+                kx = idx % s_jobs[tid].saw;
+                ky = idx / s_jobs[tid].saw;
+            }
+            const int scale = level == 0 ? 4 : level == 1 ? 2 : 1;
+            s_csad[tid] = sub ? lsad * 2 : lsad;
+            s_cx[tid] = (int16_t)((kx + s_jobs[tid].xo) * scale);
+            s_cy[tid] = (int16_t)((ky + s_jobs[tid].yo) * scale);
+        }
+    }
+    __syncthreads();
+    if (tid == 0) { // set_final_seach_centre_sb: region (0,0) first, then strict `<` in (ry outer, rx inner) order
+        unsigned long long bs = s_csad[0];
+        int bx = s_cx[0], by = s_cy[0];
+        for (int j = 1; j < njobs; j++)
+            if (s_csad[j] < bs) {
+                bs = s_csad[j];
+                bx = s_cx[j];
+                by = s_cy[j];
+            }
+        RawHme w;
+        w.x = (int16_t)bx;
+        w.y = (int16_t)by;
+        w.valid = 1;
+        w.sad = bs;
+        *out = w;
+    }
+}
+
 // -----------------------------------------------------------------------------------------------------
 // Kernel B: integer full-pel search (integer_search_sb :1868-2139 + open_loop_me_fullpel_search_sblock)
 // -----------------------------------------------------------------------------------------------------
@@ -341,7 +559,8 @@ constexpr int FP_SMEM_BYTES = 96 * 1024;
 
 __global__ void __launch_bounds__(NT_SEARCH) fullpel_kernel(const __grid_constant__ MeDev d) {
     extern __shared__ uint32_t smem[];
-    __shared__ unsigned long long s_best[85];
+    __shared__ unsigned long long s_best[85]; // (sad << 32 | raster index) over the whole window
+    __shared__ unsigned int s_cbest[85]; // (sad << 11 | index inside the current chunk): one REDUX + one atomicMin
     __shared__ HmeState s_h;
     __shared__ uint32_t s_sad2[2];
     const SvtB200MeParams &p = d.p;
@@ -427,8 +646,9 @@ __global__ void __launch_bounds__(NT_SEARCH) fullpel_kernel(const __grid_constan
     const int span = sub ? 63 : 64;
     const int wbytes = saw + 63;
     const int wpw = ((wbytes + 3) >> 2) + 1;
-    const int budget_rows = (FP_SMEM_BYTES - nrows_src * 64) / (wpw * 4);
+    const int budget_rows = (d.fp_smem_bytes - nrows_src * 64) / (wpw * 4);
     int chunk = min(sah, budget_rows - span + 1);
+    chunk = min(chunk, 2048 / saw); // chunk-local position index must fit 11 bits
     if (chunk < 1) chunk = 1;
     const int nq = (saw + 3) >> 2; // position quads per search row
     const int nr8 = sub ? 4 : 8; // rows summed per 8x8
@@ -446,14 +666,16 @@ __global__ void __launch_bounds__(NT_SEARCH) fullpel_kernel(const __grid_constan
                 wb[i] = c < wbytes ? g[(ptrdiff_t)rr * fp.stride + c] : 0;
             }
         }
+        for (int i = tid; i < 85; i += NT_SEARCH) s_cbest[i] = 0xffffffffu;
         __syncthreads();
         const int nquads = cr * nq;
-        for (int qb = 0; qb < nquads; qb += NT_SEARCH) { // uniform trip count: every lane joins the reductions
+        for (int qb = 0; qb < nquads; qb += NT_SEARCH) {
+            if (qb + (tid & ~31) >= nquads) continue; // whole warp has no position: reductions are per warp
             const int qi = qb + tid;
             const bool live = qi < nquads;
             const int ysl = live ? qi / nq : 0;
             const int xs0 = live ? (qi - ysl * nq) * 4 : 0;
-            const uint32_t idx0 = (uint32_t)((y0 + ysl) * saw + xs0);
+            const uint32_t idx0 = (uint32_t)(ysl * saw + xs0); // index inside the chunk (< 2048)
             uint32_t ok[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) ok[j] = live && (xs0 + j < saw);
@@ -482,61 +704,54 @@ __global__ void __launch_bounds__(NT_SEARCH) fullpel_kernel(const __grid_constan
                             }
                         }
                     }
-                    uint32_t bs = 0xffffffffu, bi = 0xffffffffu; // thread-local first minimum of its 4 positions
+                    uint32_t bk = 0xffffffffu; // first minimum of this thread's 4 positions (packed key)
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const uint32_t v = sub ? s8[j] << 1 : s8[j];
                         s16[j] += v;
-                        if (ok[j] && v < bs) {
-                            bs = v;
-                            bi = idx0 + j;
-                        }
+                        bk = min(bk, ok[j] ? (v << 11) + idx0 + j : 0xffffffffu);
                     }
-                    const uint32_t m = __reduce_min_sync(0xffffffffu, bs);
-                    const uint32_t mi = __reduce_min_sync(0xffffffffu, bs == m ? bi : 0xffffffffu);
-                    if (lane == 0 && m != 0xffffffffu) atomicMin(&s_best[21 + 4 * b + q], ((unsigned long long)m << 32) | mi);
+                    const uint32_t m = __reduce_min_sync(0xffffffffu, bk);
+                    if (lane == 0 && m < s_cbest[21 + 4 * b + q]) atomicMin(&s_cbest[21 + 4 * b + q], m);
                 }
                 {
-                    uint32_t bs = 0xffffffffu, bi = 0xffffffffu;
+                    uint32_t bk = 0xffffffffu;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         acc32[j] += s16[j];
-                        if (ok[j] && s16[j] < bs) {
-                            bs = s16[j];
-                            bi = idx0 + j;
-                        }
+                        bk = min(bk, ok[j] ? (s16[j] << 11) + idx0 + j : 0xffffffffu);
                     }
-                    const uint32_t m = __reduce_min_sync(0xffffffffu, bs);
-                    const uint32_t mi = __reduce_min_sync(0xffffffffu, bs == m ? bi : 0xffffffffu);
-                    if (lane == 0 && m != 0xffffffffu) atomicMin(&s_best[5 + b], ((unsigned long long)m << 32) | mi);
+                    const uint32_t m = __reduce_min_sync(0xffffffffu, bk);
+                    if (lane == 0 && m < s_cbest[5 + b]) atomicMin(&s_cbest[5 + b], m);
                 }
                 if ((b & 3) == 3) {
-                    uint32_t bs = 0xffffffffu, bi = 0xffffffffu;
+                    uint32_t bk = 0xffffffffu;
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         acc64[j] += acc32[j];
-                        if (ok[j] && acc32[j] < bs) {
-                            bs = acc32[j];
-                            bi = idx0 + j;
-                        }
+                        bk = min(bk, ok[j] ? (acc32[j] << 11) + idx0 + j : 0xffffffffu);
                         acc32[j] = 0;
                     }
-                    const uint32_t m = __reduce_min_sync(0xffffffffu, bs);
-                    const uint32_t mi = __reduce_min_sync(0xffffffffu, bs == m ? bi : 0xffffffffu);
-                    if (lane == 0 && m != 0xffffffffu) atomicMin(&s_best[1 + (b >> 2)], ((unsigned long long)m << 32) | mi);
+                    const uint32_t m = __reduce_min_sync(0xffffffffu, bk);
+                    if (lane == 0 && m < s_cbest[1 + (b >> 2)]) atomicMin(&s_cbest[1 + (b >> 2)], m);
                 }
             }
             {
-                uint32_t bs = 0xffffffffu, bi = 0xffffffffu;
+                uint32_t bk = 0xffffffffu;
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (ok[j] && acc64[j] < bs) {
-                        bs = acc64[j];
-                        bi = idx0 + j;
-                    }
-                const uint32_t m = __reduce_min_sync(0xffffffffu, bs);
-                const uint32_t mi = __reduce_min_sync(0xffffffffu, bs == m ? bi : 0xffffffffu);
-                if (lane == 0 && m != 0xffffffffu) atomicMin(&s_best[0], ((unsigned long long)m << 32) | mi);
+                for (int j = 0; j < 4; j++) bk = min(bk, ok[j] ? (acc64[j] << 11) + idx0 + j : 0xffffffffu);
+                const uint32_t m = __reduce_min_sync(0xffffffffu, bk);
+                if (lane == 0 && m < s_cbest[0]) atomicMin(&s_cbest[0], m);
+            }
+        }
+        __syncthreads();
+        // merge the chunk into the running best: chunks advance in raster order, so strict `<` on the SAD keeps
+        // the first minimum
+        for (int i = tid; i < 85; i += NT_SEARCH) {
+            const unsigned int c = s_cbest[i];
+            if (c != 0xffffffffu) {
+                const unsigned long long sadc = c >> 11;
+                if (sadc < (s_best[i] >> 32)) s_best[i] = (sadc << 32) | (unsigned int)(y0 * saw + (c & 2047u));
             }
         }
     }
@@ -811,7 +1026,8 @@ __global__ void fill32_kernel(uint32_t *p, int n, uint32_t v) {
 static bool g_attr_done = false;
 static void set_attrs() {
     if (g_attr_done) return;
-    cudaFuncSetAttribute(hme_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HME_SMEM_BYTES);
+    cudaFuncSetAttribute(hme_kernel_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, HME_SMEM_BYTES);
+    cudaFuncSetAttribute(hme_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HME_FAST_SMEM);
     cudaFuncSetAttribute(fullpel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FP_SMEM_BYTES);
     cudaFuncSetAttribute(sad_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     g_attr_done = true;
@@ -875,8 +1091,54 @@ int svt_b200_me_picture(const SvtB200MeParams *p, const SvtB200MePlanes *src,
     SVTB_CUDA_TRY(cudaMemsetAsync(out->best_sad, 0, (size_t)n_sb * 8 * 85 * 4, st));
     SVTB_CUDA_TRY(cudaMemsetAsync(out->best_mv, 0, (size_t)n_sb * 8 * 85 * 4, st));
     SVTB_CUDA_TRY(cudaMemsetAsync(d.raw, 0, (size_t)n_sb * 8 * sizeof(RawHme), st));
-    SVTB_LAUNCH(hme_kernel, dim3(n_sb, n), NT_SEARCH, HME_SMEM_BYTES, st, d);
-    SVTB_LAUNCH(fullpel_kernel, dim3(n_sb, n), NT_SEARCH, FP_SMEM_BYTES, st, d);
+    // worst-case shared memory of one HME level on the fast path (4 windows + the source block)
+    size_t hme_need = 0;
+    {
+        const int k = p->hme_search_method ? 2 : 1;
+        int maxd = 1;
+        for (int l = 0; l < p->num_lists; l++)
+            for (int r = 0; r < p->num_refs[l]; r++) {
+                int dd = p->ref_dist[l][r];
+                dd = ((dd * 5) / 8) + ((dd % 8) ? 1 : 0);
+                if (dd > maxd) maxd = dd;
+            }
+        auto level_bytes = [&](int saw, int sah, int bw, int bh) {
+            const int bhh = k == 2 ? bh / 2 : bh;
+            const size_t win = (size_t)(((saw - 1 + bw + 3) / 4) + 1) * 4 * (sah - 1 + (bhh - 1) * k + 1);
+            return 4 * win + (size_t)((bw + 3) / 4) * 4 * bhh;
+        };
+        int w0 = p->hme_level0_search_area_in_width_array[0] * maxd, h0 = p->hme_level0_search_area_in_height_array[0] * maxd;
+        if (w0 > p->hme_level0_max_search_area_in_width_array[0]) w0 = p->hme_level0_max_search_area_in_width_array[0];
+        if (h0 > p->hme_level0_max_search_area_in_height_array[0]) h0 = p->hme_level0_max_search_area_in_height_array[0];
+        size_t a = level_bytes((w0 + 15) & ~15, h0, 16, 16);
+        size_t b = level_bytes((p->hme_level1_search_area_in_width_array[0] + 7) & ~7, p->hme_level1_search_area_in_height_array[0], 32, 32);
+        size_t c = level_bytes((p->hme_level2_search_area_in_width_array[0] + 7) & ~7, p->hme_level2_search_area_in_height_array[0], 64, 64);
+        hme_need = a > b ? a : b;
+        hme_need = hme_need > c ? hme_need : c;
+        hme_need += 256;
+    }
+    if (hme_need <= (size_t)HME_FAST_SMEM)
+        SVTB_LAUNCH(hme_kernel, dim3(n_sb, n), NT_SEARCH, hme_need, st, d);
+    else
+        SVTB_LAUNCH(hme_kernel_generic, dim3(n_sb, n), NT_SEARCH, HME_SMEM_BYTES, st, d);
+    {   // shared memory of the full-pel search: source rows + the largest window (whole if it fits)
+        int maxd = 1;
+        for (int l = 0; l < p->num_lists; l++)
+            for (int r = 0; r < p->num_refs[l]; r++) {
+                int dd = p->ref_dist[l][r];
+                dd = ((dd * 5) / 8) + ((dd % 8) ? 1 : 0);
+                if (dd > maxd) maxd = dd;
+            }
+        int saw = p->search_area_width * maxd, sah = p->search_area_height * maxd;
+        if (saw > p->max_me_search_width) saw = p->max_me_search_width;
+        if (sah > p->max_me_search_height) sah = p->max_me_search_height;
+        saw = (saw + 7) & ~7;
+        const int sub = p->me_search_method != 0;
+        size_t need = (size_t)(sub ? 32 : 64) * 64 + (size_t)(((saw + 63 + 3) / 4) + 1) * 4 * (sah - 1 + (sub ? 63 : 64)) + 64;
+        if (need > (size_t)FP_SMEM_BYTES) need = FP_SMEM_BYTES;
+        d.fp_smem_bytes = (int)need;
+    }
+    SVTB_LAUNCH(fullpel_kernel, dim3(n_sb, n), NT_SEARCH, d.fp_smem_bytes, st, d);
     SVTB_LAUNCH(finalize_kernel, n_sb, 96, 0, st, d);
     SVTB_CUDA_TRY(cudaGetLastError());
     return SVT_B200_OK;

@@ -64,6 +64,21 @@ class MeOutputs(C.Structure):
                 ("rc_me_distortion", C.c_void_p)]
 
 
+class Frame(C.Structure):
+    _fields_ = [("y", C.c_void_p), ("cb", C.c_void_p), ("cr", C.c_void_p), ("stride_y", C.c_int32),
+                ("stride_c", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("bit_depth", C.c_int32)]
+
+
+class CdefSearchParams(C.Structure):
+    _fields_ = [("mi_rows", C.c_int32), ("mi_cols", C.c_int32), ("pri_damping", C.c_int32),
+                ("n_strengths", C.c_int32), ("pri_strength", C.c_int32 * 64), ("sec_strength", C.c_int32 * 64)]
+
+
+class CdefApplyParams(C.Structure):
+    _fields_ = [("mi_rows", C.c_int32), ("mi_cols", C.c_int32), ("damping", C.c_int32),
+                ("y_strength", C.c_int32 * 8), ("uv_strength", C.c_int32 * 8)]
+
+
 def preset8_me_params(width, height, n_l0=1, n_l1=1, dist=((1, 2, 3, 4), (1, 2, 3, 4)), temporal_layer=1,
                       is_ref=1):
     """ME parameters of preset 8 (ENC_M8) at >=720p, 30 fps, as set_me_hme_params_oq /
@@ -139,6 +154,10 @@ def load():
     lib.svt_b200_me_picture.argtypes = [C.POINTER(MeParams), C.POINTER(MePlanes), C.POINTER(MePlanes),
                                         C.POINTER(MeOutputs), C.c_void_p, C.c_void_p]
     lib.svt_nxm_sad_kernel_cuda.restype = C.c_uint32
+    lib.svt_b200_cdef_search.argtypes = [C.POINTER(CdefSearchParams), C.POINTER(Frame), C.POINTER(Frame), C.c_void_p,
+                                         C.c_int32, C.c_void_p, C.c_void_p]
+    lib.svt_b200_cdef_apply.argtypes = [C.POINTER(CdefApplyParams), C.POINTER(Frame), C.POINTER(Frame), C.c_void_p,
+                                        C.c_int32, C.c_void_p, C.c_void_p]
     _lib = lib
     return lib
 

@@ -166,3 +166,75 @@ def assert_me_equal(a, b, params, what=""):
             np.testing.assert_array_equal(fa["best_mv"][:, l, r], fb["best_mv"][:, l, r], f"{what} best_mv {l},{r}")
     for k in ("me_mv", "me_cand", "total_cand", "rc"):
         np.testing.assert_array_equal(fa[k], fb[k], f"{what} {k}")
+
+
+# ------------------------------------------------------------------------------------------------------
+# 4:2:0 frames for the EncDec / in-loop filter tests
+# ------------------------------------------------------------------------------------------------------
+class Yuv:
+    """A 4:2:0 picture as three numpy planes (uint8 or uint16) with a little padding so strides != width."""
+
+    def __init__(self, w, h, bit_depth=8, pad=16):
+        self.w, self.h, self.bd = w, h, bit_depth
+        dt = np.uint16 if bit_depth > 8 else np.uint8
+        cw, ch = (w + 1) // 2, (h + 1) // 2
+        self.pad = pad
+        self.bufs = [np.zeros((h + 2 * pad, w + 2 * pad), dt), np.zeros((ch + 2 * pad, cw + 2 * pad), dt),
+                     np.zeros((ch + 2 * pad, cw + 2 * pad), dt)]
+
+    def plane(self, i):
+        p = self.pad
+        b = self.bufs[i]
+        return b[p:b.shape[0] - p, p:b.shape[1] - p]
+
+    def struct(self):
+        p = self.pad
+        ptrs = []
+        for b in self.bufs:
+            ptrs.append(b.ctypes.data + (p * b.shape[1] + p) * b.itemsize)
+        return sb.Frame(ptrs[0], ptrs[1], ptrs[2], self.bufs[0].shape[1], self.bufs[1].shape[1], self.w, self.h, self.bd)
+
+    def copy(self):
+        o = Yuv(self.w, self.h, self.bd, self.pad)
+        for a, b in zip(o.bufs, self.bufs):
+            a[...] = b
+        return o
+
+
+def synth_yuv(w, h, n=0, seed=1234, bit_depth=8, noise=6):
+    rng = np.random.default_rng(seed + 31 * n)
+    f = Yuv(w, h, bit_depth)
+    y = synth_luma(w, h, n, seed, noise).astype(np.int32)
+    cw, ch = (w + 1) // 2, (h + 1) // 2
+    yy, xx = np.mgrid[0:ch, 0:cw].astype(np.float64)
+    cb = np.clip(np.rint(128 + 50 * np.sin((xx + n) / 23.0) + rng.integers(-3, 4, (ch, cw))), 0, 255).astype(np.int32)
+    cr = np.clip(np.rint(128 + 50 * np.cos((yy - n) / 19.0) + rng.integers(-3, 4, (ch, cw))), 0, 255).astype(np.int32)
+    for i, p in enumerate((y, cb, cr)):
+        if bit_depth > 8:
+            p = (p << (bit_depth - 8)) + rng.integers(0, 1 << (bit_depth - 8), p.shape)
+        f.plane(i)[...] = p
+    return f
+
+
+def degrade(f, seed=5, amp=10):
+    """A 'reconstruction': the picture with coding-like noise + 8x8 blockiness."""
+    rng = np.random.default_rng(seed)
+    o = f.copy()
+    mx = (1 << f.bd) - 1
+    sc = 1 << (f.bd - 8)
+    for i in range(3):
+        p = o.plane(i).astype(np.int32)
+        bs = 8 if i == 0 else 4
+        blk = rng.integers(-amp, amp + 1, ((p.shape[0] + bs - 1) // bs, (p.shape[1] + bs - 1) // bs)) * sc
+        p = p + np.kron(blk, np.ones((bs, bs), np.int32))[: p.shape[0], : p.shape[1]] + rng.integers(-3 * sc, 3 * sc + 1, p.shape)
+        o.plane(i)[...] = np.clip(p, 0, mx)
+    return o
+
+
+def skip_map(mi_rows, mi_cols, seed=3, frac=0.3, all_skip_fb=True):
+    rng = np.random.default_rng(seed)
+    r8, c8 = (mi_rows + 1) // 2, (mi_cols + 1) // 2
+    m = (rng.random((r8, c8 + 3)) < frac).astype(np.uint8)
+    if all_skip_fb and r8 > 8 and c8 > 8:
+        m[0:8, 8:16] = 1  # one filter block entirely skipped
+    return m

@@ -39,3 +39,48 @@ def run_gpu_me(params, src, refs, stream=None):
         else:
             v[...] = host
     return out
+
+
+class DevYuv:
+    """Device copy of a common.Yuv (same padded layout)."""
+
+    def __init__(self, yuv):
+        self.yuv = yuv
+        self.t = [torch.from_numpy(b.view(np.int16) if b.dtype == np.uint16 else b).cuda() for b in yuv.bufs]
+
+    def struct(self):
+        y = self.yuv
+        p = y.pad
+        ptrs = [t.data_ptr() + (p * b.shape[1] + p) * b.itemsize for t, b in zip(self.t, y.bufs)]
+        return sb.Frame(ptrs[0], ptrs[1], ptrs[2], y.bufs[0].shape[1], y.bufs[1].shape[1], y.w, y.h, y.bd)
+
+    def download(self):
+        o = self.yuv.copy()
+        for b, t in zip(o.bufs, self.t):
+            h = t.cpu().numpy()
+            b[...] = h.view(np.uint16) if b.dtype == np.uint16 else h
+        return o
+
+
+def run_gpu_cdef_search(p, rec, src, skip):
+    lib = sb.load()
+    nfb = ((p.mi_rows + 15) // 16) * ((p.mi_cols + 15) // 16)
+    dr, ds = DevYuv(rec), DevYuv(src)
+    dskip = dev(skip)
+    mse = torch.zeros(2 * nfb * 64, dtype=torch.int64, device="cuda")
+    rs, ss = dr.struct(), ds.struct()
+    sb.check(lib.svt_b200_cdef_search(C.byref(p), C.byref(rs), C.byref(ss), C.c_void_p(dskip.data_ptr()),
+                                      skip.shape[1], C.c_void_p(mse.data_ptr()), None), lib)
+    torch.cuda.synchronize()
+    return mse.cpu().numpy().view(np.uint64).reshape(2, nfb, 64)
+
+
+def run_gpu_cdef_apply(p, rec, skip, idx):
+    lib = sb.load()
+    dr, do = DevYuv(rec), DevYuv(rec.copy())
+    dskip, didx = dev(skip), dev(idx)
+    rs, os_ = dr.struct(), do.struct()
+    sb.check(lib.svt_b200_cdef_apply(C.byref(p), C.byref(rs), C.byref(os_), C.c_void_p(dskip.data_ptr()), skip.shape[1],
+                                     C.c_void_p(didx.data_ptr()), None), lib)
+    torch.cuda.synchronize()
+    return do.download()
