@@ -50,6 +50,27 @@ ORC_API void orc_cdef_search(const SvtB200CdefSearchParams *p, const SvtB200Fram
 ORC_API void orc_cdef_apply(const SvtB200CdefApplyParams *p, const SvtB200Frame *recon, const SvtB200Frame *out,
                             const uint8_t *skip8, int32_t skip_stride, const int8_t *fb_strength_idx);
 ORC_API int orc_cdef_strength_table(int pick_method, SvtB200CdefSearchParams *p);
+/* ---- txfm_oracle.c ---- */
+ORC_API const int32_t *orc_cospi_table(int bit);
+ORC_API const int32_t *orc_sinpi_table(int bit);
+ORC_API void orc_fdct(int32_t *x, int stride, int n, int cos_bit);
+ORC_API void orc_idct(int32_t *x, int stride, int n, int cos_bit, int clamp_bit);
+ORC_API void orc_fadst(int32_t *x, int stride, int n, int cos_bit);
+ORC_API void orc_iadst(int32_t *x, int stride, int n, int cos_bit, int clamp_bit);
+ORC_API void orc_fidentity(int32_t *x, int stride, int n);
+ORC_API void orc_fwd_txfm2d(const int16_t *input, int32_t *output, uint32_t stride, int tx_type, int tx_size, int bit_depth);
+ORC_API uint64_t orc_handle_transform64(int32_t *output, int tx_size);
+ORC_API void orc_inv_txfm2d_add(const int32_t *input, const uint16_t *pred, int32_t stride_r, uint16_t *recon,
+                                int32_t stride_w, int tx_type, int tx_size, int bd);
+ORC_API void orc_residual(const void *src, uint32_t src_stride, const void *pred, uint32_t pred_stride, int16_t *res,
+                          uint32_t res_stride, uint32_t w, uint32_t h, int hbd);
+ORC_API void orc_quantize_b(const int32_t *coeff, intptr_t n, const int16_t *zbin, const int16_t *round,
+                            const int16_t *quant, const int16_t *quant_shift, int32_t *qcoeff, int32_t *dqcoeff,
+                            const int16_t *dequant, uint16_t *eob_ptr, const int16_t *scan, const uint8_t *qm,
+                            const uint8_t *iqm, int log_scale, int hbd);
+ORC_API void orc_quantize_fp(const int32_t *coeff, intptr_t n, const int16_t *round, const int16_t *quant,
+                             int32_t *qcoeff, int32_t *dqcoeff, const int16_t *dequant, uint16_t *eob_ptr,
+                             const int16_t *scan, int log_scale, int hbd);
 #ifdef __cplusplus
 }
 #endif
