@@ -274,6 +274,122 @@ SVT_B200_API int svt_b200_cdef_apply(const SvtB200CdefApplyParams *p, const SvtB
                                      const SvtB200Frame *out, const uint8_t *skip8, int32_t skip_stride,
                                      const int8_t *fb_strength_idx, void *stream);
 
+/* =============================================================================================== */
+/* Residual / forward + inverse transform / quantisation                                           */
+/* =============================================================================================== */
+
+/* replaces svt_residual_kernel8bit / 16bit (common_dsp_rtcd.h:169,180; EbPictureOperators.c:130,106) */
+SVT_B200_API void svt_residual_kernel8bit_cuda(uint8_t *input, uint32_t input_stride, uint8_t *pred,
+                                               uint32_t pred_stride, int16_t *residual,
+                                               uint32_t residual_stride, uint32_t area_width,
+                                               uint32_t area_height);
+SVT_B200_API void svt_residual_kernel16bit_cuda(uint16_t *input, uint32_t input_stride, uint16_t *pred,
+                                                uint32_t pred_stride, int16_t *residual,
+                                                uint32_t residual_stride, uint32_t area_width,
+                                                uint32_t area_height);
+
+/* replace svt_av1_fwd_txfm2d_{WxH} (aom_dsp_rtcd.h:105-216; C impl EbTransforms.c:2301-3053).
+ * tx_type is the reference's TxType enum value (DCT_DCT=0 ... H_FLIPADST=15). */
+#define SVT_B200_DECL_FWD(W, H)                                                                      \
+    SVT_B200_API void svt_av1_fwd_txfm2d_##W##x##H##_cuda(int16_t *input, int32_t *output,           \
+                                                          uint32_t input_stride, int32_t tx_type,    \
+                                                          uint8_t bit_depth);
+SVT_B200_DECL_FWD(4, 4) SVT_B200_DECL_FWD(8, 8) SVT_B200_DECL_FWD(16, 16) SVT_B200_DECL_FWD(32, 32)
+SVT_B200_DECL_FWD(64, 64) SVT_B200_DECL_FWD(4, 8) SVT_B200_DECL_FWD(8, 4) SVT_B200_DECL_FWD(8, 16)
+SVT_B200_DECL_FWD(16, 8) SVT_B200_DECL_FWD(16, 32) SVT_B200_DECL_FWD(32, 16) SVT_B200_DECL_FWD(32, 64)
+SVT_B200_DECL_FWD(64, 32) SVT_B200_DECL_FWD(4, 16) SVT_B200_DECL_FWD(16, 4) SVT_B200_DECL_FWD(8, 32)
+SVT_B200_DECL_FWD(32, 8) SVT_B200_DECL_FWD(16, 64) SVT_B200_DECL_FWD(64, 16)
+
+/* replace svt_handle_transform64x64 / 64x32 / 32x64 / 64x16 / 16x64 (aom_dsp_rtcd.h:222-245;
+ * EbTransforms.c:2763-2931): in place on the w x h coefficient array, returns the dropped energy */
+SVT_B200_API uint64_t svt_handle_transform64x64_cuda(int32_t *output);
+SVT_B200_API uint64_t svt_handle_transform64x32_cuda(int32_t *output);
+SVT_B200_API uint64_t svt_handle_transform32x64_cuda(int32_t *output);
+SVT_B200_API uint64_t svt_handle_transform64x16_cuda(int32_t *output);
+SVT_B200_API uint64_t svt_handle_transform16x64_cuda(int32_t *output);
+SVT_B200_API uint64_t svt_b200_handle_transform64(int32_t *output, int tx_size);
+
+/* replace svt_av1_inv_txfm2d_add_{WxH} (common_dsp_rtcd.h:105-156; EbInvTransforms.c:2455-2752) */
+#define SVT_B200_DECL_INV_SQ(W)                                                                        \
+    SVT_B200_API void svt_av1_inv_txfm2d_add_##W##x##W##_cuda(                                         \
+        const int32_t *input, uint16_t *output_r, int32_t stride_r, uint16_t *output_w, int32_t stride_w, \
+        int32_t tx_type, int32_t bd);
+#define SVT_B200_DECL_INV_RECT(W, H)                                                                   \
+    SVT_B200_API void svt_av1_inv_txfm2d_add_##W##x##H##_cuda(                                         \
+        const int32_t *input, uint16_t *output_r, int32_t stride_r, uint16_t *output_w, int32_t stride_w, \
+        int32_t tx_type, int32_t tx_size, int32_t eob, int32_t bd);
+#define SVT_B200_DECL_INV_RECT_NOEOB(W, H)                                                             \
+    SVT_B200_API void svt_av1_inv_txfm2d_add_##W##x##H##_cuda(                                         \
+        const int32_t *input, uint16_t *output_r, int32_t stride_r, uint16_t *output_w, int32_t stride_w, \
+        int32_t tx_type, int32_t tx_size, int32_t bd);
+SVT_B200_DECL_INV_SQ(4) SVT_B200_DECL_INV_SQ(8) SVT_B200_DECL_INV_SQ(16) SVT_B200_DECL_INV_SQ(32)
+SVT_B200_DECL_INV_SQ(64) SVT_B200_DECL_INV_RECT_NOEOB(4, 8) SVT_B200_DECL_INV_RECT_NOEOB(8, 4)
+SVT_B200_DECL_INV_RECT(8, 16) SVT_B200_DECL_INV_RECT(16, 8) SVT_B200_DECL_INV_RECT(16, 32)
+SVT_B200_DECL_INV_RECT(32, 16) SVT_B200_DECL_INV_RECT(32, 64) SVT_B200_DECL_INV_RECT(64, 32)
+SVT_B200_DECL_INV_RECT_NOEOB(4, 16) SVT_B200_DECL_INV_RECT_NOEOB(16, 4) SVT_B200_DECL_INV_RECT(8, 32)
+SVT_B200_DECL_INV_RECT(32, 8) SVT_B200_DECL_INV_RECT(16, 64) SVT_B200_DECL_INV_RECT(64, 16)
+
+/* replace svt_aom_quantize_b / svt_aom_highbd_quantize_b (aom_dsp_rtcd.h:252,254; EbFullLoop.c:37,171) and
+ * svt_av1_quantize_fp[_32x32/_64x64] / svt_av1_highbd_quantize_fp (aom_dsp_rtcd.h:256-262; :314-600).
+ * QmVal is uint8_t in the reference. */
+SVT_B200_API void svt_aom_quantize_b_cuda(const int32_t *coeff_ptr, intptr_t n_coeffs, const int16_t *zbin_ptr,
+                                          const int16_t *round_ptr, const int16_t *quant_ptr,
+                                          const int16_t *quant_shift_ptr, int32_t *qcoeff_ptr,
+                                          int32_t *dqcoeff_ptr, const int16_t *dequant_ptr, uint16_t *eob_ptr,
+                                          const int16_t *scan, const int16_t *iscan, const uint8_t *qm_ptr,
+                                          const uint8_t *iqm_ptr, const int32_t log_scale);
+SVT_B200_API void svt_aom_highbd_quantize_b_cuda(const int32_t *coeff_ptr, intptr_t n_coeffs,
+                                                 const int16_t *zbin_ptr, const int16_t *round_ptr,
+                                                 const int16_t *quant_ptr, const int16_t *quant_shift_ptr,
+                                                 int32_t *qcoeff_ptr, int32_t *dqcoeff_ptr,
+                                                 const int16_t *dequant_ptr, uint16_t *eob_ptr,
+                                                 const int16_t *scan, const int16_t *iscan,
+                                                 const uint8_t *qm_ptr, const uint8_t *iqm_ptr,
+                                                 const int32_t log_scale);
+#define SVT_B200_DECL_QFP(NAME)                                                                          \
+    SVT_B200_API void NAME(const int32_t *coeff_ptr, intptr_t n_coeffs, const int16_t *zbin_ptr,         \
+                           const int16_t *round_ptr, const int16_t *quant_ptr,                           \
+                           const int16_t *quant_shift_ptr, int32_t *qcoeff_ptr, int32_t *dqcoeff_ptr,    \
+                           const int16_t *dequant_ptr, uint16_t *eob_ptr, const int16_t *scan,           \
+                           const int16_t *iscan);
+SVT_B200_DECL_QFP(svt_av1_quantize_fp_cuda)
+SVT_B200_DECL_QFP(svt_av1_quantize_fp_32x32_cuda)
+SVT_B200_DECL_QFP(svt_av1_quantize_fp_64x64_cuda)
+SVT_B200_API void svt_av1_highbd_quantize_fp_cuda(const int32_t *coeff_ptr, intptr_t n_coeffs,
+                                                  const int16_t *zbin_ptr, const int16_t *round_ptr,
+                                                  const int16_t *quant_ptr, const int16_t *quant_shift_ptr,
+                                                  int32_t *qcoeff_ptr, int32_t *dqcoeff_ptr,
+                                                  const int16_t *dequant_ptr, uint16_t *eob_ptr,
+                                                  const int16_t *scan, const int16_t *iscan, int16_t log_scale);
+
+/* Scan order of a transform (get_scan / av1_scan_orders[tx_size][tx_type], Common/Codec/EbCoefficients.h):
+ * writes the positions in scan order (64-wide sizes scan as their 32-wide packing); returns the count. */
+SVT_B200_API int svt_b200_get_scan(int tx_size, int tx_type, int16_t *scan_out);
+
+/* Fused per-transform-unit encode, the body of av1_encode_loop (Encoder/Codec/EbCodingLoop.c:290-...):
+ *   residual = src - pred  ->  forward transform  ->  quantise + dequantise  ->  inverse transform  ->
+ *   recon = clip(pred + residual').   One launch handles n_tus units of ONE transform size. */
+typedef struct SvtB200Tu { /* one transform unit */
+    int32_t x, y; /* top-left sample inside its plane */
+    int32_t plane; /* 0 Y, 1 Cb, 2 Cr */
+    int32_t tx_type; /* TxType enum value */
+} SvtB200Tu;
+typedef struct SvtB200QuantPlane { /* dc/ac pairs of Quants/Dequants (EbPictureControlSet.h:98-136) at this qindex */
+    int16_t zbin[2], round[2], quant[2], quant_shift[2], dequant[2];
+    int16_t round_fp[2], quant_fp[2];
+} SvtB200QuantPlane;
+typedef struct SvtB200EncodeParams {
+    int32_t tx_size; /* TxSize enum value (TX_4X4=0 ... TX_64X16=18) */
+    int32_t use_fp; /* 0: svt_aom_[highbd_]quantize_b, 1: svt_av1_[highbd_]quantize_fp (EbFullLoop.c:1527) */
+    SvtB200QuantPlane q[3];
+} SvtB200EncodeParams;
+/* tus: device array; qcoeff: device int32 [n_tus][min(w,32)*min(h,32)]; eob: device uint16 [n_tus];
+ * scratch: >= 8 KB of device memory. pred and recon may be the same frame. */
+SVT_B200_API int svt_b200_encode_tus(const SvtB200EncodeParams *p, const SvtB200Frame *src,
+                                     const SvtB200Frame *pred, const SvtB200Frame *recon,
+                                     const SvtB200Tu *tus, int32_t n_tus, int32_t *qcoeff, uint16_t *eob,
+                                     void *scratch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -400,3 +400,16 @@ REFH_API int refh_cdef_apply(int mi_rows, int mi_cols, int damping, const int32_
     filt_ctx_free(c);
     return 0;
 }
+
+/* ====================================================================================================
+ * scan orders: av1_scan_orders[tx_size][tx_type] is a static table in a header (Common/Codec/EbCoefficients.h:2563)
+ * ================================================================================================== */
+#include "EbCoefficients.h"
+REFH_API int refh_get_scan(int tx_size, int tx_type, int16_t *out) {
+    const ScanOrder *so = &av1_scan_orders[tx_size][tx_type];
+    int w = tx_size_wide[tx_size], h = tx_size_high[tx_size];
+    if (w > 32) w = 32;
+    if (h > 32) h = 32;
+    memcpy(out, so->scan, sizeof(int16_t) * w * h);
+    return w * h;
+}

@@ -1,0 +1,361 @@
+// txfm.cuh — device-side integer transforms of AV1 as SVT-AV1 v0.8.6 computes them (bit-exact).
+//
+// Replaces the hand-unrolled stage lists of Source/Lib/Encoder/Codec/EbTransforms.c:75-2271 and
+// Source/Lib/Common/Codec/EbInvTransforms.c:75-2358.  The butterfly networks are generated from their
+// recursive structure (DCT-n = butterfly ; DCT-n/2 ; ODD(n/2) ; bit reversal) instead of being spelled out;
+// every layer acts on disjoint pairs so the whole 1-D transform runs IN PLACE on a strided array in shared
+// memory, one thread per row/column of a transform block.  Only half_btf() rounds; additions are exact, so
+// evaluation order of independent sub-networks cannot change a bit.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace svtb200 {
+
+// per-translation-unit copies (no relocatable device code): every .cu that includes this header calls
+// txfm_tables_init() before launching a kernel that uses them
+static __constant__ int32_t c_cospi[4][64]; // cos_bit 10..13
+static __constant__ int32_t c_sinpi[4][5];
+
+// host: fills the constant tables on the current device (idempotent per device)
+static void txfm_tables_init() {
+    static std::mutex mu;
+    static bool done[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    if (dev < 64 && done[dev]) return;
+    int32_t cospi[4][64];
+    // eb_av1_cospi_arr_data: round(cos(i*pi/128) * 2^bit).  eb_av1_sinpi_arr_data is hand-adjusted in the reference
+    // (sinpi[1] + sinpi[2] == sinpi[4]) and therefore kept as data.
+    static const int32_t sinpi[4][5] = {{0, 330, 621, 836, 951}, {0, 660, 1241, 1672, 1901},
+                                        {0, 1321, 2482, 3344, 3803}, {0, 2642, 4964, 6689, 7606}};
+    for (int b = 10; b <= 13; b++)
+        for (int i = 0; i < 64; i++) cospi[b - 10][i] = (int32_t)floor(cos(M_PI * i / 128.0) * (double)(1 << b) + 0.5);
+    SVTB_CUDA_FATAL(cudaMemcpyToSymbol(c_cospi, cospi, sizeof(cospi)));
+    SVTB_CUDA_FATAL(cudaMemcpyToSymbol(c_sinpi, sinpi, sizeof(sinpi)));
+    if (dev < 64) done[dev] = true;
+}
+
+// Common/Codec/EbInvTransforms.h:285-312: 32-bit wrapping products, 64-bit sum, rounding shift
+__device__ __forceinline__ int32_t half_btf(int32_t w0, int32_t in0, int32_t w1, int32_t in1, int bit) {
+    const long long r = (long long)(int32_t)((uint32_t)w0 * (uint32_t)in0) + (long long)(int32_t)((uint32_t)w1 * (uint32_t)in1);
+    return (int32_t)((r + (1ll << (bit - 1))) >> bit);
+}
+__device__ __forceinline__ int32_t round_shift64(long long v, int bit) { return (int32_t)((v + (1ll << (bit - 1))) >> bit); }
+__device__ __forceinline__ int32_t wadd(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+__device__ __forceinline__ int32_t wsub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
+__device__ __forceinline__ int32_t clampv(int32_t v, int bit) { // clamp_value, EbInvTransforms.c:67
+    if (bit <= 0) return v;
+    const int32_t mx = (int32_t)((1ll << (bit - 1)) - 1), mn = (int32_t)(-(1ll << (bit - 1)));
+    return v < mn ? mn : (v > mx ? mx : v);
+}
+__device__ __forceinline__ int brev(int v, int bits) { return (int)(__brev((unsigned)v) >> (32 - bits)); }
+__device__ __forceinline__ int ilog2(int n) { return 31 - __clz(n); }
+
+#define TX(i) x[(i) * s]
+
+__device__ inline void odd_butterflies(int32_t *x, int s, int m, int S, int clamp_bit) {
+    for (int base = 0; base < m; base += S) {
+        const bool mirrored = (base / S) & 1;
+        for (int i = 0; i < S / 2; i++) {
+            const int lo = base + i, hi = base + S - 1 - i;
+            const int32_t a = TX(lo), b = TX(hi);
+            const int32_t sum = clampv(wadd(a, b), clamp_bit), dif = clampv(mirrored ? wsub(b, a) : wsub(a, b), clamp_bit);
+            TX(mirrored ? hi : lo) = sum;
+            TX(mirrored ? lo : hi) = dif;
+        }
+    }
+}
+__device__ inline void odd_rotations(int32_t *x, int s, int m, int j, const int32_t *c, int bit) {
+    const int G = m >> j;
+    for (int t = 0; t < m / 2; t++) {
+        const int u = t & (G - 1), p = m - 1 - t;
+        if (u < G / 4 || u >= 3 * G / 4) continue;
+        const int k = (32 >> j) * brev((1 << j) + t / G, j + 1);
+        const int32_t a = TX(t), b = TX(p);
+        if (u < G / 2) {
+            TX(t) = half_btf(-c[k], a, c[64 - k], b, bit);
+            TX(p) = half_btf(c[k], b, c[64 - k], a, bit);
+        } else {
+            TX(t) = half_btf(-c[64 - k], a, -c[k], b, bit);
+            TX(p) = half_btf(c[64 - k], b, -c[k], a, bit);
+        }
+    }
+}
+__device__ inline void odd_final_rotation(int32_t *x, int s, int m, const int32_t *c, int bit, bool inverse) {
+    const int n = 2 * m, L = ilog2(n);
+    for (int t = 0; t < m / 2; t++) {
+        const int p = m - 1 - t, k = (64 / n) * brev(m + t, L);
+        const int32_t a = TX(t), b = TX(p);
+        if (!inverse) {
+            TX(t) = half_btf(c[64 - k], a, c[k], b, bit);
+            TX(p) = half_btf(c[64 - k], b, -c[k], a, bit);
+        } else {
+            TX(t) = half_btf(c[64 - k], a, -c[k], b, bit);
+            TX(p) = half_btf(c[k], a, c[64 - k], b, bit);
+        }
+    }
+}
+__device__ inline void bit_reverse_permute(int32_t *x, int s, int n) {
+    const int L = ilog2(n);
+    for (int j = 0; j < n; j++) {
+        const int r = brev(j, L);
+        if (r > j) {
+            const int32_t t = TX(j);
+            TX(j) = TX(r);
+            TX(r) = t;
+        }
+    }
+}
+__device__ inline void fdct(int32_t *x, int s, int n_total, int bit) {
+    const int32_t *c = c_cospi[bit - 10];
+    for (int n = n_total; n >= 4; n >>= 1) {
+        const int m = n / 2, L = ilog2(n);
+        for (int i = 0; i < m; i++) {
+            const int32_t a = TX(i), b = TX(n - 1 - i);
+            TX(i) = wadd(a, b);
+            TX(n - 1 - i) = wsub(a, b);
+        }
+        int32_t *y = x + m * s;
+        for (int j = 0; j <= L - 3; j++) {
+            odd_rotations(y, s, m, j, c, bit);
+            odd_butterflies(y, s, m, m >> (j + 1), 0);
+        }
+        odd_final_rotation(y, s, m, c, bit, false);
+    }
+    const int32_t a = TX(0), b = TX(1);
+    TX(0) = half_btf(c[32], a, c[32], b, bit);
+    TX(1) = half_btf(-c[32], b, c[32], a, bit);
+    bit_reverse_permute(x, s, n_total);
+}
+__device__ inline void idct(int32_t *x, int s, int n_total, int bit, int clamp_bit) {
+    const int32_t *c = c_cospi[bit - 10];
+    bit_reverse_permute(x, s, n_total);
+    {
+        const int32_t a = TX(0), b = TX(1);
+        TX(0) = half_btf(c[32], a, c[32], b, bit);
+        TX(1) = half_btf(c[32], a, -c[32], b, bit);
+    }
+    for (int n = 4; n <= n_total; n <<= 1) {
+        const int m = n / 2, L = ilog2(n);
+        int32_t *y = x + m * s;
+        odd_final_rotation(y, s, m, c, bit, true);
+        for (int j = L - 3; j >= 0; j--) {
+            odd_butterflies(y, s, m, m >> (j + 1), clamp_bit);
+            odd_rotations(y, s, m, j, c, bit);
+        }
+        for (int i = 0; i < m; i++) {
+            const int32_t a = TX(i), b = TX(n - 1 - i);
+            TX(i) = clampv(wadd(a, b), clamp_bit);
+            TX(n - 1 - i) = clampv(wsub(a, b), clamp_bit);
+        }
+    }
+}
+
+// ---- ADST (EbTransforms.c:1445-1826, EbInvTransforms.c:707-1105) ----
+__device__ inline void fadst4(int32_t *x, int s, int bit) {
+    const int32_t *sp = c_sinpi[bit - 10];
+    const int32_t x0 = TX(0), x1 = TX(1), x2 = TX(2), x3 = TX(3);
+    if (!(x0 | x1 | x2 | x3)) return; // all zero stays zero
+    auto M = [](int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); };
+    const int32_t s0 = M(sp[1], x0), s1 = M(sp[4], x0), s2 = M(sp[2], x1), s3 = M(sp[1], x1), s4 = M(sp[3], x2),
+                  s5 = M(sp[4], x3), s6 = M(sp[2], x3), s7 = wsub(wadd(x0, x1), x3);
+    const int32_t y0 = wadd(wadd(s0, s2), s5), y1 = M(sp[3], s7), y2 = wadd(wsub(s1, s3), s6), y3 = s4;
+    TX(0) = round_shift64((long long)wadd(y0, y3), bit);
+    TX(1) = round_shift64((long long)y1, bit);
+    TX(2) = round_shift64((long long)wsub(y2, y3), bit);
+    TX(3) = round_shift64((long long)wadd(wsub(y2, y0), y3), bit);
+}
+__device__ inline void iadst4(int32_t *x, int s, int bit) {
+    const int32_t *sp = c_sinpi[bit - 10];
+    const int32_t x0 = TX(0), x1 = TX(1), x2 = TX(2), x3 = TX(3);
+    if (!(x0 | x1 | x2 | x3)) return;
+    auto M = [](int32_t a, int32_t b) { return (int32_t)((uint32_t)a * (uint32_t)b); };
+    int32_t s0 = M(sp[1], x0), s1 = M(sp[2], x0), s2 = M(sp[3], x1), s3 = M(sp[4], x2), s4 = M(sp[1], x2),
+            s5 = M(sp[2], x3), s6 = M(sp[4], x3), s7 = wadd(wsub(x0, x2), x3);
+    s0 = wadd(wadd(s0, s3), s5);
+    s1 = wsub(wsub(s1, s4), s6);
+    s3 = s2;
+    s2 = M(sp[3], s7);
+    TX(0) = round_shift64((long long)wadd(s0, s3), bit);
+    TX(1) = round_shift64((long long)wadd(s1, s3), bit);
+    TX(2) = round_shift64((long long)s2, bit);
+    TX(3) = round_shift64((long long)wsub(wadd(s0, s1), s3), bit);
+}
+
+__constant__ static int8_t c_adst8_in[8] = {0, -7, -3, 4, -1, 6, 2, -5};
+__constant__ static int8_t c_adst8_out[8] = {1, 6, 3, 4, 5, 2, 7, 0};
+__constant__ static int8_t c_adst16_in[16] = {0, -15, -7, 8, -3, 12, 4, -11, -1, 14, 6, -9, 2, -13, -5, 10};
+__constant__ static int8_t c_adst16_out[16] = {1, 14, 3, 12, 5, 10, 7, 8, 9, 6, 11, 4, 13, 2, 15, 0};
+
+__device__ inline void adst_rotations(int32_t *v, int n, int h, const int32_t *c, int bit) {
+    const int np = h / 2;
+    for (int g = 0; g < n; g += 2 * h)
+        for (int i = 0; i < np; i++) {
+            const int a0 = g + h + 2 * i, a1 = a0 + 1;
+            const int32_t a = v[a0], b = v[a1];
+            if (h == 2) {
+                v[a0] = half_btf(c[32], a, c[32], b, bit);
+                v[a1] = half_btf(c[32], a, -c[32], b, bit);
+                continue;
+            }
+            const int half = np / 2, q = i % half;
+            const int k = (64 / h) * (h >= 8 ? 4 * q + 1 : 1);
+            if (i < half) {
+                v[a0] = half_btf(c[k], a, c[64 - k], b, bit);
+                v[a1] = half_btf(c[64 - k], a, -c[k], b, bit);
+            } else {
+                v[a0] = half_btf(-c[64 - k], a, c[k], b, bit);
+                v[a1] = half_btf(c[k], a, c[64 - k], b, bit);
+            }
+        }
+}
+__device__ inline void adst_addsub(int32_t *v, int n, int h, int clamp_bit) {
+    for (int g = 0; g < n; g += 2 * h)
+        for (int i = 0; i < h; i++) {
+            const int32_t a = v[g + i], b = v[g + h + i];
+            v[g + i] = clampv(wadd(a, b), clamp_bit);
+            v[g + h + i] = clampv(wsub(a, b), clamp_bit);
+        }
+}
+__device__ inline void adst_final(int32_t *v, int n, const int32_t *c, int bit) {
+    for (int i = 0; i < n / 2; i++) {
+        const int k = (32 + 128 * i) / n;
+        const int32_t a = v[2 * i], b = v[2 * i + 1];
+        v[2 * i] = half_btf(c[k], a, c[64 - k], b, bit);
+        v[2 * i + 1] = half_btf(c[64 - k], a, -c[k], b, bit);
+    }
+}
+__device__ inline void fadst(int32_t *x, int s, int n, int bit) {
+    if (n == 4) {
+        fadst4(x, s, bit);
+        return;
+    }
+    const int32_t *c = c_cospi[bit - 10];
+    const int8_t *pin = n == 8 ? c_adst8_in : c_adst16_in, *pout = n == 8 ? c_adst8_out : c_adst16_out;
+    int32_t v[16];
+    for (int i = 0; i < n; i++) {
+        const int p = pin[i];
+        v[i] = p < 0 ? wsub(0, TX(-p)) : TX(p);
+    }
+    for (int h = 2; h < n; h <<= 1) {
+        adst_rotations(v, n, h, c, bit);
+        adst_addsub(v, n, h, 0);
+    }
+    adst_final(v, n, c, bit);
+    for (int i = 0; i < n; i++) TX(i) = v[pout[i]];
+}
+__device__ inline void iadst(int32_t *x, int s, int n, int bit, int clamp_bit) {
+    if (n == 4) {
+        iadst4(x, s, bit);
+        return;
+    }
+    const int32_t *c = c_cospi[bit - 10];
+    const int8_t *pin = n == 8 ? c_adst8_in : c_adst16_in, *pout = n == 8 ? c_adst8_out : c_adst16_out;
+    int32_t v[16];
+    for (int i = 0; i < n; i++) v[pout[i]] = TX(i);
+    adst_final(v, n, c, bit);
+    for (int h = n / 2; h >= 2; h >>= 1) {
+        adst_addsub(v, n, h, clamp_bit);
+        adst_rotations(v, n, h, c, bit);
+    }
+    for (int i = 0; i < n; i++) {
+        const int p = pin[i];
+        TX(p < 0 ? -p : p) = p < 0 ? wsub(0, v[i]) : v[i];
+    }
+}
+// identity (forward and inverse scale identically: EbTransforms.c:2239-2278, EbInvTransforms.c:2321-2358)
+__device__ inline void identity_scale(int32_t *x, int s, int n) {
+    for (int i = 0; i < n; i++) {
+        const int32_t v = TX(i);
+        int32_t o;
+        if (n == 4) o = round_shift64((long long)v * 5793, 12);
+        else if (n == 8) o = (int32_t)((uint32_t)v * 2u);
+        else if (n == 16) o = round_shift64((long long)v * 2 * 5793, 12);
+        else if (n == 32) o = (int32_t)((uint32_t)v * 4u);
+        else o = round_shift64((long long)v * 4 * 5793, 12);
+        TX(i) = o;
+    }
+}
+#undef TX
+
+// kind: 0 DCT, 1 ADST, 2 FLIPADST, 3 IDTX
+__device__ inline void fwd_1d(int32_t *x, int s, int n, int kind, int bit) {
+    if (kind == 0) fdct(x, s, n, bit);
+    else if (kind == 3) identity_scale(x, s, n);
+    else fadst(x, s, n, bit);
+}
+__device__ inline void inv_1d(int32_t *x, int s, int n, int kind, int bit, int clamp_bit) {
+    if (kind == 0) idct(x, s, n, bit, clamp_bit);
+    else if (kind == 3) identity_scale(x, s, n);
+    else iadst(x, s, n, bit, clamp_bit);
+}
+
+// ---- 2-D configuration (av1_transform_config / svt_av1_get_inv_txfm_cfg) -------------------------------------
+struct TxCfg {
+    int w, h; // transform size
+    int vk, hk; // 1-D kinds for columns / rows
+    int ud, lr; // flips
+    int fs0, fs1, fs2; // forward shifts (EbTransforms.h:26-44)
+    int is0, is1; // inverse shifts (EbInvTransforms.h:51-69)
+    int cbc, cbr; // forward cos_bit for columns / rows
+    int rect; // |log2(w/h)| == 1
+};
+
+
+// Forward 2-D transform of one block living in shared memory.
+//   buf: h rows of pitch `pitch` (>= w, odd pitches avoid bank conflicts for the row pass); on entry holds the
+//   residual (already flipped as cfg asks), on exit the coefficients in natural raster (r, c).
+//   lanes: `nl` cooperating threads with index `li`; contains __syncthreads-free named sync via `sync()` callable.
+template <typename Sync>
+__device__ inline void fwd_txfm2d_smem(int32_t *buf, int pitch, const TxCfg &t, int li, int nl, Sync sync) {
+    for (int c = li; c < t.w; c += nl) {
+        int32_t *col = buf + c;
+        if (t.fs0) for (int r = 0; r < t.h; r++) col[r * pitch] = (int32_t)((uint32_t)col[r * pitch] << t.fs0);
+        fwd_1d(col, pitch, t.h, t.vk, t.cbc);
+        if (t.fs1) for (int r = 0; r < t.h; r++) col[r * pitch] = round_shift64((long long)col[r * pitch], -t.fs1);
+    }
+    sync();
+    for (int r = li; r < t.h; r += nl) {
+        int32_t *row = buf + r * pitch;
+        fwd_1d(row, 1, t.w, t.hk, t.cbr);
+        for (int c = 0; c < t.w; c++) {
+            int32_t v = row[c];
+            if (t.fs2) v = round_shift64((long long)v, -t.fs2);
+            if (t.rect) v = round_shift64((long long)v * 5793, 12);
+            row[c] = v;
+        }
+    }
+    sync();
+}
+// Inverse 2-D: buf holds w x h coefficients (zero-extended for 64-wide sizes) on entry, residual on exit
+// (natural orientation: flips applied), rows then columns (inv_txfm2d_add_c, EbInvTransforms.c:2455-2532).
+template <typename Sync>
+__device__ inline void inv_txfm2d_smem(int32_t *buf, int pitch, const TxCfg &t, int bd, int li, int nl, Sync sync) {
+    const int range_row = bd == 8 ? 16 : bd == 10 ? 18 : 20, range_col = bd == 8 ? 16 : bd == 10 ? 16 : 18;
+    for (int r = li; r < t.h; r += nl) {
+        int32_t *row = buf + r * pitch;
+        for (int c = 0; c < t.w; c++) {
+            int32_t v = row[c];
+            if (t.rect) v = round_shift64((long long)v * 2896, 12);
+            row[c] = clampv(v, bd + 8);
+        }
+        inv_1d(row, 1, t.w, t.hk, 12, range_row);
+        if (t.is0) for (int c = 0; c < t.w; c++) row[c] = round_shift64((long long)row[c], -t.is0);
+    }
+    sync();
+    const int col_clamp = max(bd + 6, 16);
+    for (int c = li; c < t.w; c += nl) {
+        int32_t *col = buf + c;
+        for (int r = 0; r < t.h; r++) col[r * pitch] = clampv(col[r * pitch], col_clamp);
+        inv_1d(col, pitch, t.h, t.vk, 12, range_col);
+        for (int r = 0; r < t.h; r++) col[r * pitch] = round_shift64((long long)col[r * pitch], -t.is1);
+    }
+    sync();
+}
+
+} // namespace svtb200

@@ -79,6 +79,24 @@ class CdefApplyParams(C.Structure):
                 ("y_strength", C.c_int32 * 8), ("uv_strength", C.c_int32 * 8)]
 
 
+class Tu(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("plane", C.c_int32), ("tx_type", C.c_int32)]
+
+
+class QuantPlane(C.Structure):
+    _fields_ = [("zbin", C.c_int16 * 2), ("round", C.c_int16 * 2), ("quant", C.c_int16 * 2),
+                ("quant_shift", C.c_int16 * 2), ("dequant", C.c_int16 * 2), ("round_fp", C.c_int16 * 2),
+                ("quant_fp", C.c_int16 * 2)]
+
+
+class EncodeParams(C.Structure):
+    _fields_ = [("tx_size", C.c_int32), ("use_fp", C.c_int32), ("q", QuantPlane * 3)]
+
+
+TX_W = [4, 8, 16, 32, 64, 4, 8, 8, 16, 16, 32, 32, 64, 4, 16, 8, 32, 16, 64]
+TX_H = [4, 8, 16, 32, 64, 8, 4, 16, 8, 32, 16, 64, 32, 16, 4, 32, 8, 64, 16]
+
+
 def preset8_me_params(width, height, n_l0=1, n_l1=1, dist=((1, 2, 3, 4), (1, 2, 3, 4)), temporal_layer=1,
                       is_ref=1):
     """ME parameters of preset 8 (ENC_M8) at >=720p, 30 fps, as set_me_hme_params_oq /
@@ -154,6 +172,11 @@ def load():
     lib.svt_b200_me_picture.argtypes = [C.POINTER(MeParams), C.POINTER(MePlanes), C.POINTER(MePlanes),
                                         C.POINTER(MeOutputs), C.c_void_p, C.c_void_p]
     lib.svt_nxm_sad_kernel_cuda.restype = C.c_uint32
+    lib.svt_b200_handle_transform64.restype = C.c_uint64
+    for n in ("64x64", "64x32", "32x64", "64x16", "16x64"):
+        getattr(lib, f"svt_handle_transform{n}_cuda").restype = C.c_uint64
+    lib.svt_b200_encode_tus.argtypes = [C.POINTER(EncodeParams), C.POINTER(Frame), C.POINTER(Frame), C.POINTER(Frame),
+                                        C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.svt_b200_cdef_search.argtypes = [C.POINTER(CdefSearchParams), C.POINTER(Frame), C.POINTER(Frame), C.c_void_p,
                                          C.c_int32, C.c_void_p, C.c_void_p]
     lib.svt_b200_cdef_apply.argtypes = [C.POINTER(CdefApplyParams), C.POINTER(Frame), C.POINTER(Frame), C.c_void_p,

@@ -84,3 +84,21 @@ def run_gpu_cdef_apply(p, rec, skip, idx):
                                      C.c_void_p(didx.data_ptr()), None), lib)
     torch.cuda.synchronize()
     return do.download()
+
+
+def run_gpu_encode_tus(p, src, pred, tus):
+    lib = sb.load()
+    ts = p.tx_size
+    w, h = sb.TX_W[ts], sb.TX_H[ts]
+    n = min(w, 32) * min(h, 32)
+    ds, dp, dr = DevYuv(src), DevYuv(pred), DevYuv(pred.copy())
+    arr = (sb.Tu * len(tus))(*tus)
+    dt = torch.from_numpy(np.frombuffer(arr, dtype=np.int32).copy()).cuda()
+    q = torch.zeros(len(tus) * n, dtype=torch.int32, device="cuda")
+    eob = torch.zeros(len(tus), dtype=torch.int16, device="cuda")
+    scratch = torch.zeros(16384, dtype=torch.uint8, device="cuda")
+    ss, ps, rs = ds.struct(), dp.struct(), dr.struct()
+    sb.check(lib.svt_b200_encode_tus(C.byref(p), C.byref(ss), C.byref(ps), C.byref(rs), C.c_void_p(dt.data_ptr()), len(tus),
+                                     C.c_void_p(q.data_ptr()), C.c_void_p(eob.data_ptr()), C.c_void_p(scratch.data_ptr()), None), lib)
+    torch.cuda.synchronize()
+    return dr.download(), q.cpu().numpy().reshape(len(tus), n), eob.cpu().numpy().view(np.uint16)
