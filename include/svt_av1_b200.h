@@ -390,6 +390,53 @@ SVT_B200_API int svt_b200_encode_tus(const SvtB200EncodeParams *p, const SvtB200
                                      const SvtB200Tu *tus, int32_t n_tus, int32_t *qcoeff, uint16_t *eob,
                                      void *scratch, void *stream);
 
+/* =============================================================================================== */
+/* Deblocking loop filter                                                                          */
+/* =============================================================================================== */
+
+/* replace svt_aom_lpf_{horizontal,vertical}_{4,6,8,14} and svt_aom_highbd_lpf_* (common_dsp_rtcd.h:1039-1069;
+ * C impl Common/Codec/EbDeblockingCommon.c:251-924): one 4-sample edge segment, in place. */
+#define SVT_B200_DECL_LPF(DIR, N)                                                                          \
+    SVT_B200_API void svt_aom_lpf_##DIR##_##N##_cuda(uint8_t *s, int32_t pitch, const uint8_t *blimit,     \
+                                                     const uint8_t *limit, const uint8_t *thresh);         \
+    SVT_B200_API void svt_aom_highbd_lpf_##DIR##_##N##_cuda(uint16_t *s, int32_t pitch,                    \
+                                                            const uint8_t *blimit, const uint8_t *limit,   \
+                                                            const uint8_t *thresh, int32_t bd);
+SVT_B200_DECL_LPF(horizontal, 4) SVT_B200_DECL_LPF(horizontal, 6) SVT_B200_DECL_LPF(horizontal, 8)
+SVT_B200_DECL_LPF(horizontal, 14) SVT_B200_DECL_LPF(vertical, 4) SVT_B200_DECL_LPF(vertical, 6)
+SVT_B200_DECL_LPF(vertical, 8) SVT_B200_DECL_LPF(vertical, 14)
+
+/* Per-4x4 (luma mi unit) summary of the ModeInfo grid that set_lpf_parameters (EbDeblockingFilter.c:168-319)
+ * looks at.  The integration overlay fills it with the reference's own helpers (get_transform_size :134,
+ * get_plane_block_size, lfi_n->lvl[][][][][] or get_filter_level_delta_lf) — see INTEGRATION.md; index [0] is
+ * luma, [1] chroma (chroma reads the entry at the odd mi row/column of its 8x8, as the reference does). */
+typedef struct SvtB200DlfMi {
+    uint8_t tx_w[2], tx_h[2]; /* transform width / height in samples of that plane (4..64) */
+    uint8_t blk_w[2], blk_h[2]; /* prediction block width / height in samples of that plane */
+    uint8_t skip_inter; /* block_mi.skip && is_inter_block */
+    uint8_t lvl_y[2]; /* filter level for luma vertical edges [0] / horizontal edges [1] */
+    uint8_t lvl_u, lvl_v;
+    uint8_t pad[3];
+} SvtB200DlfMi;
+
+typedef struct SvtB200DlfParams {
+    int32_t mi_rows, mi_cols; /* picture size in 4x4 luma units */
+    int32_t mi_stride; /* entries per row of the SvtB200DlfMi array */
+    int32_t sharpness; /* frm_hdr->loop_filter_params.sharpness_level */
+    int32_t filter_level[2], filter_level_u, filter_level_v; /* frame levels: planes with level 0 are skipped
+                                                                exactly like loop_filter_sb (:629-636) */
+    int32_t plane_start, plane_end; /* [start, end) as svt_av1_loop_filter_frame's arguments */
+} SvtB200DlfParams;
+
+/* svt_av1_loop_filter_frame (EbDeblockingFilter.c:711-753): deblocks `frame` in place. mi: device array
+ * [mi_rows][mi_stride]. Two launches per call (all vertical edges, then all horizontal edges). */
+SVT_B200_API int svt_b200_dlf_frame(const SvtB200DlfParams *p, const SvtB200Frame *frame,
+                                    const SvtB200DlfMi *mi, void *stream);
+
+/* Sum of squared differences of two pictures per plane (picture_sse_calculations,
+ * EbDeblockingFilter.c:830-964), the distortion measure of svt_av1_pick_filter_level. sse: device uint64[3]. */
+SVT_B200_API int svt_b200_frame_sse(const SvtB200Frame *a, const SvtB200Frame *b, uint64_t *sse, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,10 @@ ORC_API void orc_quantize_b(const int32_t *coeff, intptr_t n, const int16_t *zbi
 ORC_API void orc_quantize_fp(const int32_t *coeff, intptr_t n, const int16_t *round, const int16_t *quant,
                              int32_t *qcoeff, int32_t *dqcoeff, const int16_t *dequant, uint16_t *eob_ptr,
                              const int16_t *scan, int log_scale, int hbd);
+/* ---- dlf_oracle.c ---- */
+ORC_API void orc_lpf_edge(void *s, int hbd, int across, int along, int len, int blimit, int limit, int thresh, int bd);
+ORC_API void orc_dlf_frame(const SvtB200DlfParams *p, const SvtB200Frame *f, const SvtB200DlfMi *mi);
+ORC_API void orc_frame_sse(const SvtB200Frame *a, const SvtB200Frame *b, uint64_t *sse);
 #ifdef __cplusplus
 }
 #endif

@@ -413,3 +413,72 @@ REFH_API int refh_get_scan(int tx_size, int tx_type, int16_t *out) {
     memcpy(out, so->scan, sizeof(int16_t) * w * h);
     return w * h;
 }
+
+/* ====================================================================================================
+ * Deblocking: svt_av1_loop_filter_frame (EbDeblockingFilter.c:711) on a picture whose ModeInfo grid is built
+ * from per-mi arrays (sb_type, tx_depth, is_inter, skip).  Also emits the flattened SvtB200DlfMi summary with
+ * the reference's own tables/inline helpers — what the integration overlay computes inside the reference.
+ * ================================================================================================== */
+#include "EbDeblockingFilter.h"
+#include "EbUtility.h"
+void svt_av1_loop_filter_init(PictureControlSet *pcs_ptr);
+
+REFH_API int refh_dlf_frame(int mi_rows, int mi_cols, const uint8_t *sb_type, const uint8_t *tx_depth,
+                            const uint8_t *is_inter, const uint8_t *skip, const int32_t *levels /*y0,y1,u,v*/,
+                            int sharpness, SvtB200Frame *frame, SvtB200DlfMi *flat /*[mi_rows][mi_cols]*/) {
+    FiltCtx *c = filt_ctx_new(mi_rows, mi_cols, frame->bit_depth, frame, NULL, NULL, 0, NULL);
+    c->ppcs->scs_ptr = c->scs;
+    c->scs->seq_header.sb_size = BLOCK_64X64;
+    c->scs->sb_size_pix = 64;
+    c->scs->max_input_luma_width = (uint16_t)(mi_cols * 4);
+    c->scs->max_input_luma_height = (uint16_t)(mi_rows * 4);
+    c->scs->max_input_pad_right = 0;
+    c->scs->max_input_pad_bottom = 0;
+    struct LoopFilter *lf = &c->ppcs->frm_hdr.loop_filter_params;
+    lf->filter_level[0] = levels[0];
+    lf->filter_level[1] = levels[1];
+    lf->filter_level_u = levels[2];
+    lf->filter_level_v = levels[3];
+    lf->sharpness_level = sharpness;
+    lf->mode_ref_delta_enabled = 0;
+    c->ppcs->frm_hdr.delta_lf_params.delta_lf_present = 0;
+    for (int r = 0; r < mi_rows; r++)
+        for (int q = 0; q < mi_cols; q++) {
+            const size_t i = (size_t)r * mi_cols + q;
+            ModeInfo *m = &c->mi[i];
+            m->mbmi.block_mi.sb_type = (BlockSize)sb_type[i];
+            m->mbmi.tx_depth = tx_depth[i];
+            m->mbmi.block_mi.ref_frame[0] = is_inter[i] ? LAST_FRAME : INTRA_FRAME;
+            m->mbmi.block_mi.skip = skip[i];
+            m->mbmi.block_mi.mode = is_inter[i] ? NEARESTMV : DC_PRED;
+            if (flat) {
+                SvtB200DlfMi *f = &flat[i];
+                memset(f, 0, sizeof(*f));
+                const BlockSize bs = (BlockSize)sb_type[i];
+                TxSize tx = is_inter[i] ? tx_depth_to_tx_size[0][bs] : tx_depth_to_tx_size[tx_depth[i]][bs];
+                if (is_inter[i] && !skip[i]) tx = tx_depth_to_tx_size[tx_depth[i]][bs];
+                const TxSize uv = av1_get_max_uv_txsize(bs, 1, 1);
+                f->tx_w[0] = (uint8_t)tx_size_wide[txsize_horz_map[tx]];
+                f->tx_h[0] = (uint8_t)tx_size_high[txsize_vert_map[tx]];
+                f->tx_w[1] = (uint8_t)tx_size_wide[txsize_horz_map[uv]];
+                f->tx_h[1] = (uint8_t)tx_size_high[txsize_vert_map[uv]];
+                const BlockSize cb = get_plane_block_size(bs, 1, 1);
+                f->blk_w[0] = block_size_wide[bs];
+                f->blk_h[0] = block_size_high[bs];
+                f->blk_w[1] = block_size_wide[cb];
+                f->blk_h[1] = block_size_high[cb];
+                f->skip_inter = skip[i] && is_inter[i];
+                f->lvl_y[0] = (uint8_t)levels[0]; /* lfi_n->lvl[..]: no ref/mode deltas, no segmentation */
+                f->lvl_y[1] = (uint8_t)levels[1];
+                f->lvl_u = (uint8_t)levels[2];
+                f->lvl_v = (uint8_t)levels[3];
+            }
+        }
+    svt_av1_loop_filter_init(c->pcs);
+    c->recon.bit_depth = frame->bit_depth > 8 ? EB_10BIT : EB_8BIT;
+    c->recon.width = (uint16_t)(mi_cols * 4);
+    c->recon.height = (uint16_t)(mi_rows * 4);
+    svt_av1_loop_filter_frame(&c->recon, c->pcs, 0, 3);
+    filt_ctx_free(c);
+    return 0;
+}

@@ -97,6 +97,18 @@ TX_W = [4, 8, 16, 32, 64, 4, 8, 8, 16, 16, 32, 32, 64, 4, 16, 8, 32, 16, 64]
 TX_H = [4, 8, 16, 32, 64, 8, 4, 16, 8, 32, 16, 64, 32, 16, 4, 32, 8, 64, 16]
 
 
+class DlfMi(C.Structure):
+    _fields_ = [("tx_w", C.c_uint8 * 2), ("tx_h", C.c_uint8 * 2), ("blk_w", C.c_uint8 * 2), ("blk_h", C.c_uint8 * 2),
+                ("skip_inter", C.c_uint8), ("lvl_y", C.c_uint8 * 2), ("lvl_u", C.c_uint8), ("lvl_v", C.c_uint8),
+                ("pad", C.c_uint8 * 3)]
+
+
+class DlfParams(C.Structure):
+    _fields_ = [("mi_rows", C.c_int32), ("mi_cols", C.c_int32), ("mi_stride", C.c_int32), ("sharpness", C.c_int32),
+                ("filter_level", C.c_int32 * 2), ("filter_level_u", C.c_int32), ("filter_level_v", C.c_int32),
+                ("plane_start", C.c_int32), ("plane_end", C.c_int32)]
+
+
 def preset8_me_params(width, height, n_l0=1, n_l1=1, dist=((1, 2, 3, 4), (1, 2, 3, 4)), temporal_layer=1,
                       is_ref=1):
     """ME parameters of preset 8 (ENC_M8) at >=720p, 30 fps, as set_me_hme_params_oq /

@@ -238,3 +238,57 @@ def skip_map(mi_rows, mi_cols, seed=3, frac=0.3, all_skip_fb=True):
     if all_skip_fb and r8 > 8 and c8 > 8:
         m[0:8, 8:16] = 1  # one filter block entirely skipped
     return m
+
+
+# ------------------------------------------------------------------------------------------------------
+# block partitions for the deblocking tests
+# ------------------------------------------------------------------------------------------------------
+# BlockSize enum values (Common/Codec/EbDefinitions.h:531-552)
+_BS = {(4, 4): 0, (4, 8): 1, (8, 4): 2, (8, 8): 3, (8, 16): 4, (16, 8): 5, (16, 16): 6, (16, 32): 7, (32, 16): 8,
+       (32, 32): 9, (32, 64): 10, (64, 32): 11, (64, 64): 12, (4, 16): 16, (16, 4): 17, (8, 32): 18, (32, 8): 19,
+       (16, 64): 20, (64, 16): 21}
+
+
+def random_partition(mi_rows, mi_cols, seed=0, p_split=0.55, p_inter=0.6, p_skip=0.4):
+    """Per-mi arrays (sb_type, tx_depth, is_inter, skip) of a random AV1-like partition of the picture."""
+    rng = np.random.default_rng(seed)
+    sbt = np.zeros((mi_rows, mi_cols), np.uint8)
+    dep = np.zeros((mi_rows, mi_cols), np.uint8)
+    inter = np.zeros((mi_rows, mi_cols), np.uint8)
+    skip = np.zeros((mi_rows, mi_cols), np.uint8)
+
+    def leaf(r, c, h, w):
+        hh, ww = min(h, mi_rows * 4 - r * 4), min(w, mi_cols * 4 - c * 4)
+        if hh <= 0 or ww <= 0:
+            return
+        bs = _BS[(w, h)]
+        d = int(rng.integers(0, 3))
+        it, sk = int(rng.random() < p_inter), int(rng.random() < p_skip)
+        r1, c1 = min(mi_rows, r + h // 4), min(mi_cols, c + w // 4)
+        sbt[r:r1, c:c1], dep[r:r1, c:c1], inter[r:r1, c:c1], skip[r:r1, c:c1] = bs, d, it, sk
+
+    def split(r, c, size):
+        if r >= mi_rows or c >= mi_cols:
+            return
+        u = rng.random()
+        if size > 4 and u < p_split:
+            half = size // 2
+            for dr in (0, half // 4):
+                for dc in (0, half // 4):
+                    split(r + dr, c + dc, half)
+        elif size > 4 and u < p_split + 0.12:   # horizontal halves (w x h/2)
+            leaf(r, c, size // 2, size)
+            leaf(r + size // 8, c, size // 2, size)
+        elif size > 4 and u < p_split + 0.24:   # vertical halves
+            leaf(r, c, size, size // 2)
+            leaf(r, c + size // 8, size, size // 2)
+        elif size >= 16 and u < p_split + 0.30:  # 4:1 strips
+            for k in range(4):
+                leaf(r + k * size // 16, c, size // 4, size)
+        else:
+            leaf(r, c, size, size)
+
+    for r in range(0, mi_rows, 16):
+        for c in range(0, mi_cols, 16):
+            split(r, c, 64)
+    return sbt, dep, inter, skip
