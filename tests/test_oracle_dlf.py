@@ -101,5 +101,5 @@ def test_dlf_frame_matches_reference(case):
     cm.oracle().orc_dlf_frame(C.byref(p), C.byref(st), flat)
     for i in range(3):
         np.testing.assert_array_equal(got.plane(i), want.plane(i), err_msg=f"plane {i}")
-    if max(levels) >= 20:  # (weak levels on noisy content may legitimately change nothing)
+    if levels[0] >= 20:  # (weak levels on noisy content may legitimately change nothing)
         assert any((want.plane(i) != frame.plane(i)).any() for i in range(3))
