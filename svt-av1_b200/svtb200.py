@@ -185,6 +185,8 @@ def load():
                                         C.POINTER(MeOutputs), C.c_void_p, C.c_void_p]
     lib.svt_nxm_sad_kernel_cuda.restype = C.c_uint32
     lib.svt_b200_handle_transform64.restype = C.c_uint64
+    lib.svt_b200_dlf_frame.argtypes = [C.POINTER(DlfParams), C.POINTER(Frame), C.c_void_p, C.c_void_p]
+    lib.svt_b200_frame_sse.argtypes = [C.POINTER(Frame), C.POINTER(Frame), C.c_void_p, C.c_void_p]
     for n in ("64x64", "64x32", "32x64", "64x16", "16x64"):
         getattr(lib, f"svt_handle_transform{n}_cuda").restype = C.c_uint64
     lib.svt_b200_encode_tus.argtypes = [C.POINTER(EncodeParams), C.POINTER(Frame), C.POINTER(Frame), C.POINTER(Frame),

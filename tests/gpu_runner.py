@@ -102,3 +102,23 @@ def run_gpu_encode_tus(p, src, pred, tus):
                                      C.c_void_p(q.data_ptr()), C.c_void_p(eob.data_ptr()), C.c_void_p(scratch.data_ptr()), None), lib)
     torch.cuda.synchronize()
     return dr.download(), q.cpu().numpy().reshape(len(tus), n), eob.cpu().numpy().view(np.uint16)
+
+
+def run_gpu_dlf(p, frame, flat):
+    lib = sb.load()
+    df = DevYuv(frame.copy())
+    dmi = torch.from_numpy(np.frombuffer(flat, dtype=np.uint8).copy()).cuda()
+    st = df.struct()
+    sb.check(lib.svt_b200_dlf_frame(C.byref(p), C.byref(st), C.c_void_p(dmi.data_ptr()), None), lib)
+    torch.cuda.synchronize()
+    return df.download()
+
+
+def run_gpu_sse(a, b):
+    lib = sb.load()
+    da, db = DevYuv(a), DevYuv(b)
+    out = torch.zeros(3, dtype=torch.int64, device="cuda")
+    sa, sbb = da.struct(), db.struct()
+    sb.check(lib.svt_b200_frame_sse(C.byref(sa), C.byref(sbb), C.c_void_p(out.data_ptr()), None), lib)
+    torch.cuda.synchronize()
+    return out.cpu().numpy().view(np.uint64)
