@@ -482,3 +482,119 @@ REFH_API int refh_dlf_frame(int mi_rows, int mi_cols, const uint8_t *sb_type, co
     filt_ctx_free(c);
     return 0;
 }
+
+/* ====================================================================================================
+ * EncDec per-TU chain with the reference's own kernels, through its RTCD pointers (C paths):
+ *   svt_residual_kernel8bit/16bit -> svt_av1_fwd_txfm2d_* (+ svt_handle_transform*) -> svt_aom_[highbd_]quantize_b or
+ *   svt_av1_[highbd_]quantize_fp -> svt_av1_inv_txfm2d_add_*   (the body of av1_encode_loop, EbCodingLoop.c:290-...)
+ * ================================================================================================== */
+static void ref_fwd(int tx_size, int16_t *res, int32_t *coeff, uint32_t stride, TxType tt, uint8_t bd) {
+    switch (tx_size) {
+    case TX_4X4: svt_av1_fwd_txfm2d_4x4(res, coeff, stride, tt, bd); break;
+    case TX_8X8: svt_av1_fwd_txfm2d_8x8(res, coeff, stride, tt, bd); break;
+    case TX_16X16: svt_av1_fwd_txfm2d_16x16(res, coeff, stride, tt, bd); break;
+    case TX_32X32: svt_av1_fwd_txfm2d_32x32(res, coeff, stride, tt, bd); break;
+    case TX_64X64: svt_av1_fwd_txfm2d_64x64(res, coeff, stride, tt, bd); svt_handle_transform64x64(coeff); break;
+    case TX_4X8: svt_av1_fwd_txfm2d_4x8(res, coeff, stride, tt, bd); break;
+    case TX_8X4: svt_av1_fwd_txfm2d_8x4(res, coeff, stride, tt, bd); break;
+    case TX_8X16: svt_av1_fwd_txfm2d_8x16(res, coeff, stride, tt, bd); break;
+    case TX_16X8: svt_av1_fwd_txfm2d_16x8(res, coeff, stride, tt, bd); break;
+    case TX_16X32: svt_av1_fwd_txfm2d_16x32(res, coeff, stride, tt, bd); break;
+    case TX_32X16: svt_av1_fwd_txfm2d_32x16(res, coeff, stride, tt, bd); break;
+    case TX_32X64: svt_av1_fwd_txfm2d_32x64(res, coeff, stride, tt, bd); svt_handle_transform32x64(coeff); break;
+    case TX_64X32: svt_av1_fwd_txfm2d_64x32(res, coeff, stride, tt, bd); svt_handle_transform64x32(coeff); break;
+    case TX_4X16: svt_av1_fwd_txfm2d_4x16(res, coeff, stride, tt, bd); break;
+    case TX_16X4: svt_av1_fwd_txfm2d_16x4(res, coeff, stride, tt, bd); break;
+    case TX_8X32: svt_av1_fwd_txfm2d_8x32(res, coeff, stride, tt, bd); break;
+    case TX_32X8: svt_av1_fwd_txfm2d_32x8(res, coeff, stride, tt, bd); break;
+    case TX_16X64: svt_av1_fwd_txfm2d_16x64(res, coeff, stride, tt, bd); svt_handle_transform16x64(coeff); break;
+    default: svt_av1_fwd_txfm2d_64x16(res, coeff, stride, tt, bd); svt_handle_transform64x16(coeff); break;
+    }
+}
+static void ref_inv(int tx_size, const int32_t *dq, uint16_t *pr, int sr, uint16_t *rc, int sw, TxType tt, int eob, int bd) {
+    switch (tx_size) {
+    case TX_4X4: svt_av1_inv_txfm2d_add_4x4(dq, pr, sr, rc, sw, tt, bd); break;
+    case TX_8X8: svt_av1_inv_txfm2d_add_8x8(dq, pr, sr, rc, sw, tt, bd); break;
+    case TX_16X16: svt_av1_inv_txfm2d_add_16x16(dq, pr, sr, rc, sw, tt, bd); break;
+    case TX_32X32: svt_av1_inv_txfm2d_add_32x32(dq, pr, sr, rc, sw, tt, bd); break;
+    case TX_64X64: svt_av1_inv_txfm2d_add_64x64(dq, pr, sr, rc, sw, tt, bd); break;
+    case TX_4X8: svt_av1_inv_txfm2d_add_4x8(dq, pr, sr, rc, sw, tt, TX_4X8, bd); break;
+    case TX_8X4: svt_av1_inv_txfm2d_add_8x4(dq, pr, sr, rc, sw, tt, TX_8X4, bd); break;
+    case TX_8X16: svt_av1_inv_txfm2d_add_8x16(dq, pr, sr, rc, sw, tt, TX_8X16, eob, bd); break;
+    case TX_16X8: svt_av1_inv_txfm2d_add_16x8(dq, pr, sr, rc, sw, tt, TX_16X8, eob, bd); break;
+    case TX_16X32: svt_av1_inv_txfm2d_add_16x32(dq, pr, sr, rc, sw, tt, TX_16X32, eob, bd); break;
+    case TX_32X16: svt_av1_inv_txfm2d_add_32x16(dq, pr, sr, rc, sw, tt, TX_32X16, eob, bd); break;
+    case TX_32X64: svt_av1_inv_txfm2d_add_32x64(dq, pr, sr, rc, sw, tt, TX_32X64, eob, bd); break;
+    case TX_64X32: svt_av1_inv_txfm2d_add_64x32(dq, pr, sr, rc, sw, tt, TX_64X32, eob, bd); break;
+    case TX_4X16: svt_av1_inv_txfm2d_add_4x16(dq, pr, sr, rc, sw, tt, TX_4X16, bd); break;
+    case TX_16X4: svt_av1_inv_txfm2d_add_16x4(dq, pr, sr, rc, sw, tt, TX_16X4, bd); break;
+    case TX_8X32: svt_av1_inv_txfm2d_add_8x32(dq, pr, sr, rc, sw, tt, TX_8X32, eob, bd); break;
+    case TX_32X8: svt_av1_inv_txfm2d_add_32x8(dq, pr, sr, rc, sw, tt, TX_32X8, eob, bd); break;
+    case TX_16X64: svt_av1_inv_txfm2d_add_16x64(dq, pr, sr, rc, sw, tt, TX_16X64, eob, bd); break;
+    default: svt_av1_inv_txfm2d_add_64x16(dq, pr, sr, rc, sw, tt, TX_64X16, eob, bd); break;
+    }
+}
+
+REFH_API int refh_encode_tus(const SvtB200EncodeParams *p, const SvtB200Frame *src, const SvtB200Frame *pred,
+                             const SvtB200Frame *recon, const SvtB200Tu *tus, int n_tus, int32_t *qcoeff, uint16_t *eobs) {
+    refh_init();
+    const int ts = p->tx_size, w = tx_size_wide[ts], h = tx_size_high[ts];
+    const int iw = w > 32 ? 32 : w, ih = h > 32 ? 32 : h, n = iw * ih;
+    const int bd = src->bit_depth, hbd = bd > 8;
+    const int log_scale = (w * h > 256) + (w * h > 1024);
+    int16_t res[64 * 64];
+    int32_t coeff[64 * 64], dq[32 * 32];
+    uint16_t p16[64 * 64], r16[64 * 64];
+    for (int i = 0; i < n_tus; i++) {
+        const SvtB200Tu *t = &tus[i];
+        const int pl = t->plane;
+        const int ss = pl ? src->stride_c : src->stride_y, ps = pl ? pred->stride_c : pred->stride_y,
+                  rs = pl ? recon->stride_c : recon->stride_y;
+        const void *sp = pl == 0 ? src->y : pl == 1 ? src->cb : src->cr;
+        const void *pp = pl == 0 ? pred->y : pl == 1 ? pred->cb : pred->cr;
+        void *rp = pl == 0 ? recon->y : pl == 1 ? recon->cb : recon->cr;
+        if (hbd)
+            svt_residual_kernel16bit((uint16_t *)sp + (size_t)t->y * ss + t->x, ss, (uint16_t *)pp + (size_t)t->y * ps + t->x, ps,
+                                     res, w, w, h);
+        else
+            svt_residual_kernel8bit((uint8_t *)sp + (size_t)t->y * ss + t->x, ss, (uint8_t *)pp + (size_t)t->y * ps + t->x, ps, res,
+                                    w, w, h);
+        ref_fwd(ts, res, coeff, w, (TxType)t->tx_type, (uint8_t)bd);
+        const ScanOrder *so = &av1_scan_orders[ts][t->tx_type];
+        const SvtB200QuantPlane *q = &p->q[pl];
+        int32_t *qc = qcoeff + (size_t)i * n;
+        uint16_t eob = 0;
+        if (p->use_fp) {
+            if (hbd)
+                svt_av1_highbd_quantize_fp(coeff, n, q->zbin, q->round_fp, q->quant_fp, q->quant_shift, qc, dq, q->dequant, &eob,
+                                           so->scan, so->iscan, (int16_t)log_scale);
+            else if (log_scale == 0)
+                svt_av1_quantize_fp(coeff, n, q->zbin, q->round_fp, q->quant_fp, q->quant_shift, qc, dq, q->dequant, &eob, so->scan, so->iscan);
+            else if (log_scale == 1)
+                svt_av1_quantize_fp_32x32(coeff, n, q->zbin, q->round_fp, q->quant_fp, q->quant_shift, qc, dq, q->dequant, &eob, so->scan, so->iscan);
+            else
+                svt_av1_quantize_fp_64x64(coeff, n, q->zbin, q->round_fp, q->quant_fp, q->quant_shift, qc, dq, q->dequant, &eob, so->scan, so->iscan);
+        } else if (hbd) {
+            svt_aom_highbd_quantize_b(coeff, n, q->zbin, q->round, q->quant, q->quant_shift, qc, dq, q->dequant, &eob, so->scan,
+                                      so->iscan, NULL, NULL, log_scale);
+        } else {
+            svt_aom_quantize_b(coeff, n, q->zbin, q->round, q->quant, q->quant_shift, qc, dq, q->dequant, &eob, so->scan, so->iscan,
+                               NULL, NULL, log_scale);
+        }
+        eobs[i] = eob;
+        /* inverse + reconstruction through the 16-bit kernels (the lowbd wrapper svt_av1_inv_txfm_add_c copies the
+         * 8-bit prediction into a 16-bit scratch the same way, EbInvTransforms.c:3302-3330) */
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++)
+                p16[y * w + x] = hbd ? ((uint16_t *)pp)[(size_t)(t->y + y) * ps + t->x + x] : ((uint8_t *)pp)[(size_t)(t->y + y) * ps + t->x + x];
+        ref_inv(ts, dq, p16, w, r16, w, (TxType)t->tx_type, eob, bd);
+        for (int y = 0; y < h; y++)
+            for (int x = 0; x < w; x++) {
+                if (hbd)
+                    ((uint16_t *)rp)[(size_t)(t->y + y) * rs + t->x + x] = r16[y * w + x];
+                else
+                    ((uint8_t *)rp)[(size_t)(t->y + y) * rs + t->x + x] = (uint8_t)r16[y * w + x];
+            }
+    }
+    return 0;
+}
