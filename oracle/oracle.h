@@ -2,6 +2,7 @@
  * Built into oracle/liboracle.so by oracle/Makefile. Never linked into libsvtav1_b200.so. */
 #ifndef SVT_B200_ORACLE_H
 #define SVT_B200_ORACLE_H
+#include <stddef.h>
 #include <stdint.h>
 #include "../include/svt_av1_b200.h"
 #ifdef __cplusplus
@@ -75,6 +76,14 @@ ORC_API void orc_quantize_fp(const int32_t *coeff, intptr_t n, const int16_t *ro
 ORC_API void orc_lpf_edge(void *s, int hbd, int across, int along, int len, int blimit, int limit, int thresh, int bd);
 ORC_API void orc_dlf_frame(const SvtB200DlfParams *p, const SvtB200Frame *f, const SvtB200DlfMi *mi);
 ORC_API void orc_frame_sse(const SvtB200Frame *a, const SvtB200Frame *b, uint64_t *sse);
+/* ---- lr_oracle.c ---- */
+ORC_API void orc_selfguided_restoration(const void *dgd, int hbd, int width, int height, int dgd_stride, int32_t *flt0,
+                                        int32_t *flt1, int flt_stride, int sgr_params_idx, int bit_depth);
+ORC_API void orc_apply_selfguided_restoration(const void *dat, int hbd, int width, int height, int stride, int eps,
+                                              const int32_t *xqd, void *dst, int dst_stride, int bit_depth);
+ORC_API void orc_wiener_convolve_add_src(const void *src, int hbd, ptrdiff_t src_stride, void *dst, ptrdiff_t dst_stride,
+                                         const int16_t *filter_x, const int16_t *filter_y, int w, int h, int round_0,
+                                         int round_1, int bd);
 #ifdef __cplusplus
 }
 #endif
