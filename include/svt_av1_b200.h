@@ -437,6 +437,31 @@ SVT_B200_API int svt_b200_dlf_frame(const SvtB200DlfParams *p, const SvtB200Fram
  * EbDeblockingFilter.c:830-964), the distortion measure of svt_av1_pick_filter_level. sse: device uint64[3]. */
 SVT_B200_API int svt_b200_frame_sse(const SvtB200Frame *a, const SvtB200Frame *b, uint64_t *sse, void *stream);
 
+/* =============================================================================================== */
+/* Loop restoration kernels (RTCD drop-ins; the frame-level stripe loop is not built yet)          */
+/* =============================================================================================== */
+
+/* replace svt_av1_selfguided_restoration / svt_apply_selfguided_restoration (common_dsp_rtcd.h:187-191;
+ * EbRestoration.c:1012-1084).  High-bit-depth planes are passed as CONVERT_TO_BYTEPTR(ptr), as in the reference. */
+SVT_B200_API void svt_av1_selfguided_restoration_cuda(const uint8_t *dgd8, int32_t width, int32_t height,
+                                                      int32_t dgd_stride, int32_t *flt0, int32_t *flt1,
+                                                      int32_t flt_stride, int32_t sgr_params_idx,
+                                                      int32_t bit_depth, int32_t highbd);
+SVT_B200_API void svt_apply_selfguided_restoration_cuda(const uint8_t *dat, int32_t width, int32_t height,
+                                                        int32_t stride, int32_t eps, const int32_t *xqd,
+                                                        uint8_t *dst, int32_t dst_stride, int32_t *tmpbuf,
+                                                        int32_t bit_depth, int32_t highbd);
+/* replace svt_av1_wiener_convolve_add_src / svt_av1_highbd_wiener_convolve_add_src (common_dsp_rtcd.h:183,185;
+ * convolve.c:105-260). conv_params points at the reference's ConvolveParams (only round_0/round_1 are read). */
+SVT_B200_API void svt_av1_wiener_convolve_add_src_cuda(const uint8_t *src, ptrdiff_t src_stride, uint8_t *dst,
+                                                       ptrdiff_t dst_stride, const int16_t *filter_x,
+                                                       const int16_t *filter_y, int32_t w, int32_t h,
+                                                       const void *conv_params);
+SVT_B200_API void svt_av1_highbd_wiener_convolve_add_src_cuda(const uint8_t *src, ptrdiff_t src_stride, uint8_t *dst,
+                                                              ptrdiff_t dst_stride, const int16_t *filter_x,
+                                                              const int16_t *filter_y, int32_t w, int32_t h,
+                                                              const void *conv_params, int32_t bd);
+
 #ifdef __cplusplus
 }
 #endif

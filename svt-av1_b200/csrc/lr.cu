@@ -1,0 +1,312 @@
+// lr.cu — loop-restoration kernels on sm_100a: self-guided filter, its projection apply, separable Wiener.
+//
+// Replaces (reference files under Source/Lib/Common/Codec):
+//   svt_av1_selfguided_restoration_c        EbRestoration.c:1012-1045 (internals :744-1010, boxsum :541-705)
+//   svt_apply_selfguided_restoration_c      EbRestoration.c:1047-1084 (svt_decode_xq :707)
+//   svt_av1_wiener_convolve_add_src_c / svt_av1_highbd_wiener_convolve_add_src_c   convolve.c:53-260
+//
+// Design: one CTA per processing unit (<= 64x64 + 3-sample rim).  The unit is staged once in shared memory;
+// the box sums of the self-guided filter are evaluated directly from it ((2r+1)^2 taps per a/b sample — the rim
+// makes every window complete, so no integral image and no edge cases), a/b for the (w+2)x(h+2) neighbourhood
+// are kept in shared memory and both radii are produced from the same tile.  The Wiener filter keeps the
+// horizontally filtered (h+7) x w intermediate in shared memory, so HBM traffic is 2 B/sample (8-bit) in both
+// cases.  This round provides the RTCD drop-ins; the frame-level stripe loop is the next §8 row.
+#include "common.cuh"
+
+using namespace svtb200;
+
+namespace {
+
+__constant__ int8_t c_sgr_r[16][2] = {{2, 1}, {2, 1}, {2, 1}, {2, 1}, {2, 1}, {2, 1}, {2, 1}, {2, 1},
+                                      {2, 1}, {2, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {2, 0}, {2, 0}};
+__constant__ int16_t c_sgr_s[16][2] = {{140, 3236}, {112, 2158}, {93, 1618}, {80, 1438}, {70, 1295}, {58, 1177}, {47, 1079}, {37, 996},
+                                       {30, 925},   {25, 863},   {-1, 2589}, {-1, 1618}, {-1, 1177}, {-1, 925},  {56, -1},   {22, -1}};
+static const int8_t h_sgr_r[16][2] = {{2, 1}, {2, 1}, {2, 1}, {2, 1}, {2, 1}, {2, 1}, {2, 1}, {2, 1},
+                                      {2, 1}, {2, 1}, {0, 1}, {0, 1}, {0, 1}, {0, 1}, {2, 0}, {2, 0}};
+
+__device__ __forceinline__ int x_by_xplus1(int z) { // eb_x_by_xplus1: round(256 z/(z+1)), 0 -> 1, 255 -> 256
+    if (z == 0) return 1;
+    if (z >= 255) return 256;
+    return (256 * z + (z + 1) / 2) / (z + 1);
+}
+__device__ __forceinline__ uint32_t rpot(uint32_t v, int n) { return n ? (v + (1u << (n - 1))) >> n : v; }
+
+constexpr int SGR_NT = 256;
+
+// tile: (h+6) x (w+6) uint16 samples (stride tw = w+6), origin at (3,3).  A/B: (h+2) x (w+2) int32.
+__device__ void sgr_pass(const uint16_t *tile, int tw, int w, int h, int32_t *A, int32_t *B, int32_t *dst, int dst_stride,
+                         int bd, int idx, int pass) {
+    const int r = c_sgr_r[idx][pass], n = (2 * r + 1) * (2 * r + 1);
+    const uint32_t s = (uint32_t)c_sgr_s[idx][pass];
+    const uint32_t one_by_n = (4096 + n / 2) / n;
+    const int bs = w + 2;
+    const bool fast = pass == 0;
+    const uint16_t *org = tile + 3 * tw + 3;
+    __syncthreads();
+    for (int t = threadIdx.x; t < (h + 2) * (w + 2); t += SGR_NT) {
+        const int i = t / bs - 1, j = t % bs - 1;
+        if (fast && ((i + 1) & 1)) continue; /* the fast pass evaluates rows -1, 1, 3, ... only */
+        uint32_t sum = 0, sq = 0;
+        for (int y = -r; y <= r; y++)
+            for (int x = -r; x <= r; x++) {
+                const uint32_t v = org[(i + y) * tw + j + x];
+                sum += v;
+                sq += v * v;
+            }
+        const uint32_t a = rpot(sq, 2 * (bd - 8)), b = rpot(sum, bd - 8);
+        const uint32_t p = (a * n < b * b) ? 0 : a * n - b * b;
+        const uint32_t z = rpot(p * s, 20);
+        const int av = x_by_xplus1((int)min(z, 255u));
+        A[t] = av;
+        B[t] = (int32_t)rpot((uint32_t)(256 - av) * sum * one_by_n, 12);
+    }
+    __syncthreads();
+#define AA(i, j) A[((i) + 1) * bs + (j) + 1]
+#define BB(i, j) B[((i) + 1) * bs + (j) + 1]
+    for (int t = threadIdx.x; t < h * w; t += SGR_NT) {
+        const int i = t / w, j = t % w;
+        int32_t a, b, nb;
+        if (!fast) {
+            nb = 5;
+            a = (AA(i, j) + AA(i, j - 1) + AA(i, j + 1) + AA(i - 1, j) + AA(i + 1, j)) * 4 +
+                (AA(i - 1, j - 1) + AA(i + 1, j - 1) + AA(i - 1, j + 1) + AA(i + 1, j + 1)) * 3;
+            b = (BB(i, j) + BB(i, j - 1) + BB(i, j + 1) + BB(i - 1, j) + BB(i + 1, j)) * 4 +
+                (BB(i - 1, j - 1) + BB(i + 1, j - 1) + BB(i - 1, j + 1) + BB(i + 1, j + 1)) * 3;
+        } else if (!(i & 1)) {
+            nb = 5;
+            a = (AA(i - 1, j) + AA(i + 1, j)) * 6 + (AA(i - 1, j - 1) + AA(i + 1, j - 1) + AA(i - 1, j + 1) + AA(i + 1, j + 1)) * 5;
+            b = (BB(i - 1, j) + BB(i + 1, j)) * 6 + (BB(i - 1, j - 1) + BB(i + 1, j - 1) + BB(i - 1, j + 1) + BB(i + 1, j + 1)) * 5;
+        } else {
+            nb = 4;
+            a = AA(i, j) * 6 + (AA(i, j - 1) + AA(i, j + 1)) * 5;
+            b = BB(i, j) * 6 + (BB(i, j - 1) + BB(i, j + 1)) * 5;
+        }
+        const int32_t v = a * (int32_t)org[i * tw + j] + b;
+        const int sh = 8 + nb - 4;
+        dst[i * dst_stride + j] = (v + (1 << (sh - 1))) >> sh;
+    }
+#undef AA
+#undef BB
+}
+
+struct SgrArgs {
+    const uint16_t *tile_in; // (h+6) x (w+6) packed samples
+    int w, h, bd, idx;
+    int32_t *flt0, *flt1; // w-strided outputs (device)
+    // apply mode
+    int apply, xq0, xq1;
+    uint16_t *out; // w-strided
+};
+__global__ void __launch_bounds__(SGR_NT) sgr_kernel(const SgrArgs a) {
+    extern __shared__ int32_t sm[];
+    const int tw = a.w + 6, th = a.h + 6;
+    int32_t *A = sm, *B = A + (a.w + 2) * (a.h + 2);
+    uint16_t *tile = reinterpret_cast<uint16_t *>(B + (a.w + 2) * (a.h + 2));
+    for (int i = threadIdx.x; i < tw * th; i += SGR_NT) tile[i] = a.tile_in[i];
+    __syncthreads();
+    const int r0 = c_sgr_r[a.idx][0], r1 = c_sgr_r[a.idx][1];
+    if (r0 > 0) sgr_pass(tile, tw, a.w, a.h, A, B, a.flt0, a.w, a.bd, a.idx, 0);
+    if (r1 > 0) sgr_pass(tile, tw, a.w, a.h, A, B, a.flt1, a.w, a.bd, a.idx, 1);
+    if (!a.apply) return;
+    __syncthreads();
+    __threadfence_block();
+    const int mx = (1 << a.bd) - 1;
+    for (int t = threadIdx.x; t < a.w * a.h; t += SGR_NT) {
+        const int i = t / a.w, j = t % a.w;
+        const int32_t u = (int32_t)tile[(i + 3) * tw + j + 3] << 4;
+        int32_t v = u << 7;
+        if (r0 > 0) v += a.xq0 * (a.flt0[t] - u);
+        if (r1 > 0) v += a.xq1 * (a.flt1[t] - u);
+        const int16_t wv = (int16_t)((v + (1 << 10)) >> 11);
+        a.out[t] = (uint16_t)(wv < 0 ? 0 : (wv > mx ? mx : wv));
+    }
+}
+
+struct WienerArgs {
+    const uint16_t *tile_in; // (h+7) x (w+7) packed samples, origin (3,3)
+    int w, h, bd, round_0, round_1;
+    int16_t fx[8], fy[8];
+    uint16_t *out; // w-strided
+};
+__global__ void __launch_bounds__(256) wiener_kernel(const WienerArgs a) {
+    extern __shared__ int32_t sm[];
+    const int tw = a.w + 7, ih = a.h + 7;
+    uint16_t *tile = reinterpret_cast<uint16_t *>(sm);
+    uint16_t *tmp = tile + tw * ih;
+    for (int i = threadIdx.x; i < tw * ih; i += blockDim.x) tile[i] = a.tile_in[i];
+    __syncthreads();
+    const int lim = (1 << (a.bd + 1 + 7 - a.round_0)) - 1;
+    for (int t = threadIdx.x; t < ih * a.w; t += blockDim.x) {
+        const int y = t / a.w, x = t % a.w;
+        int32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) sum += (int32_t)tile[y * tw + x + k] * a.fx[k];
+        sum += ((int32_t)tile[y * tw + x + 3] << 7) + (1 << (a.bd + 7 - 1));
+        const int32_t v = (sum + (1 << (a.round_0 - 1))) >> a.round_0;
+        tmp[t] = (uint16_t)(v < 0 ? 0 : (v > lim ? lim : v));
+    }
+    __syncthreads();
+    const int mx = (1 << a.bd) - 1;
+    for (int t = threadIdx.x; t < a.h * a.w; t += blockDim.x) {
+        const int y = t / a.w, x = t % a.w;
+        int32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) sum += (int32_t)tmp[(y + k) * a.w + x] * a.fy[k];
+        sum += ((int32_t)tmp[(y + 3) * a.w + x] << 7) - (1 << (a.bd + a.round_1 - 1));
+        int32_t v = (sum + (1 << (a.round_1 - 1))) >> a.round_1;
+        a.out[t] = (uint16_t)(v < 0 ? 0 : (v > mx ? mx : v));
+    }
+}
+
+static bool g_lr_attr = false;
+static void lr_attrs() {
+    if (g_lr_attr) return;
+    cudaFuncSetAttribute(sgr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(wiener_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    g_lr_attr = true;
+}
+
+// The reference passes high-bit-depth planes as CONVERT_TO_BYTEPTR(ptr) (= ptr >> 1): undo it like CONVERT_TO_SHORTPTR
+static inline const uint16_t *short_ptr(const uint8_t *p) { return (const uint16_t *)(((uintptr_t)p) << 1); }
+
+// gather a rim-extended rectangle into packed uint16
+static void gather(uint16_t *dst, const uint8_t *src8, int highbd, ptrdiff_t stride, int x0, int y0, int w, int h) {
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            const ptrdiff_t o = (ptrdiff_t)(y0 + y) * stride + x0 + x;
+            dst[(size_t)y * w + x] = highbd ? short_ptr(src8)[o] : src8[o];
+        }
+}
+
+static void sgr_run(const uint8_t *dat8, int width, int height, int stride, int eps, int bit_depth, int highbd, int32_t *flt0,
+                    int32_t *flt1, int flt_stride, const int32_t *xqd, uint8_t *dst8, int dst_stride) {
+    lr_attrs();
+    if ((size_t)(width + 6) * (height + 6) > 7396 + 2000 || width <= 0 || height <= 0 || eps < 0 || eps > 15) {
+        fprintf(stderr, "svt_av1_selfguided_restoration_cuda: unit %dx%d larger than a restoration processing unit\n", width, height);
+        abort();
+    }
+    ThreadCtx &c = tls();
+    const size_t tile_b = (size_t)(width + 6) * (height + 6) * 2, f_off = (tile_b + 15) & ~(size_t)15,
+                 fb = (size_t)width * height * 4, o_off = f_off + 2 * fb;
+    c.reserve(o_off + (size_t)width * height * 2);
+    gather((uint16_t *)c.h, dat8, highbd, stride, -3, -3, width + 6, height + 6);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.d, c.h, tile_b, cudaMemcpyHostToDevice, c.stream));
+    SgrArgs a;
+    a.tile_in = (const uint16_t *)c.d;
+    a.w = width;
+    a.h = height;
+    a.bd = bit_depth;
+    a.idx = eps;
+    a.flt0 = (int32_t *)(c.d + f_off);
+    a.flt1 = (int32_t *)(c.d + f_off + fb);
+    a.apply = xqd != nullptr;
+    a.xq0 = a.xq1 = 0;
+    if (xqd) { // svt_decode_xq
+        const int r0 = h_sgr_r[eps][0], r1 = h_sgr_r[eps][1];
+        if (r0 == 0) {
+            a.xq0 = 0;
+            a.xq1 = 128 - xqd[1];
+        } else if (r1 == 0) {
+            a.xq0 = xqd[0];
+            a.xq1 = 0;
+        } else {
+            a.xq0 = xqd[0];
+            a.xq1 = 128 - a.xq0 - xqd[1];
+        }
+    }
+    a.out = (uint16_t *)(c.d + o_off);
+    const size_t smem = (size_t)2 * (width + 2) * (height + 2) * 4 + tile_b + 16;
+    SVTB_LAUNCH(sgr_kernel, 1, SGR_NT, smem, c.stream, a);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h + f_off, c.d + f_off, 2 * fb + (size_t)width * height * 2, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_FATAL(cudaStreamSynchronize(c.stream));
+    if (!xqd) {
+        const int32_t *h0 = (const int32_t *)(c.h + f_off), *h1 = (const int32_t *)(c.h + f_off + fb);
+        for (int y = 0; y < height; y++) {
+            if (h_sgr_r[eps][0] > 0) memcpy(flt0 + (size_t)y * flt_stride, h0 + (size_t)y * width, (size_t)width * 4);
+            if (h_sgr_r[eps][1] > 0) memcpy(flt1 + (size_t)y * flt_stride, h1 + (size_t)y * width, (size_t)width * 4);
+        }
+    } else {
+        const uint16_t *ho = (const uint16_t *)(c.h + o_off);
+        for (int y = 0; y < height; y++)
+            for (int x = 0; x < width; x++) {
+                if (highbd)
+                    ((uint16_t *)short_ptr(dst8))[(ptrdiff_t)y * dst_stride + x] = ho[(size_t)y * width + x];
+                else
+                    dst8[(ptrdiff_t)y * dst_stride + x] = (uint8_t)ho[(size_t)y * width + x];
+            }
+    }
+}
+
+static void wiener_run(const uint8_t *src, ptrdiff_t src_stride, uint8_t *dst, ptrdiff_t dst_stride, const int16_t *filter_x,
+                       const int16_t *filter_y, int w, int h, int round_0, int round_1, int bd, int highbd) {
+    lr_attrs();
+    if (w <= 0 || h <= 0 || w > 128 || h > 128) {
+        fprintf(stderr, "svt_av1_wiener_convolve_add_src_cuda: %dx%d out of range\n", w, h);
+        abort();
+    }
+    ThreadCtx &c = tls();
+    const size_t tile_b = (size_t)(w + 7) * (h + 7) * 2, o_off = (tile_b + 15) & ~(size_t)15;
+    c.reserve(o_off + (size_t)w * h * 2);
+    gather((uint16_t *)c.h, src, highbd, src_stride, -3, -3, w + 7, h + 7);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.d, c.h, tile_b, cudaMemcpyHostToDevice, c.stream));
+    WienerArgs a;
+    a.tile_in = (const uint16_t *)c.d;
+    a.w = w;
+    a.h = h;
+    a.bd = bd;
+    a.round_0 = round_0;
+    a.round_1 = round_1;
+    // the reference recovers kernel + offset from a 256-byte aligned table (get_filter_base / get_filter_offset,
+    // convolve.c:49-57); with the x/y steps fixed at 16 that always resolves to the 8 taps pointed at
+    memcpy(a.fx, filter_x, 16);
+    memcpy(a.fy, filter_y, 16);
+    a.out = (uint16_t *)(c.d + o_off);
+    const size_t smem = tile_b + (size_t)(h + 7) * w * 2 + 16;
+    SVTB_LAUNCH(wiener_kernel, 1, 256, smem, c.stream, a);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h + o_off, c.d + o_off, (size_t)w * h * 2, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_FATAL(cudaStreamSynchronize(c.stream));
+    const uint16_t *ho = (const uint16_t *)(c.h + o_off);
+    for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+            if (highbd)
+                ((uint16_t *)short_ptr(dst))[(ptrdiff_t)y * dst_stride + x] = ho[(size_t)y * w + x];
+            else
+                dst[(ptrdiff_t)y * dst_stride + x] = (uint8_t)ho[(size_t)y * w + x];
+        }
+}
+
+} // namespace
+
+extern "C" {
+
+void svt_av1_selfguided_restoration_cuda(const uint8_t *dgd8, int32_t width, int32_t height, int32_t dgd_stride, int32_t *flt0,
+                                         int32_t *flt1, int32_t flt_stride, int32_t sgr_params_idx, int32_t bit_depth,
+                                         int32_t highbd) {
+    sgr_run(dgd8, width, height, dgd_stride, sgr_params_idx, bit_depth, highbd, flt0, flt1, flt_stride, nullptr, nullptr, 0);
+}
+void svt_apply_selfguided_restoration_cuda(const uint8_t *dat, int32_t width, int32_t height, int32_t stride, int32_t eps,
+                                           const int32_t *xqd, uint8_t *dst, int32_t dst_stride, int32_t *tmpbuf,
+                                           int32_t bit_depth, int32_t highbd) {
+    (void)tmpbuf;
+    sgr_run(dat, width, height, stride, eps, bit_depth, highbd, nullptr, nullptr, 0, xqd, dst, dst_stride);
+}
+// conv_params: the reference's ConvolveParams; only round_0 / round_1 are read (offsets 20 and 24 of the struct,
+// EbDefinitions.h:379-392) — passed as a pointer to keep the RTCD signature
+struct ConvolveParamsView {
+    int32_t ref, do_average;
+    void *dst;
+    int32_t dst_stride, round_0, round_1;
+};
+void svt_av1_wiener_convolve_add_src_cuda(const uint8_t *src, ptrdiff_t src_stride, uint8_t *dst, ptrdiff_t dst_stride,
+                                          const int16_t *filter_x, const int16_t *filter_y, int32_t w, int32_t h,
+                                          const void *conv_params) {
+    const ConvolveParamsView *cp = (const ConvolveParamsView *)conv_params;
+    wiener_run(src, src_stride, dst, dst_stride, filter_x, filter_y, w, h, cp->round_0, cp->round_1, 8, 0);
+}
+void svt_av1_highbd_wiener_convolve_add_src_cuda(const uint8_t *src, ptrdiff_t src_stride, uint8_t *dst, ptrdiff_t dst_stride,
+                                                 const int16_t *filter_x, const int16_t *filter_y, int32_t w, int32_t h,
+                                                 const void *conv_params, int32_t bd) {
+    const ConvolveParamsView *cp = (const ConvolveParamsView *)conv_params;
+    wiener_run(src, src_stride, dst, dst_stride, filter_x, filter_y, w, h, cp->round_0, cp->round_1, bd, 1);
+}
+}
