@@ -290,7 +290,8 @@ def run_b200(args):
     me_params = sb.preset8_me_params(W, H, N_L0, N_L1, DIST, 2, 1)
     n_sb = ((W + 63) // 64) * ((H + 63) // 64)
     nfb = n_sb
-    sets = [DeviceSet(torch, 1234 + rank, 5 * k) for k in range(RING)]
+    import sharding
+    sets = [DeviceSet(torch, sharding.stream_seed(1234, rank), 5 * k) for k in range(RING)]
     part, flat, skip8 = partition_and_mi(7)
     h_mi = torch.from_numpy(np.frombuffer(flat, dtype=np.uint8).copy()).pin_memory()
     d_mi = h_mi.cuda()
@@ -424,10 +425,7 @@ def run_b200(args):
         barrier()
         ms = e0.elapsed_time(e1)
         launches = lib.svt_b200_launch_count() - l0
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
+        ms = sharding.reduce_max_ms(ms, "cuda")
         return ms, launches
 
     sampler = ClockSampler(local)

@@ -293,7 +293,14 @@ SVT_B200_API void svt_residual_kernel16bit_cuda(uint16_t *input, uint32_t input_
 #define SVT_B200_DECL_FWD(W, H)                                                                      \
     SVT_B200_API void svt_av1_fwd_txfm2d_##W##x##H##_cuda(int16_t *input, int32_t *output,           \
                                                           uint32_t input_stride, int32_t tx_type,    \
-                                                          uint8_t bit_depth);
+                                                          uint8_t bit_depth);                        \
+    /* partial-frequency shapes svt_av1_fwd_txfm2d_WxH_N2 / _N4 (aom_dsp_rtcd.h:150-216) */           \
+    SVT_B200_API void svt_av1_fwd_txfm2d_##W##x##H##_N2_cuda(int16_t *input, int32_t *output,        \
+                                                             uint32_t input_stride, int32_t tx_type, \
+                                                             uint8_t bit_depth);                     \
+    SVT_B200_API void svt_av1_fwd_txfm2d_##W##x##H##_N4_cuda(int16_t *input, int32_t *output,        \
+                                                             uint32_t input_stride, int32_t tx_type, \
+                                                             uint8_t bit_depth);
 SVT_B200_DECL_FWD(4, 4) SVT_B200_DECL_FWD(8, 8) SVT_B200_DECL_FWD(16, 16) SVT_B200_DECL_FWD(32, 32)
 SVT_B200_DECL_FWD(64, 64) SVT_B200_DECL_FWD(4, 8) SVT_B200_DECL_FWD(8, 4) SVT_B200_DECL_FWD(8, 16)
 SVT_B200_DECL_FWD(16, 8) SVT_B200_DECL_FWD(16, 32) SVT_B200_DECL_FWD(32, 16) SVT_B200_DECL_FWD(32, 64)

@@ -60,6 +60,8 @@ ORC_API void orc_fadst(int32_t *x, int stride, int n, int cos_bit);
 ORC_API void orc_iadst(int32_t *x, int stride, int n, int cos_bit, int clamp_bit);
 ORC_API void orc_fidentity(int32_t *x, int stride, int n);
 ORC_API void orc_fwd_txfm2d(const int16_t *input, int32_t *output, uint32_t stride, int tx_type, int tx_size, int bit_depth);
+ORC_API void orc_fwd_txfm2d_pf(const int16_t *input, int32_t *output, uint32_t stride, int tx_type, int tx_size,
+                               int bit_depth, int shift);
 ORC_API uint64_t orc_handle_transform64(int32_t *output, int tx_size);
 ORC_API void orc_inv_txfm2d_add(const int32_t *input, const uint16_t *pred, int32_t stride_r, uint16_t *recon,
                                 int32_t stride_w, int tx_type, int tx_size, int bd);

@@ -407,6 +407,16 @@ void orc_fwd_txfm2d(const int16_t *input, int32_t *output, uint32_t stride, int 
     free(buf);
 }
 
+/* Partial-frequency variants (N2 / N4 shapes, EbTransforms.c:5401-5648, 7007-7250): the reference's N2/N4 cores
+ * compute exactly the top-left (w>>s) x (h>>s) coefficients of the full transform and zero the rest. */
+void orc_fwd_txfm2d_pf(const int16_t *input, int32_t *output, uint32_t stride, int tx_type, int tx_size, int bit_depth,
+                       int shift) {
+    orc_fwd_txfm2d(input, output, stride, tx_type, tx_size, bit_depth);
+    const int w = k_txw[tx_size], h = k_txh[tx_size];
+    for (int i = 0; i < w * h; i++)
+        if (i % w >= (w >> shift) || i / w >= (h >> shift)) output[i] = 0;
+}
+
 /* svt_handle_transform64x64/64x32/32x64/64x16/16x64 (EbTransforms.c:2763-2931): energy of the discarded
  * area, zero it, and re-pack the kept 32-wide coefficients contiguously. Returns the energy. */
 uint64_t orc_handle_transform64(int32_t *output, int tx_size) {

@@ -83,6 +83,7 @@ struct FwdArgs {
     int32_t *out; // block b at out + b * w*h
     const int32_t *tx_types; // per block (device) or null -> tx_type
     int tx_type, tx_size, n_blocks;
+    int pf_shift; // 0 full, 1 N2, 2 N4: keep only the top-left (w>>s) x (h>>s) coefficients (EbTransforms.c:5401,7007)
     int repack64; // 1: svt_handle_transform* semantics (zero the dropped area, pack 32-wide, energy -> energy[b])
     uint64_t *energy;
 };
@@ -130,7 +131,8 @@ __global__ void __launch_bounds__(TX_NT) fwd_txfm_kernel(const FwdArgs a) {
     if (live) {
         int32_t *dst = a.out + (size_t)b * w * h;
         if (!a.repack64) {
-            for (int i = li; i < w * h; i += T) dst[i] = buf[(i / w) * pitch + (i % w)];
+            const int kw2 = w >> a.pf_shift, kh2 = h >> a.pf_shift;
+            for (int i = li; i < w * h; i += T) dst[i] = ((i % w) < kw2 && (i / w) < kh2) ? buf[(i / w) * pitch + (i % w)] : 0;
         } else {
             // svt_handle_transform* (EbTransforms.c:2763-2931): energy of the dropped area, zero it, then re-pack the
             // kept 32-wide rows to the front.  Entries behind the packed block keep what the in-place C code leaves.
@@ -459,7 +461,7 @@ static void tx_attrs() {
 
 // ---- host side of the drop-ins --------------------------------------------------------------------------------
 static void fwd_dropin(int16_t *input, int32_t *output, uint32_t stride, int tx_type, int tx_size, int repack,
-                       uint64_t *energy_out) {
+                       uint64_t *energy_out, int pf_shift = 0) {
     txfm_tables_init();
     tx_attrs();
     const int w = h_txw[tx_size], h = h_txh[tx_size];
@@ -479,6 +481,7 @@ static void fwd_dropin(int16_t *input, int32_t *output, uint32_t stride, int tx_
     a.tx_size = tx_size;
     a.n_blocks = 1;
     a.repack64 = repack;
+    a.pf_shift = pf_shift;
     a.energy = (uint64_t *)(c.d + e_off);
     SVTB_LAUNCH(fwd_txfm_kernel, 1, TX_NT, tx_smem_bytes(tx_size), c.stream, a);
     SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h + out_off, c.d + out_off, (size_t)w * h * 4 + 16, cudaMemcpyDeviceToHost, c.stream));
@@ -566,6 +569,16 @@ extern "C" {
                                              uint8_t bit_depth) {                                                 \
         (void)bit_depth;                                                                                          \
         fwd_dropin(input, output, input_stride, tx_type, TXS, 0, nullptr);                                        \
+    }                                                                                                             \
+    void svt_av1_fwd_txfm2d_##W##x##H##_N2_cuda(int16_t *input, int32_t *output, uint32_t input_stride,           \
+                                                int32_t tx_type, uint8_t bit_depth) {                             \
+        (void)bit_depth;                                                                                          \
+        fwd_dropin(input, output, input_stride, tx_type, TXS, 0, nullptr, 1);                                     \
+    }                                                                                                             \
+    void svt_av1_fwd_txfm2d_##W##x##H##_N4_cuda(int16_t *input, int32_t *output, uint32_t input_stride,           \
+                                                int32_t tx_type, uint8_t bit_depth) {                             \
+        (void)bit_depth;                                                                                          \
+        fwd_dropin(input, output, input_stride, tx_type, TXS, 0, nullptr, 2);                                     \
     }
 FWD_DROPIN(4, 4, 0)
 FWD_DROPIN(8, 8, 1)

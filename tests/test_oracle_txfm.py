@@ -245,3 +245,23 @@ def test_residual_matches_reference():
             orc.orc_residual(cm.ptr(a), C.c_uint32(w + 4), cm.ptr(b), C.c_uint32(w + 6), cm.ptr(r1), C.c_uint32(w + 2),
                              C.c_uint32(w), C.c_uint32(h), hbd)
             np.testing.assert_array_equal(r0, r1)
+
+
+@needs_ref
+@pytest.mark.parametrize("tx_size", range(19))
+def test_partial_frequency_fwd_txfm_matches_reference(tx_size):
+    """N2 / N4 shapes: the reference's *_N2_c / *_N4_c functions vs 'full transform + zeroing' (what its own
+    test/FwdTxfm2dAsmTest.cc:257-283 asserts for the SIMD versions)."""
+    ref, orc = cm.ref(), cm.oracle()
+    w, h = TX_W[tx_size], TX_H[tx_size]
+    rng = np.random.default_rng(50 + tx_size)
+    for shape, sh in (("N2", 1), ("N4", 2)):
+        name = (f"av1_transform_two_d_{w}x{h}_{shape}_c" if w == h else f"svt_av1_fwd_txfm2d_{w}x{h}_{shape}_c")
+        f = getattr(ref, name)
+        for bd in (8, 10):
+            for tx_type in allowed_types(tx_size):
+                res = residual_block(rng, w, h, bd, "rand")
+                want, got = np.full(w * h, 5, np.int32), np.zeros(w * h, np.int32)
+                f(cm.ptr(res), cm.ptr(want), C.c_uint32(w + 5), tx_type, C.c_uint8(bd))
+                orc.orc_fwd_txfm2d_pf(cm.ptr(res), cm.ptr(got), C.c_uint32(w + 5), tx_type, tx_size, bd, sh)
+                np.testing.assert_array_equal(got, want, err_msg=f"{name} type {tx_type} bd {bd}")

@@ -236,3 +236,18 @@ def test_encode_tus_1080p_16x16_and_roundtrip_property():
     again_rec, again_q, again_eob = gr.run_gpu_encode_tus(p, src, pred, tus)
     np.testing.assert_array_equal(again_q, got_q)
     np.testing.assert_array_equal(again_rec.plane(0), got_rec.plane(0))
+
+
+@pytest.mark.parametrize("tx_size", range(19))
+def test_partial_frequency_dropins(tx_size):
+    lib, orc = sb.load(), cm.oracle()
+    w, h = TX_W[tx_size], TX_H[tx_size]
+    rng = np.random.default_rng(70 + tx_size)
+    for shape, sh in (("N2", 1), ("N4", 2)):
+        f = getattr(lib, f"svt_av1_fwd_txfm2d_{w}x{h}_{shape}_cuda")
+        for tx_type in allowed_types(tx_size)[:6]:
+            res = residual_block(rng, w, h, 10, "rand")
+            want, got = np.zeros(w * h, np.int32), np.full(w * h, 3, np.int32)
+            orc.orc_fwd_txfm2d_pf(cm.ptr(res), cm.ptr(want), C.c_uint32(w + 5), tx_type, tx_size, 10, sh)
+            f(cm.ptr(res), cm.ptr(got), C.c_uint32(w + 5), tx_type, C.c_uint8(10))
+            np.testing.assert_array_equal(got, want)
