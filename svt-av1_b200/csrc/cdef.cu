@@ -75,6 +75,56 @@ __device__ __forceinline__ int cdef_sample(const int16_t *in, int s, int pri, in
     return min(max(y, mn), mx);
 }
 
+// Search-kernel variant of cdef_sample with everything that is constant over a block hoisted by the caller:
+// tap offsets for the block's direction, damping shifts, tap weights.  kBorder = false is used for filter blocks
+// that do not touch the frame edge (no CDEF_VERY_LARGE samples in the tile): the "!= VERY_LARGE" tests vanish.
+struct CdefTaps {
+    int po[2], o2[2], o6[2];
+    int pt0, pt1, psh, ssh;
+};
+__device__ __forceinline__ CdefTaps make_taps(int pri, int sec, int dir, int pri_damping, int sec_damping, int coeff_shift, int s) {
+    CdefTaps t;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        t.po[k] = c_dir[dir][k][0] * s + c_dir[dir][k][1];
+        t.o2[k] = c_dir[(dir + 2) & 7][k][0] * s + c_dir[(dir + 2) & 7][k][1];
+        t.o6[k] = c_dir[(dir + 6) & 7][k][0] * s + c_dir[(dir + 6) & 7][k][1];
+    }
+    const int odd = (pri >> coeff_shift) & 1;
+    t.pt0 = odd ? 3 : 4;
+    t.pt1 = odd ? 3 : 2;
+    t.psh = pri ? max(0, pri_damping - msb((uint32_t)pri)) : 0;
+    t.ssh = sec ? max(0, sec_damping - msb((uint32_t)sec)) : 0;
+    return t;
+}
+template <bool kBorder>
+__device__ __forceinline__ int cdef_px(const int16_t *in, const CdefTaps &t, int pri, int sec) {
+    const int x = in[0];
+    int sum = 0, mx = x, mn = x;
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int p0 = in[t.po[k]], p1 = in[-t.po[k]];
+        const int s0 = in[t.o2[k]], s1 = in[-t.o2[k]], s2 = in[t.o6[k]], s3 = in[-t.o6[k]];
+        if (pri) sum += (k ? t.pt1 : t.pt0) * (constrain_s(p0 - x, pri, t.psh) + constrain_s(p1 - x, pri, t.psh));
+        if (sec)
+            sum += (k ? 1 : 2) * (constrain_s(s0 - x, sec, t.ssh) + constrain_s(s1 - x, sec, t.ssh) + constrain_s(s2 - x, sec, t.ssh) +
+                                  constrain_s(s3 - x, sec, t.ssh));
+        mn = min(mn, min(min(p0, p1), min(min(s0, s1), min(s2, s3))));
+        if (kBorder) {
+            if (p0 != VERY_LARGE) mx = max(mx, p0);
+            if (p1 != VERY_LARGE) mx = max(mx, p1);
+            if (s0 != VERY_LARGE) mx = max(mx, s0);
+            if (s1 != VERY_LARGE) mx = max(mx, s1);
+            if (s2 != VERY_LARGE) mx = max(mx, s2);
+            if (s3 != VERY_LARGE) mx = max(mx, s3);
+        } else {
+            mx = max(mx, max(max(p0, p1), max(max(s0, s1), max(s2, s3))));
+        }
+    }
+    const int y = x + ((8 + sum - (sum < 0)) >> 4);
+    return min(max(y, mn), mx);
+}
+
 // svt_cdef_find_dir_c on an 8x8 block of an int16 tile (serial; one thread per block)
 __device__ int find_dir(const int16_t *img, int stride, int *var, int coeff_shift) {
     const int div_table[9] = {0, 840, 420, 280, 210, 168, 140, 120, 105};
@@ -191,6 +241,8 @@ __global__ void __launch_bounds__(NT) cdef_search_kernel(const __grid_constant__
     const SvtB200CdefSearchParams &p = d.p;
     const int nvb = min(16, p.mi_rows - 16 * fbr), nhb = min(16, p.mi_cols - 16 * fbc);
     const int cs = d.coeff_shift;
+    // does the +2 rim of this filter block reach outside the frame (CDEF_VERY_LARGE samples present)?
+    const bool border = fbr == 0 || fbc == 0 || 16 * (fbr + 1) >= p.mi_rows || 16 * (fbc + 1) >= p.mi_cols;
     uint64_t *out_y = d.mse + ((size_t)fb) * 64;
     uint64_t *out_c = d.mse + ((size_t)d.nvfb * d.nhfb + fb) * 64;
     if (tid == 0) { // svt_sb_compute_cdef_list: raster list of the non-skip 8x8 blocks
@@ -249,8 +301,10 @@ __global__ void __launch_bounds__(NT) cdef_search_kernel(const __grid_constant__
                     const int dir = pri ? s_dir[b] : 0;
                     const int16_t *q = in + (by * bs + row) * TS + bx * bs;
                     const size_t so = (size_t)(y0 + by * bs + row) * sstride + x0 + bx * bs;
+                    const bool ident = t == 0 && sec == 0;
+                    const CdefTaps taps = make_taps(t, sec, dir, damping, damping, cs, TS);
                     for (int j = 0; j < bs; j++) {
-                        const int f = cdef_sample(q + j, TS, t, sec, dir, damping, damping, cs);
+                        const int f = ident ? (int)q[j] : (border ? cdef_px<true>(q + j, taps, t, sec) : cdef_px<false>(q + j, taps, t, sec));
                         const int o = ldpx<T>(sp, so + j);
                         if (pli == 0) {
                             ss += f;

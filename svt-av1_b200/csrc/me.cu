@@ -44,6 +44,25 @@ __device__ __forceinline__ void clamp_window(int origin, int pad, int pic_size, 
 }
 __device__ __forceinline__ int scaled_dist(int dist) { return ((dist * 5) / 8) + ((dist % 8) == 0 ? 0 : 1); }
 
+// Stage `rows` rows of `nbytes` bytes (arbitrary alignment, global) into shared-memory words of pitch `wpw`:
+// one warp per row, one lane per 32-bit word, aligned LDG + funnel shift instead of byte loads.  Only the aligned
+// words that overlap [src, src + nbytes) are read (at most 3 bytes of over-read, inside the padded planes).
+template <int NT>
+__device__ __forceinline__ void stage_rows(uint32_t *dst, int wpw, const uint8_t *__restrict__ src, ptrdiff_t stride, int rows,
+                                           int nbytes) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int row = warp; row < rows; row += NT / 32) {
+        const uintptr_t a = (uintptr_t)(src + (ptrdiff_t)row * stride);
+        const uint32_t *ga = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        const int sh = (int)(a & 3) * 8;
+        const int need = (nbytes + (int)(a & 3) + 3) >> 2; // aligned words covering the row
+        for (int wd = lane; wd < wpw; wd += 32) {
+            const uint32_t lo = wd < need ? ga[wd] : 0u, hi = (wd + 1) < need ? ga[wd + 1] : 0u;
+            dst[row * wpw + wd] = __funnelshift_r(lo, hi, sh);
+        }
+    }
+}
+
 // -----------------------------------------------------------------------------------------------------
 // Block-cooperative exhaustive search of one bw x bh block over a saw x sah window (svt_sad_loop_kernel).
 // `ref` points at search position (0,0); reference row of block row r at search row ys is
@@ -356,22 +375,11 @@ __device__ void hme_level_search(const uint8_t *__restrict__ src, int src_stride
     const int spw = (bw + 3) >> 2;
     uint32_t *s_src = smem;
     const uint32_t tail_mask = (bw & 3) ? ((1u << (8 * (bw & 3))) - 1u) : 0xffffffffu;
-    { // stage the source block once for all jobs
-        uint8_t *sbp = reinterpret_cast<uint8_t *>(s_src);
-        for (int i = tid; i < bh * spw * 4; i += NT) {
-            int r = i / (spw * 4), c = i - r * (spw * 4);
-            sbp[i] = c < bw ? src[(size_t)r * src_stride + c] : 0;
-        }
-    }
+    stage_rows<NT>(s_src, spw, src, src_stride, bh, bw); // the source block, once for all jobs
     const int span = (bh - 1) * k + 1;
     for (int j = 0; j < njobs; j++) {
         const HmeJob jb = jobs[j];
-        uint8_t *wb = reinterpret_cast<uint8_t *>(smem + jb.woff);
-        const int rb = jb.wpw * 4, wbytes = jb.saw - 1 + bw, rows = jb.sah - 1 + span;
-        for (int i = tid; i < rows * rb; i += NT) {
-            int r = i / rb, c = i - r * rb;
-            wb[i] = c < wbytes ? jb.ref[(size_t)r * raw_stride + c] : 0;
-        }
+        stage_rows<NT>(smem + jb.woff, jb.wpw, jb.ref, raw_stride, jb.sah - 1 + span, jb.saw - 1 + bw);
     }
     __syncthreads();
     for (int j = 0; j < njobs; j++) {
@@ -636,13 +644,7 @@ __global__ void __launch_bounds__(NT_SEARCH) fullpel_kernel(const __grid_constan
     const int nrows_src = sub ? 32 : 64;
     uint32_t *s_src = smem; // [nrows_src][16 words]
     uint32_t *s_win = smem + nrows_src * 16;
-    {
-        uint8_t *sbp = reinterpret_cast<uint8_t *>(s_src);
-        for (int i = tid; i < nrows_src * 64; i += NT_SEARCH) {
-            int rr = i >> 6, c = i & 63;
-            sbp[i] = srcb[(size_t)(sub ? 2 * rr : rr) * fp.stride + c];
-        }
-    }
+    stage_rows<NT_SEARCH>(s_src, 16, srcb, (ptrdiff_t)(sub ? 2 : 1) * fp.stride, nrows_src, 64);
     const int span = sub ? 63 : 64;
     const int wbytes = saw + 63;
     const int wpw = ((wbytes + 3) >> 2) + 1;
@@ -657,15 +659,7 @@ __global__ void __launch_bounds__(NT_SEARCH) fullpel_kernel(const __grid_constan
         const int cr = min(chunk, sah - y0);
         const int rows = cr - 1 + span;
         __syncthreads();
-        {
-            uint8_t *wb = reinterpret_cast<uint8_t *>(s_win);
-            const int rb = wpw * 4;
-            const uint8_t *g = refb + (ptrdiff_t)(yo + y0) * fp.stride + xo;
-            for (int i = tid; i < rows * rb; i += NT_SEARCH) {
-                int rr = i / rb, c = i - rr * rb;
-                wb[i] = c < wbytes ? g[(ptrdiff_t)rr * fp.stride + c] : 0;
-            }
-        }
+        stage_rows<NT_SEARCH>(s_win, wpw, refb + (ptrdiff_t)(yo + y0) * fp.stride + xo, fp.stride, rows, wbytes);
         for (int i = tid; i < 85; i += NT_SEARCH) s_cbest[i] = 0xffffffffu;
         __syncthreads();
         const int nquads = cr * nq;
