@@ -339,9 +339,14 @@ def run_b200(args):
     def planes(tl):
         return sb.MePlanes(tl[0].data_ptr(), tl[1].data_ptr(), tl[2].data_ptr())
 
-    def hot_path(me_dev, src_dev, pred_dev, mi_dev, skip_dev, idx_dev, e2e=False):
+    def hot_path(me_dev, src_dev, pred_dev, mi_dev, skip_dev, idx_dev, e2e=False, only=None):
         for i in range(F):
             f = i + 2
+            fs, fp, fr = frame_struct(sb, proto, src_dev[f]), frame_struct(sb, proto, pred_dev[f]), frame_struct(sb, proto, d_rec[i])
+            fo = frame_struct(sb, proto, d_out[i])
+            if only is not None:
+                stage_call(only, i, f, me_dev, fs, fp, fr, fo, mi_dev, skip_dev, idx_dev)
+                continue
             # 1. ME
             r = [me_dev[f - 1], me_dev[f - 2], me_dev[f - 2], me_dev[f - 2], me_dev[f + 1], me_dev[f + 2], me_dev[f + 2], me_dev[f + 2]]
             refs = (sb.MePlanes * 8)(*[planes(x) for x in r])
@@ -351,7 +356,6 @@ def run_b200(args):
                                 o["me_cand"].data_ptr(), o["total_cand"].data_ptr(), o["rc"].data_ptr())
             sb.check(lib.svt_b200_me_picture(C.byref(me_params), C.byref(s), refs, C.byref(outs), me_scratch[i].data_ptr(), sp), lib)
             # 2. EncDec final pass (fused per TU)
-            fs, fp, fr = frame_struct(sb, proto, src_dev[f]), frame_struct(sb, proto, pred_dev[f]), frame_struct(sb, proto, d_rec[i])
             for ts in tus:
                 sb.check(lib.svt_b200_encode_tus(C.byref(enc_params[ts]), C.byref(fs), C.byref(fp), C.byref(fr),
                                                  C.c_void_p(tu_dev[ts].data_ptr()), len(tus[ts]), C.c_void_p(d_q[i][ts].data_ptr()),
@@ -370,7 +374,30 @@ def run_b200(args):
                 h_idx.numpy()[...] = np.argmin(m[0, :, :8], axis=1).astype(np.int8)
                 with torch.cuda.stream(stream):
                     idx_dev.copy_(h_idx, non_blocking=True)
-            fo = frame_struct(sb, proto, d_out[i])
+            sb.check(lib.svt_b200_cdef_apply(C.byref(cap), C.byref(fr), C.byref(fo), C.c_void_p(skip_dev.data_ptr()), skip8.shape[1],
+                                             C.c_void_p(idx_dev.data_ptr()), sp), lib)
+
+    def stage_call(name, i, f, me_dev, fs, fp, fr, fo, mi_dev, skip_dev, idx_dev):
+        """One stage of one frame (used by the per-stage roofline timing)."""
+        if name == "me":
+            r = [me_dev[f - 1], me_dev[f - 2], me_dev[f - 2], me_dev[f - 2], me_dev[f + 1], me_dev[f + 2], me_dev[f + 2], me_dev[f + 2]]
+            refs = (sb.MePlanes * 8)(*[planes(x) for x in r])
+            s = planes(me_dev[f])
+            o = d_me[i]
+            outs = sb.MeOutputs(o["best_sad"].data_ptr(), o["best_mv"].data_ptr(), o["hme"].data_ptr(), o["me_mv"].data_ptr(),
+                                o["me_cand"].data_ptr(), o["total_cand"].data_ptr(), o["rc"].data_ptr())
+            sb.check(lib.svt_b200_me_picture(C.byref(me_params), C.byref(s), refs, C.byref(outs), me_scratch[i].data_ptr(), sp), lib)
+        elif name == "encdec":
+            for ts in tus:
+                sb.check(lib.svt_b200_encode_tus(C.byref(enc_params[ts]), C.byref(fs), C.byref(fp), C.byref(fr),
+                                                 C.c_void_p(tu_dev[ts].data_ptr()), len(tus[ts]), C.c_void_p(d_q[i][ts].data_ptr()),
+                                                 C.c_void_p(d_eob[i][ts].data_ptr()), C.c_void_p(enc_scratch.data_ptr()), sp), lib)
+        elif name == "dlf":
+            sb.check(lib.svt_b200_dlf_frame(C.byref(dlp), C.byref(fr), C.c_void_p(mi_dev.data_ptr()), sp), lib)
+        elif name == "cdef_search":
+            sb.check(lib.svt_b200_cdef_search(C.byref(csp), C.byref(fr), C.byref(fs), C.c_void_p(skip_dev.data_ptr()), skip8.shape[1],
+                                              C.c_void_p(d_mse[i].data_ptr()), sp), lib)
+        elif name == "cdef_apply":
             sb.check(lib.svt_b200_cdef_apply(C.byref(cap), C.byref(fr), C.byref(fo), C.c_void_p(skip_dev.data_ptr()), skip8.shape[1],
                                              C.c_void_p(idx_dev.data_ptr()), sp), lib)
 
@@ -454,41 +481,50 @@ def run_b200(args):
 
 
 def stage_breakdown(torch, lib, sb, hot_path, s, d_mi, d_skip, d_idx, stream):
-    """Per-stage device time of one frame (CUDA events on the launch stream around each stage group, warm, averaged):
-    re-issues the same calls as hot_path for frame 0 with events between the stages."""
-    # monkey-free approach: time cumulative prefixes by calling the library entry points directly is verbose; instead time
-    # the whole frame loop F frames and the launch list (profiles/) gives the per-kernel shares. Here: whole step / F.
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(2):
-        hot_path(s.me_dev, s.src_dev, s.pred_dev, d_mi, d_skip, d_idx)
-    torch.cuda.synchronize()
-    e0.record(stream)
-    n = 5
-    for _ in range(n):
-        hot_path(s.me_dev, s.src_dev, s.pred_dev, d_mi, d_skip, d_idx)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    return {"all_stages": e0.elapsed_time(e1) / (n * FRAMES_PER_STEP)}
+    """Per-stage device time per frame: each stage's launches alone, back to back over the mini-GOP's frames, CUDA
+    events on the launch stream, warm (3 untimed passes), averaged over 5 passes."""
+    out = {}
+    for name in (None, "me", "encdec", "dlf", "cdef_search", "cdef_apply"):
+        for _ in range(3):
+            hot_path(s.me_dev, s.src_dev, s.pred_dev, d_mi, d_skip, d_idx, only=name)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        n = 5
+        for _ in range(n):
+            hot_path(s.me_dev, s.src_dev, s.pred_dev, d_mi, d_skip, d_idx, only=name)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        out[name or "all_stages"] = e0.elapsed_time(e1) / (n * FRAMES_PER_STEP)
+    return out
 
 
 def roofline(stage_ms, pk, pk_kind, n_sb):
-    """Algorithmic HBM bytes of one frame through the four stages (DESIGN.md §Measurement lists the per-stage terms)
-    over the measured per-frame device time."""
+    """Algorithmic HBM bytes per frame of every stage over its measured device time; the top-level
+    fields describe the dominant stage, `stages` lists all of them."""
     luma, chroma = W * H, 2 * (W // 2) * (H // 2)
     samples = luma + chroma
     me_planes = (W + 136) * (H + 136) + (W // 2 + 64) * (H // 2 + 64) + (W // 4 + 32) * (H // 4 + 32)
-    me = me_planes * (1 + N_L0 + N_L1) + n_sb * (85 * 7 * 4 + 85 * 23 + 85 + 4) + n_sb * 8 * 85 * 8
-    encdec = samples * (1 + 1 + 4 + 1)  # src + pred in, qcoeff (int32) + recon out: 7 B/sample
-    dlf = samples * 2 * 2 + (H // 4) * (W // 4) * 16  # two passes, read + write, + the mi summary
-    cdef = samples * 2 + samples * 2  # search: recon + source; apply: recon in, out
-    alg = me + encdec + dlf + cdef
-    ms = stage_ms["all_stages"]
-    ach = alg / (ms / 1e3) / 1e9
-    return {"kernel": "whole hot path of one frame (14 launches; the launch list in profiles/ gives each kernel's share)",
-            "bound": "hbm", "achieved": ach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach / pk["hbm_gbs"], "traffic": None,
-            "peak_source": pk_kind, "algorithmic_bytes_per_frame": int(alg), "ms_per_frame": ms,
-            "note": "ME and the CDEF strength search are integer-ALU/shared-memory bound (SURVEY §8d); per-kernel HBM "
-                    "fractions are in profiles/"}
+    alg = {
+        "me": me_planes * (1 + N_L0 + N_L1) + n_sb * (85 * 7 * 4 + 85 * 23 + 85 + 4) + n_sb * 8 * 85 * 8,
+        "encdec": samples * (1 + 1 + 4 + 1),  # src + pred in, qcoeff (int32) + recon out: 7 B/sample
+        "dlf": samples * 2 * 2 + (H // 4) * (W // 4) * 16,  # two passes, read + write, + the mi summary
+        "cdef_search": samples * 2 + n_sb * 2 * 64 * 8,  # recon + source in, mse table out
+        "cdef_apply": samples * 2,
+    }
+    bound = {"me": "integer ALU / shared memory (VABSDIFF4 issue rate)", "encdec": "shared-memory butterflies, then HBM",
+             "dlf": "hbm", "cdef_search": "integer ALU (10 filters per sample)", "cdef_apply": "hbm"}
+    stages = []
+    for k, b in alg.items():
+        ach = b / (stage_ms[k] / 1e3) / 1e9
+        stages.append({"stage": k, "ms_per_frame": stage_ms[k], "algorithmic_bytes": int(b), "achieved": ach,
+                       "frac": ach / pk["hbm_gbs"], "binding": bound[k]})
+    dom = max(stages, key=lambda x: x["ms_per_frame"])
+    return {"kernel": "stage '%s' (dominant; its kernels are listed in profiles/)" % dom["stage"], "bound": "hbm",
+            "achieved": dom["achieved"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": dom["frac"], "traffic": None,
+            "peak_source": pk_kind, "stages": stages,
+            "note": "ME and the CDEF strength search are integer-ALU/shared-memory bound (SURVEY §8d): their HBM fraction is "
+                    "legitimately small; the streaming stages (dlf, cdef_apply, encdec) are the HBM-bound ones"}
 
 
 def cpu_baseline():

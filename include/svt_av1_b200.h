@@ -469,6 +469,55 @@ SVT_B200_API void svt_av1_highbd_wiener_convolve_add_src_cuda(const uint8_t *src
                                                               const int16_t *filter_y, int32_t w, int32_t h,
                                                               const void *conv_params, int32_t bd);
 
+/* =============================================================================================== */
+/* Small reductions around the transform chain + the single-position SAD family (RTCD drop-ins)    */
+/* =============================================================================================== */
+/* replace svt_aom_subtract_block / svt_aom_highbd_subtract_block (common_dsp_rtcd.h:241,243) */
+SVT_B200_API void svt_aom_subtract_block_cuda(int rows, int cols, int16_t *diff_ptr, ptrdiff_t diff_stride,
+                                              const uint8_t *src_ptr, ptrdiff_t src_stride, const uint8_t *pred_ptr,
+                                              ptrdiff_t pred_stride);
+SVT_B200_API void svt_aom_highbd_subtract_block_cuda(int rows, int cols, int16_t *diff_ptr, ptrdiff_t diff_stride,
+                                                     const uint8_t *src_ptr, ptrdiff_t src_stride,
+                                                     const uint8_t *pred_ptr, ptrdiff_t pred_stride, int bd);
+/* replace svt_full_distortion_kernel32_bits / _cbf_zero32_bits / svt_spatial_full_distortion_kernel /
+ * svt_full_distortion_kernel16_bits (common_dsp_rtcd.h:172-179) */
+SVT_B200_API void svt_full_distortion_kernel32_bits_cuda(int32_t *coeff, uint32_t coeff_stride, int32_t *recon_coeff,
+                                                         uint32_t recon_coeff_stride, uint64_t distortion_result[2],
+                                                         uint32_t area_width, uint32_t area_height);
+SVT_B200_API void svt_full_distortion_kernel_cbf_zero32_bits_cuda(int32_t *coeff, uint32_t coeff_stride,
+                                                                  uint64_t distortion_result[2], uint32_t area_width,
+                                                                  uint32_t area_height);
+SVT_B200_API uint64_t svt_spatial_full_distortion_kernel_cuda(uint8_t *input, uint32_t input_offset,
+                                                              uint32_t input_stride, uint8_t *recon,
+                                                              int32_t recon_offset, uint32_t recon_stride,
+                                                              uint32_t area_width, uint32_t area_height);
+SVT_B200_API uint64_t svt_full_distortion_kernel16_bits_cuda(uint8_t *input, uint32_t input_offset,
+                                                             uint32_t input_stride, uint8_t *recon,
+                                                             int32_t recon_offset, uint32_t recon_stride,
+                                                             uint32_t area_width, uint32_t area_height);
+/* replace svt_aom_satd / svt_av1_block_error (aom_dsp_rtcd.h:215,217) */
+SVT_B200_API int svt_aom_satd_cuda(const int32_t *coeff, int length);
+SVT_B200_API int64_t svt_av1_block_error_cuda(const int32_t *coeff, const int32_t *dqcoeff, intptr_t block_size,
+                                              int64_t *ssz);
+/* replace svt_nxm_sad_kernel_sub_sampled / sad_16b_kernel (aom_dsp_rtcd.h:643,651) */
+SVT_B200_API uint32_t svt_nxm_sad_kernel_sub_sampled_cuda(const uint8_t *src, uint32_t src_stride, const uint8_t *ref,
+                                                          uint32_t ref_stride, uint32_t height, uint32_t width);
+SVT_B200_API uint32_t sad_16b_kernel_cuda(uint16_t *src, uint32_t src_stride, uint16_t *ref, uint32_t ref_stride,
+                                          uint32_t height, uint32_t width);
+/* replace svt_aom_sadMxN / svt_aom_sadMxNx4d (aom_dsp_rtcd.h:264-388) */
+#define SVT_B200_DECL_SAD(W, H)                                                                           \
+    SVT_B200_API uint32_t svt_aom_sad##W##x##H##_cuda(const uint8_t *src_ptr, int src_stride,             \
+                                                      const uint8_t *ref_ptr, int ref_stride);            \
+    SVT_B200_API void svt_aom_sad##W##x##H##x4d_cuda(const uint8_t *src_ptr, int src_stride,              \
+                                                     const uint8_t *const ref_ptr[], int ref_stride,      \
+                                                     uint32_t *sad_array);
+SVT_B200_DECL_SAD(128, 128) SVT_B200_DECL_SAD(128, 64) SVT_B200_DECL_SAD(64, 128) SVT_B200_DECL_SAD(64, 64)
+SVT_B200_DECL_SAD(64, 32) SVT_B200_DECL_SAD(64, 16) SVT_B200_DECL_SAD(32, 64) SVT_B200_DECL_SAD(32, 32)
+SVT_B200_DECL_SAD(32, 16) SVT_B200_DECL_SAD(32, 8) SVT_B200_DECL_SAD(16, 64) SVT_B200_DECL_SAD(16, 32)
+SVT_B200_DECL_SAD(16, 16) SVT_B200_DECL_SAD(16, 8) SVT_B200_DECL_SAD(16, 4) SVT_B200_DECL_SAD(8, 32)
+SVT_B200_DECL_SAD(8, 16) SVT_B200_DECL_SAD(8, 8) SVT_B200_DECL_SAD(8, 4) SVT_B200_DECL_SAD(4, 16)
+SVT_B200_DECL_SAD(4, 8) SVT_B200_DECL_SAD(4, 4)
+
 #ifdef __cplusplus
 }
 #endif
