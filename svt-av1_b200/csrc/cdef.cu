@@ -349,6 +349,241 @@ __global__ void __launch_bounds__(NT) cdef_search_kernel(const __grid_constant__
     }
 }
 
+// ---- search, separable form ---------------------------------------------------------------------------------------
+// Every strength table the encoder uses (get_cdef_filter_strengths) is a GRID: gi = pi * nsec + si.  The filter sum
+// of cdef_filter_block is P(pri) + S(sec) with P over the 4 primary taps and S over the 8 secondary taps, and the
+// clamp range [min, max] depends on the tap set only, so per pixel the search needs S and min/max once per
+// direction set (direction 0 for the pri == 0 entries — `t ? dir : 0` in svt_cdef_filter_fb — and the block's
+// direction for the rest) and P once per primary strength: for the 5x2 table of preset 8 that is 32 constrain()
+// evaluations per pixel instead of 72, 24 tile loads instead of 108.
+struct CdefGrid {
+    int npri, nsec;
+    int pri[16], sec[4];
+};
+struct CdefSearchGridDev {
+    CdefSearchDev d;
+    CdefGrid g;
+};
+
+template <typename T, int BS, int NSEC, bool LUMA, bool kBorder>
+__device__ __noinline__ void plane_search_grid(const CdefSearchDev &d, const CdefGrid &g, const int16_t *in, int count,
+                                                  const uint8_t *s_by, const uint8_t *s_bx, const int8_t *s_dir, const int *s_var,
+                                                  unsigned long long *s_mse, int pli, int y0, int x0, int damping) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int cs = d.coeff_shift;
+    const T *sp = reinterpret_cast<const T *>(d.source.p[pli]);
+    const int sstride = d.source.stride[pli];
+    constexpr int PX = 4; // samples per thread: a quarter (chroma: a whole) block row
+    constexpr int TPB = BS * BS / PX; // threads per block: 16 (luma 8x8) or 4 (chroma 4x4)
+    constexpr int BPP = NT / TPB; // blocks per pass
+    for (int b0 = 0; b0 < count; b0 += BPP) {
+        if (b0 + (tid & ~31) / TPB >= count) continue; // whole warp idle (shuffles below are per warp)
+        const int b = b0 + tid / TPB, sub = tid % TPB;
+        const int row = sub / (BS / PX), col = (sub % (BS / PX)) * PX;
+        const bool live = b < count;
+        const int bb = live ? b : 0;
+        const int by = s_by[bb], bx = s_bx[bb];
+        const int16_t *q = in + (by * BS + row) * TS + bx * BS + col;
+        const T *so = sp + (size_t)(y0 + by * BS + row) * sstride + x0 + bx * BS + col;
+        const int bdir = s_dir[bb], var = s_var[bb];
+        int x[PX], o[PX], mn[PX], mx[PX], S[PX][NSEC];
+        unsigned int sd = 0, sd2 = 0;
+#pragma unroll
+        for (int j = 0; j < PX; j++) {
+            x[j] = q[j];
+            o[j] = (int)so[j];
+            if (LUMA) {
+                sd += o[j];
+                sd2 += o[j] * o[j];
+            }
+        }
+        if (LUMA) {
+#pragma unroll
+            for (int s = 1; s < TPB; s <<= 1) {
+                sd += __shfl_xor_sync(0xffffffffu, sd, s);
+                sd2 += __shfl_xor_sync(0xffffffffu, sd2, s);
+            }
+        }
+        int have = -1; // direction set S/mn/mx currently hold: 0 = direction 0, 1 = block direction
+        for (int pi = 0; pi < g.npri; pi++) {
+            const int pri = g.pri[pi] << cs;
+            const int want = pri ? 1 : 0;
+            const int dir = pri ? bdir : 0;
+            if (want != have) { // uniform over the CTA
+                have = want;
+                int o2[2], o6[2], po[2];
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    po[k] = c_dir[dir][k][0] * TS + c_dir[dir][k][1];
+                    o2[k] = c_dir[(dir + 2) & 7][k][0] * TS + c_dir[(dir + 2) & 7][k][1];
+                    o6[k] = c_dir[(dir + 6) & 7][k][0] * TS + c_dir[(dir + 6) & 7][k][1];
+                }
+#pragma unroll
+                for (int j = 0; j < PX; j++) {
+                    int tp[12];
+#pragma unroll
+                    for (int k = 0; k < 2; k++) {
+                        tp[4 * k + 0] = q[j + o2[k]], tp[4 * k + 1] = q[j - o2[k]];
+                        tp[4 * k + 2] = q[j + o6[k]], tp[4 * k + 3] = q[j - o6[k]];
+                        tp[8 + 2 * k] = q[j + po[k]], tp[9 + 2 * k] = q[j - po[k]];
+                    }
+                    int lo = x[j], hi = x[j];
+#pragma unroll
+                    for (int i = 0; i < 12; i++) {
+                        lo = min(lo, tp[i]);
+                        hi = (kBorder && tp[i] == VERY_LARGE) ? hi : max(hi, tp[i]);
+                    }
+                    mn[j] = lo;
+                    mx[j] = hi;
+#pragma unroll
+                    for (int si = 0; si < NSEC; si++) {
+                        const int sec = g.sec[si] << cs;
+                        int acc = 0;
+                        if (sec) {
+                            const int ssh = max(0, damping - msb((uint32_t)sec));
+#pragma unroll
+                            for (int k = 0; k < 2; k++) {
+                                const int w = k ? 1 : 2;
+                                acc += w * (constrain_s(tp[4 * k] - x[j], sec, ssh) + constrain_s(tp[4 * k + 1] - x[j], sec, ssh) +
+                                            constrain_s(tp[4 * k + 2] - x[j], sec, ssh) + constrain_s(tp[4 * k + 3] - x[j], sec, ssh));
+                            }
+                        }
+                        S[j][si] = acc;
+                    }
+                }
+            }
+            const int t = LUMA ? adjust_strength(pri, var) : pri;
+            const int odd = (t >> cs) & 1;
+            const int pt0 = odd ? 3 : 4, pt1 = odd ? 3 : 2;
+            const int psh = t ? max(0, damping - msb((uint32_t)t)) : 0;
+            const int po0 = c_dir[dir][0][0] * TS + c_dir[dir][0][1], po1 = c_dir[dir][1][0] * TS + c_dir[dir][1][1];
+            unsigned int ss[NSEC], ss2[NSEC], ssd[NSEC];
+#pragma unroll
+            for (int si = 0; si < NSEC; si++) ss[si] = ss2[si] = ssd[si] = 0;
+#pragma unroll
+            for (int j = 0; j < PX; j++) {
+                int P = 0;
+                if (t) {
+                    P = pt0 * (constrain_s(q[j + po0] - x[j], t, psh) + constrain_s(q[j - po0] - x[j], t, psh)) +
+                        pt1 * (constrain_s(q[j + po1] - x[j], t, psh) + constrain_s(q[j - po1] - x[j], t, psh));
+                }
+#pragma unroll
+                for (int si = 0; si < NSEC; si++) {
+                    const int sum = P + S[j][si];
+                    const int y = x[j] + ((8 + sum - (sum < 0)) >> 4);
+                    const int f = min(max(y, mn[j]), mx[j]);
+                    if (LUMA) {
+                        ss[si] += f;
+                        ss2[si] += f * f;
+                        ssd[si] += f * o[j];
+                    } else {
+                        ss[si] += (o[j] - f) * (o[j] - f);
+                    }
+                }
+            }
+#pragma unroll
+            for (int si = 0; si < NSEC; si++) {
+                unsigned long long v;
+                if (LUMA) { // 16 lanes = one 8x8 block
+#pragma unroll
+                    for (int s = 1; s < TPB; s <<= 1) {
+                        ss[si] += __shfl_xor_sync(0xffffffffu, ss[si], s);
+                        ss2[si] += __shfl_xor_sync(0xffffffffu, ss2[si], s);
+                        ssd[si] += __shfl_xor_sync(0xffffffffu, ssd[si], s);
+                    }
+                    v = (live && sub == 0) ? dist8x8_from_sums(ss[si], sd, ss2[si], sd2, ssd[si], cs) : 0ull;
+                    v += __shfl_xor_sync(0xffffffffu, v, 16);
+                } else {
+                    v = live ? ss[si] : 0u;
+#pragma unroll
+                    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+                }
+                if (lane == 0 && v) atomicAdd(&s_mse[pi * NSEC + si], v);
+            }
+        }
+    }
+}
+
+template <typename T, int NSEC>
+__global__ void __launch_bounds__(NT, 2) cdef_search_grid_kernel(const __grid_constant__ CdefSearchGridDev gd) {
+    __shared__ int16_t tile[68 * TS];
+    __shared__ uint8_t s_by[64], s_bx[64];
+    __shared__ int8_t s_dir[64];
+    __shared__ int s_var[64];
+    __shared__ int s_count;
+    __shared__ unsigned long long s_mse[64];
+    const CdefSearchDev &d = gd.d;
+    const int tid = threadIdx.x;
+    const int fb = blockIdx.x, fbr = fb / d.nhfb, fbc = fb - fbr * d.nhfb;
+    const SvtB200CdefSearchParams &p = d.p;
+    const int nvb = min(16, p.mi_rows - 16 * fbr), nhb = min(16, p.mi_cols - 16 * fbc);
+    const int cs = d.coeff_shift;
+    const bool border = fbr == 0 || fbc == 0 || 16 * (fbr + 1) >= p.mi_rows || 16 * (fbc + 1) >= p.mi_cols;
+    uint64_t *out_y = d.mse + ((size_t)fb) * 64;
+    uint64_t *out_c = d.mse + ((size_t)d.nvfb * d.nhfb + fb) * 64;
+    if (tid == 0) { // svt_sb_compute_cdef_list: raster list of the non-skip 8x8 blocks
+        int n = 0;
+        for (int r = 0; r < nvb; r += 2)
+            for (int c = 0; c < nhb; c += 2)
+                if (!d.skip8[(size_t)((16 * fbr + r) >> 1) * d.skip_stride + ((16 * fbc + c) >> 1)]) {
+                    s_by[n] = (uint8_t)(r >> 1);
+                    s_bx[n] = (uint8_t)(c >> 1);
+                    n++;
+                }
+        s_count = n;
+    }
+    __syncthreads();
+    const int count = s_count;
+    if (count == 0) { // svt_sb_all_skip: not searched; entries defined as 0
+        for (int i = tid; i < 64; i += NT) {
+            out_y[i] = 0;
+            out_c[i] = 0;
+        }
+        return;
+    }
+    for (int pli = 0; pli < 3; pli++) {
+        const int sh = pli ? 1 : 0;
+        const int pw = (p.mi_cols * 4) >> sh, ph = (p.mi_rows * 4) >> sh;
+        const int bh = (nvb * 4) >> sh, bw = (nhb * 4) >> sh;
+        const int y0 = (fbr * 64) >> sh, x0 = (fbc * 64) >> sh;
+        __syncthreads();
+        load_tile<T>(d.recon.p[pli], d.recon.stride[pli], pw, ph, y0, x0, bh, bw, tile);
+        for (int i = tid; i < 64; i += NT) s_mse[i] = 0;
+        __syncthreads();
+        const int16_t *in = tile + 2 * TS + 2;
+        if (pli == 0) {
+            if (tid < count) {
+                int v;
+                s_dir[tid] = (int8_t)find_dir(in + 8 * s_by[tid] * TS + 8 * s_bx[tid], TS, &v, cs);
+                s_var[tid] = v;
+            }
+            __syncthreads();
+        }
+        const int damping = p.pri_damping + cs - (pli != 0);
+        if (pli == 0) {
+            if (border)
+                plane_search_grid<T, 8, NSEC, true, true>(d, gd.g, in, count, s_by, s_bx, s_dir, s_var, s_mse, pli, y0, x0, damping);
+            else
+                plane_search_grid<T, 8, NSEC, true, false>(d, gd.g, in, count, s_by, s_bx, s_dir, s_var, s_mse, pli, y0, x0, damping);
+        } else {
+            if (border)
+                plane_search_grid<T, 4, NSEC, false, true>(d, gd.g, in, count, s_by, s_bx, s_dir, s_var, s_mse, pli, y0, x0, damping);
+            else
+                plane_search_grid<T, 4, NSEC, false, false>(d, gd.g, in, count, s_by, s_bx, s_dir, s_var, s_mse, pli, y0, x0, damping);
+        }
+        __syncthreads();
+        for (int gi = tid; gi < 64; gi += NT) {
+            const unsigned long long v = gi < p.n_strengths ? (s_mse[gi] >> (2 * cs)) : 0;
+            if (pli == 0)
+                out_y[gi] = v;
+            else if (pli == 1)
+                out_c[gi] = v;
+            else
+                out_c[gi] += v;
+        }
+    }
+}
+
 struct CdefApplyDev {
     SvtB200CdefApplyParams p;
     FrameDev recon, out;
@@ -496,7 +731,33 @@ int svt_b200_cdef_search(const SvtB200CdefSearchParams *p, const SvtB200Frame *r
     d.nhfb = (p->mi_cols + 15) / 16;
     d.coeff_shift = recon->bit_depth - 8;
     cudaStream_t st = (cudaStream_t)stream;
-    if (d.recon.hbd)
+    // grid-structured table (every table of get_cdef_filter_strengths is one): separable kernel
+    CdefSearchGridDev gd;
+    int nsec = 1;
+    while (nsec < p->n_strengths && p->pri_strength[nsec] == p->pri_strength[0]) nsec++;
+    bool grid = (nsec == 2 || nsec == 4) && p->n_strengths % nsec == 0 && p->n_strengths / nsec <= 16;
+    for (int gi = 0; grid && gi < p->n_strengths; gi++)
+        grid = p->pri_strength[gi] == p->pri_strength[gi / nsec * nsec] && p->sec_strength[gi] == p->sec_strength[gi % nsec];
+    if (grid) {
+        gd.d = d;
+        gd.g.npri = p->n_strengths / nsec;
+        gd.g.nsec = nsec;
+        memset(gd.g.pri, 0, sizeof(gd.g.pri));
+        memset(gd.g.sec, 0, sizeof(gd.g.sec));
+        for (int i = 0; i < gd.g.npri; i++) gd.g.pri[i] = p->pri_strength[i * nsec];
+        for (int i = 0; i < nsec; i++) gd.g.sec[i] = p->sec_strength[i];
+        if (d.recon.hbd) {
+            if (nsec == 2)
+                SVTB_LAUNCH((cdef_search_grid_kernel<uint16_t, 2>), d.nvfb * d.nhfb, NT, 0, st, gd);
+            else
+                SVTB_LAUNCH((cdef_search_grid_kernel<uint16_t, 4>), d.nvfb * d.nhfb, NT, 0, st, gd);
+        } else {
+            if (nsec == 2)
+                SVTB_LAUNCH((cdef_search_grid_kernel<uint8_t, 2>), d.nvfb * d.nhfb, NT, 0, st, gd);
+            else
+                SVTB_LAUNCH((cdef_search_grid_kernel<uint8_t, 4>), d.nvfb * d.nhfb, NT, 0, st, gd);
+        }
+    } else if (d.recon.hbd)
         SVTB_LAUNCH(cdef_search_kernel<uint16_t>, d.nvfb * d.nhfb, NT, 0, st, d);
     else
         SVTB_LAUNCH(cdef_search_kernel<uint8_t>, d.nvfb * d.nhfb, NT, 0, st, d);

@@ -357,17 +357,132 @@ __global__ void __launch_bounds__(NT_SEARCH) hme_kernel_generic(const __grid_con
 
 
 // ---- Kernel A (fast path): all 2x2 search regions of an HME level are searched concurrently ----------------
-// Per level: every region's window + the (shared) source block are staged once, then each region ("job") is
-// searched by the whole CTA with `tpp` threads per candidate position (rows interleaved) so that small search
-// areas (8x3 at levels 1/2) still use all lanes; partial SADs are combined with xor-shuffles, the per-job
-// argmin with a shared-memory 64-bit atomicMin.  Requires all windows of a level to fit in HME_FAST_SMEM.
+// Per level: every region's window + the (shared) source block are staged once.  Full-width blocks (sbw == 64) use
+// the aligned-task scheme of the full-pel kernel: a task is Q positions of one search row with the same byte
+// alignment, x = 4Q*m + c + 4k, so that one shifted copy of the window row (W + Q - 1 SHF) feeds W*Q VABSDIFF4 and
+// all loads are 8/16-byte LDS.  The rows of a task are split over `tpp` threads so that the tiny level-1/2 areas
+// (8x3) still fill the CTA; every warp works for ONE region, so the per-region argmin is a warp reduction plus one
+// shared 64-bit atomicMin.  Ragged blocks (picture width not a multiple of 64) take hme_level_search below.
 constexpr int HME_FAST_SMEM = 64 * 1024;
 struct HmeJob {
     const uint8_t *ref; // search position (0,0)
     int xo, yo, saw, sah;
     int woff, wpw; // window offset (words) in smem, words per row
+    int q, gpr, t0, nt; // positions per task (2|4), task groups per row, first (padded) task id, padded task count
 };
 
+__host__ __device__ __forceinline__ int hme_pitch_words(int saw, int w, int q) {
+    const int g = (saw + 4 * q - 1) / (4 * q);
+    int p = (q * g + w + 3) & ~3;
+    return (p & 4) ? p : p + 4;
+}
+
+template <int W, int Q>
+__device__ __forceinline__ void hme_task_rows(const uint32_t *__restrict__ s_src, const uint32_t *__restrict__ wbase, int wpw, int k,
+                                              int sh, int r0, int rstep, int bh, uint32_t (&acc)[Q]) {
+    uint32_t a[Q][2];
+#pragma unroll
+    for (int q = 0; q < Q; q++) a[q][0] = a[q][1] = 0;
+    for (int r = r0; r < bh; r += rstep) {
+        uint32_t s[W], w[W + Q], f[W + Q - 1];
+        const uint32_t *sp = s_src + r * W;
+        const uint32_t *wp = wbase + r * k * wpw;
+#pragma unroll
+        for (int i = 0; i < W / 4; i++) {
+            const uint4 v = reinterpret_cast<const uint4 *>(sp)[i];
+            s[4 * i] = v.x, s[4 * i + 1] = v.y, s[4 * i + 2] = v.z, s[4 * i + 3] = v.w;
+        }
+        if (Q == 4) {
+#pragma unroll
+            for (int i = 0; i < (W + Q) / 4; i++) {
+                const uint4 v = reinterpret_cast<const uint4 *>(wp)[i];
+                w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < (W + Q) / 2; i++) {
+                const uint2 v = reinterpret_cast<const uint2 *>(wp)[i];
+                w[2 * i] = v.x, w[2 * i + 1] = v.y;
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < W + Q - 1; i++) f[i] = __funnelshift_r(w[i], w[i + 1], sh);
+#pragma unroll
+        for (int i = 0; i < W; i++)
+#pragma unroll
+            for (int q = 0; q < Q; q++) a[q][i & 1] = sad4(s[i], f[i + q], a[q][i & 1]);
+    }
+#pragma unroll
+    for (int q = 0; q < Q; q++) acc[q] = a[q][0] + a[q][1];
+}
+
+// one task round of a warp: decode, search, reduce.  Returns this lane's best key (~0 if none).
+template <int W, int Q>
+__device__ __forceinline__ unsigned long long hme_task(const HmeJob &jb, const uint32_t *s_src, const uint32_t *smem, int u, bool live,
+                                                       int k, int bh, int tpp, int sub) {
+    const int tpr = 4 * jb.gpr;
+    const int ys = live ? u / tpr : 0;
+    const int rem = live ? u - ys * tpr : 0;
+    const int m = rem >> 2, c = rem & 3;
+    uint32_t acc[Q];
+    hme_task_rows<W, Q>(s_src, smem + jb.woff + ys * jb.wpw + m * Q, jb.wpw, k, c * 8, sub, tpp, bh, acc);
+    for (int o = 1; o < tpp; o <<= 1)
+#pragma unroll
+        for (int q = 0; q < Q; q++) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
+    unsigned long long best = ~0ull;
+    if (live && sub == 0) {
+#pragma unroll
+        for (int q = 0; q < Q; q++) {
+            const int x = 4 * Q * m + c + 4 * q;
+            const unsigned long long key = ((unsigned long long)acc[q] << 32) | (uint32_t)(ys * jb.saw + x);
+            if (x < jb.saw && key < best) best = key;
+        }
+    }
+    return best;
+}
+
+template <int NT>
+__device__ void stage_rows_flat(uint32_t *dst, int wpw, const uint8_t *__restrict__ src, ptrdiff_t stride, int rows, int nbytes) {
+    for (int i = threadIdx.x; i < rows * wpw; i += NT) {
+        const int row = i / wpw, wd = i - row * wpw;
+        const uintptr_t a = (uintptr_t)(src + (ptrdiff_t)row * stride);
+        const uint32_t *ga = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        const int need = (nbytes + (int)(a & 3) + 3) >> 2;
+        const uint32_t lo = wd < need ? ga[wd] : 0u, hi = (wd + 1) < need ? ga[wd + 1] : 0u;
+        dst[i] = __funnelshift_r(lo, hi, (int)(a & 3) * 8);
+    }
+}
+
+template <int NT, int W>
+__device__ void hme_level_search_aligned(const uint8_t *__restrict__ src, int src_stride, int raw_stride, int k, int bh,
+                                         const HmeJob *jobs, int njobs, int tpp, int ntasks, uint32_t *smem,
+                                         unsigned long long *s_key) {
+    const int tid = threadIdx.x;
+    stage_rows_flat<NT>(smem, W, src, src_stride, bh, 4 * W);
+    const int span = (bh - 1) * k + 1;
+    for (int j = 0; j < njobs; j++) {
+        const HmeJob jb = jobs[j];
+        stage_rows_flat<NT>(smem + jb.woff, jb.wpw, jb.ref, raw_stride, jb.sah - 1 + span, jb.saw - 1 + 4 * W);
+    }
+    __syncthreads();
+    const int sub = tid & (tpp - 1), gpt = NT / tpp;
+    for (int g0 = 0; g0 < ntasks; g0 += gpt) {
+        if (g0 + (tid & ~31) / tpp >= ntasks) continue; // warp-uniform
+        const int t = g0 + tid / tpp;
+        int j = 0;
+        while (j + 1 < njobs && t >= jobs[j + 1].t0) j++; // warp-uniform: task ranges are padded to whole warps
+        const HmeJob jb = jobs[j];
+        const int u = t - jb.t0;
+        const bool live = u < jb.sah * 4 * jb.gpr;
+        unsigned long long best = jb.q == 4 ? hme_task<W, 4>(jb, smem, smem, u, live, k, bh, tpp, sub)
+                                            : hme_task<W, 2>(jb, smem, smem, u, live, k, bh, tpp, sub);
+        best = warp_min_u64(best);
+        if ((tid & 31) == 0 && best != ~0ull) atomicMin(&s_key[j], best);
+    }
+    __syncthreads();
+}
+
+// ragged-width fallback: one job after the other, word-granular loads, tail mask
 template <int NT>
 __device__ void hme_level_search(const uint8_t *__restrict__ src, int src_stride, int raw_stride, int k, int bw, int bh,
                                  const HmeJob *jobs, int njobs, uint32_t *smem, unsigned long long *s_key) {
@@ -428,8 +543,10 @@ __device__ void hme_level_search(const uint8_t *__restrict__ src, int src_stride
 }
 
 __global__ void __launch_bounds__(NT_SEARCH) hme_kernel(const __grid_constant__ MeDev d) {
-    extern __shared__ uint32_t smem[];
+    extern __shared__ uint4 smem4[];
+    uint32_t *smem = reinterpret_cast<uint32_t *>(smem4);
     __shared__ HmeJob s_jobs[4];
+    __shared__ int s_tpp, s_ntasks;
     __shared__ unsigned long long s_key[4];
     __shared__ int s_cx[4], s_cy[4];
     __shared__ unsigned long long s_csad[4];
@@ -451,6 +568,7 @@ __global__ void __launch_bounds__(NT_SEARCH) hme_kernel(const __grid_constant__ 
     const int ox = sx * 64, oy = sy * 64;
     const int sbw = min(p.full.width - ox, 64), sbh = min(p.full.height - oy, 64);
     const int sub = p.hme_search_method != 0;
+    const bool aligned = sbw == 64; // block rows are whole 16-byte groups at every level
     const int mult = scaled_dist(p.ref_dist[l][r]) * 100;
     const int nrw = p.number_hme_search_region_in_width, nrh = p.number_hme_search_region_in_height;
     const int njobs = nrw * nrh;
@@ -509,22 +627,45 @@ __global__ void __launch_bounds__(NT_SEARCH) hme_kernel(const __grid_constant__ 
             jb.yo = yo;
             jb.saw = saw;
             jb.sah = sah;
-            jb.wpw = ((saw - 1 + bw + 3) >> 2) + 1;
-            jb.woff = 0;
+            jb.q = (saw & 15) ? 2 : 4;
+            jb.gpr = (saw + 4 * jb.q - 1) / (4 * jb.q);
+            jb.wpw = aligned ? hme_pitch_words(saw, bw >> 2, jb.q) : ((saw - 1 + bw + 3) >> 2) + 1;
+            jb.woff = jb.t0 = jb.nt = 0;
             s_jobs[tid] = jb;
             s_key[tid] = ~0ull;
         }
         __syncthreads();
-        if (tid == 0) { // window offsets (words) after the source block
+        if (tid == 0) { // window offsets (words) after the source block; task ranges padded to whole warps
             int off = ((bw + 3) >> 2) * bh;
             for (int j = 0; j < njobs; j++) {
                 s_jobs[j].woff = off;
                 off += s_jobs[j].wpw * (s_jobs[j].sah - 1 + (bh - 1) * k + 1);
             }
+            int tpp = 32;
+            for (;; tpp >>= 1) {
+                const int pad = 32 / tpp;
+                int tot = 0;
+                for (int j = 0; j < njobs; j++) {
+                    s_jobs[j].t0 = tot;
+                    s_jobs[j].nt = (s_jobs[j].sah * 4 * s_jobs[j].gpr + pad - 1) / pad * pad;
+                    tot += s_jobs[j].nt;
+                }
+                s_ntasks = tot;
+                if (tpp == 1 || (tpp <= bh && tot * tpp <= NT_SEARCH)) break;
+            }
+            s_tpp = tpp;
         }
         __syncthreads();
         const uint8_t *s = srcp + (size_t)(pl.origin_y + o_y) * pl.stride + pl.origin_x + o_x;
-        hme_level_search<NT_SEARCH>(s, sub ? pl.stride * 2 : pl.stride, pl.stride, k, bw, bh, s_jobs, njobs, smem, s_key);
+        const int sstr = sub ? pl.stride * 2 : pl.stride;
+        if (!aligned)
+            hme_level_search<NT_SEARCH>(s, sstr, pl.stride, k, bw, bh, s_jobs, njobs, smem, s_key);
+        else if (level == 0)
+            hme_level_search_aligned<NT_SEARCH, 4>(s, sstr, pl.stride, k, bh, s_jobs, njobs, s_tpp, s_ntasks, smem, s_key);
+        else if (level == 1)
+            hme_level_search_aligned<NT_SEARCH, 8>(s, sstr, pl.stride, k, bh, s_jobs, njobs, s_tpp, s_ntasks, smem, s_key);
+        else
+            hme_level_search_aligned<NT_SEARCH, 16>(s, sstr, pl.stride, k, bh, s_jobs, njobs, s_tpp, s_ntasks, smem, s_key);
         if (tid < njobs) {
             const unsigned long long key = s_key[tid];
             const uint32_t sad = (uint32_t)(key >> 32), idx = (uint32_t)key;
@@ -562,15 +703,37 @@ __global__ void __launch_bounds__(NT_SEARCH) hme_kernel(const __grid_constant__ 
 
 // -----------------------------------------------------------------------------------------------------
 // Kernel B: integer full-pel search (integer_search_sb :1868-2139 + open_loop_me_fullpel_search_sblock)
+//
+// Work decomposition.  A "task" is FOUR search positions of one search row that share their byte alignment:
+// x = 16m + c + 4k (k = 0..3).  Per 64-pixel source row the task loads the 16 source words (4 LDS.128) and the 20
+// window words starting at word 4m (5 LDS.128, 16-byte aligned), forms the 19 words of the window shifted by c bytes
+// (one SHF each) and feeds them to 64 VABSDIFF4: the shifted stream is shared by the four positions, so the inner
+// loop is 1.44 issue slots per VABSDIFF4.  The 8x8 SADs of a band of eight blocks live in 32 accumulators; 16x16,
+// 32x32 and 64x64 SADs are their sums (ext_all_sad_calculation_8x8_16x16 / ext_eight_sad_calculation_32x32_64x64).
+// Positions that do not exist (x >= saw, dead lanes) start their 8x8 accumulators at BIAS = one more than the
+// largest 8x8 SAD, so at every level (4x, 16x, 64x BIAS) they lose against any real position without a select.
+// First-minimum-in-raster-order = argmin of the packed key (sad << SH) + index: REDUX.MIN per PU, then the lane
+// that owns the PU keeps the running minimum in a register; one shared atomicMin per lane per task round.
 // -----------------------------------------------------------------------------------------------------
 constexpr int FP_SMEM_BYTES = 96 * 1024;
 
-__global__ void __launch_bounds__(NT_SEARCH) fullpel_kernel(const __grid_constant__ MeDev d) {
-    extern __shared__ uint32_t smem[];
+__host__ __device__ __forceinline__ int fp_pitch_words(int saw) {
+    const int w = 4 * ((saw + 15) >> 4) + 20;
+    return (w & 4) ? w : w + 4; // odd number of 16-byte units: consecutive rows start in different banks
+}
+
+template <bool SUB>
+__global__ void __launch_bounds__(NT_SEARCH, 2) fullpel_kernel(const __grid_constant__ MeDev d) {
+    extern __shared__ uint4 smem4[];
+    uint32_t *smem = reinterpret_cast<uint32_t *>(smem4);
     __shared__ unsigned long long s_best[85]; // (sad << 32 | raster index) over the whole window
-    __shared__ unsigned int s_cbest[85]; // (sad << 11 | index inside the current chunk): one REDUX + one atomicMin
+    __shared__ unsigned int s_cbest[85]; // (sad << SH | index inside the current chunk)
     __shared__ HmeState s_h;
     __shared__ uint32_t s_sad2[2];
+    constexpr int SH = SUB ? 12 : 11; // SUB keeps the un-doubled SAD (19 bits) in the key
+    constexpr uint32_t BIAS = SUB ? 8192u : 16384u;
+    constexpr int NR = SUB ? 4 : 8, KR = SUB ? 2 : 1; // rows summed per 8x8, window rows per summed row
+    constexpr int NSRC = SUB ? 32 : 64;
     const SvtB200MeParams &p = d.p;
     const int tid = threadIdx.x, lane = tid & 31;
     const int sb = blockIdx.x, slot = blockIdx.y;
@@ -595,7 +758,6 @@ __global__ void __launch_bounds__(NT_SEARCH) fullpel_kernel(const __grid_constan
     const SvtB200Plane &fp = p.full;
     const int pic_w = fp.width, pic_h = fp.height;
     const int sbw = min(pic_w - ox, 64), sbh = min(pic_h - oy, 64);
-    const int sub = p.me_search_method != 0;
     const uint8_t *srcb = d.src.full + (size_t)(fp.origin_y + oy) * fp.stride + fp.origin_x + ox;
     const uint8_t *refb = d.refs[l][r].full + (size_t)(fp.origin_y + oy) * fp.stride + fp.origin_x + ox;
 
@@ -641,19 +803,31 @@ __global__ void __launch_bounds__(NT_SEARCH) fullpel_kernel(const __grid_constan
     for (int i = tid; i < 85; i += NT_SEARCH) s_best[i] = ((unsigned long long)kMaxSadValue << 32) | 0xffffffffull;
 
     // ---- stage the source rows that take part in the SAD (even rows only with sub-sampling) ----
-    const int nrows_src = sub ? 32 : 64;
-    uint32_t *s_src = smem; // [nrows_src][16 words]
-    uint32_t *s_win = smem + nrows_src * 16;
-    stage_rows<NT_SEARCH>(s_src, 16, srcb, (ptrdiff_t)(sub ? 2 : 1) * fp.stride, nrows_src, 64);
-    const int span = sub ? 63 : 64;
+    uint32_t *s_src = smem; // [NSRC][16 words]
+    uint32_t *s_win = smem + NSRC * 16;
+    stage_rows<NT_SEARCH>(s_src, 16, srcb, (ptrdiff_t)KR * fp.stride, NSRC, 64);
+    const int span = SUB ? 63 : 64;
     const int wbytes = saw + 63;
-    const int wpw = ((wbytes + 3) >> 2) + 1;
-    const int budget_rows = (d.fp_smem_bytes - nrows_src * 64) / (wpw * 4);
+    const int wpw = fp_pitch_words(saw);
+    const int budget_rows = (d.fp_smem_bytes - NSRC * 64) / (wpw * 4);
     int chunk = min(sah, budget_rows - span + 1);
     chunk = min(chunk, 2048 / saw); // chunk-local position index must fit 11 bits
     if (chunk < 1) chunk = 1;
-    const int nq = (saw + 3) >> 2; // position quads per search row
-    const int nr8 = sub ? 4 : 8; // rows summed per 8x8
+    const int tpr = 4 * ((saw + 15) >> 4); // tasks per search row
+
+    // which PU this lane owns in the lane-resident running minima
+    int pu8[2], puh = -1;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int by8 = 4 * h + (lane >> 3), bx8 = lane & 7;
+        pu8[h] = 21 + 4 * c_tab16[(by8 >> 1) * 4 + (bx8 >> 1)] + (by8 & 1) * 2 + (bx8 & 1);
+    }
+    if (lane < 16)
+        puh = 5 + c_tab16[lane];
+    else if (lane < 20)
+        puh = 1 + (lane - 16);
+    else if (lane == 20)
+        puh = 0;
 
     for (int y0 = 0; y0 < sah; y0 += chunk) {
         const int cr = min(chunk, sah - y0);
@@ -662,81 +836,112 @@ __global__ void __launch_bounds__(NT_SEARCH) fullpel_kernel(const __grid_constan
         stage_rows<NT_SEARCH>(s_win, wpw, refb + (ptrdiff_t)(yo + y0) * fp.stride + xo, fp.stride, rows, wbytes);
         for (int i = tid; i < 85; i += NT_SEARCH) s_cbest[i] = 0xffffffffu;
         __syncthreads();
-        const int nquads = cr * nq;
-        for (int qb = 0; qb < nquads; qb += NT_SEARCH) {
-            if (qb + (tid & ~31) >= nquads) continue; // whole warp has no position: reductions are per warp
-            const int qi = qb + tid;
-            const bool live = qi < nquads;
-            const int ysl = live ? qi / nq : 0;
-            const int xs0 = live ? (qi - ysl * nq) * 4 : 0;
-            const uint32_t idx0 = (uint32_t)(ysl * saw + xs0); // index inside the chunk (< 2048)
-            uint32_t ok[4];
+        const int ntasks = cr * tpr;
+        for (int qb = 0; qb < ntasks; qb += NT_SEARCH) {
+            if (qb + (tid & ~31) >= ntasks) continue; // whole warp has no task: reductions are per warp
+            const int t = qb + tid;
+            const bool live = t < ntasks;
+            const int ysl = live ? t / tpr : 0;
+            const int rem = live ? t - ysl * tpr : 0;
+            const int x0 = (rem >> 2) * 16 + (rem & 3);
+            const int sh = (rem & 3) * 8;
+            uint32_t idx[4], bias[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) ok[j] = live && (xs0 + j < saw);
-            uint32_t acc32[4] = {0, 0, 0, 0}, acc64[4] = {0, 0, 0, 0};
-            for (int b = 0; b < 16; b++) { // internal (z-order) 16x16 index; 4 consecutive form one 32x32
-                const int ras = c_inv16[b];
-                const int by = ras >> 2, bx = ras & 3;
-                uint32_t s16[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 4; k++) {
+                idx[k] = (uint32_t)(ysl * saw + x0 + 4 * k); // index inside the chunk (< 2048 when valid)
+                bias[k] = (live && x0 + 4 * k < saw) ? 0u : BIAS;
+            }
+            const uint32_t *wbase = s_win + ysl * wpw + (rem >> 2) * 4;
+            uint32_t best8 = 0xffffffffu, besth = 0xffffffffu;
+            uint32_t a64[4] = {0, 0, 0, 0}, a32[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+            for (int bp = 0; bp < 4; bp++) { // pairs of 8-row bands = rows of 16x16 blocks
+                uint32_t a16[4][4];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int py = by * 16 + (q >> 1) * 8, px = bx * 16 + (q & 1) * 8;
-                    uint32_t s8[4] = {0, 0, 0, 0};
-                    if (live) {
-                        const uint32_t *sp = s_src + (sub ? (py >> 1) : py) * 16 + (px >> 2);
-                        const uint32_t *wp = s_win + (ysl + py) * wpw + ((xs0 + px) >> 2);
+                for (int k = 0; k < 4; k++)
 #pragma unroll
-                        for (int rr = 0; rr < 8; rr++) {
-                            if (rr < nr8) {
-                                const uint32_t a0 = sp[rr * 16], a1 = sp[rr * 16 + 1];
-                                const uint32_t *w = wp + (sub ? 2 * rr : rr) * wpw;
-                                const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-                                s8[0] = sad4(a1, w1, sad4(a0, w0, s8[0]));
-                                s8[1] = sad4(a1, __funnelshift_r(w1, w2, 8), sad4(a0, __funnelshift_r(w0, w1, 8), s8[1]));
-                                s8[2] = sad4(a1, __funnelshift_r(w1, w2, 16), sad4(a0, __funnelshift_r(w0, w1, 16), s8[2]));
-                                s8[3] = sad4(a1, __funnelshift_r(w1, w2, 24), sad4(a0, __funnelshift_r(w0, w1, 24), s8[3]));
-                            }
+                    for (int j = 0; j < 4; j++) a16[k][j] = 0;
+#pragma unroll
+                for (int bb = 0; bb < 2; bb++) {
+                    const int band = 2 * bp + bb;
+                    uint32_t a8[4][8];
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+#pragma unroll
+                        for (int j = 0; j < 8; j++) a8[k][j] = bias[k];
+                    const uint32_t *srow = s_src + band * NR * 16;
+                    const uint32_t *wrow = wbase + band * 8 * wpw;
+#pragma unroll
+                    for (int rr = 0; rr < NR; rr++) {
+                        const uint4 *sp = reinterpret_cast<const uint4 *>(srow + rr * 16);
+                        const uint4 *wp = reinterpret_cast<const uint4 *>(wrow + rr * KR * wpw);
+                        uint32_t s[16], w[20], f[19];
+#pragma unroll
+                        for (int i = 0; i < 4; i++) {
+                            const uint4 v = sp[i];
+                            s[4 * i] = v.x, s[4 * i + 1] = v.y, s[4 * i + 2] = v.z, s[4 * i + 3] = v.w;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 5; i++) {
+                            const uint4 v = wp[i];
+                            w[4 * i] = v.x, w[4 * i + 1] = v.y, w[4 * i + 2] = v.z, w[4 * i + 3] = v.w;
+                        }
+#pragma unroll
+                        for (int i = 0; i < 19; i++) f[i] = __funnelshift_r(w[i], w[i + 1], sh);
+#pragma unroll
+                        for (int i = 0; i < 16; i++)
+#pragma unroll
+                            for (int k = 0; k < 4; k++) a8[k][i >> 1] = sad4(s[i], f[i + k], a8[k][i >> 1]);
+                    }
+                    const int lrel = lane - ((band & 3) << 3);
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        uint32_t bk = min(min((a8[0][j] << SH) + idx[0], (a8[1][j] << SH) + idx[1]),
+                                          min((a8[2][j] << SH) + idx[2], (a8[3][j] << SH) + idx[3]));
+                        const uint32_t m = __reduce_min_sync(0xffffffffu, bk);
+                        if (lrel == j) best8 = min(best8, m);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) a16[k][j >> 1] += a8[k][j];
+                    }
+                    if (band & 3) {
+                        if ((band & 3) == 3) { // a half of the SB is complete: hand its 32 8x8 minima over
+                            atomicMin(&s_cbest[pu8[band >> 2]], best8);
+                            best8 = 0xffffffffu;
                         }
                     }
-                    uint32_t bk = 0xffffffffu; // first minimum of this thread's 4 positions (packed key)
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        const uint32_t v = sub ? s8[j] << 1 : s8[j];
-                        s16[j] += v;
-                        bk = min(bk, ok[j] ? (v << 11) + idx0 + j : 0xffffffffu);
-                    }
-                    const uint32_t m = __reduce_min_sync(0xffffffffu, bk);
-                    if (lane == 0 && m < s_cbest[21 + 4 * b + q]) atomicMin(&s_cbest[21 + 4 * b + q], m);
                 }
-                {
-                    uint32_t bk = 0xffffffffu;
+                const int lrel16 = lane - 4 * bp;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        acc32[j] += s16[j];
-                        bk = min(bk, ok[j] ? (s16[j] << 11) + idx0 + j : 0xffffffffu);
-                    }
+                for (int j = 0; j < 4; j++) {
+                    uint32_t bk = min(min((a16[0][j] << SH) + idx[0], (a16[1][j] << SH) + idx[1]),
+                                      min((a16[2][j] << SH) + idx[2], (a16[3][j] << SH) + idx[3]));
                     const uint32_t m = __reduce_min_sync(0xffffffffu, bk);
-                    if (lane == 0 && m < s_cbest[5 + b]) atomicMin(&s_cbest[5 + b], m);
+                    if (lrel16 == j) besth = min(besth, m);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) a32[k][j >> 1] += a16[k][j];
                 }
-                if ((b & 3) == 3) {
-                    uint32_t bk = 0xffffffffu;
+                if (bp & 1) {
+                    const int lrel32 = lane - 16 - (bp >> 1) * 2;
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        acc64[j] += acc32[j];
-                        bk = min(bk, ok[j] ? (acc32[j] << 11) + idx0 + j : 0xffffffffu);
-                        acc32[j] = 0;
+                    for (int j = 0; j < 2; j++) {
+                        uint32_t bk = min(min((a32[0][j] << SH) + idx[0], (a32[1][j] << SH) + idx[1]),
+                                          min((a32[2][j] << SH) + idx[2], (a32[3][j] << SH) + idx[3]));
+                        const uint32_t m = __reduce_min_sync(0xffffffffu, bk);
+                        if (lrel32 == j) besth = min(besth, m);
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            a64[k] += a32[k][j];
+                            a32[k][j] = 0;
+                        }
                     }
-                    const uint32_t m = __reduce_min_sync(0xffffffffu, bk);
-                    if (lane == 0 && m < s_cbest[1 + (b >> 2)]) atomicMin(&s_cbest[1 + (b >> 2)], m);
                 }
             }
             {
-                uint32_t bk = 0xffffffffu;
-#pragma unroll
-                for (int j = 0; j < 4; j++) bk = min(bk, ok[j] ? (acc64[j] << 11) + idx0 + j : 0xffffffffu);
+                uint32_t bk = min(min((a64[0] << SH) + idx[0], (a64[1] << SH) + idx[1]),
+                                  min((a64[2] << SH) + idx[2], (a64[3] << SH) + idx[3]));
                 const uint32_t m = __reduce_min_sync(0xffffffffu, bk);
-                if (lane == 0 && m < s_cbest[0]) atomicMin(&s_cbest[0], m);
+                if (lane == 20) besth = min(besth, m);
             }
+            if (puh >= 0) atomicMin(&s_cbest[puh], besth);
         }
         __syncthreads();
         // merge the chunk into the running best: chunks advance in raster order, so strict `<` on the SAD keeps
@@ -744,7 +949,7 @@ __global__ void __launch_bounds__(NT_SEARCH) fullpel_kernel(const __grid_constan
         for (int i = tid; i < 85; i += NT_SEARCH) {
             const unsigned int c = s_cbest[i];
             if (c != 0xffffffffu) {
-                const unsigned long long sadc = c >> 11;
+                const unsigned long long sadc = SUB ? (unsigned long long)(c >> SH) << 1 : (unsigned long long)(c >> SH);
                 if (sadc < (s_best[i] >> 32)) s_best[i] = (sadc << 32) | (unsigned int)(y0 * saw + (c & 2047u));
             }
         }
@@ -1022,7 +1227,8 @@ static void set_attrs() {
     if (g_attr_done) return;
     cudaFuncSetAttribute(hme_kernel_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, HME_SMEM_BYTES);
     cudaFuncSetAttribute(hme_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HME_FAST_SMEM);
-    cudaFuncSetAttribute(fullpel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FP_SMEM_BYTES);
+    cudaFuncSetAttribute(fullpel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FP_SMEM_BYTES);
+    cudaFuncSetAttribute(fullpel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FP_SMEM_BYTES);
     cudaFuncSetAttribute(sad_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     g_attr_done = true;
 }
@@ -1098,7 +1304,9 @@ int svt_b200_me_picture(const SvtB200MeParams *p, const SvtB200MePlanes *src,
             }
         auto level_bytes = [&](int saw, int sah, int bw, int bh) {
             const int bhh = k == 2 ? bh / 2 : bh;
-            const size_t win = (size_t)(((saw - 1 + bw + 3) / 4) + 1) * 4 * (sah - 1 + (bhh - 1) * k + 1);
+            int wpw = ((saw - 1 + bw + 3) / 4) + 1;
+            wpw = std::max(wpw, std::max(hme_pitch_words(saw, bw / 4, 2), hme_pitch_words(saw, bw / 4, 4)));
+            const size_t win = (size_t)wpw * 4 * (sah - 1 + (bhh - 1) * k + 1);
             return 4 * win + (size_t)((bw + 3) / 4) * 4 * bhh;
         };
         int w0 = p->hme_level0_search_area_in_width_array[0] * maxd, h0 = p->hme_level0_search_area_in_height_array[0] * maxd;
@@ -1128,11 +1336,14 @@ int svt_b200_me_picture(const SvtB200MeParams *p, const SvtB200MePlanes *src,
         if (sah > p->max_me_search_height) sah = p->max_me_search_height;
         saw = (saw + 7) & ~7;
         const int sub = p->me_search_method != 0;
-        size_t need = (size_t)(sub ? 32 : 64) * 64 + (size_t)(((saw + 63 + 3) / 4) + 1) * 4 * (sah - 1 + (sub ? 63 : 64)) + 64;
+        size_t need = (size_t)(sub ? 32 : 64) * 64 + (size_t)fp_pitch_words(saw) * 4 * (sah - 1 + (sub ? 63 : 64)) + 64;
         if (need > (size_t)FP_SMEM_BYTES) need = FP_SMEM_BYTES;
         d.fp_smem_bytes = (int)need;
     }
-    SVTB_LAUNCH(fullpel_kernel, dim3(n_sb, n), NT_SEARCH, d.fp_smem_bytes, st, d);
+    if (p->me_search_method != 0)
+        SVTB_LAUNCH(fullpel_kernel<true>, dim3(n_sb, n), NT_SEARCH, d.fp_smem_bytes, st, d);
+    else
+        SVTB_LAUNCH(fullpel_kernel<false>, dim3(n_sb, n), NT_SEARCH, d.fp_smem_bytes, st, d);
     SVTB_LAUNCH(finalize_kernel, n_sb, 96, 0, st, d);
     SVTB_CUDA_TRY(cudaGetLastError());
     return SVT_B200_OK;

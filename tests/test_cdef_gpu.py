@@ -65,6 +65,26 @@ def test_cdef_search_vs_oracle(case):
     np.testing.assert_array_equal(got, want)
 
 
+@pytest.mark.parametrize("case", [(192, 136, 8), (200, 72, 10)])
+def test_cdef_search_arbitrary_table(case):
+    """A strength list that is NOT a pri x sec grid takes the generic (one pass per strength) kernel."""
+    import gpu_runner as gr
+    w, h, bd = case
+    src, rec, mi_rows, mi_cols, skip = cdef_picture_case(w, h, bd, seed=5)
+    p = sb.CdefSearchParams()
+    p.mi_rows, p.mi_cols, p.pri_damping = mi_rows, mi_cols, 5
+    pris, secs = (0, 3, 3, 7, 15, 1, 0), (0, 1, 4, 2, 0, 4, 2)
+    p.n_strengths = len(pris)
+    for i, (a, b) in enumerate(zip(pris, secs)):
+        p.pri_strength[i], p.sec_strength[i] = a, b
+    nfb = ((mi_rows + 15) // 16) * ((mi_cols + 15) // 16)
+    want = np.zeros((2, nfb, 64), np.uint64)
+    rs, ss = rec.struct(), src.struct()
+    cm.oracle().orc_cdef_search(C.byref(p), C.byref(rs), C.byref(ss), cm.ptr(skip), skip.shape[1], cm.ptr(want))
+    got = gr.run_gpu_cdef_search(p, rec, src, skip)
+    np.testing.assert_array_equal(got, want)
+
+
 @pytest.mark.parametrize("case", [(192, 136, 8), (192, 136, 10), (264, 72, 8), (1920, 1080, 8)])
 def test_cdef_apply_vs_oracle(case):
     import gpu_runner as gr
