@@ -82,7 +82,8 @@ def workload_config(frames):
     return {"workload": f"{W}x{H} 8-bit yuv420p preset 8 hot path, {frames} frames/step (BASELINE configs[1] geometry)",
             "stages": ["me(hme+fullpel, %d+%d refs)" % (N_L0, N_L1), "encdec(residual+fwd txfm+quant+inv txfm+recon, all TUs)",
                        "dlf(frame, levels %s)" % (QINDEX_LEVELS,), "cdef(search 10 strengths + apply)"],
-            "l2_policy": f"ring of {RING} distinct input sets (> L2) cycled between steps"}
+            "l2_policy": f"ring of {RING} distinct input sets (> L2) cycled between steps",
+            "issue": "4 pictures in flight, one CUDA stream each"}
 
 
 def make_frames(seed, n):
@@ -339,43 +340,65 @@ def run_b200(args):
     def planes(tl):
         return sb.MePlanes(tl[0].data_ptr(), tl[1].data_ptr(), tl[2].data_ptr())
 
-    def hot_path(me_dev, src_dev, pred_dev, mi_dev, skip_dev, idx_dev, e2e=False, only=None):
+    # Pictures are independent once their references are resident, so the mini-GOP is issued the way the reference's
+    # picture-level pipeline would: NS pictures in flight, one CUDA stream each (kernel tails, copies and the host-side
+    # CDEF strength decision of one picture overlap the kernels of the others).
+    NS = 4
+    streams = [torch.cuda.Stream() for _ in range(NS)]
+    sps = [C.c_void_p(st.cuda_stream) for st in streams]
+    copy_stream = torch.cuda.Stream()
+    enc_scratch_s = [torch.empty(16384, dtype=torch.uint8, device="cuda") for _ in range(NS)]
+    e_idx = [torch.empty(nfb, dtype=torch.int8, device="cuda") for _ in range(F)]
+    h_idx_f = [torch.zeros(nfb, dtype=torch.int8).pin_memory() for _ in range(F)]
+
+    def frame_front(i, me_dev, src_dev, pred_dev, mi_dev, skip_dev, q, scratch):
+        """ME -> EncDec -> deblocking -> CDEF strength search of picture i on stream q."""
+        f = i + 2
+        fs, fp, fr = frame_struct(sb, proto, src_dev[f]), frame_struct(sb, proto, pred_dev[f]), frame_struct(sb, proto, d_rec[i])
+        r = [me_dev[f - 1], me_dev[f - 2], me_dev[f - 2], me_dev[f - 2], me_dev[f + 1], me_dev[f + 2], me_dev[f + 2], me_dev[f + 2]]
+        refs = (sb.MePlanes * 8)(*[planes(x) for x in r])
+        s = planes(me_dev[f])
+        o = d_me[i]
+        outs = sb.MeOutputs(o["best_sad"].data_ptr(), o["best_mv"].data_ptr(), o["hme"].data_ptr(), o["me_mv"].data_ptr(),
+                            o["me_cand"].data_ptr(), o["total_cand"].data_ptr(), o["rc"].data_ptr())
+        sb.check(lib.svt_b200_me_picture(C.byref(me_params), C.byref(s), refs, C.byref(outs), me_scratch[i].data_ptr(), q), lib)
+        for ts in tus:
+            sb.check(lib.svt_b200_encode_tus(C.byref(enc_params[ts]), C.byref(fs), C.byref(fp), C.byref(fr),
+                                             C.c_void_p(tu_dev[ts].data_ptr()), len(tus[ts]), C.c_void_p(d_q[i][ts].data_ptr()),
+                                             C.c_void_p(d_eob[i][ts].data_ptr()), C.c_void_p(scratch.data_ptr()), q), lib)
+        sb.check(lib.svt_b200_dlf_frame(C.byref(dlp), C.byref(fr), C.c_void_p(mi_dev.data_ptr()), q), lib)
+        sb.check(lib.svt_b200_cdef_search(C.byref(csp), C.byref(fr), C.byref(fs), C.c_void_p(skip_dev.data_ptr()), skip8.shape[1],
+                                          C.c_void_p(d_mse[i].data_ptr()), q), lib)
+
+    def frame_back(i, skip_dev, idx_dev, q):
+        """CDEF apply of picture i with the per-filter-block strength indices in idx_dev."""
+        fr, fo = frame_struct(sb, proto, d_rec[i]), frame_struct(sb, proto, d_out[i])
+        sb.check(lib.svt_b200_cdef_apply(C.byref(cap), C.byref(fr), C.byref(fo), C.c_void_p(skip_dev.data_ptr()), skip8.shape[1],
+                                         C.c_void_p(idx_dev.data_ptr()), q), lib)
+
+    def fork():
+        ev = torch.cuda.Event()
+        ev.record(stream)
+        for st in streams + [copy_stream]:
+            st.wait_event(ev)
+
+    def join():
+        for st in streams + [copy_stream]:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            stream.wait_event(ev)
+
+    def hot_path(me_dev, src_dev, pred_dev, mi_dev, skip_dev, idx_dev, only=None):
+        """Single-stream issue (per-stage timing)."""
         for i in range(F):
             f = i + 2
             fs, fp, fr = frame_struct(sb, proto, src_dev[f]), frame_struct(sb, proto, pred_dev[f]), frame_struct(sb, proto, d_rec[i])
             fo = frame_struct(sb, proto, d_out[i])
             if only is not None:
                 stage_call(only, i, f, me_dev, fs, fp, fr, fo, mi_dev, skip_dev, idx_dev)
-                continue
-            # 1. ME
-            r = [me_dev[f - 1], me_dev[f - 2], me_dev[f - 2], me_dev[f - 2], me_dev[f + 1], me_dev[f + 2], me_dev[f + 2], me_dev[f + 2]]
-            refs = (sb.MePlanes * 8)(*[planes(x) for x in r])
-            s = planes(me_dev[f])
-            o = d_me[i]
-            outs = sb.MeOutputs(o["best_sad"].data_ptr(), o["best_mv"].data_ptr(), o["hme"].data_ptr(), o["me_mv"].data_ptr(),
-                                o["me_cand"].data_ptr(), o["total_cand"].data_ptr(), o["rc"].data_ptr())
-            sb.check(lib.svt_b200_me_picture(C.byref(me_params), C.byref(s), refs, C.byref(outs), me_scratch[i].data_ptr(), sp), lib)
-            # 2. EncDec final pass (fused per TU)
-            for ts in tus:
-                sb.check(lib.svt_b200_encode_tus(C.byref(enc_params[ts]), C.byref(fs), C.byref(fp), C.byref(fr),
-                                                 C.c_void_p(tu_dev[ts].data_ptr()), len(tus[ts]), C.c_void_p(d_q[i][ts].data_ptr()),
-                                                 C.c_void_p(d_eob[i][ts].data_ptr()), C.c_void_p(enc_scratch.data_ptr()), sp), lib)
-            # 3. deblocking (in place on the reconstruction)
-            sb.check(lib.svt_b200_dlf_frame(C.byref(dlp), C.byref(fr), C.c_void_p(mi_dev.data_ptr()), sp), lib)
-            # 4. CDEF search, (host) strength decision, apply
-            sb.check(lib.svt_b200_cdef_search(C.byref(csp), C.byref(fr), C.byref(fs), C.c_void_p(skip_dev.data_ptr()), skip8.shape[1],
-                                              C.c_void_p(d_mse[i].data_ptr()), sp), lib)
-            if e2e:
-                with torch.cuda.stream(stream):
-                    h_mse[i].copy_(d_mse[i], non_blocking=True)
-                stream.synchronize()
-                # stand-in for finish_cdef_search (host side, out of scope §8a): best of the first 8 strengths per block
-                m = h_mse[i].numpy().view(np.uint64).reshape(2, nfb, 64)
-                h_idx.numpy()[...] = np.argmin(m[0, :, :8], axis=1).astype(np.int8)
-                with torch.cuda.stream(stream):
-                    idx_dev.copy_(h_idx, non_blocking=True)
-            sb.check(lib.svt_b200_cdef_apply(C.byref(cap), C.byref(fr), C.byref(fo), C.c_void_p(skip_dev.data_ptr()), skip8.shape[1],
-                                             C.c_void_p(idx_dev.data_ptr()), sp), lib)
+            else:
+                frame_front(i, me_dev, src_dev, pred_dev, mi_dev, skip_dev, sp, enc_scratch)
+                frame_back(i, skip_dev, idx_dev, sp)
 
     def stage_call(name, i, f, me_dev, fs, fp, fr, fo, mi_dev, skip_dev, idx_dev):
         """One stage of one frame (used by the per-stage roofline timing)."""
@@ -403,31 +426,61 @@ def run_b200(args):
 
     def step_resident(k):
         s = sets[k % RING]
-        hot_path(s.me_dev, s.src_dev, s.pred_dev, d_mi, d_skip, d_idx)
+        fork()
+        for i in range(F):
+            q = i % NS
+            frame_front(i, s.me_dev, s.src_dev, s.pred_dev, d_mi, d_skip, sps[q], enc_scratch_s[q])
+            frame_back(i, d_skip, d_idx, sps[q])
+        join()
 
     def step_e2e(k):
         s = sets[k % RING]
-        with torch.cuda.stream(stream):
+        fork()
+        # H2D: the ME planes of the F+4 pictures (shared by neighbouring pictures) on the copy stream, in display order
+        me_ready = []
+        with torch.cuda.stream(copy_stream):
+            e_mi.copy_(h_mi, non_blocking=True)
+            e_skip.copy_(h_skip, non_blocking=True)
             for j in range(F + 4):
                 for a, b in zip(e_me[j], s.me_host[j]):
                     a.copy_(b, non_blocking=True)
-            for j in range(2, F + 2):
-                for a, b in zip(e_src[j], s.src_host[j]):
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                me_ready.append(ev)
+        mse_ready = []
+        for i in range(F):
+            q, f = i % NS, i + 2
+            with torch.cuda.stream(streams[q]):
+                for a, b in zip(e_src[f], s.src_host[f]):
                     a.copy_(b, non_blocking=True)
-                for a, b in zip(e_pred[j], s.pred_host[j]):
+                for a, b in zip(e_pred[f], s.pred_host[f]):
                     a.copy_(b, non_blocking=True)
-            e_mi.copy_(h_mi, non_blocking=True)
-            e_skip.copy_(h_skip, non_blocking=True)
-        hot_path(e_me, e_src, e_pred, e_mi, e_skip, d_idx, e2e=True)
-        with torch.cuda.stream(stream):
-            for i in range(F):
+            streams[q].wait_event(me_ready[f + 2])
+            frame_front(i, e_me, e_src, e_pred, e_mi, e_skip, sps[q], enc_scratch_s[q])
+            with torch.cuda.stream(streams[q]):
+                h_mse[i].copy_(d_mse[i], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(streams[q])
+                mse_ready.append(ev)
+                # results that do not depend on the CDEF decision go home while the host decides
                 for kk, t in h_me[i].items():
                     t.copy_(d_me[i][kk], non_blocking=True)
                 for ts in tus:
                     h_q[i][ts].copy_(d_q[i][ts], non_blocking=True)
                     h_eob[i][ts].copy_(d_eob[i][ts], non_blocking=True)
+        for i in range(F):
+            q = i % NS
+            mse_ready[i].synchronize()
+            # stand-in for finish_cdef_search (host side, out of scope §8a): best of the first 8 strengths per block
+            m = h_mse[i].numpy().view(np.uint64).reshape(2, nfb, 64)
+            h_idx_f[i].numpy()[...] = np.argmin(m[0, :, :8], axis=1).astype(np.int8)
+            with torch.cuda.stream(streams[q]):
+                e_idx[i].copy_(h_idx_f[i], non_blocking=True)
+            frame_back(i, e_skip, e_idx[i], sps[q])
+            with torch.cuda.stream(streams[q]):
                 for a, b in zip(h_out[i], d_out[i]):
                     a.copy_(b, non_blocking=True)
+        join()
 
     h2d = (sum(t.numel() * t.element_size() for t in sets[0].me_host[0]) * (F + 4) +
            2 * F * sum(t.numel() * t.element_size() for t in sets[0].src_host[0]) + h_mi.numel() + h_skip.numel() + F * nfb)
