@@ -125,65 +125,116 @@ __device__ __forceinline__ int cdef_px(const int16_t *in, const CdefTaps &t, int
     return min(max(y, mn), mx);
 }
 
-// svt_cdef_find_dir_c on an 8x8 block of an int16 tile (serial; one thread per block)
-__device__ int find_dir(const int16_t *img, int stride, int *var, int coeff_shift) {
-    const int div_table[9] = {0, 840, 420, 280, 210, 168, 140, 120, 105};
-    int partial[8][15];
+// svt_cdef_find_dir_c (EbCdef.c:132-232) on an 8x8 block of an int16 tile, EIGHT lanes per block (L = lane & 7, the
+// eight lanes are consecutive and all active).  Lane L holds row L and column L of the block.  A directional line sum
+// ("partial") gathers one sample per row: with a rotate-by-(L -/+ j) shuffle of register j every lane collects the
+// two lines whose index is L mod 8 — e.g. for direction 0 (bin = i + j) lane L gets x[i][j] from lane i = (L - j) & 7,
+// which belongs to bin L when j <= L and to bin L + 8 otherwise.  Directions 1/3 use the row-pair sums, 5/7 are the
+// same patterns on the transposed block.  Weights 840/k are the reference's div_table.  Costs are then summed over
+// the eight lanes; every lane returns the direction and *var.
+__device__ __forceinline__ int find_dir8(const int16_t *img, int stride, int *var, int coeff_shift) {
+    const int lane = threadIdx.x & 31, L = lane & 7, base = lane & ~7;
+    int x[8], t[8];
 #pragma unroll
-    for (int a = 0; a < 8; a++)
-#pragma unroll
-        for (int b = 0; b < 15; b++) partial[a][b] = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++)
+    for (int j = 0; j < 8; j++) {
+        x[j] = (img[L * stride + j] >> coeff_shift) - 128;
+        t[j] = (img[j * stride + L] >> coeff_shift) - 128;
+    }
+    int c[8];
+    { // directions 2 (bin = i) and 6 (bin = j)
+        int sr = 0, sc = 0;
 #pragma unroll
         for (int j = 0; j < 8; j++) {
-            const int x = (img[i * stride + j] >> coeff_shift) - 128;
-            partial[0][i + j] += x;
-            partial[1][i + j / 2] += x;
-            partial[2][i] += x;
-            partial[3][3 + i - j / 2] += x;
-            partial[4][7 + i - j] += x;
-            partial[5][3 - i / 2 + j] += x;
-            partial[6][j] += x;
-            partial[7][i / 2 + j] += x;
+            sr += x[j];
+            sc += t[j];
         }
-    int cost[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        cost[2] += partial[2][i] * partial[2][i];
-        cost[6] += partial[6][i] * partial[6][i];
+        c[2] = sr * sr * 105;
+        c[6] = sc * sc * 105;
     }
-    cost[2] *= div_table[8];
-    cost[6] *= div_table[8];
+    { // direction 0: bin = i + j;  direction 4: bin = 7 + i - j
+        int a0 = 0, b0 = 0, a4 = 0, b4 = 0;
 #pragma unroll
-    for (int i = 0; i < 7; i++) {
-        cost[0] += (partial[0][i] * partial[0][i] + partial[0][14 - i] * partial[0][14 - i]) * div_table[i + 1];
-        cost[4] += (partial[4][i] * partial[4][i] + partial[4][14 - i] * partial[4][14 - i]) * div_table[i + 1];
+        for (int j = 0; j < 8; j++) {
+            const int v0 = __shfl_sync(0xffffffffu, x[j], base + ((L - j) & 7));
+            const int v4 = __shfl_sync(0xffffffffu, x[j], base + ((L + j) & 7));
+            if (j <= L)
+                a0 += v0; // bin L
+            else
+                b0 += v0; // bin L + 8
+            if (L + j < 8)
+                a4 += v4; // bin 7 + L
+            else
+                b4 += v4; // bin L - 1
+        }
+        c[0] = a0 * a0 * (840 / (L + 1)) + (L < 7 ? b0 * b0 * (840 / (7 - L)) : 0);
+        c[4] = a4 * a4 * (840 / (8 - L)) + (L > 0 ? b4 * b4 * (840 / L) : 0);
     }
-    cost[0] += partial[0][7] * partial[0][7] * div_table[8];
-    cost[4] += partial[4][7] * partial[4][7] * div_table[8];
+    // odd directions: bins 0..10, weight 105 for bins 3..7, 420/(b+1) for b < 3, 420/(11-b) for b > 7
+    const int w_lo = L < 3 ? 420 / (L + 1) : 105; // bin L
+    const int w_lo8 = L < 3 ? 420 / (3 - L) : 0; // bin L + 8 (exists for L <= 2)
+    const int w_hi = L < 5 ? 105 : 420 / (8 - L); // bin 3 + L
+    const int w_hi5 = L >= 5 ? 420 / (L - 4) : 0; // bin L - 5 (exists for L >= 5)
+    int a1 = 0, b1 = 0, a3 = 0, b3 = 0, a7 = 0, b7 = 0, a5 = 0, b5 = 0;
 #pragma unroll
-    for (int d = 1; d < 8; d += 2) {
-#pragma unroll
-        for (int j = 0; j < 5; j++) cost[d] += partial[d][3 + j] * partial[d][3 + j];
-        cost[d] *= div_table[8];
-#pragma unroll
-        for (int j = 0; j < 3; j++)
-            cost[d] += (partial[d][j] * partial[d][j] + partial[d][10 - j] * partial[d][10 - j]) * div_table[2 * j + 2];
+    for (int s = 0; s < 4; s++) {
+        const int pr = x[2 * s] + x[2 * s + 1]; // row L, column pair s
+        const int pc = t[2 * s] + t[2 * s + 1]; // column L, row pair s
+        const int v1 = __shfl_sync(0xffffffffu, pr, base + ((L - s) & 7)); // direction 1: bin = i + j/2
+        const int v3 = __shfl_sync(0xffffffffu, pr, base + ((L + s) & 7)); // direction 3: bin = 3 + i - j/2
+        const int v7 = __shfl_sync(0xffffffffu, pc, base + ((L - s) & 7)); // direction 7: bin = i/2 + j
+        const int v5 = __shfl_sync(0xffffffffu, pc, base + ((L + s) & 7)); // direction 5: bin = 3 - i/2 + j
+        if (s <= L) {
+            a1 += v1;
+            a7 += v7;
+        } else {
+            b1 += v1;
+            b7 += v7;
+        }
+        if (L + s < 8) {
+            a3 += v3;
+            a5 += v5;
+        } else {
+            b3 += v3;
+            b5 += v5;
+        }
     }
+    c[1] = a1 * a1 * w_lo + b1 * b1 * w_lo8;
+    c[7] = a7 * a7 * w_lo + b7 * b7 * w_lo8;
+    c[3] = a3 * a3 * w_hi + b3 * b3 * w_hi5;
+    c[5] = a5 * a5 * w_hi + b5 * b5 * w_hi5;
+#pragma unroll
+    for (int d = 0; d < 8; d++)
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) c[d] += __shfl_xor_sync(0xffffffffu, c[d], o);
     int best_cost = 0, best_dir = 0;
 #pragma unroll
     for (int d = 0; d < 8; d++)
-        if (cost[d] > best_cost) {
-            best_cost = cost[d];
+        if (c[d] > best_cost) {
+            best_cost = c[d];
             best_dir = d;
         }
     int orth = 0;
 #pragma unroll
     for (int d = 0; d < 8; d++)
-        if (d == ((best_dir + 4) & 7)) orth = cost[d];
+        if (d == ((best_dir + 4) & 7)) orth = c[d];
     *var = (best_cost - orth) >> 10;
     return best_dir;
+}
+
+// directions + variances of `count` listed blocks (by/bx in 8x8 units inside the tile), eight lanes per block
+__device__ __forceinline__ void find_dirs(const int16_t *in, const uint8_t *s_by, const uint8_t *s_bx, int count, int cs, int8_t *s_dir,
+                                          int *s_var) {
+    const int tid = threadIdx.x;
+    for (int b0 = 0; b0 < count; b0 += NT / 8) {
+        const int b = b0 + (tid >> 3);
+        const int bb = b < count ? b : 0;
+        int v;
+        const int dir = find_dir8(in + 8 * s_by[bb] * TS + 8 * s_bx[bb], TS, &v, cs);
+        if (b < count && (tid & 7) == 0) {
+            s_dir[b] = (int8_t)dir;
+            s_var[b] = v;
+        }
+    }
 }
 
 struct FrameDev {
@@ -196,14 +247,56 @@ __device__ __forceinline__ int ldpx(const void *p, size_t off) {
     return reinterpret_cast<const T *>(p)[off];
 }
 
-// Stage the filter block of plane `pli` (+2 rim; outside the frame = VERY_LARGE) into an int16 tile.
+// Stage the filter block of plane `pli` (+2 rim; outside the frame = VERY_LARGE) into an int16 tile.  Work item = four
+// horizontally adjacent samples starting at a frame x that is a multiple of 4 (tile columns 4g-2 .. 4g+1, written as
+// two aligned 32-bit shared stores); interior groups are read with one or two 32-bit global loads, groups that
+// touch the frame edge sample by sample.  Two items per thread are loaded before the first is stored (the staging is
+// global-latency bound: ncu long_scoreboard on the store).
 template <typename T>
-__device__ void load_tile(const void *plane, int stride, int pw, int ph, int y0, int x0, int bh, int bw, int16_t *tile) {
-    const int rw = bw + 4;
-    for (int i = threadIdx.x; i < (bh + 4) * rw; i += NT) {
-        const int r = i / rw, c = i - r * rw;
-        const int yy = y0 + r - 2, xx = x0 + c - 2;
-        tile[r * TS + c] = (yy >= 0 && yy < ph && xx >= 0 && xx < pw) ? (int16_t)ldpx<T>(plane, (size_t)yy * stride + xx) : (int16_t)VERY_LARGE;
+__device__ __forceinline__ void load_group(const T *plane, int stride, int pw, int ph, int yy, int xx, int (&v)[4]) {
+    if (yy < 0 || yy >= ph) {
+        v[0] = v[1] = v[2] = v[3] = VERY_LARGE;
+        return;
+    }
+    const T *p = plane + (size_t)yy * stride + xx;
+    if (xx >= 0 && xx + 3 < pw) {
+        if (sizeof(T) == 1) {
+            const uintptr_t a = (uintptr_t)p;
+            const uint32_t *g = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+            const uint32_t w = __funnelshift_r(g[0], (a & 3) ? g[1] : 0u, (int)(a & 3) * 8);
+            v[0] = w & 0xff, v[1] = (w >> 8) & 0xff, v[2] = (w >> 16) & 0xff, v[3] = w >> 24;
+            return;
+        }
+        if (((uintptr_t)p & 3) == 0) {
+            const uint32_t w0 = reinterpret_cast<const uint32_t *>(p)[0], w1 = reinterpret_cast<const uint32_t *>(p)[1];
+            v[0] = w0 & 0xffff, v[1] = w0 >> 16, v[2] = w1 & 0xffff, v[3] = w1 >> 16;
+            return;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) v[j] = (xx + j >= 0 && xx + j < pw) ? (int)p[j] : VERY_LARGE;
+}
+template <typename T>
+__device__ void load_tile(const void *plane_v, int stride, int pw, int ph, int y0, int x0, int bh, int bw, int16_t *tile) {
+    const T *plane = reinterpret_cast<const T *>(plane_v);
+    const int gpr = (bw + 9) >> 2, total = (bh + 4) * gpr; // groups per tile row (bw is even)
+    for (int i = threadIdx.x; i < total; i += 2 * NT) {
+        int v[2][4], r[2], g[2];
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int ii = i + u * NT;
+            r[u] = ii / gpr;
+            g[u] = ii - r[u] * gpr;
+            if (ii < total) load_group<T>(plane, stride, pw, ph, y0 + r[u] - 2, x0 - 4 + 4 * g[u], v[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            if (i + u * NT >= total) continue;
+            const int c0 = 4 * g[u] - 2; // tile column of the group's first sample
+            uint32_t *row = reinterpret_cast<uint32_t *>(tile + r[u] * TS);
+            if (c0 >= 0 && c0 + 1 < bw + 4) row[c0 >> 1] = (uint32_t)(uint16_t)v[u][0] | ((uint32_t)(uint16_t)v[u][1] << 16);
+            if (c0 + 3 < bw + 4) row[(c0 + 2) >> 1] = (uint32_t)(uint16_t)v[u][2] | ((uint32_t)(uint16_t)v[u][3] << 16);
+        }
     }
 }
 
@@ -245,16 +338,22 @@ __global__ void __launch_bounds__(NT) cdef_search_kernel(const __grid_constant__
     const bool border = fbr == 0 || fbc == 0 || 16 * (fbr + 1) >= p.mi_rows || 16 * (fbc + 1) >= p.mi_cols;
     uint64_t *out_y = d.mse + ((size_t)fb) * 64;
     uint64_t *out_c = d.mse + ((size_t)d.nvfb * d.nhfb + fb) * 64;
-    if (tid == 0) { // svt_sb_compute_cdef_list: raster list of the non-skip 8x8 blocks
-        int n = 0;
-        for (int r = 0; r < nvb; r += 2)
-            for (int c = 0; c < nhb; c += 2)
-                if (!d.skip8[(size_t)((16 * fbr + r) >> 1) * d.skip_stride + ((16 * fbc + c) >> 1)]) {
-                    s_by[n] = (uint8_t)(r >> 1);
-                    s_bx[n] = (uint8_t)(c >> 1);
-                    n++;
-                }
-        s_count = n;
+    if (tid < 32) { // svt_sb_compute_cdef_list: raster list of the non-skip 8x8 blocks (two blocks per lane, ballots)
+        unsigned int m[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int b = tid + 32 * h, r = (b >> 3) * 2, c = (b & 7) * 2;
+            const bool on = r < nvb && c < nhb && !d.skip8[(size_t)((16 * fbr + r) >> 1) * d.skip_stride + ((16 * fbc + c) >> 1)];
+            m[h] = __ballot_sync(0xffffffffu, on);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+            if ((m[h] >> tid) & 1u) {
+                const int n = (h ? __popc(m[0]) : 0) + __popc(m[h] & ((1u << tid) - 1u));
+                s_by[n] = (uint8_t)((tid + 32 * h) >> 3);
+                s_bx[n] = (uint8_t)(tid & 7);
+            }
+        if (tid == 0) s_count = __popc(m[0]) + __popc(m[1]);
     }
     __syncthreads();
     const int count = s_count;
@@ -276,11 +375,7 @@ __global__ void __launch_bounds__(NT) cdef_search_kernel(const __grid_constant__
         __syncthreads();
         const int16_t *in = tile + 2 * TS + 2;
         if (pli == 0) {
-            if (tid < count) {
-                int v;
-                s_dir[tid] = (int8_t)find_dir(in + 8 * s_by[tid] * TS + 8 * s_bx[tid], TS, &v, cs);
-                s_var[tid] = v;
-            }
+            find_dirs(in, s_by, s_bx, count, cs, s_dir, s_var);
             __syncthreads();
         }
         const int damping = p.pri_damping + cs - (pli != 0);
@@ -505,7 +600,7 @@ __device__ __noinline__ void plane_search_grid(const CdefSearchDev &d, const Cde
 }
 
 template <typename T, int NSEC>
-__global__ void __launch_bounds__(NT, 2) cdef_search_grid_kernel(const __grid_constant__ CdefSearchGridDev gd) {
+__global__ void __launch_bounds__(NT, 4) cdef_search_grid_kernel(const __grid_constant__ CdefSearchGridDev gd) {
     __shared__ int16_t tile[68 * TS];
     __shared__ uint8_t s_by[64], s_bx[64];
     __shared__ int8_t s_dir[64];
@@ -521,16 +616,22 @@ __global__ void __launch_bounds__(NT, 2) cdef_search_grid_kernel(const __grid_co
     const bool border = fbr == 0 || fbc == 0 || 16 * (fbr + 1) >= p.mi_rows || 16 * (fbc + 1) >= p.mi_cols;
     uint64_t *out_y = d.mse + ((size_t)fb) * 64;
     uint64_t *out_c = d.mse + ((size_t)d.nvfb * d.nhfb + fb) * 64;
-    if (tid == 0) { // svt_sb_compute_cdef_list: raster list of the non-skip 8x8 blocks
-        int n = 0;
-        for (int r = 0; r < nvb; r += 2)
-            for (int c = 0; c < nhb; c += 2)
-                if (!d.skip8[(size_t)((16 * fbr + r) >> 1) * d.skip_stride + ((16 * fbc + c) >> 1)]) {
-                    s_by[n] = (uint8_t)(r >> 1);
-                    s_bx[n] = (uint8_t)(c >> 1);
-                    n++;
-                }
-        s_count = n;
+    if (tid < 32) { // svt_sb_compute_cdef_list: raster list of the non-skip 8x8 blocks (two blocks per lane, ballots)
+        unsigned int m[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int b = tid + 32 * h, r = (b >> 3) * 2, c = (b & 7) * 2;
+            const bool on = r < nvb && c < nhb && !d.skip8[(size_t)((16 * fbr + r) >> 1) * d.skip_stride + ((16 * fbc + c) >> 1)];
+            m[h] = __ballot_sync(0xffffffffu, on);
+        }
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+            if ((m[h] >> tid) & 1u) {
+                const int n = (h ? __popc(m[0]) : 0) + __popc(m[h] & ((1u << tid) - 1u));
+                s_by[n] = (uint8_t)((tid + 32 * h) >> 3);
+                s_bx[n] = (uint8_t)(tid & 7);
+            }
+        if (tid == 0) s_count = __popc(m[0]) + __popc(m[1]);
     }
     __syncthreads();
     const int count = s_count;
@@ -552,11 +653,7 @@ __global__ void __launch_bounds__(NT, 2) cdef_search_grid_kernel(const __grid_co
         __syncthreads();
         const int16_t *in = tile + 2 * TS + 2;
         if (pli == 0) {
-            if (tid < count) {
-                int v;
-                s_dir[tid] = (int8_t)find_dir(in + 8 * s_by[tid] * TS + 8 * s_bx[tid], TS, &v, cs);
-                s_var[tid] = v;
-            }
+            find_dirs(in, s_by, s_bx, count, cs, s_dir, s_var);
             __syncthreads();
         }
         const int damping = p.pri_damping + cs - (pli != 0);
@@ -638,10 +735,14 @@ __global__ void __launch_bounds__(NT) cdef_apply_kernel(const __grid_constant__ 
         __syncthreads();
         const int16_t *in = tile + 2 * TS + 2;
         if (pli == 0 && filt) {
-            if (tid < 64 && !s_skip[tid]) {
+            for (int b0 = 0; b0 < 64; b0 += NT / 8) { // eight lanes per block; skipped blocks are computed and dropped
+                const int b = b0 + (tid >> 3);
                 int v;
-                s_dir[tid] = (int8_t)find_dir(in + 8 * (tid >> 3) * TS + 8 * (tid & 7), TS, &v, cs);
-                s_var[tid] = v;
+                const int dir = find_dir8(in + 8 * (b >> 3) * TS + 8 * (b & 7), TS, &v, cs);
+                if (!s_skip[b] && (tid & 7) == 0) {
+                    s_dir[b] = (int8_t)dir;
+                    s_var[b] = v;
+                }
             }
             __syncthreads();
         }
@@ -664,12 +765,13 @@ __global__ void __launch_bounds__(NT) cdef_apply_kernel(const __grid_constant__ 
 
 // drop-in kernels ----------------------------------------------------------------------------------------
 __global__ void find_dir_kernel(const uint16_t *img, int stride, int coeff_shift, int *out) {
+    __shared__ int16_t t[64];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) t[i] = (int16_t)img[(i >> 3) * stride + (i & 7)];
+    __syncthreads();
+    int v;
+    const int dir = find_dir8(t, 8, &v, coeff_shift); // one warp = four redundant groups of eight lanes
     if (threadIdx.x == 0) {
-        int16_t t[64];
-        for (int i = 0; i < 8; i++)
-            for (int j = 0; j < 8; j++) t[i * 8 + j] = (int16_t)img[i * stride + j];
-        int v;
-        out[0] = find_dir(t, 8, &v, coeff_shift);
+        out[0] = dir;
         out[1] = v;
     }
 }

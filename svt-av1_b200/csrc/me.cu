@@ -47,11 +47,10 @@ __device__ __forceinline__ int scaled_dist(int dist) { return ((dist * 5) / 8) +
 // Stage `rows` rows of `nbytes` bytes (arbitrary alignment, global) into shared-memory words of pitch `wpw`:
 // one warp per row, one lane per 32-bit word, aligned LDG + funnel shift instead of byte loads.  Only the aligned
 // words that overlap [src, src + nbytes) are read (at most 3 bytes of over-read, inside the padded planes).
-template <int NT>
-__device__ __forceinline__ void stage_rows(uint32_t *dst, int wpw, const uint8_t *__restrict__ src, ptrdiff_t stride, int rows,
-                                           int nbytes) {
+__device__ __forceinline__ void stage_rows_n(uint32_t *dst, int wpw, const uint8_t *__restrict__ src, ptrdiff_t stride, int rows,
+                                             int nbytes, int nwarps) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int row = warp; row < rows; row += NT / 32) {
+    for (int row = warp; row < rows; row += nwarps) {
         const uintptr_t a = (uintptr_t)(src + (ptrdiff_t)row * stride);
         const uint32_t *ga = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
         const int sh = (int)(a & 3) * 8;
@@ -61,6 +60,11 @@ __device__ __forceinline__ void stage_rows(uint32_t *dst, int wpw, const uint8_t
             dst[row * wpw + wd] = __funnelshift_r(lo, hi, sh);
         }
     }
+}
+template <int NT>
+__device__ __forceinline__ void stage_rows(uint32_t *dst, int wpw, const uint8_t *__restrict__ src, ptrdiff_t stride, int rows,
+                                           int nbytes) {
+    stage_rows_n(dst, wpw, src, stride, rows, nbytes, NT / 32);
 }
 
 // -----------------------------------------------------------------------------------------------------
@@ -151,12 +155,15 @@ struct RawHme { // one (sb, list, ref): result of the last enabled HME level, be
     uint64_t sad;
 };
 
+struct HmeState;
 struct MeDev {
     SvtB200MeParams p;
     SvtB200MePlanes src;
     SvtB200MePlanes refs[2][4];
     SvtB200MeOutputs out;
     RawHme *raw; // [n_sb][2][4]
+    HmeState *hstate; // [n_sb]: search centres / pruning / search-area divisors, written by the SB's last HME CTA
+    unsigned int *hme_done; // [n_sb]: HME CTAs of the SB that have published their result
     int sbs_x, sbs_y;
     int slot_l[8], slot_r[8], n_slots;
     int fp_smem_bytes; // dynamic shared memory given to fullpel_kernel
@@ -215,6 +222,26 @@ __device__ void derive_hme_state(const SvtB200MeParams &p, const RawHme *raw /*[
     }
 }
 
+// Tail of both HME kernels (thread 0): publish this (SB, reference) result; the CTA that completes the SB derives the
+// cross-reference state ONCE for the full-pel and finalize kernels (it was a serial prologue in each of their CTAs).
+__device__ void hme_publish(const MeDev &d, int sb, RawHme *out, const RawHme &w) {
+    *out = w;
+    __threadfence();
+    const unsigned int prev = atomicAdd(&d.hme_done[sb], 1u);
+    if (prev + 1 == (unsigned int)d.n_slots) {
+        __threadfence();
+        RawHme raw[8];
+        const ulonglong2 *g = reinterpret_cast<const ulonglong2 *>(d.raw + (size_t)sb * 8);
+        for (int i = 0; i < 8; i++) { // L2 reads: the other CTAs' results were written by other SMs
+            const ulonglong2 v = __ldcg(g + i);
+            memcpy(&raw[i], &v, sizeof(RawHme));
+        }
+        HmeState h;
+        derive_hme_state(d.p, raw, h);
+        d.hstate[sb] = h;
+    }
+}
+
 constexpr int HME_SMEM_BYTES = 40 * 1024;
 
 // Kernel A (generic fallback, any window size: regions searched one after another, windows chunked through
@@ -232,7 +259,7 @@ __global__ void __launch_bounds__(NT_SEARCH) hme_kernel_generic(const __grid_con
     if (!active) {
         if (threadIdx.x == 0) {
             RawHme z = {0, 0, 0, 0};
-            *out = z;
+            hme_publish(d, sb, out, z);
         }
         return;
     }
@@ -351,7 +378,7 @@ __global__ void __launch_bounds__(NT_SEARCH) hme_kernel_generic(const __grid_con
         w.y = (int16_t)best_y;
         w.valid = 1;
         w.sad = best_sad;
-        *out = w;
+        hme_publish(d, sb, out, w);
     }
 }
 
@@ -369,6 +396,7 @@ struct HmeJob {
     int xo, yo, saw, sah;
     int woff, wpw; // window offset (words) in smem, words per row
     int q, gpr, t0, nt; // positions per task (2|4), task groups per row, first (padded) task id, padded task count
+    uint32_t magic; // ceil(2^32 / (4 * gpr)): task id -> search row by one IMAD.HI
 };
 
 __host__ __device__ __forceinline__ int hme_pitch_words(int saw, int w, int q) {
@@ -383,6 +411,7 @@ __device__ __forceinline__ void hme_task_rows(const uint32_t *__restrict__ s_src
     uint32_t a[Q][2];
 #pragma unroll
     for (int q = 0; q < Q; q++) a[q][0] = a[q][1] = 0;
+#pragma unroll 1
     for (int r = r0; r < bh; r += rstep) {
         uint32_t s[W], w[W + Q], f[W + Q - 1];
         const uint32_t *sp = s_src + r * W;
@@ -416,12 +445,14 @@ __device__ __forceinline__ void hme_task_rows(const uint32_t *__restrict__ s_src
     for (int q = 0; q < Q; q++) acc[q] = a[q][0] + a[q][1];
 }
 
-// one task round of a warp: decode, search, reduce.  Returns this lane's best key (~0 if none).
+// one task round of a warp: decode, search, reduce.  Returns this lane's best key (~0 if none): packed 32-bit
+// (sad << kshift | index) when the level's SAD and index ranges fit (kshift != 0), else the index in the low word of a
+// 64-bit key; the caller reduces accordingly.
 template <int W, int Q>
 __device__ __forceinline__ unsigned long long hme_task(const HmeJob &jb, const uint32_t *s_src, const uint32_t *smem, int u, bool live,
-                                                       int k, int bh, int tpp, int sub) {
+                                                       int k, int bh, int tpp, int sub, int kshift) {
     const int tpr = 4 * jb.gpr;
-    const int ys = live ? u / tpr : 0;
+    const int ys = live ? (int)__umulhi((uint32_t)u, jb.magic) : 0; // u / tpr (u < 2^16, tpr <= 2^8: exact)
     const int rem = live ? u - ys * tpr : 0;
     const int m = rem >> 2, c = rem & 3;
     uint32_t acc[Q];
@@ -431,38 +462,72 @@ __device__ __forceinline__ unsigned long long hme_task(const HmeJob &jb, const u
         for (int q = 0; q < Q; q++) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], o);
     unsigned long long best = ~0ull;
     if (live && sub == 0) {
+        const int x0 = 4 * Q * m + c;
+        const uint32_t i0 = (uint32_t)(ys * jb.saw + x0);
+        if (kshift) {
+            uint32_t b32 = 0xffffffffu;
 #pragma unroll
-        for (int q = 0; q < Q; q++) {
-            const int x = 4 * Q * m + c + 4 * q;
-            const unsigned long long key = ((unsigned long long)acc[q] << 32) | (uint32_t)(ys * jb.saw + x);
-            if (x < jb.saw && key < best) best = key;
+            for (int q = 0; q < Q; q++) b32 = min(b32, (x0 + 4 * q < jb.saw) ? (acc[q] << kshift) + i0 + 4 * q : 0xffffffffu);
+            best = b32;
+        } else {
+#pragma unroll
+            for (int q = 0; q < Q; q++) {
+                const unsigned long long key = ((unsigned long long)acc[q] << 32) | (i0 + 4 * q);
+                if (x0 + 4 * q < jb.saw && key < best) best = key;
+            }
         }
     }
     return best;
 }
 
-template <int NT>
-__device__ void stage_rows_flat(uint32_t *dst, int wpw, const uint8_t *__restrict__ src, ptrdiff_t stride, int rows, int nbytes) {
-    for (int i = threadIdx.x; i < rows * wpw; i += NT) {
-        const int row = i / wpw, wd = i - row * wpw;
-        const uintptr_t a = (uintptr_t)(src + (ptrdiff_t)row * stride);
-        const uint32_t *ga = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
-        const int need = (nbytes + (int)(a & 3) + 3) >> 2;
-        const uint32_t lo = wd < need ? ga[wd] : 0u, hi = (wd + 1) < need ? ga[wd + 1] : 0u;
-        dst[i] = __funnelshift_r(lo, hi, (int)(a & 3) * 8);
+// Stage `rows` rows of `nbytes` bytes (arbitrary alignment, global) into shared-memory words of pitch `wpw`; element
+// i = row * wpw + word is handled by thread i mod nt.  Four independent elements per thread are loaded before the
+// first is stored, so four global-load latencies overlap (the staging phases are latency-bound: ncu long_scoreboard).
+__device__ __forceinline__ void stage_flat(uint32_t *dst, int wpw, const uint8_t *__restrict__ src, ptrdiff_t stride, int rows,
+                                           int nbytes, int nt) {
+    const int total = rows * wpw;
+    int i = threadIdx.x;
+    int row = i / wpw, wd = i - row * wpw;
+    const int dr = nt / wpw, dw = nt - dr * wpw; // advance of (row, word) per step of nt elements: no division in the loop
+    while (i < total) {
+        uint32_t lo[4], hi[4];
+        int sh[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            lo[u] = hi[u] = 0;
+            sh[u] = 0;
+            if (i + u * nt < total) {
+                const uintptr_t a = (uintptr_t)(src + (ptrdiff_t)row * stride);
+                const uint32_t *ga = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+                const int need = (nbytes + (int)(a & 3) + 3) >> 2; // aligned words covering the row
+                if (wd < need) lo[u] = ga[wd];
+                if (wd + 1 < need) hi[u] = ga[wd + 1];
+                sh[u] = (int)(a & 3) * 8;
+            }
+            row += dr;
+            wd += dw;
+            if (wd >= wpw) {
+                wd -= wpw;
+                row++;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (i + u * nt < total) dst[i + u * nt] = __funnelshift_r(lo[u], hi[u], sh[u]);
+        i += 4 * nt;
     }
 }
 
 template <int NT, int W>
 __device__ void hme_level_search_aligned(const uint8_t *__restrict__ src, int src_stride, int raw_stride, int k, int bh,
-                                         const HmeJob *jobs, int njobs, int tpp, int ntasks, uint32_t *smem,
+                                         const HmeJob *jobs, int njobs, int tpp, int ntasks, int kshift, uint32_t *smem,
                                          unsigned long long *s_key) {
     const int tid = threadIdx.x;
-    stage_rows_flat<NT>(smem, W, src, src_stride, bh, 4 * W);
+    stage_flat(smem, W, src, src_stride, bh, 4 * W, NT);
     const int span = (bh - 1) * k + 1;
     for (int j = 0; j < njobs; j++) {
         const HmeJob jb = jobs[j];
-        stage_rows_flat<NT>(smem + jb.woff, jb.wpw, jb.ref, raw_stride, jb.sah - 1 + span, jb.saw - 1 + 4 * W);
+        stage_flat(smem + jb.woff, jb.wpw, jb.ref, raw_stride, jb.sah - 1 + span, jb.saw - 1 + 4 * W, NT);
     }
     __syncthreads();
     const int sub = tid & (tpp - 1), gpt = NT / tpp;
@@ -474,9 +539,14 @@ __device__ void hme_level_search_aligned(const uint8_t *__restrict__ src, int sr
         const HmeJob jb = jobs[j];
         const int u = t - jb.t0;
         const bool live = u < jb.sah * 4 * jb.gpr;
-        unsigned long long best = jb.q == 4 ? hme_task<W, 4>(jb, smem, smem, u, live, k, bh, tpp, sub)
-                                            : hme_task<W, 2>(jb, smem, smem, u, live, k, bh, tpp, sub);
-        best = warp_min_u64(best);
+        unsigned long long best = jb.q == 4 ? hme_task<W, 4>(jb, smem, smem, u, live, k, bh, tpp, sub, kshift)
+                                            : hme_task<W, 2>(jb, smem, smem, u, live, k, bh, tpp, sub, kshift);
+        if (kshift) {
+            const uint32_t m32 = __reduce_min_sync(0xffffffffu, (uint32_t)best);
+            best = m32 == 0xffffffffu ? ~0ull : ((unsigned long long)(m32 >> kshift) << 32) | (m32 & ((1u << kshift) - 1u));
+        } else {
+            best = warp_min_u64(best);
+        }
         if ((tid & 31) == 0 && best != ~0ull) atomicMin(&s_key[j], best);
     }
     __syncthreads();
@@ -542,11 +612,11 @@ __device__ void hme_level_search(const uint8_t *__restrict__ src, int src_stride
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(NT_SEARCH) hme_kernel(const __grid_constant__ MeDev d) {
+__global__ void __launch_bounds__(NT_SEARCH, 4) hme_kernel(const __grid_constant__ MeDev d) {
     extern __shared__ uint4 smem4[];
     uint32_t *smem = reinterpret_cast<uint32_t *>(smem4);
     __shared__ HmeJob s_jobs[4];
-    __shared__ int s_tpp, s_ntasks;
+    __shared__ int s_tpp, s_ntasks, s_kshift;
     __shared__ unsigned long long s_key[4];
     __shared__ int s_cx[4], s_cy[4];
     __shared__ unsigned long long s_csad[4];
@@ -560,7 +630,7 @@ __global__ void __launch_bounds__(NT_SEARCH) hme_kernel(const __grid_constant__ 
     if (!active) {
         if (tid == 0) {
             RawHme z = {0, 0, 0, 0};
-            *out = z;
+            hme_publish(d, sb, out, z);
         }
         return;
     }
@@ -587,7 +657,11 @@ __global__ void __launch_bounds__(NT_SEARCH) hme_kernel(const __grid_constant__ 
         const uint8_t *srcp = level == 0 ? d.src.sixteenth : level == 1 ? d.src.quarter : d.src.full;
         const uint8_t *refp = level == 0 ? rp.sixteenth : level == 1 ? rp.quarter : rp.full;
         __syncthreads(); // previous level's results (s_cx/s_cy) are final; smem free
-        if (tid < njobs) { // job geometry: the window arithmetic of hme_level_0/1/2
+        if (tid < 4) { // job geometry: the window arithmetic of hme_level_0/1/2, one lane per search region
+            const bool jl = tid < njobs;
+            HmeJob jb;
+            memset(&jb, 0, sizeof(jb));
+            if (jl) {
             const int rx = tid % nrw, ry = tid / nrw;
             int saw, sah, xo, yo;
             if (level == 0) {
@@ -621,7 +695,6 @@ __global__ void __launch_bounds__(NT_SEARCH) hme_kernel(const __grid_constant__ 
                 saw = saw < 8 ? saw : saw & ~0x07;
                 clamp_window(o_y, level == 1 ? pl.origin_y - 1 : 63, pl.height, yo, sah);
             }
-            HmeJob jb;
             jb.ref = refp + (size_t)(pl.origin_y + o_y + yo) * pl.stride + pl.origin_x + o_x + xo;
             jb.xo = xo;
             jb.yo = yo;
@@ -629,31 +702,47 @@ __global__ void __launch_bounds__(NT_SEARCH) hme_kernel(const __grid_constant__ 
             jb.sah = sah;
             jb.q = (saw & 15) ? 2 : 4;
             jb.gpr = (saw + 4 * jb.q - 1) / (4 * jb.q);
+            jb.magic = (uint32_t)((0x100000000ull + 4 * jb.gpr - 1) / (4 * jb.gpr));
             jb.wpw = aligned ? hme_pitch_words(saw, bw >> 2, jb.q) : ((saw - 1 + bw + 3) >> 2) + 1;
-            jb.woff = jb.t0 = jb.nt = 0;
-            s_jobs[tid] = jb;
-            s_key[tid] = ~0ull;
-        }
-        __syncthreads();
-        if (tid == 0) { // window offsets (words) after the source block; task ranges padded to whole warps
-            int off = ((bw + 3) >> 2) * bh;
-            for (int j = 0; j < njobs; j++) {
-                s_jobs[j].woff = off;
-                off += s_jobs[j].wpw * (s_jobs[j].sah - 1 + (bh - 1) * k + 1);
             }
-            int tpp = 32;
+            // window offsets (words) after the source block, task ranges padded to whole warps, rows-per-task split and
+            // key packing: prefix sums / maxima over the four job lanes by shuffles (no serial section, one barrier)
+            const unsigned m4 = 0xfu;
+            const int wsz = jl ? jb.wpw * (jb.sah - 1 + (bh - 1) * k + 1) : 0;
+            int inc = wsz, v = __shfl_up_sync(m4, inc, 1);
+            if (tid >= 1) inc += v;
+            v = __shfl_up_sync(m4, inc, 2);
+            if (tid >= 2) inc += v;
+            jb.woff = ((bw + 3) >> 2) * bh + inc - wsz;
+            const int T = jl ? jb.sah * 4 * jb.gpr : 0;
+            int tpp = 32, tot = 0;
             for (;; tpp >>= 1) {
                 const int pad = 32 / tpp;
-                int tot = 0;
-                for (int j = 0; j < njobs; j++) {
-                    s_jobs[j].t0 = tot;
-                    s_jobs[j].nt = (s_jobs[j].sah * 4 * s_jobs[j].gpr + pad - 1) / pad * pad;
-                    tot += s_jobs[j].nt;
-                }
-                s_ntasks = tot;
-                if (tpp == 1 || (tpp <= bh && tot * tpp <= NT_SEARCH)) break;
+                jb.nt = (T + pad - 1) & ~(pad - 1);
+                inc = jb.nt;
+                v = __shfl_up_sync(m4, inc, 1);
+                if (tid >= 1) inc += v;
+                v = __shfl_up_sync(m4, inc, 2);
+                if (tid >= 2) inc += v;
+                tot = __shfl_sync(m4, inc, 3);
+                jb.t0 = inc - jb.nt;
+                if (tpp == 1 || (tpp <= bh && tot * tpp <= NT_SEARCH)) break; // same decision in all four lanes
             }
-            s_tpp = tpp;
+            int maxp = jl ? jb.saw * jb.sah : 1;
+            maxp = max(maxp, __shfl_xor_sync(m4, maxp, 1));
+            maxp = max(maxp, __shfl_xor_sync(m4, maxp, 2));
+            if (jl) {
+                s_jobs[tid] = jb;
+                s_key[tid] = ~0ull;
+            }
+            if (tid == 0) {
+                s_tpp = tpp;
+                s_ntasks = tot;
+                // packed 32-bit keys when (largest SAD of the level, largest position index) fit together
+                const int ibits = 32 - __clz(maxp - 1 > 0 ? maxp - 1 : 1);
+                const int sbits = 32 - __clz(255 * bw * bh);
+                s_kshift = (ibits + sbits <= 31) ? ibits : 0;
+            }
         }
         __syncthreads();
         const uint8_t *s = srcp + (size_t)(pl.origin_y + o_y) * pl.stride + pl.origin_x + o_x;
@@ -661,11 +750,11 @@ __global__ void __launch_bounds__(NT_SEARCH) hme_kernel(const __grid_constant__ 
         if (!aligned)
             hme_level_search<NT_SEARCH>(s, sstr, pl.stride, k, bw, bh, s_jobs, njobs, smem, s_key);
         else if (level == 0)
-            hme_level_search_aligned<NT_SEARCH, 4>(s, sstr, pl.stride, k, bh, s_jobs, njobs, s_tpp, s_ntasks, smem, s_key);
+            hme_level_search_aligned<NT_SEARCH, 4>(s, sstr, pl.stride, k, bh, s_jobs, njobs, s_tpp, s_ntasks, s_kshift, smem, s_key);
         else if (level == 1)
-            hme_level_search_aligned<NT_SEARCH, 8>(s, sstr, pl.stride, k, bh, s_jobs, njobs, s_tpp, s_ntasks, smem, s_key);
+            hme_level_search_aligned<NT_SEARCH, 8>(s, sstr, pl.stride, k, bh, s_jobs, njobs, s_tpp, s_ntasks, s_kshift, smem, s_key);
         else
-            hme_level_search_aligned<NT_SEARCH, 16>(s, sstr, pl.stride, k, bh, s_jobs, njobs, s_tpp, s_ntasks, smem, s_key);
+            hme_level_search_aligned<NT_SEARCH, 16>(s, sstr, pl.stride, k, bh, s_jobs, njobs, s_tpp, s_ntasks, s_kshift, smem, s_key);
         if (tid < njobs) {
             const unsigned long long key = s_key[tid];
             const uint32_t sad = (uint32_t)(key >> 32), idx = (uint32_t)key;
@@ -697,7 +786,7 @@ __global__ void __launch_bounds__(NT_SEARCH) hme_kernel(const __grid_constant__ 
         w.y = (int16_t)by;
         w.valid = 1;
         w.sad = bs;
-        *out = w;
+        hme_publish(d, sb, out, w);
     }
 }
 
@@ -728,26 +817,21 @@ __global__ void __launch_bounds__(NT_SEARCH, 2) fullpel_kernel(const __grid_cons
     uint32_t *smem = reinterpret_cast<uint32_t *>(smem4);
     __shared__ unsigned long long s_best[85]; // (sad << 32 | raster index) over the whole window
     __shared__ unsigned int s_cbest[85]; // (sad << SH | index inside the current chunk)
-    __shared__ HmeState s_h;
     __shared__ uint32_t s_sad2[2];
     constexpr int SH = SUB ? 12 : 11; // SUB keeps the un-doubled SAD (19 bits) in the key
     constexpr uint32_t BIAS = SUB ? 8192u : 16384u;
     constexpr int NR = SUB ? 4 : 8, KR = SUB ? 2 : 1; // rows summed per 8x8, window rows per summed row
     constexpr int NSRC = SUB ? 32 : 64;
     const SvtB200MeParams &p = d.p;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, nt = blockDim.x; // nt: 64..256, chosen by the host (load balance)
     const int sb = blockIdx.x, slot = blockIdx.y;
     const int l = d.slot_l[slot], r = d.slot_r[slot];
     uint32_t *o_sad = d.out.best_sad + ((size_t)(sb * 2 + l) * 4 + r) * 85;
     uint32_t *o_mv = d.out.best_mv + ((size_t)(sb * 2 + l) * 4 + r) * 85;
 
-    if (tid == 0) {
-        derive_hme_state(p, d.raw + (size_t)sb * 8, s_h);
-        s_sad2[0] = s_sad2[1] = 0;
-    }
-    __syncthreads();
-    if (!s_h.do_ref[l][r]) { // pruned by HME: the reference skips the search; slots are defined as 0
-        for (int i = tid; i < 85; i += NT_SEARCH) {
+    const HmeState &hs = d.hstate[sb]; // derived once per SB by the last HME CTA (hme_publish)
+    if (!hs.do_ref[l][r]) { // pruned by HME: the reference skips the search; slots are defined as 0
+        for (int i = tid; i < 85; i += nt) {
             o_sad[i] = 0;
             o_mv[i] = 0;
         }
@@ -761,15 +845,23 @@ __global__ void __launch_bounds__(NT_SEARCH, 2) fullpel_kernel(const __grid_cons
     const uint8_t *srcb = d.src.full + (size_t)(fp.origin_y + oy) * fp.stride + fp.origin_x + ox;
     const uint8_t *refb = d.refs[l][r].full + (size_t)(fp.origin_y + oy) * fp.stride + fp.origin_x + ox;
 
-    int xsc = s_h.sc_x[l][r], ysc = s_h.sc_y[l][r];
+    int xsc = hs.sc_x[l][r], ysc = hs.sc_y[l][r];
     const int dist = scaled_dist(p.ref_dist[l][r]);
     int saw = (int16_t)min(p.search_area_width * dist, p.max_me_search_width);
     int sah = (int16_t)min(p.search_area_height * dist, p.max_me_search_height);
-    const int dv = (int)s_h.divisor[l][r];
+    const int dv = (int)hs.divisor[l][r];
     saw = (int16_t)(((saw / dv) + 7) & ~0x07);
     sah = (int16_t)max(1, sah / dv);
 
-    if ((xsc != 0 || ysc != 0) && p.is_used_as_reference_flag) { // check_00_center :1348-1421
+    // ---- stage the source rows that take part in the SAD (even rows only with sub-sampling) ----
+    uint32_t *s_src = smem; // [NSRC][16 words]
+    uint32_t *s_win = smem + NSRC * 16;
+    if (tid == 0) s_sad2[0] = s_sad2[1] = 0;
+    for (int i = tid; i < 85; i += nt) s_best[i] = ((unsigned long long)kMaxSadValue << 32) | 0xffffffffull;
+    stage_flat(s_src, 16, srcb, (ptrdiff_t)KR * fp.stride, NSRC, 64, nt);
+    __syncthreads();
+
+    if ((xsc != 0 || ysc != 0) && p.is_used_as_reference_flag) { // check_00_center :1348-1421 (even rows, SAD << 1)
         int cx = xsc, cy = ysc;
         if (ox + cx < -63) cx = -63 - ox;
         if (ox + cx > fp.width - 1) cx = cx - ((ox + cx) - (fp.width - 1));
@@ -777,12 +869,19 @@ __global__ void __launch_bounds__(NT_SEARCH, 2) fullpel_kernel(const __grid_cons
         if (oy + cy > fp.height - 1) cy = cy - ((oy + cy) - (fp.height - 1));
         const uint8_t *rh = refb + (ptrdiff_t)cy * fp.stride + cx;
         uint32_t z = 0, h = 0;
-        const int rows = sbh >> 1;
-        for (int i = tid; i < rows * sbw; i += NT_SEARCH) {
-            int rr = i / sbw, c = i - rr * sbw;
-            int s = srcb[(size_t)rr * 2 * fp.stride + c];
-            z += abs(s - (int)refb[(size_t)rr * 2 * fp.stride + c]);
-            h += abs(s - (int)rh[(ptrdiff_t)rr * 2 * fp.stride + c]);
+        const int rows = sbh >> 1, nw = (sbw + 3) >> 2;
+        for (int i = tid; i < rows * nw; i += nt) { // one source word (4 samples) against both candidates
+            const int rr = i / nw, wq = i - rr * nw;
+            const uint32_t mask = (4 * wq + 4 > sbw) ? (1u << (8 * (sbw - 4 * wq))) - 1u : 0xffffffffu;
+            const uint32_t sv = s_src[(SUB ? rr : 2 * rr) * 16 + wq] & mask;
+            const uintptr_t a0 = (uintptr_t)(refb + (ptrdiff_t)rr * 2 * fp.stride + 4 * wq);
+            const uintptr_t a1 = (uintptr_t)(rh + (ptrdiff_t)rr * 2 * fp.stride + 4 * wq);
+            const uint32_t *g0 = reinterpret_cast<const uint32_t *>(a0 & ~(uintptr_t)3);
+            const uint32_t *g1 = reinterpret_cast<const uint32_t *>(a1 & ~(uintptr_t)3);
+            const uint32_t v0 = __funnelshift_r(g0[0], (a0 & 3) ? g0[1] : 0u, (int)(a0 & 3) * 8);
+            const uint32_t v1 = __funnelshift_r(g1[0], (a1 & 3) ? g1[1] : 0u, (int)(a1 & 3) * 8);
+            z = sad4(sv, v0 & mask, z);
+            h = sad4(sv, v1 & mask, h);
         }
         z = __reduce_add_sync(0xffffffffu, z);
         h = __reduce_add_sync(0xffffffffu, h);
@@ -800,12 +899,6 @@ __global__ void __launch_bounds__(NT_SEARCH, 2) fullpel_kernel(const __grid_cons
     saw = saw < 8 ? saw : saw & ~0x07;
     clamp_window(oy, 63, pic_h, yo, sah);
 
-    for (int i = tid; i < 85; i += NT_SEARCH) s_best[i] = ((unsigned long long)kMaxSadValue << 32) | 0xffffffffull;
-
-    // ---- stage the source rows that take part in the SAD (even rows only with sub-sampling) ----
-    uint32_t *s_src = smem; // [NSRC][16 words]
-    uint32_t *s_win = smem + NSRC * 16;
-    stage_rows<NT_SEARCH>(s_src, 16, srcb, (ptrdiff_t)KR * fp.stride, NSRC, 64);
     const int span = SUB ? 63 : 64;
     const int wbytes = saw + 63;
     const int wpw = fp_pitch_words(saw);
@@ -833,11 +926,11 @@ __global__ void __launch_bounds__(NT_SEARCH, 2) fullpel_kernel(const __grid_cons
         const int cr = min(chunk, sah - y0);
         const int rows = cr - 1 + span;
         __syncthreads();
-        stage_rows<NT_SEARCH>(s_win, wpw, refb + (ptrdiff_t)(yo + y0) * fp.stride + xo, fp.stride, rows, wbytes);
-        for (int i = tid; i < 85; i += NT_SEARCH) s_cbest[i] = 0xffffffffu;
+        stage_flat(s_win, wpw, refb + (ptrdiff_t)(yo + y0) * fp.stride + xo, fp.stride, rows, wbytes, nt);
+        for (int i = tid; i < 85; i += nt) s_cbest[i] = 0xffffffffu;
         __syncthreads();
         const int ntasks = cr * tpr;
-        for (int qb = 0; qb < ntasks; qb += NT_SEARCH) {
+        for (int qb = 0; qb < ntasks; qb += nt) {
             if (qb + (tid & ~31) >= ntasks) continue; // whole warp has no task: reductions are per warp
             const int t = qb + tid;
             const bool live = t < ntasks;
@@ -946,7 +1039,7 @@ __global__ void __launch_bounds__(NT_SEARCH, 2) fullpel_kernel(const __grid_cons
         __syncthreads();
         // merge the chunk into the running best: chunks advance in raster order, so strict `<` on the SAD keeps
         // the first minimum
-        for (int i = tid; i < 85; i += NT_SEARCH) {
+        for (int i = tid; i < 85; i += nt) {
             const unsigned int c = s_cbest[i];
             if (c != 0xffffffffu) {
                 const unsigned long long sadc = SUB ? (unsigned long long)(c >> SH) << 1 : (unsigned long long)(c >> SH);
@@ -955,7 +1048,7 @@ __global__ void __launch_bounds__(NT_SEARCH, 2) fullpel_kernel(const __grid_cons
         }
     }
     __syncthreads();
-    for (int i = tid; i < 85; i += NT_SEARCH) {
+    for (int i = tid; i < 85; i += nt) {
         const unsigned long long key = s_best[i];
         const uint32_t sad = (uint32_t)(key >> 32), idx = (uint32_t)key;
         uint32_t mv = 0;
@@ -980,7 +1073,7 @@ __global__ void __launch_bounds__(96) finalize_kernel(const __grid_constant__ Me
     const uint32_t *bsad = d.out.best_sad + (size_t)sb * 2 * 4 * 85;
     const uint32_t *bmv = d.out.best_mv + (size_t)sb * 2 * 4 * 85;
     if (tid == 0) {
-        derive_hme_state(p, d.raw + (size_t)sb * 8, s_h);
+        s_h = d.hstate[sb];
         const bool prune_ref = p.enable_hme_flag && p.enable_hme_level2_flag;
         if (prune_ref && p.enable_me_hme_ref_pruning) {
             for (int l = 0; l < p.num_lists; l++)
@@ -1245,7 +1338,7 @@ extern "C" {
 size_t svt_b200_me_scratch_bytes(const SvtB200MeParams *p) {
     if (!p) return 0;
     const size_t n_sb = (size_t)((p->full.width + 63) / 64) * ((p->full.height + 63) / 64);
-    return n_sb * 8 * sizeof(RawHme);
+    return n_sb * (8 * sizeof(RawHme) + sizeof(HmeState) + sizeof(unsigned int));
 }
 
 int svt_b200_me_picture(const SvtB200MeParams *p, const SvtB200MePlanes *src,
@@ -1290,7 +1383,9 @@ int svt_b200_me_picture(const SvtB200MeParams *p, const SvtB200MePlanes *src,
     // slots of unused references are defined as zero
     SVTB_CUDA_TRY(cudaMemsetAsync(out->best_sad, 0, (size_t)n_sb * 8 * 85 * 4, st));
     SVTB_CUDA_TRY(cudaMemsetAsync(out->best_mv, 0, (size_t)n_sb * 8 * 85 * 4, st));
-    SVTB_CUDA_TRY(cudaMemsetAsync(d.raw, 0, (size_t)n_sb * 8 * sizeof(RawHme), st));
+    d.hstate = (HmeState *)(d.raw + (size_t)n_sb * 8);
+    d.hme_done = (unsigned int *)(d.hstate + n_sb);
+    SVTB_CUDA_TRY(cudaMemsetAsync(d.raw, 0, (size_t)n_sb * (8 * sizeof(RawHme) + sizeof(HmeState) + sizeof(unsigned int)), st));
     // worst-case shared memory of one HME level on the fast path (4 windows + the source block)
     size_t hme_need = 0;
     {
@@ -1323,6 +1418,7 @@ int svt_b200_me_picture(const SvtB200MeParams *p, const SvtB200MePlanes *src,
         SVTB_LAUNCH(hme_kernel, dim3(n_sb, n), NT_SEARCH, hme_need, st, d);
     else
         SVTB_LAUNCH(hme_kernel_generic, dim3(n_sb, n), NT_SEARCH, HME_SMEM_BYTES, st, d);
+    int fp_threads = NT_SEARCH;
     {   // shared memory of the full-pel search: source rows + the largest window (whole if it fits)
         int maxd = 1;
         for (int l = 0; l < p->num_lists; l++)
@@ -1339,11 +1435,33 @@ int svt_b200_me_picture(const SvtB200MeParams *p, const SvtB200MePlanes *src,
         size_t need = (size_t)(sub ? 32 : 64) * 64 + (size_t)fp_pitch_words(saw) * 4 * (sah - 1 + (sub ? 63 : 64)) + 64;
         if (need > (size_t)FP_SMEM_BYTES) need = FP_SMEM_BYTES;
         d.fp_smem_bytes = (int)need;
+        // CTA size: a warp-task is 32 tasks of 4 positions; pick the warp count that divides the per-reference task
+        // counts best (idle warps only hold registers until the CTA's last round ends)
+        static const int cand[5] = {4, 3, 6, 2, 8};
+        long best_cost = -1;
+        for (int ci = 0; ci < 5; ci++) {
+            long cost = 0;
+            for (int l = 0; l < p->num_lists; l++)
+                for (int r = 0; r < p->num_refs[l]; r++) {
+                    int dd = p->ref_dist[l][r];
+                    dd = ((dd * 5) / 8) + ((dd % 8) ? 1 : 0);
+                    int w = p->search_area_width * dd, h = p->search_area_height * dd;
+                    if (w > p->max_me_search_width) w = p->max_me_search_width;
+                    if (h > p->max_me_search_height) h = p->max_me_search_height;
+                    w = (w + 7) & ~7;
+                    const int tw = (h * 4 * ((w + 15) >> 4) + 31) / 32;
+                    cost += (long)((tw + cand[ci] - 1) / cand[ci]) * cand[ci];
+                }
+            if (best_cost < 0 || cost < best_cost) {
+                best_cost = cost;
+                fp_threads = cand[ci] * 32;
+            }
+        }
     }
     if (p->me_search_method != 0)
-        SVTB_LAUNCH(fullpel_kernel<true>, dim3(n_sb, n), NT_SEARCH, d.fp_smem_bytes, st, d);
+        SVTB_LAUNCH(fullpel_kernel<true>, dim3(n_sb, n), fp_threads, d.fp_smem_bytes, st, d);
     else
-        SVTB_LAUNCH(fullpel_kernel<false>, dim3(n_sb, n), NT_SEARCH, d.fp_smem_bytes, st, d);
+        SVTB_LAUNCH(fullpel_kernel<false>, dim3(n_sb, n), fp_threads, d.fp_smem_bytes, st, d);
     SVTB_LAUNCH(finalize_kernel, n_sb, 96, 0, st, d);
     SVTB_CUDA_TRY(cudaGetLastError());
     return SVT_B200_OK;

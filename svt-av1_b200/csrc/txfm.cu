@@ -106,23 +106,20 @@ __global__ void __launch_bounds__(TX_NT) fwd_txfm_kernel(const FwdArgs a) {
     __syncthreads();
     if (live) {
         for (int c = li; c < t.w; c += T) { /* column pass */
-            int32_t *col = buf + c;
-            if (t.fs0) for (int r = 0; r < t.h; r++) col[r * pitch] = (int32_t)((uint32_t)col[r * pitch] << t.fs0);
-            fwd_1d(col, pitch, t.h, t.vk, t.cbc);
-            if (t.fs1) for (int r = 0; r < t.h; r++) col[r * pitch] = round_shift64((long long)col[r * pitch], -t.fs1);
+            const int fs0 = t.fs0, fs1 = t.fs1;
+            fwd_1d_pass(buf + c, pitch, t.h, t.vk, t.cbc, [=](int32_t v) { return (int32_t)((uint32_t)v << fs0); },
+                        [=](int32_t v) { return fs1 ? round_shift64((long long)v, -fs1) : v; });
         }
     }
     __syncthreads();
     if (live) {
         for (int r = li; r < t.h; r += T) { /* row pass */
-            int32_t *row = buf + r * pitch;
-            fwd_1d(row, 1, t.w, t.hk, t.cbr);
-            for (int c = 0; c < t.w; c++) {
-                int32_t v = row[c];
-                if (t.fs2) v = round_shift64((long long)v, -t.fs2);
-                if (t.rect) v = round_shift64((long long)v * 5793, 12);
-                row[c] = v;
-            }
+            const int fs2 = t.fs2, rect = t.rect;
+            fwd_1d_pass(buf + r * pitch, 1, t.w, t.hk, t.cbr, [](int32_t v) { return v; }, [=](int32_t v) {
+                if (fs2) v = round_shift64((long long)v, -fs2);
+                if (rect) v = round_shift64((long long)v * 5793, 12);
+                return v;
+            });
         }
     }
     __syncthreads();
@@ -190,24 +187,19 @@ __global__ void __launch_bounds__(TX_NT) inv_txfm_kernel(const InvArgs a) {
     const int range_row = bd == 8 ? 16 : bd == 10 ? 18 : 20, range_col = bd == 8 ? 16 : bd == 10 ? 16 : 18;
     if (live) {
         for (int r = li; r < t.h; r += T) {
-            int32_t *row = buf + r * pitch;
-            for (int c = 0; c < t.w; c++) {
-                int32_t v = row[c];
-                if (t.rect) v = round_shift64((long long)v * 2896, 12);
-                row[c] = clampv(v, bd + 8);
-            }
-            inv_1d(row, 1, t.w, t.hk, 12, range_row);
-            if (t.is0) for (int c = 0; c < t.w; c++) row[c] = round_shift64((long long)row[c], -t.is0);
+            const int rect = t.rect, is0 = t.is0;
+            inv_1d_pass(buf + r * pitch, 1, t.w, t.hk, 12, range_row, [=](int32_t v) {
+                if (rect) v = round_shift64((long long)v * 2896, 12);
+                return clampv(v, bd + 8);
+            }, [=](int32_t v) { return is0 ? round_shift64((long long)v, -is0) : v; });
         }
     }
     __syncthreads();
     if (live) {
         const int col_clamp = max(bd + 6, 16);
         for (int c = li; c < t.w; c += T) {
-            int32_t *col = buf + c;
-            for (int r = 0; r < t.h; r++) col[r * pitch] = clampv(col[r * pitch], col_clamp);
-            inv_1d(col, pitch, t.h, t.vk, 12, range_col);
-            for (int r = 0; r < t.h; r++) col[r * pitch] = round_shift64((long long)col[r * pitch], 4);
+            inv_1d_pass(buf + c, pitch, t.h, t.vk, 12, range_col, [=](int32_t v) { return clampv(v, col_clamp); },
+                        [](int32_t v) { return round_shift64((long long)v, 4); });
         }
     }
     __syncthreads();
@@ -360,22 +352,19 @@ __global__ void __launch_bounds__(TX_NT) encode_tu_kernel(const __grid_constant_
     __syncthreads();
     if (live)
         for (int c = li; c < t.w; c += Tn) {
-            int32_t *col = buf + c;
-            if (t.fs0) for (int r = 0; r < t.h; r++) col[r * pitch] = (int32_t)((uint32_t)col[r * pitch] << t.fs0);
-            fwd_1d(col, pitch, t.h, t.vk, t.cbc);
-            if (t.fs1) for (int r = 0; r < t.h; r++) col[r * pitch] = round_shift64((long long)col[r * pitch], -t.fs1);
+            const int fs0 = t.fs0, fs1 = t.fs1;
+            fwd_1d_pass(buf + c, pitch, t.h, t.vk, t.cbc, [=](int32_t v) { return (int32_t)((uint32_t)v << fs0); },
+                        [=](int32_t v) { return fs1 ? round_shift64((long long)v, -fs1) : v; });
         }
     __syncthreads();
     if (live)
         for (int r = li; r < t.h; r += Tn) {
-            int32_t *row = buf + r * pitch;
-            fwd_1d(row, 1, t.w, t.hk, t.cbr);
-            for (int c = 0; c < t.w; c++) {
-                int32_t v = row[c];
-                if (t.fs2) v = round_shift64((long long)v, -t.fs2);
-                if (t.rect) v = round_shift64((long long)v * 5793, 12);
-                row[c] = v;
-            }
+            const int fs2 = t.fs2, rect = t.rect;
+            fwd_1d_pass(buf + r * pitch, 1, t.w, t.hk, t.cbr, [](int32_t v) { return v; }, [=](int32_t v) {
+                if (fs2) v = round_shift64((long long)v, -fs2);
+                if (rect) v = round_shift64((long long)v * 5793, 12);
+                return v;
+            });
         }
     __syncthreads();
     // quantise + dequantise in place (coefficients outside the kept 32x32 of 64-wide sizes are dropped = 0)
@@ -405,24 +394,19 @@ __global__ void __launch_bounds__(TX_NT) encode_tu_kernel(const __grid_constant_
     if (live) {
         if (li == 0) d.eob[b] = (uint16_t)s_eob[lb];
         for (int r = li; r < t.h; r += Tn) {
-            int32_t *row = buf + r * pitch;
-            for (int c = 0; c < t.w; c++) {
-                int32_t v = row[c];
-                if (t.rect) v = round_shift64((long long)v * 2896, 12);
-                row[c] = clampv(v, bd + 8);
-            }
-            inv_1d(row, 1, t.w, t.hk, 12, range_row);
-            if (t.is0) for (int c = 0; c < t.w; c++) row[c] = round_shift64((long long)row[c], -t.is0);
+            const int rect = t.rect, is0 = t.is0;
+            inv_1d_pass(buf + r * pitch, 1, t.w, t.hk, 12, range_row, [=](int32_t v) {
+                if (rect) v = round_shift64((long long)v * 2896, 12);
+                return clampv(v, bd + 8);
+            }, [=](int32_t v) { return is0 ? round_shift64((long long)v, -is0) : v; });
         }
     }
     __syncthreads();
     if (live) {
         const int col_clamp = max(bd + 6, 16);
         for (int c = li; c < t.w; c += Tn) {
-            int32_t *col = buf + c;
-            for (int r = 0; r < t.h; r++) col[r * pitch] = clampv(col[r * pitch], col_clamp);
-            inv_1d(col, pitch, t.h, t.vk, 12, range_col);
-            for (int r = 0; r < t.h; r++) col[r * pitch] = round_shift64((long long)col[r * pitch], 4);
+            inv_1d_pass(buf + c, pitch, t.h, t.vk, 12, range_col, [=](int32_t v) { return clampv(v, col_clamp); },
+                        [](int32_t v) { return round_shift64((long long)v, 4); });
         }
     }
     __syncthreads();
