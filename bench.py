@@ -3,9 +3,9 @@
 
 A "step" is one pass of the hot path over one mini-GOP of FRAMES_PER_STEP synthetic 1920x1080 8-bit frames
 (BASELINE.json configs[1] geometry, preset-8 parameters).  Per frame, in the order the reference's pipeline runs:
-  1. open-loop ME        motion_estimation_kernel: HME + full-pel search, 2+2 references     (3 launches)
+  1. open-loop ME        motion_estimation_kernel: HME + full-pel search (+ SB epilogue), 2+2 refs (2 launches)
   2. EncDec final pass   residual -> fwd txfm -> quant/dequant -> inverse txfm -> recon, every TU (3 launches)
-  3. deblocking          svt_av1_loop_filter_frame, all planes                                  (6 launches)
+  3. deblocking          svt_av1_loop_filter_frame, all planes                                  (2 launches)
   4. CDEF                cdef_seg_search (10 strengths, preset 8) + svt_av1_cdef_frame          (2 launches)
   value : frames/s with all inputs resident in HBM (CUDA events on the launch stream, max over ranks)
   e2e   : same work through the C ABI with HOST (pinned) buffers: H2D of the source/prediction planes, ME planes

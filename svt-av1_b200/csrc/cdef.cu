@@ -28,11 +28,11 @@ __constant__ int8_t c_dir[8][2][2] = {{{-1, 1}, {-2, 2}}, {{0, 1}, {-1, 2}}, {{0
 __device__ __forceinline__ int msb(uint32_t n) { return 31 - __clz((int)n); }
 
 // constrain() of EbCdef.c:86-93 with the shift (max(0, damping - msb(threshold))) hoisted by the caller
+// sign(diff) * min(|diff|, lim) == clamp(diff, -lim, lim) for lim >= 0; -lim = min(0, (|diff| >> shift) - threshold)
+// is one VIADDMNMX (DPX add+min), so the whole function is IABS, SHF, VIADDMNMX, neg, VIMNMX, VIMNMX.
 __device__ __forceinline__ int constrain_s(int diff, int threshold, int shift) {
-    const int mag = abs(diff);
-    const int lim = max(0, threshold - (mag >> shift));
-    const int v = min(mag, lim);
-    return diff < 0 ? -v : v;
+    const int nlim = __viaddmin_s32(abs(diff) >> shift, -threshold, 0);
+    return min(max(diff, nlim), -nlim);
 }
 __device__ __forceinline__ int adjust_strength(int strength, int var) {
     const int i = (var >> 6) ? min(msb((uint32_t)(var >> 6)), 12) : 0;
@@ -460,11 +460,17 @@ struct CdefSearchGridDev {
     CdefGrid g;
 };
 
+constexpr int CDEF_COMPACT_NG = 20; // strength tables up to this size park the per-block sums for a compact distortion pass
 template <typename T, int BS, int NSEC, bool LUMA, bool kBorder>
 __device__ __noinline__ void plane_search_grid(const CdefSearchDev &d, const CdefGrid &g, const int16_t *in, int count,
                                                   const uint8_t *s_by, const uint8_t *s_bx, const int8_t *s_dir, const int *s_var,
-                                                  unsigned long long *s_mse, int pli, int y0, int x0, int damping) {
+                                                  unsigned long long *s_mse, uint32_t *s_sums, int pli, int y0, int x0, int damping) {
     const int tid = threadIdx.x, lane = tid & 31;
+    const int ng = g.npri * NSEC;
+    // The 8x8 luma distortion is ~100 double-precision instructions evaluated by ONE lane per block: inside the strength
+    // loop it is issued for 2 active lanes per warp.  With a small table the three sums per (block, strength) are parked
+    // in shared memory and evaluated afterwards with all lanes busy (one (strength, block) pair per thread).
+    const bool compact = LUMA && ng <= CDEF_COMPACT_NG;
     const int cs = d.coeff_shift;
     const T *sp = reinterpret_cast<const T *>(d.source.p[pli]);
     const int sstride = d.source.stride[pli];
@@ -586,6 +592,17 @@ __device__ __noinline__ void plane_search_grid(const CdefSearchDev &d, const Cde
                         ss2[si] += __shfl_xor_sync(0xffffffffu, ss2[si], s);
                         ssd[si] += __shfl_xor_sync(0xffffffffu, ssd[si], s);
                     }
+                    if (compact) {
+                        if (live && sub == 0) {
+                            uint32_t *e = s_sums + (b * CDEF_COMPACT_NG + pi * NSEC + si) * 3;
+                            e[0] = ss[si], e[1] = ss2[si], e[2] = ssd[si];
+                            if (pi == 0 && si == 0) {
+                                s_sums[64 * CDEF_COMPACT_NG * 3 + 2 * b] = sd;
+                                s_sums[64 * CDEF_COMPACT_NG * 3 + 2 * b + 1] = sd2;
+                            }
+                        }
+                        continue;
+                    }
                     v = (live && sub == 0) ? dist8x8_from_sums(ss[si], sd, ss2[si], sd2, ssd[si], cs) : 0ull;
                     v += __shfl_xor_sync(0xffffffffu, v, 16);
                 } else {
@@ -595,6 +612,20 @@ __device__ __noinline__ void plane_search_grid(const CdefSearchDev &d, const Cde
                 }
                 if (lane == 0 && v) atomicAdd(&s_mse[pi * NSEC + si], v);
             }
+        }
+    }
+    if (compact) { // item = strength * 64 + block: a warp works for one strength
+        __syncthreads();
+        for (int it = tid; it < ng * 64; it += NT) {
+            const int gi = it >> 6, b = it & 63;
+            unsigned long long v = 0;
+            if (b < count) {
+                const uint32_t *e = s_sums + (b * CDEF_COMPACT_NG + gi) * 3;
+                v = dist8x8_from_sums(e[0], s_sums[64 * CDEF_COMPACT_NG * 3 + 2 * b], e[1], s_sums[64 * CDEF_COMPACT_NG * 3 + 2 * b + 1], e[2], cs);
+            }
+#pragma unroll
+            for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+            if (lane == 0 && v) atomicAdd(&s_mse[gi], v);
         }
     }
 }
@@ -607,6 +638,7 @@ __global__ void __launch_bounds__(NT, 4) cdef_search_grid_kernel(const __grid_co
     __shared__ int s_var[64];
     __shared__ int s_count;
     __shared__ unsigned long long s_mse[64];
+    __shared__ uint32_t s_sums[64 * CDEF_COMPACT_NG * 3 + 128]; // parked (sum f, sum f^2, sum f*o) per (block, strength) + (sum o, sum o^2)
     const CdefSearchDev &d = gd.d;
     const int tid = threadIdx.x;
     const int fb = blockIdx.x, fbr = fb / d.nhfb, fbc = fb - fbr * d.nhfb;
@@ -659,14 +691,14 @@ __global__ void __launch_bounds__(NT, 4) cdef_search_grid_kernel(const __grid_co
         const int damping = p.pri_damping + cs - (pli != 0);
         if (pli == 0) {
             if (border)
-                plane_search_grid<T, 8, NSEC, true, true>(d, gd.g, in, count, s_by, s_bx, s_dir, s_var, s_mse, pli, y0, x0, damping);
+                plane_search_grid<T, 8, NSEC, true, true>(d, gd.g, in, count, s_by, s_bx, s_dir, s_var, s_mse, s_sums, pli, y0, x0, damping);
             else
-                plane_search_grid<T, 8, NSEC, true, false>(d, gd.g, in, count, s_by, s_bx, s_dir, s_var, s_mse, pli, y0, x0, damping);
+                plane_search_grid<T, 8, NSEC, true, false>(d, gd.g, in, count, s_by, s_bx, s_dir, s_var, s_mse, s_sums, pli, y0, x0, damping);
         } else {
             if (border)
-                plane_search_grid<T, 4, NSEC, false, true>(d, gd.g, in, count, s_by, s_bx, s_dir, s_var, s_mse, pli, y0, x0, damping);
+                plane_search_grid<T, 4, NSEC, false, true>(d, gd.g, in, count, s_by, s_bx, s_dir, s_var, s_mse, s_sums, pli, y0, x0, damping);
             else
-                plane_search_grid<T, 4, NSEC, false, false>(d, gd.g, in, count, s_by, s_bx, s_dir, s_var, s_mse, pli, y0, x0, damping);
+                plane_search_grid<T, 4, NSEC, false, false>(d, gd.g, in, count, s_by, s_bx, s_dir, s_var, s_mse, s_sums, pli, y0, x0, damping);
         }
         __syncthreads();
         for (int gi = tid; gi < 64; gi += NT) {
@@ -702,6 +734,8 @@ __global__ void __launch_bounds__(NT) cdef_apply_kernel(const __grid_constant__ 
     const SvtB200CdefApplyParams &p = d.p;
     const int nvb = min(16, p.mi_rows - 16 * fbr), nhb = min(16, p.mi_cols - 16 * fbc);
     const int cs = d.coeff_shift;
+    // does the +2 rim of this filter block reach outside the frame (CDEF_VERY_LARGE samples present)?
+    const bool border = fbr == 0 || fbc == 0 || 16 * (fbr + 1) >= p.mi_rows || 16 * (fbc + 1) >= p.mi_cols;
     const int idx = d.fb_idx[fb];
     int level = 0, sec = 0, uv_level = 0, uv_sec = 0;
     if (idx >= 0) {
@@ -750,15 +784,30 @@ __global__ void __launch_bounds__(NT) cdef_apply_kernel(const __grid_constant__ 
         const int damping = p.damping + cs - (pli != 0);
         T *op = reinterpret_cast<T *>(const_cast<void *>(d.out.p[pli]));
         const int ostride = d.out.stride[pli];
-        for (int i = tid; i < bh * bw; i += NT) {
-            const int r = i / bw, c = i - r * bw;
-            const int b = (r / bs) * 8 + (c / bs);
-            int v = in[r * TS + c];
+        // four samples of one block row per thread: direction, strengths, tap offsets and shifts are per-block values
+        const int q4 = bw >> 2;
+        for (int i = tid; i < bh * q4; i += NT) {
+            const int r = i / q4, c = (i - r * q4) << 2;
+            const int b = (r >> (3 - sh)) * 8 + (c >> (3 - sh));
+            const int16_t *q = in + r * TS + c;
+            int o[4] = {q[0], q[1], q[2], q[3]};
             if (filt && !s_skip[b]) {
                 const int t = pli ? pri : adjust_strength(pri, s_var[b]);
-                v = cdef_sample(in + r * TS + c, TS, t, s2, pri ? s_dir[b] : 0, damping, damping, cs);
+                if (t | s2) {
+                    const CdefTaps taps = make_taps(t, s2, pri ? s_dir[b] : 0, damping, damping, cs, TS);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) o[j] = border ? cdef_px<true>(q + j, taps, t, s2) : cdef_px<false>(q + j, taps, t, s2);
+                }
             }
-            op[(size_t)(y0 + r) * ostride + x0 + c] = (T)v;
+            T *dst = op + (size_t)(y0 + r) * ostride + x0 + c;
+            if (sizeof(T) == 1 && ((uintptr_t)dst & 3) == 0)
+                *reinterpret_cast<uint32_t *>(dst) = (uint32_t)o[0] | ((uint32_t)o[1] << 8) | ((uint32_t)o[2] << 16) | ((uint32_t)o[3] << 24);
+            else if (sizeof(T) == 2 && ((uintptr_t)dst & 7) == 0)
+                *reinterpret_cast<uint2 *>(dst) = make_uint2((uint32_t)o[0] | ((uint32_t)o[1] << 16), (uint32_t)o[2] | ((uint32_t)o[3] << 16));
+            else {
+#pragma unroll
+                for (int j = 0; j < 4; j++) dst[j] = (T)o[j];
+            }
         }
     }
 }

@@ -12,6 +12,8 @@
 // so the whole picture is two launches: every vertical edge in parallel, then every horizontal edge — one thread
 // per sample line of an edge, edge parameters (length, level) derived on the fly from a 16-byte-per-4x4 summary of
 // the mode-info grid.  HBM traffic: the picture is read and written once per pass (2 B/sample + 1 B/edge, §8d).
+#include <algorithm>
+
 #include "common.cuh"
 
 using namespace svtb200;
@@ -136,7 +138,8 @@ __device__ __forceinline__ void thresholds(int level, int sharpness, int &blimit
 // One thread per sample line of a 4x4 unit's leading edge.  vert = 1: thread = (row y, unit column ux);
 // vert = 0: thread = (unit row uy, column x) so that a warp walks along a row of the picture (coalesced).
 template <typename T>
-__global__ void __launch_bounds__(256) dlf_pass_kernel(const __grid_constant__ DlfDev d, int plane, int vert) {
+__global__ void __launch_bounds__(256) dlf_pass_kernel(const __grid_constant__ DlfDev d, int planes, int vert) {
+    const int plane = (planes >> (2 * blockIdx.z)) & 3; // the planes of one direction share a launch (grid.z)
     const int ss = plane ? 1 : 0;
     const int pw = (d.p.mi_cols * 4) >> ss, ph = (d.p.mi_rows * 4) >> ss;
     const int nx = vert ? pw / 4 : pw, ny = vert ? ph : ph / 4;
@@ -265,20 +268,24 @@ int svt_b200_dlf_frame(const SvtB200DlfParams *p, const SvtB200Frame *frame, con
     cudaStream_t st = (cudaStream_t)stream;
     const bool hbd = frame->bit_depth > 8;
     // all vertical edges of every plane first, then all horizontal edges (see the header comment)
-    for (int vert = 1; vert >= 0; vert--)
-        for (int plane = p->plane_start; plane < p->plane_end; plane++) {
-            if (plane == 0 && !p->filter_level[0] && !p->filter_level[1]) break; // loop_filter_sb :629-636
-            if (plane == 1 && !p->filter_level_u) continue;
-            if (plane == 2 && !p->filter_level_v) continue;
-            const int ss = plane ? 1 : 0;
-            const int pw = (p->mi_cols * 4) >> ss, ph = (p->mi_rows * 4) >> ss;
-            const int nx = vert ? pw / 4 : pw, ny = vert ? ph : ph / 4;
-            dim3 grid((nx + 255) / 256, ny);
-            if (hbd)
-                SVTB_LAUNCH(dlf_pass_kernel<uint16_t>, grid, 256, 0, st, d, plane, vert);
-            else
-                SVTB_LAUNCH(dlf_pass_kernel<uint8_t>, grid, 256, 0, st, d, plane, vert);
-        }
+    int planes = 0, n_planes = 0, max_w = 0, max_h = 0;
+    for (int plane = p->plane_start; plane < p->plane_end; plane++) {
+        if (plane == 0 && !p->filter_level[0] && !p->filter_level[1]) break; // loop_filter_sb :629-636
+        if (plane == 1 && !p->filter_level_u) continue;
+        if (plane == 2 && !p->filter_level_v) continue;
+        const int ss = plane ? 1 : 0;
+        planes |= plane << (2 * n_planes++);
+        max_w = std::max(max_w, (p->mi_cols * 4) >> ss);
+        max_h = std::max(max_h, (p->mi_rows * 4) >> ss);
+    }
+    for (int vert = 1; vert >= 0 && n_planes; vert--) {
+        const int nx = vert ? max_w / 4 : max_w, ny = vert ? max_h : max_h / 4;
+        dim3 grid((nx + 255) / 256, ny, n_planes);
+        if (hbd)
+            SVTB_LAUNCH(dlf_pass_kernel<uint16_t>, grid, 256, 0, st, d, planes, vert);
+        else
+            SVTB_LAUNCH(dlf_pass_kernel<uint8_t>, grid, 256, 0, st, d, planes, vert);
+    }
     SVTB_CUDA_TRY(cudaGetLastError());
     return SVT_B200_OK;
 }

@@ -164,6 +164,7 @@ struct MeDev {
     RawHme *raw; // [n_sb][2][4]
     HmeState *hstate; // [n_sb]: search centres / pruning / search-area divisors, written by the SB's last HME CTA
     unsigned int *hme_done; // [n_sb]: HME CTAs of the SB that have published their result
+    unsigned int *fp_done; // [n_sb]: full-pel CTAs of the SB that have stored their results
     int sbs_x, sbs_y;
     int slot_l[8], slot_r[8], n_slots;
     int fp_smem_bytes; // dynamic shared memory given to fullpel_kernel
@@ -518,22 +519,63 @@ __device__ __forceinline__ void stage_flat(uint32_t *dst, int wpw, const uint8_t
     }
 }
 
+// Stage `rows` rows into shared memory with a GROUP of `gsize` (power of two) threads, `t` = index inside the group:
+// a row is covered by lw = min(pow2 >= wpw, gsize) lanes, gsize / lw rows per pass, so that row and word come from
+// shifts (the generic flat mapping costs two integer divisions per call, which dominated the small HME windows).
+// Four rows are in flight per thread.
+__device__ __forceinline__ void stage_group(uint32_t *dst, int wpw, const uint8_t *__restrict__ src, ptrdiff_t stride, int rows,
+                                            int nbytes, int t, int gsize) {
+    int lg = 32 - __clz(wpw - 1); // log2(pow2 >= wpw), wpw >= 2
+    const int lgs = 31 - __clz(gsize);
+    if (lg > lgs) lg = lgs;
+    const int lw = 1 << lg, rpp = gsize >> lg, wd0 = t & (lw - 1);
+    for (int row0 = t >> lg; row0 < rows; row0 += 4 * rpp) {
+        for (int wd = wd0; wd < wpw; wd += lw) {
+            uint32_t lo[4], hi[4];
+            int sh[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int row = row0 + u * rpp;
+                lo[u] = hi[u] = 0;
+                sh[u] = 0;
+                if (row < rows) {
+                    const uintptr_t a = (uintptr_t)(src + (ptrdiff_t)row * stride);
+                    const uint32_t *ga = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+                    const int need = (nbytes + (int)(a & 3) + 3) >> 2;
+                    if (wd < need) lo[u] = ga[wd];
+                    if (wd + 1 < need) hi[u] = ga[wd + 1];
+                    sh[u] = (int)(a & 3) * 8;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int row = row0 + u * rpp;
+                if (row < rows) dst[row * wpw + wd] = __funnelshift_r(lo[u], hi[u], sh[u]);
+            }
+        }
+    }
+}
+
 template <int NT, int W>
 __device__ void hme_level_search_aligned(const uint8_t *__restrict__ src, int src_stride, int raw_stride, int k, int bh,
                                          const HmeJob *jobs, int njobs, int tpp, int ntasks, int kshift, uint32_t *smem,
                                          unsigned long long *s_key) {
     const int tid = threadIdx.x;
-    stage_flat(smem, W, src, src_stride, bh, 4 * W, NT);
+    stage_group(smem, W, src, src_stride, bh, 4 * W, tid, NT); // the source block: all threads
     const int span = (bh - 1) * k + 1;
-    for (int j = 0; j < njobs; j++) {
-        const HmeJob jb = jobs[j];
-        stage_flat(smem + jb.woff, jb.wpw, jb.ref, raw_stride, jb.sah - 1 + span, jb.saw - 1 + 4 * W, NT);
+    { // the windows: one quarter of the CTA per search region, concurrently
+        constexpr int GS = NT / 4;
+        for (int j = tid / GS; j < njobs; j += 4) {
+            const HmeJob jb = jobs[j];
+            stage_group(smem + jb.woff, jb.wpw, jb.ref, raw_stride, jb.sah - 1 + span, jb.saw - 1 + 4 * W, tid % GS, GS);
+        }
     }
     __syncthreads();
-    const int sub = tid & (tpp - 1), gpt = NT / tpp;
+    const int ltpp = 31 - __clz(tpp); // tpp is a power of two: shifts instead of divisions
+    const int sub = tid & (tpp - 1), gpt = NT >> ltpp;
     for (int g0 = 0; g0 < ntasks; g0 += gpt) {
-        if (g0 + (tid & ~31) / tpp >= ntasks) continue; // warp-uniform
-        const int t = g0 + tid / tpp;
+        if (g0 + ((tid & ~31) >> ltpp) >= ntasks) continue; // warp-uniform
+        const int t = g0 + (tid >> ltpp);
         int j = 0;
         while (j + 1 < njobs && t >= jobs[j + 1].t0) j++; // warp-uniform: task ranges are padded to whole warps
         const HmeJob jb = jobs[j];
@@ -791,6 +833,113 @@ __global__ void __launch_bounds__(NT_SEARCH, 4) hme_kernel(const __grid_constant
 }
 
 // -----------------------------------------------------------------------------------------------------
+// SB epilogue: me_prune_ref (:2145-2199), construct_me_candidate_array (:2825-2905), MeSbResults (:2964-3040).
+// Run by the LAST full-pel CTA of the SB (all blockDim.x threads; `sm` = >= 640 bytes of free shared memory).
+// Results of the other references were written by other SMs in this same launch: read them through L2 (__ldcg).
+// -----------------------------------------------------------------------------------------------------
+__device__ void finalize_sb(const MeDev &d, int sb, uint32_t *sm) {
+    HmeState &s_h = *reinterpret_cast<HmeState *>(sm); // 160 B
+    uint32_t *s_first = sm + 40; // [85]
+    uint32_t *s_refsad = sm + 128; // [8]: sum of the 64 8x8 SADs per reference (< 2^26)
+    const SvtB200MeParams &p = d.p;
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+    const uint32_t *bsad = d.out.best_sad + (size_t)sb * 2 * 4 * 85;
+    const uint32_t *bmv = d.out.best_mv + (size_t)sb * 2 * 4 * 85;
+    if (tid == 0) s_h = d.hstate[sb];
+    if (tid < 8) s_refsad[tid] = 0;
+    __syncthreads();
+    const bool prune = p.enable_hme_flag && p.enable_hme_level2_flag && p.enable_me_hme_ref_pruning;
+    if (prune) {
+        for (int i = tid; i < 8 * 64; i += nt) { // warp-uniform slot: 64 consecutive items per reference
+            const int slot = i >> 6, l = slot >> 2, r = slot & 3;
+            uint32_t v = 0;
+            if (l < p.num_lists && r < p.num_refs[l] && s_h.do_ref[l][r]) v = __ldcg(bsad + slot * 85 + 21 + (i & 63));
+            v = __reduce_add_sync(0xffffffffu, v);
+            if (lane == 0 && v) atomicAdd(&s_refsad[slot], v);
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        if (prune) {
+            for (int l = 0; l < p.num_lists; l++)
+                for (int r = 0; r < p.num_refs[l]; r++)
+                    s_h.sad[l][r] = s_h.do_ref[l][r] ? (uint64_t)s_refsad[l * 4 + r] : (uint64_t)kMaxSadValue * 64;
+            uint64_t best = s_h.sad[0][0];
+            for (int l = 0; l < 2; l++)
+                for (int r = 0; r < 4; r++) best = s_h.sad[l][r] < best ? s_h.sad[l][r] : best;
+            const uint32_t th = (uint32_t)p.prune_ref_if_me_sad_dev_bigger_than_th & 0xFFFFu;
+            for (int l = 0; l < 2; l++)
+                for (int r = 0; r < 4; r++)
+                    if (th != 0xFFFFu && (s_h.sad[l][r] - best) * 100 > (uint64_t)th * best) s_h.do_ref[l][r] = 0;
+        }
+        for (int l = 0; l < 2; l++)
+            for (int r = 0; r < 4; r++) {
+                SvtB200HmeResult o;
+                o.sc_x = s_h.sc_x[l][r];
+                o.sc_y = s_h.sc_y[l][r];
+                o.do_ref = s_h.do_ref[l][r];
+                o.hme_sad = s_h.sad[l][r];
+                d.out.hme[(size_t)sb * 8 + l * 4 + r] = o;
+            }
+    }
+    __syncthreads();
+    for (int pu = tid; pu < 85; pu += nt) {
+        uint8_t *cand = d.out.me_cand + ((size_t)sb * 85 + pu) * 23;
+        int16_t *mv = d.out.me_mv + ((size_t)sb * 85 + pu) * 7 * 2;
+        for (int i = 0; i < 23; i++) cand[i] = 0;
+        for (int i = 0; i < 14; i++) mv[i] = 0;
+        uint32_t first = 0;
+        int n = 0;
+        if (pu < p.max_number_of_pus_per_sb) {
+            const int n_idx = pu > 20 ? c_tab8[pu - 21] + 21 : pu > 4 ? c_tab16[pu - 5] + 5 : pu;
+            for (int l = 0; l < p.num_lists; l++)
+                for (int r = 0; r < p.num_refs[l]; r++) {
+                    if (!s_h.do_ref[l][r]) continue;
+                    if (n == 0) first = __ldcg(bsad + (l * 4 + r) * 85 + n_idx);
+                    if (n < 23) cand[n] = (uint8_t)(l | (l == 0 ? (r << 2) : (r << 4)) | (l == 1 ? 0x80 : 0));
+                    n++;
+                }
+            if (p.num_lists > 1) {
+                for (int a = 0; a < p.num_refs[0]; a++)
+                    for (int b = 0; b < p.num_refs[1]; b++)
+                        if (s_h.do_ref[0][a] && s_h.do_ref[1][b]) {
+                            if (n < 23) cand[n] = (uint8_t)(2 | (a << 2) | (b << 4) | 0x80);
+                            n++;
+                        }
+                for (int a = 1; a < p.num_refs[0]; a++)
+                    if (s_h.do_ref[0][0] && s_h.do_ref[0][a]) {
+                        if (n < 23) cand[n] = (uint8_t)(2 | (a << 4));
+                        n++;
+                    }
+                if (p.num_refs[1] == 3 && s_h.do_ref[1][0] && s_h.do_ref[1][2]) {
+                    if (n < 23) cand[n] = (uint8_t)(2 | (2 << 4) | 0x40 | 0x80);
+                    n++;
+                }
+            }
+            for (int l = 0; l < p.num_lists; l++)
+                for (int r = 0; r < p.num_refs[l]; r++) {
+                    const uint32_t v = __ldcg(bmv + (l * 4 + r) * 85 + n_idx);
+                    const int s = (l ? 4 : 0) + r;
+                    mv[2 * s] = (int16_t)(v & 0xffff);
+                    mv[2 * s + 1] = (int16_t)(v >> 16);
+                }
+        }
+        d.out.total_cand[(size_t)sb * 85 + pu] = (uint8_t)min(n, 23);
+        s_first[pu] = first;
+    }
+    __syncthreads();
+    if (tid < 32) { // rc_me_distortion: sum of the first candidate's 8x8 (or 16x16) SADs
+        uint32_t rc = 0;
+        if (p.rc_dist_from_8x8)
+            rc = s_first[21 + tid] + s_first[21 + 32 + tid];
+        else if (tid < 16)
+            rc = s_first[5 + tid];
+        rc = __reduce_add_sync(0xffffffffu, rc);
+        if (tid == 0) d.out.rc_me_distortion[sb] = rc;
+    }
+}
+
+// -----------------------------------------------------------------------------------------------------
 // Kernel B: integer full-pel search (integer_search_sb :1868-2139 + open_loop_me_fullpel_search_sblock)
 //
 // Work decomposition.  A "task" is FOUR search positions of one search row that share their byte alignment:
@@ -835,8 +984,7 @@ __global__ void __launch_bounds__(NT_SEARCH, 2) fullpel_kernel(const __grid_cons
             o_sad[i] = 0;
             o_mv[i] = 0;
         }
-        return;
-    }
+    } else {
     const int sx = sb % d.sbs_x, sy = sb / d.sbs_x;
     const int ox = sx * 64, oy = sy * 64;
     const SvtB200Plane &fp = p.full;
@@ -1060,106 +1208,18 @@ __global__ void __launch_bounds__(NT_SEARCH, 2) fullpel_kernel(const __grid_cons
         o_sad[i] = sad;
         o_mv[i] = mv;
     }
+    } // searched reference
+    // the SB's last full-pel CTA runs the SB epilogue (was a separate, latency-bound launch)
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_sad2[0] = (atomicAdd(&d.fp_done[sb], 1u) + 1u == (unsigned int)d.n_slots);
+    __syncthreads();
+    if (s_sad2[0]) {
+        __threadfence();
+        finalize_sb(d, sb, smem);
+    }
 }
 
-// -----------------------------------------------------------------------------------------------------
-// Kernel C: me_prune_ref (:2145-2199), construct_me_candidate_array (:2825-2905), MeSbResults (:2964-3040)
-// -----------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(96) finalize_kernel(const __grid_constant__ MeDev d) {
-    __shared__ HmeState s_h;
-    __shared__ uint32_t s_first[85];
-    const SvtB200MeParams &p = d.p;
-    const int tid = threadIdx.x, sb = blockIdx.x;
-    const uint32_t *bsad = d.out.best_sad + (size_t)sb * 2 * 4 * 85;
-    const uint32_t *bmv = d.out.best_mv + (size_t)sb * 2 * 4 * 85;
-    if (tid == 0) {
-        s_h = d.hstate[sb];
-        const bool prune_ref = p.enable_hme_flag && p.enable_hme_level2_flag;
-        if (prune_ref && p.enable_me_hme_ref_pruning) {
-            for (int l = 0; l < p.num_lists; l++)
-                for (int r = 0; r < p.num_refs[l]; r++) {
-                    if (!s_h.do_ref[l][r]) {
-                        s_h.sad[l][r] = (uint64_t)kMaxSadValue * 64;
-                        continue;
-                    }
-                    uint64_t s = 0;
-                    for (int i = 0; i < 64; i++) s += bsad[(l * 4 + r) * 85 + 21 + i];
-                    s_h.sad[l][r] = s;
-                }
-            uint64_t best = s_h.sad[0][0];
-            for (int l = 0; l < 2; l++)
-                for (int r = 0; r < 4; r++) best = s_h.sad[l][r] < best ? s_h.sad[l][r] : best;
-            const uint32_t th = (uint32_t)p.prune_ref_if_me_sad_dev_bigger_than_th & 0xFFFFu;
-            for (int l = 0; l < 2; l++)
-                for (int r = 0; r < 4; r++)
-                    if (th != 0xFFFFu && (s_h.sad[l][r] - best) * 100 > (uint64_t)th * best) s_h.do_ref[l][r] = 0;
-        }
-        for (int l = 0; l < 2; l++)
-            for (int r = 0; r < 4; r++) {
-                SvtB200HmeResult o;
-                o.sc_x = s_h.sc_x[l][r];
-                o.sc_y = s_h.sc_y[l][r];
-                o.do_ref = s_h.do_ref[l][r];
-                o.hme_sad = s_h.sad[l][r];
-                d.out.hme[(size_t)sb * 8 + l * 4 + r] = o;
-            }
-    }
-    __syncthreads();
-    if (tid < 85) {
-        const int pu = tid;
-        uint8_t *cand = d.out.me_cand + ((size_t)sb * 85 + pu) * 23;
-        int16_t *mv = d.out.me_mv + ((size_t)sb * 85 + pu) * 7 * 2;
-        for (int i = 0; i < 23; i++) cand[i] = 0;
-        for (int i = 0; i < 14; i++) mv[i] = 0;
-        uint32_t first = 0;
-        int n = 0;
-        if (pu < p.max_number_of_pus_per_sb) {
-            const int n_idx = pu > 20 ? c_tab8[pu - 21] + 21 : pu > 4 ? c_tab16[pu - 5] + 5 : pu;
-            for (int l = 0; l < p.num_lists; l++)
-                for (int r = 0; r < p.num_refs[l]; r++) {
-                    if (!s_h.do_ref[l][r]) continue;
-                    if (n == 0) first = bsad[(l * 4 + r) * 85 + n_idx];
-                    if (n < 23) cand[n] = (uint8_t)(l | (l == 0 ? (r << 2) : (r << 4)) | (l == 1 ? 0x80 : 0));
-                    n++;
-                }
-            if (p.num_lists > 1) {
-                for (int a = 0; a < p.num_refs[0]; a++)
-                    for (int b = 0; b < p.num_refs[1]; b++)
-                        if (s_h.do_ref[0][a] && s_h.do_ref[1][b]) {
-                            if (n < 23) cand[n] = (uint8_t)(2 | (a << 2) | (b << 4) | 0x80);
-                            n++;
-                        }
-                for (int a = 1; a < p.num_refs[0]; a++)
-                    if (s_h.do_ref[0][0] && s_h.do_ref[0][a]) {
-                        if (n < 23) cand[n] = (uint8_t)(2 | (a << 4));
-                        n++;
-                    }
-                if (p.num_refs[1] == 3 && s_h.do_ref[1][0] && s_h.do_ref[1][2]) {
-                    if (n < 23) cand[n] = (uint8_t)(2 | (2 << 4) | 0x40 | 0x80);
-                    n++;
-                }
-            }
-            for (int l = 0; l < p.num_lists; l++)
-                for (int r = 0; r < p.num_refs[l]; r++) {
-                    const uint32_t v = bmv[(l * 4 + r) * 85 + n_idx];
-                    const int s = (l ? 4 : 0) + r;
-                    mv[2 * s] = (int16_t)(v & 0xffff);
-                    mv[2 * s + 1] = (int16_t)(v >> 16);
-                }
-        }
-        d.out.total_cand[(size_t)sb * 85 + pu] = (uint8_t)min(n, 23);
-        s_first[pu] = first;
-    }
-    __syncthreads();
-    if (tid == 0) {
-        uint32_t rc = 0;
-        if (p.rc_dist_from_8x8)
-            for (int i = 0; i < 64; i++) rc += s_first[21 + i];
-        else
-            for (int i = 0; i < 16; i++) rc += s_first[5 + i];
-        d.out.rc_me_distortion[sb] = rc;
-    }
-}
 
 // -----------------------------------------------------------------------------------------------------
 // Small kernels behind the RTCD drop-ins (single block worth of work each; fidelity, not throughput)
@@ -1338,7 +1398,7 @@ extern "C" {
 size_t svt_b200_me_scratch_bytes(const SvtB200MeParams *p) {
     if (!p) return 0;
     const size_t n_sb = (size_t)((p->full.width + 63) / 64) * ((p->full.height + 63) / 64);
-    return n_sb * (8 * sizeof(RawHme) + sizeof(HmeState) + sizeof(unsigned int));
+    return n_sb * (8 * sizeof(RawHme) + sizeof(HmeState) + 2 * sizeof(unsigned int));
 }
 
 int svt_b200_me_picture(const SvtB200MeParams *p, const SvtB200MePlanes *src,
@@ -1385,7 +1445,8 @@ int svt_b200_me_picture(const SvtB200MeParams *p, const SvtB200MePlanes *src,
     SVTB_CUDA_TRY(cudaMemsetAsync(out->best_mv, 0, (size_t)n_sb * 8 * 85 * 4, st));
     d.hstate = (HmeState *)(d.raw + (size_t)n_sb * 8);
     d.hme_done = (unsigned int *)(d.hstate + n_sb);
-    SVTB_CUDA_TRY(cudaMemsetAsync(d.raw, 0, (size_t)n_sb * (8 * sizeof(RawHme) + sizeof(HmeState) + sizeof(unsigned int)), st));
+    d.fp_done = d.hme_done + n_sb;
+    SVTB_CUDA_TRY(cudaMemsetAsync(d.raw, 0, (size_t)n_sb * (8 * sizeof(RawHme) + sizeof(HmeState) + 2 * sizeof(unsigned int)), st));
     // worst-case shared memory of one HME level on the fast path (4 windows + the source block)
     size_t hme_need = 0;
     {
@@ -1462,7 +1523,6 @@ int svt_b200_me_picture(const SvtB200MeParams *p, const SvtB200MePlanes *src,
         SVTB_LAUNCH(fullpel_kernel<true>, dim3(n_sb, n), fp_threads, d.fp_smem_bytes, st, d);
     else
         SVTB_LAUNCH(fullpel_kernel<false>, dim3(n_sb, n), fp_threads, d.fp_smem_bytes, st, d);
-    SVTB_LAUNCH(finalize_kernel, n_sb, 96, 0, st, d);
     SVTB_CUDA_TRY(cudaGetLastError());
     return SVT_B200_OK;
 }

@@ -318,17 +318,50 @@ struct EncodeDev {
     int hbd, bd;
     const TuDev *tus;
     int n_tus, tx_size;
-    const int16_t *scan[3]; // device scan tables: default / mrow (V_*) / mcol (H_*) for this tx_size
+    const int16_t *iscan[3]; // device INVERSE scan tables (raster position -> scan index): default / mrow (V_*) / mcol (H_*)
     QuantTab q[3]; // per plane
     int quant_mode; // 0 quantize_b, 2 quantize_fp (the highbd variants are chosen from hbd)
     int32_t *qcoeff; // [n_tus][iw*ih]
     uint16_t *eob; // [n_tus]
 };
+// four horizontally adjacent samples at p (any alignment): aligned 32-bit loads + funnel shift for bytes
 template <typename T>
+__device__ __forceinline__ void load4(const T *p, int (&v)[4]) {
+    if (sizeof(T) == 1) {
+        const uintptr_t a = (uintptr_t)p;
+        const uint32_t *g = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+        const uint32_t w = __funnelshift_r(g[0], (a & 3) ? g[1] : 0u, (int)(a & 3) * 8);
+        v[0] = w & 0xff, v[1] = (w >> 8) & 0xff, v[2] = (w >> 16) & 0xff, v[3] = w >> 24;
+    } else if (((uintptr_t)p & 3) == 0) {
+        const uint32_t w0 = reinterpret_cast<const uint32_t *>(p)[0], w1 = reinterpret_cast<const uint32_t *>(p)[1];
+        v[0] = w0 & 0xffff, v[1] = w0 >> 16, v[2] = w1 & 0xffff, v[3] = w1 >> 16;
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) v[j] = (int)p[j];
+    }
+}
+template <typename T>
+__device__ __forceinline__ void store4(T *p, const int (&v)[4]) {
+    if (sizeof(T) == 1 && ((uintptr_t)p & 3) == 0) {
+        *reinterpret_cast<uint32_t *>(p) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
+    } else if (sizeof(T) == 2 && ((uintptr_t)p & 3) == 0) {
+        reinterpret_cast<uint32_t *>(p)[0] = (uint32_t)v[0] | ((uint32_t)v[1] << 16);
+        reinterpret_cast<uint32_t *>(p)[1] = (uint32_t)v[2] | ((uint32_t)v[3] << 16);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) p[j] = (T)v[j];
+    }
+}
+
+// TS >= 0: kernel specialised for that tx_size (TX_4X4..TX_32X32: every loop bound, the 1-D sizes and the dispatch
+// inside fwd/inv_1d_pass are compile-time, which also keeps the straight-line transform code of the other sizes out of
+// the instruction cache); TS = -1: any size.
+template <typename T, int TS>
 __global__ void __launch_bounds__(TX_NT) encode_tu_kernel(const __grid_constant__ EncodeDev d) {
     extern __shared__ int32_t sm[];
-    const int w = c_txw[d.tx_size], h = c_txh[d.tx_size];
+    const int w = TS >= 0 ? (4 << TS) : c_txw[d.tx_size], h = TS >= 0 ? (4 << TS) : c_txh[d.tx_size];
     const int iw = min(w, 32), ih = min(h, 32), n = iw * ih;
+    const int lw = 31 - __clz(w), liw = 31 - __clz(iw);
     const int Tn = max(w, h), bpc = TX_NT / Tn, pitch = tx_pitch(w);
     const int lb = threadIdx.x / Tn, li = threadIdx.x % Tn;
     const int b = blockIdx.x * bpc + lb;
@@ -337,15 +370,20 @@ __global__ void __launch_bounds__(TX_NT) encode_tu_kernel(const __grid_constant_
     __shared__ int s_eob[TX_NT / 4];
     TuDev tu = {0, 0, 0, 0};
     if (live) tu = d.tus[b];
-    const TxCfg t = make_txcfg(d.tx_size, tu.tx_type);
+    TxCfg t = make_txcfg(TS >= 0 ? TS : d.tx_size, tu.tx_type);
+    if (TS >= 0) t.w = t.h = 4 << TS;
     const int pl = tu.plane;
-    if (live) {
+    if (live) { // residual, four samples per step
         const T *sp = reinterpret_cast<const T *>(d.src[pl]) + (size_t)tu.y * d.src_stride[pl] + tu.x;
         const T *pp = reinterpret_cast<const T *>(d.pred[pl]) + (size_t)tu.y * d.pred_stride[pl] + tu.x;
-        for (int i = li; i < w * h; i += Tn) {
-            const int r = i / w, c = i - r * w;
-            const int rr = t.ud ? h - 1 - r : r, cc = t.lr ? w - 1 - c : c;
-            buf[r * pitch + c] = (int16_t)((int)sp[(size_t)rr * d.src_stride[pl] + cc] - (int)pp[(size_t)rr * d.pred_stride[pl] + cc]);
+        for (int i = li; i < (w * h) >> 2; i += Tn) {
+            const int r = i >> (lw - 2), c = (i & ((w >> 2) - 1)) << 2;
+            const int rr = t.ud ? h - 1 - r : r, cc = t.lr ? w - 4 - c : c;
+            int sv[4], pv[4];
+            load4<T>(sp + (size_t)rr * d.src_stride[pl] + cc, sv);
+            load4<T>(pp + (size_t)rr * d.pred_stride[pl] + cc, pv);
+#pragma unroll
+            for (int j = 0; j < 4; j++) buf[r * pitch + c + j] = sv[t.lr ? 3 - j : j] - pv[t.lr ? 3 - j : j];
         }
         if (li == 0) s_eob[lb] = 0;
     }
@@ -367,26 +405,29 @@ __global__ void __launch_bounds__(TX_NT) encode_tu_kernel(const __grid_constant_
             });
         }
     __syncthreads();
-    // quantise + dequantise in place (coefficients outside the kept 32x32 of 64-wide sizes are dropped = 0)
+    // quantise + dequantise in place, in raster order (every coefficient is quantised independently; the scan order
+    // only defines eob = 1 + the largest scan index of a non-zero level, looked up for the non-zero levels only).
+    // Coefficients outside the kept 32x32 of 64-wide sizes are dropped = 0.
     if (live) {
         const int log_scale = (w * h > 256) + (w * h > 1024); // av1_get_tx_scale
         const int mode = d.quant_mode + (d.hbd ? 1 : 0);
-        const int16_t *scan = d.scan[(t.vk != 3 && t.hk == 3) ? 1 : (t.vk == 3 && t.hk != 3) ? 2 : 0];
+        const int16_t *iscan = d.iscan[(t.vk != 3 && t.hk == 3) ? 1 : (t.vk == 3 && t.hk != 3) ? 2 : 0];
         int32_t *qout = d.qcoeff + (size_t)b * n;
         int eob = 0;
         for (int i = li; i < n; i += Tn) {
-            const int rc = scan[i], r = rc / iw, c = rc - r * iw;
+            const int r = i >> liw, c = i & (iw - 1);
             int32_t qc, dqc;
-            quant_one(mode, buf[r * pitch + c], rc != 0, d.q[pl], log_scale, 32, 32, qc, dqc);
-            qout[rc] = qc;
+            quant_one(mode, buf[r * pitch + c], i != 0, d.q[pl], log_scale, 32, 32, qc, dqc);
+            qout[i] = qc;
             buf[r * pitch + c] = dqc;
-            if (qc) eob = max(eob, i + 1);
+            if (qc) eob = max(eob, (int)iscan[i] + 1);
         }
         if (eob) atomicMax(&s_eob[lb], eob);
-        for (int i = li; i < w * h; i += Tn) { // zero the dropped high-frequency area of 64-wide transforms
-            const int r = i / w, c = i - r * w;
-            if (r >= ih || c >= iw) buf[r * pitch + c] = 0;
-        }
+        if (w > 32 || h > 32)
+            for (int i = li; i < w * h; i += Tn) { // zero the dropped high-frequency area of 64-wide transforms
+                const int r = i >> lw, c = i & (w - 1);
+                if (r >= ih || c >= iw) buf[r * pitch + c] = 0;
+            }
     }
     __syncthreads();
     const int bd = d.bd;
@@ -410,15 +451,21 @@ __global__ void __launch_bounds__(TX_NT) encode_tu_kernel(const __grid_constant_
         }
     }
     __syncthreads();
-    if (live) {
+    if (live) { // reconstruction, four samples per step
         const T *pp = reinterpret_cast<const T *>(d.pred[pl]) + (size_t)tu.y * d.pred_stride[pl] + tu.x;
         T *rp = reinterpret_cast<T *>(d.recon[pl]) + (size_t)tu.y * d.recon_stride[pl] + tu.x;
         const int mx = (1 << bd) - 1;
-        for (int i = li; i < w * h; i += Tn) {
-            const int r = i / w, c = i - r * w;
-            const int32_t res = buf[(t.ud ? h - 1 - r : r) * pitch + (t.lr ? w - 1 - c : c)];
-            const int v = (int)pp[(size_t)r * d.pred_stride[pl] + c] + res;
-            rp[(size_t)r * d.recon_stride[pl] + c] = (T)(v < 0 ? 0 : (v > mx ? mx : v));
+        for (int i = li; i < (w * h) >> 2; i += Tn) {
+            const int r = i >> (lw - 2), c = (i & ((w >> 2) - 1)) << 2;
+            int pv[4], o[4];
+            load4<T>(pp + (size_t)r * d.pred_stride[pl] + c, pv);
+            const int32_t *br = buf + (t.ud ? h - 1 - r : r) * pitch;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int v = pv[j] + br[t.lr ? w - 1 - (c + j) : c + j];
+                o[j] = v < 0 ? 0 : (v > mx ? mx : v);
+            }
+            store4<T>(rp + (size_t)r * d.recon_stride[pl] + c, o);
         }
     }
 }
@@ -438,8 +485,8 @@ static void tx_attrs() {
     if (g_tx_attr) return;
     cudaFuncSetAttribute(fwd_txfm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     cudaFuncSetAttribute(inv_txfm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(encode_tu_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(encode_tu_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(encode_tu_kernel<uint8_t, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+    cudaFuncSetAttribute(encode_tu_kernel<uint16_t, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
     g_tx_attr = true;
 }
 
@@ -792,6 +839,34 @@ int svt_b200_get_scan(int tx_size, int tx_type, int16_t *scan_out) {
     return n;
 }
 
+
+} // extern "C"
+namespace {
+// device-resident inverse scan tables: [device][tx_size] -> 3 x 1024 int16
+const int16_t *iscan_tables(int tx_size) {
+    static std::mutex mu;
+    static int16_t *tabs[64][19] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(mu);
+    if (tabs[dev][tx_size]) return tabs[dev][tx_size];
+    static int16_t hs[1024], hi[3][1024];
+    const int types[3] = {0, 10, 11}; // DCT_DCT (default scan), V_DCT (mrow), H_DCT (mcol)
+    const int n = (h_txw[tx_size] > 32 ? 32 : h_txw[tx_size]) * (h_txh[tx_size] > 32 ? 32 : h_txh[tx_size]);
+    for (int k = 0; k < 3; k++) {
+        svt_b200_get_scan(tx_size, types[k], hs);
+        for (int i = 0; i < 1024; i++) hi[k][i] = 0;
+        for (int i = 0; i < n; i++) hi[k][hs[i]] = (int16_t)i;
+    }
+    int16_t *dp = nullptr;
+    if (cudaMalloc(&dp, sizeof(hi)) != cudaSuccess) return nullptr;
+    if (cudaMemcpy(dp, hi, sizeof(hi), cudaMemcpyHostToDevice) != cudaSuccess) return nullptr;
+    tabs[dev][tx_size] = dp;
+    return dp;
+}
+} // namespace
+extern "C" {
+
 int svt_b200_encode_tus(const SvtB200EncodeParams *p, const SvtB200Frame *src, const SvtB200Frame *pred,
                         const SvtB200Frame *recon, const SvtB200Tu *tus, int32_t n_tus, int32_t *qcoeff, uint16_t *eob,
                         void *scratch, void *stream) {
@@ -829,18 +904,30 @@ int svt_b200_encode_tus(const SvtB200EncodeParams *p, const SvtB200Frame *src, c
     d.quant_mode = p->use_fp ? 2 : 0;
     d.qcoeff = qcoeff;
     d.eob = eob;
-    // scan tables for this size live at the start of `scratch` (3 x 1024 int16), refreshed per call (6 KB)
-    int16_t hs[3][1024];
-    svt_b200_get_scan(p->tx_size, 0, hs[0]);
-    svt_b200_get_scan(p->tx_size, 10, hs[1]);
-    svt_b200_get_scan(p->tx_size, 11, hs[2]);
+    // inverse scan tables of this size: built once per (device, tx_size) and kept resident (`scratch` is unused since
+    // then; the parameter stays for ABI stability)
+    (void)scratch;
+    const int16_t *tab = iscan_tables(p->tx_size);
+    if (!tab) return SVT_B200_ERR_CUDA;
+    for (int i = 0; i < 3; i++) d.iscan[i] = tab + i * 1024;
     cudaStream_t st = (cudaStream_t)stream;
-    SVTB_CUDA_TRY(cudaMemcpyAsync(scratch, hs, sizeof(hs), cudaMemcpyHostToDevice, st));
-    for (int i = 0; i < 3; i++) d.scan[i] = (const int16_t *)scratch + i * 1024;
-    if (d.hbd)
-        SVTB_LAUNCH(encode_tu_kernel<uint16_t>, tx_grid(p->tx_size, n_tus), TX_NT, tx_smem_bytes(p->tx_size), st, d);
-    else
-        SVTB_LAUNCH(encode_tu_kernel<uint8_t>, tx_grid(p->tx_size, n_tus), TX_NT, tx_smem_bytes(p->tx_size), st, d);
+    const int grid = tx_grid(p->tx_size, n_tus);
+    const size_t smem = tx_smem_bytes(p->tx_size);
+#define SVTB_ENC(TSV)                                                                          \
+    do {                                                                                       \
+        if (d.hbd)                                                                             \
+            SVTB_LAUNCH((encode_tu_kernel<uint16_t, TSV>), grid, TX_NT, smem, st, d);          \
+        else                                                                                   \
+            SVTB_LAUNCH((encode_tu_kernel<uint8_t, TSV>), grid, TX_NT, smem, st, d);           \
+    } while (0)
+    switch (p->tx_size) {
+    case 0: SVTB_ENC(0); break;
+    case 1: SVTB_ENC(1); break;
+    case 2: SVTB_ENC(2); break;
+    case 3: SVTB_ENC(3); break;
+    default: SVTB_ENC(-1); break;
+    }
+#undef SVTB_ENC
     SVTB_CUDA_TRY(cudaGetLastError());
     return SVT_B200_OK;
 }
