@@ -224,7 +224,7 @@ def reference_frames_per_second(n_frames, repeats=1):
 def run_reference(args):
     import common as cm
     if not cm.have_ref():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built on this box"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref not built on this box"})
         return
     cores = os.cpu_count() or 1
     sample = max(1, min(FRAMES_PER_STEP if cores < 16 else 2 * FRAMES_PER_STEP, cores))
@@ -238,7 +238,7 @@ def run_reference(args):
                              "sample": f"{nfr} frames per step of the same 1080p workload, one frame per thread, unmodified "
                                        "reference C paths (-O2, no SIMD: no nasm in the image)"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -528,7 +528,7 @@ def run_b200(args):
     if rank == 0:
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -592,6 +592,18 @@ def cpu_baseline():
                       "reference C (-O2, no SIMD)"}
 
 
+_REAL_STDOUT = None
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -600,6 +612,12 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON result): anything libraries print to fd 1 (e.g. NCCL's version banner)
+    # is routed to stderr, and emit() writes the result to the real stdout
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         if int(os.environ.get("RANK", 0)) == 0:
             run_reference(args)

@@ -423,7 +423,10 @@ typedef struct SvtB200DlfMi {
     uint8_t skip_inter; /* block_mi.skip && is_inter_block */
     uint8_t lvl_y[2]; /* filter level for luma vertical edges [0] / horizontal edges [1] */
     uint8_t lvl_u, lvl_v;
-    uint8_t pad[3];
+    uint8_t lvl_class; /* segment_id * 16 + ref_frame[0] * 2 + mode_lf_lut[mode]: the only block properties the level
+                          table lfi_n->lvl[plane][seg][dir][ref][mode] is indexed by (EbDeblockingCommon.c:42-73); read
+                          instead of lvl_* by the entries that take a level table (svt_b200_pick_filter_level) */
+    uint8_t pad[2];
 } SvtB200DlfMi;
 
 typedef struct SvtB200DlfParams {
@@ -439,6 +442,41 @@ typedef struct SvtB200DlfParams {
  * [mi_rows][mi_stride]. Two launches per call (all vertical edges, then all horizontal edges). */
 SVT_B200_API int svt_b200_dlf_frame(const SvtB200DlfParams *p, const SvtB200Frame *frame,
                                     const SvtB200DlfMi *mi, void *stream);
+
+/* What svt_av1_loop_filter_frame_init (EbDeblockingCommon.c:78-145) reads besides the four frame levels. */
+typedef struct SvtB200LfFrameInit {
+    int32_t mode_ref_delta_enabled; /* lf->mode_ref_delta_enabled */
+    int8_t ref_deltas[8], mode_deltas[2]; /* lf->ref_deltas[REF_FRAMES], lf->mode_deltas[MAX_MODE_LF_DELTAS] */
+    int32_t segmentation_enabled; /* frm_hdr->segmentation_params.segmentation_enabled */
+    uint8_t seg_feature_mask[8]; /* bit f: feature f active for the segment (features 1..4 = ALT_LF_Y_V, Y_H, U, V) */
+    int16_t seg_feature_data[8][8]; /* segmentation_params.feature_data[segment][feature] */
+} SvtB200LfFrameInit;
+
+/* The level table of svt_av1_loop_filter_frame_init for frame levels {y vertical, y horizontal, u, v}:
+ * lut[plane][dir][lvl_class]. Host function (no GPU work). */
+SVT_B200_API int svt_b200_lf_level_lut(const SvtB200LfFrameInit *init, const int32_t levels[4], uint8_t lut[3][2][128]);
+
+/* svt_av1_pick_filter_level (EbDeblockingFilter.c:1193-1297) with search_filter_level / try_filter_frame /
+ * picture_sse_calculations (:1027-1191, :966-1026, :830-964).  method: LpfPickMethod (0 full image, 1 sub-image,
+ * 2 from q, 3 minimal).  For methods 0/1 every trial is one device deblocking pass of one plane of `recon` + one SSE
+ * against `source` + a plane copy back from `temp`; the bisection itself runs on the host (one 8-byte D2H per trial).
+ * recon is unchanged on return.  Blocks take their level from the table of svt_b200_lf_level_lut via lvl_class
+ * (delta_lf_present pictures are not searched by the reference's callers either). */
+typedef struct SvtB200LpfPickParams {
+    SvtB200DlfParams dlf; /* geometry; the levels / sharpness fields are ignored (sharpness is forced to 0, :1202) */
+    SvtB200LfFrameInit init;
+    int32_t method; /* LPF_PICK_FROM_FULL_IMAGE 0, LPF_PICK_FROM_SUBIMAGE 1, LPF_PICK_FROM_Q 2, LPF_PICK_MINIMAL_LPF 3 */
+    int32_t loop_filter_mode; /* pcs->parent_pcs_ptr->loop_filter_mode (<= 2: one +-2 refinement, else bisection) */
+    int32_t tx_mode_only_4x4; /* frm_hdr->tx_mode == ONLY_4X4 */
+    int32_t q_ac; /* svt_av1_ac_quant_q3(base_q_idx, 0, bit_depth), method 2 only */
+    int32_t key_frame; /* frm_hdr->frame_type == KEY_FRAME, method 2 only */
+    int32_t last_level[4]; /* lf->filter_level[0], [1], filter_level_u, filter_level_v on entry */
+} SvtB200LpfPickParams;
+/* scratch: >= 1 KB of device memory.  levels_out: host int32[4] = {filter_level[0], [1], u, v}. temp: a frame of the same
+ * geometry as recon (contents are overwritten). */
+SVT_B200_API int svt_b200_pick_filter_level(const SvtB200LpfPickParams *p, const SvtB200Frame *recon,
+                                            const SvtB200Frame *source, const SvtB200Frame *temp,
+                                            const SvtB200DlfMi *mi, void *scratch, int32_t *levels_out, void *stream);
 
 /* Sum of squared differences of two pictures per plane (picture_sse_calculations,
  * EbDeblockingFilter.c:830-964), the distortion measure of svt_av1_pick_filter_level. sse: device uint64[3]. */

@@ -193,3 +193,147 @@ void orc_frame_sse(const SvtB200Frame *a, const SvtB200Frame *b, uint64_t *sse) 
         sse[pl] = s;
     }
 }
+
+/* ---- svt_av1_loop_filter_frame_init (Common/Codec/EbDeblockingCommon.c:78-145) as a table over the level class
+ *      cls = segment_id * 16 + ref_frame[0] * 2 + mode_lf_lut[mode] -------------------------------------------- */
+void orc_lf_level_lut(const SvtB200LfFrameInit *init, const int32_t levels[4], uint8_t lut[3][2][128]) {
+    static const int feature[3][2] = {{1, 2}, {3, 3}, {4, 4}}; /* seg_lvl_lf_lut */
+    memset(lut, 0, 3 * 2 * 128);
+    for (int plane = 0; plane < 3; plane++) {
+        const int lv[2] = {plane == 0 ? levels[0] : levels[1 + plane], plane == 0 ? levels[1] : levels[1 + plane]};
+        if (plane == 0 && !lv[0] && !lv[1]) break;
+        if (plane && !lv[0]) continue;
+        for (int cls = 0; cls < 128; cls++) {
+            const int seg = cls >> 4, ref = (cls >> 1) & 7, mode = cls & 1;
+            for (int dir = 0; dir < 2; dir++) {
+                int l = lv[dir];
+                if (init->segmentation_enabled && (init->seg_feature_mask[seg] >> feature[plane][dir] & 1)) {
+                    l += init->seg_feature_data[seg][feature[plane][dir]];
+                    l = l < 0 ? 0 : l > 63 ? 63 : l;
+                }
+                if (init->mode_ref_delta_enabled) {
+                    const int scale = 1 << (l >> 5);
+                    l += init->ref_deltas[ref] * scale + (ref ? init->mode_deltas[mode] * scale : 0);
+                    l = l < 0 ? 0 : l > 63 ? 63 : l;
+                }
+                lut[plane][dir][cls] = (uint8_t)l;
+            }
+        }
+    }
+}
+
+/* ---- svt_av1_pick_filter_level (Encoder/Codec/EbDeblockingFilter.c:1193-1297) -------------------------------- */
+typedef struct {
+    const SvtB200LpfPickParams *p;
+    const SvtB200Frame *recon, *source, *temp;
+    const SvtB200DlfMi *mi;
+    SvtB200DlfMi *mi_lv; /* copy of mi whose lvl_* fields carry the trial levels */
+    int32_t hdr[4]; /* frm_hdr->loop_filter_params levels */
+} PickState;
+
+static void copy_plane(const SvtB200Frame *s, const SvtB200Frame *d, int plane) { /* svt_copy_buffer :756-823 */
+    const int es = s->bit_depth > 8 ? 2 : 1, w = plane ? s->width >> 1 : s->width, h = plane ? s->height >> 1 : s->height;
+    const uint8_t *sp = plane == 0 ? s->y : plane == 1 ? s->cb : s->cr;
+    uint8_t *dp = plane == 0 ? d->y : plane == 1 ? d->cb : d->cr;
+    const size_t ss = (size_t)(plane ? s->stride_c : s->stride_y) * es, ds = (size_t)(plane ? d->stride_c : d->stride_y) * es;
+    for (int y = 0; y < h; y++) memcpy(dp + y * ds, sp + y * ss, (size_t)w * es);
+}
+
+static int64_t try_level(PickState *st, int level, int plane, int dir) { /* try_filter_frame :966-1026 */
+    if (plane == 0) {
+        if (dir == 0 || dir == 2) st->hdr[0] = level;
+        if (dir == 1 || dir == 2) st->hdr[1] = level;
+    } else {
+        st->hdr[1 + plane] = level;
+    }
+    uint8_t lut[3][2][128];
+    orc_lf_level_lut(&st->p->init, st->hdr, lut);
+    const SvtB200DlfParams *g = &st->p->dlf;
+    for (int r = 0; r < g->mi_rows; r++)
+        for (int c = 0; c < g->mi_cols; c++) {
+            SvtB200DlfMi *m = &st->mi_lv[(size_t)r * g->mi_stride + c];
+            const int cls = m->lvl_class & 127;
+            m->lvl_y[0] = lut[0][0][cls], m->lvl_y[1] = lut[0][1][cls], m->lvl_u = lut[1][0][cls], m->lvl_v = lut[2][0][cls];
+        }
+    SvtB200DlfParams dp = *g;
+    dp.sharpness = 0;
+    dp.filter_level[0] = st->hdr[0], dp.filter_level[1] = st->hdr[1], dp.filter_level_u = st->hdr[2], dp.filter_level_v = st->hdr[3];
+    dp.plane_start = plane, dp.plane_end = plane + 1;
+    orc_dlf_frame(&dp, st->recon, st->mi_lv);
+    uint64_t sse[3];
+    orc_frame_sse(st->source, st->recon, sse); /* picture_sse_calculations :830-964 (one plane is used) */
+    copy_plane(st->temp, st->recon, plane);
+    return (int64_t)sse[plane];
+}
+
+static int search_level(PickState *st, int plane, int dir) { /* search_filter_level :1027-1191 */
+    const int last = plane == 0 ? st->p->last_level[dir] : st->p->last_level[1 + plane];
+    int mid = last < 0 ? 0 : last > 63 ? 63 : last, step = mid < 16 ? 4 : mid / 4, direction = 0;
+    int64_t err[64];
+    for (int i = 0; i < 64; i++) err[i] = -1;
+    copy_plane(st->recon, st->temp, plane);
+    int64_t best = err[mid] = try_level(st, mid, plane, dir);
+    int pick = mid;
+    const int once = st->p->loop_filter_mode <= 2;
+    if (once) step = 2;
+    while (step > 0) {
+        const int hi = mid + step > 63 ? 63 : mid + step, lo = mid - step < 0 ? 0 : mid - step;
+        int64_t bias = (best >> (15 - mid / 8)) * step;
+        if (!st->p->tx_mode_only_4x4) bias >>= 1;
+        if (direction <= 0 && lo != mid) {
+            if (err[lo] < 0) err[lo] = try_level(st, lo, plane, dir);
+            if (err[lo] < best + bias) {
+                if (err[lo] < best) best = err[lo];
+                pick = lo;
+            }
+        }
+        if (direction >= 0 && hi != mid) {
+            if (err[hi] < 0) err[hi] = try_level(st, hi, plane, dir);
+            if (err[hi] < best - bias) {
+                if (!once) best = err[hi];
+                pick = hi;
+            }
+        }
+        if (once) break;
+        if (pick == mid) {
+            step /= 2;
+            direction = 0;
+        } else {
+            direction = pick < mid ? -1 : 1;
+            mid = pick;
+        }
+    }
+    return pick;
+}
+
+void orc_pick_filter_level(const SvtB200LpfPickParams *p, const SvtB200Frame *recon, const SvtB200Frame *source,
+                           const SvtB200Frame *temp, const SvtB200DlfMi *mi, int32_t *levels_out) {
+    if (p->method == 3) {
+        levels_out[0] = levels_out[1] = 0;
+        levels_out[2] = p->last_level[2], levels_out[3] = p->last_level[3];
+        return;
+    }
+    if (p->method == 2) { /* LPF_PICK_FROM_Q :1209-1249 */
+        const int bd = recon->bit_depth;
+        const int64_t q = p->q_ac;
+        int g;
+        if (bd == 8) g = p->key_frame ? (int)((q * 17563 - 421574 + (1 << 17)) >> 18) : (int)((q * 6017 + 650707 + (1 << 17)) >> 18);
+        else if (bd == 10) g = (int)((q * 20723 + 4060632 + (1 << 19)) >> 20);
+        else g = (int)((q * 20723 + 16242526 + (1 << 21)) >> 22);
+        if (bd != 8 && p->key_frame) g -= 4;
+        g = g > 2 ? g - 2 : g > 1 ? g - 1 : g;
+        const int gc = g > 1 ? g / 2 : g;
+        levels_out[0] = levels_out[1] = g < 0 ? 0 : g > 63 ? 63 : g;
+        levels_out[2] = levels_out[3] = gc < 0 ? 0 : gc > 63 ? 63 : gc;
+        return;
+    }
+    PickState st = {p, recon, source, temp, mi, NULL, {p->last_level[0], p->last_level[1], p->last_level[2], p->last_level[3]}};
+    const size_t n = (size_t)p->dlf.mi_rows * p->dlf.mi_stride;
+    st.mi_lv = (SvtB200DlfMi *)malloc(n * sizeof(SvtB200DlfMi));
+    memcpy(st.mi_lv, mi, n * sizeof(SvtB200DlfMi));
+    st.hdr[0] = st.hdr[1] = search_level(&st, 0, 2);
+    st.hdr[2] = search_level(&st, 1, 0);
+    st.hdr[3] = search_level(&st, 2, 0);
+    for (int i = 0; i < 4; i++) levels_out[i] = st.hdr[i];
+    free(st.mi_lv);
+}

@@ -78,6 +78,9 @@ ORC_API void orc_quantize_fp(const int32_t *coeff, intptr_t n, const int16_t *ro
 ORC_API void orc_lpf_edge(void *s, int hbd, int across, int along, int len, int blimit, int limit, int thresh, int bd);
 ORC_API void orc_dlf_frame(const SvtB200DlfParams *p, const SvtB200Frame *f, const SvtB200DlfMi *mi);
 ORC_API void orc_frame_sse(const SvtB200Frame *a, const SvtB200Frame *b, uint64_t *sse);
+ORC_API void orc_lf_level_lut(const SvtB200LfFrameInit *init, const int32_t levels[4], uint8_t lut[3][2][128]);
+ORC_API void orc_pick_filter_level(const SvtB200LpfPickParams *p, const SvtB200Frame *recon, const SvtB200Frame *source,
+                                   const SvtB200Frame *temp, const SvtB200DlfMi *mi, int32_t *levels_out);
 /* ---- lr_oracle.c ---- */
 ORC_API void orc_selfguided_restoration(const void *dgd, int hbd, int width, int height, int dgd_stride, int32_t *flt0,
                                         int32_t *flt1, int flt_stride, int sgr_params_idx, int bit_depth);

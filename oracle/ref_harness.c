@@ -423,10 +423,10 @@ REFH_API int refh_get_scan(int tx_size, int tx_type, int16_t *out) {
 #include "EbUtility.h"
 void svt_av1_loop_filter_init(PictureControlSet *pcs_ptr);
 
-REFH_API int refh_dlf_frame(int mi_rows, int mi_cols, const uint8_t *sb_type, const uint8_t *tx_depth,
-                            const uint8_t *is_inter, const uint8_t *skip, const int32_t *levels /*y0,y1,u,v*/,
-                            int sharpness, SvtB200Frame *frame, SvtB200DlfMi *flat /*[mi_rows][mi_cols]*/) {
-    FiltCtx *c = filt_ctx_new(mi_rows, mi_cols, frame->bit_depth, frame, NULL, NULL, 0, NULL);
+static FiltCtx *dlf_ctx(int mi_rows, int mi_cols, const uint8_t *sb_type, const uint8_t *tx_depth, const uint8_t *is_inter,
+                        const uint8_t *skip, const int32_t *levels /*y0,y1,u,v*/, int sharpness, SvtB200Frame *frame,
+                        const SvtB200Frame *source, SvtB200DlfMi *flat /*[mi_rows][mi_cols]*/) {
+    FiltCtx *c = filt_ctx_new(mi_rows, mi_cols, frame->bit_depth, frame, source, NULL, 0, NULL);
     c->ppcs->scs_ptr = c->scs;
     c->scs->seq_header.sb_size = BLOCK_64X64;
     c->scs->sb_size_pix = 64;
@@ -434,6 +434,7 @@ REFH_API int refh_dlf_frame(int mi_rows, int mi_cols, const uint8_t *sb_type, co
     c->scs->max_input_luma_height = (uint16_t)(mi_rows * 4);
     c->scs->max_input_pad_right = 0;
     c->scs->max_input_pad_bottom = 0;
+    c->scs->subsampling_x = c->scs->subsampling_y = 1;
     struct LoopFilter *lf = &c->ppcs->frm_hdr.loop_filter_params;
     lf->filter_level[0] = levels[0];
     lf->filter_level[1] = levels[1];
@@ -472,13 +473,60 @@ REFH_API int refh_dlf_frame(int mi_rows, int mi_cols, const uint8_t *sb_type, co
                 f->lvl_y[1] = (uint8_t)levels[1];
                 f->lvl_u = (uint8_t)levels[2];
                 f->lvl_v = (uint8_t)levels[3];
+                /* segment 0, ref_frame[0], mode_lf_lut[mode] (NEARESTMV -> 1, DC_PRED -> 0) */
+                f->lvl_class = (uint8_t)((is_inter[i] ? LAST_FRAME : INTRA_FRAME) * 2 + (is_inter[i] ? 1 : 0));
             }
         }
     svt_av1_loop_filter_init(c->pcs);
     c->recon.bit_depth = frame->bit_depth > 8 ? EB_10BIT : EB_8BIT;
     c->recon.width = (uint16_t)(mi_cols * 4);
     c->recon.height = (uint16_t)(mi_rows * 4);
+    return c;
+}
+
+REFH_API int refh_dlf_frame(int mi_rows, int mi_cols, const uint8_t *sb_type, const uint8_t *tx_depth,
+                            const uint8_t *is_inter, const uint8_t *skip, const int32_t *levels /*y0,y1,u,v*/,
+                            int sharpness, SvtB200Frame *frame, SvtB200DlfMi *flat /*[mi_rows][mi_cols]*/) {
+    FiltCtx *c = dlf_ctx(mi_rows, mi_cols, sb_type, tx_depth, is_inter, skip, levels, sharpness, frame, NULL, flat);
     svt_av1_loop_filter_frame(&c->recon, c->pcs, 0, 3);
+    filt_ctx_free(c);
+    return 0;
+}
+
+/* svt_av1_pick_filter_level (EbDeblockingFilter.c:1193) on the same picture description; `temp` is the DlfContext's
+ * temp_lf_recon_picture; mode_ref_delta (ref_deltas / mode_deltas) optional. */
+#include "EbDlfProcess.h"
+REFH_API int refh_pick_filter_level(int mi_rows, int mi_cols, const uint8_t *sb_type, const uint8_t *tx_depth,
+                                    const uint8_t *is_inter, const uint8_t *skip, const int32_t *last_levels, int method,
+                                    int loop_filter_mode, int tx_mode_only_4x4, int base_q_idx, int key_frame,
+                                    const int8_t *ref_deltas /*8 or NULL*/, const int8_t *mode_deltas /*2*/,
+                                    SvtB200Frame *recon, const SvtB200Frame *source, SvtB200Frame *temp, int32_t *levels_out) {
+    FiltCtx *c = dlf_ctx(mi_rows, mi_cols, sb_type, tx_depth, is_inter, skip, last_levels, 0, recon, source, NULL);
+    FrameHeader *fh = &c->ppcs->frm_hdr;
+    c->ppcs->loop_filter_mode = (uint8_t)loop_filter_mode;
+    fh->tx_mode = tx_mode_only_4x4 ? ONLY_4X4 : TX_MODE_SELECT;
+    fh->quantization_params.base_q_idx = (uint8_t)base_q_idx;
+    fh->frame_type = key_frame ? KEY_FRAME : INTER_FRAME;
+    if (ref_deltas) {
+        fh->loop_filter_params.mode_ref_delta_enabled = 1;
+        for (int i = 0; i < 8; i++) fh->loop_filter_params.ref_deltas[i] = ref_deltas[i];
+        for (int i = 0; i < 2; i++) fh->loop_filter_params.mode_deltas[i] = mode_deltas[i];
+    }
+    DlfContext ctx;
+    memset(&ctx, 0, sizeof(ctx));
+    EbPictureBufferDesc tdesc = c->recon;
+    tdesc.buffer_y = temp->y;
+    tdesc.buffer_cb = temp->cb;
+    tdesc.buffer_cr = temp->cr;
+    tdesc.stride_y = (uint16_t)temp->stride_y;
+    tdesc.stride_cb = tdesc.stride_cr = (uint16_t)temp->stride_c;
+    ctx.temp_lf_recon_picture_ptr = &tdesc;
+    ctx.temp_lf_recon_picture16bit_ptr = &tdesc;
+    svt_av1_pick_filter_level(&ctx, &c->input, c->pcs, (LpfPickMethod)method);
+    levels_out[0] = fh->loop_filter_params.filter_level[0];
+    levels_out[1] = fh->loop_filter_params.filter_level[1];
+    levels_out[2] = fh->loop_filter_params.filter_level_u;
+    levels_out[3] = fh->loop_filter_params.filter_level_v;
     filt_ctx_free(c);
     return 0;
 }

@@ -103,6 +103,7 @@ struct DlfDev {
     int stride[3];
     int bd;
     const SvtB200DlfMi *mi;
+    const uint8_t *lut; // device [3][2][128] level table indexed by lvl_class, or null: per-mi levels
 };
 
 // set_lpf_parameters on the flattened summary
@@ -116,8 +117,15 @@ __device__ __forceinline__ int edge_params(const DlfDev &d, int plane, int vert,
     if ((coord & (ts - 1)) || !coord) return 0;
     const SvtB200DlfMi *prev = vert ? cur - (1 << ss) : cur - (size_t)(1 << ss) * p.mi_stride;
     const int pv_ts = vert ? prev->tx_w[ss] : prev->tx_h[ss];
-    const int cl = plane == 0 ? cur->lvl_y[vert ? 0 : 1] : plane == 1 ? cur->lvl_u : cur->lvl_v;
-    const int pl = plane == 0 ? prev->lvl_y[vert ? 0 : 1] : plane == 1 ? prev->lvl_u : prev->lvl_v;
+    int cl, pl;
+    if (d.lut) { // get_filter_level: lfi_n->lvl[plane][segment][dir][ref][mode], dir 0 = vertical edges
+        const uint8_t *t = d.lut + (plane * 2 + (vert ? 0 : 1)) * 128;
+        cl = t[cur->lvl_class & 127];
+        pl = t[prev->lvl_class & 127];
+    } else {
+        cl = plane == 0 ? cur->lvl_y[vert ? 0 : 1] : plane == 1 ? cur->lvl_u : cur->lvl_v;
+        pl = plane == 0 ? prev->lvl_y[vert ? 0 : 1] : plane == 1 ? prev->lvl_u : prev->lvl_v;
+    }
     const bool pu_edge = !(coord & ((vert ? cur->blk_w[ss] : cur->blk_h[ss]) - 1));
     if (!((cl || pl) && (!prev->skip_inter || !cur->skip_inter || pu_edge))) return 0;
     const int mn = min(ts, pv_ts);
@@ -250,7 +258,8 @@ LPF_DROPIN(vertical, 1, 6)
 LPF_DROPIN(vertical, 1, 8)
 LPF_DROPIN(vertical, 1, 14)
 
-int svt_b200_dlf_frame(const SvtB200DlfParams *p, const SvtB200Frame *frame, const SvtB200DlfMi *mi, void *stream) {
+static int dlf_frame_impl(const SvtB200DlfParams *p, const SvtB200Frame *frame, const SvtB200DlfMi *mi, const uint8_t *lut,
+                          void *stream) {
     if (!p || !frame || !mi || !frame->y || !frame->cb || !frame->cr || p->mi_rows <= 0 || p->mi_cols <= 0 ||
         p->mi_stride < p->mi_cols) {
         set_error("svt_b200_dlf_frame: bad argument");
@@ -265,6 +274,7 @@ int svt_b200_dlf_frame(const SvtB200DlfParams *p, const SvtB200Frame *frame, con
     d.stride[1] = d.stride[2] = frame->stride_c;
     d.bd = frame->bit_depth;
     d.mi = mi;
+    d.lut = lut;
     cudaStream_t st = (cudaStream_t)stream;
     const bool hbd = frame->bit_depth > 8;
     // all vertical edges of every plane first, then all horizontal edges (see the header comment)
@@ -287,6 +297,208 @@ int svt_b200_dlf_frame(const SvtB200DlfParams *p, const SvtB200Frame *frame, con
             SVTB_LAUNCH(dlf_pass_kernel<uint8_t>, grid, 256, 0, st, d, planes, vert);
     }
     SVTB_CUDA_TRY(cudaGetLastError());
+    return SVT_B200_OK;
+}
+
+int svt_b200_dlf_frame(const SvtB200DlfParams *p, const SvtB200Frame *frame, const SvtB200DlfMi *mi, void *stream) {
+    return dlf_frame_impl(p, frame, mi, nullptr, stream);
+}
+
+// svt_av1_loop_filter_frame_init (EbDeblockingCommon.c:78-145): lvl[plane][seg][dir][ref][mode] as lut[plane][dir][class]
+int svt_b200_lf_level_lut(const SvtB200LfFrameInit *init, const int32_t levels[4], uint8_t lut[3][2][128]) {
+    if (!init || !levels || !lut) return SVT_B200_ERR_ARG;
+    static const int seg_lvl_lf_lut[3][2] = {{1, 2}, {3, 3}, {4, 4}}; // SEG_LVL_ALT_LF_Y_V, _Y_H, _U, _V
+    const int filt[3] = {levels[0], levels[2], levels[3]}, filt_r[3] = {levels[1], levels[2], levels[3]};
+    memset(lut, 0, 3 * 2 * 128);
+    for (int plane = 0; plane < 3; plane++) {
+        if (plane == 0 && !filt[0] && !filt_r[0]) break;
+        if (plane && !filt[plane]) continue;
+        for (int seg = 0; seg < 8; seg++)
+            for (int dir = 0; dir < 2; dir++) {
+                int lvl_seg = dir == 0 ? filt[plane] : filt_r[plane];
+                const int f = seg_lvl_lf_lut[plane][dir];
+                if (init->segmentation_enabled && ((init->seg_feature_mask[seg] >> f) & 1)) {
+                    lvl_seg += init->seg_feature_data[seg][f];
+                    lvl_seg = lvl_seg < 0 ? 0 : (lvl_seg > 63 ? 63 : lvl_seg);
+                }
+                for (int ref = 0; ref < 8; ref++)
+                    for (int mode = 0; mode < 2; mode++) {
+                        int v = lvl_seg;
+                        if (init->mode_ref_delta_enabled) {
+                            const int scale = 1 << (lvl_seg >> 5);
+                            // INTRA_FRAME has a single entry ([0]); entry [1] is never read (mode_lf_lut of intra modes is 0)
+                            v = ref == 0 ? lvl_seg + init->ref_deltas[0] * scale
+                                         : lvl_seg + init->ref_deltas[ref] * scale + init->mode_deltas[mode] * scale;
+                            v = v < 0 ? 0 : (v > 63 ? 63 : v);
+                        }
+                        lut[plane][dir][seg * 16 + ref * 2 + mode] = (uint8_t)v;
+                    }
+            }
+    }
+    return SVT_B200_OK;
+}
+
+namespace {
+struct PickCtx {
+    const SvtB200LpfPickParams *p;
+    const SvtB200Frame *recon, *source, *temp;
+    const SvtB200DlfMi *mi;
+    uint8_t *d_lut; // device 768 B
+    unsigned long long *d_sse; // device
+    cudaStream_t st;
+    int32_t cur[4]; // frame levels as the search progresses (frm_hdr->loop_filter_params)
+};
+int plane_copy(const SvtB200Frame *src, const SvtB200Frame *dst, int plane, cudaStream_t st) {
+    const int es = src->bit_depth > 8 ? 2 : 1;
+    const int w = plane ? src->width >> 1 : src->width, h = plane ? src->height >> 1 : src->height;
+    const void *s = plane == 0 ? src->y : plane == 1 ? src->cb : src->cr;
+    void *d = plane == 0 ? dst->y : plane == 1 ? dst->cb : dst->cr;
+    const size_t ss = (size_t)(plane ? src->stride_c : src->stride_y) * es, ds = (size_t)(plane ? dst->stride_c : dst->stride_y) * es;
+    return cudaMemcpy2DAsync(d, ds, s, ss, (size_t)w * es, h, cudaMemcpyDeviceToDevice, st) == cudaSuccess ? 0 : -1;
+}
+// try_filter_frame (:966-1026): filter one plane of recon at the trial level, SSE against the source, restore the plane
+int64_t try_filter(PickCtx &c, int level, int plane, int dir) {
+    int32_t lv[4] = {c.cur[0], c.cur[1], c.cur[2], c.cur[3]};
+    if (plane == 0) {
+        if (dir != 1) lv[0] = level; // dir 0: only [0]; dir 2: both
+        if (dir != 0) lv[1] = level;
+    } else {
+        lv[1 + plane] = level;
+    }
+    // the trial levels stay in the frame header (set base filters ... :1007-1014)
+    for (int i = 0; i < 4; i++) c.cur[i] = lv[i];
+    ThreadCtx &t = tls();
+    t.reserve(1024);
+    uint8_t(*lut)[2][128] = reinterpret_cast<uint8_t(*)[2][128]>(t.h);
+    svt_b200_lf_level_lut(&c.p->init, lv, lut);
+    SvtB200DlfParams dp = c.p->dlf;
+    dp.sharpness = 0;
+    dp.filter_level[0] = lv[0], dp.filter_level[1] = lv[1], dp.filter_level_u = lv[2], dp.filter_level_v = lv[3];
+    dp.plane_start = plane, dp.plane_end = plane + 1;
+    // the pinned staging buffer is reused by the next trial: the previous trial ended with a stream synchronise
+    if (cudaMemcpyAsync(c.d_lut, t.h, 768, cudaMemcpyHostToDevice, c.st) != cudaSuccess) return -1;
+    if (dlf_frame_impl(&dp, c.recon, c.mi, c.d_lut, c.st) != SVT_B200_OK) return -1;
+    if (cudaMemsetAsync(c.d_sse, 0, 8, c.st) != cudaSuccess) return -1;
+    const int w = plane ? c.recon->width >> 1 : c.recon->width, h = plane ? c.recon->height >> 1 : c.recon->height;
+    const void *a = plane == 0 ? c.source->y : plane == 1 ? c.source->cb : c.source->cr;
+    const void *b = plane == 0 ? c.recon->y : plane == 1 ? c.recon->cb : c.recon->cr;
+    const int sa = plane ? c.source->stride_c : c.source->stride_y, sb = plane ? c.recon->stride_c : c.recon->stride_y;
+    const int grid = h < 592 ? h : 592;
+    if (c.recon->bit_depth > 8)
+        SVTB_LAUNCH(sse_kernel<uint16_t>, grid, 256, 0, c.st, (const uint16_t *)a, sa, (const uint16_t *)b, sb, w, h, c.d_sse);
+    else
+        SVTB_LAUNCH(sse_kernel<uint8_t>, grid, 256, 0, c.st, (const uint8_t *)a, sa, (const uint8_t *)b, sb, w, h, c.d_sse);
+    if (plane_copy(c.temp, c.recon, plane, c.st)) return -1; // re-instate the unfiltered plane
+    unsigned long long *h_sse = reinterpret_cast<unsigned long long *>(t.h + 768);
+    if (cudaMemcpyAsync(h_sse, c.d_sse, 8, cudaMemcpyDeviceToHost, c.st) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(c.st) != cudaSuccess) return -1;
+    return (int64_t)*h_sse;
+}
+// search_filter_level (:1027-1191)
+int search_level(PickCtx &c, int plane, int dir, int *err) {
+    const int lvl = plane == 0 ? c.p->last_level[dir == 2 ? 2 : dir] : plane == 1 ? c.p->last_level[2] : c.p->last_level[3];
+    int filt_mid = lvl < 0 ? 0 : (lvl > 63 ? 63 : lvl);
+    int filter_step = filt_mid < 16 ? 4 : filt_mid / 4;
+    int filt_direction = 0;
+    int64_t ss_err[64];
+    for (int i = 0; i < 64; i++) ss_err[i] = -1;
+    if (plane_copy(c.recon, c.temp, plane, c.st)) { *err = 1; return 0; }
+    int64_t best_err = try_filter(c, filt_mid, plane, dir);
+    if (best_err < 0) { *err = 1; return 0; }
+    int filt_best = filt_mid;
+    ss_err[filt_mid] = best_err;
+    const bool one_step = c.p->loop_filter_mode <= 2;
+    if (one_step) filter_step = 2;
+    while (filter_step > 0) {
+        const int filt_high = filt_mid + filter_step > 63 ? 63 : filt_mid + filter_step;
+        const int filt_low = filt_mid - filter_step < 0 ? 0 : filt_mid - filter_step;
+        int64_t bias = (best_err >> (15 - (filt_mid / 8))) * filter_step; // bias against raising the level
+        if (!c.p->tx_mode_only_4x4) bias >>= 1;
+        if (filt_direction <= 0 && filt_low != filt_mid) {
+            if (ss_err[filt_low] < 0) {
+                ss_err[filt_low] = try_filter(c, filt_low, plane, dir);
+                if (ss_err[filt_low] < 0) { *err = 1; return 0; }
+            }
+            if (ss_err[filt_low] < best_err + bias) {
+                if (ss_err[filt_low] < best_err) best_err = ss_err[filt_low];
+                filt_best = filt_low;
+            }
+        }
+        if (filt_direction >= 0 && filt_high != filt_mid) {
+            if (ss_err[filt_high] < 0) {
+                ss_err[filt_high] = try_filter(c, filt_high, plane, dir);
+                if (ss_err[filt_high] < 0) { *err = 1; return 0; }
+            }
+            if (ss_err[filt_high] < best_err - bias) {
+                if (!one_step) best_err = ss_err[filt_high]; // the <= 2 branch (:1117-1118) does not update best_err
+                filt_best = filt_high;
+            }
+        }
+        if (one_step) break;
+        if (filt_best == filt_mid) {
+            filter_step /= 2;
+            filt_direction = 0;
+        } else {
+            filt_direction = filt_best < filt_mid ? -1 : 1;
+            filt_mid = filt_best;
+        }
+    }
+    return filt_best;
+}
+} // namespace
+
+int svt_b200_pick_filter_level(const SvtB200LpfPickParams *p, const SvtB200Frame *recon, const SvtB200Frame *source,
+                               const SvtB200Frame *temp, const SvtB200DlfMi *mi, void *scratch, int32_t *levels_out, void *stream) {
+    if (!p || !levels_out || p->method < 0 || p->method > 3) {
+        set_error("svt_b200_pick_filter_level: bad argument");
+        return SVT_B200_ERR_ARG;
+    }
+    if (p->method == 3) { // LPF_PICK_MINIMAL_LPF: only the luma levels are touched
+        levels_out[0] = levels_out[1] = 0;
+        levels_out[2] = p->last_level[2];
+        levels_out[3] = p->last_level[3];
+        return SVT_B200_OK;
+    }
+    if (p->method == 2) { // LPF_PICK_FROM_Q (:1209-1249)
+        const int bd = recon ? recon->bit_depth : 8, q = p->q_ac;
+        auto rpo2 = [](long long v, int n) { return (int)((v + (1ll << (n - 1))) >> n); };
+        int g = bd == 8 ? (p->key_frame ? rpo2((long long)q * 17563 - 421574, 18) : rpo2((long long)q * 6017 + 650707, 18))
+                        : bd == 10 ? rpo2((long long)q * 20723 + 4060632, 20) : rpo2((long long)q * 20723 + 16242526, 22);
+        if (bd != 8 && p->key_frame) g -= 4;
+        g = g > 2 ? g - 2 : g > 1 ? g - 1 : g;
+        const int gc = g > 1 ? g / 2 : g;
+        auto cl = [](int v) { return v < 0 ? 0 : (v > 63 ? 63 : v); };
+        levels_out[0] = levels_out[1] = cl(g);
+        levels_out[2] = levels_out[3] = cl(gc);
+        return SVT_B200_OK;
+    }
+    if (!recon || !source || !temp || !mi || !scratch || recon->bit_depth != source->bit_depth || recon->bit_depth != temp->bit_depth ||
+        recon->width != source->width || recon->height != source->height) {
+        set_error("svt_b200_pick_filter_level: bad argument");
+        return SVT_B200_ERR_ARG;
+    }
+    PickCtx c;
+    c.p = p, c.recon = recon, c.source = source, c.temp = temp, c.mi = mi;
+    c.d_lut = (uint8_t *)scratch;
+    c.d_sse = (unsigned long long *)((uint8_t *)scratch + 768);
+    c.st = (cudaStream_t)stream;
+    for (int i = 0; i < 4; i++) c.cur[i] = p->last_level[i];
+    int err = 0;
+    const int y = search_level(c, 0, 2, &err);
+    if (!err) {
+        c.cur[0] = c.cur[1] = y;
+        const int u = search_level(c, 1, 0, &err);
+        if (!err) {
+            c.cur[2] = u;
+            const int v = search_level(c, 2, 0, &err);
+            if (!err) c.cur[3] = v;
+        }
+    }
+    if (err) {
+        set_error("svt_b200_pick_filter_level: CUDA failure");
+        return SVT_B200_ERR_CUDA;
+    }
+    for (int i = 0; i < 4; i++) levels_out[i] = c.cur[i];
     return SVT_B200_OK;
 }
 

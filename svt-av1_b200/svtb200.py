@@ -100,13 +100,24 @@ TX_H = [4, 8, 16, 32, 64, 8, 4, 16, 8, 32, 16, 64, 32, 16, 4, 32, 8, 64, 16]
 class DlfMi(C.Structure):
     _fields_ = [("tx_w", C.c_uint8 * 2), ("tx_h", C.c_uint8 * 2), ("blk_w", C.c_uint8 * 2), ("blk_h", C.c_uint8 * 2),
                 ("skip_inter", C.c_uint8), ("lvl_y", C.c_uint8 * 2), ("lvl_u", C.c_uint8), ("lvl_v", C.c_uint8),
-                ("pad", C.c_uint8 * 3)]
+                ("lvl_class", C.c_uint8), ("pad", C.c_uint8 * 2)]
 
 
 class DlfParams(C.Structure):
     _fields_ = [("mi_rows", C.c_int32), ("mi_cols", C.c_int32), ("mi_stride", C.c_int32), ("sharpness", C.c_int32),
                 ("filter_level", C.c_int32 * 2), ("filter_level_u", C.c_int32), ("filter_level_v", C.c_int32),
                 ("plane_start", C.c_int32), ("plane_end", C.c_int32)]
+
+
+class LfFrameInit(C.Structure):
+    _fields_ = [("mode_ref_delta_enabled", C.c_int32), ("ref_deltas", C.c_int8 * 8), ("mode_deltas", C.c_int8 * 2),
+                ("segmentation_enabled", C.c_int32), ("seg_feature_mask", C.c_uint8 * 8),
+                ("seg_feature_data", (C.c_int16 * 8) * 8)]
+
+
+class LpfPickParams(C.Structure):
+    _fields_ = [("dlf", DlfParams), ("init", LfFrameInit), ("method", C.c_int32), ("loop_filter_mode", C.c_int32),
+                ("tx_mode_only_4x4", C.c_int32), ("q_ac", C.c_int32), ("key_frame", C.c_int32), ("last_level", C.c_int32 * 4)]
 
 
 def preset8_me_params(width, height, n_l0=1, n_l1=1, dist=((1, 2, 3, 4), (1, 2, 3, 4)), temporal_layer=1,

@@ -114,6 +114,19 @@ def run_gpu_dlf(p, frame, flat):
     return df.download()
 
 
+def run_gpu_pick(p, rec, src, flat):
+    lib = sb.load()
+    dr, ds, dt = DevYuv(rec.copy()), DevYuv(src), DevYuv(rec.copy())
+    dmi = torch.from_numpy(np.frombuffer(flat, dtype=np.uint8).copy()).cuda()
+    scratch = torch.zeros(1024, dtype=torch.uint8, device="cuda")
+    rs, ss, ts = dr.struct(), ds.struct(), dt.struct()
+    out = (C.c_int32 * 4)()
+    sb.check(lib.svt_b200_pick_filter_level(C.byref(p), C.byref(rs), C.byref(ss), C.byref(ts), C.c_void_p(dmi.data_ptr()),
+                                            C.c_void_p(scratch.data_ptr()), out, None), lib)
+    torch.cuda.synchronize()
+    return list(out), dr.download()
+
+
 def run_gpu_sse(a, b):
     lib = sb.load()
     da, db = DevYuv(a), DevYuv(b)

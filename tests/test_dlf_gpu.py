@@ -59,6 +59,7 @@ def flat_mi(mi_rows, mi_cols, part, levels):
             f.blk_w[0], f.blk_h[0], f.blk_w[1], f.blk_h[1] = BW[bs], BH[bs], cw, ch
             f.skip_inter = sk and it
             f.lvl_y[0], f.lvl_y[1], f.lvl_u, f.lvl_v = levels
+            f.lvl_class = (1 * 2 + 1) if it else 0   # segment 0, LAST_FRAME / NEARESTMV-class or INTRA_FRAME
     return flat
 
 
@@ -97,3 +98,42 @@ def test_frame_sse():
         sa, sbb = a.struct(), b.struct()
         cm.oracle().orc_frame_sse(C.byref(sa), C.byref(sbb), cm.ptr(want))
         np.testing.assert_array_equal(gr.run_gpu_sse(a, b), want)
+
+
+@pytest.mark.parametrize("case", [(192, 136, 8, 1, 0, 3, (20, 24, 12, 9), 0, None), (192, 136, 8, 2, 0, 1, (8, 8, 4, 4), 0, None),
+                                  (128, 128, 10, 3, 1, 3, (40, 40, 33, 20), 1, None), (264, 72, 8, 4, 0, 2, (0, 0, 0, 0), 0, None),
+                                  (192, 136, 8, 5, 0, 3, (30, 30, 16, 16), 0, ((1, 0, 0, 0, -1, 0, -1, -1), (0, 0))),
+                                  (1920, 1080, 8, 6, 0, 3, (24, 20, 14, 10), 0, None)])
+def test_pick_filter_level_vs_oracle(case):
+    """svt_av1_pick_filter_level: the searched levels equal the oracle's (itself pinned against the reference) and the
+    reconstruction is left untouched, at small sizes and at the full 1080p geometry."""
+    import gpu_runner as gr
+    from test_oracle_dlf import pick_case, pick_params
+    w, h, bd, seed, method, mode, last, only4, deltas = case
+    mi_rows, mi_cols, part, src, rec = pick_case(w, h, bd, seed)
+    flat = flat_mi(mi_rows, mi_cols, part, last)
+    p = pick_params(mi_rows, mi_cols, method, mode, last, only4, deltas=deltas)
+    r, t = rec.copy(), rec.copy()
+    rs, ss, ts = r.struct(), src.struct(), t.struct()
+    want = (C.c_int32 * 4)()
+    cm.oracle().orc_pick_filter_level(C.byref(p), C.byref(rs), C.byref(ss), C.byref(ts), flat, want)
+    got, after = gr.run_gpu_pick(p, rec, src, flat)
+    assert got == list(want)
+    for i in range(3):
+        np.testing.assert_array_equal(after.plane(i), rec.plane(i))
+
+
+@pytest.mark.parametrize("bd,key", [(8, 0), (8, 1), (10, 0), (10, 1), (12, 0), (12, 1)])
+def test_pick_filter_level_from_q_and_minimal(bd, key):
+    lib = sb.load()
+    fr = sb.Frame(0, 0, 0, 0, 0, 64, 64, bd)
+    for q in (4, 33, 120, 700, 1336, 5000, 21387):
+        for method in (2, 3):
+            p = sb.LpfPickParams()
+            p.method, p.q_ac, p.key_frame = method, q, key
+            for i in range(4):
+                p.last_level[i] = 7 + i
+            a, b = (C.c_int32 * 4)(), (C.c_int32 * 4)()
+            sb.check(lib.svt_b200_pick_filter_level(C.byref(p), C.byref(fr), None, None, None, None, a, None), lib)
+            cm.oracle().orc_pick_filter_level(C.byref(p), C.byref(fr), None, None, None, b)
+            assert list(a) == list(b)

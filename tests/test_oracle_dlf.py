@@ -103,3 +103,119 @@ def test_dlf_frame_matches_reference(case):
         np.testing.assert_array_equal(got.plane(i), want.plane(i), err_msg=f"plane {i}")
     if levels[0] >= 20:  # (weak levels on noisy content may legitimately change nothing)
         assert any((want.plane(i) != frame.plane(i)).any() for i in range(3))
+
+
+# ---- svt_av1_pick_filter_level -------------------------------------------------------------------------------------
+def pick_case(w, h, bd, seed):
+    """A source picture, its 'reconstruction' with blocking artefacts along the partition, and the partition."""
+    mi_rows, mi_cols = h // 4, w // 4
+    part = cm.random_partition(mi_rows, mi_cols, seed)
+    src = cm.synth_yuv(w, h, 1, seed, bd)
+    rec = cm.degrade(src, seed + 7, amp=14)
+    return mi_rows, mi_cols, part, src, rec
+
+
+def pick_params(mi_rows, mi_cols, method, mode, last, only4=0, q_ac=120, key=0, deltas=None):
+    p = sb.LpfPickParams()
+    p.dlf.mi_rows, p.dlf.mi_cols, p.dlf.mi_stride = mi_rows, mi_cols, mi_cols
+    p.dlf.plane_start, p.dlf.plane_end = 0, 3
+    p.method, p.loop_filter_mode, p.tx_mode_only_4x4, p.q_ac, p.key_frame = method, mode, only4, q_ac, key
+    for i in range(4):
+        p.last_level[i] = last[i]
+    if deltas:
+        p.init.mode_ref_delta_enabled = 1
+        for i in range(8):
+            p.init.ref_deltas[i] = deltas[0][i]
+        for i in range(2):
+            p.init.mode_deltas[i] = deltas[1][i]
+    return p
+
+
+def run_ref_pick(mi_rows, mi_cols, part, src, rec, method, mode, last, only4=0, base_q_idx=120, key=0, deltas=None):
+    sbt, dep, inter, skip = (np.ascontiguousarray(x) for x in part)
+    r, t = rec.copy(), rec.copy()
+    rs, ss, ts = r.struct(), src.struct(), t.struct()
+    lv = (C.c_int32 * 4)(*last)
+    out = (C.c_int32 * 4)()
+    rd = (C.c_int8 * 8)(*deltas[0]) if deltas else None
+    md = (C.c_int8 * 2)(*deltas[1]) if deltas else None
+    cm.refh().refh_pick_filter_level(mi_rows, mi_cols, cm.ptr(sbt), cm.ptr(dep), cm.ptr(inter), cm.ptr(skip), lv, method, mode,
+                                     only4, base_q_idx, key, rd, md, C.byref(rs), C.byref(ss), C.byref(ts), out)
+    return list(out), r
+
+
+PICK_CASES = [(192, 136, 8, 1, 0, 3, (20, 24, 12, 9), 0, None), (192, 136, 8, 2, 0, 1, (8, 8, 4, 4), 0, None),
+              (128, 128, 10, 3, 0, 3, (40, 40, 33, 20), 1, None), (264, 72, 8, 4, 1, 2, (0, 0, 0, 0), 0, None),
+              (192, 136, 8, 5, 0, 3, (30, 30, 16, 16), 0, ((1, 0, 0, 0, -1, 0, -1, -1), (0, 0))),
+              (136, 200, 10, 6, 0, 2, (63, 63, 63, 63), 0, ((2, -1, 0, 1, -1, 0, -2, -1), (1, -1)))]
+
+
+@needs_ref
+@pytest.mark.parametrize("case", PICK_CASES)
+def test_pick_filter_level_matches_reference(case):
+    w, h, bd, seed, method, mode, last, only4, deltas = case
+    mi_rows, mi_cols, part, src, rec = pick_case(w, h, bd, seed)
+    want, ref_rec = run_ref_pick(mi_rows, mi_cols, part, src, rec, method, mode, last, only4, deltas=deltas)
+    for i in range(3):  # the reference restores the unfiltered picture after every trial
+        np.testing.assert_array_equal(ref_rec.plane(i), rec.plane(i))
+    from test_dlf_gpu import flat_mi
+    flat = flat_mi(mi_rows, mi_cols, part, last)
+    p = pick_params(mi_rows, mi_cols, method, mode, last, only4, deltas=deltas)
+    r, t = rec.copy(), rec.copy()
+    rs, ss, ts = r.struct(), src.struct(), t.struct()
+    got = (C.c_int32 * 4)()
+    cm.oracle().orc_pick_filter_level(C.byref(p), C.byref(rs), C.byref(ss), C.byref(ts), flat, got)
+    assert list(got) == want
+    for i in range(3):
+        np.testing.assert_array_equal(r.plane(i), rec.plane(i))
+
+
+@needs_ref
+@pytest.mark.parametrize("bd,key,q", [(8, 0, 60), (8, 1, 900), (8, 1, 8), (10, 0, 500), (10, 1, 3000), (12, 0, 9000)])
+def test_pick_filter_level_from_q(bd, key, q):
+    """LPF_PICK_FROM_Q: the formula on the reference's own svt_av1_ac_quant_q3 value."""
+    import ctypes
+    ref = cm.refh()
+    ref.svt_av1_ac_quant_q3.restype = ctypes.c_int16
+    for base_q in (1, 40, 120, 200, 255):
+        qv = ref.svt_av1_ac_quant_q3(base_q, 0, bd)
+        if bd == 12:
+            continue  # the harness pictures are 8/10-bit; the 12-bit branch is covered by the oracle-vs-GPU test
+        mi_rows, mi_cols, part, src, rec = pick_case(64, 64, bd, 1)
+        want, _ = run_ref_pick(mi_rows, mi_cols, part, src, rec, 2, 1, (5, 5, 5, 5), 0, base_q, key)
+        p = pick_params(mi_rows, mi_cols, 2, 1, (5, 5, 5, 5), q_ac=qv, key=key)
+        rs, ss = rec.struct(), src.struct()
+        got = (C.c_int32 * 4)()
+        cm.oracle().orc_pick_filter_level(C.byref(p), C.byref(rs), C.byref(ss), C.byref(rs), None, got)
+        assert list(got) == want, (bd, key, base_q)
+
+
+def test_level_lut_matches_loop_filter_frame_init():
+    """svt_b200_lf_level_lut (host function of the product library) vs orc_lf_level_lut on random delta / segment sets,
+    plus the plain-picture property of svt_av1_loop_filter_frame_init (the table is the frame level everywhere)."""
+    lib = sb.load()
+    rng = np.random.default_rng(3)
+    for _ in range(40):
+        init = sb.LfFrameInit()
+        init.mode_ref_delta_enabled = int(rng.integers(0, 2))
+        for i in range(8):
+            init.ref_deltas[i] = int(rng.integers(-8, 9))
+        for i in range(2):
+            init.mode_deltas[i] = int(rng.integers(-8, 9))
+        init.segmentation_enabled = int(rng.integers(0, 2))
+        for sg in range(8):
+            init.seg_feature_mask[sg] = int(rng.integers(0, 32))
+            for f in range(8):
+                init.seg_feature_data[sg][f] = int(rng.integers(-63, 64))
+        lv = (C.c_int32 * 4)(*[int(x) for x in rng.integers(0, 64, 4)])
+        lut, lut2 = ((C.c_uint8 * 128) * 2 * 3)(), ((C.c_uint8 * 128) * 2 * 3)()
+        cm.oracle().orc_lf_level_lut(C.byref(init), lv, lut)
+        assert lib.svt_b200_lf_level_lut(C.byref(init), lv, lut2) == 0
+        a, b = np.ctypeslib.as_array(lut).reshape(3, 2, 128), np.ctypeslib.as_array(lut2).reshape(3, 2, 128)
+        # class entries with ref = INTRA_FRAME and mode 1 do not exist in the reference's table: ignore them
+        keep = np.array([not ((c >> 1) & 7 == 0 and (c & 1)) for c in range(128)])
+        np.testing.assert_array_equal(a[:, :, keep], b[:, :, keep])
+        if not init.mode_ref_delta_enabled and not init.segmentation_enabled and lv[0] + lv[1]:
+            assert (a[0, 0] == lv[0]).all() and (a[0, 1] == lv[1]).all()
+            assert (a[1] == lv[2]).all() and (a[2] == lv[3]).all()
+        assert a.max() <= 63
