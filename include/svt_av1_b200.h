@@ -483,7 +483,7 @@ SVT_B200_API int svt_b200_pick_filter_level(const SvtB200LpfPickParams *p, const
 SVT_B200_API int svt_b200_frame_sse(const SvtB200Frame *a, const SvtB200Frame *b, uint64_t *sse, void *stream);
 
 /* =============================================================================================== */
-/* Loop restoration kernels (RTCD drop-ins; the frame-level stripe loop is not built yet)          */
+/* Loop restoration: RTCD drop-ins of the filters + the frame-level filter                         */
 /* =============================================================================================== */
 
 /* replace svt_av1_selfguided_restoration / svt_apply_selfguided_restoration (common_dsp_rtcd.h:187-191;
@@ -555,6 +555,32 @@ SVT_B200_DECL_SAD(32, 16) SVT_B200_DECL_SAD(32, 8) SVT_B200_DECL_SAD(16, 64) SVT
 SVT_B200_DECL_SAD(16, 16) SVT_B200_DECL_SAD(16, 8) SVT_B200_DECL_SAD(16, 4) SVT_B200_DECL_SAD(8, 32)
 SVT_B200_DECL_SAD(8, 16) SVT_B200_DECL_SAD(8, 8) SVT_B200_DECL_SAD(8, 4) SVT_B200_DECL_SAD(4, 16)
 SVT_B200_DECL_SAD(4, 8) SVT_B200_DECL_SAD(4, 4)
+
+/* RestorationUnitInfo (Common/Codec/EbRestoration.h): what svt_av1_loop_restoration_filter_unit reads per unit. */
+typedef struct SvtB200LrUnit {
+    int32_t restoration_type; /* RESTORE_NONE 0, RESTORE_WIENER 1, RESTORE_SGRPROJ 2 */
+    int16_t vfilter[8], hfilter[8]; /* wiener_info.vfilter / hfilter (InterpKernel; tap [7] is 0) */
+    int32_t sgr_ep, sgr_xqd[2]; /* sgrproj_info.ep, .xqd */
+} SvtB200LrUnit;
+typedef struct SvtB200LrPlane {
+    int32_t frame_restoration_type; /* rsi->frame_restoration_type: 0 = plane passes through unchanged */
+    int32_t restoration_unit_size; /* rsi->restoration_unit_size (multiple of 64; chroma: of 32) */
+    const SvtB200LrUnit *units; /* DEVICE array [vert_units][horz_units], unit counts as count_units_in_tile
+                                   (EbRestoration.c:175) derives them from the plane size */
+} SvtB200LrPlane;
+typedef struct SvtB200LrFrameParams {
+    SvtB200LrPlane plane[3];
+    int32_t optimized_lr; /* rsi->optimized_lr: stripe context of 1 replicated CDEF row instead of deblocked rows */
+} SvtB200LrFrameParams;
+
+/* svt_av1_loop_restoration_filter_frame (Common/Codec/EbRestoration.c:1293-1364) with the stripe protocol of
+ * svt_av1_loop_restoration_filter_unit (:1162-1261), setup/restore_processing_stripe_boundary (:353-507) and the
+ * boundary lines of svt_av1_loop_restoration_save_boundary_lines (:1645-1868), single tile, no super-resolution.
+ * cdef: the picture after CDEF (filter input); deblocked: the picture after deblocking, before CDEF (its rows are
+ * the 2-row stripe context the reference saves with after_cdef = 0); out: the restored picture (must not alias).
+ * One launch; every 64x64 (chroma 32x32) processing unit of every stripe is one CTA. */
+SVT_B200_API int svt_b200_lr_frame(const SvtB200LrFrameParams *p, const SvtB200Frame *cdef, const SvtB200Frame *deblocked,
+                                   const SvtB200Frame *out, void *stream);
 
 #ifdef __cplusplus
 }
