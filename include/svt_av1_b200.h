@@ -396,6 +396,12 @@ SVT_B200_API int svt_b200_encode_tus(const SvtB200EncodeParams *p, const SvtB200
                                      const SvtB200Frame *pred, const SvtB200Frame *recon,
                                      const SvtB200Tu *tus, int32_t n_tus, int32_t *qcoeff, uint16_t *eob,
                                      void *scratch, void *stream);
+/* Same, plus cul_level[n_tus] (device int32, may be NULL): the value av1_quantize_inv_quantize returns
+ * (EbFullLoop.c:1596-1608): min(63, sum |qcoeff|) with set_dc_sign of the DC level (bit 6 negative, +128 positive). */
+SVT_B200_API int svt_b200_encode_tus_cul(const SvtB200EncodeParams *p, const SvtB200Frame *src,
+                                         const SvtB200Frame *pred, const SvtB200Frame *recon,
+                                         const SvtB200Tu *tus, int32_t n_tus, int32_t *qcoeff, uint16_t *eob,
+                                         int32_t *cul_level, void *stream);
 
 /* =============================================================================================== */
 /* Deblocking loop filter                                                                          */

@@ -167,3 +167,189 @@ void orc_wiener_convolve_add_src(const void *src, int hbd, ptrdiff_t src_stride,
         }
     free(tmp);
 }
+
+/* ====================================================================================================================
+ * svt_av1_loop_restoration_filter_frame (Common/Codec/EbRestoration.c:1293-1364), restated the way the reference does
+ * it: a working copy of the CDEF picture extended by 3 samples (svt_extend_frame :216-260), boundary lines saved from
+ * the deblocked and CDEF pictures (svt_av1_loop_restoration_save_boundary_lines :1645-1868), and per restoration unit
+ * / stripe the overwrite - filter - restore protocol (svt_av1_loop_restoration_filter_unit :1162-1261,
+ * setup/restore_processing_stripe_boundary :353-507).  Single tile, no super-resolution.  Samples are handled as
+ * uint16 internally (the arithmetic is the same for both depths).
+ * ================================================================================================================== */
+#define LR_EXT 8 /* working-plane border (>= RESTORATION_BORDER 3 + the 8th Wiener tap) */
+typedef struct {
+    uint16_t *buf; /* (h + 2 EXT) x stride, origin at (EXT, EXT) */
+    int w, h, stride;
+} WorkPlane;
+static uint16_t *wp_at(const WorkPlane *p, int x, int y) { return p->buf + (size_t)(y + LR_EXT) * p->stride + x + LR_EXT; }
+static int plane_px(const void *base, int hbd, int stride, int x, int y) {
+    return hbd ? ((const uint16_t *)base)[(size_t)y * stride + x] : ((const uint8_t *)base)[(size_t)y * stride + x];
+}
+
+void orc_lr_frame(const SvtB200LrFrameParams *p, const SvtB200Frame *cdef, const SvtB200Frame *dblk, const SvtB200Frame *out,
+                  const SvtB200LrUnit *const units[3] /* host arrays */) {
+    const int hbd = cdef->bit_depth > 8, bd = cdef->bit_depth;
+    for (int plane = 0; plane < 3; plane++) {
+        const int ss = plane ? 1 : 0;
+        const int pw = (cdef->width + ss) >> ss, ph = (cdef->height + ss) >> ss;
+        const void *cb = plane == 0 ? cdef->y : plane == 1 ? cdef->cb : cdef->cr;
+        const void *db = plane == 0 ? dblk->y : plane == 1 ? dblk->cb : dblk->cr;
+        void *ob = plane == 0 ? out->y : plane == 1 ? out->cb : out->cr;
+        const int cs = plane ? cdef->stride_c : cdef->stride_y, dstr = plane ? dblk->stride_c : dblk->stride_y,
+                  os = plane ? out->stride_c : out->stride_y;
+        const SvtB200LrPlane *rp = &p->plane[plane];
+        if (!rp->frame_restoration_type) { /* plane untouched */
+            for (int y = 0; y < ph; y++)
+                for (int x = 0; x < pw; x++) {
+                    const int v = plane_px(cb, hbd, cs, x, y);
+                    if (hbd) ((uint16_t *)ob)[(size_t)y * os + x] = (uint16_t)v;
+                    else ((uint8_t *)ob)[(size_t)y * os + x] = (uint8_t)v;
+                }
+            continue;
+        }
+        /* working copy, extended by replication (only RESTORATION_BORDER = 3 is ever read through a filter tap with
+         * a non-zero weight; the wider border keeps the 8th Wiener tap inside the buffer) */
+        WorkPlane wk = {NULL, pw, ph, pw + 2 * LR_EXT};
+        wk.buf = (uint16_t *)calloc((size_t)(ph + 2 * LR_EXT) * wk.stride, 2);
+        for (int y = -3; y < ph + 3; y++)
+            for (int x = -3; x < pw + 3; x++) {
+                const int yy = y < 0 ? 0 : y >= ph ? ph - 1 : y, xx = x < 0 ? 0 : x >= pw ? pw - 1 : x;
+                *wp_at(&wk, x, y) = (uint16_t)plane_px(cb, hbd, cs, xx, yy);
+            }
+        /* boundary lines: per stripe 2 rows above and 2 rows below, each extended by 4 columns */
+        const int SH = 64 >> ss, off = 8 >> ss;
+        const int n_stripes = (ph + off + SH - 1) / SH, bstride = pw + 8;
+        uint16_t *above = (uint16_t *)calloc((size_t)n_stripes * 2 * bstride, 2), *below = (uint16_t *)calloc((size_t)n_stripes * 2 * bstride, 2);
+        for (int s = 0; s < n_stripes; s++) {
+            const int y0 = s * SH - off > 0 ? s * SH - off : 0, y1 = (s + 1) * SH - off < ph ? (s + 1) * SH - off : ph;
+            for (int ab = 0; ab < 2; ab++) { /* 0: above, 1: below */
+                uint16_t *dst = (ab ? below : above) + (size_t)s * 2 * bstride + 4;
+                const int use_deblock = ab ? (y1 < ph) : (s > 0);
+                for (int i = 0; i < 2; i++) {
+                    int row;
+                    const void *srcp;
+                    int sstr;
+                    if (use_deblock) { /* save_deblock_boundary_lines: rows y0-2.. / y1.., the last one repeated if short */
+                        const int r0 = ab ? y1 : y0 - 2, lines = ph - r0 < 2 ? ph - r0 : 2;
+                        row = r0 + (i < lines ? i : 0);
+                        srcp = db, sstr = dstr;
+                    } else { /* save_cdef_boundary_lines: the outermost CDEF row of the picture, twice */
+                        row = ab ? y1 - 1 : y0;
+                        srcp = cb, sstr = cs;
+                    }
+                    for (int x = -4; x < pw + 4; x++)
+                        dst[(size_t)i * bstride + x] = (uint16_t)plane_px(srcp, hbd, sstr, x < 0 ? 0 : x >= pw ? pw - 1 : x, row);
+                }
+            }
+        }
+        /* units (foreach_rest_unit_in_tile :1366-1411) */
+        const int U = rp->restoration_unit_size, ext = U * 3 / 2;
+        const int hunits = (pw + (U >> 1)) / U > 1 ? (pw + (U >> 1)) / U : 1;
+        uint16_t *res = (uint16_t *)calloc((size_t)ph * pw, 2); /* dst frame */
+        int round_0 = 3, round_1 = 11; /* get_conv_params_wiener :104-128 */
+        if (bd + 7 - round_0 + 2 > 16) {
+            const int e = bd + 7 - round_0 + 2 - 16;
+            round_0 += e, round_1 -= e;
+        }
+        for (int y0u = 0, ui = 0; y0u < ph; ui++) {
+            const int rem_h = ph - y0u, uh = rem_h < ext ? rem_h : U;
+            int v_start = y0u - off > 0 ? y0u - off : 0, v_end = y0u + uh;
+            if (v_end < ph) v_end -= off;
+            for (int x0u = 0, uj = 0; x0u < pw; uj++) {
+                const int rem_w = pw - x0u, uw = rem_w < ext ? rem_w : U;
+                const SvtB200LrUnit *u = &units[plane][ui * hunits + uj];
+                if (u->restoration_type == 0) {
+                    for (int y = v_start; y < v_end; y++)
+                        for (int x = x0u; x < x0u + uw; x++) res[(size_t)y * pw + x] = *wp_at(&wk, x, y);
+                } else {
+                    for (int i = 0; i < v_end - v_start;) {
+                        const int vs = v_start + i;
+                        const int first = vs == 0, this_h = SH - (first ? off : 0), last = vs + this_h >= ph;
+                        const int copy_above = !first, copy_below = !last;
+                        const int stripe = (vs + off) / SH;
+                        const int nominal = SH - (stripe == 0 ? off : 0), h = nominal < v_end - vs ? nominal : v_end - vs;
+                        /* setup_processing_stripe_boundary: save + overwrite columns x0u-4 .. x0u+uw+4 */
+                        uint16_t save[2][3][64 * 6 + 8 + 400];
+                        const int lw = uw + 8;
+                        if (lw > (int)(sizeof(save[0][0]) / 2)) abort();
+                        if (!p->optimized_lr) {
+                            if (copy_above)
+                                for (int r = -3; r < 0; r++) {
+                                    const int br = r + 2 > 0 ? r + 2 : 0;
+                                    for (int x = 0; x < lw; x++) {
+                                        uint16_t *d = wp_at(&wk, x0u - 4 + x, vs + r);
+                                        save[0][r + 3][x] = *d;
+                                        *d = above[((size_t)stripe * 2 + br) * bstride + 4 + x0u - 4 + x];
+                                    }
+                                }
+                            if (copy_below)
+                                for (int r = 0; r < 3; r++) {
+                                    const int br = r < 1 ? r : 1;
+                                    for (int x = 0; x < lw; x++) {
+                                        uint16_t *d = wp_at(&wk, x0u - 4 + x, vs + h + r);
+                                        save[1][r][x] = *d;
+                                        *d = below[((size_t)stripe * 2 + br) * bstride + 4 + x0u - 4 + x];
+                                    }
+                                }
+                        } else {
+                            if (copy_above)
+                                for (int x = 0; x < lw; x++) {
+                                    uint16_t *d = wp_at(&wk, x0u - 4 + x, vs - 3);
+                                    save[0][0][x] = *d;
+                                    *d = *wp_at(&wk, x0u - 4 + x, vs - 2);
+                                }
+                            if (copy_below)
+                                for (int x = 0; x < lw; x++) {
+                                    uint16_t *d = wp_at(&wk, x0u - 4 + x, vs + h + 2);
+                                    save[1][2][x] = *d;
+                                    *d = *wp_at(&wk, x0u - 4 + x, vs + h + 1);
+                                }
+                        }
+                        /* stripe filter, processing units of 64 >> ss_x columns */
+                        const int PW = 64 >> ss;
+                        for (int j = 0; j < uw; j += PW) {
+                            const int w = PW < uw - j ? PW : uw - j;
+                            uint16_t tmp[64 * 64];
+                            if (u->restoration_type == 1)
+                                orc_wiener_convolve_add_src(wp_at(&wk, x0u + j, vs), 1, wk.stride, tmp, 64, u->hfilter, u->vfilter, w, h,
+                                                            round_0, round_1, bd);
+                            else
+                                orc_apply_selfguided_restoration(wp_at(&wk, x0u + j, vs), 1, w, h, wk.stride, u->sgr_ep, u->sgr_xqd, tmp,
+                                                                 64, bd);
+                            for (int y = 0; y < h; y++)
+                                for (int x = 0; x < w; x++) res[(size_t)(vs + y) * pw + x0u + j + x] = tmp[y * 64 + x];
+                        }
+                        /* restore_processing_stripe_boundary */
+                        if (!p->optimized_lr) {
+                            if (copy_above)
+                                for (int r = -3; r < 0; r++)
+                                    for (int x = 0; x < lw; x++) *wp_at(&wk, x0u - 4 + x, vs + r) = save[0][r + 3][x];
+                            if (copy_below)
+                                for (int r = 0; r < 3; r++) {
+                                    if (vs + h + r >= v_end + 3) break;
+                                    for (int x = 0; x < lw; x++) *wp_at(&wk, x0u - 4 + x, vs + h + r) = save[1][r][x];
+                                }
+                        } else {
+                            if (copy_above)
+                                for (int x = 0; x < lw; x++) *wp_at(&wk, x0u - 4 + x, vs - 3) = save[0][0][x];
+                            if (copy_below && vs + h + 2 < v_end + 3)
+                                for (int x = 0; x < lw; x++) *wp_at(&wk, x0u - 4 + x, vs + h + 2) = save[1][2][x];
+                        }
+                        i += h;
+                    }
+                }
+                x0u += uw;
+            }
+            y0u += uh;
+        }
+        for (int y = 0; y < ph; y++)
+            for (int x = 0; x < pw; x++) {
+                if (hbd) ((uint16_t *)ob)[(size_t)y * os + x] = res[(size_t)y * pw + x];
+                else ((uint8_t *)ob)[(size_t)y * os + x] = (uint8_t)res[(size_t)y * pw + x];
+            }
+        free(res);
+        free(above);
+        free(below);
+        free(wk.buf);
+    }
+}

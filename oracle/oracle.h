@@ -89,6 +89,8 @@ ORC_API void orc_apply_selfguided_restoration(const void *dat, int hbd, int widt
 ORC_API void orc_wiener_convolve_add_src(const void *src, int hbd, ptrdiff_t src_stride, void *dst, ptrdiff_t dst_stride,
                                          const int16_t *filter_x, const int16_t *filter_y, int w, int h, int round_0,
                                          int round_1, int bd);
+ORC_API void orc_lr_frame(const SvtB200LrFrameParams *p, const SvtB200Frame *cdef, const SvtB200Frame *dblk, const SvtB200Frame *out,
+                          const SvtB200LrUnit *const units[3]);
 #ifdef __cplusplus
 }
 #endif

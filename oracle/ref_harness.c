@@ -532,6 +532,98 @@ REFH_API int refh_pick_filter_level(int mi_rows, int mi_cols, const uint8_t *sb_
 }
 
 /* ====================================================================================================
+ * Loop restoration, frame level: svt_av1_loop_restoration_save_boundary_lines (after deblocking and after CDEF) +
+ * svt_av1_loop_restoration_filter_frame, on Yv12BufferConfig views of our frames (which must carry a border of at
+ * least 8 samples: the reference extends / overwrites it in place).  `cdef` is filtered in place.
+ * ================================================================================================== */
+#include "EbRestoration.h"
+static void yv12_view(Yv12BufferConfig *y, const SvtB200Frame *f, int hbd) {
+    memset(y, 0, sizeof(*y));
+    const int w = f->width, h = f->height;
+    y->y_width = (w + 7) & ~7;
+    y->y_height = (h + 7) & ~7;
+    y->uv_width = y->y_width >> 1;
+    y->uv_height = y->y_height >> 1;
+    y->y_crop_width = w;
+    y->y_crop_height = h;
+    y->uv_crop_width = (w + 1) >> 1;
+    y->uv_crop_height = (h + 1) >> 1;
+    y->y_stride = f->stride_y;
+    y->uv_stride = f->stride_c;
+    y->y_buffer = hbd ? CONVERT_TO_BYTEPTR(f->y) : (uint8_t *)f->y;
+    y->u_buffer = hbd ? CONVERT_TO_BYTEPTR(f->cb) : (uint8_t *)f->cb;
+    y->v_buffer = hbd ? CONVERT_TO_BYTEPTR(f->cr) : (uint8_t *)f->cr;
+    y->subsampling_x = y->subsampling_y = 1;
+    y->bit_depth = (uint32_t)f->bit_depth;
+    y->flags = hbd ? YV12_FLAG_HIGHBITDEPTH : 0;
+    y->border = 8;
+}
+REFH_API int refh_lr_frame(SvtB200Frame *cdef, const SvtB200Frame *dblk, const int32_t *frame_types, const int32_t *unit_sizes,
+                           const SvtB200LrUnit *const *units /*[3] host arrays*/, int optimized_lr) {
+    refh_init();
+    const int hbd = cdef->bit_depth > 8;
+    Av1Common *cm = calloc(1, sizeof(Av1Common));
+    cm->use_highbitdepth = hbd;
+    cm->bit_depth = cdef->bit_depth;
+    cm->subsampling_x = cm->subsampling_y = 1;
+    cm->mi_rows = (cdef->height + 3) >> 2;
+    cm->mi_cols = (cdef->width + 3) >> 2;
+    cm->frm_size.frame_width = cm->frm_size.superres_upscaled_width = (uint16_t)cdef->width;
+    cm->frm_size.frame_height = cm->frm_size.superres_upscaled_height = (uint16_t)cdef->height;
+    cm->frm_size.superres_denominator = 8;
+    for (int p = 0; p < 3; p++) {
+        cm->rst_info[p].frame_restoration_type = (RestorationType)frame_types[p];
+        cm->rst_info[p].restoration_unit_size = unit_sizes[p];
+    }
+    if (svt_av1_alloc_restoration_buffers(cm) != EB_ErrorNone) return -1;
+    cm->rst_tmpbuf = (int32_t *)svt_aom_memalign(16, RESTORATION_TMPBUF_SIZE);
+    for (int p = 0; p < 3; p++) {
+        RestorationInfo *rsi = &cm->rst_info[p];
+        for (int i = 0; i < rsi->units_per_tile; i++) {
+            RestorationUnitInfo *ri = &rsi->unit_info[i];
+            const SvtB200LrUnit *u = &units[p][i];
+            ri->restoration_type = (RestorationType)u->restoration_type;
+            for (int k = 0; k < 8; k++) {
+                ri->wiener_info.vfilter[k] = u->vfilter[k];
+                ri->wiener_info.hfilter[k] = u->hfilter[k];
+            }
+            ri->sgrproj_info.ep = u->sgr_ep;
+            ri->sgrproj_info.xqd[0] = u->sgr_xqd[0];
+            ri->sgrproj_info.xqd[1] = u->sgr_xqd[1];
+        }
+    }
+    Yv12BufferConfig fc, fd;
+    yv12_view(&fc, cdef, hbd);
+    yv12_view(&fd, dblk, hbd);
+    svt_av1_loop_restoration_save_boundary_lines(&fd, cm, 0);
+    svt_av1_loop_restoration_save_boundary_lines(&fc, cm, 1);
+    svt_av1_loop_restoration_filter_frame(&fc, cm, optimized_lr);
+    for (int p = 0; p < 3; p++) {
+        free(cm->rst_info[p].unit_info);
+        free(cm->rst_info[p].boundaries.stripe_boundary_above);
+        free(cm->rst_info[p].boundaries.stripe_boundary_below);
+    }
+    svt_aom_free(cm->rst_tmpbuf);
+    free(cm);
+    return 0;
+}
+REFH_API int refh_lr_units(int width, int height, int plane, int unit_size, int *hunits, int *vunits) {
+    Av1Common cm;
+    memset(&cm, 0, sizeof(cm));
+    cm.subsampling_x = cm.subsampling_y = 1;
+    cm.frm_size.frame_width = cm.frm_size.superres_upscaled_width = (uint16_t)width;
+    cm.frm_size.frame_height = cm.frm_size.superres_upscaled_height = (uint16_t)height;
+    RestorationInfo rsi;
+    memset(&rsi, 0, sizeof(rsi));
+    rsi.restoration_unit_size = unit_size;
+    if (svt_av1_alloc_restoration_struct(&cm, &rsi, plane > 0) != EB_ErrorNone) return -1;
+    *hunits = rsi.horz_units_per_tile;
+    *vunits = rsi.vert_units_per_tile;
+    free(rsi.unit_info);
+    return rsi.units_per_tile;
+}
+
+/* ====================================================================================================
  * EncDec per-TU chain with the reference's own kernels, through its RTCD pointers (C paths):
  *   svt_residual_kernel8bit/16bit -> svt_av1_fwd_txfm2d_* (+ svt_handle_transform*) -> svt_aom_[highbd_]quantize_b or
  *   svt_av1_[highbd_]quantize_fp -> svt_av1_inv_txfm2d_add_*   (the body of av1_encode_loop, EbCodingLoop.c:290-...)

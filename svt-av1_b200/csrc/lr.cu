@@ -11,6 +11,8 @@
 // are kept in shared memory and both radii are produced from the same tile.  The Wiener filter keeps the
 // horizontally filtered (h+7) x w intermediate in shared memory, so HBM traffic is 2 B/sample (8-bit) in both
 // cases.  This round provides the RTCD drop-ins; the frame-level stripe loop is the next §8 row.
+#include <algorithm>
+
 #include "common.cuh"
 
 using namespace svtb200;
@@ -158,11 +160,156 @@ __global__ void __launch_bounds__(256) wiener_kernel(const WienerArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Frame-level loop restoration (svt_av1_loop_restoration_filter_frame).  Work item = one processing unit (64 luma /
+// 32 chroma samples wide) of one stripe (64 / 32 rows, the first one 8 / 4 rows shorter).  Stripes and processing-unit
+// columns are global partitions of the plane (restoration units are unions of them), so an item is (plane, stripe,
+// column) in closed form and the unit it belongs to follows from its top-left sample.  The reference overwrites the 3
+// rows above / below a stripe IN PLACE with saved boundary lines, filters, and restores them; that input is a pure
+// function of (CDEF picture, deblocked picture): rows {-3,-2,-1} = deblocked rows {y0-2, y0-2, y0-1}, rows
+// {h, h+1, h+2} = deblocked rows {y1, y1+1, y1+1} (clamped to the plane), columns clamped to the plane
+// (extend_lines / svt_extend_frame); the first / last stripe of the picture keeps the CDEF rows (clamped).  The CTA
+// composes that tile in shared memory and runs the same filter cores as the drop-ins.
+// ---------------------------------------------------------------------------------------------------------------
+struct LrPlaneDev {
+    const void *cdef, *dblk;
+    void *out;
+    int stride_c, stride_d, stride_o;
+    int w, h, ss; // plane size, 1 for chroma
+    int rtype, unit_size, hunits, vunits;
+    const SvtB200LrUnit *units;
+    int n_stripes, n_cols, item0;
+};
+struct LrFrameDev {
+    LrPlaneDev pl[3];
+    int bd, optimized, n_items;
+};
+constexpr int LR_SMEM = (71 * 71 * 2 + 15) / 16 * 16 + 2 * 66 * 66 * 4 + 2 * 64 * 64 * 4; // tile + A/B + flt0/flt1
+
+template <typename T>
+__global__ void __launch_bounds__(SGR_NT) lr_frame_kernel(const __grid_constant__ LrFrameDev d) {
+    extern __shared__ int32_t sm[];
+    const int item = blockIdx.x;
+    const int pi = item >= d.pl[2].item0 ? 2 : item >= d.pl[1].item0 ? 1 : 0;
+    const LrPlaneDev &pl = d.pl[pi];
+    const int li = item - pl.item0, s = li / pl.n_cols, c = li - s * pl.n_cols;
+    const int SH = 64 >> pl.ss, off = 8 >> pl.ss, PW = 64 >> pl.ss;
+    const int ys = max(0, s * SH - off), ye = min((s + 1) * SH - off, pl.h), h = ye - ys;
+    const int xs = c * PW, w = min(PW, pl.w - xs);
+    const T *cdef = reinterpret_cast<const T *>(pl.cdef);
+    const T *dblk = reinterpret_cast<const T *>(pl.dblk);
+    T *out = reinterpret_cast<T *>(pl.out);
+    int type = 0;
+    const SvtB200LrUnit *u = nullptr;
+    if (pl.rtype) {
+        const int ui = min((ys + (s ? off : 0)) / pl.unit_size, pl.vunits - 1), uj = min(xs / pl.unit_size, pl.hunits - 1);
+        u = pl.units + ui * pl.hunits + uj;
+        type = u->restoration_type;
+    }
+    if (type == 0) { // RESTORE_NONE: copy_tile
+        for (int t = threadIdx.x; t < w * h; t += SGR_NT) {
+            const int i = t / w, j = t - i * w;
+            out[(size_t)(ys + i) * pl.stride_o + xs + j] = cdef[(size_t)(ys + i) * pl.stride_c + xs + j];
+        }
+        return;
+    }
+    // ---- compose the (h+7) x (w+7) input tile, origin (3,3) ----
+    uint16_t *tile = reinterpret_cast<uint16_t *>(sm);
+    const int tw = w + 7, th = h + 7;
+    const bool copy_above = s > 0, copy_below = (s + 1) * SH - off < pl.h;
+    for (int t = threadIdx.x; t < tw * th; t += SGR_NT) {
+        const int r = t / tw - 3, cx = t - (t / tw) * tw - 3;
+        const int x = min(max(xs + cx, 0), pl.w - 1);
+        int yy = ys + r;
+        bool from_dblk = false;
+        if (r < 0 && copy_above) {
+            if (!d.optimized) {
+                yy = ys - 2 + max(r + 2, 0);
+                from_dblk = true;
+            } else if (r == -3) {
+                yy = ys - 2;
+            }
+        } else if (r >= h && copy_below) {
+            const int i = r - h;
+            if (!d.optimized) {
+                yy = ye + min(i, 1);
+                from_dblk = true;
+            } else if (i >= 2) {
+                yy = ye + 1;
+            }
+        }
+        yy = min(max(yy, 0), pl.h - 1);
+        tile[t] = from_dblk ? (uint16_t)dblk[(size_t)yy * pl.stride_d + x] : (uint16_t)cdef[(size_t)yy * pl.stride_c + x];
+    }
+    __syncthreads();
+    const int bd = d.bd, mx = (1 << bd) - 1;
+    if (type == 1) { // RESTORE_WIENER: wiener_filter_stripe[_highbd] with get_conv_params_wiener(bd)
+        int round_0 = 3, round_1 = 11;
+        if (bd + 7 - round_0 + 2 > 16) {
+            const int e = bd + 7 - round_0 + 2 - 16;
+            round_0 += e;
+            round_1 -= e;
+        }
+        uint16_t *tmp = tile + ((tw * th + 7) & ~7);
+        const int lim = (1 << (bd + 1 + 7 - round_0)) - 1;
+        for (int t = threadIdx.x; t < th * w; t += SGR_NT) {
+            const int y = t / w, x = t - y * w;
+            int32_t sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) sum += (int32_t)tile[y * tw + x + k] * u->hfilter[k];
+            sum += ((int32_t)tile[y * tw + x + 3] << 7) + (1 << (bd + 7 - 1));
+            const int32_t v = (sum + (1 << (round_0 - 1))) >> round_0;
+            tmp[t] = (uint16_t)(v < 0 ? 0 : (v > lim ? lim : v));
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < h * w; t += SGR_NT) {
+            const int y = t / w, x = t - y * w;
+            int32_t sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) sum += (int32_t)tmp[(y + k) * w + x] * u->vfilter[k];
+            sum += ((int32_t)tmp[(y + 3) * w + x] << 7) - (1 << (bd + round_1 - 1));
+            const int32_t v = (sum + (1 << (round_1 - 1))) >> round_1;
+            out[(size_t)(ys + y) * pl.stride_o + xs + x] = (T)(v < 0 ? 0 : (v > mx ? mx : v));
+        }
+        return;
+    }
+    // RESTORE_SGRPROJ: svt_apply_selfguided_restoration (the SGR cores read a (h+6) x (w+6) tile of pitch tw)
+    int32_t *A = sm + ((71 * 71 * 2 + 15) / 16 * 16) / 4, *B = A + 66 * 66, *flt0 = B + 66 * 66, *flt1 = flt0 + 64 * 64;
+    const int idx = u->sgr_ep;
+    const int r0 = c_sgr_r[idx][0], r1 = c_sgr_r[idx][1];
+    if (r0 > 0) sgr_pass(tile, tw, w, h, A, B, flt0, w, bd, idx, 0);
+    if (r1 > 0) sgr_pass(tile, tw, w, h, A, B, flt1, w, bd, idx, 1);
+    __syncthreads();
+    int xq0, xq1; // svt_decode_xq
+    if (r0 == 0) {
+        xq0 = 0;
+        xq1 = 128 - u->sgr_xqd[1];
+    } else if (r1 == 0) {
+        xq0 = u->sgr_xqd[0];
+        xq1 = 0;
+    } else {
+        xq0 = u->sgr_xqd[0];
+        xq1 = 128 - xq0 - u->sgr_xqd[1];
+    }
+    for (int t = threadIdx.x; t < w * h; t += SGR_NT) {
+        const int i = t / w, j = t - i * w;
+        const int32_t uu = (int32_t)tile[(i + 3) * tw + j + 3] << 4;
+        int32_t v = uu << 7;
+        if (r0 > 0) v += xq0 * (flt0[t] - uu);
+        if (r1 > 0) v += xq1 * (flt1[t] - uu);
+        const int16_t wv = (int16_t)((v + (1 << 10)) >> 11);
+        out[(size_t)(ys + i) * pl.stride_o + xs + j] = (T)(wv < 0 ? 0 : (wv > mx ? mx : wv));
+    }
+}
+
 static bool g_lr_attr = false;
 static void lr_attrs() {
     if (g_lr_attr) return;
     cudaFuncSetAttribute(sgr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     cudaFuncSetAttribute(wiener_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    cudaFuncSetAttribute(lr_frame_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, LR_SMEM);
+    cudaFuncSetAttribute(lr_frame_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, LR_SMEM);
     g_lr_attr = true;
 }
 
@@ -308,5 +455,57 @@ void svt_av1_highbd_wiener_convolve_add_src_cuda(const uint8_t *src, ptrdiff_t s
                                                  const void *conv_params, int32_t bd) {
     const ConvolveParamsView *cp = (const ConvolveParamsView *)conv_params;
     wiener_run(src, src_stride, dst, dst_stride, filter_x, filter_y, w, h, cp->round_0, cp->round_1, bd, 1);
+}
+
+int svt_b200_lr_frame(const SvtB200LrFrameParams *p, const SvtB200Frame *cdef, const SvtB200Frame *deblocked, const SvtB200Frame *out,
+                      void *stream) {
+    if (!p || !cdef || !deblocked || !out || cdef->bit_depth != deblocked->bit_depth || cdef->bit_depth != out->bit_depth ||
+        cdef->width != out->width || cdef->height != out->height || out->y == cdef->y || out->y == deblocked->y) {
+        set_error("svt_b200_lr_frame: bad argument (out must not alias the inputs)");
+        return SVT_B200_ERR_ARG;
+    }
+    lr_attrs();
+    LrFrameDev d;
+    memset(&d, 0, sizeof(d));
+    d.bd = cdef->bit_depth;
+    d.optimized = p->optimized_lr != 0;
+    int items = 0;
+    for (int i = 0; i < 3; i++) {
+        LrPlaneDev &pl = d.pl[i];
+        const int ss = i ? 1 : 0;
+        pl.cdef = i == 0 ? cdef->y : i == 1 ? cdef->cb : cdef->cr;
+        pl.dblk = i == 0 ? deblocked->y : i == 1 ? deblocked->cb : deblocked->cr;
+        pl.out = i == 0 ? out->y : i == 1 ? out->cb : out->cr;
+        pl.stride_c = i ? cdef->stride_c : cdef->stride_y;
+        pl.stride_d = i ? deblocked->stride_c : deblocked->stride_y;
+        pl.stride_o = i ? out->stride_c : out->stride_y;
+        pl.ss = ss;
+        pl.w = (cdef->width + ss) >> ss; // ROUND_POWER_OF_TWO(frame size, ss): whole_frame_rect
+        pl.h = (cdef->height + ss) >> ss;
+        pl.rtype = p->plane[i].frame_restoration_type;
+        pl.unit_size = p->plane[i].restoration_unit_size;
+        if (pl.rtype) {
+            if (!p->plane[i].units || pl.unit_size < (64 >> ss) || (pl.unit_size % (64 >> ss))) {
+                set_error("svt_b200_lr_frame: bad restoration unit size / missing unit array");
+                return SVT_B200_ERR_ARG;
+            }
+            pl.hunits = std::max((pl.w + (pl.unit_size >> 1)) / pl.unit_size, 1); // count_units_in_tile
+            pl.vunits = std::max((pl.h + (pl.unit_size >> 1)) / pl.unit_size, 1);
+            pl.units = p->plane[i].units;
+        }
+        const int SH = 64 >> ss, off = 8 >> ss;
+        pl.n_stripes = (pl.h + off + SH - 1) / SH;
+        pl.n_cols = (pl.w + SH - 1) / SH;
+        pl.item0 = items;
+        items += pl.n_stripes * pl.n_cols;
+    }
+    d.n_items = items;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d.bd > 8)
+        SVTB_LAUNCH(lr_frame_kernel<uint16_t>, items, SGR_NT, LR_SMEM, st, d);
+    else
+        SVTB_LAUNCH(lr_frame_kernel<uint8_t>, items, SGR_NT, LR_SMEM, st, d);
+    SVTB_CUDA_TRY(cudaGetLastError());
+    return SVT_B200_OK;
 }
 }

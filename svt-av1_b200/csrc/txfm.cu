@@ -323,6 +323,7 @@ struct EncodeDev {
     int quant_mode; // 0 quantize_b, 2 quantize_fp (the highbd variants are chosen from hbd)
     int32_t *qcoeff; // [n_tus][iw*ih]
     uint16_t *eob; // [n_tus]
+    int32_t *cul_level; // [n_tus] or null: av1_quantize_inv_quantize's return value (EbFullLoop.c:1596-1608)
 };
 // four horizontally adjacent samples at p (any alignment): aligned 32-bit loads + funnel shift for bytes
 template <typename T>
@@ -367,12 +368,13 @@ __global__ void __launch_bounds__(TX_NT) encode_tu_kernel(const __grid_constant_
     const int b = blockIdx.x * bpc + lb;
     const bool live = b < d.n_tus && lb < bpc;
     int32_t *buf = sm + lb * (pitch * h);
-    __shared__ int s_eob[TX_NT / 4];
+    __shared__ int s_eob[TX_NT / 4], s_cul[TX_NT / 4];
     TuDev tu = {0, 0, 0, 0};
     if (live) tu = d.tus[b];
     TxCfg t = make_txcfg(TS >= 0 ? TS : d.tx_size, tu.tx_type);
     if (TS >= 0) t.w = t.h = 4 << TS;
     const int pl = tu.plane;
+    int dc_sign = 0; // set_dc_sign: 1 negative, 2 positive DC level (held by the thread that quantises position 0)
     if (live) { // residual, four samples per step
         const T *sp = reinterpret_cast<const T *>(d.src[pl]) + (size_t)tu.y * d.src_stride[pl] + tu.x;
         const T *pp = reinterpret_cast<const T *>(d.pred[pl]) + (size_t)tu.y * d.pred_stride[pl] + tu.x;
@@ -385,7 +387,7 @@ __global__ void __launch_bounds__(TX_NT) encode_tu_kernel(const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 4; j++) buf[r * pitch + c + j] = sv[t.lr ? 3 - j : j] - pv[t.lr ? 3 - j : j];
         }
-        if (li == 0) s_eob[lb] = 0;
+        if (li == 0) s_eob[lb] = s_cul[lb] = 0;
     }
     __syncthreads();
     if (live)
@@ -413,16 +415,23 @@ __global__ void __launch_bounds__(TX_NT) encode_tu_kernel(const __grid_constant_
         const int mode = d.quant_mode + (d.hbd ? 1 : 0);
         const int16_t *iscan = d.iscan[(t.vk != 3 && t.hk == 3) ? 1 : (t.vk == 3 && t.hk != 3) ? 2 : 0];
         int32_t *qout = d.qcoeff + (size_t)b * n;
-        int eob = 0;
+        int eob = 0, lvl = 0;
         for (int i = li; i < n; i += Tn) {
             const int r = i >> liw, c = i & (iw - 1);
             int32_t qc, dqc;
             quant_one(mode, buf[r * pitch + c], i != 0, d.q[pl], log_scale, 32, 32, qc, dqc);
             qout[i] = qc;
             buf[r * pitch + c] = dqc;
-            if (qc) eob = max(eob, (int)iscan[i] + 1);
+            if (qc) {
+                eob = max(eob, (int)iscan[i] + 1);
+                lvl += min(abs(qc), 64); // cul_level saturates at COEFF_CONTEXT_MASK = 63: 64 per term is enough
+                if (i == 0) dc_sign = qc < 0 ? 1 : 2;
+            }
         }
-        if (eob) atomicMax(&s_eob[lb], eob);
+        if (eob) {
+            atomicMax(&s_eob[lb], eob);
+            atomicAdd(&s_cul[lb], lvl);
+        }
         if (w > 32 || h > 32)
             for (int i = li; i < w * h; i += Tn) { // zero the dropped high-frequency area of 64-wide transforms
                 const int r = i >> lw, c = i & (w - 1);
@@ -433,7 +442,10 @@ __global__ void __launch_bounds__(TX_NT) encode_tu_kernel(const __grid_constant_
     const int bd = d.bd;
     const int range_row = bd == 8 ? 16 : bd == 10 ? 18 : 20, range_col = bd == 8 ? 16 : bd == 10 ? 16 : 18;
     if (live) {
-        if (li == 0) d.eob[b] = (uint16_t)s_eob[lb];
+        if (li == 0) {
+            d.eob[b] = (uint16_t)s_eob[lb];
+            if (d.cul_level) d.cul_level[b] = min(63, s_cul[lb]) + (dc_sign == 1 ? 64 : dc_sign == 2 ? 128 : 0);
+        }
         for (int r = li; r < t.h; r += Tn) {
             const int rect = t.rect, is0 = t.is0;
             inv_1d_pass(buf + r * pitch, 1, t.w, t.hk, 12, range_row, [=](int32_t v) {
@@ -870,7 +882,14 @@ extern "C" {
 int svt_b200_encode_tus(const SvtB200EncodeParams *p, const SvtB200Frame *src, const SvtB200Frame *pred,
                         const SvtB200Frame *recon, const SvtB200Tu *tus, int32_t n_tus, int32_t *qcoeff, uint16_t *eob,
                         void *scratch, void *stream) {
-    if (!p || !src || !pred || !recon || !tus || !qcoeff || !eob || !scratch || n_tus < 0 || p->tx_size < 0 || p->tx_size > 18 ||
+    (void)scratch; // kept for ABI stability: the scan tables are resident per device since round 1
+    return svt_b200_encode_tus_cul(p, src, pred, recon, tus, n_tus, qcoeff, eob, nullptr, stream);
+}
+
+int svt_b200_encode_tus_cul(const SvtB200EncodeParams *p, const SvtB200Frame *src, const SvtB200Frame *pred,
+                            const SvtB200Frame *recon, const SvtB200Tu *tus, int32_t n_tus, int32_t *qcoeff, uint16_t *eob,
+                            int32_t *cul_level, void *stream) {
+    if (!p || !src || !pred || !recon || !tus || !qcoeff || !eob || n_tus < 0 || p->tx_size < 0 || p->tx_size > 18 ||
         src->bit_depth != pred->bit_depth || src->bit_depth != recon->bit_depth) {
         set_error("svt_b200_encode_tus: bad argument");
         return SVT_B200_ERR_ARG;
@@ -904,9 +923,9 @@ int svt_b200_encode_tus(const SvtB200EncodeParams *p, const SvtB200Frame *src, c
     d.quant_mode = p->use_fp ? 2 : 0;
     d.qcoeff = qcoeff;
     d.eob = eob;
+    d.cul_level = cul_level;
     // inverse scan tables of this size: built once per (device, tx_size) and kept resident (`scratch` is unused since
     // then; the parameter stays for ABI stability)
-    (void)scratch;
     const int16_t *tab = iscan_tables(p->tx_size);
     if (!tab) return SVT_B200_ERR_CUDA;
     for (int i = 0; i < 3; i++) d.iscan[i] = tab + i * 1024;

@@ -120,6 +120,19 @@ class LpfPickParams(C.Structure):
                 ("tx_mode_only_4x4", C.c_int32), ("q_ac", C.c_int32), ("key_frame", C.c_int32), ("last_level", C.c_int32 * 4)]
 
 
+class LrUnit(C.Structure):
+    _fields_ = [("restoration_type", C.c_int32), ("vfilter", C.c_int16 * 8), ("hfilter", C.c_int16 * 8), ("sgr_ep", C.c_int32),
+                ("sgr_xqd", C.c_int32 * 2)]
+
+
+class LrPlane(C.Structure):
+    _fields_ = [("frame_restoration_type", C.c_int32), ("restoration_unit_size", C.c_int32), ("units", C.c_void_p)]
+
+
+class LrFrameParams(C.Structure):
+    _fields_ = [("plane", LrPlane * 3), ("optimized_lr", C.c_int32)]
+
+
 def preset8_me_params(width, height, n_l0=1, n_l1=1, dist=((1, 2, 3, 4), (1, 2, 3, 4)), temporal_layer=1,
                       is_ref=1):
     """ME parameters of preset 8 (ENC_M8) at >=720p, 30 fps, as set_me_hme_params_oq /

@@ -86,7 +86,7 @@ def run_gpu_cdef_apply(p, rec, skip, idx):
     return do.download()
 
 
-def run_gpu_encode_tus(p, src, pred, tus):
+def run_gpu_encode_tus(p, src, pred, tus, with_cul=False):
     lib = sb.load()
     ts = p.tx_size
     w, h = sb.TX_W[ts], sb.TX_H[ts]
@@ -96,12 +96,13 @@ def run_gpu_encode_tus(p, src, pred, tus):
     dt = torch.from_numpy(np.frombuffer(arr, dtype=np.int32).copy()).cuda()
     q = torch.zeros(len(tus) * n, dtype=torch.int32, device="cuda")
     eob = torch.zeros(len(tus), dtype=torch.int16, device="cuda")
-    scratch = torch.zeros(16384, dtype=torch.uint8, device="cuda")
+    cul = torch.full((len(tus),), -1, dtype=torch.int32, device="cuda")
     ss, ps, rs = ds.struct(), dp.struct(), dr.struct()
-    sb.check(lib.svt_b200_encode_tus(C.byref(p), C.byref(ss), C.byref(ps), C.byref(rs), C.c_void_p(dt.data_ptr()), len(tus),
-                                     C.c_void_p(q.data_ptr()), C.c_void_p(eob.data_ptr()), C.c_void_p(scratch.data_ptr()), None), lib)
+    sb.check(lib.svt_b200_encode_tus_cul(C.byref(p), C.byref(ss), C.byref(ps), C.byref(rs), C.c_void_p(dt.data_ptr()), len(tus),
+                                         C.c_void_p(q.data_ptr()), C.c_void_p(eob.data_ptr()), C.c_void_p(cul.data_ptr()), None), lib)
     torch.cuda.synchronize()
-    return dr.download(), q.cpu().numpy().reshape(len(tus), n), eob.cpu().numpy().view(np.uint16)
+    out = (dr.download(), q.cpu().numpy().reshape(len(tus), n), eob.cpu().numpy().view(np.uint16))
+    return out + (cul.cpu().numpy(),) if with_cul else out
 
 
 def run_gpu_dlf(p, frame, flat):
@@ -125,6 +126,26 @@ def run_gpu_pick(p, rec, src, flat):
                                             C.c_void_p(scratch.data_ptr()), out, None), lib)
     torch.cuda.synchronize()
     return list(out), dr.download()
+
+
+def run_gpu_lr(cdef, dblk, units, unit_sizes, frame_types, optimized):
+    lib = sb.load()
+    dc, dd = DevYuv(cdef), DevYuv(dblk)
+    blank = cdef.copy()
+    for b in blank.bufs:
+        b[...] = 0
+    do = DevYuv(blank)
+    dus = [torch.from_numpy(np.frombuffer(u, dtype=np.uint8).copy()).cuda() for u in units]
+    p = sb.LrFrameParams()
+    for i in range(3):
+        p.plane[i].frame_restoration_type = frame_types[i]
+        p.plane[i].restoration_unit_size = unit_sizes[i]
+        p.plane[i].units = dus[i].data_ptr()
+    p.optimized_lr = optimized
+    cs, ds, os_ = dc.struct(), dd.struct(), do.struct()
+    sb.check(lib.svt_b200_lr_frame(C.byref(p), C.byref(cs), C.byref(ds), C.byref(os_), None), lib)
+    torch.cuda.synchronize()
+    return do.download()
 
 
 def run_gpu_sse(a, b):

@@ -62,3 +62,23 @@ def test_wiener_dropins():
                 orc.orc_wiener_convolve_add_src(C.c_void_p(p), int(hbd), C.c_ssize_t(stride), cm.ptr(d1), C.c_ssize_t(w + 5), cm.ptr(fx),
                                                 cm.ptr(fy), w, h, cp.round_0, cp.round_1, bd)
                 np.testing.assert_array_equal(d0, d1, err_msg=f"bd{bd} {mode} {w}x{h}")
+
+
+@pytest.mark.parametrize("case", [(192, 136, 8, 1, (64, 32, 32), ("mix", "mix", "mix"), (3, 3, 3), 0),
+                                  (192, 136, 10, 2, (64, 32, 32), ("wiener", "sgr", "mix"), (1, 2, 3), 0),
+                                  (264, 200, 8, 4, (64, 64, 32), ("sgr", "wiener", "mix"), (2, 1, 3), 1),
+                                  (328, 72, 10, 5, (256, 128, 128), ("mix", "mix", "mix"), (3, 3, 3), 0),
+                                  (200, 328, 8, 6, (64, 32, 64), ("mix", "none", "wiener"), (3, 0, 1), 1),
+                                  (1920, 1080, 8, 7, (64, 32, 32), ("mix", "mix", "mix"), (3, 3, 3), 0),
+                                  (1920, 1080, 10, 8, (256, 128, 128), ("sgr", "wiener", "mix"), (2, 1, 3), 0)])
+def test_lr_frame_vs_oracle(case):
+    """svt_av1_loop_restoration_filter_frame: the closed-form (plane, stripe, column) CTA decomposition against the
+    oracle's in-place save / overwrite / restore walk (itself pinned against the reference), incl. full 1080p."""
+    import gpu_runner as gr
+    from test_oracle_lr_frame import lr_case, run_oracle_lr
+    w, h, bd, seed, unit_sizes, modes, frame_types, optimized = case
+    cdef, dblk, units = lr_case(w, h, bd, seed, unit_sizes, modes)
+    want = run_oracle_lr(cdef, dblk, units, unit_sizes, frame_types, optimized)
+    got = gr.run_gpu_lr(cdef, dblk, units, unit_sizes, frame_types, optimized)
+    for i in range(3):
+        np.testing.assert_array_equal(got.plane(i), want.plane(i), err_msg=f"plane {i}")

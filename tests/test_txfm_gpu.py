@@ -203,9 +203,14 @@ def test_encode_tus_vs_oracle(case):
         p.q[i] = quant_plane(rng, bd)
     tus = make_tus(rng, ts, W, H, limit=160)
     want_rec, want_q, want_eob = oracle_encode_tus(p, src, pred, tus, use_fp)
-    got_rec, got_q, got_eob = gr.run_gpu_encode_tus(p, src, pred, tus)
+    got_rec, got_q, got_eob, got_cul = gr.run_gpu_encode_tus(p, src, pred, tus, with_cul=True)
     np.testing.assert_array_equal(got_eob, want_eob)
     np.testing.assert_array_equal(got_q, want_q)
+    # cul_level of av1_quantize_inv_quantize (EbFullLoop.c:1596-1608) from the ORACLE's levels: min(63, sum |q|), then
+    # set_dc_sign (|= 64 for a negative DC level, += 128 for a positive one)
+    want_cul = np.minimum(63, np.abs(want_q.astype(np.int64)).sum(axis=1))
+    want_cul = want_cul + np.where(want_q[:, 0] < 0, 64, np.where(want_q[:, 0] > 0, 128, 0))
+    np.testing.assert_array_equal(got_cul, want_cul)
     for i in range(3):
         np.testing.assert_array_equal(got_rec.plane(i), want_rec.plane(i), err_msg=f"plane {i}")
 
