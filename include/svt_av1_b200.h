@@ -232,6 +232,18 @@ SVT_B200_API void svt_cdef_filter_block_cuda(uint8_t *dst8, uint16_t *dst16, int
                                              int32_t sec_strength, int32_t dir, int32_t pri_damping,
                                              int32_t sec_damping, int32_t bsize, int32_t coeff_shift);
 
+/* replace svt_compute_cdef_dist_16bit / _8bit (aom_dsp_rtcd.h:67-70; compute_cdef_dist_c / _8bit_c, EbEncCdef.c:134-220):
+ * distortion of the filtered blocks of one filter block against the packed source blocks (luma 8x8: the perceptual
+ * double-precision measure; otherwise SSE), >> 2*coeff_shift.  dlist: the reference's CdefList array {by, bx, skip}.
+ * bsize: BlockSize (BLOCK_4X4 0, 4X8 1, 8X4 2, 8X8 3). */
+SVT_B200_API uint64_t svt_compute_cdef_dist_16bit_cuda(const uint16_t *dst, int32_t dstride, const uint16_t *src,
+                                                       const void *dlist, int32_t cdef_count, int32_t bsize,
+                                                       int32_t coeff_shift, int32_t pli);
+SVT_B200_API uint64_t svt_compute_cdef_dist_8bit_cuda(const uint8_t *dst8, int32_t dstride, const uint8_t *src8,
+                                                      const void *dlist, int32_t cdef_count, int32_t bsize,
+                                                      int32_t coeff_shift, int32_t pli);
+
+
 #define SVT_B200_CDEF_MAX_STRENGTHS 64 /* TOTAL_STRENGTHS (EbDefinitions.h:1675-1690) */
 
 /* Strength search of cdef_kernel: replaces cdef_seg_search / cdef_seg_search16bit
@@ -587,6 +599,39 @@ typedef struct SvtB200LrFrameParams {
  * One launch; every 64x64 (chroma 32x32) processing unit of every stripe is one CTA. */
 SVT_B200_API int svt_b200_lr_frame(const SvtB200LrFrameParams *p, const SvtB200Frame *cdef, const SvtB200Frame *deblocked,
                                    const SvtB200Frame *out, void *stream);
+
+/* =============================================================================================== */
+/* Loop restoration search: the reductions (the double-precision solves stay on the host)          */
+/* =============================================================================================== */
+
+/* replace svt_av1_compute_stats / svt_av1_compute_stats_highbd (aom_dsp_rtcd.h:71-74; EbRestorationPick.c:704-790):
+ * Wiener normal equations M[win^2], H[win^2 x win^2] (int64, exact) of one restoration unit. High-bit-depth planes are
+ * passed as CONVERT_TO_BYTEPTR pointers, as in the reference. */
+SVT_B200_API void svt_av1_compute_stats_cuda(int32_t wiener_win, const uint8_t *dgd8, const uint8_t *src8,
+                                             int32_t h_start, int32_t h_end, int32_t v_start, int32_t v_end,
+                                             int32_t dgd_stride, int32_t src_stride, int64_t *M, int64_t *H);
+SVT_B200_API void svt_av1_compute_stats_highbd_cuda(int32_t wiener_win, const uint8_t *dgd8, const uint8_t *src8,
+                                                    int32_t h_start, int32_t h_end, int32_t v_start, int32_t v_end,
+                                                    int32_t dgd_stride, int32_t src_stride, int64_t *M, int64_t *H,
+                                                    int32_t bit_depth);
+/* replace svt_av1_lowbd_pixel_proj_error / svt_av1_highbd_pixel_proj_error (aom_dsp_rtcd.h:84-87;
+ * EbRestorationPick.c:174-315). params: the reference's SgrParamsType {r[2], s[2]}. */
+SVT_B200_API int64_t svt_av1_lowbd_pixel_proj_error_cuda(const uint8_t *src8, int32_t width, int32_t height,
+                                                         int32_t src_stride, const uint8_t *dat8, int32_t dat_stride,
+                                                         int32_t *flt0, int32_t flt0_stride, int32_t *flt1,
+                                                         int32_t flt1_stride, int32_t xq[2], const void *params);
+SVT_B200_API int64_t svt_av1_highbd_pixel_proj_error_cuda(const uint8_t *src8, int32_t width, int32_t height,
+                                                          int32_t src_stride, const uint8_t *dat8, int32_t dat_stride,
+                                                          int32_t *flt0, int32_t flt0_stride, int32_t *flt1,
+                                                          int32_t flt1_stride, int32_t xq[2], const void *params);
+/* The compute_stats calls of search_wiener for every restoration unit of one plane in three launches, pictures resident
+ * on the device.  rects: DEVICE int32 [n_units][4] = {h_start, h_end, v_start, v_end} (RestorationTileLimits); reads of
+ * dgd outside the plane are clamped (= the 3-sample replicated border the reference extends the picture by);
+ * out: DEVICE int64 [n_units][win^2 + win^4] (M, then H); scratch: DEVICE, >= 8 * n_units bytes. */
+SVT_B200_API int svt_b200_lr_wiener_stats(const SvtB200Frame *dgd, const SvtB200Frame *src, int32_t plane,
+                                          int32_t wiener_win, const int32_t *rects, int32_t n_units,
+                                          int32_t max_unit_w, int32_t max_unit_h, int64_t *out, void *scratch,
+                                          void *stream);
 
 #ifdef __cplusplus
 }

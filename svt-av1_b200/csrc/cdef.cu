@@ -845,6 +845,64 @@ static int frame_dev(const SvtB200Frame *f, FrameDev *o) {
     return 0;
 }
 
+// compute_cdef_dist_c / compute_cdef_dist_8bit_c (EbEncCdef.c:134-220) on packed blocks: thread = one block
+__global__ void cdef_dist_kernel(const uint16_t *dst, const uint16_t *src, int count, int bw, int bh, int luma8x8, int coeff_shift,
+                                 unsigned long long *out) {
+    unsigned long long acc = 0;
+    for (int b = threadIdx.x; b < count; b += blockDim.x) {
+        const uint16_t *d = dst + b * bw * bh, *s = src + b * bw * bh;
+        if (luma8x8) {
+            unsigned long long ss = 0, sd = 0, ss2 = 0, sd2 = 0, ssd = 0;
+            for (int i = 0; i < 64; i++) {
+                const unsigned long long sv = s[i], dv = d[i];
+                ss += sv, sd += dv, ss2 += sv * sv, sd2 += dv * dv, ssd += sv * dv;
+            }
+            acc += dist8x8_from_sums(ss, sd, ss2, sd2, ssd, coeff_shift);
+        } else {
+            for (int i = 0; i < bw * bh; i++) {
+                const int e = (int)d[i] - (int)s[i];
+                acc += (unsigned long long)(e * e);
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+struct CdefListView { // CdefList (Common/Codec/EbCdef.h): uint8_t by, bx, skip
+    uint8_t by, bx, skip;
+};
+uint64_t cdef_dist_dropin(const void *dst, int hbd, int dstride, const void *src, const void *dlist_v, int count, int bsize,
+                          int coeff_shift, int pli) {
+    if (count <= 0) return 0;
+    const CdefListView *dl = (const CdefListView *)dlist_v;
+    // BlockSize: BLOCK_4X4 0, BLOCK_4X8 1, BLOCK_8X4 2, BLOCK_8X8 3
+    const int bw = (bsize == 3 || bsize == 2) ? 8 : 4, bh = (bsize == 3 || bsize == 1) ? 8 : 4, n = bw * bh;
+    ThreadCtx &c = tls();
+    const size_t half = ((size_t)count * n * 2 + 15) & ~(size_t)15;
+    c.reserve(2 * half + 16);
+    uint16_t *hd = (uint16_t *)c.h, *hs = (uint16_t *)(c.h + half);
+    for (int b = 0; b < count; b++) {
+        const int y0 = dl[b].by * bh, x0 = dl[b].bx * bw;
+        for (int i = 0; i < bh; i++)
+            for (int j = 0; j < bw; j++) {
+                const size_t o = (size_t)(y0 + i) * dstride + x0 + j;
+                hd[b * n + i * bw + j] = hbd ? ((const uint16_t *)dst)[o] : ((const uint8_t *)dst)[o];
+                hs[b * n + i * bw + j] = hbd ? ((const uint16_t *)src)[b * n + i * bw + j] : ((const uint8_t *)src)[b * n + i * bw + j];
+            }
+    }
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.d, c.h, 2 * half, cudaMemcpyHostToDevice, c.stream));
+    unsigned long long *d_out = (unsigned long long *)(c.d + 2 * half);
+    SVTB_CUDA_FATAL(cudaMemsetAsync(d_out, 0, 8, c.stream));
+    SVTB_LAUNCH(cdef_dist_kernel, 1, 64, 0, c.stream, (const uint16_t *)c.d, (const uint16_t *)(c.d + half), count, bw, bh,
+                (int)(bsize == 3 && pli == 0), coeff_shift, d_out);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h, d_out, 8, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_FATAL(cudaStreamSynchronize(c.stream));
+    unsigned long long v;
+    memcpy(&v, c.h, 8);
+    return v >> (2 * coeff_shift);
+}
+
 } // namespace
 
 extern "C" {
@@ -977,5 +1035,14 @@ void svt_cdef_filter_block_cuda(uint8_t *dst8, uint16_t *dst16, int32_t dstride,
             else
                 dst16[i * dstride + j] = o[i * 8 + j];
         }
+}
+
+uint64_t svt_compute_cdef_dist_16bit_cuda(const uint16_t *dst, int32_t dstride, const uint16_t *src, const void *dlist,
+                                          int32_t cdef_count, int32_t bsize, int32_t coeff_shift, int32_t pli) {
+    return cdef_dist_dropin(dst, 1, dstride, src, dlist, cdef_count, bsize, coeff_shift, pli);
+}
+uint64_t svt_compute_cdef_dist_8bit_cuda(const uint8_t *dst8, int32_t dstride, const uint8_t *src8, const void *dlist,
+                                         int32_t cdef_count, int32_t bsize, int32_t coeff_shift, int32_t pli) {
+    return cdef_dist_dropin(dst8, 0, dstride, src8, dlist, cdef_count, bsize, coeff_shift, pli);
 }
 }

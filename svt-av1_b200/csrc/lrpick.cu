@@ -1,0 +1,342 @@
+// lrpick.cu — the reductions of the loop-restoration SEARCH on sm_100a.
+//
+// Replaces (reference files under Source/Lib/Encoder/Codec):
+//   svt_av1_compute_stats_c / svt_av1_compute_stats_highbd_c   EbRestorationPick.c:704-790 (find_average EbRestorationPick.h:24-44)
+//   svt_av1_lowbd_pixel_proj_error_c / svt_av1_highbd_pixel_proj_error_c   EbRestorationPick.c:174-315
+//
+// compute_stats builds the Wiener normal equations of one restoration unit: with y = the win x win window of the
+// degraded picture around a sample (minus the unit average, column-major: idx = (dx+hw)*win + (dy+hw)) and x = the
+// source sample (minus the average), M[k] = sum y[k] x and H[k][l] = sum y[k] y[l] over the unit (int64, exact).
+// That is 49*50/2 + 49 multiply-accumulates per luma sample — integer work with exact 64-bit sums, so it runs on the
+// integer pipes, not on tensor cores.  Decomposition: a CTA owns a 32x16 sample tile of one unit (staged once with
+// its halo as int16 differences); H is cut into win x win blocks "window column kc x window column lc" (28 block pairs
+// for win 7) and a thread owns one block pair for a 1/8 subset of the tile's samples: 2*win LDS feed win*win IMAD into
+// register accumulators (int32 is safe for the <= 64 samples a thread sees, also at 12 bit).  Threads of a CTA merge
+// through shared-memory int32 atomics, CTAs through one 64-bit global atomic per entry.  The linear solves of the
+// search stay on the host (double precision, tiny), as in SURVEY.md §8(a).
+#include <algorithm>
+
+#include "common.cuh"
+
+using namespace svtb200;
+
+namespace {
+
+constexpr int ST_TW = 32, ST_TH = 16, ST_NT = 256;
+
+struct StatsUnit { // one restoration unit of a plane
+    int h_start, h_end, v_start, v_end;
+};
+struct StatsDev {
+    const void *dgd, *src; // planes (device), sample (0,0)
+    int dgd_stride, src_stride, pw, ph; // reads of dgd outside [0,pw)x[0,ph) are clamped (= the replicated border)
+    int clamp; // 0: the caller guarantees a halo of win/2 valid samples around every unit (drop-in staging)
+    const StatsUnit *units;
+    int n_units;
+    unsigned long long *sum; // [n_units] sample sums for the average
+    long long *out; // [n_units][win2 + win2*win2]: M then H (upper triangle filled; mirrored by finish_kernel)
+    int divider; // 1 / 4 / 16 (high bit depth 8/10/12)
+};
+
+template <typename T>
+__global__ void __launch_bounds__(256) stats_sum_kernel(const StatsDev d) {
+    const StatsUnit u = d.units[blockIdx.y];
+    const int w = u.h_end - u.h_start, h = u.v_end - u.v_start;
+    const T *p = reinterpret_cast<const T *>(d.dgd);
+    unsigned long long acc = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w * h; i += gridDim.x * blockDim.x) {
+        const int y = i / w, x = i - y * w;
+        acc += p[(size_t)(u.v_start + y) * d.dgd_stride + u.h_start + x];
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(&d.sum[blockIdx.y], acc);
+}
+
+template <typename T, int WIN>
+__global__ void __launch_bounds__(ST_NT) stats_kernel(const StatsDev d, int tiles_x_max) {
+    constexpr int HW = WIN / 2, WIN2 = WIN * WIN, TW = ST_TW + 2 * HW, TH = ST_TH + 2 * HW;
+    constexpr int NPAIR = WIN * (WIN + 1) / 2, NSUB = (ST_NT - 32) / NPAIR; // 28 pairs x 8 sample subsets (win 7)
+    __shared__ int16_t s_y[TH * TW];
+    __shared__ int16_t s_x[ST_TH * ST_TW];
+    __shared__ unsigned long long s_acc[WIN2 + WIN2 * WIN2]; // 64-bit: a 512-sample tile overflows int32 at 12 bit
+    const StatsUnit u = d.units[blockIdx.y];
+    const int uw = u.h_end - u.h_start, uh = u.v_end - u.v_start;
+    const int tx = blockIdx.x % tiles_x_max, ty = blockIdx.x / tiles_x_max;
+    const int x0 = u.h_start + tx * ST_TW, y0 = u.v_start + ty * ST_TH;
+    if (x0 >= u.h_end || y0 >= u.v_end) return;
+    const int tw = min(ST_TW, u.h_end - x0), th = min(ST_TH, u.v_end - y0);
+    const int avg = (int)(d.sum[blockIdx.y] / (unsigned long long)(uw * uh)); // find_average: truncating division
+    const T *dg = reinterpret_cast<const T *>(d.dgd);
+    const T *sr = reinterpret_cast<const T *>(d.src);
+    const int tid = threadIdx.x;
+    for (int i = tid; i < TH * TW; i += ST_NT) {
+        const int r = i / TW, c = i - r * TW;
+        int yy = y0 + r - HW, xx = x0 + c - HW;
+        if (d.clamp) {
+            yy = min(max(yy, 0), d.ph - 1);
+            xx = min(max(xx, 0), d.pw - 1);
+        }
+        const bool need = r < th + 2 * HW && c < tw + 2 * HW;
+        s_y[i] = need ? (int16_t)((int)dg[(size_t)yy * d.dgd_stride + xx] - avg) : (int16_t)0;
+    }
+    for (int i = tid; i < ST_TH * ST_TW; i += ST_NT) {
+        const int r = i / ST_TW, c = i - r * ST_TW;
+        s_x[i] = (r < th && c < tw) ? (int16_t)((int)sr[(size_t)(y0 + r) * d.src_stride + x0 + c] - avg) : (int16_t)0;
+    }
+    for (int i = tid; i < WIN2 + WIN2 * WIN2; i += ST_NT) s_acc[i] = 0;
+    __syncthreads();
+    if (tid < NPAIR * NSUB) { // H: block pair (kc <= lc), sample subset `sub`
+        const int pair = tid % NPAIR, sub = tid / NPAIR;
+        int kc = 0, rem = pair; // pair -> (kc, lc), kc <= lc
+        while (rem >= WIN - kc) {
+            rem -= WIN - kc;
+            kc++;
+        }
+        const int lc = kc + rem;
+        int acc[WIN][WIN];
+#pragma unroll
+        for (int a = 0; a < WIN; a++)
+#pragma unroll
+            for (int b = 0; b < WIN; b++) acc[a][b] = 0;
+        for (int px = sub; px < th * tw; px += NSUB) {
+            const int pi = px / tw, pj = px - pi * tw;
+            int yk[WIN], yl[WIN];
+#pragma unroll
+            for (int a = 0; a < WIN; a++) {
+                yk[a] = s_y[(pi + a) * TW + pj + kc];
+                yl[a] = s_y[(pi + a) * TW + pj + lc];
+            }
+#pragma unroll
+            for (int a = 0; a < WIN; a++)
+#pragma unroll
+                for (int b = 0; b < WIN; b++) acc[a][b] += yk[a] * yl[b];
+        }
+#pragma unroll
+        for (int a = 0; a < WIN; a++)
+#pragma unroll
+            for (int b = 0; b < WIN; b++) {
+                const int k = kc * WIN + a, l = lc * WIN + b;
+                if (l >= k && acc[a][b]) atomicAdd(&s_acc[WIN2 + k * WIN2 + l], (unsigned long long)(long long)acc[a][b]);
+            }
+    } else if (tid >= ST_NT - 32) { // M: the last warp
+        const int lane = tid & 31;
+        for (int k = lane; k < WIN2; k += 32) {
+            const int kcol = k / WIN, krow = k - kcol * WIN;
+            long long acc = 0;
+            for (int px = 0; px < th * tw; px++) {
+                const int pi = px / tw, pj = px - pi * tw;
+                acc += (int)s_y[(pi + krow) * TW + pj + kcol] * (int)s_x[pi * ST_TW + pj];
+            }
+            s_acc[k] = (unsigned long long)acc;
+        }
+    }
+    __syncthreads();
+    long long *out = d.out + (size_t)blockIdx.y * (WIN2 + WIN2 * WIN2);
+    for (int i = tid; i < WIN2 + WIN2 * WIN2; i += ST_NT) {
+        const unsigned long long v = s_acc[i];
+        if (v) atomicAdd(reinterpret_cast<unsigned long long *>(out + i), v);
+    }
+}
+
+// high-bit-depth divider (truncating, as C's `/=`) and the mirror of the upper triangle
+__global__ void stats_finish_kernel(long long *out, int n_units, int win2, int divider) {
+    long long *o = out + (size_t)blockIdx.x * (win2 + win2 * win2);
+    for (int i = threadIdx.x; i < win2 + win2 * win2; i += blockDim.x) {
+        if (i >= win2) {
+            const int k = (i - win2) / win2, l = (i - win2) - k * win2;
+            if (l < k) continue;
+        }
+        if (divider > 1) o[i] /= divider;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < win2 * win2; i += blockDim.x) {
+        const int k = i / win2, l = i - k * win2;
+        if (l < k) o[win2 + i] = o[win2 + l * win2 + k];
+    }
+}
+
+int stats_launch(StatsDev &d, int win, int hbd, int max_uw, int max_uh, cudaStream_t st) {
+    const int win2 = win * win;
+    if (cudaMemsetAsync(d.sum, 0, (size_t)d.n_units * 8, st) != cudaSuccess) return -1;
+    if (cudaMemsetAsync(d.out, 0, (size_t)d.n_units * (win2 + win2 * win2) * 8, st) != cudaSuccess) return -1;
+    const int tiles_x = (max_uw + ST_TW - 1) / ST_TW, tiles_y = (max_uh + ST_TH - 1) / ST_TH;
+    const dim3 gs(std::min(64, (max_uw * max_uh + 255) / 256), d.n_units), gt(tiles_x * tiles_y, d.n_units);
+    if (hbd) {
+        SVTB_LAUNCH(stats_sum_kernel<uint16_t>, gs, 256, 0, st, d);
+        if (win == 7)
+            SVTB_LAUNCH((stats_kernel<uint16_t, 7>), gt, ST_NT, 0, st, d, tiles_x);
+        else
+            SVTB_LAUNCH((stats_kernel<uint16_t, 5>), gt, ST_NT, 0, st, d, tiles_x);
+    } else {
+        SVTB_LAUNCH(stats_sum_kernel<uint8_t>, gs, 256, 0, st, d);
+        if (win == 7)
+            SVTB_LAUNCH((stats_kernel<uint8_t, 7>), gt, ST_NT, 0, st, d, tiles_x);
+        else
+            SVTB_LAUNCH((stats_kernel<uint8_t, 5>), gt, ST_NT, 0, st, d, tiles_x);
+    }
+    SVTB_LAUNCH(stats_finish_kernel, d.n_units, 256, 0, st, d.out, d.n_units, win2, d.divider);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+// ---- RTCD drop-in (host pointers): stage the unit + halo, run, copy M and H back -------------------------------
+void stats_dropin(int win, const void *dgd, const void *src, int hbd, int h_start, int h_end, int v_start, int v_end, int dgd_stride,
+                  int src_stride, int64_t *M, int64_t *H, int bit_depth) {
+    const int hw = win / 2, win2 = win * win;
+    const int uw = h_end - h_start, uh = v_end - v_start;
+    if ((win != 7 && win != 5) || uw <= 0 || uh <= 0) {
+        fprintf(stderr, "svt_av1_compute_stats_cuda: unsupported window %d / empty unit\n", win);
+        abort();
+    }
+    const int es = hbd ? 2 : 1, dw = uw + 2 * hw, dh = uh + 2 * hw;
+    ThreadCtx &c = tls();
+    const size_t dgd_b = ((size_t)dw * dh * es + 15) & ~(size_t)15, src_b = ((size_t)uw * uh * es + 15) & ~(size_t)15;
+    const size_t out_b = (size_t)(win2 + win2 * win2) * 8, tot = dgd_b + src_b + 64 + out_b;
+    c.reserve(tot);
+    for (int y = 0; y < dh; y++)
+        memcpy(c.h + (size_t)y * dw * es, (const uint8_t *)dgd + ((ptrdiff_t)(v_start - hw + y) * dgd_stride + h_start - hw) * es, (size_t)dw * es);
+    for (int y = 0; y < uh; y++)
+        memcpy(c.h + dgd_b + (size_t)y * uw * es, (const uint8_t *)src + ((ptrdiff_t)(v_start + y) * src_stride + h_start) * es, (size_t)uw * es);
+    StatsUnit hu = {hw, hw + uw, hw, hw + uh};
+    memcpy(c.h + dgd_b + src_b, &hu, sizeof(hu));
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.d, c.h, dgd_b + src_b + 16, cudaMemcpyHostToDevice, c.stream));
+    StatsDev d;
+    d.dgd = c.d;
+    d.src = c.d + dgd_b - ((size_t)hw * uw + hw) * es; // so that (hw, hw) addresses the first staged source sample
+    d.dgd_stride = dw;
+    d.src_stride = uw;
+    d.pw = dw;
+    d.ph = dh;
+    d.clamp = 0;
+    d.units = (const StatsUnit *)(c.d + dgd_b + src_b);
+    d.n_units = 1;
+    d.sum = (unsigned long long *)(c.d + dgd_b + src_b + 32);
+    d.out = (long long *)(c.d + dgd_b + src_b + 64);
+    d.divider = !hbd ? 1 : bit_depth == 12 ? 16 : bit_depth == 10 ? 4 : 1;
+    if (stats_launch(d, win, hbd, uw, uh, c.stream)) fatal("svt_av1_compute_stats_cuda", cudaGetLastError());
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h, d.out, out_b, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_FATAL(cudaStreamSynchronize(c.stream));
+    memcpy(M, c.h, (size_t)win2 * 8);
+    memcpy(H, c.h + (size_t)win2 * 8, (size_t)win2 * win2 * 8);
+}
+
+// ---- pixel projection error -----------------------------------------------------------------------------------
+struct ProjArgs {
+    const void *src, *dat;
+    const int32_t *flt0, *flt1;
+    int w, h, src_stride, dat_stride, f0s, f1s, xq0, xq1, r0, r1, hbd;
+    unsigned long long *out;
+};
+__global__ void __launch_bounds__(256) proj_error_kernel(const ProjArgs a) {
+    long long acc = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.w * a.h; i += gridDim.x * blockDim.x) {
+        const int y = i / a.w, x = i - y * a.w;
+        const int s = a.hbd ? ((const uint16_t *)a.src)[(size_t)y * a.src_stride + x] : ((const uint8_t *)a.src)[(size_t)y * a.src_stride + x];
+        const int dv = a.hbd ? ((const uint16_t *)a.dat)[(size_t)y * a.dat_stride + x] : ((const uint8_t *)a.dat)[(size_t)y * a.dat_stride + x];
+        int e;
+        if (a.r0 > 0 || a.r1 > 0) {
+            const int u = dv << 4; // SGRPROJ_RST_BITS
+            int v = a.hbd ? (1 << 10) : (u << 7); // highbd: half; lowbd: u << SGRPROJ_PRJ_BITS (rounded below)
+            if (a.r0 > 0) v += a.xq0 * (a.flt0[(size_t)y * a.f0s + x] - u);
+            if (a.r1 > 0) v += a.xq1 * (a.flt1[(size_t)y * a.f1s + x] - u);
+            e = a.hbd ? (v >> 11) + dv - s : ((v + (1 << 10)) >> 11) - s;
+        } else {
+            e = dv - s;
+        }
+        acc += (long long)(e * e);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(a.out, (unsigned long long)acc);
+}
+
+int64_t proj_dropin(const void *src, int width, int height, int src_stride, const void *dat, int dat_stride, const int32_t *flt0,
+                    int f0s, const int32_t *flt1, int f1s, const int32_t *xq, const int32_t *params /* SgrParamsType: r[2], s[2] */,
+                    int hbd) {
+    if (width <= 0 || height <= 0) return 0;
+    const int es = hbd ? 2 : 1, r0 = params[0], r1 = params[1];
+    ThreadCtx &c = tls();
+    const size_t pb = ((size_t)width * height * es + 15) & ~(size_t)15, fb = (size_t)width * height * 4;
+    c.reserve(2 * pb + 2 * fb + 16);
+    for (int y = 0; y < height; y++) {
+        memcpy(c.h + (size_t)y * width * es, (const uint8_t *)src + (size_t)y * src_stride * es, (size_t)width * es);
+        memcpy(c.h + pb + (size_t)y * width * es, (const uint8_t *)dat + (size_t)y * dat_stride * es, (size_t)width * es);
+        if (r0 > 0) memcpy(c.h + 2 * pb + (size_t)y * width * 4, flt0 + (size_t)y * f0s, (size_t)width * 4);
+        if (r1 > 0) memcpy(c.h + 2 * pb + fb + (size_t)y * width * 4, flt1 + (size_t)y * f1s, (size_t)width * 4);
+    }
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.d, c.h, 2 * pb + 2 * fb, cudaMemcpyHostToDevice, c.stream));
+    ProjArgs a;
+    a.src = c.d;
+    a.dat = c.d + pb;
+    a.flt0 = (const int32_t *)(c.d + 2 * pb);
+    a.flt1 = (const int32_t *)(c.d + 2 * pb + fb);
+    a.w = width, a.h = height, a.src_stride = a.dat_stride = a.f0s = a.f1s = width;
+    a.xq0 = xq[0], a.xq1 = xq[1], a.r0 = r0, a.r1 = r1, a.hbd = hbd;
+    a.out = (unsigned long long *)(c.d + 2 * pb + 2 * fb);
+    SVTB_CUDA_FATAL(cudaMemsetAsync(a.out, 0, 8, c.stream));
+    SVTB_LAUNCH(proj_error_kernel, std::min(64, (width * height + 255) / 256), 256, 0, c.stream, a);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h, a.out, 8, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_FATAL(cudaStreamSynchronize(c.stream));
+    int64_t v;
+    memcpy(&v, c.h, 8);
+    return v;
+}
+
+static inline const void *short_ptr(const uint8_t *p) { return (const void *)(((uintptr_t)p) << 1); } // CONVERT_TO_SHORTPTR
+
+} // namespace
+
+extern "C" {
+
+void svt_av1_compute_stats_cuda(int32_t wiener_win, const uint8_t *dgd8, const uint8_t *src8, int32_t h_start, int32_t h_end,
+                                int32_t v_start, int32_t v_end, int32_t dgd_stride, int32_t src_stride, int64_t *M, int64_t *H) {
+    stats_dropin(wiener_win, dgd8, src8, 0, h_start, h_end, v_start, v_end, dgd_stride, src_stride, M, H, 8);
+}
+void svt_av1_compute_stats_highbd_cuda(int32_t wiener_win, const uint8_t *dgd8, const uint8_t *src8, int32_t h_start, int32_t h_end,
+                                       int32_t v_start, int32_t v_end, int32_t dgd_stride, int32_t src_stride, int64_t *M, int64_t *H,
+                                       int32_t bit_depth) {
+    stats_dropin(wiener_win, short_ptr(dgd8), short_ptr(src8), 1, h_start, h_end, v_start, v_end, dgd_stride, src_stride, M, H, bit_depth);
+}
+int64_t svt_av1_lowbd_pixel_proj_error_cuda(const uint8_t *src8, int32_t width, int32_t height, int32_t src_stride, const uint8_t *dat8,
+                                            int32_t dat_stride, int32_t *flt0, int32_t flt0_stride, int32_t *flt1, int32_t flt1_stride,
+                                            int32_t xq[2], const void *params) {
+    return proj_dropin(src8, width, height, src_stride, dat8, dat_stride, flt0, flt0_stride, flt1, flt1_stride, xq,
+                       (const int32_t *)params, 0);
+}
+int64_t svt_av1_highbd_pixel_proj_error_cuda(const uint8_t *src8, int32_t width, int32_t height, int32_t src_stride, const uint8_t *dat8,
+                                             int32_t dat_stride, int32_t *flt0, int32_t flt0_stride, int32_t *flt1, int32_t flt1_stride,
+                                             int32_t xq[2], const void *params) {
+    return proj_dropin(short_ptr(src8), width, height, src_stride, short_ptr(dat8), dat_stride, flt0, flt0_stride, flt1, flt1_stride,
+                       xq, (const int32_t *)params, 1);
+}
+
+// Wiener statistics of every restoration unit of one plane, device resident (the batched form of the search's
+// compute_stats calls: search_wiener, EbRestorationPick.c).  rects: DEVICE array of n_units {h_start, h_end, v_start,
+// v_end}; out: DEVICE int64 [n_units][win2 + win2*win2] (M then H); scratch: >= 8 * n_units bytes (device).
+int svt_b200_lr_wiener_stats(const SvtB200Frame *dgd, const SvtB200Frame *src, int32_t plane, int32_t wiener_win,
+                             const int32_t *rects, int32_t n_units, int32_t max_unit_w, int32_t max_unit_h, int64_t *out,
+                             void *scratch, void *stream) {
+    if (!dgd || !src || !rects || !out || !scratch || plane < 0 || plane > 2 || (wiener_win != 7 && wiener_win != 5) || n_units <= 0 ||
+        dgd->bit_depth != src->bit_depth || max_unit_w <= 0 || max_unit_h <= 0) {
+        set_error("svt_b200_lr_wiener_stats: bad argument");
+        return SVT_B200_ERR_ARG;
+    }
+    const int ss = plane ? 1 : 0;
+    StatsDev d;
+    d.dgd = plane == 0 ? dgd->y : plane == 1 ? dgd->cb : dgd->cr;
+    d.src = plane == 0 ? src->y : plane == 1 ? src->cb : src->cr;
+    d.dgd_stride = plane ? dgd->stride_c : dgd->stride_y;
+    d.src_stride = plane ? src->stride_c : src->stride_y;
+    d.pw = (dgd->width + ss) >> ss;
+    d.ph = (dgd->height + ss) >> ss;
+    d.clamp = 1;
+    d.units = reinterpret_cast<const StatsUnit *>(rects);
+    d.n_units = n_units;
+    d.sum = (unsigned long long *)scratch;
+    d.out = (long long *)out;
+    d.divider = dgd->bit_depth == 12 ? 16 : dgd->bit_depth == 10 ? 4 : 1;
+    if (stats_launch(d, wiener_win, dgd->bit_depth > 8, max_unit_w, max_unit_h, (cudaStream_t)stream)) {
+        set_error("svt_b200_lr_wiener_stats: launch failed");
+        return SVT_B200_ERR_CUDA;
+    }
+    return SVT_B200_OK;
+}
+}
