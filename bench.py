@@ -8,8 +8,9 @@ A "step" is one pass of the hot path over one mini-GOP of FRAMES_PER_STEP synthe
   3. deblocking          svt_av1_loop_filter_frame, all planes                                  (2 launches)
   4. CDEF                cdef_seg_search (10 strengths, preset 8) + svt_av1_cdef_frame          (2 launches)
   value : frames/s with all inputs resident in HBM (CUDA events on the launch stream, max over ranks)
-  e2e   : same work through the C ABI with HOST (pinned) buffers: H2D of the source/prediction planes, ME planes
-          and mode-info summary; D2H of MeSbResults, quantised coefficients + eobs, CDEF mse and the final recon.
+  e2e   : same work through the C ABI with HOST (pinned) buffers: H2D of the ME planes (the full-resolution one doubles as
+          the source luma), source chroma, prediction planes and mode-info summary; D2H of MeSbResults, the quantised
+          levels in scan order up to eob (svt_b200_pack_levels) + eobs + offsets, CDEF mse and the final recon.
   --impl reference : the reference's own C implementation (oracle/_ref, unmodified sources, its RTCD C paths)
           of the same four stages on the host cores, one frame per thread, on a bounded sample.
 Multi-GPU (torchrun): independent streams sharded one per rank, no data-path collective ("weak" scaling).
@@ -49,22 +50,29 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
+    """One long-running `nvidia-smi -lms` child sampling the SM clock and the throttle reasons while the timed regions
+    run (a blocking pipe read in this thread: no fork / GIL traffic in the timed loop)."""
+
     def __init__(self, idx):
         super().__init__(daemon=True)
-        self.idx, self.rows, self.stop_flag = idx, [], False
+        self.idx, self.rows, self.stop_flag, self.proc = idx, [], False, None
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if line.strip():
+                    self.rows.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+        finally:
+            if self.proc is not None:
+                self.proc.kill()
 
     def summary(self):
         if not self.rows:
@@ -83,7 +91,7 @@ def workload_config(frames):
             "stages": ["me(hme+fullpel, %d+%d refs)" % (N_L0, N_L1), "encdec(residual+fwd txfm+quant+inv txfm+recon, all TUs)",
                        "dlf(frame, levels %s)" % (QINDEX_LEVELS,), "cdef(search 10 strengths + apply)"],
             "l2_policy": f"ring of {RING} distinct input sets (> L2) cycled between steps",
-            "issue": "4 pictures in flight, one CUDA stream each"}
+            "issue": "4 pictures in flight, one CUDA stream each; steps double-buffered, no barrier between steps"}
 
 
 def make_frames(seed, n):
@@ -263,6 +271,38 @@ class DeviceSet:
         self.pred_host = [[torch.from_numpy(b).pin_memory() for b in f.bufs] for f in pred]
         self.src_dev = [[t.cuda() for t in f] for f in self.src_host]
         self.pred_dev = [[t.cuda() for t in f] for f in self.pred_host]
+        # e2e uploads as ONE pinned block per picture (fewer, larger copies): the three ME planes; and
+        # {source Cb, Cr, prediction Y, Cb, Cr}
+        self.me_flat = [flat_pack(torch, pics) for pics in self.me_host]
+        self.in_flat = [flat_pack(torch, f[1:] + g) for f, g in zip(self.src_host, self.pred_host)]
+
+
+def flat_layout(tensors, align=256):
+    offs, o = [], 0
+    for t in tensors:
+        offs.append(o)
+        o += (t.numel() * t.element_size() + align - 1) // align * align
+    return offs, o
+
+
+def flat_pack(torch, tensors):
+    """The tensors copied back to back (256-byte aligned) into one pinned uint8 block."""
+    offs, total = flat_layout(tensors)
+    flat = torch.empty(total, dtype=torch.uint8).pin_memory()
+    for t, o in zip(tensors, offs):
+        n = t.numel() * t.element_size()
+        flat[o:o + n].copy_(t.contiguous().view(torch.uint8).reshape(-1))
+    return flat
+
+
+def flat_views(torch, flat, like):
+    """Views into `flat` with the shapes / dtypes of the tensors in `like` (same layout as flat_pack)."""
+    offs, _ = flat_layout(like)
+    out = []
+    for t, o in zip(like, offs):
+        n = t.numel() * t.element_size()
+        out.append(flat[o:o + n].view(t.dtype).reshape(t.shape))
+    return out
 
 
 def frame_struct(sb, yuv, tensors):
@@ -310,182 +350,297 @@ def run_b200(args):
     h_idx = torch.zeros(nfb, dtype=torch.int8).pin_memory()
 
     F = FRAMES_PER_STEP
-
-    def me_out(pinned=False):
-        mk = (lambda n, dt: torch.empty(n, dtype=dt).pin_memory()) if pinned else (lambda n, dt: torch.empty(n, dtype=dt, device="cuda"))
-        return {"best_sad": mk(n_sb * 8 * 85, torch.int32), "best_mv": mk(n_sb * 8 * 85, torch.int32),
-                "hme": mk(n_sb * 8 * 16, torch.uint8), "me_mv": mk(n_sb * 85 * 7 * 2, torch.int16),
-                "me_cand": mk(n_sb * 85 * 23, torch.uint8), "total_cand": mk(n_sb * 85, torch.uint8), "rc": mk(n_sb, torch.int32)}
-
-    d_me = [me_out() for _ in range(F)]
-    h_me = [{k: me_out(True)[k] for k in ("me_mv", "me_cand", "total_cand", "rc")} for _ in range(F)]
-    me_scratch = [torch.empty(lib.svt_b200_me_scratch_bytes(C.byref(me_params)), dtype=torch.uint8, device="cuda") for _ in range(F)]
-    d_q = [{ts: torch.empty(len(tus[ts]) * n_coef[ts], dtype=torch.int32, device="cuda") for ts in tus} for _ in range(F)]
-    d_eob = [{ts: torch.empty(len(tus[ts]), dtype=torch.int16, device="cuda") for ts in tus} for _ in range(F)]
-    h_q = [{ts: torch.empty(len(tus[ts]) * n_coef[ts], dtype=torch.int32).pin_memory() for ts in tus} for _ in range(F)]
-    h_eob = [{ts: torch.empty(len(tus[ts]), dtype=torch.int16).pin_memory() for ts in tus} for _ in range(F)]
-    enc_scratch = torch.empty(16384, dtype=torch.uint8, device="cuda")
-    d_mse = [torch.empty(2 * nfb * 64, dtype=torch.int64, device="cuda") for _ in range(F)]
-    h_mse = [torch.empty(2 * nfb * 64, dtype=torch.int64).pin_memory() for _ in range(F)]
     proto = sets[0].src[0]
-    d_rec = [[torch.empty_like(t) for t in sets[0].src_dev[0]] for _ in range(F)]
-    d_out = [[torch.empty_like(t) for t in sets[0].src_dev[0]] for _ in range(F)]
-    h_out = [[torch.empty(t.shape, dtype=t.dtype).pin_memory() for t in sets[0].src_dev[0]] for _ in range(F)]
-    # device staging of the e2e arm
-    e_me = [[torch.empty_like(t) for t in pics] for pics in sets[0].me_dev]
-    e_src = [[torch.empty_like(t) for t in f] for f in sets[0].src_dev]
-    e_pred = [[torch.empty_like(t) for t in f] for f in sets[0].pred_dev]
-    e_mi, e_skip = torch.empty_like(d_mi), torch.empty_like(d_skip)
+    full_geo = sets[0].geos[0]  # the padded full-resolution ME plane: it IS the source luma, uploaded once
+
+    def pinned(n, dt):
+        return torch.empty(n, dtype=dt).pin_memory()
+
+    def dev(n, dt):
+        return torch.empty(n, dtype=dt, device="cuda")
+
+    class StepBuffers:
+        """Everything one step (mini-GOP) writes: the instances rotate so that the next step's uploads and front halves
+        can be issued while the host still finishes the current step (no pipeline drain between steps)."""
+
+        def __init__(self):
+            def me_out(mk):
+                return {"best_sad": mk(n_sb * 8 * 85, torch.int32), "best_mv": mk(n_sb * 8 * 85, torch.int32),
+                        "hme": mk(n_sb * 8 * 16, torch.uint8), "me_mv": mk(n_sb * 85 * 7 * 2, torch.int16),
+                        "me_cand": mk(n_sb * 85 * 23, torch.uint8), "total_cand": mk(n_sb * 85, torch.uint8), "rc": mk(n_sb, torch.int32)}
+            self.d_me = [me_out(dev) for _ in range(F)]
+            self.me_scratch = [dev(lib.svt_b200_me_scratch_bytes(C.byref(me_params)), torch.uint8) for _ in range(F)]
+            self.d_q = [{ts: dev(len(tus[ts]) * n_coef[ts], torch.int32) for ts in tus} for _ in range(F)]
+            self.d_eob = [{ts: dev(len(tus[ts]), torch.int16) for ts in tus} for _ in range(F)]
+            self.d_mse = [dev(2 * nfb * 64, torch.int64) for _ in range(F)]
+            self.d_rec = [[torch.empty_like(t) for t in sets[0].src_dev[0]] for _ in range(F)]
+            self.d_out = [[torch.empty_like(t) for t in sets[0].src_dev[0]] for _ in range(F)]
+            # ---- e2e arm.  Uploads and read-backs are ONE block per picture and direction (the step issues ~80 copies
+            # instead of ~200: the Python-side issue time was the end-to-end bound), the library writes into views.
+            s0 = sets[0]
+            self.e_me_flat = [dev(s0.me_flat[0].numel(), torch.uint8) for _ in range(F + 4)]
+            self.e_me = [flat_views(torch, fl, s0.me_host[0]) for fl in self.e_me_flat]
+            self.e_in_flat = [dev(s0.in_flat[0].numel(), torch.uint8) for _ in range(F + 4)]
+            ins = [flat_views(torch, fl, s0.src_host[0][1:] + s0.pred_host[0]) for fl in self.e_in_flat]
+            self.e_src = [[None] + v[:2] for v in ins]  # luma comes from the ME plane
+            self.e_pred = [v[2:] for v in ins]
+            self.e_mi, self.e_skip = torch.empty_like(d_mi), torch.empty_like(d_skip)
+            self.e_idx = [dev(nfb, torch.int8) for _ in range(F)]
+            self.h_idx = [torch.zeros(nfb, dtype=torch.int8).pin_memory() for _ in range(F)]
+            self.d_pack = [{ts: torch.empty_like(self.d_q[i][ts]) for ts in tus} for i in range(F)]
+            self.h_pack = [{ts: pinned(self.d_q[i][ts].numel(), torch.int32) for ts in tus} for i in range(F)]
+            # small urgent read-back: CDEF mse table + the three packed sizes
+            like_fast = [torch.empty(2 * nfb * 64, dtype=torch.int64), torch.empty(4, dtype=torch.int32)]
+            # bulk read-back of the front half: MeSbResults, eobs, level offsets
+            like_bulk = ([torch.empty(n_sb * 85 * 7 * 2, dtype=torch.int16), torch.empty(n_sb * 85 * 23, dtype=torch.uint8),
+                          torch.empty(n_sb * 85, dtype=torch.uint8), torch.empty(n_sb, dtype=torch.int32)] +
+                         [torch.empty(len(tus[ts]), dtype=torch.int16) for ts in tus] +
+                         [torch.empty(len(tus[ts]) + 1, dtype=torch.int32) for ts in tus])
+            like_out = [torch.empty(t.shape, dtype=t.dtype) for t in s0.src_dev[0]]
+            nb = [flat_layout(x)[1] for x in (like_fast, like_bulk, like_out)]
+            self.d_fast_flat, self.h_fast_flat = [dev(nb[0], torch.uint8) for _ in range(F)], [pinned(nb[0], torch.uint8) for _ in range(F)]
+            self.d_bulk_flat, self.h_bulk_flat = [dev(nb[1], torch.uint8) for _ in range(F)], [pinned(nb[1], torch.uint8) for _ in range(F)]
+            self.d_out_flat, self.h_out_flat = [dev(nb[2], torch.uint8) for _ in range(F)], [pinned(nb[2], torch.uint8) for _ in range(F)]
+            self.e_mse, self.d_tot, self.h_mse, self.h_tot = [], [], [], []
+            self.e_me_out, self.e_eob, self.d_off, self.e_out = [], [], [], []
+            for i in range(F):
+                a, b = flat_views(torch, self.d_fast_flat[i], like_fast), flat_views(torch, self.h_fast_flat[i], like_fast)
+                self.e_mse.append(a[0]); self.d_tot.append(a[1]); self.h_mse.append(b[0]); self.h_tot.append(b[1])
+                v = flat_views(torch, self.d_bulk_flat[i], like_bulk)
+                o = dict(self.d_me[i])
+                o.update({"me_mv": v[0], "me_cand": v[1], "total_cand": v[2], "rc": v[3]})
+                self.e_me_out.append(o)
+                self.e_eob.append({ts: v[4 + j] for j, ts in enumerate(tus)})
+                self.d_off.append({ts: v[4 + len(tus) + j] for j, ts in enumerate(tus)})
+                self.e_out.append(flat_views(torch, self.d_out_flat[i], like_out))
+            self.done = []  # events: every stream's last operation on this instance
+
+    NB = 3  # three instances: step k's uploads wait for step k-3, whose last kernels sit BEFORE step k-1's front halves
+    bufs = [StepBuffers() for _ in range(NB)]
+    enc_scratch = dev(16384, torch.uint8)
 
     def planes(tl):
         return sb.MePlanes(tl[0].data_ptr(), tl[1].data_ptr(), tl[2].data_ptr())
 
     # Pictures are independent once their references are resident, so the mini-GOP is issued the way the reference's
     # picture-level pipeline would: NS pictures in flight, one CUDA stream each (kernel tails, copies and the host-side
-    # CDEF strength decision of one picture overlap the kernels of the others).
+    # CDEF strength decision of one picture overlap the kernels of the others).  Picture i always uses stream i % NS,
+    # so its buffers are ordered by the stream; steps are NOT separated by a barrier.
     NS = 4
     streams = [torch.cuda.Stream() for _ in range(NS)]
     sps = [C.c_void_p(st.cuda_stream) for st in streams]
     copy_stream = torch.cuda.Stream()
-    enc_scratch_s = [torch.empty(16384, dtype=torch.uint8, device="cuda") for _ in range(NS)]
-    e_idx = [torch.empty(nfb, dtype=torch.int8, device="cuda") for _ in range(F)]
-    h_idx_f = [torch.zeros(nfb, dtype=torch.int8).pin_memory() for _ in range(F)]
+    d2h_count = [0]
 
-    def frame_front(i, me_dev, src_dev, pred_dev, mi_dev, skip_dev, q, scratch):
-        """ME -> EncDec -> deblocking -> CDEF strength search of picture i on stream q."""
+    def e2e_src_frame(B, f):
+        y = B.e_me[f][0].data_ptr() + full_geo.origin_y * full_geo.stride + full_geo.origin_x
+        pd = proto.pad
+        cb, cr = (t.data_ptr() + pd * b.shape[1] + pd for t, b in zip(B.e_src[f][1:], proto.bufs[1:]))
+        return sb.Frame(y, cb, cr, full_geo.stride, proto.bufs[1].shape[1], proto.w, proto.h, proto.bd)
+
+    def frame_front(B, i, me_dev, src_dev, pred_dev, mi_dev, skip_dev, q, fs=None, pack=False):
+        """ME -> EncDec -> deblocking -> CDEF strength search of picture i on stream q (pack = the e2e arm: results
+        land in the read-back blocks)."""
         f = i + 2
-        fs, fp, fr = frame_struct(sb, proto, src_dev[f]), frame_struct(sb, proto, pred_dev[f]), frame_struct(sb, proto, d_rec[i])
+        if fs is None:
+            fs = frame_struct(sb, proto, src_dev[f])
+        fp, fr = frame_struct(sb, proto, pred_dev[f]), frame_struct(sb, proto, B.d_rec[i])
+        o_me, o_eob, o_mse = (B.e_me_out[i], B.e_eob[i], B.e_mse[i]) if pack else (B.d_me[i], B.d_eob[i], B.d_mse[i])
         r = [me_dev[f - 1], me_dev[f - 2], me_dev[f - 2], me_dev[f - 2], me_dev[f + 1], me_dev[f + 2], me_dev[f + 2], me_dev[f + 2]]
         refs = (sb.MePlanes * 8)(*[planes(x) for x in r])
         s = planes(me_dev[f])
-        o = d_me[i]
+        o = o_me
         outs = sb.MeOutputs(o["best_sad"].data_ptr(), o["best_mv"].data_ptr(), o["hme"].data_ptr(), o["me_mv"].data_ptr(),
                             o["me_cand"].data_ptr(), o["total_cand"].data_ptr(), o["rc"].data_ptr())
-        sb.check(lib.svt_b200_me_picture(C.byref(me_params), C.byref(s), refs, C.byref(outs), me_scratch[i].data_ptr(), q), lib)
+        sb.check(lib.svt_b200_me_picture(C.byref(me_params), C.byref(s), refs, C.byref(outs), B.me_scratch[i].data_ptr(), q), lib)
         for ts in tus:
             sb.check(lib.svt_b200_encode_tus(C.byref(enc_params[ts]), C.byref(fs), C.byref(fp), C.byref(fr),
-                                             C.c_void_p(tu_dev[ts].data_ptr()), len(tus[ts]), C.c_void_p(d_q[i][ts].data_ptr()),
-                                             C.c_void_p(d_eob[i][ts].data_ptr()), C.c_void_p(scratch.data_ptr()), q), lib)
+                                             C.c_void_p(tu_dev[ts].data_ptr()), len(tus[ts]), C.c_void_p(B.d_q[i][ts].data_ptr()),
+                                             C.c_void_p(o_eob[ts].data_ptr()), C.c_void_p(enc_scratch.data_ptr()), q), lib)
+            if pack:  # levels in scan order up to eob: what goes back to the host's entropy coder
+                sb.check(lib.svt_b200_pack_levels(ts, 0, C.c_void_p(B.d_q[i][ts].data_ptr()), C.c_void_p(o_eob[ts].data_ptr()),
+                                                  len(tus[ts]), C.c_void_p(B.d_pack[i][ts].data_ptr()), C.c_void_p(B.d_off[i][ts].data_ptr()),
+                                                  C.c_void_p(B.d_tot[i].data_ptr() + 4 * ts), q), lib)
         sb.check(lib.svt_b200_dlf_frame(C.byref(dlp), C.byref(fr), C.c_void_p(mi_dev.data_ptr()), q), lib)
         sb.check(lib.svt_b200_cdef_search(C.byref(csp), C.byref(fr), C.byref(fs), C.c_void_p(skip_dev.data_ptr()), skip8.shape[1],
-                                          C.c_void_p(d_mse[i].data_ptr()), q), lib)
+                                          C.c_void_p(o_mse.data_ptr()), q), lib)
 
-    def frame_back(i, skip_dev, idx_dev, q):
+    def frame_back(B, i, skip_dev, idx_dev, q, e2e=False):
         """CDEF apply of picture i with the per-filter-block strength indices in idx_dev."""
-        fr, fo = frame_struct(sb, proto, d_rec[i]), frame_struct(sb, proto, d_out[i])
+        fr, fo = frame_struct(sb, proto, B.d_rec[i]), frame_struct(sb, proto, B.e_out[i] if e2e else B.d_out[i])
         sb.check(lib.svt_b200_cdef_apply(C.byref(cap), C.byref(fr), C.byref(fo), C.c_void_p(skip_dev.data_ptr()), skip8.shape[1],
                                          C.c_void_p(idx_dev.data_ptr()), q), lib)
 
-    def fork():
-        ev = torch.cuda.Event()
-        ev.record(stream)
-        for st in streams + [copy_stream]:
-            st.wait_event(ev)
+    def all_streams():
+        return streams + [copy_stream, d2h_fast, d2h_bulk]
 
-    def join():
-        for st in streams + [copy_stream]:
+    def start_timing(e0):
+        e0.record(stream)
+        for st in all_streams():
+            st.wait_event(e0)
+
+    def end_timing(e1):
+        for st in all_streams():
             ev = torch.cuda.Event()
             ev.record(st)
             stream.wait_event(ev)
+        e1.record(stream)
 
     def hot_path(me_dev, src_dev, pred_dev, mi_dev, skip_dev, idx_dev, only=None):
         """Single-stream issue (per-stage timing)."""
+        B = bufs[0]
         for i in range(F):
             f = i + 2
-            fs, fp, fr = frame_struct(sb, proto, src_dev[f]), frame_struct(sb, proto, pred_dev[f]), frame_struct(sb, proto, d_rec[i])
-            fo = frame_struct(sb, proto, d_out[i])
+            fs, fp, fr = frame_struct(sb, proto, src_dev[f]), frame_struct(sb, proto, pred_dev[f]), frame_struct(sb, proto, B.d_rec[i])
+            fo = frame_struct(sb, proto, B.d_out[i])
             if only is not None:
                 stage_call(only, i, f, me_dev, fs, fp, fr, fo, mi_dev, skip_dev, idx_dev)
             else:
-                frame_front(i, me_dev, src_dev, pred_dev, mi_dev, skip_dev, sp, enc_scratch)
-                frame_back(i, skip_dev, idx_dev, sp)
+                frame_front(B, i, me_dev, src_dev, pred_dev, mi_dev, skip_dev, sp)
+                frame_back(B, i, skip_dev, idx_dev, sp)
 
     def stage_call(name, i, f, me_dev, fs, fp, fr, fo, mi_dev, skip_dev, idx_dev):
         """One stage of one frame (used by the per-stage roofline timing)."""
+        B = bufs[0]
         if name == "me":
             r = [me_dev[f - 1], me_dev[f - 2], me_dev[f - 2], me_dev[f - 2], me_dev[f + 1], me_dev[f + 2], me_dev[f + 2], me_dev[f + 2]]
             refs = (sb.MePlanes * 8)(*[planes(x) for x in r])
             s = planes(me_dev[f])
-            o = d_me[i]
+            o = B.d_me[i]
             outs = sb.MeOutputs(o["best_sad"].data_ptr(), o["best_mv"].data_ptr(), o["hme"].data_ptr(), o["me_mv"].data_ptr(),
                                 o["me_cand"].data_ptr(), o["total_cand"].data_ptr(), o["rc"].data_ptr())
-            sb.check(lib.svt_b200_me_picture(C.byref(me_params), C.byref(s), refs, C.byref(outs), me_scratch[i].data_ptr(), sp), lib)
+            sb.check(lib.svt_b200_me_picture(C.byref(me_params), C.byref(s), refs, C.byref(outs), B.me_scratch[i].data_ptr(), sp), lib)
         elif name == "encdec":
             for ts in tus:
                 sb.check(lib.svt_b200_encode_tus(C.byref(enc_params[ts]), C.byref(fs), C.byref(fp), C.byref(fr),
-                                                 C.c_void_p(tu_dev[ts].data_ptr()), len(tus[ts]), C.c_void_p(d_q[i][ts].data_ptr()),
-                                                 C.c_void_p(d_eob[i][ts].data_ptr()), C.c_void_p(enc_scratch.data_ptr()), sp), lib)
+                                                 C.c_void_p(tu_dev[ts].data_ptr()), len(tus[ts]), C.c_void_p(B.d_q[i][ts].data_ptr()),
+                                                 C.c_void_p(B.d_eob[i][ts].data_ptr()), C.c_void_p(enc_scratch.data_ptr()), sp), lib)
         elif name == "dlf":
             sb.check(lib.svt_b200_dlf_frame(C.byref(dlp), C.byref(fr), C.c_void_p(mi_dev.data_ptr()), sp), lib)
         elif name == "cdef_search":
             sb.check(lib.svt_b200_cdef_search(C.byref(csp), C.byref(fr), C.byref(fs), C.c_void_p(skip_dev.data_ptr()), skip8.shape[1],
-                                              C.c_void_p(d_mse[i].data_ptr()), sp), lib)
+                                              C.c_void_p(B.d_mse[i].data_ptr()), sp), lib)
         elif name == "cdef_apply":
             sb.check(lib.svt_b200_cdef_apply(C.byref(cap), C.byref(fr), C.byref(fo), C.c_void_p(skip_dev.data_ptr()), skip8.shape[1],
                                              C.c_void_p(idx_dev.data_ptr()), sp), lib)
 
-    def step_resident(k):
-        s = sets[k % RING]
-        fork()
+    def step_resident(k, last):
+        s, B = sets[k % RING], bufs[k % NB]
         for i in range(F):
             q = i % NS
-            frame_front(i, s.me_dev, s.src_dev, s.pred_dev, d_mi, d_skip, sps[q], enc_scratch_s[q])
-            frame_back(i, d_skip, d_idx, sps[q])
-        join()
+            frame_front(B, i, s.me_dev, s.src_dev, s.pred_dev, d_mi, d_skip, sps[q])
+            frame_back(B, i, d_skip, d_idx, sps[q])
 
-    def step_e2e(k):
-        s = sets[k % RING]
-        fork()
-        # H2D: the ME planes of the F+4 pictures (shared by neighbouring pictures) on the copy stream, in display order
-        me_ready = []
+    pending = {}
+
+    dbg = {"front": 0.0, "wait": 0.0, "back": 0.0} if os.environ.get("BENCH_DEBUG") else None
+    timeline = {}
+    d2h_fast, d2h_bulk = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def e2e_front(k):
+        """Uploads + front halves (up to the CDEF strength search) of every picture of step k.  Copies never sit on a
+        compute stream: uploads on the copy stream, the small urgent read-back (CDEF table + packed sizes) and the bulk
+        read-back on their own streams, tied to the kernels by events."""
+        s, B = sets[k % RING], bufs[k % NB]
+        for st in all_streams():  # the instance was last used by step k-NB
+            for ev in B.done:
+                st.wait_event(ev)
+        me_ready, in_ready = [], []
         with torch.cuda.stream(copy_stream):
-            e_mi.copy_(h_mi, non_blocking=True)
-            e_skip.copy_(h_skip, non_blocking=True)
-            for j in range(F + 4):
-                for a, b in zip(e_me[j], s.me_host[j]):
-                    a.copy_(b, non_blocking=True)
+            B.e_mi.copy_(h_mi, non_blocking=True)
+            B.e_skip.copy_(h_skip, non_blocking=True)
+            for j in range(F + 4):  # ME planes of the F+4 pictures (shared by neighbouring pictures), display order
+                B.e_me_flat[j].copy_(s.me_flat[j], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(copy_stream)
                 me_ready.append(ev)
+                i = j - 4  # picture i needs ME pictures i .. i+4: its chroma / prediction planes follow picture i+4
+                if i >= 0:
+                    f = i + 2
+                    B.e_in_flat[f].copy_(s.in_flat[f], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(copy_stream)
+                    in_ready.append(ev)
         mse_ready = []
+        tl = timeline.setdefault(k, {}) if dbg is not None else None
+        if tl is not None:
+            tl["h2d_end"] = torch.cuda.Event(enable_timing=True)
+            tl["h2d_end"].record(copy_stream)
         for i in range(F):
             q, f = i % NS, i + 2
-            with torch.cuda.stream(streams[q]):
-                for a, b in zip(e_src[f], s.src_host[f]):
-                    a.copy_(b, non_blocking=True)
-                for a, b in zip(e_pred[f], s.pred_host[f]):
-                    a.copy_(b, non_blocking=True)
-            streams[q].wait_event(me_ready[f + 2])
-            frame_front(i, e_me, e_src, e_pred, e_mi, e_skip, sps[q], enc_scratch_s[q])
-            with torch.cuda.stream(streams[q]):
-                h_mse[i].copy_(d_mse[i], non_blocking=True)
+            streams[q].wait_event(in_ready[i])
+            if tl is not None:
+                tl["fs%d" % i] = torch.cuda.Event(enable_timing=True)
+                tl["fs%d" % i].record(streams[q])
+            frame_front(B, i, B.e_me, B.e_src, B.e_pred, B.e_mi, B.e_skip, sps[q], fs=e2e_src_frame(B, f), pack=True)
+            done = torch.cuda.Event(enable_timing=dbg is not None)
+            done.record(streams[q])
+            if tl is not None:
+                tl["fe%d" % i] = done
+            d2h_fast.wait_event(done)
+            with torch.cuda.stream(d2h_fast):
+                B.h_fast_flat[i].copy_(B.d_fast_flat[i], non_blocking=True)  # CDEF mse table + packed sizes
                 ev = torch.cuda.Event()
-                ev.record(streams[q])
+                ev.record(d2h_fast)
                 mse_ready.append(ev)
-                # results that do not depend on the CDEF decision go home while the host decides
-                for kk, t in h_me[i].items():
-                    t.copy_(d_me[i][kk], non_blocking=True)
-                for ts in tus:
-                    h_q[i][ts].copy_(d_q[i][ts], non_blocking=True)
-                    h_eob[i][ts].copy_(d_eob[i][ts], non_blocking=True)
+            d2h_bulk.wait_event(done)
+            with torch.cuda.stream(d2h_bulk):  # MeSbResults, eobs, level offsets: independent of the CDEF decision
+                B.h_bulk_flat[i].copy_(B.d_bulk_flat[i], non_blocking=True)
+        pending[k] = mse_ready
+
+
+    def step_e2e(k, last):
+        t0 = time.perf_counter()
+        if k not in pending:
+            e2e_front(k)
+        if not last:
+            e2e_front(k + 1)  # keep the GPU fed while the host decides the CDEF strengths of step k
+        if dbg is not None:
+            dbg["front"] += time.perf_counter() - t0
+        B = bufs[k % NB]
+        mse_ready = pending.pop(k)
+        packed = 0
         for i in range(F):
             q = i % NS
-            mse_ready[i].synchronize()
+            t1 = time.perf_counter()
+            while not mse_ready[i].query():  # spin: an event wait that sleeps costs a wake-up latency per picture
+                pass
+            if dbg is not None:
+                dbg["wait"] += time.perf_counter() - t1
+                dbg.setdefault("wait_by_frame", [0.0] * F)[i] += time.perf_counter() - t1
             # stand-in for finish_cdef_search (host side, out of scope §8a): best of the first 8 strengths per block
-            m = h_mse[i].numpy().view(np.uint64).reshape(2, nfb, 64)
-            h_idx_f[i].numpy()[...] = np.argmin(m[0, :, :8], axis=1).astype(np.int8)
+            m = B.h_mse[i].numpy().view(np.uint64).reshape(2, nfb, 64)
+            B.h_idx[i].numpy()[...] = np.argmin(m[0, :, :8], axis=1).astype(np.int8)
             with torch.cuda.stream(streams[q]):
-                e_idx[i].copy_(h_idx_f[i], non_blocking=True)
-            frame_back(i, e_skip, e_idx[i], sps[q])
-            with torch.cuda.stream(streams[q]):
-                for a, b in zip(h_out[i], d_out[i]):
-                    a.copy_(b, non_blocking=True)
-        join()
+                B.e_idx[i].copy_(B.h_idx[i], non_blocking=True)
+            frame_back(B, i, B.e_skip, B.e_idx[i], sps[q], e2e=True)
+            done = torch.cuda.Event(enable_timing=dbg is not None)
+            done.record(streams[q])
+            if dbg is not None:
+                timeline[k]["be%d" % i] = done
+            d2h_bulk.wait_event(done)
+            with torch.cuda.stream(d2h_bulk):
+                for ts in tus:  # the packed levels: their size came back with the CDEF table
+                    n = int(B.h_tot[i][ts])
+                    if n:
+                        B.h_pack[i][ts][:n].copy_(B.d_pack[i][ts][:n], non_blocking=True)
+                    packed += 4 * n
+                B.h_out_flat[i].copy_(B.d_out_flat[i], non_blocking=True)
+        d2h_count[0] = packed
+        if dbg is not None:
+            dbg["back"] = dbg["back"] + (time.perf_counter() - t0)
+            print("e2e host seconds (cumulative): %s" % dbg, file=sys.stderr)
+        B.done = []
+        for st in all_streams():
+            ev = torch.cuda.Event()
+            ev.record(st)
+            B.done.append(ev)
 
-    h2d = (sum(t.numel() * t.element_size() for t in sets[0].me_host[0]) * (F + 4) +
-           2 * F * sum(t.numel() * t.element_size() for t in sets[0].src_host[0]) + h_mi.numel() + h_skip.numel() + F * nfb)
-    d2h = F * (sum(t.numel() * t.element_size() for t in h_me[0].values()) + sum(t.numel() * 4 for t in h_q[0].values()) +
-               sum(t.numel() * 2 for t in h_eob[0].values()) + h_mse[0].numel() * 8 + sum(t.numel() * t.element_size() for t in h_out[0]))
+    B0 = bufs[0]
+    h2d = sets[0].me_flat[0].numel() * (F + 4) + sets[0].in_flat[0].numel() * F + h_mi.numel() + h_skip.numel() + F * nfb
+
+    def d2h_bytes():  # the fixed-size read-back blocks + the packed levels of the last e2e step
+        return F * (B0.h_fast_flat[0].numel() + B0.h_bulk_flat[0].numel() + B0.h_out_flat[0].numel()) + d2h_count[0]
 
     def barrier():
         if world > 1:
@@ -494,14 +649,14 @@ def run_b200(args):
 
     def timed(fn, steps, warmup):
         for k in range(warmup):
-            fn(k)
+            fn(k, k == warmup - 1)
         barrier()
         l0 = lib.svt_b200_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
+        start_timing(e0)
         for k in range(steps):
-            fn(warmup + k)
-        e1.record(stream)
+            fn(warmup + k, k == steps - 1)
+        end_timing(e1)
         barrier()
         ms = e0.elapsed_time(e1)
         launches = lib.svt_b200_launch_count() - l0
@@ -512,6 +667,14 @@ def run_b200(args):
     sampler.start()
     ms, launches = timed(step_resident, args.steps, args.warmup)
     ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    if dbg is not None:
+        ks = sorted(timeline)
+        base = timeline[ks[-3]]["h2d_end"]
+        for kk in ks[-3:]:
+            tl = timeline[kk]
+            print("step %d GPU timeline (ms after step %d's uploads ended): h2d_end %.2f | " % (kk, ks[-3], base.elapsed_time(tl["h2d_end"])) +
+                  " ".join("f%d[%.2f-%.2f]b%.2f" % (i, base.elapsed_time(tl["fs%d" % i]), base.elapsed_time(tl["fe%d" % i]),
+                                                    base.elapsed_time(tl["be%d" % i])) for i in range(F)), file=sys.stderr)
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -523,7 +686,7 @@ def run_b200(args):
     line = {"metric": METRIC, "value": frames / (ms / 1e3), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic", "config": workload_config(F), "clocks": sampler.summary(),
-            "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "e2e": {"value": frames / (ms_e2e / 1e3), "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_bytes())},
             "gpu_launches": int(launches), "roofline": roof, "stage_ms_per_frame": stage_ms}
     if rank == 0:
         if world == 1 and not args.no_cpu:

@@ -408,6 +408,13 @@ SVT_B200_API int svt_b200_encode_tus(const SvtB200EncodeParams *p, const SvtB200
                                      const SvtB200Frame *pred, const SvtB200Frame *recon,
                                      const SvtB200Tu *tus, int32_t n_tus, int32_t *qcoeff, uint16_t *eob,
                                      void *scratch, void *stream);
+/* Device -> host hand-over of the levels: the entropy coder reads a TU's levels in scan order up to eob
+ * (av1_write_coeffs_txb_1d), so instead of n int32 per TU the host can fetch `packed` = the eob[b] levels of TU b in scan
+ * order at packed[offsets[b] .. offsets[b+1]) (offsets: exclusive prefix sum of eob, n_tus + 1 entries; *total = the
+ * sum).  tx_class selects the scan: 0 default, 1 mrow (V_* types), 2 mcol (H_* types) — a call covers TUs of one class.
+ * All pointers are device pointers; packed must hold n_tus * min(w,32) * min(h,32) entries in the worst case. */
+SVT_B200_API int svt_b200_pack_levels(int32_t tx_size, int32_t tx_class, const int32_t *qcoeff, const uint16_t *eob,
+                                      int32_t n_tus, int32_t *packed, uint32_t *offsets, uint32_t *total, void *stream);
 /* Same, plus cul_level[n_tus] (device int32, may be NULL): the value av1_quantize_inv_quantize returns
  * (EbFullLoop.c:1596-1608): min(63, sum |qcoeff|) with set_dc_sign of the DC level (bit 6 negative, +128 positive). */
 SVT_B200_API int svt_b200_encode_tus_cul(const SvtB200EncodeParams *p, const SvtB200Frame *src,

@@ -482,6 +482,46 @@ __global__ void __launch_bounds__(TX_NT) encode_tu_kernel(const __grid_constant_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Level packing for the device -> host hand-over: the entropy coder reads a TU's levels in scan order up to eob, and
+// after quantisation most of a TU is zero, so the D2H stream is "eob levels per TU in scan order" + offsets instead
+// of n int32 per TU (at qindex ~170 that is > 10x fewer bytes; D2H of the raster int32 blocks bounded the end-to-end
+// rate).  Two launches: exclusive scan of eob (one CTA; <= 32 K TUs per call is far above a 4K frame's count per
+// transform size), then the gather.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) eob_scan_kernel(const uint16_t *eob, int n, uint32_t *offsets /*[n+1]*/, uint32_t *total) {
+    __shared__ uint32_t s_part[1024];
+    const int per = (n + 1023) / 1024, t = threadIdx.x;
+    uint32_t sum = 0;
+    for (int i = t * per; i < min(n, (t + 1) * per); i++) sum += eob[i];
+    s_part[t] = sum;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) { // Hillis-Steele inclusive scan of the 1024 partial sums
+        const uint32_t v = t >= o ? s_part[t - o] : 0;
+        __syncthreads();
+        s_part[t] += v;
+        __syncthreads();
+    }
+    uint32_t run = t ? s_part[t - 1] : 0;
+    for (int i = t * per; i < min(n, (t + 1) * per); i++) {
+        offsets[i] = run;
+        run += eob[i];
+    }
+    if (t == 1023) {
+        offsets[n] = s_part[1023];
+        *total = s_part[1023];
+    }
+}
+__global__ void __launch_bounds__(256) pack_levels_kernel(const int32_t *qcoeff, const uint16_t *eob, const uint32_t *offsets,
+                                                          const int16_t *scan, int n_tus, int n, int32_t *out) {
+    const int b = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31; // one warp per TU
+    if (b >= n_tus) return;
+    const int e = eob[b];
+    const int32_t *q = qcoeff + (size_t)b * n;
+    int32_t *o = out + offsets[b];
+    for (int i = lane; i < e; i += 32) o[i] = q[scan[i]];
+}
+
 static size_t tx_smem_bytes(int tx_size) {
     const int w = h_txw[tx_size], h = h_txh[tx_size];
     const int T = w > h ? w : h, bpc = TX_NT / T;
@@ -854,21 +894,52 @@ int svt_b200_get_scan(int tx_size, int tx_type, int16_t *scan_out) {
 
 } // extern "C"
 namespace {
+const int16_t *scan_tables(int tx_size);
+}
+extern "C" {
+// see include/svt_av1_b200.h
+int svt_b200_pack_levels(int32_t tx_size, int32_t tx_class, const int32_t *qcoeff, const uint16_t *eob, int32_t n_tus, int32_t *packed,
+                         uint32_t *offsets, uint32_t *total, void *stream) {
+    if (tx_size < 0 || tx_size > 18 || tx_class < 0 || tx_class > 2 || !qcoeff || !eob || !packed || !offsets || !total || n_tus < 0 ||
+        n_tus > (1 << 20)) {
+        set_error("svt_b200_pack_levels: bad argument");
+        return SVT_B200_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_tus == 0) {
+        SVTB_CUDA_TRY(cudaMemsetAsync(total, 0, 4, st));
+        SVTB_CUDA_TRY(cudaMemsetAsync(offsets, 0, 4, st));
+        return SVT_B200_OK;
+    }
+    const int16_t *tab = scan_tables(tx_size);
+    if (!tab) return SVT_B200_ERR_CUDA;
+    const int n = (h_txw[tx_size] > 32 ? 32 : h_txw[tx_size]) * (h_txh[tx_size] > 32 ? 32 : h_txh[tx_size]);
+    SVTB_LAUNCH(eob_scan_kernel, 1, 1024, 0, st, eob, n_tus, offsets, total);
+    SVTB_LAUNCH(pack_levels_kernel, (n_tus + 7) / 8, 256, 0, st, qcoeff, eob, offsets, tab + 3072 + tx_class * 1024, n_tus, n, packed);
+    SVTB_CUDA_TRY(cudaGetLastError());
+    return SVT_B200_OK;
+}
+
+} // extern "C"
+namespace {
 // device-resident inverse scan tables: [device][tx_size] -> 3 x 1024 int16
-const int16_t *iscan_tables(int tx_size) {
+const int16_t *scan_tables(int tx_size) { // [3][1024] inverse scans, then [3][1024] forward scans
     static std::mutex mu;
     static int16_t *tabs[64][19] = {};
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64) return nullptr;
     std::lock_guard<std::mutex> lk(mu);
     if (tabs[dev][tx_size]) return tabs[dev][tx_size];
-    static int16_t hs[1024], hi[3][1024];
+    static int16_t hs[1024], hi[6][1024];
     const int types[3] = {0, 10, 11}; // DCT_DCT (default scan), V_DCT (mrow), H_DCT (mcol)
     const int n = (h_txw[tx_size] > 32 ? 32 : h_txw[tx_size]) * (h_txh[tx_size] > 32 ? 32 : h_txh[tx_size]);
     for (int k = 0; k < 3; k++) {
         svt_b200_get_scan(tx_size, types[k], hs);
-        for (int i = 0; i < 1024; i++) hi[k][i] = 0;
-        for (int i = 0; i < n; i++) hi[k][hs[i]] = (int16_t)i;
+        for (int i = 0; i < 1024; i++) hi[k][i] = hi[3 + k][i] = 0;
+        for (int i = 0; i < n; i++) {
+            hi[k][hs[i]] = (int16_t)i;
+            hi[3 + k][i] = hs[i];
+        }
     }
     int16_t *dp = nullptr;
     if (cudaMalloc(&dp, sizeof(hi)) != cudaSuccess) return nullptr;
@@ -926,7 +997,7 @@ int svt_b200_encode_tus_cul(const SvtB200EncodeParams *p, const SvtB200Frame *sr
     d.cul_level = cul_level;
     // inverse scan tables of this size: built once per (device, tx_size) and kept resident (`scratch` is unused since
     // then; the parameter stays for ABI stability)
-    const int16_t *tab = iscan_tables(p->tx_size);
+    const int16_t *tab = scan_tables(p->tx_size);
     if (!tab) return SVT_B200_ERR_CUDA;
     for (int i = 0; i < 3; i++) d.iscan[i] = tab + i * 1024;
     cudaStream_t st = (cudaStream_t)stream;

@@ -256,3 +256,37 @@ def test_partial_frequency_dropins(tx_size):
             orc.orc_fwd_txfm2d_pf(cm.ptr(res), cm.ptr(want), C.c_uint32(w + 5), tx_type, tx_size, 10, sh)
             f(cm.ptr(res), cm.ptr(got), C.c_uint32(w + 5), tx_type, C.c_uint8(10))
             np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("tx_size,tx_class", [(0, 0), (1, 0), (2, 0), (2, 1), (3, 2), (4, 0), (9, 0), (12, 0)])
+def test_pack_levels(tx_size, tx_class):
+    """svt_b200_pack_levels: the eob levels of every TU in scan order + exclusive offsets, vs numpy."""
+    import torch
+    lib = sb.load()
+    rng = np.random.default_rng(300 + tx_size)
+    n = min(TX_W[tx_size], 32) * min(TX_H[tx_size], 32)
+    scan = np.zeros(1024, np.int16)
+    assert lib.svt_b200_get_scan(tx_size, {0: 0, 1: 10, 2: 11}[tx_class], cm.ptr(scan)) >= 0
+    n_tus = 2500
+    q = np.zeros((n_tus, n), np.int32)
+    eob = np.zeros(n_tus, np.uint16)
+    for b in range(n_tus):
+        e = int(rng.integers(0, n + 1)) if b % 3 else int(rng.integers(0, 4))
+        eob[b] = e
+        lv = rng.integers(-300, 301, e)
+        if e:
+            lv[-1] = lv[-1] or 1
+        q[b, scan[:e]] = lv
+    dq, de = torch.from_numpy(q).cuda(), torch.from_numpy(eob.view(np.int16)).cuda()
+    packed = torch.zeros(n_tus * n, dtype=torch.int32, device="cuda")
+    off = torch.zeros(n_tus + 1, dtype=torch.int32, device="cuda")
+    tot = torch.zeros(1, dtype=torch.int32, device="cuda")
+    sb.check(lib.svt_b200_pack_levels(tx_size, tx_class, C.c_void_p(dq.data_ptr()), C.c_void_p(de.data_ptr()), n_tus,
+                                      C.c_void_p(packed.data_ptr()), C.c_void_p(off.data_ptr()), C.c_void_p(tot.data_ptr()), None), lib)
+    torch.cuda.synchronize()
+    want_off = np.concatenate([[0], np.cumsum(eob.astype(np.int64))])
+    np.testing.assert_array_equal(off.cpu().numpy(), want_off)
+    assert int(tot.item()) == want_off[-1]
+    got = packed.cpu().numpy()
+    for b in range(0, n_tus, 7):
+        np.testing.assert_array_equal(got[want_off[b]:want_off[b + 1]], q[b, scan[:eob[b]]])
