@@ -438,38 +438,48 @@ def run_b200(args):
         cb, cr = (t.data_ptr() + pd * b.shape[1] + pd for t, b in zip(B.e_src[f][1:], proto.bufs[1:]))
         return sb.Frame(y, cb, cr, full_geo.stride, proto.bufs[1].shape[1], proto.w, proto.h, proto.bd)
 
-    def frame_front(B, i, me_dev, src_dev, pred_dev, mi_dev, skip_dev, q, fs=None, pack=False):
+    arg_cache = {}  # ctypes argument blocks per (buffer set, input set, picture): pointers never change between steps
+
+    def frame_front(B, i, me_dev, src_dev, pred_dev, mi_dev, skip_dev, q, fs_fn=None, pack=False):
         """ME -> EncDec -> deblocking -> CDEF strength search of picture i on stream q (pack = the e2e arm: results
         land in the read-back blocks)."""
-        f = i + 2
-        if fs is None:
-            fs = frame_struct(sb, proto, src_dev[f])
-        fp, fr = frame_struct(sb, proto, pred_dev[f]), frame_struct(sb, proto, B.d_rec[i])
-        o_me, o_eob, o_mse = (B.e_me_out[i], B.e_eob[i], B.e_mse[i]) if pack else (B.d_me[i], B.d_eob[i], B.d_mse[i])
-        r = [me_dev[f - 1], me_dev[f - 2], me_dev[f - 2], me_dev[f - 2], me_dev[f + 1], me_dev[f + 2], me_dev[f + 2], me_dev[f + 2]]
-        refs = (sb.MePlanes * 8)(*[planes(x) for x in r])
-        s = planes(me_dev[f])
-        o = o_me
-        outs = sb.MeOutputs(o["best_sad"].data_ptr(), o["best_mv"].data_ptr(), o["hme"].data_ptr(), o["me_mv"].data_ptr(),
-                            o["me_cand"].data_ptr(), o["total_cand"].data_ptr(), o["rc"].data_ptr())
-        sb.check(lib.svt_b200_me_picture(C.byref(me_params), C.byref(s), refs, C.byref(outs), B.me_scratch[i].data_ptr(), q), lib)
-        for ts in tus:
-            sb.check(lib.svt_b200_encode_tus(C.byref(enc_params[ts]), C.byref(fs), C.byref(fp), C.byref(fr),
-                                             C.c_void_p(tu_dev[ts].data_ptr()), len(tus[ts]), C.c_void_p(B.d_q[i][ts].data_ptr()),
-                                             C.c_void_p(o_eob[ts].data_ptr()), C.c_void_p(enc_scratch.data_ptr()), q), lib)
+        key = (id(B), id(me_dev), i, pack)
+        a = arg_cache.get(key)
+        if a is None:
+            f = i + 2
+            fs = fs_fn(B, f) if fs_fn else frame_struct(sb, proto, src_dev[f])
+            fp, fr = frame_struct(sb, proto, pred_dev[f]), frame_struct(sb, proto, B.d_rec[i])
+            o, o_eob, o_mse = (B.e_me_out[i], B.e_eob[i], B.e_mse[i]) if pack else (B.d_me[i], B.d_eob[i], B.d_mse[i])
+            r = [me_dev[f - 1], me_dev[f - 2], me_dev[f - 2], me_dev[f - 2], me_dev[f + 1], me_dev[f + 2], me_dev[f + 2], me_dev[f + 2]]
+            refs = (sb.MePlanes * 8)(*[planes(x) for x in r])
+            s = planes(me_dev[f])
+            outs = sb.MeOutputs(o["best_sad"].data_ptr(), o["best_mv"].data_ptr(), o["hme"].data_ptr(), o["me_mv"].data_ptr(),
+                                o["me_cand"].data_ptr(), o["total_cand"].data_ptr(), o["rc"].data_ptr())
+            enc = [(C.byref(enc_params[ts]), C.c_void_p(tu_dev[ts].data_ptr()), len(tus[ts]), C.c_void_p(B.d_q[i][ts].data_ptr()),
+                    C.c_void_p(o_eob[ts].data_ptr()), ts, C.c_void_p(B.d_pack[i][ts].data_ptr()), C.c_void_p(B.d_off[i][ts].data_ptr()),
+                    C.c_void_p(B.d_tot[i].data_ptr() + 4 * ts)) for ts in tus]
+            a = (fs, fp, fr, refs, s, outs, enc, B.me_scratch[i].data_ptr(), C.c_void_p(mi_dev.data_ptr()), C.c_void_p(skip_dev.data_ptr()),
+                 C.c_void_p(o_mse.data_ptr()), C.c_void_p(enc_scratch.data_ptr()))
+            arg_cache[key] = a
+        fs, fp, fr, refs, s, outs, enc, scr, mi_p, skip_p, mse_p, es_p = a
+        sb.check(lib.svt_b200_me_picture(C.byref(me_params), C.byref(s), refs, C.byref(outs), scr, q), lib)
+        for (ep, tu_p, n, q_p, eob_p, ts, pk_p, off_p, tot_p) in enc:
+            sb.check(lib.svt_b200_encode_tus(ep, C.byref(fs), C.byref(fp), C.byref(fr), tu_p, n, q_p, eob_p, es_p, q), lib)
             if pack:  # levels in scan order up to eob: what goes back to the host's entropy coder
-                sb.check(lib.svt_b200_pack_levels(ts, 0, C.c_void_p(B.d_q[i][ts].data_ptr()), C.c_void_p(o_eob[ts].data_ptr()),
-                                                  len(tus[ts]), C.c_void_p(B.d_pack[i][ts].data_ptr()), C.c_void_p(B.d_off[i][ts].data_ptr()),
-                                                  C.c_void_p(B.d_tot[i].data_ptr() + 4 * ts), q), lib)
-        sb.check(lib.svt_b200_dlf_frame(C.byref(dlp), C.byref(fr), C.c_void_p(mi_dev.data_ptr()), q), lib)
-        sb.check(lib.svt_b200_cdef_search(C.byref(csp), C.byref(fr), C.byref(fs), C.c_void_p(skip_dev.data_ptr()), skip8.shape[1],
-                                          C.c_void_p(o_mse.data_ptr()), q), lib)
+                sb.check(lib.svt_b200_pack_levels(ts, 0, q_p, eob_p, n, pk_p, off_p, tot_p, q), lib)
+        sb.check(lib.svt_b200_dlf_frame(C.byref(dlp), C.byref(fr), mi_p, q), lib)
+        sb.check(lib.svt_b200_cdef_search(C.byref(csp), C.byref(fr), C.byref(fs), skip_p, skip8.shape[1], mse_p, q), lib)
 
     def frame_back(B, i, skip_dev, idx_dev, q, e2e=False):
         """CDEF apply of picture i with the per-filter-block strength indices in idx_dev."""
-        fr, fo = frame_struct(sb, proto, B.d_rec[i]), frame_struct(sb, proto, B.e_out[i] if e2e else B.d_out[i])
-        sb.check(lib.svt_b200_cdef_apply(C.byref(cap), C.byref(fr), C.byref(fo), C.c_void_p(skip_dev.data_ptr()), skip8.shape[1],
-                                         C.c_void_p(idx_dev.data_ptr()), q), lib)
+        key = (id(B), "back", i, e2e, id(idx_dev))
+        a = arg_cache.get(key)
+        if a is None:
+            a = (frame_struct(sb, proto, B.d_rec[i]), frame_struct(sb, proto, B.e_out[i] if e2e else B.d_out[i]),
+                 C.c_void_p(skip_dev.data_ptr()), C.c_void_p(idx_dev.data_ptr()))
+            arg_cache[key] = a
+        fr, fo, skip_p, idx_p = a
+        sb.check(lib.svt_b200_cdef_apply(C.byref(cap), C.byref(fr), C.byref(fo), skip_p, skip8.shape[1], idx_p, q), lib)
 
     def all_streams():
         return streams + [copy_stream, d2h_fast, d2h_bulk]
@@ -572,7 +582,7 @@ def run_b200(args):
             if tl is not None:
                 tl["fs%d" % i] = torch.cuda.Event(enable_timing=True)
                 tl["fs%d" % i].record(streams[q])
-            frame_front(B, i, B.e_me, B.e_src, B.e_pred, B.e_mi, B.e_skip, sps[q], fs=e2e_src_frame(B, f), pack=True)
+            frame_front(B, i, B.e_me, B.e_src, B.e_pred, B.e_mi, B.e_skip, sps[q], fs_fn=e2e_src_frame, pack=True)
             done = torch.cuda.Event(enable_timing=dbg is not None)
             done.record(streams[q])
             if tl is not None:

@@ -232,6 +232,9 @@ SVT_B200_API void svt_cdef_filter_block_cuda(uint8_t *dst8, uint16_t *dst16, int
                                              int32_t sec_strength, int32_t dir, int32_t pri_damping,
                                              int32_t sec_damping, int32_t bsize, int32_t coeff_shift);
 
+/* replace svt_copy_rect8_8bit_to_16bit (common_dsp_rtcd.h:1036-1037; EbCdef.c:118-123): widening rectangle copy */
+SVT_B200_API void svt_copy_rect8_8bit_to_16bit_cuda(uint16_t *dst, int32_t dstride, const uint8_t *src, int32_t sstride,
+                                                    int32_t v, int32_t h);
 /* replace svt_compute_cdef_dist_16bit / _8bit (aom_dsp_rtcd.h:67-70; compute_cdef_dist_c / _8bit_c, EbEncCdef.c:134-220):
  * distortion of the filtered blocks of one filter block against the packed source blocks (luma 8x8: the perceptual
  * double-precision measure; otherwise SSE), >> 2*coeff_shift.  dlist: the reference's CdefList array {by, bx, skip}.
@@ -631,6 +634,14 @@ SVT_B200_API int64_t svt_av1_highbd_pixel_proj_error_cuda(const uint8_t *src8, i
                                                           int32_t src_stride, const uint8_t *dat8, int32_t dat_stride,
                                                           int32_t *flt0, int32_t flt0_stride, int32_t *flt1,
                                                           int32_t flt1_stride, int32_t xq[2], const void *params);
+/* replace svt_get_proj_subspace (aom_dsp_rtcd.h:219-220; EbRestorationPick.c:337-440): the projection coefficients xq[2]
+ * of the self-guided filter.  The five sums are exact 64-bit integer reductions on the device (the reference's double
+ * accumulations are exact too: integer terms, partial sums < 2^53); the 2x2 solve repeats the reference's double
+ * expressions on the host. */
+SVT_B200_API void svt_get_proj_subspace_cuda(const uint8_t *src8, int32_t width, int32_t height, int32_t src_stride,
+                                             const uint8_t *dat8, int32_t dat_stride, int32_t use_highbitdepth,
+                                             int32_t *flt0, int32_t flt0_stride, int32_t *flt1, int32_t flt1_stride,
+                                             int32_t *xq, const void *params);
 /* The compute_stats calls of search_wiener for every restoration unit of one plane in three launches, pictures resident
  * on the device.  rects: DEVICE int32 [n_units][4] = {h_start, h_end, v_start, v_end} (RestorationTileLimits); reads of
  * dgd outside the plane are clamped (= the 3-sample replicated border the reference extends the picture by);

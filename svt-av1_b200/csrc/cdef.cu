@@ -12,6 +12,8 @@
 // of once per strength.  A thread owns one row of one 8x8 (or 4x4 chroma) block; block sums for the
 // distortion are reduced with 8-lane shuffles.  The 8x8 luma distortion keeps the reference's double formula
 // with explicit round-to-nearest intrinsics (no FMA contraction) so it is bit-identical (0 ULP).
+#include <algorithm>
+
 #include "common.cuh"
 
 using namespace svtb200;
@@ -903,6 +905,9 @@ uint64_t cdef_dist_dropin(const void *dst, int hbd, int dstride, const void *src
     return v >> (2 * coeff_shift);
 }
 
+__global__ void copy_rect8_kernel(uint16_t *dst, const uint8_t *src, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
 } // namespace
 
 extern "C" {
@@ -1044,5 +1049,18 @@ uint64_t svt_compute_cdef_dist_16bit_cuda(const uint16_t *dst, int32_t dstride, 
 uint64_t svt_compute_cdef_dist_8bit_cuda(const uint8_t *dst8, int32_t dstride, const uint8_t *src8, const void *dlist,
                                          int32_t cdef_count, int32_t bsize, int32_t coeff_shift, int32_t pli) {
     return cdef_dist_dropin(dst8, 0, dstride, src8, dlist, cdef_count, bsize, coeff_shift, pli);
+}
+
+void svt_copy_rect8_8bit_to_16bit_cuda(uint16_t *dst, int32_t dstride, const uint8_t *src, int32_t sstride, int32_t v, int32_t h) {
+    if (v <= 0 || h <= 0) return;
+    ThreadCtx &c = tls();
+    const size_t n = (size_t)v * h, in_b = (n + 15) & ~(size_t)15;
+    c.reserve(in_b + 2 * n);
+    for (int i = 0; i < v; i++) memcpy(c.h + (size_t)i * h, src + (size_t)i * sstride, (size_t)h);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.d, c.h, n, cudaMemcpyHostToDevice, c.stream));
+    SVTB_LAUNCH(copy_rect8_kernel, (int)std::min<size_t>(64, (n + 255) / 256), 256, 0, c.stream, (uint16_t *)(c.d + in_b), (const uint8_t *)c.d, (int)n);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h + in_b, c.d + in_b, 2 * n, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_FATAL(cudaStreamSynchronize(c.stream));
+    for (int i = 0; i < v; i++) memcpy(dst + (size_t)i * dstride, c.h + in_b + (size_t)i * h * 2, (size_t)h * 2);
 }
 }

@@ -280,6 +280,87 @@ int64_t proj_dropin(const void *src, int width, int height, int src_stride, cons
     return v;
 }
 
+// svt_get_proj_subspace_c (EbRestorationPick.c:337-440): the five sums over the unit.  The reference accumulates them
+// in double, but every term is an integer (u, s, f1, f2 are integers) and every partial sum stays below 2^53, so the
+// double sums are exact and equal these 64-bit integer sums; the 2x2 solve below repeats the reference's expressions.
+__global__ void __launch_bounds__(256) proj_sums_kernel(const ProjArgs a, long long *out /*[5]: H00 H11 H01 C0 C1*/) {
+    long long h00 = 0, h11 = 0, h01 = 0, c0 = 0, c1 = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.w * a.h; i += gridDim.x * blockDim.x) {
+        const int y = i / a.w, x = i - y * a.w;
+        const int sv = a.hbd ? ((const uint16_t *)a.src)[(size_t)y * a.src_stride + x] : ((const uint8_t *)a.src)[(size_t)y * a.src_stride + x];
+        const int dv = a.hbd ? ((const uint16_t *)a.dat)[(size_t)y * a.dat_stride + x] : ((const uint8_t *)a.dat)[(size_t)y * a.dat_stride + x];
+        const long long u = dv << 4, s = (long long)(sv << 4) - u;
+        const long long f1 = a.r0 > 0 ? (long long)a.flt0[(size_t)y * a.f0s + x] - u : 0;
+        const long long f2 = a.r1 > 0 ? (long long)a.flt1[(size_t)y * a.f1s + x] - u : 0;
+        h00 += f1 * f1, h11 += f2 * f2, h01 += f1 * f2, c0 += f1 * s, c1 += f2 * s;
+    }
+    long long v[5] = {h00, h11, h01, c0, c1};
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if ((threadIdx.x & 31) == 0 && v[k]) atomicAdd(reinterpret_cast<unsigned long long *>(out + k), (unsigned long long)v[k]);
+    }
+}
+
+void proj_subspace_dropin(const void *src, int width, int height, int src_stride, const void *dat, int dat_stride, int hbd,
+                          const int32_t *flt0, int f0s, const int32_t *flt1, int f1s, int *xq, const int32_t *params) {
+    xq[0] = xq[1] = 0;
+    if (width <= 0 || height <= 0) return;
+    const int es = hbd ? 2 : 1, r0 = params[0], r1 = params[1];
+    ThreadCtx &c = tls();
+    const size_t pb = ((size_t)width * height * es + 15) & ~(size_t)15, fb = (size_t)width * height * 4;
+    c.reserve(2 * pb + 2 * fb + 64);
+    for (int y = 0; y < height; y++) {
+        memcpy(c.h + (size_t)y * width * es, (const uint8_t *)src + (size_t)y * src_stride * es, (size_t)width * es);
+        memcpy(c.h + pb + (size_t)y * width * es, (const uint8_t *)dat + (size_t)y * dat_stride * es, (size_t)width * es);
+        if (r0 > 0) memcpy(c.h + 2 * pb + (size_t)y * width * 4, flt0 + (size_t)y * f0s, (size_t)width * 4);
+        if (r1 > 0) memcpy(c.h + 2 * pb + fb + (size_t)y * width * 4, flt1 + (size_t)y * f1s, (size_t)width * 4);
+    }
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.d, c.h, 2 * pb + 2 * fb, cudaMemcpyHostToDevice, c.stream));
+    ProjArgs a;
+    a.src = c.d;
+    a.dat = c.d + pb;
+    a.flt0 = (const int32_t *)(c.d + 2 * pb);
+    a.flt1 = (const int32_t *)(c.d + 2 * pb + fb);
+    a.w = width, a.h = height, a.src_stride = a.dat_stride = a.f0s = a.f1s = width;
+    a.xq0 = a.xq1 = 0, a.r0 = r0, a.r1 = r1, a.hbd = hbd;
+    a.out = nullptr;
+    long long *d_out = (long long *)(c.d + 2 * pb + 2 * fb);
+    SVTB_CUDA_FATAL(cudaMemsetAsync(d_out, 0, 40, c.stream));
+    SVTB_LAUNCH(proj_sums_kernel, std::min(64, (width * height + 255) / 256), 256, 0, c.stream, a, d_out);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h, d_out, 40, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_FATAL(cudaStreamSynchronize(c.stream));
+    long long v[5];
+    memcpy(v, c.h, 40);
+    const int size = width * height;
+    double H[2][2], C[2], det, x[2];
+    H[0][0] = (double)v[0], H[1][1] = (double)v[1], H[0][1] = (double)v[2], C[0] = (double)v[3], C[1] = (double)v[4];
+    H[0][0] /= size;
+    H[0][1] /= size;
+    H[1][1] /= size;
+    H[1][0] = H[0][1];
+    C[0] /= size;
+    C[1] /= size;
+    if (r0 == 0) {
+        det = H[1][1];
+        if (det < 1e-8) return; // ill-posed, default values
+        x[1] = C[1] / det;
+        xq[1] = (int)rint(x[1] * (1 << 7));
+    } else if (r1 == 0) {
+        det = H[0][0];
+        if (det < 1e-8) return;
+        x[0] = C[0] / det;
+        xq[0] = (int)rint(x[0] * (1 << 7));
+    } else {
+        det = (H[0][0] * H[1][1] - H[0][1] * H[1][0]);
+        if (det < 1e-8) return;
+        x[0] = (H[1][1] * C[0] - H[0][1] * C[1]) / det;
+        x[1] = (H[0][0] * C[1] - H[1][0] * C[0]) / det;
+        xq[0] = (int)rint(x[0] * (1 << 7));
+        xq[1] = (int)rint(x[1] * (1 << 7));
+    }
+}
+
 static inline const void *short_ptr(const uint8_t *p) { return (const void *)(((uintptr_t)p) << 1); } // CONVERT_TO_SHORTPTR
 
 } // namespace
@@ -306,6 +387,14 @@ int64_t svt_av1_highbd_pixel_proj_error_cuda(const uint8_t *src8, int32_t width,
                                              int32_t xq[2], const void *params) {
     return proj_dropin(short_ptr(src8), width, height, src_stride, short_ptr(dat8), dat_stride, flt0, flt0_stride, flt1, flt1_stride,
                        xq, (const int32_t *)params, 1);
+}
+
+void svt_get_proj_subspace_cuda(const uint8_t *src8, int32_t width, int32_t height, int32_t src_stride, const uint8_t *dat8,
+                                int32_t dat_stride, int32_t use_highbitdepth, int32_t *flt0, int32_t flt0_stride, int32_t *flt1,
+                                int32_t flt1_stride, int32_t *xq, const void *params) {
+    proj_subspace_dropin(use_highbitdepth ? short_ptr(src8) : (const void *)src8, width, height, src_stride,
+                         use_highbitdepth ? short_ptr(dat8) : (const void *)dat8, dat_stride, use_highbitdepth != 0, flt0, flt0_stride, flt1,
+                         flt1_stride, xq, (const int32_t *)params);
 }
 
 // Wiener statistics of every restoration unit of one plane, device resident (the batched form of the search's

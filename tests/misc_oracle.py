@@ -95,3 +95,27 @@ def pixel_proj_error(src, dat, flt0, flt1, xq, r, highbd):
     else:
         e = d - s
     return int((e * e).sum())
+
+
+def get_proj_subspace(src, dat, flt0, flt1, r):
+    """svt_get_proj_subspace_c (EbRestorationPick.c:337-440): xq[2].  Sums as exact integers, solve in float64 with the
+    reference's expressions (Python floats are IEEE doubles; no contraction)."""
+    import math
+    u = dat.astype(np.int64) << 4
+    s = (src.astype(np.int64) << 4) - u
+    f1 = (flt0.astype(np.int64) - u) if r[0] > 0 else np.zeros_like(u)
+    f2 = (flt1.astype(np.int64) - u) if r[1] > 0 else np.zeros_like(u)
+    size = u.size
+    h00, h11, h01 = float(int((f1 * f1).sum())) / size, float(int((f2 * f2).sum())) / size, float(int((f1 * f2).sum())) / size
+    c0, c1 = float(int((f1 * s).sum())) / size, float(int((f2 * s).sum())) / size
+
+    def rint(v):  # round half to even, as rint() in the default rounding mode
+        return int(round(v))
+    if r[0] == 0:
+        return [0, 0] if h11 < 1e-8 else [0, rint(c1 / h11 * 128)]
+    if r[1] == 0:
+        return [0, 0] if h00 < 1e-8 else [rint(c0 / h00 * 128), 0]
+    det = h00 * h11 - h01 * h01
+    if det < 1e-8:
+        return [0, 0]
+    return [rint((h11 * c0 - h01 * c1) / det * 128), rint((h00 * c1 - h01 * c0) / det * 128)]

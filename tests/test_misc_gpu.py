@@ -180,3 +180,33 @@ def test_lr_wiener_stats_picture(case):
             m2, h2 = mo.compute_stats(win, ext, sext, hs + 3, he + 3, vs + 3, ve + 3, bd)
             np.testing.assert_array_equal(got[i, :n2], m2, err_msg=f"M unit {i}")
             np.testing.assert_array_equal(got[i, n2:], h2.reshape(-1), err_msg=f"H unit {i}")
+
+
+@pytest.mark.parametrize("bd", [8, 10])
+def test_get_proj_subspace_dropin(bd):
+    import ctypes as C
+    import misc_oracle as mo
+    from test_oracle_misc import _proj_case
+    lib = sb.load()
+    rng = np.random.default_rng(170 + bd)
+    for r in ((2, 1), (2, 0), (0, 1)):
+        for (w, h, flat) in ((64, 64, False), (33, 17, False), (48, 40, True), (384, 96, False)):
+            src, dat, f0, f1 = _proj_case(rng, bd, w, h, flat)
+            xq = (C.c_int32 * 2)(7, 7)
+            params = (C.c_int32 * 4)(r[0], r[1], 0, 0)
+            sp = C.c_void_p(src.ctypes.data >> 1) if bd > 8 else cm.ptr(src)
+            dp = C.c_void_p(dat.ctypes.data >> 1) if bd > 8 else cm.ptr(dat)
+            lib.svt_get_proj_subspace_cuda(sp, w, h, src.shape[1], dp, dat.shape[1], int(bd > 8), cm.ptr(f0), f0.shape[1], cm.ptr(f1), f1.shape[1],
+                                           xq, params)
+            assert [xq[0], xq[1]] == mo.get_proj_subspace(src[:, :w], dat[:, :w], f0[:, :w], f1[:, :w], r)
+
+
+def test_copy_rect8_dropin():
+    lib = sb.load()
+    rng = np.random.default_rng(5)
+    for (v, h) in ((8, 8), (70, 70), (3, 129)):
+        src = rng.integers(0, 256, (v, h + 7)).astype(np.uint8)
+        dst = np.full((v, h + 3), 9999, np.uint16)
+        lib.svt_copy_rect8_8bit_to_16bit_cuda(cm.ptr(dst), dst.shape[1], cm.ptr(src), src.shape[1], v, h)
+        np.testing.assert_array_equal(dst[:, :h], src[:, :h])
+        assert (dst[:, h:] == 9999).all()

@@ -150,3 +150,33 @@ def test_pixel_proj_error_restatement_matches_reference(bd):
             want = f(sp, w, h, src.shape[1], dp, dat.shape[1], cm.ptr(f0), f0.shape[1], cm.ptr(f1), f1.shape[1], xq, params)
             got = mo.pixel_proj_error(src[:, :w], dat[:, :w], f0[:, :w], f1[:, :w], (xq[0], xq[1]), r, bd > 8)
             assert got == want
+
+
+def _proj_case(rng, bd, w, h, flat=False):
+    dt = np.uint16 if bd > 8 else np.uint8
+    src = rng.integers(0, 1 << bd, (h, w + 5)).astype(dt)
+    dat = np.clip(src.astype(np.int64) + rng.integers(-9, 10, src.shape), 0, (1 << bd) - 1).astype(dt)
+    if flat:
+        f0 = (dat.astype(np.int64) << 4).astype(np.int32)
+        f1 = f0.copy()
+    else:
+        f0 = ((dat.astype(np.int64) << 4) + rng.integers(-200, 201, dat.shape)).astype(np.int32)
+        f1 = ((src.astype(np.int64) << 4) + rng.integers(-90, 91, dat.shape)).astype(np.int32)
+    return src, dat, f0, f1
+
+
+@needs_ref
+@pytest.mark.parametrize("bd", [8, 10])
+def test_get_proj_subspace_restatement_matches_reference(bd):
+    ref = cm.refh()
+    rng = np.random.default_rng(70 + bd)
+    for r in ((2, 1), (2, 0), (0, 1)):
+        for (w, h, flat) in ((64, 64, False), (33, 17, False), (48, 40, True), (384, 96, False)):
+            src, dat, f0, f1 = _proj_case(rng, bd, w, h, flat)
+            xq = (C.c_int32 * 2)(7, 7)
+            params = (C.c_int32 * 4)(r[0], r[1], 0, 0)
+            sp = C.c_void_p(src.ctypes.data >> 1) if bd > 8 else cm.ptr(src)
+            dp = C.c_void_p(dat.ctypes.data >> 1) if bd > 8 else cm.ptr(dat)
+            ref.svt_get_proj_subspace_c(sp, w, h, src.shape[1], dp, dat.shape[1], int(bd > 8), cm.ptr(f0), f0.shape[1], cm.ptr(f1), f1.shape[1],
+                                        xq, params)
+            assert mo.get_proj_subspace(src[:, :w], dat[:, :w], f0[:, :w], f1[:, :w], r) == [xq[0], xq[1]]
