@@ -351,6 +351,12 @@ SVT_B200_DECL_INV_RECT(32, 16) SVT_B200_DECL_INV_RECT(32, 64) SVT_B200_DECL_INV_
 SVT_B200_DECL_INV_RECT_NOEOB(4, 16) SVT_B200_DECL_INV_RECT_NOEOB(16, 4) SVT_B200_DECL_INV_RECT(8, 32)
 SVT_B200_DECL_INV_RECT(32, 8) SVT_B200_DECL_INV_RECT(16, 64) SVT_B200_DECL_INV_RECT(64, 16)
 
+/* replace svt_av1_inv_txfm_add (common_dsp_rtcd.h:155-156; EbInvTransforms.c:3302-3323): the 8-bit entry — prediction
+ * and reconstruction are uint8 planes, txfm_param is the reference's TxfmParam (tx_type, tx_size, bd, eob are read; lossless
+ * is not supported). */
+SVT_B200_API void svt_av1_inv_txfm_add_cuda(const int32_t *dqcoeff, uint8_t *dst_r, int32_t stride_r, uint8_t *dst_w,
+                                            int32_t stride_w, const void *txfm_param);
+
 /* replace svt_aom_quantize_b / svt_aom_highbd_quantize_b (aom_dsp_rtcd.h:252,254; EbFullLoop.c:37,171) and
  * svt_av1_quantize_fp[_32x32/_64x64] / svt_av1_highbd_quantize_fp (aom_dsp_rtcd.h:256-262; :314-600).
  * QmVal is uint8_t in the reference. */

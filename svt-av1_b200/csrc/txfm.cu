@@ -852,6 +852,32 @@ extern "C" uint64_t svt_b200_handle_transform64(int32_t *output, int tx_size) {
 // ---------------------------------------------------------------------------------------------------------------
 extern "C" {
 
+// svt_av1_inv_txfm_add_c (EbInvTransforms.c:3302-3323): the low-bit-depth wrapper — widen the prediction to 16 bit, run
+// the (high-bit-depth) inverse transform at bd = 8, narrow the result.  TxfmParam (EbDefinitions.h:779-791) is read
+// through a layout view: packed 1-byte enums tx_type / tx_size, then int32 lossless, bd, is_hbd, tx_set_type, eob.
+struct TxfmParamView {
+    uint8_t tx_type, tx_size;
+    int32_t lossless, bd, is_hbd;
+    uint8_t tx_set_type;
+    int32_t eob;
+};
+void svt_av1_inv_txfm_add_cuda(const int32_t *dqcoeff, uint8_t *dst_r, int32_t stride_r, uint8_t *dst_w, int32_t stride_w,
+                               const void *txfm_param) {
+    const TxfmParamView *tp = (const TxfmParamView *)txfm_param;
+    const int tx_size = tp->tx_size, tx_type = tp->tx_type;
+    if (tx_size > 18 || tx_type > 15 || tp->lossless) {
+        fprintf(stderr, "svt_av1_inv_txfm_add_cuda: tx_size %d / tx_type %d / lossless %d is not supported\n", tx_size, tx_type, tp->lossless);
+        abort();
+    }
+    const int w = h_txw[tx_size], h = h_txh[tx_size];
+    uint16_t tmp[64 * 64];
+    for (int r = 0; r < h; r++)
+        for (int c = 0; c < w; c++) tmp[r * 64 + c] = dst_r[(size_t)r * stride_r + c];
+    inv_dropin(dqcoeff, tmp, 64, tmp, 64, tx_type, tx_size, tp->bd);
+    for (int r = 0; r < h; r++)
+        for (int c = 0; c < w; c++) dst_w[(size_t)r * stride_w + c] = (uint8_t)tmp[r * 64 + c];
+}
+
 int svt_b200_get_scan(int tx_size, int tx_type, int16_t *scan_out) {
     // get_scan (Common/Codec/EbCoefficients.c / av1_scan_orders): 64-wide sizes scan as their 32-wide packing;
     // 2-D types: zig-zag (diagonals alternate for squares, fixed direction for rectangles); V_* (row-identity):

@@ -290,3 +290,33 @@ def test_pack_levels(tx_size, tx_class):
     got = packed.cpu().numpy()
     for b in range(0, n_tus, 7):
         np.testing.assert_array_equal(got[want_off[b]:want_off[b + 1]], q[b, scan[:eob[b]]])
+
+
+class TxfmParam(C.Structure):  # EbDefinitions.h:779-791 (tx_type / tx_size / tx_set_type are 1-byte packed enums)
+    _fields_ = [("tx_type", C.c_uint8), ("tx_size", C.c_uint8), ("lossless", C.c_int32), ("bd", C.c_int32), ("is_hbd", C.c_int32),
+                ("tx_set_type", C.c_uint8), ("eob", C.c_int32)]
+
+
+@pytest.mark.parametrize("tx_size", [0, 1, 2, 3, 4, 5, 8, 11, 13, 18])
+def test_inv_txfm_add_lowbd_dropin(tx_size):
+    """svt_av1_inv_txfm_add (8-bit wrapper): vs the oracle's inverse on the widened prediction, and vs the reference's own
+    svt_av1_inv_txfm_add_c when oracle/_ref is present."""
+    lib, orc = sb.load(), cm.oracle()
+    w, h = TX_W[tx_size], TX_H[tx_size]
+    rng = np.random.default_rng(400 + tx_size)
+    for tx_type in allowed_types(tx_size)[:4]:
+        coeff = np.zeros(min(w, 32) * min(h, 32), np.int32)
+        nz = rng.choice(coeff.size, min(12, coeff.size), replace=False)
+        coeff[nz] = rng.integers(-900, 901, nz.size)
+        pred = rng.integers(0, 256, (h, w + 5)).astype(np.uint8)
+        got = np.zeros((h, w + 9), np.uint8)
+        tp = TxfmParam(tx_type, tx_size, 0, 8, 0, 0, int(coeff.size))
+        lib.svt_av1_inv_txfm_add_cuda(cm.ptr(coeff), cm.ptr(pred), pred.shape[1], cm.ptr(got), got.shape[1], C.byref(tp))
+        p16 = np.ascontiguousarray(pred[:, :w].astype(np.uint16))
+        want = np.zeros((h, w), np.uint16)
+        orc.orc_inv_txfm2d_add(cm.ptr(coeff), cm.ptr(p16), w, cm.ptr(want), w, tx_type, tx_size, 8)
+        np.testing.assert_array_equal(got[:, :w], want.astype(np.uint8))
+        if cm.have_ref():
+            ref = np.zeros((h, w + 9), np.uint8)
+            cm.refh().svt_av1_inv_txfm_add_c(cm.ptr(coeff), cm.ptr(pred), pred.shape[1], cm.ptr(ref), ref.shape[1], C.byref(tp))
+            np.testing.assert_array_equal(got[:, :w], ref[:, :w])
