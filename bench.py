@@ -740,14 +740,23 @@ def roofline(stage_ms, pk, pk_kind, n_sb):
     }
     bound = {"me": "integer ALU / shared memory (VABSDIFF4 issue rate)", "encdec": "shared-memory butterflies, then HBM",
              "dlf": "hbm", "cdef_search": "integer ALU (10 filters per sample)", "cdef_apply": "hbm"}
+    # DRAM bytes per frame from the committed `ncu --set full` capture of one frame (profiles/ncu_traffic.json, written
+    # by tools/ncu_summary.py): sums over the launches of the stage's kernels
+    kernels = {"me": ("hme_kernel", "fullpel_kernel"), "encdec": ("encode_tu_kernel",), "dlf": ("dlf_pass_kernel",),
+               "cdef_search": ("cdef_search_grid_kernel",), "cdef_apply": ("cdef_apply_kernel",)}
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    except Exception:
+        ncu = {}
     stages = []
     for k, b in alg.items():
         ach = b / (stage_ms[k] / 1e3) / 1e9
-        stages.append({"stage": k, "ms_per_frame": stage_ms[k], "algorithmic_bytes": int(b), "achieved": ach,
-                       "frac": ach / pk["hbm_gbs"], "binding": bound[k]})
+        tr = sum(ncu[n]["dram_bytes"] for n in kernels[k]) if all(n in ncu for n in kernels[k]) else None
+        stages.append({"stage": k, "kernels": list(kernels[k]), "ms_per_frame": stage_ms[k], "algorithmic_bytes": int(b), "achieved": ach,
+                       "frac": ach / pk["hbm_gbs"], "traffic": tr, "binding": bound[k]})
     dom = max(stages, key=lambda x: x["ms_per_frame"])
-    return {"kernel": "stage '%s' (dominant; its kernels are listed in profiles/)" % dom["stage"], "bound": "hbm",
-            "achieved": dom["achieved"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": dom["frac"], "traffic": None,
+    return {"kernel": "stage '%s' = %s (dominant; per-kernel ncu data in profiles/)" % (dom["stage"], " + ".join(dom["kernels"])), "bound": "hbm",
+            "achieved": dom["achieved"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": dom["frac"], "traffic": dom["traffic"],
             "peak_source": pk_kind, "stages": stages,
             "note": "ME and the CDEF strength search are integer-ALU/shared-memory bound (SURVEY §8d): their HBM fraction is "
                     "legitimately small; the streaming stages (dlf, cdef_apply, encdec) are the HBM-bound ones"}

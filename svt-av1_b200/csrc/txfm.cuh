@@ -3,9 +3,10 @@
 // Replaces the hand-unrolled stage lists of Source/Lib/Encoder/Codec/EbTransforms.c:75-2271 and
 // Source/Lib/Common/Codec/EbInvTransforms.c:75-2358.  The butterfly networks are generated from their
 // recursive structure (DCT-n = butterfly ; DCT-n/2 ; ODD(n/2) ; bit reversal) instead of being spelled out;
-// every layer acts on disjoint pairs so the whole 1-D transform runs IN PLACE on a strided array in shared
-// memory, one thread per row/column of a transform block.  Only half_btf() rounds; additions are exact, so
-// evaluation order of independent sub-networks cannot change a bit.
+// every layer acts on disjoint pairs.  Two forms of the same structure functions: fully unrolled templates on a
+// register array (n <= 32: one thread loads a row/column, transforms it in registers, stores it) and an in-place
+// strided shared-memory form (n = 64).  Only half_btf() rounds; additions are exact, so evaluation order of
+// independent sub-networks cannot change a bit.
 #pragma once
 #include <cmath>
 #include <cstdint>
@@ -188,87 +189,6 @@ __device__ inline void iadst4(int32_t *x, int s, int bit) {
     TX(3) = round_shift64((long long)wsub(wadd(s0, s1), s3), bit);
 }
 
-__constant__ static int8_t c_adst8_in[8] = {0, -7, -3, 4, -1, 6, 2, -5};
-__constant__ static int8_t c_adst8_out[8] = {1, 6, 3, 4, 5, 2, 7, 0};
-__constant__ static int8_t c_adst16_in[16] = {0, -15, -7, 8, -3, 12, 4, -11, -1, 14, 6, -9, 2, -13, -5, 10};
-__constant__ static int8_t c_adst16_out[16] = {1, 14, 3, 12, 5, 10, 7, 8, 9, 6, 11, 4, 13, 2, 15, 0};
-
-__device__ inline void adst_rotations(int32_t *v, int n, int h, const int32_t *c, int bit) {
-    const int np = h / 2;
-    for (int g = 0; g < n; g += 2 * h)
-        for (int i = 0; i < np; i++) {
-            const int a0 = g + h + 2 * i, a1 = a0 + 1;
-            const int32_t a = v[a0], b = v[a1];
-            if (h == 2) {
-                v[a0] = half_btf(c[32], a, c[32], b, bit);
-                v[a1] = half_btf(c[32], a, -c[32], b, bit);
-                continue;
-            }
-            const int half = np / 2, q = i % half;
-            const int k = (64 / h) * (h >= 8 ? 4 * q + 1 : 1);
-            if (i < half) {
-                v[a0] = half_btf(c[k], a, c[64 - k], b, bit);
-                v[a1] = half_btf(c[64 - k], a, -c[k], b, bit);
-            } else {
-                v[a0] = half_btf(-c[64 - k], a, c[k], b, bit);
-                v[a1] = half_btf(c[k], a, c[64 - k], b, bit);
-            }
-        }
-}
-__device__ inline void adst_addsub(int32_t *v, int n, int h, int clamp_bit) {
-    for (int g = 0; g < n; g += 2 * h)
-        for (int i = 0; i < h; i++) {
-            const int32_t a = v[g + i], b = v[g + h + i];
-            v[g + i] = clampv(wadd(a, b), clamp_bit);
-            v[g + h + i] = clampv(wsub(a, b), clamp_bit);
-        }
-}
-__device__ inline void adst_final(int32_t *v, int n, const int32_t *c, int bit) {
-    for (int i = 0; i < n / 2; i++) {
-        const int k = (32 + 128 * i) / n;
-        const int32_t a = v[2 * i], b = v[2 * i + 1];
-        v[2 * i] = half_btf(c[k], a, c[64 - k], b, bit);
-        v[2 * i + 1] = half_btf(c[64 - k], a, -c[k], b, bit);
-    }
-}
-__device__ inline void fadst(int32_t *x, int s, int n, int bit) {
-    if (n == 4) {
-        fadst4(x, s, bit);
-        return;
-    }
-    const int32_t *c = c_cospi[bit - 10];
-    const int8_t *pin = n == 8 ? c_adst8_in : c_adst16_in, *pout = n == 8 ? c_adst8_out : c_adst16_out;
-    int32_t v[16];
-    for (int i = 0; i < n; i++) {
-        const int p = pin[i];
-        v[i] = p < 0 ? wsub(0, TX(-p)) : TX(p);
-    }
-    for (int h = 2; h < n; h <<= 1) {
-        adst_rotations(v, n, h, c, bit);
-        adst_addsub(v, n, h, 0);
-    }
-    adst_final(v, n, c, bit);
-    for (int i = 0; i < n; i++) TX(i) = v[pout[i]];
-}
-__device__ inline void iadst(int32_t *x, int s, int n, int bit, int clamp_bit) {
-    if (n == 4) {
-        iadst4(x, s, bit);
-        return;
-    }
-    const int32_t *c = c_cospi[bit - 10];
-    const int8_t *pin = n == 8 ? c_adst8_in : c_adst16_in, *pout = n == 8 ? c_adst8_out : c_adst16_out;
-    int32_t v[16];
-    for (int i = 0; i < n; i++) v[pout[i]] = TX(i);
-    adst_final(v, n, c, bit);
-    for (int h = n / 2; h >= 2; h >>= 1) {
-        adst_addsub(v, n, h, clamp_bit);
-        adst_rotations(v, n, h, c, bit);
-    }
-    for (int i = 0; i < n; i++) {
-        const int p = pin[i];
-        TX(p < 0 ? -p : p) = p < 0 ? wsub(0, v[i]) : v[i];
-    }
-}
 // identity (forward and inverse scale identically: EbTransforms.c:2239-2278, EbInvTransforms.c:2321-2358)
 __device__ inline void identity_scale(int32_t *x, int s, int n) {
     for (int i = 0; i < n; i++) {
@@ -285,17 +205,6 @@ __device__ inline void identity_scale(int32_t *x, int s, int n) {
 #undef TX
 
 // kind: 0 DCT, 1 ADST, 2 FLIPADST, 3 IDTX
-__device__ inline void fwd_1d(int32_t *x, int s, int n, int kind, int bit) {
-    if (kind == 0) fdct(x, s, n, bit);
-    else if (kind == 3) identity_scale(x, s, n);
-    else fadst(x, s, n, bit);
-}
-__device__ inline void inv_1d(int32_t *x, int s, int n, int kind, int bit, int clamp_bit) {
-    if (kind == 0) idct(x, s, n, bit, clamp_bit);
-    else if (kind == 3) identity_scale(x, s, n);
-    else iadst(x, s, n, bit, clamp_bit);
-}
-
 
 // ---------------------------------------------------------------------------------------------------------------
 // Register-resident, fully unrolled versions of the same networks (n <= 32).  The structure functions above are
@@ -613,56 +522,5 @@ struct TxCfg {
     int rect; // |log2(w/h)| == 1
 };
 
-
-// Forward 2-D transform of one block living in shared memory.
-//   buf: h rows of pitch `pitch` (>= w, odd pitches avoid bank conflicts for the row pass); on entry holds the
-//   residual (already flipped as cfg asks), on exit the coefficients in natural raster (r, c).
-//   lanes: `nl` cooperating threads with index `li`; contains __syncthreads-free named sync via `sync()` callable.
-template <typename Sync>
-__device__ inline void fwd_txfm2d_smem(int32_t *buf, int pitch, const TxCfg &t, int li, int nl, Sync sync) {
-    for (int c = li; c < t.w; c += nl) {
-        int32_t *col = buf + c;
-        if (t.fs0) for (int r = 0; r < t.h; r++) col[r * pitch] = (int32_t)((uint32_t)col[r * pitch] << t.fs0);
-        fwd_1d(col, pitch, t.h, t.vk, t.cbc);
-        if (t.fs1) for (int r = 0; r < t.h; r++) col[r * pitch] = round_shift64((long long)col[r * pitch], -t.fs1);
-    }
-    sync();
-    for (int r = li; r < t.h; r += nl) {
-        int32_t *row = buf + r * pitch;
-        fwd_1d(row, 1, t.w, t.hk, t.cbr);
-        for (int c = 0; c < t.w; c++) {
-            int32_t v = row[c];
-            if (t.fs2) v = round_shift64((long long)v, -t.fs2);
-            if (t.rect) v = round_shift64((long long)v * 5793, 12);
-            row[c] = v;
-        }
-    }
-    sync();
-}
-// Inverse 2-D: buf holds w x h coefficients (zero-extended for 64-wide sizes) on entry, residual on exit
-// (natural orientation: flips applied), rows then columns (inv_txfm2d_add_c, EbInvTransforms.c:2455-2532).
-template <typename Sync>
-__device__ inline void inv_txfm2d_smem(int32_t *buf, int pitch, const TxCfg &t, int bd, int li, int nl, Sync sync) {
-    const int range_row = bd == 8 ? 16 : bd == 10 ? 18 : 20, range_col = bd == 8 ? 16 : bd == 10 ? 16 : 18;
-    for (int r = li; r < t.h; r += nl) {
-        int32_t *row = buf + r * pitch;
-        for (int c = 0; c < t.w; c++) {
-            int32_t v = row[c];
-            if (t.rect) v = round_shift64((long long)v * 2896, 12);
-            row[c] = clampv(v, bd + 8);
-        }
-        inv_1d(row, 1, t.w, t.hk, 12, range_row);
-        if (t.is0) for (int c = 0; c < t.w; c++) row[c] = round_shift64((long long)row[c], -t.is0);
-    }
-    sync();
-    const int col_clamp = max(bd + 6, 16);
-    for (int c = li; c < t.w; c += nl) {
-        int32_t *col = buf + c;
-        for (int r = 0; r < t.h; r++) col[r * pitch] = clampv(col[r * pitch], col_clamp);
-        inv_1d(col, pitch, t.h, t.vk, 12, range_col);
-        for (int r = 0; r < t.h; r++) col[r * pitch] = round_shift64((long long)col[r * pitch], -t.is1);
-    }
-    sync();
-}
 
 } // namespace svtb200

@@ -21,6 +21,8 @@ STALL = "smsp__average_warps_issue_stalled_"
 
 def main():
     rep = sys.argv[1]
+    json_out = sys.argv[2] if len(sys.argv) > 2 else None
+    traffic = {}
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
@@ -28,6 +30,16 @@ def main():
     seen = set()
     for r in rows[2:]:
         name = r[ki]
+        if json_out:
+            def val(metric):
+                v = float(r[hdr.index(metric)].replace(",", "")) if metric in hdr else 0.0
+                u = units[hdr.index(metric)] if metric in hdr else ""
+                return v * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0, "msecond": 1e3, "usecond": 1.0, "nsecond": 1e-3}.get(u, 1.0)
+            short = name.split("(")[0].split("::")[-1].split("<")[0].strip()
+            t = traffic.setdefault(short, {"launches": 0, "dram_bytes": 0.0, "time_us": 0.0})
+            t["launches"] += 1
+            t["dram_bytes"] += val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+            t["time_us"] += val("gpu__time_duration.sum")
         if name in seen:
             continue
         seen.add(name)
@@ -35,6 +47,11 @@ def main():
         for i, h in enumerate(hdr):
             if h in KEEP or (h.startswith(STALL) and h.endswith("_per_issue_active.ratio") and float(r[i] or 0) >= 0.2):
                 print("  %-90s %s %s" % (h, r[i], units[i]))
+
+
+    if json_out:
+        import json
+        json.dump(traffic, open(json_out, "w"), indent=1)
 
 
 if __name__ == "__main__":
