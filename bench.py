@@ -36,6 +36,7 @@ MI_ROWS, MI_COLS = H // 4, W // 4
 FRAMES_PER_STEP = 8
 N_L0, N_L1 = 2, 2
 DIST = ((1, 2, 3, 4), (1, 2, 3, 4))
+PICTURES_IN_FLIGHT = 4  # pictures issued concurrently (one CUDA stream each)
 RING = 4  # distinct mini-GOP input sets cycled between steps so that the working set exceeds the 126 MB L2
 QINDEX_LEVELS = (24, 20, 14, 10)  # deblocking levels (Y vert, Y horz, U, V)
 BASE_Q_IDX = 172  # qp 43
@@ -426,7 +427,7 @@ def run_b200(args):
     # picture-level pipeline would: NS pictures in flight, one CUDA stream each (kernel tails, copies and the host-side
     # CDEF strength decision of one picture overlap the kernels of the others).  Picture i always uses stream i % NS,
     # so its buffers are ordered by the stream; steps are NOT separated by a barrier.
-    NS = 4
+    NS = int(os.environ.get("BENCH_STREAMS", PICTURES_IN_FLIGHT))
     streams = [torch.cuda.Stream() for _ in range(NS)]
     sps = [C.c_void_p(st.cuda_stream) for st in streams]
     copy_stream = torch.cuda.Stream()

@@ -654,7 +654,7 @@ __device__ void hme_level_search(const uint8_t *__restrict__ src, int src_stride
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(NT_SEARCH, 4) hme_kernel(const __grid_constant__ MeDev d) {
+__global__ void __launch_bounds__(NT_SEARCH, 6) hme_kernel(const __grid_constant__ MeDev d) {
     extern __shared__ uint4 smem4[];
     uint32_t *smem = reinterpret_cast<uint32_t *>(smem4);
     __shared__ HmeJob s_jobs[4];
