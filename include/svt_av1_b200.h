@@ -657,6 +657,23 @@ SVT_B200_API int svt_b200_lr_wiener_stats(const SvtB200Frame *dgd, const SvtB200
                                           int32_t max_unit_w, int32_t max_unit_h, int64_t *out, void *scratch,
                                           void *stream);
 
+/* The self-guided side of the search (search_selfguided_restoration, EbRestorationPick.c:583-661) for every restoration
+ * unit of one plane and every parameter set of eps[] (host array, values 0..15) at once, pictures resident on the device:
+ *  - svt_b200_lr_sgr_filter_sums: apply_sgr (:554-581; the filter per 64x64 / 32x32 processing unit tiled from the unit's
+ *    origin, reads outside the plane clamped) with both outputs kept in flt = DEVICE int32 [n_eps][2][plane_h][plane_w], and
+ *    the five sums of svt_get_proj_subspace in sums = DEVICE int64 [n_units][n_eps][5] = {H00, H11, H01, C0, C1} (before the
+ *    division by the unit size; the 2x2 solve stays on the host);
+ *  - svt_b200_lr_sgr_proj_error: get_pixel_proj_error (:316-360) for one decoded xq pair per (unit, ep): xq = DEVICE int32
+ *    [n_units][n_eps][2], err = DEVICE int64 [n_units][n_eps]; one call per step of finer_search_pixel_proj_error.
+ * rects: DEVICE int32 [n_units][4] = {h_start, h_end, v_start, v_end}. */
+SVT_B200_API int svt_b200_lr_sgr_filter_sums(const SvtB200Frame *dgd, const SvtB200Frame *src, int32_t plane,
+                                             const int32_t *rects, int32_t n_units, int32_t max_unit_w, int32_t max_unit_h,
+                                             const int32_t *eps, int32_t n_eps, int32_t *flt, int64_t *sums, void *stream);
+SVT_B200_API int svt_b200_lr_sgr_proj_error(const SvtB200Frame *dgd, const SvtB200Frame *src, int32_t plane,
+                                            const int32_t *rects, int32_t n_units, int32_t max_unit_w, int32_t max_unit_h,
+                                            const int32_t *eps, int32_t n_eps, const int32_t *flt, const int32_t *xq,
+                                            int64_t *err, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -303,6 +303,110 @@ __global__ void __launch_bounds__(SGR_NT) lr_frame_kernel(const __grid_constant_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Self-guided SEARCH, device resident (search_selfguided_restoration, EbRestorationPick.c:583-661): for every
+// restoration unit and every parameter set ep of a list, apply_sgr (:554-581: the filter per processing unit, tiled
+// from the unit's origin) with both outputs kept in HBM (16 sets x 2 x 4 B x 3.1 M samples = 400 MB at 1080p: what
+// 180 GB are for), plus the five sums of svt_get_proj_subspace per (unit, ep).  A second entry evaluates
+// get_pixel_proj_error for one candidate xq per (unit, ep), so the host's hill climb (finer_search_pixel_proj_error)
+// costs one launch + one small read-back per step for ALL units and parameter sets at once.
+// ---------------------------------------------------------------------------------------------------------------
+struct SgrSearchDev {
+    const void *dgd, *src;
+    int dgd_stride, src_stride, pw, ph, ss, bd;
+    const int32_t *rects; // [n_units][4] h_start, h_end, v_start, v_end
+    int eps[16], n_eps, tiles_x;
+    int32_t *flt; // [n_eps][2][ph][pw]
+    long long *sums; // [n_units][n_eps][5]: H00 H11 H01 C0 C1
+    const int32_t *xq; // [n_units][n_eps][2]
+    long long *err; // [n_units][n_eps]
+};
+
+template <typename T>
+__global__ void __launch_bounds__(SGR_NT) sgr_search_filter_kernel(const __grid_constant__ SgrSearchDev d) {
+    extern __shared__ int32_t sm[];
+    const int unit = blockIdx.y, ei = blockIdx.z, idx = d.eps[ei];
+    const int32_t *rc = d.rects + 4 * unit;
+    const int PU = 64 >> d.ss;
+    const int tx = blockIdx.x % d.tiles_x, ty = blockIdx.x / d.tiles_x;
+    const int xs = rc[0] + tx * PU, ys = rc[2] + ty * PU;
+    if (xs >= rc[1] || ys >= rc[3]) return;
+    const int w = min(PU, rc[1] - xs), h = min(PU, rc[3] - ys);
+    const T *dg = reinterpret_cast<const T *>(d.dgd);
+    const T *sr = reinterpret_cast<const T *>(d.src);
+    uint16_t *tile = reinterpret_cast<uint16_t *>(sm);
+    const int tw = w + 6, th = h + 6;
+    for (int t = threadIdx.x; t < tw * th; t += SGR_NT) { // the unit's surroundings, clamped = the extended picture
+        const int r = t / tw, c = t - r * tw;
+        const int yy = min(max(ys + r - 3, 0), d.ph - 1), xx = min(max(xs + c - 3, 0), d.pw - 1);
+        tile[t] = (uint16_t)dg[(size_t)yy * d.dgd_stride + xx];
+    }
+    int32_t *A = sm + ((71 * 71 * 2 + 15) / 16 * 16) / 4, *B = A + 66 * 66, *flt0 = B + 66 * 66, *flt1 = flt0 + 64 * 64;
+    const int r0 = c_sgr_r[idx][0], r1 = c_sgr_r[idx][1];
+    if (r0 > 0) sgr_pass(tile, tw, w, h, A, B, flt0, w, d.bd, idx, 0);
+    if (r1 > 0) sgr_pass(tile, tw, w, h, A, B, flt1, w, d.bd, idx, 1);
+    __syncthreads();
+    const size_t plane = (size_t)d.pw * d.ph;
+    int32_t *g0 = d.flt + (size_t)ei * 2 * plane, *g1 = g0 + plane;
+    long long v[5] = {0, 0, 0, 0, 0};
+    for (int t = threadIdx.x; t < w * h; t += SGR_NT) {
+        const int i = t / w, j = t - i * w;
+        const size_t o = (size_t)(ys + i) * d.pw + xs + j;
+        const long long u = (long long)tile[(i + 3) * tw + j + 3] << 4;
+        const long long s = ((long long)sr[(size_t)(ys + i) * d.src_stride + xs + j] << 4) - u;
+        long long f1 = 0, f2 = 0;
+        if (r0 > 0) {
+            g0[o] = flt0[t];
+            f1 = flt0[t] - u;
+        }
+        if (r1 > 0) {
+            g1[o] = flt1[t];
+            f2 = flt1[t] - u;
+        }
+        v[0] += f1 * f1, v[1] += f2 * f2, v[2] += f1 * f2, v[3] += f1 * s, v[4] += f2 * s;
+    }
+    long long *out = d.sums + ((size_t)unit * d.n_eps + ei) * 5;
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        for (int o = 16; o > 0; o >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+        if ((threadIdx.x & 31) == 0 && v[k]) atomicAdd(reinterpret_cast<unsigned long long *>(out + k), (unsigned long long)v[k]);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) sgr_search_error_kernel(const __grid_constant__ SgrSearchDev d) {
+    const int unit = blockIdx.y, ei = blockIdx.z, idx = d.eps[ei];
+    const int32_t *rc = d.rects + 4 * unit;
+    const int w = rc[1] - rc[0], h = rc[3] - rc[2];
+    const T *dg = reinterpret_cast<const T *>(d.dgd);
+    const T *sr = reinterpret_cast<const T *>(d.src);
+    const int r0 = c_sgr_r[idx][0], r1 = c_sgr_r[idx][1];
+    const int xq0 = d.xq[((size_t)unit * d.n_eps + ei) * 2], xq1 = d.xq[((size_t)unit * d.n_eps + ei) * 2 + 1];
+    const size_t plane = (size_t)d.pw * d.ph;
+    const int32_t *g0 = d.flt + (size_t)ei * 2 * plane, *g1 = g0 + plane;
+    const bool hbd = sizeof(T) == 2;
+    long long acc = 0;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < w * h; t += gridDim.x * blockDim.x) {
+        const int i = t / w, j = t - i * w;
+        const int y = rc[2] + i, x = rc[0] + j;
+        const int dv = dg[(size_t)y * d.dgd_stride + x], s = sr[(size_t)y * d.src_stride + x];
+        int e;
+        if (r0 > 0 || r1 > 0) { // svt_av1_{lowbd,highbd}_pixel_proj_error_c
+            const int u = dv << 4;
+            int v = hbd ? (1 << 10) : (u << 7);
+            if (r0 > 0) v += xq0 * (g0[(size_t)y * d.pw + x] - u);
+            if (r1 > 0) v += xq1 * (g1[(size_t)y * d.pw + x] - u);
+            e = hbd ? (v >> 11) + dv - s : ((v + (1 << 10)) >> 11) - s;
+        } else {
+            e = dv - s;
+        }
+        acc += (long long)(e * e);
+    }
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0 && acc) atomicAdd(reinterpret_cast<unsigned long long *>(d.err + (size_t)unit * d.n_eps + ei), (unsigned long long)acc);
+}
+
 static bool g_lr_attr = false;
 static void lr_attrs() {
     if (g_lr_attr) return;
@@ -310,6 +414,8 @@ static void lr_attrs() {
     cudaFuncSetAttribute(wiener_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     cudaFuncSetAttribute(lr_frame_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, LR_SMEM);
     cudaFuncSetAttribute(lr_frame_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, LR_SMEM);
+    cudaFuncSetAttribute(sgr_search_filter_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, LR_SMEM);
+    cudaFuncSetAttribute(sgr_search_filter_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, LR_SMEM);
     g_lr_attr = true;
 }
 
@@ -505,6 +611,77 @@ int svt_b200_lr_frame(const SvtB200LrFrameParams *p, const SvtB200Frame *cdef, c
         SVTB_LAUNCH(lr_frame_kernel<uint16_t>, items, SGR_NT, LR_SMEM, st, d);
     else
         SVTB_LAUNCH(lr_frame_kernel<uint8_t>, items, SGR_NT, LR_SMEM, st, d);
+    SVTB_CUDA_TRY(cudaGetLastError());
+    return SVT_B200_OK;
+}
+
+static int sgr_search_setup(SgrSearchDev &d, const SvtB200Frame *dgd, const SvtB200Frame *src, int plane, const int32_t *rects, int n_units,
+                            const int32_t *eps, int n_eps, int32_t *flt) {
+    if (!dgd || !src || !rects || !eps || !flt || plane < 0 || plane > 2 || n_units <= 0 || n_eps <= 0 || n_eps > 16 ||
+        dgd->bit_depth != src->bit_depth)
+        return -1;
+    memset(&d, 0, sizeof(d));
+    const int ss = plane ? 1 : 0;
+    d.dgd = plane == 0 ? dgd->y : plane == 1 ? dgd->cb : dgd->cr;
+    d.src = plane == 0 ? src->y : plane == 1 ? src->cb : src->cr;
+    d.dgd_stride = plane ? dgd->stride_c : dgd->stride_y;
+    d.src_stride = plane ? src->stride_c : src->stride_y;
+    d.pw = (dgd->width + ss) >> ss;
+    d.ph = (dgd->height + ss) >> ss;
+    d.ss = ss;
+    d.bd = dgd->bit_depth;
+    d.rects = rects;
+    d.n_eps = n_eps;
+    for (int i = 0; i < n_eps; i++) {
+        if (eps[i] < 0 || eps[i] > 15) return -1;
+        d.eps[i] = eps[i];
+    }
+    d.flt = flt;
+    return 0;
+}
+
+int svt_b200_lr_sgr_filter_sums(const SvtB200Frame *dgd, const SvtB200Frame *src, int32_t plane, const int32_t *rects, int32_t n_units,
+                                int32_t max_unit_w, int32_t max_unit_h, const int32_t *eps, int32_t n_eps, int32_t *flt, int64_t *sums,
+                                void *stream) {
+    SgrSearchDev d;
+    if (!sums || max_unit_w <= 0 || max_unit_h <= 0 || sgr_search_setup(d, dgd, src, plane, rects, n_units, eps, n_eps, flt)) {
+        set_error("svt_b200_lr_sgr_filter_sums: bad argument");
+        return SVT_B200_ERR_ARG;
+    }
+    lr_attrs();
+    d.sums = (long long *)sums;
+    const int PU = 64 >> d.ss;
+    d.tiles_x = (max_unit_w + PU - 1) / PU;
+    const int tiles_y = (max_unit_h + PU - 1) / PU;
+    cudaStream_t st = (cudaStream_t)stream;
+    SVTB_CUDA_TRY(cudaMemsetAsync(sums, 0, (size_t)n_units * n_eps * 5 * 8, st));
+    const dim3 grid(d.tiles_x * tiles_y, n_units, n_eps);
+    if (d.bd > 8)
+        SVTB_LAUNCH(sgr_search_filter_kernel<uint16_t>, grid, SGR_NT, LR_SMEM, st, d);
+    else
+        SVTB_LAUNCH(sgr_search_filter_kernel<uint8_t>, grid, SGR_NT, LR_SMEM, st, d);
+    SVTB_CUDA_TRY(cudaGetLastError());
+    return SVT_B200_OK;
+}
+
+int svt_b200_lr_sgr_proj_error(const SvtB200Frame *dgd, const SvtB200Frame *src, int32_t plane, const int32_t *rects, int32_t n_units,
+                               int32_t max_unit_w, int32_t max_unit_h, const int32_t *eps, int32_t n_eps, const int32_t *flt,
+                               const int32_t *xq, int64_t *err, void *stream) {
+    SgrSearchDev d;
+    if (!xq || !err || max_unit_w <= 0 || max_unit_h <= 0 ||
+        sgr_search_setup(d, dgd, src, plane, rects, n_units, eps, n_eps, const_cast<int32_t *>(flt))) {
+        set_error("svt_b200_lr_sgr_proj_error: bad argument");
+        return SVT_B200_ERR_ARG;
+    }
+    d.xq = xq;
+    d.err = (long long *)err;
+    cudaStream_t st = (cudaStream_t)stream;
+    SVTB_CUDA_TRY(cudaMemsetAsync(err, 0, (size_t)n_units * n_eps * 8, st));
+    const dim3 grid(std::min(16, (max_unit_w * max_unit_h + 255) / 256), n_units, n_eps);
+    if (d.bd > 8)
+        SVTB_LAUNCH(sgr_search_error_kernel<uint16_t>, grid, 256, 0, st, d);
+    else
+        SVTB_LAUNCH(sgr_search_error_kernel<uint8_t>, grid, 256, 0, st, d);
     SVTB_CUDA_TRY(cudaGetLastError());
     return SVT_B200_OK;
 }

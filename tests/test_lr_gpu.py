@@ -82,3 +82,82 @@ def test_lr_frame_vs_oracle(case):
     got = gr.run_gpu_lr(cdef, dblk, units, unit_sizes, frame_types, optimized)
     for i in range(3):
         np.testing.assert_array_equal(got.plane(i), want.plane(i), err_msg=f"plane {i}")
+
+
+SGR_R = [(2, 1)] * 10 + [(0, 1)] * 4 + [(2, 0)] * 2  # eb_sgr_params radii
+
+
+@pytest.mark.parametrize("case", [(192, 136, 8, 64, (0, 3, 11, 15)), (200, 104, 10, 128, (5, 12, 14)), (640, 360, 8, 64, tuple(range(16)))])
+def test_lr_sgr_search_picture(case):
+    """svt_b200_lr_sgr_filter_sums / svt_b200_lr_sgr_proj_error: every unit x parameter set of a plane at once against the
+    oracle's self-guided filter applied per processing unit (apply_sgr) + numpy sums / errors."""
+    import torch
+    import gpu_runner as gr
+    import misc_oracle as mo
+    w, h, bd, unit, eps = case
+    lib, orc = sb.load(), cm.oracle()
+    src = cm.synth_yuv(w, h, 1, 31, bd)
+    dgd = cm.degrade(src, 32, amp=8)
+    dd, ds = gr.DevYuv(dgd), gr.DevYuv(src)
+    rng = np.random.default_rng(9)
+    for plane in (0, 1):
+        U, PU = (unit, 64) if plane == 0 else (unit // 2, 32)
+        off = 8 if plane == 0 else 4
+        pw, ph = (w, h) if plane == 0 else ((w + 1) // 2, (h + 1) // 2)
+        rects, y0 = [], 0
+        while y0 < ph:  # foreach_rest_unit_in_tile, with the stripe offset of the vertical limits
+            uh = ph - y0 if ph - y0 < U * 3 // 2 else U
+            vs, ve = max(0, y0 - off), (y0 + uh - off if y0 + uh < ph else ph)
+            x0 = 0
+            while x0 < pw:
+                uw = pw - x0 if pw - x0 < U * 3 // 2 else U
+                rects.append((x0, x0 + uw, vs, ve))
+                x0 += uw
+            y0 += uh
+        n_u, n_e = len(rects), len(eps)
+        r = torch.tensor(rects, dtype=torch.int32, device="cuda")
+        flt = torch.zeros(n_e * 2 * ph * pw, dtype=torch.int32, device="cuda")
+        sums = torch.zeros(n_u * n_e * 5, dtype=torch.int64, device="cuda")
+        mw, mh = max(a[1] - a[0] for a in rects), max(a[3] - a[2] for a in rects)
+        a, b = dd.struct(), ds.struct()
+        ep_arr = (C.c_int32 * n_e)(*eps)
+        sb.check(lib.svt_b200_lr_sgr_filter_sums(C.byref(a), C.byref(b), plane, C.c_void_p(r.data_ptr()), n_u, mw, mh, ep_arr, n_e,
+                                                 C.c_void_p(flt.data_ptr()), C.c_void_p(sums.data_ptr()), None), lib)
+        xq = rng.integers(-60, 90, (n_u, n_e, 2)).astype(np.int32)
+        dxq = torch.from_numpy(xq).cuda()
+        err = torch.zeros(n_u * n_e, dtype=torch.int64, device="cuda")
+        sb.check(lib.svt_b200_lr_sgr_proj_error(C.byref(a), C.byref(b), plane, C.c_void_p(r.data_ptr()), n_u, mw, mh, ep_arr, n_e,
+                                                C.c_void_p(flt.data_ptr()), C.c_void_p(dxq.data_ptr()), C.c_void_p(err.data_ptr()), None), lib)
+        torch.cuda.synchronize()
+        g_flt = flt.cpu().numpy().reshape(n_e, 2, ph, pw)
+        g_sums = sums.cpu().numpy().reshape(n_u, n_e, 5)
+        g_err = err.cpu().numpy().reshape(n_u, n_e)
+        ext = np.ascontiguousarray(np.pad(dgd.plane(plane), 8, mode="edge"))
+        sp = src.plane(plane)
+        hbd = bd > 8
+        check_units = range(n_u) if n_u <= 12 else sorted(set([0, n_u - 1] + list(rng.choice(n_u, 8, replace=False))))
+        for ui in check_units:
+            hs, he, vs, ve = rects[ui]
+            for ei, ep in enumerate(eps):
+                f0, f1 = np.zeros((ve - vs, he - hs), np.int32), np.zeros((ve - vs, he - hs), np.int32)
+                for i in range(0, ve - vs, PU):      # apply_sgr: processing units tiled from the unit's origin
+                    for j in range(0, he - hs, PU):
+                        ww, hh = min(PU, he - hs - j), min(PU, ve - vs - i)
+                        t0, t1 = np.zeros((hh, ww), np.int32), np.zeros((hh, ww), np.int32)
+                        p = ext.ctypes.data + ((vs + i + 8) * ext.shape[1] + hs + j + 8) * ext.itemsize
+                        orc.orc_selfguided_restoration(C.c_void_p(p), int(hbd), ww, hh, ext.shape[1], cm.ptr(t0), cm.ptr(t1), ww, ep, bd)
+                        f0[i:i + hh, j:j + ww], f1[i:i + hh, j:j + ww] = t0, t1
+                r0, r1 = SGR_R[ep]
+                if r0:
+                    np.testing.assert_array_equal(g_flt[ei, 0, vs:ve, hs:he], f0, err_msg=f"flt0 plane {plane} unit {ui} ep {ep}")
+                if r1:
+                    np.testing.assert_array_equal(g_flt[ei, 1, vs:ve, hs:he], f1, err_msg=f"flt1 plane {plane} unit {ui} ep {ep}")
+                d = dgd.plane(plane)[vs:ve, hs:he].astype(np.int64)
+                s = sp[vs:ve, hs:he].astype(np.int64)
+                u = d << 4
+                a1 = (f0.astype(np.int64) - u) if r0 else np.zeros_like(u)
+                a2 = (f1.astype(np.int64) - u) if r1 else np.zeros_like(u)
+                sv = (s << 4) - u
+                want = [int((a1 * a1).sum()), int((a2 * a2).sum()), int((a1 * a2).sum()), int((a1 * sv).sum()), int((a2 * sv).sum())]
+                assert list(g_sums[ui, ei]) == want, (plane, ui, ep)
+                assert g_err[ui, ei] == mo.pixel_proj_error(s, d, f0, f1, (int(xq[ui, ei, 0]), int(xq[ui, ei, 1])), (r0, r1), hbd)
