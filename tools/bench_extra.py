@@ -1,0 +1,131 @@
+#!/usr/bin/env python
+"""Device time of the §8 rows that are not part of the preset-8 headline step (loop restoration, deblocking level search),
+1080p 8-bit, next to the reference C implementation of the same call on the host (oracle/_ref, single thread).
+One JSON object on stdout; run on the GPU box: python tools/bench_extra.py > gpurun_out/extra.json"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "svt-av1_b200"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import common as cm  # noqa: E402
+import gpu_runner as gr  # noqa: E402
+import svtb200 as sb  # noqa: E402
+from test_oracle_lr_frame import lr_case, run_ref_lr  # noqa: E402
+from test_oracle_dlf import pick_case, pick_params, run_ref_pick  # noqa: E402
+from test_dlf_gpu import flat_mi  # noqa: E402
+
+W, H, BD = 1920, 1080, 8
+lib = sb.load()
+peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
+
+
+def gpu_ms(fn, n=20):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+out = {"geometry": f"{W}x{H} {BD}-bit 4:2:0", "hbm_peak_gbs": peak, "rows": []}
+samples = W * H * 3 // 2
+
+# ---- svt_av1_loop_restoration_filter_frame ------------------------------------------------------------------------
+unit_sizes, ftypes = (64, 32, 32), (3, 3, 3)
+cdef, dblk, units = lr_case(W, H, BD, 7, unit_sizes, ("mix", "mix", "mix"))
+dc, dd = gr.DevYuv(cdef), gr.DevYuv(dblk)
+do = gr.DevYuv(cdef.copy())
+dus = [torch.from_numpy(np.frombuffer(u, dtype=np.uint8).copy()).cuda() for u in units]
+p = sb.LrFrameParams()
+for i in range(3):
+    p.plane[i].frame_restoration_type, p.plane[i].restoration_unit_size, p.plane[i].units = ftypes[i], unit_sizes[i], dus[i].data_ptr()
+cs, ds, os_ = dc.struct(), dd.struct(), do.struct()
+ms = gpu_ms(lambda: sb.check(lib.svt_b200_lr_frame(C.byref(p), C.byref(cs), C.byref(ds), C.byref(os_), None), lib))
+t0 = time.perf_counter()
+run_ref_lr(cdef, dblk, units, unit_sizes, ftypes, 0)
+ref_ms = (time.perf_counter() - t0) * 1e3
+alg = samples * 2
+out["rows"].append({"entry": "svt_b200_lr_frame (units 64/32, Wiener/SGR/none mixed)", "gpu_ms": ms, "algorithmic_bytes": alg,
+                    "achieved_gbs": alg / ms / 1e6, "hbm_frac": alg / ms / 1e6 / peak, "reference_c_ms_1thread": ref_ms})
+
+# ---- search_wiener's compute_stats for the whole luma plane --------------------------------------------------------
+src = cm.synth_yuv(W, H, 1, 21, BD)
+dgd = cm.degrade(src, 22, amp=8)
+dg, dsrc = gr.DevYuv(dgd), gr.DevYuv(src)
+rects = [(x, min(x + 64, W), y, min(y + 64, H)) for y in range(0, H, 64) for x in range(0, W, 64)]
+r = torch.tensor(rects, dtype=torch.int32, device="cuda")
+stats = torch.zeros(len(rects) * (49 + 49 * 49), dtype=torch.int64, device="cuda")
+scr = torch.zeros(len(rects), dtype=torch.int64, device="cuda")
+a, b = dg.struct(), dsrc.struct()
+ms = gpu_ms(lambda: sb.check(lib.svt_b200_lr_wiener_stats(C.byref(a), C.byref(b), 0, 7, C.c_void_p(r.data_ptr()), len(rects), 64, 64,
+                                                          C.c_void_p(stats.data_ptr()), C.c_void_p(scr.data_ptr()), None), lib))
+ref = cm.refh()
+ext, sext = np.pad(dgd.plane(0), 3, mode="edge"), np.pad(src.plane(0), 3, mode="edge")
+M, Hm = np.zeros(49, np.int64), np.zeros(49 * 49, np.int64)
+t0 = time.perf_counter()
+for (hs, he, vs, ve) in rects[::8]:
+    ref.svt_av1_compute_stats_c(7, cm.ptr(ext), cm.ptr(sext), hs + 3, he + 3, vs + 3, ve + 3, ext.shape[1], sext.shape[1], cm.ptr(M), cm.ptr(Hm))
+ref_ms = (time.perf_counter() - t0) * 1e3 * 8
+macs = W * H * (49 * 50 // 2 + 49)
+out["rows"].append({"entry": "svt_b200_lr_wiener_stats (luma, win 7, 510 units)", "gpu_ms": ms, "int_macs": macs, "achieved_tmacs": macs / ms / 1e9,
+                    "reference_c_ms_1thread": ref_ms})
+
+# ---- self-guided search: all 16 parameter sets, luma -----------------------------------------------------------------
+eps = (C.c_int32 * 16)(*range(16))
+flt = torch.zeros(16 * 2 * W * H, dtype=torch.int32, device="cuda")
+sums = torch.zeros(len(rects) * 16 * 5, dtype=torch.int64, device="cuda")
+ms = gpu_ms(lambda: sb.check(lib.svt_b200_lr_sgr_filter_sums(C.byref(a), C.byref(b), 0, C.c_void_p(r.data_ptr()), len(rects), 64, 64, eps, 16,
+                                                             C.c_void_p(flt.data_ptr()), C.c_void_p(sums.data_ptr()), None), lib), n=5)
+xq = torch.zeros(len(rects) * 16 * 2, dtype=torch.int32, device="cuda")
+err = torch.zeros(len(rects) * 16, dtype=torch.int64, device="cuda")
+ms2 = gpu_ms(lambda: sb.check(lib.svt_b200_lr_sgr_proj_error(C.byref(a), C.byref(b), 0, C.c_void_p(r.data_ptr()), len(rects), 64, 64, eps, 16,
+                                                             C.c_void_p(flt.data_ptr()), C.c_void_p(xq.data_ptr()), C.c_void_p(err.data_ptr()), None), lib), n=5)
+f0, f1 = np.zeros((64, 64), np.int32), np.zeros((64, 64), np.int32)
+t0 = time.perf_counter()
+for (hs, he, vs, ve) in rects[::32]:
+    for ep in range(16):
+        ref.svt_av1_selfguided_restoration_c(C.c_void_p(ext.ctypes.data + (vs + 3) * ext.shape[1] + hs + 3), he - hs, ve - vs, ext.shape[1],
+                                             cm.ptr(f0), cm.ptr(f1), 64, ep, 8, 0)
+ref_ms = (time.perf_counter() - t0) * 1e3 * 32
+out["rows"].append({"entry": "svt_b200_lr_sgr_filter_sums (luma, 16 parameter sets, 510 units)", "gpu_ms": ms,
+                    "hbm_bytes_written": 16 * 2 * 4 * W * H, "achieved_gbs": 16 * 2 * 4 * W * H / ms / 1e6,
+                    "reference_c_ms_1thread (filter only)": ref_ms})
+out["rows"].append({"entry": "svt_b200_lr_sgr_proj_error (one hill-climb step, 16 sets x 510 units)", "gpu_ms": ms2,
+                    "algorithmic_bytes": 16 * (2 * 4 + 2) * W * H, "achieved_gbs": 16 * (2 * 4 + 2) * W * H / ms2 / 1e6})
+
+# ---- svt_av1_pick_filter_level (full-image search) -------------------------------------------------------------------
+mi_rows, mi_cols, part, psrc, prec = pick_case(W, H, BD, 6)
+last = (24, 20, 14, 10)
+flat = flat_mi(mi_rows, mi_cols, part, last)
+pp = pick_params(mi_rows, mi_cols, 0, 3, last)
+t0 = time.perf_counter()
+got, _ = gr.run_gpu_pick(pp, prec, psrc, flat)  # includes the uploads of this helper
+torch.cuda.synchronize()
+dr, dsrc2, dt = gr.DevYuv(prec.copy()), gr.DevYuv(psrc), gr.DevYuv(prec.copy())
+dmi = torch.from_numpy(np.frombuffer(flat, dtype=np.uint8).copy()).cuda()
+scratch = torch.zeros(1024, dtype=torch.uint8, device="cuda")
+rs, ss2, ts = dr.struct(), dsrc2.struct(), dt.struct()
+lv = (C.c_int32 * 4)()
+t0 = time.perf_counter()
+for _ in range(3):
+    sb.check(lib.svt_b200_pick_filter_level(C.byref(pp), C.byref(rs), C.byref(ss2), C.byref(ts), C.c_void_p(dmi.data_ptr()),
+                                            C.c_void_p(scratch.data_ptr()), lv, None), lib)
+wall = (time.perf_counter() - t0) / 3 * 1e3
+t0 = time.perf_counter()
+want, _ = run_ref_pick(mi_rows, mi_cols, part, psrc, prec, 0, 3, last)
+ref_ms = (time.perf_counter() - t0) * 1e3
+out["rows"].append({"entry": "svt_b200_pick_filter_level (LPF_PICK_FROM_FULL_IMAGE, loop_filter_mode 3)", "wall_ms_incl_host_bisection": wall,
+                    "levels": list(lv), "reference_levels": want, "reference_c_ms_1thread": ref_ms})
+print(json.dumps(out, indent=1))
