@@ -276,6 +276,9 @@ class DeviceSet:
         # {source Cb, Cr, prediction Y, Cb, Cr}
         self.me_flat = [flat_pack(torch, pics) for pics in self.me_host]
         self.in_flat = [flat_pack(torch, f[1:] + g) for f, g in zip(self.src_host, self.pred_host)]
+        # ... and the whole step's uploads as two pinned blocks (the next step is uploaded while this one computes)
+        self.me_step = torch.cat(self.me_flat).pin_memory()
+        self.in_step = torch.cat(self.in_flat[2:2 + FRAMES_PER_STEP]).pin_memory()
 
 
 def flat_layout(tensors, align=256):
@@ -379,17 +382,19 @@ def run_b200(args):
             # ---- e2e arm.  Uploads and read-backs are ONE block per picture and direction (the step issues ~80 copies
             # instead of ~200: the Python-side issue time was the end-to-end bound), the library writes into views.
             s0 = sets[0]
-            self.e_me_flat = [dev(s0.me_flat[0].numel(), torch.uint8) for _ in range(F + 4)]
-            self.e_me = [flat_views(torch, fl, s0.me_host[0]) for fl in self.e_me_flat]
-            self.e_in_flat = [dev(s0.in_flat[0].numel(), torch.uint8) for _ in range(F + 4)]
-            ins = [flat_views(torch, fl, s0.src_host[0][1:] + s0.pred_host[0]) for fl in self.e_in_flat]
-            self.e_src = [[None] + v[:2] for v in ins]  # luma comes from the ME plane
-            self.e_pred = [v[2:] for v in ins]
+            msz, isz = s0.me_flat[0].numel(), s0.in_flat[0].numel()
+            self.e_me_all, self.e_in_all = dev(msz * (F + 4), torch.uint8), dev(isz * F, torch.uint8)
+            self.e_me = [flat_views(torch, self.e_me_all[j * msz:(j + 1) * msz], s0.me_host[0]) for j in range(F + 4)]
+            ins = [flat_views(torch, self.e_in_all[j * isz:(j + 1) * isz], s0.src_host[0][1:] + s0.pred_host[0]) for j in range(F)]
+            pad2 = [None, None]  # pictures 0, 1 and F+2, F+3 are references only
+            self.e_src = pad2 + [[None] + v[:2] for v in ins] + pad2  # luma comes from the ME plane
+            self.e_pred = pad2 + [v[2:] for v in ins] + pad2
             self.e_mi, self.e_skip = torch.empty_like(d_mi), torch.empty_like(d_skip)
             self.e_idx = [dev(nfb, torch.int8) for _ in range(F)]
             self.h_idx = [torch.zeros(nfb, dtype=torch.int8).pin_memory() for _ in range(F)]
-            self.d_pack = [{ts: torch.empty_like(self.d_q[i][ts]) for ts in tus} for i in range(F)]
-            self.h_pack = [{ts: pinned(self.d_q[i][ts].numel(), torch.int32) for ts in tus} for i in range(F)]
+            cap = sum(self.d_q[0][ts].numel() for ts in tus)  # one packed level stream per picture (all transform sizes)
+            self.d_pack = [dev(cap, torch.int32) for _ in range(F)]
+            self.h_pack = [pinned(cap, torch.int32) for _ in range(F)]
             # small urgent read-back: CDEF mse table + the three packed sizes
             like_fast = [torch.empty(2 * nfb * 64, dtype=torch.int64), torch.empty(4, dtype=torch.int32)]
             # bulk read-back of the front half: MeSbResults, eobs, level offsets
@@ -456,18 +461,20 @@ def run_b200(args):
             s = planes(me_dev[f])
             outs = sb.MeOutputs(o["best_sad"].data_ptr(), o["best_mv"].data_ptr(), o["hme"].data_ptr(), o["me_mv"].data_ptr(),
                                 o["me_cand"].data_ptr(), o["total_cand"].data_ptr(), o["rc"].data_ptr())
+            order = list(tus)  # the packed stream chains the transform sizes: each call starts where the previous one ended
             enc = [(C.byref(enc_params[ts]), C.c_void_p(tu_dev[ts].data_ptr()), len(tus[ts]), C.c_void_p(B.d_q[i][ts].data_ptr()),
-                    C.c_void_p(o_eob[ts].data_ptr()), ts, C.c_void_p(B.d_pack[i][ts].data_ptr()), C.c_void_p(B.d_off[i][ts].data_ptr()),
-                    C.c_void_p(B.d_tot[i].data_ptr() + 4 * ts)) for ts in tus]
+                    C.c_void_p(o_eob[ts].data_ptr()), ts, C.c_void_p(B.d_pack[i].data_ptr()), C.c_void_p(B.d_off[i][ts].data_ptr()),
+                    C.c_void_p(B.d_tot[i].data_ptr() + 4 * n_), C.c_void_p(B.d_tot[i].data_ptr() + 4 * (n_ - 1)) if n_ else None)
+                   for n_, ts in enumerate(order)]
             a = (fs, fp, fr, refs, s, outs, enc, B.me_scratch[i].data_ptr(), C.c_void_p(mi_dev.data_ptr()), C.c_void_p(skip_dev.data_ptr()),
                  C.c_void_p(o_mse.data_ptr()), C.c_void_p(enc_scratch.data_ptr()))
             arg_cache[key] = a
         fs, fp, fr, refs, s, outs, enc, scr, mi_p, skip_p, mse_p, es_p = a
         sb.check(lib.svt_b200_me_picture(C.byref(me_params), C.byref(s), refs, C.byref(outs), scr, q), lib)
-        for (ep, tu_p, n, q_p, eob_p, ts, pk_p, off_p, tot_p) in enc:
+        for (ep, tu_p, n, q_p, eob_p, ts, pk_p, off_p, tot_p, base_p) in enc:
             sb.check(lib.svt_b200_encode_tus(ep, C.byref(fs), C.byref(fp), C.byref(fr), tu_p, n, q_p, eob_p, es_p, q), lib)
             if pack:  # levels in scan order up to eob: what goes back to the host's entropy coder
-                sb.check(lib.svt_b200_pack_levels(ts, 0, q_p, eob_p, n, pk_p, off_p, tot_p, q), lib)
+                sb.check(lib.svt_b200_pack_levels_at(ts, 0, q_p, eob_p, n, pk_p, off_p, tot_p, base_p, q), lib)
         sb.check(lib.svt_b200_dlf_frame(C.byref(dlp), C.byref(fr), mi_p, q), lib)
         sb.check(lib.svt_b200_cdef_search(C.byref(csp), C.byref(fr), C.byref(fs), skip_p, skip8.shape[1], mse_p, q), lib)
 
@@ -584,22 +591,13 @@ def run_b200(args):
         for st in all_streams():  # the instance was last used by step k-NB
             for ev in B.done:
                 st.wait_event(ev)
-        me_ready, in_ready = [], []
-        with torch.cuda.stream(copy_stream):
+        with torch.cuda.stream(copy_stream):  # the whole step's inputs: two blocks (+ the mode-info summaries)
             B.e_mi.copy_(h_mi, non_blocking=True)
             B.e_skip.copy_(h_skip, non_blocking=True)
-            for j in range(F + 4):  # ME planes of the F+4 pictures (shared by neighbouring pictures), display order
-                B.e_me_flat[j].copy_(s.me_flat[j], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-                me_ready.append(ev)
-                i = j - 4  # picture i needs ME pictures i .. i+4: its chroma / prediction planes follow picture i+4
-                if i >= 0:
-                    f = i + 2
-                    B.e_in_flat[f].copy_(s.in_flat[f], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(copy_stream)
-                    in_ready.append(ev)
+            B.e_me_all.copy_(s.me_step, non_blocking=True)
+            B.e_in_all.copy_(s.in_step, non_blocking=True)
+            up_ready = torch.cuda.Event()
+            up_ready.record(copy_stream)
         mse_ready = []
         tl = timeline.setdefault(k, {}) if dbg is not None else None
         if tl is not None:
@@ -607,7 +605,7 @@ def run_b200(args):
             tl["h2d_end"].record(copy_stream)
         for i in range(F):
             q, f = i % NS, i + 2
-            streams[q].wait_event(in_ready[i])
+            streams[q].wait_event(up_ready)
             if tl is not None:
                 tl["fs%d" % i] = torch.cuda.Event(enable_timing=True)
                 tl["fs%d" % i].record(streams[q])
@@ -660,11 +658,10 @@ def run_b200(args):
                 timeline[k]["be%d" % i] = done
             d2h_bulk.wait_event(done)
             with torch.cuda.stream(d2h_bulk):
-                for ts in tus:  # the packed levels: their size came back with the CDEF table
-                    n = int(B.h_tot[i][ts])
-                    if n:
-                        B.h_pack[i][ts][:n].copy_(B.d_pack[i][ts][:n], non_blocking=True)
-                    packed += 4 * n
+                n = int(B.h_tot[i][len(tus) - 1])  # the packed level stream: its length came back with the CDEF table
+                if n:
+                    B.h_pack[i][:n].copy_(B.d_pack[i][:n], non_blocking=True)
+                packed += 4 * n
                 B.h_out_flat[i].copy_(B.d_out_flat[i], non_blocking=True)
         d2h_count[0] = packed
         if dbg is not None:
@@ -677,7 +674,7 @@ def run_b200(args):
             B.done.append(ev)
 
     B0 = bufs[0]
-    h2d = sets[0].me_flat[0].numel() * (F + 4) + sets[0].in_flat[0].numel() * F + h_mi.numel() + h_skip.numel() + F * nfb
+    h2d = sets[0].me_step.numel() + sets[0].in_step.numel() + h_mi.numel() + h_skip.numel() + F * nfb
 
     def d2h_bytes():  # the fixed-size read-back blocks + the packed levels of the last e2e step
         return F * (B0.h_fast_flat[0].numel() + B0.h_bulk_flat[0].numel() + B0.h_out_flat[0].numel()) + d2h_count[0]

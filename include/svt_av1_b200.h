@@ -424,6 +424,12 @@ SVT_B200_API int svt_b200_encode_tus(const SvtB200EncodeParams *p, const SvtB200
  * All pointers are device pointers; packed must hold n_tus * min(w,32) * min(h,32) entries in the worst case. */
 SVT_B200_API int svt_b200_pack_levels(int32_t tx_size, int32_t tx_class, const int32_t *qcoeff, const uint16_t *eob,
                                       int32_t n_tus, int32_t *packed, uint32_t *offsets, uint32_t *total, void *stream);
+/* Same, appending to a stream that already holds *base entries (base: DEVICE uint32, e.g. the `total` of the previous
+ * call): offsets start at *base and *total = *base + sum(eob).  Lets the calls of one picture (one per transform size)
+ * build ONE packed stream, fetched with one copy. */
+SVT_B200_API int svt_b200_pack_levels_at(int32_t tx_size, int32_t tx_class, const int32_t *qcoeff, const uint16_t *eob,
+                                         int32_t n_tus, int32_t *packed, uint32_t *offsets, uint32_t *total,
+                                         const uint32_t *base, void *stream);
 /* Same, plus cul_level[n_tus] (device int32, may be NULL): the value av1_quantize_inv_quantize returns
  * (EbFullLoop.c:1596-1608): min(63, sum |qcoeff|) with set_dc_sign of the DC level (bit 6 negative, +128 positive). */
 SVT_B200_API int svt_b200_encode_tus_cul(const SvtB200EncodeParams *p, const SvtB200Frame *src,

@@ -489,7 +489,8 @@ __global__ void __launch_bounds__(TX_NT) encode_tu_kernel(const __grid_constant_
 // rate).  Two launches: exclusive scan of eob (one CTA; <= 32 K TUs per call is far above a 4K frame's count per
 // transform size), then the gather.
 // ---------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) eob_scan_kernel(const uint16_t *eob, int n, uint32_t *offsets /*[n+1]*/, uint32_t *total) {
+__global__ void __launch_bounds__(1024) eob_scan_kernel(const uint16_t *eob, int n, uint32_t *offsets /*[n+1]*/, uint32_t *total,
+                                                        const uint32_t *base /* device: first offset, or null = 0 */) {
     __shared__ uint32_t s_part[1024];
     const int per = (n + 1023) / 1024, t = threadIdx.x;
     uint32_t sum = 0;
@@ -502,14 +503,15 @@ __global__ void __launch_bounds__(1024) eob_scan_kernel(const uint16_t *eob, int
         s_part[t] += v;
         __syncthreads();
     }
-    uint32_t run = t ? s_part[t - 1] : 0;
+    const uint32_t b0 = base ? *base : 0u;
+    uint32_t run = b0 + (t ? s_part[t - 1] : 0);
     for (int i = t * per; i < min(n, (t + 1) * per); i++) {
         offsets[i] = run;
         run += eob[i];
     }
     if (t == 1023) {
-        offsets[n] = s_part[1023];
-        *total = s_part[1023];
+        offsets[n] = b0 + s_part[1023];
+        *total = b0 + s_part[1023];
     }
 }
 __global__ void __launch_bounds__(256) pack_levels_kernel(const int32_t *qcoeff, const uint16_t *eob, const uint32_t *offsets,
@@ -926,6 +928,11 @@ extern "C" {
 // see include/svt_av1_b200.h
 int svt_b200_pack_levels(int32_t tx_size, int32_t tx_class, const int32_t *qcoeff, const uint16_t *eob, int32_t n_tus, int32_t *packed,
                          uint32_t *offsets, uint32_t *total, void *stream) {
+    return svt_b200_pack_levels_at(tx_size, tx_class, qcoeff, eob, n_tus, packed, offsets, total, nullptr, stream);
+}
+
+int svt_b200_pack_levels_at(int32_t tx_size, int32_t tx_class, const int32_t *qcoeff, const uint16_t *eob, int32_t n_tus, int32_t *packed,
+                            uint32_t *offsets, uint32_t *total, const uint32_t *base, void *stream) {
     if (tx_size < 0 || tx_size > 18 || tx_class < 0 || tx_class > 2 || !qcoeff || !eob || !packed || !offsets || !total || n_tus < 0 ||
         n_tus > (1 << 20)) {
         set_error("svt_b200_pack_levels: bad argument");
@@ -933,14 +940,19 @@ int svt_b200_pack_levels(int32_t tx_size, int32_t tx_class, const int32_t *qcoef
     }
     cudaStream_t st = (cudaStream_t)stream;
     if (n_tus == 0) {
-        SVTB_CUDA_TRY(cudaMemsetAsync(total, 0, 4, st));
-        SVTB_CUDA_TRY(cudaMemsetAsync(offsets, 0, 4, st));
+        if (base) {
+            SVTB_CUDA_TRY(cudaMemcpyAsync(total, base, 4, cudaMemcpyDeviceToDevice, st));
+            SVTB_CUDA_TRY(cudaMemcpyAsync(offsets, base, 4, cudaMemcpyDeviceToDevice, st));
+        } else {
+            SVTB_CUDA_TRY(cudaMemsetAsync(total, 0, 4, st));
+            SVTB_CUDA_TRY(cudaMemsetAsync(offsets, 0, 4, st));
+        }
         return SVT_B200_OK;
     }
     const int16_t *tab = scan_tables(tx_size);
     if (!tab) return SVT_B200_ERR_CUDA;
     const int n = (h_txw[tx_size] > 32 ? 32 : h_txw[tx_size]) * (h_txh[tx_size] > 32 ? 32 : h_txh[tx_size]);
-    SVTB_LAUNCH(eob_scan_kernel, 1, 1024, 0, st, eob, n_tus, offsets, total);
+    SVTB_LAUNCH(eob_scan_kernel, 1, 1024, 0, st, eob, n_tus, offsets, total, base);
     SVTB_LAUNCH(pack_levels_kernel, (n_tus + 7) / 8, 256, 0, st, qcoeff, eob, offsets, tab + 3072 + tx_class * 1024, n_tus, n, packed);
     SVTB_CUDA_TRY(cudaGetLastError());
     return SVT_B200_OK;

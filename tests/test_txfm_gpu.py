@@ -292,6 +292,43 @@ def test_pack_levels(tx_size, tx_class):
         np.testing.assert_array_equal(got[want_off[b]:want_off[b + 1]], q[b, scan[:eob[b]]])
 
 
+def test_pack_levels_at_chained():
+    """svt_b200_pack_levels_at: three transform sizes chained into ONE packed stream (each call starts where the previous
+    one ended, the start read on the device), plus the n_tus == 0 pass-through."""
+    import torch
+    lib = sb.load()
+    rng = np.random.default_rng(911)
+    packed = torch.zeros(1 << 21, dtype=torch.int32, device="cuda")
+    tot = torch.zeros(5, dtype=torch.int32, device="cuda")
+    want, base, offs_want, offs_got = [], 0, [], []
+    sizes = [(2, 700), (1, 900), (4, 0), (0, 1500)]
+    for k, (tx_size, n_tus) in enumerate(sizes):
+        n = min(TX_W[tx_size], 32) * min(TX_H[tx_size], 32)
+        scan = np.zeros(1024, np.int16)
+        assert lib.svt_b200_get_scan(tx_size, 0, cm.ptr(scan)) >= 0
+        q = np.zeros((max(n_tus, 1), n), np.int32)
+        eob = np.zeros(max(n_tus, 1), np.uint16)
+        for b in range(n_tus):
+            e = int(rng.integers(0, n + 1)) if b % 4 else 0
+            eob[b] = e
+            q[b, scan[:e]] = rng.integers(1, 200, e) * rng.choice([-1, 1], e)
+            want.append(q[b, scan[:e]])
+        dq, de = torch.from_numpy(q).cuda(), torch.from_numpy(eob.view(np.int16)).cuda()
+        off = torch.zeros(n_tus + 1, dtype=torch.int32, device="cuda")
+        base_p = C.c_void_p(tot.data_ptr() + 4 * (k - 1)) if k else None
+        sb.check(lib.svt_b200_pack_levels_at(tx_size, 0, C.c_void_p(dq.data_ptr()), C.c_void_p(de.data_ptr()), n_tus,
+                                             C.c_void_p(packed.data_ptr()), C.c_void_p(off.data_ptr()),
+                                             C.c_void_p(tot.data_ptr() + 4 * k), base_p, None), lib)
+        torch.cuda.synchronize()
+        offs_got.append(off.cpu().numpy())
+        offs_want.append(base + np.concatenate([[0], np.cumsum(eob[:n_tus].astype(np.int64))]))
+        base = int(offs_want[-1][-1])
+    for g, w in zip(offs_got, offs_want):
+        np.testing.assert_array_equal(g, w)
+    np.testing.assert_array_equal(tot.cpu().numpy()[:4], [o[-1] for o in offs_want])
+    np.testing.assert_array_equal(packed.cpu().numpy()[:base], np.concatenate(want))
+
+
 class TxfmParam(C.Structure):  # EbDefinitions.h:779-791 (tx_type / tx_size / tx_set_type are 1-byte packed enums)
     _fields_ = [("tx_type", C.c_uint8), ("tx_size", C.c_uint8), ("lossless", C.c_int32), ("bd", C.c_int32), ("is_hbd", C.c_int32),
                 ("tx_set_type", C.c_uint8), ("eob", C.c_int32)]
