@@ -680,6 +680,94 @@ SVT_B200_API int svt_b200_lr_sgr_proj_error(const SvtB200Frame *dgd, const SvtB2
                                             const int32_t *eps, int32_t n_eps, const int32_t *flt, const int32_t *xq,
                                             int64_t *err, void *stream);
 
+/* =============================================================================================== */
+/* Inter prediction (translational): the sub-pel interpolation filters          */
+/* =============================================================================================== */
+
+/* Layout-compatible mirrors of the two reference structs the convolve pointers take
+ * (InterpFilterParams EbDefinitions.h:493-498, ConvolveParams EbDefinitions.h:379-392). */
+typedef struct SvtB200InterpFilterParams {
+    const int16_t *filter_ptr; /* [subpel_shifts][taps] */
+    uint16_t taps, subpel_shifts;
+    int32_t interp_filter; /* InterpFilter enum (unused here) */
+} SvtB200InterpFilterParams;
+typedef struct SvtB200ConvolveParams {
+    int32_t ref, do_average;
+    uint16_t *dst; /* CONV_BUF of the compound path */
+    int32_t dst_stride, round_0, round_1, plane, is_compound, use_jnt_comp_avg, fwd_offset, bck_offset,
+        use_dist_wtd_comp_avg;
+} SvtB200ConvolveParams;
+
+/* replace svt_av1_convolve_{2d_sr,x_sr,y_sr,2d_copy_sr} and svt_av1_jnt_convolve_{2d,x,y,2d_copy}
+ * (common_dsp_rtcd.h:194-211; C impl EbInterPrediction.c:349-480, :552-745) and their highbd forms (:212-229; C impl
+ * :747-1145).  Host pointers, same argument meaning; taps are always 8 (the reference's 4-tap kernels are zero padded).
+ * The jnt forms read (do_average) or write conv_params->dst exactly as the C code does. */
+#define SVT_B200_CONVOLVE_DECL(NAME)                                                                                  \
+    SVT_B200_API void NAME##_cuda(const uint8_t *src, int32_t src_stride, uint8_t *dst, int32_t dst_stride, int32_t w, \
+                                  int32_t h, SvtB200InterpFilterParams *filter_params_x,                               \
+                                  SvtB200InterpFilterParams *filter_params_y, const int32_t subpel_x_q4,               \
+                                  const int32_t subpel_y_q4, SvtB200ConvolveParams *conv_params);
+#define SVT_B200_HBD_CONVOLVE_DECL(NAME)                                                                               \
+    SVT_B200_API void NAME##_cuda(const uint16_t *src, int32_t src_stride, uint16_t *dst, int32_t dst_stride,          \
+                                  int32_t w, int32_t h, const SvtB200InterpFilterParams *filter_params_x,              \
+                                  const SvtB200InterpFilterParams *filter_params_y, const int32_t subpel_x_q4,         \
+                                  const int32_t subpel_y_q4, SvtB200ConvolveParams *conv_params, int32_t bd);
+SVT_B200_CONVOLVE_DECL(svt_av1_convolve_2d_copy_sr)
+SVT_B200_CONVOLVE_DECL(svt_av1_convolve_2d_sr)
+SVT_B200_CONVOLVE_DECL(svt_av1_convolve_x_sr)
+SVT_B200_CONVOLVE_DECL(svt_av1_convolve_y_sr)
+SVT_B200_CONVOLVE_DECL(svt_av1_jnt_convolve_2d_copy)
+SVT_B200_CONVOLVE_DECL(svt_av1_jnt_convolve_2d)
+SVT_B200_CONVOLVE_DECL(svt_av1_jnt_convolve_x)
+SVT_B200_CONVOLVE_DECL(svt_av1_jnt_convolve_y)
+SVT_B200_HBD_CONVOLVE_DECL(svt_av1_highbd_convolve_2d_copy_sr)
+SVT_B200_HBD_CONVOLVE_DECL(svt_av1_highbd_convolve_2d_sr)
+SVT_B200_HBD_CONVOLVE_DECL(svt_av1_highbd_convolve_x_sr)
+SVT_B200_HBD_CONVOLVE_DECL(svt_av1_highbd_convolve_y_sr)
+SVT_B200_HBD_CONVOLVE_DECL(svt_av1_highbd_jnt_convolve_2d_copy)
+SVT_B200_HBD_CONVOLVE_DECL(svt_av1_highbd_jnt_convolve_2d)
+SVT_B200_HBD_CONVOLVE_DECL(svt_av1_highbd_jnt_convolve_x)
+SVT_B200_HBD_CONVOLVE_DECL(svt_av1_highbd_jnt_convolve_y)
+
+/* replace svt_aom_convolve8_horiz / svt_aom_convolve8_vert (common_dsp_rtcd.h:230-233; convolve.c:249-308): filter_x /
+ * filter_y point INTO a 256-byte aligned [16][8] kernel table (get_filter_base / get_filter_offset, convolve.c), the
+ * position steps by x_step_q4 / y_step_q4 sixteenths per output sample. */
+SVT_B200_API void svt_aom_convolve8_horiz_cuda(const uint8_t *src, ptrdiff_t src_stride, uint8_t *dst, ptrdiff_t dst_stride,
+                                               const int16_t *filter_x, int x_step_q4, const int16_t *filter_y,
+                                               int y_step_q4, int w, int h);
+SVT_B200_API void svt_aom_convolve8_vert_cuda(const uint8_t *src, ptrdiff_t src_stride, uint8_t *dst, ptrdiff_t dst_stride,
+                                              const int16_t *filter_x, int x_step_q4, const int16_t *filter_y,
+                                              int y_step_q4, int w, int h);
+
+/* The interpolation kernel av1_get_interp_filter_params_with_block_size(filter, w) selects (EbInterPrediction.c:1251-1262:
+ * the 4-tap tables when w <= 4), row `subpel` (0..15), as this library holds it. Returns 0, or <0 on a bad argument. */
+SVT_B200_API int svt_b200_get_interp_kernel(int32_t interp_filter, int32_t w, int32_t subpel, int16_t out[8]);
+
+/* One enc_make_inter_predictor call (EbEncInterPrediction.c:3663-3762; unscaled references, no masked compound / OBMC /
+ * warp / intra-BC), or the List0 + List1 pair of calls of a BI_PRED block merged (n_refs == 2: what av1_inter_prediction
+ * :4330-4930 issues with do_average 0 then 1; the CONV_BUF intermediate stays on chip).  All positions in samples of
+ * `plane`; the host decomposes a block into its per-plane jobs exactly as av1_inter_prediction does (including the
+ * sub8x8 chroma case, :4150-4330, where each job carries the neighbour's MV / reference and the b4 size). */
+typedef struct SvtB200InterJob {
+    uint8_t plane;  /* 0 Y, 1 Cb, 2 Cr (ss_x = ss_y = plane != 0) */
+    uint8_t n_refs; /* 1, or 2 = compound */
+    uint8_t bw, bh; /* blk_width, blk_height (also select the 4-tap kernels when <= 4) */
+    uint8_t ref[2]; /* index into refs[] */
+    uint8_t filter_x, filter_y; /* av1_extract_interp_filter(interp_filters, 1 / 0): 0 regular, 1 smooth, 2 sharp, 3 bilinear */
+    uint8_t use_jnt_comp_avg, fwd_offset, bck_offset, reserved; /* svt_av1_dist_wtd_comp_weight_assign (:310-347) */
+    int16_t dst_x, dst_y; /* where the block lands in the prediction plane */
+    int16_t pre_x, pre_y; /* pu_origin_{x,y}[_chroma] */
+    int16_t mv_row[2], mv_col[2]; /* MvUnit mv[list].y / .x, 1/8 luma sample */
+    int32_t mb_to_left_edge, mb_to_right_edge, mb_to_top_edge, mb_to_bottom_edge; /* blk_ptr->av1xd */
+} SvtB200InterJob;
+
+/* Every job of a picture in one launch: refs[] = the n_refs_frames reference pictures (recon, padded at least as far as
+ * clamp_mv_to_umv_border_sb lets a block reach: bw + 4 + 4 samples beyond the picture, as EbPictureBufferDesc pads
+ * them), pred = the prediction picture, jobs = DEVICE array.  8-bit -> uint8_t planes, 10-bit -> uint16_t planes
+ * (av1_inter_prediction with is16bit).  Jobs must not overlap in pred.  Asynchronous on `stream`. */
+SVT_B200_API int svt_b200_inter_predict(const SvtB200Frame *refs, int32_t n_ref_frames, const SvtB200Frame *pred,
+                                        const SvtB200InterJob *jobs, int32_t n_jobs, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,15 @@ ORC_API void orc_wiener_convolve_add_src(const void *src, int hbd, ptrdiff_t src
                                          int round_1, int bd);
 ORC_API void orc_lr_frame(const SvtB200LrFrameParams *p, const SvtB200Frame *cdef, const SvtB200Frame *dblk, const SvtB200Frame *out,
                           const SvtB200LrUnit *const units[3]);
+/* ---- interp_oracle.c ---- */
+ORC_API void orc_interp_kernel(int filter, int w, int subpel, int16_t out[8]);
+ORC_API void orc_convolve(const void *src, int hbd, int src_stride, void *dst, int dst_stride, int w, int h, const int16_t *fx,
+                          const int16_t *fy, int round_0, int round_1, int bd, int compound, int do_average, int use_jnt,
+                          int fwd_offset, int bck_offset, uint16_t *conv_dst, int conv_stride);
+ORC_API void orc_convolve8(const uint8_t *src, ptrdiff_t src_stride, uint8_t *dst, ptrdiff_t dst_stride, const int16_t *table,
+                           int q0, int step, int w, int h, int vert);
+ORC_API void orc_inter_predict(const SvtB200Frame *refs, int n_ref_frames, const SvtB200Frame *pred, const SvtB200InterJob *jobs,
+                               int n_jobs);
 #ifdef __cplusplus
 }
 #endif

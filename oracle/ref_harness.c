@@ -738,3 +738,110 @@ REFH_API int refh_encode_tus(const SvtB200EncodeParams *p, const SvtB200Frame *s
     }
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* Inter prediction: the reference's sixteen convolve functions by index, its kernel tables, and                      */
+/* enc_make_inter_predictor per job of svt_b200_inter_predict.                                                        */
+/* ------------------------------------------------------------------------------------------------------------------ */
+#include "EbInterPrediction.h"
+#include "EbCodingUnit.h"
+#include "convolve.h"
+
+void enc_make_inter_predictor(uint8_t *src_ptr, uint8_t *dst_ptr, int16_t pre_y, int16_t pre_x, MV mv,
+                              const struct ScaleFactors *const sf, ConvolveParams *conv_params, InterpFilters interp_filters,
+                              InterInterCompoundData *interinter_comp, uint16_t frame_width, uint16_t frame_height,
+                              uint8_t blk_width, uint8_t blk_height, BlockSize bsize, MacroBlockD *av1xd, int32_t src_stride,
+                              int32_t dst_stride, uint8_t plane, const uint32_t ss_y, const uint32_t ss_x, uint8_t bit_depth,
+                              uint8_t use_intrabc, uint8_t is_masked_compound, uint8_t is16bit); /* EbEncInterPrediction.c:3663 */
+void asm_set_convolve_asm_table(void);
+void asm_set_convolve_hbd_asm_table(void);
+
+REFH_API void refh_interp_kernel(int filter, int w, int subpel, int16_t out[8]) {
+    InterpFilterParams p = av1_get_interp_filter_params_with_block_size((InterpFilter)filter, w);
+    memcpy(out, p.filter_ptr + 8 * (subpel & 15), 16);
+}
+
+/* which = sx * 4 + sy * 2 + compound, the index order of convolve[sx][sy][is_compound] (EbInterPrediction.c:1162-1175) */
+REFH_API void refh_convolve(int which, int hbd, const void *src, int src_stride, void *dst, int dst_stride, int w, int h,
+                            int filter_x, int filter_y, int subpel_x, int subpel_y, int round_0, int round_1, int do_average,
+                            int use_jnt, int fwd_offset, int bck_offset, uint16_t *conv_dst, int conv_stride, int bd) {
+    static const AomConvolveFn lo[8] = {svt_av1_convolve_2d_copy_sr_c, svt_av1_jnt_convolve_2d_copy_c, svt_av1_convolve_y_sr_c,
+                                        svt_av1_jnt_convolve_y_c,      svt_av1_convolve_x_sr_c,        svt_av1_jnt_convolve_x_c,
+                                        svt_av1_convolve_2d_sr_c,      svt_av1_jnt_convolve_2d_c};
+    static const aom_highbd_convolve_fn_t hi[8] = {
+        svt_av1_highbd_convolve_2d_copy_sr_c, svt_av1_highbd_jnt_convolve_2d_copy_c, svt_av1_highbd_convolve_y_sr_c,
+        svt_av1_highbd_jnt_convolve_y_c,      svt_av1_highbd_convolve_x_sr_c,        svt_av1_highbd_jnt_convolve_x_c,
+        svt_av1_highbd_convolve_2d_sr_c,      svt_av1_highbd_jnt_convolve_2d_c};
+    InterpFilterParams px = av1_get_interp_filter_params_with_block_size((InterpFilter)filter_x, w);
+    InterpFilterParams py = av1_get_interp_filter_params_with_block_size((InterpFilter)filter_y, h);
+    ConvolveParams cp;
+    memset(&cp, 0, sizeof(cp));
+    cp.do_average = do_average;
+    cp.dst = conv_dst;
+    cp.dst_stride = conv_stride;
+    cp.round_0 = round_0;
+    cp.round_1 = round_1;
+    cp.is_compound = which & 1;
+    cp.use_jnt_comp_avg = cp.use_dist_wtd_comp_avg = use_jnt;
+    cp.fwd_offset = fwd_offset;
+    cp.bck_offset = bck_offset;
+    if (hbd)
+        hi[which]((const uint16_t *)src, src_stride, (uint16_t *)dst, dst_stride, w, h, &px, &py, subpel_x, subpel_y, &cp, bd);
+    else
+        lo[which]((const uint8_t *)src, src_stride, (uint8_t *)dst, dst_stride, w, h, &px, &py, subpel_x, subpel_y, &cp);
+}
+
+REFH_API void refh_convolve8(const uint8_t *src, ptrdiff_t src_stride, uint8_t *dst, ptrdiff_t dst_stride, int filter, int q0,
+                             int step, int w, int h, int vert) {
+    InterpFilterParams p = av1_get_interp_filter_params_with_block_size((InterpFilter)filter, 8);
+    const int16_t *f = p.filter_ptr + 8 * q0; /* the tables are 256-byte aligned (EbInterPrediction.c:258) */
+    if (vert)
+        svt_aom_convolve8_vert_c(src, src_stride, dst, dst_stride, NULL, 0, f, step, w, h);
+    else
+        svt_aom_convolve8_horiz_c(src, src_stride, dst, dst_stride, f, step, NULL, 0, w, h);
+}
+
+/* The jobs through enc_make_inter_predictor, set up as av1_inter_prediction does (EbEncInterPrediction.c:4330-4930):
+ * identity scale factors, get_conv_params_no_round(0, do_average, 0, tmp_dst, 128 / 64, is_compound, bit_depth), the
+ * jnt weights copied into the second call's ConvolveParams. */
+REFH_API void refh_inter_predict(const SvtB200Frame *refs, int n_ref_frames, const SvtB200Frame *pred, const SvtB200InterJob *jobs,
+                                 int n_jobs) {
+    refh_init();
+    asm_set_convolve_asm_table();
+    asm_set_convolve_hbd_asm_table();
+    const int bd = pred->bit_depth, hbd = bd > 8;
+    static uint16_t tmp_dst[128 * 128];
+    (void)n_ref_frames;
+    for (int j = 0; j < n_jobs; j++) {
+        const SvtB200InterJob *b = &jobs[j];
+        const int ss = b->plane != 0, compound = b->n_refs == 2;
+        const int dstride = b->plane ? pred->stride_c : pred->stride_y;
+        uint8_t *dplane = (uint8_t *)(b->plane == 0 ? pred->y : b->plane == 1 ? pred->cb : pred->cr);
+        uint8_t *dst = dplane + (((ptrdiff_t)b->dst_y * dstride + b->dst_x) << hbd);
+        MacroBlockD xd;
+        memset(&xd, 0, sizeof(xd));
+        xd.mb_to_left_edge = b->mb_to_left_edge;
+        xd.mb_to_right_edge = b->mb_to_right_edge;
+        xd.mb_to_top_edge = b->mb_to_top_edge;
+        xd.mb_to_bottom_edge = b->mb_to_bottom_edge;
+        for (int r = 0; r < b->n_refs; r++) {
+            const SvtB200Frame *rf = &refs[b->ref[r]];
+            const int sstride = b->plane ? rf->stride_c : rf->stride_y;
+            uint8_t *splane = (uint8_t *)(b->plane == 0 ? rf->y : b->plane == 1 ? rf->cb : rf->cr);
+            ScaleFactors sf;
+            svt_av1_setup_scale_factors_for_frame(&sf, rf->width, rf->height, rf->width, rf->height);
+            ConvolveParams cp = get_conv_params_no_round(0, r, 0, tmp_dst, b->plane ? 64 : 128, compound, bd);
+            if (r == 1) {
+                cp.use_jnt_comp_avg = cp.use_dist_wtd_comp_avg = b->use_jnt_comp_avg;
+                cp.fwd_offset = b->fwd_offset;
+                cp.bck_offset = b->bck_offset;
+            }
+            MV mv;
+            mv.row = b->mv_row[r];
+            mv.col = b->mv_col[r];
+            enc_make_inter_predictor(splane, dst, b->pre_y, b->pre_x, mv, &sf, &cp, av1_make_interp_filters(b->filter_y, b->filter_x),
+                                     NULL, (uint16_t)rf->width, (uint16_t)rf->height, b->bw, b->bh, BLOCK_8X8, &xd, sstride, dstride,
+                                     b->plane, ss, ss, (uint8_t)bd, 0, 0, (uint8_t)hbd);
+        }
+    }
+}

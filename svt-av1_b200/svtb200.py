@@ -133,6 +133,33 @@ class LrFrameParams(C.Structure):
     _fields_ = [("plane", LrPlane * 3), ("optimized_lr", C.c_int32)]
 
 
+class InterpFilterParams(C.Structure):  # EbDefinitions.h:493-498
+    _fields_ = [("filter_ptr", C.c_void_p), ("taps", C.c_uint16), ("subpel_shifts", C.c_uint16), ("interp_filter", C.c_int32)]
+
+
+class ConvolveParams(C.Structure):  # EbDefinitions.h:379-392
+    _fields_ = [("ref", C.c_int32), ("do_average", C.c_int32), ("dst", C.c_void_p), ("dst_stride", C.c_int32),
+                ("round_0", C.c_int32), ("round_1", C.c_int32), ("plane", C.c_int32), ("is_compound", C.c_int32),
+                ("use_jnt_comp_avg", C.c_int32), ("fwd_offset", C.c_int32), ("bck_offset", C.c_int32),
+                ("use_dist_wtd_comp_avg", C.c_int32)]
+
+
+class InterJob(C.Structure):
+    _fields_ = [("plane", C.c_uint8), ("n_refs", C.c_uint8), ("bw", C.c_uint8), ("bh", C.c_uint8), ("ref", C.c_uint8 * 2),
+                ("filter_x", C.c_uint8), ("filter_y", C.c_uint8), ("use_jnt_comp_avg", C.c_uint8), ("fwd_offset", C.c_uint8),
+                ("bck_offset", C.c_uint8), ("reserved", C.c_uint8), ("dst_x", C.c_int16), ("dst_y", C.c_int16),
+                ("pre_x", C.c_int16), ("pre_y", C.c_int16), ("mv_row", C.c_int16 * 2), ("mv_col", C.c_int16 * 2),
+                ("mb_to_left_edge", C.c_int32), ("mb_to_right_edge", C.c_int32), ("mb_to_top_edge", C.c_int32),
+                ("mb_to_bottom_edge", C.c_int32)]
+
+
+INTER_JOB_DTYPE = [("plane", "u1"), ("n_refs", "u1"), ("bw", "u1"), ("bh", "u1"), ("ref", "u1", 2), ("filter_x", "u1"),
+                   ("filter_y", "u1"), ("use_jnt_comp_avg", "u1"), ("fwd_offset", "u1"), ("bck_offset", "u1"), ("reserved", "u1"),
+                   ("dst_x", "<i2"), ("dst_y", "<i2"), ("pre_x", "<i2"), ("pre_y", "<i2"), ("mv_row", "<i2", 2),
+                   ("mv_col", "<i2", 2), ("mb_to_left_edge", "<i4"), ("mb_to_right_edge", "<i4"), ("mb_to_top_edge", "<i4"),
+                   ("mb_to_bottom_edge", "<i4")]
+
+
 def preset8_me_params(width, height, n_l0=1, n_l1=1, dist=((1, 2, 3, 4), (1, 2, 3, 4)), temporal_layer=1,
                       is_ref=1):
     """ME parameters of preset 8 (ENC_M8) at >=720p, 30 fps, as set_me_hme_params_oq /
