@@ -1,0 +1,486 @@
+// interp.cu — translational inter prediction: the AV1 sub-pel interpolation filters.
+//
+// Replaces, in svt-av1 v0.8.6 (Source/Lib/Common/Codec/EbInterPrediction.c unless noted):
+//   svt_av1_convolve_{2d_sr,x_sr,y_sr,2d_copy_sr}_c :349-470, svt_av1_jnt_convolve_{2d,x,y,2d_copy}_c :552-745 and the
+//   highbd forms :747-1145 (RTCD drop-ins, host pointers); svt_aom_convolve8_{horiz,vert}_c (convolve.c:249-308);
+//   and, batched per picture, the enc_make_inter_predictor calls of av1_inter_prediction
+//   (Encoder/Codec/EbEncInterPrediction.c:3591-3762, :4040-4930): MV clamp (clamp_mv_to_umv_border_sb :24-45), split
+//   into whole-sample position + 1/16 phase, dispatch on (phase_x != 0, phase_y != 0, compound), and for compound blocks
+//   the second reference averaged (plain or distance weighted) into the first without the CONV_BUF round trip.
+//
+// Work decomposition: one warp filters one tile of <= 16x16 output samples. The (tw+7)x(th+7) source window is staged
+// once in shared memory (16-bit), the horizontal pass writes the int16 intermediate the reference keeps in im_block,
+// the vertical pass produces 8 outputs per lane. The sixteen reference functions differ only in which pass runs and in
+// the rounding, so all of them are one device routine (conv_tile) + one finishing step.
+// Bound: HBM/L2 traffic (read ~(1 + 7/16)^2 x, write 1 x per sample; ~20 multiply-adds per sample).
+#include <mutex>
+
+#include "common.cuh"
+
+namespace svtb200 {
+namespace {
+
+// AV1 interpolation kernels, half coefficients (every tap is even; spec 7.11.3.4 Subpel_Filters): regular, smooth, sharp,
+// and the 4-tap regular / smooth used when the block is <= 4 wide (av1_get_interp_filter_params_with_block_size :1251-1262).
+// BILINEAR is computed. tests/test_interp_gpu.py pins svt_b200_get_interp_kernel against the reference's tables.
+#define K_ROW(a, b, c, d, e, f, g, h) {a, b, c, d, e, f, g, h}
+const int8_t h_half_taps[5][16][8] = {
+    {K_ROW(0, 0, 0, 64, 0, 0, 0, 0), K_ROW(0, 1, -3, 63, 4, -1, 0, 0), K_ROW(0, 1, -5, 61, 9, -2, 0, 0), K_ROW(0, 1, -6, 58, 14, -4, 1, 0),
+     K_ROW(0, 1, -7, 55, 19, -5, 1, 0), K_ROW(0, 1, -7, 51, 24, -6, 1, 0), K_ROW(0, 1, -8, 47, 29, -6, 1, 0),
+     K_ROW(0, 1, -7, 42, 33, -6, 1, 0), K_ROW(0, 1, -7, 38, 38, -7, 1, 0), K_ROW(0, 1, -6, 33, 42, -7, 1, 0),
+     K_ROW(0, 1, -6, 29, 47, -8, 1, 0), K_ROW(0, 1, -6, 24, 51, -7, 1, 0), K_ROW(0, 1, -5, 19, 55, -7, 1, 0),
+     K_ROW(0, 1, -4, 14, 58, -6, 1, 0), K_ROW(0, 0, -2, 9, 61, -5, 1, 0), K_ROW(0, 0, -1, 4, 63, -3, 1, 0)},
+    {K_ROW(0, 0, 0, 64, 0, 0, 0, 0), K_ROW(0, 1, 14, 31, 17, 1, 0, 0), K_ROW(0, 0, 13, 31, 18, 2, 0, 0), K_ROW(0, 0, 11, 31, 20, 2, 0, 0),
+     K_ROW(0, 0, 10, 30, 21, 3, 0, 0), K_ROW(0, 0, 9, 29, 22, 4, 0, 0), K_ROW(0, 0, 8, 28, 23, 5, 0, 0), K_ROW(0, -1, 8, 27, 24, 6, 0, 0),
+     K_ROW(0, -1, 7, 26, 26, 7, -1, 0), K_ROW(0, 0, 6, 24, 27, 8, -1, 0), K_ROW(0, 0, 5, 23, 28, 8, 0, 0), K_ROW(0, 0, 4, 22, 29, 9, 0, 0),
+     K_ROW(0, 0, 3, 21, 30, 10, 0, 0), K_ROW(0, 0, 2, 20, 31, 11, 0, 0), K_ROW(0, 0, 2, 18, 31, 13, 0, 0), K_ROW(0, 0, 1, 17, 31, 14, 1, 0)},
+    {K_ROW(0, 0, 0, 64, 0, 0, 0, 0), K_ROW(-1, 1, -3, 63, 4, -1, 1, 0), K_ROW(-1, 3, -6, 62, 8, -3, 2, -1),
+     K_ROW(-1, 4, -9, 60, 13, -5, 3, -1), K_ROW(-2, 5, -11, 58, 19, -7, 3, -1), K_ROW(-2, 5, -11, 54, 24, -9, 4, -1),
+     K_ROW(-2, 5, -12, 50, 30, -10, 4, -1), K_ROW(-2, 5, -12, 45, 35, -11, 5, -1), K_ROW(-2, 6, -12, 40, 40, -12, 6, -2),
+     K_ROW(-1, 5, -11, 35, 45, -12, 5, -2), K_ROW(-1, 4, -10, 30, 50, -12, 5, -2), K_ROW(-1, 4, -9, 24, 54, -11, 5, -2),
+     K_ROW(-1, 3, -7, 19, 58, -11, 5, -2), K_ROW(-1, 3, -5, 13, 60, -9, 4, -1), K_ROW(-1, 2, -3, 8, 62, -6, 3, -1),
+     K_ROW(0, 1, -1, 4, 63, -3, 1, -1)},
+    {K_ROW(0, 0, 0, 64, 0, 0, 0, 0), K_ROW(0, 0, -2, 63, 4, -1, 0, 0), K_ROW(0, 0, -4, 61, 9, -2, 0, 0), K_ROW(0, 0, -5, 58, 14, -3, 0, 0),
+     K_ROW(0, 0, -6, 55, 19, -4, 0, 0), K_ROW(0, 0, -6, 51, 24, -5, 0, 0), K_ROW(0, 0, -7, 47, 29, -5, 0, 0),
+     K_ROW(0, 0, -6, 42, 33, -5, 0, 0), K_ROW(0, 0, -6, 38, 38, -6, 0, 0), K_ROW(0, 0, -5, 33, 42, -6, 0, 0),
+     K_ROW(0, 0, -5, 29, 47, -7, 0, 0), K_ROW(0, 0, -5, 24, 51, -6, 0, 0), K_ROW(0, 0, -4, 19, 55, -6, 0, 0),
+     K_ROW(0, 0, -3, 14, 58, -5, 0, 0), K_ROW(0, 0, -2, 9, 61, -4, 0, 0), K_ROW(0, 0, -1, 4, 63, -2, 0, 0)},
+    {K_ROW(0, 0, 0, 64, 0, 0, 0, 0), K_ROW(0, 0, 15, 31, 17, 1, 0, 0), K_ROW(0, 0, 13, 31, 18, 2, 0, 0), K_ROW(0, 0, 11, 31, 20, 2, 0, 0),
+     K_ROW(0, 0, 10, 30, 21, 3, 0, 0), K_ROW(0, 0, 9, 29, 22, 4, 0, 0), K_ROW(0, 0, 8, 28, 23, 5, 0, 0), K_ROW(0, 0, 7, 27, 24, 6, 0, 0),
+     K_ROW(0, 0, 6, 26, 26, 6, 0, 0), K_ROW(0, 0, 6, 24, 27, 7, 0, 0), K_ROW(0, 0, 5, 23, 28, 8, 0, 0), K_ROW(0, 0, 4, 22, 29, 9, 0, 0),
+     K_ROW(0, 0, 3, 21, 30, 10, 0, 0), K_ROW(0, 0, 2, 20, 31, 11, 0, 0), K_ROW(0, 0, 2, 18, 31, 13, 0, 0), K_ROW(0, 0, 1, 17, 31, 15, 0, 0)}};
+__constant__ int8_t c_half_taps[5][16][8];
+
+int upload_tables() { // once per device
+    static std::mutex mu;
+    static bool done[64] = {};
+    int dev = 0;
+    SVTB_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev >= 64) return SVT_B200_ERR_ARG;
+    std::lock_guard<std::mutex> lk(mu);
+    if (!done[dev]) {
+        SVTB_CUDA_TRY(cudaMemcpyToSymbol(c_half_taps, h_half_taps, sizeof(h_half_taps)));
+        done[dev] = true;
+    }
+    return SVT_B200_OK;
+}
+
+// which table a filter id resolves to for a block `w` wide: -1 = bilinear
+__host__ __device__ inline int table_of(int filter, int w) {
+    if (filter == 3) return -1;
+    if (w <= 4) return filter == 1 ? 4 : 3; // sharp -> the regular 4-tap kernel
+    return filter;
+}
+__device__ __forceinline__ void load_taps(int filter, int w, int subpel, int (&f)[8]) {
+    const int t = table_of(filter, w);
+    if (t < 0) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) f[k] = 0;
+        f[3] = 128 - 8 * subpel;
+        f[4] = 8 * subpel;
+    } else {
+        const int2 v = *reinterpret_cast<const int2 *>(c_half_taps[t][subpel]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            f[k] = 2 * (int)(int8_t)(v.x >> (8 * k));
+            f[4 + k] = 2 * (int)(int8_t)(v.y >> (8 * k));
+        }
+    }
+}
+
+constexpr int TILE = 16, WIN = TILE + 7, WIN_P = 24;
+struct WarpSmem {
+    uint16_t src[WIN * WIN_P]; // the source window, 16-bit
+    int16_t im[WIN * TILE];    // the horizontal pass of the 2-D forms (im_block)
+};
+
+__device__ __forceinline__ int rshift_round(int v, int n) { return (v + ((1 << n) >> 1)) >> n; } // ROUND_POWER_OF_TWO
+__device__ __forceinline__ int clip_bd(int v, int bd) { return min(max(v, 0), (1 << bd) - 1); }
+// i / d for i < 1024, d <= 32 (inv = ceil(2^16 / d))
+__device__ __forceinline__ int div_small(int i, int inv) { return (i * inv) >> 16; }
+
+struct Rounds {
+    int r0, r1, bd;
+};
+// get_conv_params_no_round (convolve.h:44-71)
+__host__ __device__ inline Rounds conv_rounds(int bd, bool compound) {
+    Rounds r{3, compound ? 7 : 11, bd};
+    const int over = bd + 7 - r.r0 + 2 - 16;
+    if (over > 0) {
+        r.r0 += over;
+        if (!compound) r.r1 -= over;
+    }
+    return r;
+}
+
+// One reference's filtering of a tile: src addresses the tile's sample (0,0) in the reference plane. On return val[j]
+// belongs to output i = lane + 32 j (row-major in the tw x th tile): without `compound` the prediction sample, with it
+// this reference's intermediate (what the jnt forms store to / combine with CONV_BUF).
+template <typename T>
+__device__ __forceinline__ void conv_tile(const T *__restrict__ src, int stride, int tw, int th, bool sx, bool sy, const int (&fx)[8],
+                                          const int (&fy)[8], Rounds rd, bool compound, WarpSmem &s, int lane, int (&val)[8]) {
+    const int x0 = sx ? -3 : 0, y0 = sy ? -3 : 0;
+    const int ww = tw + (sx ? 7 : 0), wh = th + (sy ? 7 : 0);
+    const int inv_ww = (65536 + ww - 1) / ww, inv_tw = (65536 + tw - 1) / tw;
+    const int offset_bits = rd.bd + 14 - rd.r0;
+    const int round_offset = (1 << (offset_bits - rd.r1)) + (1 << (offset_bits - rd.r1 - 1));
+    const int bits2 = 14 - rd.r0 - rd.r1;
+    __syncwarp(); // the previous user of the window is done
+    for (int i = lane; i < ww * wh; i += 32) {
+        const int r = div_small(i, inv_ww), c = i - r * ww;
+        s.src[r * WIN_P + c] = src[(ptrdiff_t)(y0 + r) * stride + x0 + c];
+    }
+    __syncwarp();
+    if (sx && sy) {
+        for (int i = lane; i < wh * tw; i += 32) {
+            const int r = div_small(i, inv_tw), c = i - r * tw;
+            int sum = 1 << (rd.bd + 6);
+#pragma unroll
+            for (int k = 0; k < 8; k++) sum += fx[k] * s.src[r * WIN_P + c + k];
+            s.im[r * TILE + c] = (int16_t)rshift_round(sum, rd.r0);
+        }
+        __syncwarp();
+    }
+    const int n = tw * th;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int i = lane + 32 * j;
+        if (i >= n) break;
+        const int y = div_small(i, inv_tw), x = i - y * tw;
+        int res;
+        if (sx && sy) {
+            int sum = 1 << offset_bits;
+#pragma unroll
+            for (int k = 0; k < 8; k++) sum += fy[k] * s.im[(y + k) * TILE + x];
+            res = rshift_round(sum, rd.r1);
+            if (!compound)
+                res = clip_bd(rshift_round((int)(int16_t)(uint16_t)(res - round_offset), bits2), rd.bd);
+            else
+                res = (uint16_t)res;
+        } else if (sx) {
+            int sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) sum += fx[k] * s.src[y * WIN_P + x + k];
+            sum = rshift_round(sum, rd.r0);
+            res = compound ? (1 << (7 - rd.r1)) * sum + round_offset : clip_bd(rshift_round(sum, 7 - rd.r0), rd.bd);
+        } else if (sy) {
+            int sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; k++) sum += fy[k] * s.src[(y + k) * WIN_P + x];
+            res = compound ? rshift_round(sum * (1 << (7 - rd.r0)), rd.r1) + round_offset : clip_bd(rshift_round(sum, 7), rd.bd);
+        } else {
+            const int p = s.src[y * WIN_P + x];
+            res = compound ? (int)(uint16_t)((uint16_t)(p << bits2) + (uint16_t)round_offset) : p;
+        }
+        val[j] = res;
+    }
+}
+
+// the do_average branch of the jnt forms
+__device__ __forceinline__ int jnt_average(int first, int res, bool use_jnt, int fwd, int bck, Rounds rd) {
+    const int offset_bits = rd.bd + 14 - rd.r0;
+    const int round_offset = (1 << (offset_bits - rd.r1)) + (1 << (offset_bits - rd.r1 - 1));
+    int tmp = use_jnt ? (first * fwd + res * bck) >> 4 : (first + res) >> 1;
+    tmp -= round_offset;
+    return clip_bd(rshift_round(tmp, 14 - rd.r0 - rd.r1), rd.bd);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Picture-level entry: one CTA (2 warps) per job, warps stride over the job's 16x16 tiles
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int MAX_REF_FRAMES = 8;
+struct InterDev {
+    const void *ref[MAX_REF_FRAMES][3];
+    int ref_stride[MAX_REF_FRAMES][2];
+    void *pred[3];
+    int pred_stride[2];
+    const SvtB200InterJob *jobs;
+    int n_jobs, bd;
+};
+constexpr int INTER_NT = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(INTER_NT) inter_pred_kernel(const __grid_constant__ InterDev d) {
+    __shared__ WarpSmem sm[INTER_NT / 32];
+    const SvtB200InterJob b = d.jobs[blockIdx.x];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpSmem &s = sm[warp];
+    const int pl = b.plane, ss = pl != 0, compound = b.n_refs == 2;
+    const int bw = b.bw, bh = b.bh;
+    const Rounds rd = conv_rounds(d.bd, compound);
+    const int ntx = (bw + TILE - 1) / TILE, nty = (bh + TILE - 1) / TILE;
+    T *dplane = (T *)d.pred[pl];
+    const int dstride = d.pred_stride[ss];
+    // clamp_mv_to_umv_border_sb: the MV in 1/16 sample of this plane, kept within (bw + 4) samples of the picture
+    const int sc = 1 << (1 - ss);
+    const int spel_left = (4 + bw) << 4, spel_top = (4 + bh) << 4;
+    for (int t = warp; t < ntx * nty; t += INTER_NT / 32) {
+        const int ty = t / ntx, tx = t - ty * ntx;
+        const int tw = min(TILE, bw - tx * TILE), th = min(TILE, bh - ty * TILE);
+        int first[8], val[8];
+        for (int r = 0; r <= compound; r++) {
+            int col = (int16_t)(b.mv_col[r] * sc), row = (int16_t)(b.mv_row[r] * sc);
+            col = (int16_t)clampi(col, b.mb_to_left_edge * sc - spel_left, b.mb_to_right_edge * sc + spel_left - 16);
+            row = (int16_t)clampi(row, b.mb_to_top_edge * sc - spel_top, b.mb_to_bottom_edge * sc + spel_top - 16);
+            const int spx = col & 15, spy = row & 15;
+            const int px = ((b.pre_x << 4) + col) >> 4, py = ((b.pre_y << 4) + row) >> 4;
+            int fx[8], fy[8];
+            load_taps(b.filter_x, bw, spx, fx);
+            load_taps(b.filter_y, bh, spy, fy);
+            const int rf = b.ref[r];
+            const T *src = (const T *)d.ref[rf][pl] + (ptrdiff_t)(py + ty * TILE) * d.ref_stride[rf][ss] + px + tx * TILE;
+            conv_tile<T>(src, d.ref_stride[rf][ss], tw, th, spx != 0, spy != 0, fx, fy, rd, compound, s, lane, val);
+            if (compound && r == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) first[j] = (uint16_t)val[j]; // through CONV_BUF (uint16)
+            }
+        }
+        const int inv_tw = (65536 + tw - 1) / tw;
+        T *dst = dplane + (ptrdiff_t)(b.dst_y + ty * TILE) * dstride + b.dst_x + tx * TILE;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const int i = lane + 32 * j;
+            if (i >= tw * th) break;
+            const int y = div_small(i, inv_tw), x = i - y * tw;
+            const int v = compound ? jnt_average(first[j], val[j], b.use_jnt_comp_avg, b.fwd_offset, b.bck_offset, rd) : val[j];
+            dst[(ptrdiff_t)y * dstride + x] = (T)v;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// RTCD drop-ins: one block through staging
+// ---------------------------------------------------------------------------------------------------------------------
+struct ConvArgs {
+    const void *win; // staged (w + 7) x (h + 7) source window, sample (0,0) of the block at (3,3)
+    uint16_t *conv;  // CONV_BUF, w x h
+    void *out;       // w x h
+    int w, h, r0, r1, bd;
+    int sx, sy, compound, do_average, use_jnt, fwd, bck;
+    int16_t fx[8], fy[8];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(32) convolve_dropin_kernel(const __grid_constant__ ConvArgs a) {
+    __shared__ WarpSmem s;
+    const int lane = threadIdx.x;
+    const int tx = blockIdx.x, ty = blockIdx.y;
+    const int tw = min(TILE, a.w - tx * TILE), th = min(TILE, a.h - ty * TILE);
+    const int stride = a.w + 7;
+    int fx[8], fy[8], val[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        fx[k] = a.fx[k];
+        fy[k] = a.fy[k];
+    }
+    const Rounds rd{a.r0, a.r1, a.bd};
+    const T *src = (const T *)a.win + (ptrdiff_t)(3 + ty * TILE) * stride + 3 + tx * TILE;
+    conv_tile<T>(src, stride, tw, th, a.sx != 0, a.sy != 0, fx, fy, rd, a.compound != 0, s, lane, val);
+    const int inv_tw = (65536 + tw - 1) / tw;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const int i = lane + 32 * j;
+        if (i >= tw * th) break;
+        const int y = div_small(i, inv_tw), x = i - y * tw;
+        const size_t o = (size_t)(ty * TILE + y) * a.w + tx * TILE + x;
+        if (!a.compound)
+            ((T *)a.out)[o] = (T)val[j];
+        else if (!a.do_average)
+            a.conv[o] = (uint16_t)val[j];
+        else
+            ((T *)a.out)[o] = (T)jnt_average(a.conv[o], val[j], a.use_jnt != 0, a.fwd, a.bck, rd);
+    }
+}
+
+template <typename T>
+void gather_rect(T *dst, const T *src, ptrdiff_t stride, int x0, int y0, int w, int h) {
+    for (int y = 0; y < h; y++) memcpy(dst + (size_t)y * w, src + (ptrdiff_t)(y0 + y) * stride + x0, sizeof(T) * (size_t)w);
+}
+
+// `form` = sx * 4 + sy * 2 + compound: which of convolve[sx][sy][is_compound] (:1162-1175) this call is
+template <typename T>
+void convolve_run(const char *name, int form, const T *src, int src_stride, T *dst, int dst_stride, int w, int h,
+                  const SvtB200InterpFilterParams *fpx, const SvtB200InterpFilterParams *fpy, int spx, int spy,
+                  const SvtB200ConvolveParams *cp, int bd) {
+    const int sx = form >> 2 & 1, sy = form >> 1 & 1, compound = form & 1;
+    if (w <= 0 || h <= 0 || w > 128 || h > 128 || !src || !cp || (sx && (!fpx || fpx->taps != 8)) || (sy && (!fpy || fpy->taps != 8)) ||
+        (compound && !cp->dst) || (!(compound && !cp->do_average) && !dst)) {
+        fprintf(stderr, "%s_cuda: bad argument (w %d h %d; 8-tap kernels only)\n", name, w, h);
+        abort();
+    }
+    ThreadCtx &c = tls();
+    const int ww = w + 7, wh = h + 7;
+    const size_t win_b = (sizeof(T) * ww * wh + 15) & ~(size_t)15, conv_b = ((size_t)2 * w * h + 15) & ~(size_t)15;
+    c.reserve(win_b + conv_b + sizeof(T) * w * h);
+    gather_rect<T>((T *)c.h, src, src_stride, -3, -3, ww, wh);
+    size_t up = win_b;
+    if (compound && cp->do_average) {
+        gather_rect<uint16_t>((uint16_t *)(c.h + win_b), cp->dst, cp->dst_stride, 0, 0, w, h);
+        up += conv_b;
+    }
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.d, c.h, up, cudaMemcpyHostToDevice, c.stream));
+    ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.win = c.d;
+    a.conv = (uint16_t *)(c.d + win_b);
+    a.out = c.d + win_b + conv_b;
+    a.w = w, a.h = h, a.r0 = cp->round_0, a.r1 = cp->round_1, a.bd = bd;
+    a.sx = sx, a.sy = sy, a.compound = compound, a.do_average = cp->do_average;
+    a.use_jnt = cp->use_jnt_comp_avg, a.fwd = cp->fwd_offset, a.bck = cp->bck_offset;
+    if (sx) memcpy(a.fx, fpx->filter_ptr + 8 * (spx & 15), 16); // av1_get_interp_filter_subpel_kernel
+    if (sy) memcpy(a.fy, fpy->filter_ptr + 8 * (spy & 15), 16);
+    SVTB_LAUNCH(convolve_dropin_kernel<T>, dim3((w + TILE - 1) / TILE, (h + TILE - 1) / TILE), 32, 0, c.stream, a);
+    const bool to_conv = compound && !cp->do_average;
+    const size_t off = to_conv ? win_b : win_b + conv_b, nb = to_conv ? (size_t)2 * w * h : sizeof(T) * w * h;
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h + off, c.d + off, nb, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_FATAL(cudaStreamSynchronize(c.stream));
+    for (int y = 0; y < h; y++) {
+        if (to_conv)
+            memcpy(cp->dst + (ptrdiff_t)y * cp->dst_stride, c.h + off + (size_t)2 * y * w, (size_t)2 * w);
+        else
+            memcpy(dst + (ptrdiff_t)y * dst_stride, c.h + off + sizeof(T) * y * w, sizeof(T) * w);
+    }
+}
+
+// svt_aom_convolve8_horiz / vert: position q0 + i * step sixteenths along the filtered axis
+struct Conv8Args {
+    const uint8_t *win; // staged window; the sample the first output is centred on sits at (3,3) along the filtered axis
+    uint8_t *out;
+    int w, h, stride, q0, step, vert;
+    int16_t table[16][8];
+};
+__global__ void convolve8_kernel(const __grid_constant__ Conv8Args a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.w * a.h) return;
+    const int y = i / a.w, x = i - y * a.w;
+    const int q = a.q0 + (a.vert ? y : x) * a.step;
+    const int16_t *f = a.table[q & 15];
+    const uint8_t *p = a.vert ? a.win + (size_t)(q >> 4) * a.stride + x : a.win + (size_t)y * a.stride + (q >> 4);
+    const int inc = a.vert ? a.stride : 1;
+    int sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) sum += f[k] * p[k * inc];
+    a.out[i] = (uint8_t)clip_bd(rshift_round(sum, 7), 8);
+}
+
+void convolve8_run(const uint8_t *src, ptrdiff_t src_stride, uint8_t *dst, ptrdiff_t dst_stride, const int16_t *filter, int step,
+                   int w, int h, int vert) {
+    if (w <= 0 || h <= 0 || w > 128 || h > 128 || step <= 0 || step > 64 || !filter || !src || !dst) {
+        fprintf(stderr, "svt_aom_convolve8_%s_cuda: bad argument\n", vert ? "vert" : "horiz");
+        abort();
+    }
+    // get_filter_base / get_filter_offset (convolve.c:49-57): the pointer addresses one row of a 256-byte aligned table
+    const int16_t *base = (const int16_t *)((uintptr_t)filter & ~(uintptr_t)0xFF);
+    Conv8Args a;
+    memcpy(a.table, base, sizeof(a.table));
+    a.q0 = (int)((filter - base) / 8);
+    a.step = step, a.w = w, a.h = h, a.vert = vert;
+    const int span = ((((vert ? h : w) - 1) * step + a.q0) >> 4) + 8; // samples touched along the filtered axis
+    const int ww = vert ? w : span, wh = vert ? span : h;
+    a.stride = ww;
+    ThreadCtx &c = tls();
+    const size_t win_b = ((size_t)ww * wh + 15) & ~(size_t)15;
+    c.reserve(win_b + (size_t)w * h);
+    gather_rect<uint8_t>(c.h, src, src_stride, vert ? 0 : -3, vert ? -3 : 0, ww, wh);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.d, c.h, win_b, cudaMemcpyHostToDevice, c.stream));
+    a.win = c.d;
+    a.out = c.d + win_b;
+    SVTB_LAUNCH(convolve8_kernel, (w * h + 127) / 128, 128, 0, c.stream, a);
+    SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h + win_b, c.d + win_b, (size_t)w * h, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_FATAL(cudaStreamSynchronize(c.stream));
+    for (int y = 0; y < h; y++) memcpy(dst + (ptrdiff_t)y * dst_stride, c.h + win_b + (size_t)y * w, (size_t)w);
+}
+
+} // namespace
+} // namespace svtb200
+
+using namespace svtb200;
+
+extern "C" {
+
+#define SVTB_CONVOLVE_DEF(NAME, FORM)                                                                                            \
+    void NAME##_cuda(const uint8_t *src, int32_t src_stride, uint8_t *dst, int32_t dst_stride, int32_t w, int32_t h,             \
+                     SvtB200InterpFilterParams *fpx, SvtB200InterpFilterParams *fpy, const int32_t spx, const int32_t spy,       \
+                     SvtB200ConvolveParams *cp) {                                                                                \
+        convolve_run<uint8_t>(#NAME, FORM, src, src_stride, dst, dst_stride, w, h, fpx, fpy, spx, spy, cp, 8);                   \
+    }
+#define SVTB_HBD_CONVOLVE_DEF(NAME, FORM)                                                                                        \
+    void NAME##_cuda(const uint16_t *src, int32_t src_stride, uint16_t *dst, int32_t dst_stride, int32_t w, int32_t h,           \
+                     const SvtB200InterpFilterParams *fpx, const SvtB200InterpFilterParams *fpy, const int32_t spx,              \
+                     const int32_t spy, SvtB200ConvolveParams *cp, int32_t bd) {                                                 \
+        convolve_run<uint16_t>(#NAME, FORM, src, src_stride, dst, dst_stride, w, h, fpx, fpy, spx, spy, cp, bd);                 \
+    }
+SVTB_CONVOLVE_DEF(svt_av1_convolve_2d_copy_sr, 0)
+SVTB_CONVOLVE_DEF(svt_av1_jnt_convolve_2d_copy, 1)
+SVTB_CONVOLVE_DEF(svt_av1_convolve_y_sr, 2)
+SVTB_CONVOLVE_DEF(svt_av1_jnt_convolve_y, 3)
+SVTB_CONVOLVE_DEF(svt_av1_convolve_x_sr, 4)
+SVTB_CONVOLVE_DEF(svt_av1_jnt_convolve_x, 5)
+SVTB_CONVOLVE_DEF(svt_av1_convolve_2d_sr, 6)
+SVTB_CONVOLVE_DEF(svt_av1_jnt_convolve_2d, 7)
+SVTB_HBD_CONVOLVE_DEF(svt_av1_highbd_convolve_2d_copy_sr, 0)
+SVTB_HBD_CONVOLVE_DEF(svt_av1_highbd_jnt_convolve_2d_copy, 1)
+SVTB_HBD_CONVOLVE_DEF(svt_av1_highbd_convolve_y_sr, 2)
+SVTB_HBD_CONVOLVE_DEF(svt_av1_highbd_jnt_convolve_y, 3)
+SVTB_HBD_CONVOLVE_DEF(svt_av1_highbd_convolve_x_sr, 4)
+SVTB_HBD_CONVOLVE_DEF(svt_av1_highbd_jnt_convolve_x, 5)
+SVTB_HBD_CONVOLVE_DEF(svt_av1_highbd_convolve_2d_sr, 6)
+SVTB_HBD_CONVOLVE_DEF(svt_av1_highbd_jnt_convolve_2d, 7)
+
+void svt_aom_convolve8_horiz_cuda(const uint8_t *src, ptrdiff_t src_stride, uint8_t *dst, ptrdiff_t dst_stride, const int16_t *filter_x,
+                                  int x_step_q4, const int16_t *filter_y, int y_step_q4, int w, int h) {
+    (void)filter_y, (void)y_step_q4;
+    convolve8_run(src, src_stride, dst, dst_stride, filter_x, x_step_q4, w, h, 0);
+}
+void svt_aom_convolve8_vert_cuda(const uint8_t *src, ptrdiff_t src_stride, uint8_t *dst, ptrdiff_t dst_stride, const int16_t *filter_x,
+                                 int x_step_q4, const int16_t *filter_y, int y_step_q4, int w, int h) {
+    (void)filter_x, (void)x_step_q4;
+    convolve8_run(src, src_stride, dst, dst_stride, filter_y, y_step_q4, w, h, 1);
+}
+
+int svt_b200_get_interp_kernel(int32_t interp_filter, int32_t w, int32_t subpel, int16_t out[8]) {
+    if (interp_filter < 0 || interp_filter > 3 || w <= 0 || subpel < 0 || subpel > 15 || !out) {
+        set_error("svt_b200_get_interp_kernel: bad argument");
+        return SVT_B200_ERR_ARG;
+    }
+    const int t = table_of(interp_filter, w);
+    for (int k = 0; k < 8; k++) out[k] = t < 0 ? 0 : (int16_t)(2 * h_half_taps[t][subpel][k]);
+    if (t < 0) {
+        out[3] = (int16_t)(128 - 8 * subpel);
+        out[4] = (int16_t)(8 * subpel);
+    }
+    return SVT_B200_OK;
+}
+
+int svt_b200_inter_predict(const SvtB200Frame *refs, int32_t n_ref_frames, const SvtB200Frame *pred, const SvtB200InterJob *jobs,
+                           int32_t n_jobs, void *stream) {
+    if (!refs || !pred || n_ref_frames < 1 || n_ref_frames > MAX_REF_FRAMES || n_jobs < 0 || (n_jobs && !jobs) ||
+        (pred->bit_depth != 8 && pred->bit_depth != 10 && pred->bit_depth != 12)) {
+        set_error("svt_b200_inter_predict: bad argument (1..%d reference pictures)", MAX_REF_FRAMES);
+        return SVT_B200_ERR_ARG;
+    }
+    if (n_jobs == 0) return SVT_B200_OK;
+    if (int rc = upload_tables()) return rc;
+    InterDev d;
+    memset(&d, 0, sizeof(d));
+    for (int i = 0; i < n_ref_frames; i++) {
+        if (refs[i].bit_depth != pred->bit_depth) {
+            set_error("svt_b200_inter_predict: reference %d has another bit depth", i);
+            return SVT_B200_ERR_ARG;
+        }
+        d.ref[i][0] = refs[i].y, d.ref[i][1] = refs[i].cb, d.ref[i][2] = refs[i].cr;
+        d.ref_stride[i][0] = refs[i].stride_y, d.ref_stride[i][1] = refs[i].stride_c;
+    }
+    d.pred[0] = pred->y, d.pred[1] = pred->cb, d.pred[2] = pred->cr;
+    d.pred_stride[0] = pred->stride_y, d.pred_stride[1] = pred->stride_c;
+    d.jobs = jobs, d.n_jobs = n_jobs, d.bd = pred->bit_depth;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d.bd == 8)
+        SVTB_LAUNCH(inter_pred_kernel<uint8_t>, n_jobs, INTER_NT, 0, st, d);
+    else
+        SVTB_LAUNCH(inter_pred_kernel<uint16_t>, n_jobs, INTER_NT, 0, st, d);
+    SVTB_CUDA_TRY(cudaGetLastError());
+    return SVT_B200_OK;
+}
+
+} // extern "C"

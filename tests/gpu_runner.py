@@ -156,3 +156,16 @@ def run_gpu_sse(a, b):
     sb.check(lib.svt_b200_frame_sse(C.byref(sa), C.byref(sbb), C.c_void_p(out.data_ptr()), None), lib)
     torch.cuda.synchronize()
     return out.cpu().numpy().view(np.uint64)
+
+
+def run_gpu_inter_predict(refs, pred, jobs):
+    """refs: list of common.Yuv, pred: common.Yuv (written), jobs: numpy record array (sb.INTER_JOB_DTYPE)."""
+    lib = sb.load()
+    d_refs = [DevYuv(r) for r in refs]
+    d_pred = DevYuv(pred)
+    arr = (sb.Frame * len(refs))(*[r.struct() for r in d_refs])
+    ps = d_pred.struct()
+    d_jobs = torch.from_numpy(np.ascontiguousarray(jobs).view(np.uint8)).cuda()
+    sb.check(lib.svt_b200_inter_predict(arr, len(refs), C.byref(ps), C.c_void_p(d_jobs.data_ptr()), len(jobs), None), lib)
+    torch.cuda.synchronize()
+    return d_pred.download()
