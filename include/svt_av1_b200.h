@@ -761,12 +761,17 @@ typedef struct SvtB200InterJob {
     int32_t mb_to_left_edge, mb_to_right_edge, mb_to_top_edge, mb_to_bottom_edge; /* blk_ptr->av1xd */
 } SvtB200InterJob;
 
-/* Every job of a picture in one launch: refs[] = the n_refs_frames reference pictures (recon, padded at least as far as
+/* Every job of a picture: refs[] = the n_ref_frames reference pictures (recon, padded at least as far as
  * clamp_mv_to_umv_border_sb lets a block reach: bw + 4 + 4 samples beyond the picture, as EbPictureBufferDesc pads
- * them), pred = the prediction picture, jobs = DEVICE array.  8-bit -> uint8_t planes, 10-bit -> uint16_t planes
- * (av1_inter_prediction with is16bit).  Jobs must not overlap in pred.  Asynchronous on `stream`. */
+ * them), pred = the prediction picture, jobs = DEVICE array.  8-bit -> uint8_t planes, 10/12-bit -> uint16_t planes
+ * (av1_inter_prediction with is16bit).  Jobs must not overlap in pred.  scratch: DEVICE memory holding the list of
+ * 16x16 tiles the jobs expand to; svt_b200_inter_predict_scratch_bytes() sizes it for non-overlapping jobs of a
+ * width x height picture.  A smaller scratch (>= 256 bytes) only costs speed, never correctness.  Asynchronous on
+ * `stream` (two launches). */
+SVT_B200_API size_t svt_b200_inter_predict_scratch_bytes(int32_t n_jobs, int32_t width, int32_t height);
 SVT_B200_API int svt_b200_inter_predict(const SvtB200Frame *refs, int32_t n_ref_frames, const SvtB200Frame *pred,
-                                        const SvtB200InterJob *jobs, int32_t n_jobs, void *stream);
+                                        const SvtB200InterJob *jobs, int32_t n_jobs, void *scratch, size_t scratch_bytes,
+                                        void *stream);
 
 #ifdef __cplusplus
 }

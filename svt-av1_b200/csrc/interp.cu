@@ -13,6 +13,7 @@
 // the vertical pass produces 8 outputs per lane. The sixteen reference functions differ only in which pass runs and in
 // the rounding, so all of them are one device routine (conv_tile) + one finishing step.
 // Bound: HBM/L2 traffic (read ~(1 + 7/16)^2 x, write 1 x per sample; ~20 multiply-adds per sample).
+#include <algorithm>
 #include <mutex>
 
 #include "common.cuh"
@@ -71,33 +72,53 @@ __host__ __device__ inline int table_of(int filter, int w) {
     if (w <= 4) return filter == 1 ? 4 : 3; // sharp -> the regular 4-tap kernel
     return filter;
 }
-__device__ __forceinline__ void load_taps(int filter, int w, int subpel, int (&f)[8]) {
+// the 8 half taps of a kernel row, packed one per byte (taps 0..3, taps 4..7)
+__device__ __forceinline__ uint2 load_half_taps(int filter, int w, int subpel) {
     const int t = table_of(filter, w);
-    if (t < 0) {
+    if (t < 0) return make_uint2((uint32_t)(64 - 4 * subpel) << 24, (uint32_t)(4 * subpel)); // bilinear: taps 3 and 4
+    const int2 v = *reinterpret_cast<const int2 *>(c_half_taps[t][subpel]);
+    return make_uint2((uint32_t)v.x, (uint32_t)v.y);
+}
+__device__ __forceinline__ void unpack_taps(uint2 p, int (&f)[8]) {
 #pragma unroll
-        for (int k = 0; k < 8; k++) f[k] = 0;
-        f[3] = 128 - 8 * subpel;
-        f[4] = 8 * subpel;
-    } else {
-        const int2 v = *reinterpret_cast<const int2 *>(c_half_taps[t][subpel]);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            f[k] = 2 * (int)(int8_t)(v.x >> (8 * k));
-            f[4 + k] = 2 * (int)(int8_t)(v.y >> (8 * k));
-        }
+    for (int k = 0; k < 4; k++) {
+        f[k] = (int)(int8_t)(p.x >> (8 * k));
+        f[4 + k] = (int)(int8_t)(p.y >> (8 * k));
     }
 }
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) { // 4 x (u8 * s8) + c
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_lo_us(uint32_t a, uint32_t b, int c) { // 2 x (u16 * s8 (bytes 0, 1 of b)) + c
+    int d;
+    asm("dp2a.lo.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi_us(uint32_t a, uint32_t b, int c) { // ... bytes 2, 3 of b
+    int d;
+    asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 
-constexpr int TILE = 16, WIN = TILE + 7, WIN_P = 24;
+constexpr int TILE = 16, WIN = TILE + 7, IM_P = 18; // IM_P: int16 pitch of an intermediate row (9 words: conflict free)
 struct WarpSmem {
-    uint16_t src[WIN * WIN_P]; // the source window, 16-bit
-    int16_t im[WIN * TILE];    // the horizontal pass of the 2-D forms (im_block)
+    int16_t im[WIN * IM_P];      // the horizontal pass (im_block), or the samples themselves when it does not run
+    uint16_t first[TILE * TILE]; // CONV_BUF of the tile (compound), lane-private slots
 };
 
 __device__ __forceinline__ int rshift_round(int v, int n) { return (v + ((1 << n) >> 1)) >> n; } // ROUND_POWER_OF_TWO
 __device__ __forceinline__ int clip_bd(int v, int bd) { return min(max(v, 0), (1 << bd) - 1); }
 // i / d for i < 1024, d <= 32 (inv = ceil(2^16 / d))
 __device__ __forceinline__ int div_small(int i, int inv) { return (i * inv) >> 16; }
+// ceil(2^16 / d), d = 1..32 without a division: exact for these d in fp32
+__device__ __forceinline__ int inv_small(int d) { return (int)ceilf(__fdividef(65536.0f, (float)d) - 0.01f); }
+// ROUND_POWER_OF_TWO(sum + off, n) of a sum whose taps were divided by 2^H (all taps and offsets are multiples of 2^H)
+template <int H>
+__device__ __forceinline__ int rr(int s, int off, int n) {
+    return (s + (off >> H) + (1 << (n - 1 - H))) >> (n - H);
+}
 
 struct Rounds {
     int r0, r1, bd;
@@ -113,64 +134,137 @@ __host__ __device__ inline Rounds conv_rounds(int bd, bool compound) {
     return r;
 }
 
-// One reference's filtering of a tile: src addresses the tile's sample (0,0) in the reference plane. On return val[j]
-// belongs to output i = lane + 32 j (row-major in the tw x th tile): without `compound` the prediction sample, with it
-// this reference's intermediate (what the jnt forms store to / combine with CONV_BUF).
+// One row of the source window (<= 23 samples) in registers, read with aligned 32-bit loads and realigned.
 template <typename T>
-__device__ __forceinline__ void conv_tile(const T *__restrict__ src, int stride, int tw, int th, bool sx, bool sy, const int (&fx)[8],
-                                          const int (&fy)[8], Rounds rd, bool compound, WarpSmem &s, int lane, int (&val)[8]) {
-    const int x0 = sx ? -3 : 0, y0 = sy ? -3 : 0;
-    const int ww = tw + (sx ? 7 : 0), wh = th + (sy ? 7 : 0);
-    const int inv_ww = (65536 + ww - 1) / ww, inv_tw = (65536 + tw - 1) / tw;
+struct Row;
+template <>
+struct Row<uint8_t> {
+    uint32_t W[6];
+    __device__ __forceinline__ void load(const uint8_t *rp, int n) {
+        const int mis = (int)((uintptr_t)rp & 3);
+        const uint32_t *p = (const uint32_t *)(rp - mis);
+        const int nw = (mis + n + 3) >> 2;
+        uint32_t w[7];
+#pragma unroll
+        for (int i = 0; i < 7; i++) w[i] = i < nw ? __ldg(p + i) : 0u;
+#pragma unroll
+        for (int i = 0; i < 6; i++) W[i] = __funnelshift_r(w[i], w[i + 1], 8 * mis);
+    }
+    __device__ __forceinline__ int sample(int k) const { return (int)((W[k >> 2] >> (8 * (k & 3))) & 0xffu); }
+    __device__ __forceinline__ uint32_t quad(int x) const { return (x & 3) ? __funnelshift_r(W[x >> 2], W[(x >> 2) + 1], 8 * (x & 3)) : W[x >> 2]; }
+    // sum over the 8 half taps of samples x .. x + 7
+    __device__ __forceinline__ int hsum_half(int x, uint2 t) const { return dp4a_us(quad(x + 4), t.y, dp4a_us(quad(x), t.x, 0)); }
+};
+template <>
+struct Row<uint16_t> {
+    uint32_t W[12];
+    __device__ __forceinline__ void load(const uint16_t *rp, int n) {
+        const int mis = (int)((uintptr_t)rp & 3);
+        const uint32_t *p = (const uint32_t *)((const uint8_t *)rp - mis);
+        const int nw = (mis + 2 * n + 3) >> 2;
+        uint32_t w[13];
+#pragma unroll
+        for (int i = 0; i < 13; i++) w[i] = i < nw ? __ldg(p + i) : 0u;
+#pragma unroll
+        for (int i = 0; i < 12; i++) W[i] = __funnelshift_r(w[i], w[i + 1], 8 * mis);
+    }
+    __device__ __forceinline__ int sample(int k) const { return (int)((W[k >> 1] >> (16 * (k & 1))) & 0xffffu); }
+    __device__ __forceinline__ uint32_t pair(int x) const { return (x & 1) ? __funnelshift_r(W[x >> 1], W[(x >> 1) + 1], 16) : W[x >> 1]; }
+    __device__ __forceinline__ int hsum_half(int x, uint2 t) const {
+        return dp2a_hi_us(pair(x + 6), t.y, dp2a_lo_us(pair(x + 4), t.y, dp2a_hi_us(pair(x + 2), t.x, dp2a_lo_us(pair(x), t.x, 0))));
+    }
+};
+
+// One reference's filtering of a tile: src addresses the tile's sample (0,0) in the reference plane.
+//   phase A  lane r owns row r of the (th + 7) x (tw + 7) window: it reads the row into registers, runs the horizontal
+//            filter for the 16 columns and leaves the int16 row (im_block of the reference) in shared memory;
+//   phase B  lane (x, g) owns a column strip of <= 8 rows: sliding 8-tap window down the column.
+// H = 1: taps are the AV1 kernels halved (hx packed per byte for dp4a / dp2a, fy[] = halves); H = 0: fx[] / fy[] hold
+// arbitrary int16 taps (the drop-ins, whose caller owns the table).
+// On return val[j] belongs to output (yb + j, x) of the tile (see strip_of): without `compound` the prediction sample,
+// with it this reference's intermediate (what the jnt forms store to / combine with CONV_BUF).
+struct Strip {
+    int x, yb, rows; // rows = 0: idle lane
+    int rpg;         // rows per strip (warp uniform): rows <= rpg <= 8
+};
+__device__ __forceinline__ Strip strip_of(int tw, int th, int lane) {
+    const int inv_tw = inv_small(tw);
+    const int ng = div_small(32, inv_tw), g = div_small(lane, inv_tw);
+    const int rpg = div_small(th + ng - 1, inv_small(ng));
+    Strip s;
+    s.x = lane - g * tw;
+    s.yb = g * rpg;
+    s.rows = g < ng ? max(0, min(rpg, th - s.yb)) : 0;
+    s.rpg = rpg;
+    return s;
+}
+
+template <typename T, int H>
+__device__ __forceinline__ void conv_tile(const T *__restrict__ src, int stride, int tw, int th, bool sx, bool sy, uint2 hx,
+                                          const int (&fx)[8], const int (&fy)[8], Rounds rd, bool compound, WarpSmem &s, int lane,
+                                          Strip st, int (&val)[8]) {
+    const int wh = th + (sy ? 7 : 0);
     const int offset_bits = rd.bd + 14 - rd.r0;
     const int round_offset = (1 << (offset_bits - rd.r1)) + (1 << (offset_bits - rd.r1 - 1));
     const int bits2 = 14 - rd.r0 - rd.r1;
-    __syncwarp(); // the previous user of the window is done
-    for (int i = lane; i < ww * wh; i += 32) {
-        const int r = div_small(i, inv_ww), c = i - r * ww;
-        s.src[r * WIN_P + c] = src[(ptrdiff_t)(y0 + r) * stride + x0 + c];
+    __syncwarp(); // the previous readers of im are done
+    if (lane < wh) {
+        Row<T> row;
+        row.load(src + (ptrdiff_t)(lane - (sy ? 3 : 0)) * stride - (sx ? 3 : 0), tw + (sx ? 7 : 0));
+        uint32_t *out = reinterpret_cast<uint32_t *>(s.im + lane * IM_P);
+        if (sx) {
+            const int off = sy ? 1 << (rd.bd + 6) : 0; // the 2-D forms offset the first pass
+#pragma unroll
+            for (int x = 0; x < TILE; x += 2) {
+                if (x == TILE / 2 && tw <= TILE / 2) break; // narrow tile: the upper columns are not needed
+                int v[2];
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    int sum;
+                    if (H) {
+                        sum = row.hsum_half(x + e, hx);
+                    } else {
+                        sum = 0;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) sum += fx[k] * row.sample(x + e + k);
+                    }
+                    v[e] = rr<H>(sum, off, rd.r0);
+                }
+                out[x >> 1] = (uint32_t)(v[0] & 0xffff) | (uint32_t)v[1] << 16;
+            }
+        } else {
+#pragma unroll
+            for (int x = 0; x < TILE; x += 2) {
+                if (x == TILE / 2 && tw <= TILE / 2) break;
+                out[x >> 1] = (uint32_t)row.sample(x) | (uint32_t)row.sample(x + 1) << 16;
+            }
+        }
     }
     __syncwarp();
-    if (sx && sy) {
-        for (int i = lane; i < wh * tw; i += 32) {
-            const int r = div_small(i, inv_tw), c = i - r * tw;
-            int sum = 1 << (rd.bd + 6);
+    int v[15];
 #pragma unroll
-            for (int k = 0; k < 8; k++) sum += fx[k] * s.src[r * WIN_P + c + k];
-            s.im[r * TILE + c] = (int16_t)rshift_round(sum, rd.r0);
-        }
-        __syncwarp();
+    for (int k = 0; k < 15; k++) {
+        if (k >= st.rpg + (sy ? 7 : 0)) break; // warp uniform
+        v[k] = (k < st.rows + (sy ? 7 : 0)) ? (int)s.im[(st.yb + k) * IM_P + st.x] : 0;
     }
-    const int n = tw * th;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        const int i = lane + 32 * j;
-        if (i >= n) break;
-        const int y = div_small(i, inv_tw), x = i - y * tw;
+        if (j >= st.rpg) break; // warp uniform
         int res;
-        if (sx && sy) {
-            int sum = 1 << offset_bits;
+        if (sy) {
+            int sum = 0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) sum += fy[k] * s.im[(y + k) * TILE + x];
-            res = rshift_round(sum, rd.r1);
-            if (!compound)
-                res = clip_bd(rshift_round((int)(int16_t)(uint16_t)(res - round_offset), bits2), rd.bd);
-            else
-                res = (uint16_t)res;
+            for (int k = 0; k < 8; k++) sum += fy[k] * v[j + k];
+            if (sx) { // 2-D
+                res = rr<H>(sum, 1 << offset_bits, rd.r1);
+                res = compound ? (int)(uint16_t)res : clip_bd(rshift_round((int)(int16_t)(uint16_t)(res - round_offset), bits2), rd.bd);
+            } else {
+                res = compound ? rr<H>(sum << (7 - rd.r0), 0, rd.r1) + round_offset : clip_bd(rr<H>(sum, 0, 7), rd.bd);
+            }
         } else if (sx) {
-            int sum = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) sum += fx[k] * s.src[y * WIN_P + x + k];
-            sum = rshift_round(sum, rd.r0);
-            res = compound ? (1 << (7 - rd.r1)) * sum + round_offset : clip_bd(rshift_round(sum, 7 - rd.r0), rd.bd);
-        } else if (sy) {
-            int sum = 0;
-#pragma unroll
-            for (int k = 0; k < 8; k++) sum += fy[k] * s.src[(y + k) * WIN_P + x];
-            res = compound ? rshift_round(sum * (1 << (7 - rd.r0)), rd.r1) + round_offset : clip_bd(rshift_round(sum, 7), rd.bd);
+            res = compound ? (1 << (7 - rd.r1)) * v[j] + round_offset : clip_bd(rshift_round(v[j], 7 - rd.r0), rd.bd);
         } else {
-            const int p = s.src[y * WIN_P + x];
-            res = compound ? (int)(uint16_t)((uint16_t)(p << bits2) + (uint16_t)round_offset) : p;
+            res = compound ? (int)(uint16_t)((uint16_t)(v[j] << bits2) + (uint16_t)round_offset) : v[j];
         }
         val[j] = res;
     }
@@ -186,7 +280,11 @@ __device__ __forceinline__ int jnt_average(int first, int res, bool use_jnt, int
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Picture-level entry: one CTA (2 warps) per job, warps stride over the job's 16x16 tiles
+// Picture-level entry. The unit of work is one 16x16 tile of one job (both references of a compound block):
+//   inter_expand_kernel  one thread per job reserves its tiles in an item list (warp scan + one atomic per warp),
+//   inter_tiles_kernel   persistent warps stride over the items.
+// A job whose tiles do not fit the caller's scratch (or that has more than 64 tiles) is filtered by the expanding warp
+// itself, so the result never depends on the scratch size.
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int MAX_REF_FRAMES = 8;
 struct InterDev {
@@ -196,55 +294,95 @@ struct InterDev {
     int pred_stride[2];
     const SvtB200InterJob *jobs;
     int n_jobs, bd;
+    uint32_t *count; // items reserved so far (zeroed before the expansion)
+    uint32_t *items; // job << 6 | tile, or ITEM_HOLE
+    int cap;
 };
-constexpr int INTER_NT = 64;
+constexpr int INTER_NT = 128;
+constexpr uint32_t ITEM_HOLE = 0xFFFFFFFFu;
+typedef WarpSmem InterSmem;
+
+__device__ __forceinline__ int job_tiles(const SvtB200InterJob &b) { return ((b.bw + TILE - 1) / TILE) * ((b.bh + TILE - 1) / TILE); }
 
 template <typename T>
-__global__ void __launch_bounds__(INTER_NT) inter_pred_kernel(const __grid_constant__ InterDev d) {
-    __shared__ WarpSmem sm[INTER_NT / 32];
-    const SvtB200InterJob b = d.jobs[blockIdx.x];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpSmem &s = sm[warp];
+__device__ __forceinline__ void predict_tile(const InterDev &d, const SvtB200InterJob &b, int t, InterSmem &sm, int lane) {
     const int pl = b.plane, ss = pl != 0, compound = b.n_refs == 2;
     const int bw = b.bw, bh = b.bh;
     const Rounds rd = conv_rounds(d.bd, compound);
-    const int ntx = (bw + TILE - 1) / TILE, nty = (bh + TILE - 1) / TILE;
-    T *dplane = (T *)d.pred[pl];
-    const int dstride = d.pred_stride[ss];
+    const int ntx = (bw + TILE - 1) / TILE;
+    const int ty = div_small(t, inv_small(ntx)), tx = t - ty * ntx;
+    const int tw = min(TILE, bw - tx * TILE), th = min(TILE, bh - ty * TILE);
+    const Strip st = strip_of(tw, th, lane);
     // clamp_mv_to_umv_border_sb: the MV in 1/16 sample of this plane, kept within (bw + 4) samples of the picture
     const int sc = 1 << (1 - ss);
     const int spel_left = (4 + bw) << 4, spel_top = (4 + bh) << 4;
-    for (int t = warp; t < ntx * nty; t += INTER_NT / 32) {
-        const int ty = t / ntx, tx = t - ty * ntx;
-        const int tw = min(TILE, bw - tx * TILE), th = min(TILE, bh - ty * TILE);
-        int first[8], val[8];
-        for (int r = 0; r <= compound; r++) {
-            int col = (int16_t)(b.mv_col[r] * sc), row = (int16_t)(b.mv_row[r] * sc);
-            col = (int16_t)clampi(col, b.mb_to_left_edge * sc - spel_left, b.mb_to_right_edge * sc + spel_left - 16);
-            row = (int16_t)clampi(row, b.mb_to_top_edge * sc - spel_top, b.mb_to_bottom_edge * sc + spel_top - 16);
-            const int spx = col & 15, spy = row & 15;
-            const int px = ((b.pre_x << 4) + col) >> 4, py = ((b.pre_y << 4) + row) >> 4;
-            int fx[8], fy[8];
-            load_taps(b.filter_x, bw, spx, fx);
-            load_taps(b.filter_y, bh, spy, fy);
-            const int rf = b.ref[r];
-            const T *src = (const T *)d.ref[rf][pl] + (ptrdiff_t)(py + ty * TILE) * d.ref_stride[rf][ss] + px + tx * TILE;
-            conv_tile<T>(src, d.ref_stride[rf][ss], tw, th, spx != 0, spy != 0, fx, fy, rd, compound, s, lane, val);
-            if (compound && r == 0) {
+    int val[8];
+#pragma unroll 1
+    for (int r = 0; r <= compound; r++) {
+        int col = (int16_t)((r ? b.mv_col[1] : b.mv_col[0]) * sc), row = (int16_t)((r ? b.mv_row[1] : b.mv_row[0]) * sc);
+        col = (int16_t)clampi(col, b.mb_to_left_edge * sc - spel_left, b.mb_to_right_edge * sc + spel_left - 16);
+        row = (int16_t)clampi(row, b.mb_to_top_edge * sc - spel_top, b.mb_to_bottom_edge * sc + spel_top - 16);
+        const int spx = col & 15, spy = row & 15;
+        const int px = ((b.pre_x << 4) + col) >> 4, py = ((b.pre_y << 4) + row) >> 4;
+        const uint2 hx = load_half_taps(b.filter_x, bw, spx);
+        int fy[8];
+        unpack_taps(load_half_taps(b.filter_y, bh, spy), fy);
+        const int rf = r ? b.ref[1] : b.ref[0];
+        const T *src = (const T *)d.ref[rf][pl] + (ptrdiff_t)(py + ty * TILE) * d.ref_stride[rf][ss] + px + tx * TILE;
+        conv_tile<T, 1>(src, d.ref_stride[rf][ss], tw, th, spx != 0, spy != 0, hx, fy, fy, rd, compound, sm, lane, st, val);
+        if (compound && r == 0) {
 #pragma unroll
-                for (int j = 0; j < 8; j++) first[j] = (uint16_t)val[j]; // through CONV_BUF (uint16)
-            }
+            for (int j = 0; j < 8; j++) sm.first[j * 32 + lane] = (uint16_t)val[j]; // through CONV_BUF (uint16), lane-private
         }
-        const int inv_tw = (65536 + tw - 1) / tw;
-        T *dst = dplane + (ptrdiff_t)(b.dst_y + ty * TILE) * dstride + b.dst_x + tx * TILE;
+    }
+    T *dst = (T *)d.pred[pl] + (ptrdiff_t)(b.dst_y + ty * TILE + st.yb) * d.pred_stride[ss] + b.dst_x + tx * TILE + st.x;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {
-            const int i = lane + 32 * j;
-            if (i >= tw * th) break;
-            const int y = div_small(i, inv_tw), x = i - y * tw;
-            const int v = compound ? jnt_average(first[j], val[j], b.use_jnt_comp_avg, b.fwd_offset, b.bck_offset, rd) : val[j];
-            dst[(ptrdiff_t)y * dstride + x] = (T)v;
-        }
+    for (int j = 0; j < 8; j++) {
+        if (j >= st.rows) break;
+        const int v = compound ? jnt_average(sm.first[j * 32 + lane], val[j], b.use_jnt_comp_avg, b.fwd_offset, b.bck_offset, rd) : val[j];
+        dst[(ptrdiff_t)j * d.pred_stride[ss]] = (T)v;
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(INTER_NT) inter_expand_kernel(const __grid_constant__ InterDev d) {
+    __shared__ InterSmem sm[INTER_NT / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * INTER_NT + threadIdx.x;
+    const int nt = j < d.n_jobs ? job_tiles(d.jobs[j]) : 0;
+    int incl = nt; // inclusive scan over the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t base = 0;
+    if (lane == 0 && total) base = atomicAdd(d.count, (uint32_t)total);
+    base = __shfl_sync(0xffffffffu, base, 0) + incl - nt;
+    const bool fits = nt <= 64 && base + nt <= (uint32_t)d.cap;
+    for (int t = 0; t < nt; t++)
+        if (base + t < (uint32_t)d.cap) d.items[base + t] = fits ? ((uint32_t)j << 6 | t) : ITEM_HOLE;
+    uint32_t inl = __ballot_sync(0xffffffffu, nt && !fits); // rare: filtered here, one job after the other
+    while (inl) {
+        const int src_lane = __ffs(inl) - 1;
+        inl &= inl - 1;
+        const int jj = __shfl_sync(0xffffffffu, j, src_lane);
+        const SvtB200InterJob b = d.jobs[jj];
+        for (int t = 0; t < job_tiles(b); t++) predict_tile<T>(d, b, t, sm[warp], lane);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(INTER_NT, 6) inter_tiles_kernel(const __grid_constant__ InterDev d) {
+    __shared__ InterSmem sm[INTER_NT / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t n = min(*d.count, (uint32_t)d.cap);
+    for (uint32_t i = blockIdx.x * (INTER_NT / 32) + warp; i < n; i += gridDim.x * (INTER_NT / 32)) {
+        const uint32_t item = d.items[i];
+        if (item == ITEM_HOLE) continue;
+        const SvtB200InterJob b = d.jobs[item >> 6];
+        predict_tile<T>(d, b, item & 63, sm[warp], lane);
     }
 }
 
@@ -267,6 +405,7 @@ __global__ void __launch_bounds__(32) convolve_dropin_kernel(const __grid_consta
     const int tx = blockIdx.x, ty = blockIdx.y;
     const int tw = min(TILE, a.w - tx * TILE), th = min(TILE, a.h - ty * TILE);
     const int stride = a.w + 7;
+    const Strip st = strip_of(tw, th, lane);
     int fx[8], fy[8], val[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -275,14 +414,11 @@ __global__ void __launch_bounds__(32) convolve_dropin_kernel(const __grid_consta
     }
     const Rounds rd{a.r0, a.r1, a.bd};
     const T *src = (const T *)a.win + (ptrdiff_t)(3 + ty * TILE) * stride + 3 + tx * TILE;
-    conv_tile<T>(src, stride, tw, th, a.sx != 0, a.sy != 0, fx, fy, rd, a.compound != 0, s, lane, val);
-    const int inv_tw = (65536 + tw - 1) / tw;
+    conv_tile<T, 0>(src, stride, tw, th, a.sx != 0, a.sy != 0, make_uint2(0, 0), fx, fy, rd, a.compound != 0, s, lane, st, val);
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        const int i = lane + 32 * j;
-        if (i >= tw * th) break;
-        const int y = div_small(i, inv_tw), x = i - y * tw;
-        const size_t o = (size_t)(ty * TILE + y) * a.w + tx * TILE + x;
+        if (j >= st.rows) break;
+        const size_t o = (size_t)(ty * TILE + st.yb + j) * a.w + tx * TILE + st.x;
         if (!a.compound)
             ((T *)a.out)[o] = (T)val[j];
         else if (!a.do_average)
@@ -452,11 +588,18 @@ int svt_b200_get_interp_kernel(int32_t interp_filter, int32_t w, int32_t subpel,
     return SVT_B200_OK;
 }
 
+size_t svt_b200_inter_predict_scratch_bytes(int32_t n_jobs, int32_t width, int32_t height) {
+    if (n_jobs < 0 || width <= 0 || height <= 0) return 0;
+    // one item per 16x16 tile: non-overlapping jobs have at most one partial tile each + the tiles of 1.5 pictures
+    const size_t tiles = (size_t)((width + 15) / 16 + 1) * ((height + 15) / 16 + 1);
+    return 256 + 4 * ((size_t)n_jobs + 2 * tiles);
+}
+
 int svt_b200_inter_predict(const SvtB200Frame *refs, int32_t n_ref_frames, const SvtB200Frame *pred, const SvtB200InterJob *jobs,
-                           int32_t n_jobs, void *stream) {
-    if (!refs || !pred || n_ref_frames < 1 || n_ref_frames > MAX_REF_FRAMES || n_jobs < 0 || (n_jobs && !jobs) ||
-        (pred->bit_depth != 8 && pred->bit_depth != 10 && pred->bit_depth != 12)) {
-        set_error("svt_b200_inter_predict: bad argument (1..%d reference pictures)", MAX_REF_FRAMES);
+                           int32_t n_jobs, void *scratch, size_t scratch_bytes, void *stream) {
+    if (!refs || !pred || n_ref_frames < 1 || n_ref_frames > MAX_REF_FRAMES || n_jobs < 0 || n_jobs >= (1 << 26) || (n_jobs && !jobs) ||
+        !scratch || scratch_bytes < 256 || (pred->bit_depth != 8 && pred->bit_depth != 10 && pred->bit_depth != 12)) {
+        set_error("svt_b200_inter_predict: bad argument (1..%d reference pictures, scratch >= 256 bytes)", MAX_REF_FRAMES);
         return SVT_B200_ERR_ARG;
     }
     if (n_jobs == 0) return SVT_B200_OK;
@@ -474,11 +617,33 @@ int svt_b200_inter_predict(const SvtB200Frame *refs, int32_t n_ref_frames, const
     d.pred[0] = pred->y, d.pred[1] = pred->cb, d.pred[2] = pred->cr;
     d.pred_stride[0] = pred->stride_y, d.pred_stride[1] = pred->stride_c;
     d.jobs = jobs, d.n_jobs = n_jobs, d.bd = pred->bit_depth;
+    d.count = (uint32_t *)scratch;
+    d.items = (uint32_t *)scratch + 64;
+    d.cap = (int)std::min<size_t>((scratch_bytes - 256) / 4, (size_t)1 << 30);
     cudaStream_t st = (cudaStream_t)stream;
-    if (d.bd == 8)
-        SVTB_LAUNCH(inter_pred_kernel<uint8_t>, n_jobs, INTER_NT, 0, st, d);
-    else
-        SVTB_LAUNCH(inter_pred_kernel<uint16_t>, n_jobs, INTER_NT, 0, st, d);
+    static int n_sm = 0;
+    if (!n_sm) {
+        int dev = 0;
+        SVTB_CUDA_TRY(cudaGetDevice(&dev));
+        SVTB_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+    }
+    SVTB_CUDA_TRY(cudaMemsetAsync(d.count, 0, 4, st));
+    static int occ[2] = {0, 0}; // resident CTAs per SM of the persistent kernel
+    const int hb = d.bd > 8;
+    if (!occ[hb]) {
+        if (hb)
+            SVTB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], inter_tiles_kernel<uint16_t>, INTER_NT, 0));
+        else
+            SVTB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], inter_tiles_kernel<uint8_t>, INTER_NT, 0));
+    }
+    const int g1 = (n_jobs + INTER_NT - 1) / INTER_NT, g2 = n_sm * std::max(occ[hb], 1);
+    if (d.bd == 8) {
+        SVTB_LAUNCH(inter_expand_kernel<uint8_t>, g1, INTER_NT, 0, st, d);
+        SVTB_LAUNCH(inter_tiles_kernel<uint8_t>, g2, INTER_NT, 0, st, d);
+    } else {
+        SVTB_LAUNCH(inter_expand_kernel<uint16_t>, g1, INTER_NT, 0, st, d);
+        SVTB_LAUNCH(inter_tiles_kernel<uint16_t>, g2, INTER_NT, 0, st, d);
+    }
     SVTB_CUDA_TRY(cudaGetLastError());
     return SVT_B200_OK;
 }

@@ -158,14 +158,19 @@ def run_gpu_sse(a, b):
     return out.cpu().numpy().view(np.uint64)
 
 
-def run_gpu_inter_predict(refs, pred, jobs):
+def run_gpu_inter_predict(refs, pred, jobs, scratch_bytes=None):
     """refs: list of common.Yuv, pred: common.Yuv (written), jobs: numpy record array (sb.INTER_JOB_DTYPE)."""
     lib = sb.load()
+    lib.svt_b200_inter_predict_scratch_bytes.restype = C.c_size_t
+    if scratch_bytes is None:
+        scratch_bytes = lib.svt_b200_inter_predict_scratch_bytes(len(jobs), pred.w, pred.h)
+    scratch = torch.zeros(scratch_bytes, dtype=torch.uint8, device="cuda")
     d_refs = [DevYuv(r) for r in refs]
     d_pred = DevYuv(pred)
     arr = (sb.Frame * len(refs))(*[r.struct() for r in d_refs])
     ps = d_pred.struct()
     d_jobs = torch.from_numpy(np.ascontiguousarray(jobs).view(np.uint8)).cuda()
-    sb.check(lib.svt_b200_inter_predict(arr, len(refs), C.byref(ps), C.c_void_p(d_jobs.data_ptr()), len(jobs), None), lib)
+    sb.check(lib.svt_b200_inter_predict(arr, len(refs), C.byref(ps), C.c_void_p(d_jobs.data_ptr()), len(jobs),
+                                        C.c_void_p(scratch.data_ptr()), C.c_size_t(scratch_bytes), None), lib)
     torch.cuda.synchronize()
     return d_pred.download()

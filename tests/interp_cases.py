@@ -30,14 +30,14 @@ def ref_picture(w, h, bd, seed, kind="texture"):
     return f
 
 
-def _leaves(x, y, n, rng, out, min_n=4):
+def _leaves(x, y, n, rng, out, min_n=4, square_only=False):
     """Random AV1 partition of the n x n square at (x, y): split, or one of none / horz / vert / horz4 / vert4."""
     if n > min_n and rng.random() < (0.9 if n == 64 else 0.55 if n == 32 else 0.4 if n == 16 else 0.3):
         for dy in (0, n // 2):
             for dx in (0, n // 2):
-                _leaves(x + dx, y + dy, n // 2, rng, out, min_n)
+                _leaves(x + dx, y + dy, n // 2, rng, out, min_n, square_only)
         return
-    kind = rng.integers(0, 5) if n >= 8 else 0
+    kind = rng.integers(0, 5) if n >= 8 and not square_only else 0
     if kind == 0:
         out.append((x, y, n, n))
     elif kind == 1:
@@ -52,8 +52,9 @@ def _leaves(x, y, n, rng, out, min_n=4):
         out.append((x, y, n, n))
 
 
-def make_jobs(w, h, n_ref_frames, seed, sb_size=64, mv_range=96, far_mv_every=37, compound_frac=0.35):
-    """Jobs of a whole picture as a numpy record array (sb.INTER_JOB_DTYPE)."""
+def make_jobs(w, h, n_ref_frames, seed, sb_size=64, mv_range=96, far_mv_every=37, compound_frac=0.35, min_n=4, square_only=False):
+    """Jobs of a whole picture as a numpy record array (sb.INTER_JOB_DTYPE). min_n=8, square_only=True: the block sizes preset 8
+    itself uses (square blocks down to 8x8, no 4xN / Nx4)."""
     rng = np.random.default_rng(seed)
     mi_cols, mi_rows = 2 * ((w + 7) >> 3), 2 * ((h + 7) >> 3)
     blocks = []
@@ -64,7 +65,7 @@ def make_jobs(w, h, n_ref_frames, seed, sb_size=64, mv_range=96, far_mv_every=37
                 continue
             for oy in range(0, sb_size, 64):
                 for ox in range(0, sb_size, 64):
-                    _leaves(sx + ox, sy + oy, 64, rng, blocks)
+                    _leaves(sx + ox, sy + oy, 64, rng, blocks, min_n, square_only)
     jobs = []
     last_mode = {}  # (x>>2, y>>2) -> (mv_row, mv_col, ref) of the block covering that mi: the sub8x8 chroma case reads it
 

@@ -133,3 +133,16 @@ def test_inter_predict_1080p(bd):
     again = gr.run_gpu_inter_predict(refs, cm.Yuv(w, h, bd, pad=ic.REF_PAD), jobs)
     for i in range(3):
         np.testing.assert_array_equal(again.bufs[i], got.bufs[i])
+
+
+@pytest.mark.parametrize("scratch_bytes", [256, 256 + 4 * 300, 256 + 4 * 2000])
+def test_inter_predict_small_scratch(scratch_bytes):
+    """A scratch too small for the tile list only moves work into the expanding warps: same picture."""
+    import gpu_runner as gr
+    w, h, bd = 320, 192, 8
+    refs = [ic.ref_picture(w, h, bd, 70 + i) for i in range(2)]
+    jobs = ic.make_jobs(w, h, len(refs), 5, sb_size=128)
+    want = ic.run_cpu(cm.oracle().orc_inter_predict, refs, cm.Yuv(w, h, bd, pad=ic.REF_PAD), jobs)
+    got = gr.run_gpu_inter_predict(refs, cm.Yuv(w, h, bd, pad=ic.REF_PAD), jobs, scratch_bytes=scratch_bytes)
+    for i in range(3):
+        np.testing.assert_array_equal(got.bufs[i], want.bufs[i], f"plane {i}")

@@ -108,22 +108,27 @@ out["rows"].append({"entry": "svt_b200_lr_sgr_proj_error (one hill-climb step, 1
 # ---- svt_b200_inter_predict: every block of a 1080p picture (random AV1 partition, 35 % compound, 4 references) ------
 import interp_cases as ic  # noqa: E402
 irefs = [ic.ref_picture(W, H, BD, 900 + i) for i in range(4)]
-ijobs = ic.make_jobs(W, H, len(irefs), 39)
 d_irefs = [gr.DevYuv(x) for x in irefs]
 ipred = cm.Yuv(W, H, BD, pad=ic.REF_PAD)
 d_ipred = gr.DevYuv(ipred)
 iarr = (sb.Frame * len(irefs))(*[x.struct() for x in d_irefs])
 ips = d_ipred.struct()
-d_ijobs = torch.from_numpy(np.ascontiguousarray(ijobs).view(np.uint8)).cuda()
-ms = gpu_ms(lambda: sb.check(lib.svt_b200_inter_predict(iarr, len(irefs), C.byref(ips), C.c_void_p(d_ijobs.data_ptr()), len(ijobs), None), lib))
-t0 = time.perf_counter()
-ic.run_cpu(cm.refh().refh_inter_predict, irefs, ipred, ijobs)
-ref_ms = (time.perf_counter() - t0) * 1e3
-area = int((ijobs["bw"].astype(np.int64) * ijobs["bh"] * ijobs["n_refs"]).sum())
-alg = area + samples  # one read per predicted sample and reference + one write per sample (window overlap not counted)
-out["rows"].append({"entry": "svt_b200_inter_predict (%d jobs, %d compound)" % (len(ijobs), int((ijobs["n_refs"] == 2).sum())), "gpu_ms": ms,
-                    "algorithmic_bytes": alg, "achieved_gbs": alg / ms / 1e6, "hbm_frac": alg / ms / 1e6 / peak,
-                    "reference_c_ms_1thread": ref_ms})
+lib.svt_b200_inter_predict_scratch_bytes.restype = C.c_size_t
+for what, ijobs in (("every AV1 block shape down to 4x4 / 2x2 chroma", ic.make_jobs(W, H, len(irefs), 39)),
+                    ("square blocks 8x8..64x64 (preset-8 like)", ic.make_jobs(W, H, len(irefs), 40, min_n=8, square_only=True))):
+    isb = lib.svt_b200_inter_predict_scratch_bytes(len(ijobs), W, H)
+    iscr = torch.zeros(isb, dtype=torch.uint8, device="cuda")
+    d_ijobs = torch.from_numpy(np.ascontiguousarray(ijobs).view(np.uint8)).cuda()
+    ms = gpu_ms(lambda: sb.check(lib.svt_b200_inter_predict(iarr, len(irefs), C.byref(ips), C.c_void_p(d_ijobs.data_ptr()), len(ijobs),
+                                                            C.c_void_p(iscr.data_ptr()), C.c_size_t(isb), None), lib))
+    t0 = time.perf_counter()
+    ic.run_cpu(cm.refh().refh_inter_predict, irefs, ipred, ijobs)
+    ref_ms = (time.perf_counter() - t0) * 1e3
+    area = int((ijobs["bw"].astype(np.int64) * ijobs["bh"] * ijobs["n_refs"]).sum())
+    alg = area + samples  # one read per predicted sample and reference + one write per sample (window overlap not counted)
+    out["rows"].append({"entry": "svt_b200_inter_predict, %s: %d jobs, %d compound" % (what, len(ijobs), int((ijobs["n_refs"] == 2).sum())),
+                        "gpu_ms": ms, "algorithmic_bytes": alg, "achieved_gbs": alg / ms / 1e6, "hbm_frac": alg / ms / 1e6 / peak,
+                        "reference_c_ms_1thread": ref_ms})
 
 # ---- svt_av1_pick_filter_level (full-image search) -------------------------------------------------------------------
 mi_rows, mi_cols, part, psrc, prec = pick_case(W, H, BD, 6)
