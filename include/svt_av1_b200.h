@@ -765,7 +765,7 @@ typedef struct SvtB200InterJob {
  * clamp_mv_to_umv_border_sb lets a block reach: bw + 4 + 4 samples beyond the picture, as EbPictureBufferDesc pads
  * them), pred = the prediction picture, jobs = DEVICE array.  8-bit -> uint8_t planes, 10/12-bit -> uint16_t planes
  * (av1_inter_prediction with is16bit).  Jobs must not overlap in pred.  scratch: DEVICE memory holding the list of
- * 16x16 tiles the jobs expand to; svt_b200_inter_predict_scratch_bytes() sizes it for non-overlapping jobs of a
+ * 16x8 tiles the jobs expand to; svt_b200_inter_predict_scratch_bytes() sizes it for non-overlapping jobs of a
  * width x height picture.  A smaller scratch (>= 256 bytes) only costs speed, never correctness.  Asynchronous on
  * `stream` (two launches). */
 SVT_B200_API size_t svt_b200_inter_predict_scratch_bytes(int32_t n_jobs, int32_t width, int32_t height);

@@ -102,10 +102,12 @@ __device__ __forceinline__ int dp2a_hi_us(uint32_t a, uint32_t b, int c) { // ..
     return d;
 }
 
-constexpr int TILE = 16, WIN = TILE + 7, IM_P = 18; // IM_P: int16 pitch of an intermediate row (9 words: conflict free)
-struct WarpSmem {
-    int16_t im[WIN * IM_P];      // the horizontal pass (im_block), or the samples themselves when it does not run
-    uint16_t first[TILE * TILE]; // CONV_BUF of the tile (compound), lane-private slots
+// A tile is <= 16 x 8 predicted samples and belongs to one HALF warp (16 lanes): its window has <= 15 rows, one per lane.
+constexpr int TILE_W = 16, TILE_H = 8, WIN = TILE_H + 7, IM_P = 18; // IM_P: int16 pitch of an intermediate row (9 words)
+struct HalfSmem {
+    int16_t im[WIN * IM_P];           // the horizontal pass (im_block), or the samples themselves when it does not run
+    uint16_t first[TILE_W * TILE_H];  // CONV_BUF of the tile (compound), lane-private slots
+    uint32_t pad;
 };
 
 __device__ __forceinline__ int rshift_round(int v, int n) { return (v + ((1 << n) >> 1)) >> n; } // ROUND_POWER_OF_TWO
@@ -175,7 +177,9 @@ struct Row<uint16_t> {
     }
 };
 
-// One reference's filtering of a tile: src addresses the tile's sample (0,0) in the reference plane.
+// One reference's filtering of a tile by a half warp (`sub` = lane & 15): src addresses the tile's sample (0,0) in the
+// reference plane. The two halves of a warp work on unrelated tiles; everything below is per half except the two
+// __syncwarp(), which every lane reaches (a half with nothing to do passes th = 0 and an empty strip).
 //   phase A  lane r owns row r of the (th + 7) x (tw + 7) window: it reads the row into registers, runs the horizontal
 //            filter for the 16 columns and leaves the int16 row (im_block of the reference) in shared memory;
 //   phase B  lane (x, g) owns a column strip of <= 8 rows: sliding 8-tap window down the column.
@@ -185,14 +189,14 @@ struct Row<uint16_t> {
 // with it this reference's intermediate (what the jnt forms store to / combine with CONV_BUF).
 struct Strip {
     int x, yb, rows; // rows = 0: idle lane
-    int rpg;         // rows per strip (warp uniform): rows <= rpg <= 8
+    int rpg;         // rows per strip (uniform in the half): rows <= rpg <= 8
 };
-__device__ __forceinline__ Strip strip_of(int tw, int th, int lane) {
-    const int inv_tw = inv_small(tw);
-    const int ng = div_small(32, inv_tw), g = div_small(lane, inv_tw);
+__device__ __forceinline__ Strip strip_of(int tw, int th, int sub) {
+    const int inv_tw = inv_small(max(tw, 1));
+    const int ng = div_small(16, inv_tw), g = div_small(sub, inv_tw);
     const int rpg = div_small(th + ng - 1, inv_small(ng));
     Strip s;
-    s.x = lane - g * tw;
+    s.x = sub - g * tw;
     s.yb = g * rpg;
     s.rows = g < ng ? max(0, min(rpg, th - s.yb)) : 0;
     s.rpg = rpg;
@@ -201,22 +205,22 @@ __device__ __forceinline__ Strip strip_of(int tw, int th, int lane) {
 
 template <typename T, int H>
 __device__ __forceinline__ void conv_tile(const T *__restrict__ src, int stride, int tw, int th, bool sx, bool sy, uint2 hx,
-                                          const int (&fx)[8], const int (&fy)[8], Rounds rd, bool compound, WarpSmem &s, int lane,
+                                          const int (&fx)[8], const int (&fy)[8], Rounds rd, bool compound, HalfSmem &s, int sub,
                                           Strip st, int (&val)[8]) {
-    const int wh = th + (sy ? 7 : 0);
+    const int wh = th ? th + (sy ? 7 : 0) : 0;
     const int offset_bits = rd.bd + 14 - rd.r0;
     const int round_offset = (1 << (offset_bits - rd.r1)) + (1 << (offset_bits - rd.r1 - 1));
     const int bits2 = 14 - rd.r0 - rd.r1;
     __syncwarp(); // the previous readers of im are done
-    if (lane < wh) {
+    if (sub < wh) {
         Row<T> row;
-        row.load(src + (ptrdiff_t)(lane - (sy ? 3 : 0)) * stride - (sx ? 3 : 0), tw + (sx ? 7 : 0));
-        uint32_t *out = reinterpret_cast<uint32_t *>(s.im + lane * IM_P);
+        row.load(src + (ptrdiff_t)(sub - (sy ? 3 : 0)) * stride - (sx ? 3 : 0), tw + (sx ? 7 : 0));
+        uint32_t *out = reinterpret_cast<uint32_t *>(s.im + sub * IM_P);
         if (sx) {
             const int off = sy ? 1 << (rd.bd + 6) : 0; // the 2-D forms offset the first pass
 #pragma unroll
-            for (int x = 0; x < TILE; x += 2) {
-                if (x == TILE / 2 && tw <= TILE / 2) break; // narrow tile: the upper columns are not needed
+            for (int x = 0; x < TILE_W; x += 2) {
+                if (x == TILE_W / 2 && tw <= TILE_W / 2) break; // narrow tile: the upper columns are not needed
                 int v[2];
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
@@ -234,8 +238,8 @@ __device__ __forceinline__ void conv_tile(const T *__restrict__ src, int stride,
             }
         } else {
 #pragma unroll
-            for (int x = 0; x < TILE; x += 2) {
-                if (x == TILE / 2 && tw <= TILE / 2) break;
+            for (int x = 0; x < TILE_W; x += 2) {
+                if (x == TILE_W / 2 && tw <= TILE_W / 2) break;
                 out[x >> 1] = (uint32_t)row.sample(x) | (uint32_t)row.sample(x + 1) << 16;
             }
         }
@@ -244,12 +248,12 @@ __device__ __forceinline__ void conv_tile(const T *__restrict__ src, int stride,
     int v[15];
 #pragma unroll
     for (int k = 0; k < 15; k++) {
-        if (k >= st.rpg + (sy ? 7 : 0)) break; // warp uniform
+        if (k >= st.rpg + (sy ? 7 : 0) || !st.rpg) break;
         v[k] = (k < st.rows + (sy ? 7 : 0)) ? (int)s.im[(st.yb + k) * IM_P + st.x] : 0;
     }
 #pragma unroll
     for (int j = 0; j < 8; j++) {
-        if (j >= st.rpg) break; // warp uniform
+        if (j >= st.rpg) break;
         int res;
         if (sy) {
             int sum = 0;
@@ -295,59 +299,67 @@ struct InterDev {
     const SvtB200InterJob *jobs;
     int n_jobs, bd;
     uint32_t *count; // items reserved so far (zeroed before the expansion)
-    uint32_t *items; // job << 6 | tile, or ITEM_HOLE
+    uint32_t *items; // job << ITEM_TILE_BITS | tile, or ITEM_HOLE
     int cap;
 };
 constexpr int INTER_NT = 128;
 constexpr uint32_t ITEM_HOLE = 0xFFFFFFFFu;
-typedef WarpSmem InterSmem;
+constexpr int ITEM_TILE_BITS = 7; // <= 128 tiles of 16 x 8 per job (128 x 128)
 
-__device__ __forceinline__ int job_tiles(const SvtB200InterJob &b) { return ((b.bw + TILE - 1) / TILE) * ((b.bh + TILE - 1) / TILE); }
+__device__ __forceinline__ int job_tiles(const SvtB200InterJob &b) {
+    return ((b.bw + TILE_W - 1) / TILE_W) * ((b.bh + TILE_H - 1) / TILE_H);
+}
 
+// One tile per half warp: `valid` halves predict tile t of job b, the others only keep the warp's barriers company.
 template <typename T>
-__device__ __forceinline__ void predict_tile(const InterDev &d, const SvtB200InterJob &b, int t, InterSmem &sm, int lane) {
-    const int pl = b.plane, ss = pl != 0, compound = b.n_refs == 2;
+__device__ __forceinline__ void predict_tile(const InterDev &d, const SvtB200InterJob &b, int t, bool valid, HalfSmem &sm, int sub) {
+    const int pl = b.plane, ss = pl != 0, compound = valid && b.n_refs == 2;
     const int bw = b.bw, bh = b.bh;
     const Rounds rd = conv_rounds(d.bd, compound);
-    const int ntx = (bw + TILE - 1) / TILE;
-    const int ty = div_small(t, inv_small(ntx)), tx = t - ty * ntx;
-    const int tw = min(TILE, bw - tx * TILE), th = min(TILE, bh - ty * TILE);
-    const Strip st = strip_of(tw, th, lane);
+    const int ntx = (bw + TILE_W - 1) / TILE_W;
+    const int ty = div_small(t, inv_small(max(ntx, 1))), tx = t - ty * ntx;
+    const int tw = valid ? min(TILE_W, bw - tx * TILE_W) : 0, th = valid ? min(TILE_H, bh - ty * TILE_H) : 0;
+    const Strip st = strip_of(tw, th, sub);
+    const Strip idle{0, 0, 0, 0};
     // clamp_mv_to_umv_border_sb: the MV in 1/16 sample of this plane, kept within (bw + 4) samples of the picture
     const int sc = 1 << (1 - ss);
     const int spel_left = (4 + bw) << 4, spel_top = (4 + bh) << 4;
+    const int passes = __any_sync(0xffffffffu, compound) ? 2 : 1;
     int val[8];
 #pragma unroll 1
-    for (int r = 0; r <= compound; r++) {
+    for (int r = 0; r < passes; r++) {
+        const bool act = valid && r <= compound;
         int col = (int16_t)((r ? b.mv_col[1] : b.mv_col[0]) * sc), row = (int16_t)((r ? b.mv_row[1] : b.mv_row[0]) * sc);
         col = (int16_t)clampi(col, b.mb_to_left_edge * sc - spel_left, b.mb_to_right_edge * sc + spel_left - 16);
         row = (int16_t)clampi(row, b.mb_to_top_edge * sc - spel_top, b.mb_to_bottom_edge * sc + spel_top - 16);
         const int spx = col & 15, spy = row & 15;
         const int px = ((b.pre_x << 4) + col) >> 4, py = ((b.pre_y << 4) + row) >> 4;
-        const uint2 hx = load_half_taps(b.filter_x, bw, spx);
+        const uint2 hx = load_half_taps(b.filter_x & 3, bw, spx);
         int fy[8];
-        unpack_taps(load_half_taps(b.filter_y, bh, spy), fy);
-        const int rf = r ? b.ref[1] : b.ref[0];
-        const T *src = (const T *)d.ref[rf][pl] + (ptrdiff_t)(py + ty * TILE) * d.ref_stride[rf][ss] + px + tx * TILE;
-        conv_tile<T, 1>(src, d.ref_stride[rf][ss], tw, th, spx != 0, spy != 0, hx, fy, fy, rd, compound, sm, lane, st, val);
+        unpack_taps(load_half_taps(b.filter_y & 3, bh, spy), fy);
+        const int rf = (r ? b.ref[1] : b.ref[0]) & (MAX_REF_FRAMES - 1);
+        const T *src = (const T *)d.ref[rf][pl] + (ptrdiff_t)(py + ty * TILE_H) * d.ref_stride[rf][ss] + px + tx * TILE_W;
+        conv_tile<T, 1>(src, d.ref_stride[rf][ss], tw, act ? th : 0, spx != 0, spy != 0, hx, fy, fy, rd, compound, sm, sub,
+                        act ? st : idle, val);
         if (compound && r == 0) {
 #pragma unroll
-            for (int j = 0; j < 8; j++) sm.first[j * 32 + lane] = (uint16_t)val[j]; // through CONV_BUF (uint16), lane-private
+            for (int j = 0; j < 8; j++) sm.first[j * 16 + sub] = (uint16_t)val[j]; // through CONV_BUF (uint16), lane-private
         }
     }
-    T *dst = (T *)d.pred[pl] + (ptrdiff_t)(b.dst_y + ty * TILE + st.yb) * d.pred_stride[ss] + b.dst_x + tx * TILE + st.x;
+    if (!valid) return;
+    T *dst = (T *)d.pred[pl] + (ptrdiff_t)(b.dst_y + ty * TILE_H + st.yb) * d.pred_stride[ss] + b.dst_x + tx * TILE_W + st.x;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         if (j >= st.rows) break;
-        const int v = compound ? jnt_average(sm.first[j * 32 + lane], val[j], b.use_jnt_comp_avg, b.fwd_offset, b.bck_offset, rd) : val[j];
+        const int v = compound ? jnt_average(sm.first[j * 16 + sub], val[j], b.use_jnt_comp_avg, b.fwd_offset, b.bck_offset, rd) : val[j];
         dst[(ptrdiff_t)j * d.pred_stride[ss]] = (T)v;
     }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(INTER_NT) inter_expand_kernel(const __grid_constant__ InterDev d) {
-    __shared__ InterSmem sm[INTER_NT / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ HalfSmem sm[INTER_NT / 16];
+    const int lane = threadIdx.x & 31;
     const int j = blockIdx.x * INTER_NT + threadIdx.x;
     const int nt = j < d.n_jobs ? job_tiles(d.jobs[j]) : 0;
     int incl = nt; // inclusive scan over the warp
@@ -360,29 +372,35 @@ __global__ void __launch_bounds__(INTER_NT) inter_expand_kernel(const __grid_con
     uint32_t base = 0;
     if (lane == 0 && total) base = atomicAdd(d.count, (uint32_t)total);
     base = __shfl_sync(0xffffffffu, base, 0) + incl - nt;
-    const bool fits = nt <= 64 && base + nt <= (uint32_t)d.cap;
+    const bool fits = nt <= (1 << ITEM_TILE_BITS) && base + nt <= (uint32_t)d.cap;
     for (int t = 0; t < nt; t++)
-        if (base + t < (uint32_t)d.cap) d.items[base + t] = fits ? ((uint32_t)j << 6 | t) : ITEM_HOLE;
+        if (base + t < (uint32_t)d.cap) d.items[base + t] = fits ? ((uint32_t)j << ITEM_TILE_BITS | t) : ITEM_HOLE;
     uint32_t inl = __ballot_sync(0xffffffffu, nt && !fits); // rare: filtered here, one job after the other
     while (inl) {
         const int src_lane = __ffs(inl) - 1;
         inl &= inl - 1;
         const int jj = __shfl_sync(0xffffffffu, j, src_lane);
         const SvtB200InterJob b = d.jobs[jj];
-        for (int t = 0; t < job_tiles(b); t++) predict_tile<T>(d, b, t, sm[warp], lane);
+        const int n = job_tiles(b);
+        for (int t = 0; t < n; t += 2) {
+            const int tt = t + (lane >> 4);
+            predict_tile<T>(d, b, tt, tt < n, sm[threadIdx.x >> 4], lane & 15);
+        }
     }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(INTER_NT, 6) inter_tiles_kernel(const __grid_constant__ InterDev d) {
-    __shared__ InterSmem sm[INTER_NT / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ HalfSmem sm[INTER_NT / 16];
+    const int half = threadIdx.x >> 4, sub = threadIdx.x & 15; // half warps, each with its own item
     const uint32_t n = min(*d.count, (uint32_t)d.cap);
-    for (uint32_t i = blockIdx.x * (INTER_NT / 32) + warp; i < n; i += gridDim.x * (INTER_NT / 32)) {
-        const uint32_t item = d.items[i];
-        if (item == ITEM_HOLE) continue;
-        const SvtB200InterJob b = d.jobs[item >> 6];
-        predict_tile<T>(d, b, item & 63, sm[warp], lane);
+    const uint32_t n_pairs = (n + 1) >> 1, step = gridDim.x * (INTER_NT / 32);
+    for (uint32_t i = blockIdx.x * (INTER_NT / 32) + (threadIdx.x >> 5); i < n_pairs; i += step) {
+        const uint32_t k = 2 * i + (half & 1);
+        const uint32_t item = k < n ? d.items[k] : ITEM_HOLE;
+        const bool valid = item != ITEM_HOLE;
+        const SvtB200InterJob b = d.jobs[valid ? item >> ITEM_TILE_BITS : 0];
+        predict_tile<T>(d, b, (int)(item & ((1u << ITEM_TILE_BITS) - 1)), valid, sm[half], sub);
     }
 }
 
@@ -400,12 +418,13 @@ struct ConvArgs {
 
 template <typename T>
 __global__ void __launch_bounds__(32) convolve_dropin_kernel(const __grid_constant__ ConvArgs a) {
-    __shared__ WarpSmem s;
-    const int lane = threadIdx.x;
-    const int tx = blockIdx.x, ty = blockIdx.y;
-    const int tw = min(TILE, a.w - tx * TILE), th = min(TILE, a.h - ty * TILE);
+    __shared__ HalfSmem s[2];
+    const int half = threadIdx.x >> 4, sub = threadIdx.x & 15;
+    const int tx = blockIdx.x, ty = blockIdx.y * 2 + half; // the two halves take vertically adjacent tiles
+    const bool valid = ty * TILE_H < a.h;
+    const int tw = valid ? min(TILE_W, a.w - tx * TILE_W) : 0, th = valid ? min(TILE_H, a.h - ty * TILE_H) : 0;
     const int stride = a.w + 7;
-    const Strip st = strip_of(tw, th, lane);
+    const Strip st = strip_of(tw, th, sub);
     int fx[8], fy[8], val[8];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -413,12 +432,12 @@ __global__ void __launch_bounds__(32) convolve_dropin_kernel(const __grid_consta
         fy[k] = a.fy[k];
     }
     const Rounds rd{a.r0, a.r1, a.bd};
-    const T *src = (const T *)a.win + (ptrdiff_t)(3 + ty * TILE) * stride + 3 + tx * TILE;
-    conv_tile<T, 0>(src, stride, tw, th, a.sx != 0, a.sy != 0, make_uint2(0, 0), fx, fy, rd, a.compound != 0, s, lane, st, val);
+    const T *src = (const T *)a.win + (ptrdiff_t)(3 + ty * TILE_H) * stride + 3 + tx * TILE_W;
+    conv_tile<T, 0>(src, stride, tw, th, a.sx != 0, a.sy != 0, make_uint2(0, 0), fx, fy, rd, a.compound != 0, s[half], sub, st, val);
 #pragma unroll
     for (int j = 0; j < 8; j++) {
         if (j >= st.rows) break;
-        const size_t o = (size_t)(ty * TILE + st.yb + j) * a.w + tx * TILE + st.x;
+        const size_t o = (size_t)(ty * TILE_H + st.yb + j) * a.w + tx * TILE_W + st.x;
         if (!a.compound)
             ((T *)a.out)[o] = (T)val[j];
         else if (!a.do_average)
@@ -465,7 +484,7 @@ void convolve_run(const char *name, int form, const T *src, int src_stride, T *d
     a.use_jnt = cp->use_jnt_comp_avg, a.fwd = cp->fwd_offset, a.bck = cp->bck_offset;
     if (sx) memcpy(a.fx, fpx->filter_ptr + 8 * (spx & 15), 16); // av1_get_interp_filter_subpel_kernel
     if (sy) memcpy(a.fy, fpy->filter_ptr + 8 * (spy & 15), 16);
-    SVTB_LAUNCH(convolve_dropin_kernel<T>, dim3((w + TILE - 1) / TILE, (h + TILE - 1) / TILE), 32, 0, c.stream, a);
+    SVTB_LAUNCH(convolve_dropin_kernel<T>, dim3((w + TILE_W - 1) / TILE_W, (h + 2 * TILE_H - 1) / (2 * TILE_H)), 32, 0, c.stream, a);
     const bool to_conv = compound && !cp->do_average;
     const size_t off = to_conv ? win_b : win_b + conv_b, nb = to_conv ? (size_t)2 * w * h : sizeof(T) * w * h;
     SVTB_CUDA_FATAL(cudaMemcpyAsync(c.h + off, c.d + off, nb, cudaMemcpyDeviceToHost, c.stream));
@@ -590,14 +609,15 @@ int svt_b200_get_interp_kernel(int32_t interp_filter, int32_t w, int32_t subpel,
 
 size_t svt_b200_inter_predict_scratch_bytes(int32_t n_jobs, int32_t width, int32_t height) {
     if (n_jobs < 0 || width <= 0 || height <= 0) return 0;
-    // one item per 16x16 tile: non-overlapping jobs have at most one partial tile each + the tiles of 1.5 pictures
-    const size_t tiles = (size_t)((width + 15) / 16 + 1) * ((height + 15) / 16 + 1);
-    return 256 + 4 * ((size_t)n_jobs + 2 * tiles);
+    // one item per 16x8 tile: a block of AV1 shape has at most 1 + area / 64 of them, and non-overlapping jobs cover at most
+    // the three planes of the (64-aligned) picture
+    const size_t area = (size_t)(width + 64) * (height + 64) * 3 / 2;
+    return 256 + 4 * ((size_t)n_jobs + area / 64);
 }
 
 int svt_b200_inter_predict(const SvtB200Frame *refs, int32_t n_ref_frames, const SvtB200Frame *pred, const SvtB200InterJob *jobs,
                            int32_t n_jobs, void *scratch, size_t scratch_bytes, void *stream) {
-    if (!refs || !pred || n_ref_frames < 1 || n_ref_frames > MAX_REF_FRAMES || n_jobs < 0 || n_jobs >= (1 << 26) || (n_jobs && !jobs) ||
+    if (!refs || !pred || n_ref_frames < 1 || n_ref_frames > MAX_REF_FRAMES || n_jobs < 0 || n_jobs >= (1 << (32 - ITEM_TILE_BITS)) || (n_jobs && !jobs) ||
         !scratch || scratch_bytes < 256 || (pred->bit_depth != 8 && pred->bit_depth != 10 && pred->bit_depth != 12)) {
         set_error("svt_b200_inter_predict: bad argument (1..%d reference pictures, scratch >= 256 bytes)", MAX_REF_FRAMES);
         return SVT_B200_ERR_ARG;
