@@ -203,6 +203,16 @@ SVT_B200_API int svt_b200_me_picture(const SvtB200MeParams *p, const SvtB200MePl
                                      const SvtB200MePlanes refs[SVT_B200_ME_LISTS][SVT_B200_ME_MAX_REFS],
                                      const SvtB200MeOutputs *out, void *scratch, void *stream);
 
+/* The 1/4 and 1/16 planes of one picture from its full-resolution luma, padding included:
+ * filtered != 0 replaces downsample_filtering_input_picture[_ime] (EbPictureAnalysisProcess.c:3606-3720; downsample_2d
+ * :223-256: 2x2 average, quarter from full, sixteenth from quarter — every preset <= M9), filtered == 0
+ * downsample_decimation_input_picture[_ime] (:3312-3360; decimation_2d :193-216: top-left sample, both from full), each
+ * followed by generate_padding (EbMcp.c:112-164).  planes: DEVICE buffers, `full` read (its padding is not needed),
+ * `quarter` / `sixteenth` written in full.  With this the HME planes need not be uploaded.  Requires
+ * quarter = full / 2 and sixteenth = full / 4 in both dimensions (rounded down).  Asynchronous on `stream`. */
+SVT_B200_API int svt_b200_me_downsample(const SvtB200Plane *full, const SvtB200Plane *quarter, const SvtB200Plane *sixteenth,
+                                        const SvtB200MePlanes *planes, int32_t filtered, void *stream);
+
 /* =============================================================================================== */
 /* Pictures for the EncDec / in-loop-filter entries                                                */
 /* =============================================================================================== */

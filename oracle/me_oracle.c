@@ -521,3 +521,49 @@ void orc_me_picture(const SvtB200MeParams *p, const SvtB200MePlanes *src, const 
                       total_cand + (size_t)sb * 85, rc_me_distortion + sb);
         }
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * The 1/4 and 1/16 luma planes HME searches (picture-analysis decimation).
+ * Follows Source/Lib/Encoder/Codec/EbPictureAnalysisProcess.c: downsample_2d :223-256 (2x2 average, rounding),
+ * decimation_2d :193-216 (top-left sample), downsample_filtering_input_picture[_ime] :3606-3720 (quarter from full,
+ * sixteenth from quarter) / downsample_decimation_input_picture[_ime] :3312-3360 (both from full), followed by
+ * generate_padding (Common/Codec/EbMcp.c:112-164: rows first, then whole padded rows up and down).
+ * planes->full holds the picture (its own padding is not touched); the other two planes are written in full.
+ * ------------------------------------------------------------------------------------------------------------------- */
+static void orc_pad_plane(uint8_t *buf, const SvtB200Plane *g) {
+    for (int y = 0; y < g->height; y++) {
+        uint8_t *row = buf + (size_t)(g->origin_y + y) * g->stride + g->origin_x;
+        memset(row - g->origin_x, row[0], (size_t)g->origin_x);
+        memset(row + g->width, row[g->width - 1], (size_t)g->origin_x);
+    }
+    for (int k = 1; k <= g->origin_y; k++) {
+        memcpy(buf + (size_t)(g->origin_y - k) * g->stride, buf + (size_t)g->origin_y * g->stride, (size_t)g->stride);
+        memcpy(buf + (size_t)(g->origin_y + g->height - 1 + k) * g->stride, buf + (size_t)(g->origin_y + g->height - 1) * g->stride,
+               (size_t)g->stride);
+    }
+}
+static void orc_shrink(const uint8_t *in, int in_stride, int in_w, int in_h, uint8_t *out, int out_stride, int step, int filtered) {
+    const int half = step >> 1;
+    if (filtered) {
+        for (int y = half, oy = 0; y < in_h; y += step, oy++)
+            for (int x = half, ox = 0; x < in_w; x += step, ox++)
+                out[oy * out_stride + ox] = (uint8_t)((in[(y - 1) * in_stride + x - 1] + in[(y - 1) * in_stride + x] +
+                                                       in[y * in_stride + x - 1] + in[y * in_stride + x] + 2) >> 2);
+    } else {
+        for (int y = 0; y < in_h; y += step)
+            for (int x = 0; x < in_w; x += step) out[(y / step) * out_stride + x / step] = in[y * in_stride + x];
+    }
+}
+ORC_API void orc_me_downsample(const SvtB200Plane *full, const SvtB200Plane *quarter, const SvtB200Plane *sixteenth,
+                               const SvtB200MePlanes *planes, int filtered) {
+    const uint8_t *f = (const uint8_t *)planes->full + (size_t)full->origin_y * full->stride + full->origin_x;
+    uint8_t *q = (uint8_t *)planes->quarter + (size_t)quarter->origin_y * quarter->stride + quarter->origin_x;
+    uint8_t *s = (uint8_t *)planes->sixteenth + (size_t)sixteenth->origin_y * sixteenth->stride + sixteenth->origin_x;
+    orc_shrink(f, full->stride, full->width, full->height, q, quarter->stride, 2, filtered);
+    orc_pad_plane((uint8_t *)planes->quarter, quarter);
+    if (filtered)
+        orc_shrink(q, quarter->stride, quarter->width, quarter->height, s, sixteenth->stride, 2, 1);
+    else
+        orc_shrink(f, full->stride, full->width, full->height, s, sixteenth->stride, 4, 0);
+    orc_pad_plane((uint8_t *)planes->sixteenth, sixteenth);
+}

@@ -41,6 +41,8 @@ ORC_API void orc_me_picture(const SvtB200MeParams *p, const SvtB200MePlanes *src
                             const SvtB200MePlanes refs[2][4], uint32_t *best_sad, uint32_t *best_mv,
                             SvtB200HmeResult *hme, int16_t *me_mv, uint8_t *me_cand, uint8_t *total_cand,
                             uint32_t *rc_me_distortion);
+ORC_API void orc_me_downsample(const SvtB200Plane *full, const SvtB200Plane *quarter, const SvtB200Plane *sixteenth,
+                               const SvtB200MePlanes *planes, int filtered);
 /* ---- cdef_oracle.c ---- */
 ORC_API int32_t orc_cdef_find_dir(const uint16_t *img, int32_t stride, int32_t *var, int32_t coeff_shift);
 ORC_API void orc_cdef_filter_block(uint8_t *dst8, uint16_t *dst16, int32_t dstride, const uint16_t *in,

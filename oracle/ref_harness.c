@@ -845,3 +845,22 @@ REFH_API void refh_inter_predict(const SvtB200Frame *refs, int n_ref_frames, con
         }
     }
 }
+
+/* downsample_filtering_input_picture_ime / downsample_decimation_input_picture_ime (EbPictureAnalysisProcess.c:3667-3720,
+ * :3362-3410) on plain buffers */
+void downsample_filtering_input_picture_ime(EbPictureBufferDesc *input_padded_picture_ptr, EbPictureBufferDesc *quarter_picture_ptr,
+                                            EbPictureBufferDesc *sixteenth_picture_ptr);
+void downsample_decimation_input_picture_ime(EbPictureBufferDesc *input_padded_picture_ptr,
+                                             EbPictureBufferDesc *quarter_decimated_picture_ptr,
+                                             EbPictureBufferDesc *sixteenth_decimated_picture_ptr);
+REFH_API void refh_me_downsample(const SvtB200Plane *full, const SvtB200Plane *quarter, const SvtB200Plane *sixteenth,
+                                 const SvtB200MePlanes *planes, int filtered) {
+    EbPictureBufferDesc f, q, s;
+    plane_desc(&f, full, planes->full);
+    plane_desc(&q, quarter, planes->quarter);
+    plane_desc(&s, sixteenth, planes->sixteenth);
+    if (filtered)
+        downsample_filtering_input_picture_ime(&f, &q, &s);
+    else
+        downsample_decimation_input_picture_ime(&f, &q, &s);
+}

@@ -182,3 +182,73 @@ SAD_MXN(128, 128) SAD_MXN(128, 64) SAD_MXN(64, 128) SAD_MXN(64, 64) SAD_MXN(64, 
 SAD_MXN(32, 32) SAD_MXN(32, 16) SAD_MXN(32, 8) SAD_MXN(16, 64) SAD_MXN(16, 32) SAD_MXN(16, 16) SAD_MXN(16, 8)
 SAD_MXN(16, 4) SAD_MXN(8, 32) SAD_MXN(8, 16) SAD_MXN(8, 8) SAD_MXN(8, 4) SAD_MXN(4, 16) SAD_MXN(4, 8) SAD_MXN(4, 4)
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// svt_b200_me_downsample: the 1/4 and 1/16 HME planes on the device, padding included.
+// Replication padding = the shrink evaluated at the output coordinate clamped into the plane, so one launch per level
+// writes the whole padded buffer: 4 output samples (one 32-bit store) per thread. Streaming, HBM/L2 bound and tiny
+// (2.1 MB read, 0.8 MB written at 1080p).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+struct ShrinkArgs {
+    const uint8_t *in; // sample (0,0) of the input picture
+    uint8_t *out;      // element (0,0) of the padded output buffer
+    int in_stride, in_w, in_h;
+    int out_stride, out_w, out_h, pad_x, pad_y;
+    int step, filtered;
+};
+__global__ void __launch_bounds__(256) shrink_kernel(const __grid_constant__ ShrinkArgs a) {
+    const int gx = (blockIdx.x * blockDim.x + threadIdx.x) * 4, gy = blockIdx.y; // in the padded buffer
+    if (gx >= a.out_stride) return;
+    const int cy = clampi(gy - a.pad_y, 0, a.out_h - 1);
+    const int half = a.step >> 1;
+    uint32_t word = 0;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        const int cx = clampi(gx + e - a.pad_x, 0, a.out_w - 1);
+        int v;
+        if (a.filtered) { // downsample_2d: the 2x2 samples left/above position (half + step * c)
+            const int y = min(half + a.step * cy, a.in_h - 1), x = min(half + a.step * cx, a.in_w - 1);
+            const uint8_t *p = a.in + (size_t)(y - 1) * a.in_stride + x - 1;
+            v = (__ldg(p) + __ldg(p + 1) + __ldg(p + a.in_stride) + __ldg(p + a.in_stride + 1) + 2) >> 2;
+        } else { // decimation_2d
+            v = __ldg(a.in + (size_t)min(a.step * cy, a.in_h - 1) * a.in_stride + min(a.step * cx, a.in_w - 1));
+        }
+        word |= (uint32_t)v << (8 * e);
+    }
+    uint8_t *o = a.out + (size_t)gy * a.out_stride + gx;
+    if (gx + 4 <= a.out_stride && (((uintptr_t)o) & 3) == 0)
+        *reinterpret_cast<uint32_t *>(o) = word;
+    else
+        for (int e = 0; e < 4 && gx + e < a.out_stride; e++) o[e] = (uint8_t)(word >> (8 * e));
+}
+int shrink_launch(const uint8_t *in, const SvtB200Plane &gi, uint8_t *out, const SvtB200Plane &go, int step, int filtered,
+                  cudaStream_t st) {
+    ShrinkArgs a;
+    a.in = in + (size_t)gi.origin_y * gi.stride + gi.origin_x;
+    a.out = out;
+    a.in_stride = gi.stride, a.in_w = gi.width, a.in_h = gi.height;
+    a.out_stride = go.stride, a.out_w = go.width, a.out_h = go.height, a.pad_x = go.origin_x, a.pad_y = go.origin_y;
+    a.step = step, a.filtered = filtered;
+    const int rows = go.height + 2 * go.origin_y;
+    SVTB_LAUNCH(shrink_kernel, dim3((go.stride + 1023) / 1024, rows), 256, 0, st, a);
+    SVTB_CUDA_TRY(cudaGetLastError());
+    return SVT_B200_OK;
+}
+} // namespace
+
+extern "C" int svt_b200_me_downsample(const SvtB200Plane *full, const SvtB200Plane *quarter, const SvtB200Plane *sixteenth,
+                                      const SvtB200MePlanes *planes, int32_t filtered, void *stream) {
+    if (!full || !quarter || !sixteenth || !planes || !planes->full || !planes->quarter || !planes->sixteenth || full->width < 8 ||
+        full->height < 8 || quarter->width != full->width >> 1 || quarter->height != full->height >> 1 ||
+        sixteenth->width != full->width >> 2 || sixteenth->height != full->height >> 2 ||
+        quarter->stride < quarter->width + 2 * quarter->origin_x || sixteenth->stride < sixteenth->width + 2 * sixteenth->origin_x) {
+        set_error("svt_b200_me_downsample: bad argument (quarter = full / 2, sixteenth = full / 4)");
+        return SVT_B200_ERR_ARG;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    if (int rc = shrink_launch(planes->full, *full, (uint8_t *)planes->quarter, *quarter, 2, filtered != 0, st)) return rc;
+    if (filtered) // sixteenth from the quarter plane just written
+        return shrink_launch(planes->quarter, *quarter, (uint8_t *)planes->sixteenth, *sixteenth, 2, 1, st);
+    return shrink_launch(planes->full, *full, (uint8_t *)planes->sixteenth, *sixteenth, 4, 0, st);
+}

@@ -135,3 +135,20 @@ def test_me_picture_1080p_full_size():
     refs_same = [src] * 8
     same = gr.run_gpu_me(params, src, refs_same)
     assert (same.best_sad[:, 0, 0] == 0).all()
+
+
+@pytest.mark.parametrize("filtered", [1, 0])
+@pytest.mark.parametrize("w,h", [(1920, 1080), (640, 360), (322, 182), (176, 144), (70, 66)])
+def test_me_downsample_vs_oracle(w, h, filtered):
+    """svt_b200_me_downsample: both HME planes with their padding, every byte of the buffers, vs the oracle."""
+    import torch
+    from test_oracle_me import downsample_case, run_downsample
+    lib = sb.load()
+    geos, full, q0, s0 = downsample_case(w, h, 7 + filtered)
+    want_q, want_s = run_downsample(cm.oracle().orc_me_downsample, geos, full, q0.copy(), s0.copy(), filtered)
+    d_full, d_q, d_s = torch.from_numpy(full).cuda(), torch.from_numpy(q0).cuda(), torch.from_numpy(s0).cuda()
+    planes = sb.MePlanes(d_full.data_ptr(), d_q.data_ptr(), d_s.data_ptr())
+    sb.check(lib.svt_b200_me_downsample(C.byref(geos[0]), C.byref(geos[1]), C.byref(geos[2]), C.byref(planes), filtered, None), lib)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d_q.cpu().numpy(), want_q)
+    np.testing.assert_array_equal(d_s.cpu().numpy(), want_s)

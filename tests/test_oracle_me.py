@@ -114,3 +114,37 @@ def test_me_static_content_exercises_zero_centre_and_sr_shrink():
     params, want = cm.run_ref_me(w, h, 8, 2, 2, dist, 1, 1, geos, src, refs)
     got = cm.run_oracle_me(params, src, refs)
     cm.assert_me_equal(got, want, params, "static")
+
+
+DOWNSAMPLE_SIZES = [(1920, 1080), (640, 360), (322, 182), (176, 144), (70, 66)]
+
+
+def downsample_case(w, h, seed):
+    """Full-resolution padded luma + zeroed 1/4 and 1/16 buffers (a canary value in the padding)."""
+    geos = sb.me_geometry(w, h)
+    rng = np.random.default_rng(seed)
+    img = cm.synth_luma(w, h, 3, seed) if seed % 2 else rng.integers(0, 256, (h, w)).astype(np.uint8)
+    full = cm.pad_plane(img, geos[0])
+    q = np.full((geos[1].height + 2 * geos[1].origin_y, geos[1].stride), 0xA5, np.uint8)
+    s = np.full((geos[2].height + 2 * geos[2].origin_y, geos[2].stride), 0x5A, np.uint8)
+    return geos, full, q, s
+
+
+def run_downsample(fn, geos, full, q, s, filtered):
+    planes = sb.MePlanes(full.ctypes.data, q.ctypes.data, s.ctypes.data)
+    fn(C.byref(geos[0]), C.byref(geos[1]), C.byref(geos[2]), C.byref(planes), filtered)
+    return q, s
+
+
+@pytest.mark.skipif(not cm.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("filtered", [1, 0])
+@pytest.mark.parametrize("w,h", DOWNSAMPLE_SIZES)
+def test_me_downsample_matches_reference(w, h, filtered):
+    """orc_me_downsample vs downsample_filtering_input_picture_ime / downsample_decimation_input_picture_ime."""
+    for seed in (1, 2):
+        geos, full, q0, s0 = downsample_case(w, h, seed)
+        qa, sa = run_downsample(cm.oracle().orc_me_downsample, geos, full, q0.copy(), s0.copy(), filtered)
+        qb, sbb = run_downsample(cm.refh().refh_me_downsample, geos, full, q0.copy(), s0.copy(), filtered)
+        np.testing.assert_array_equal(qa, qb)
+        np.testing.assert_array_equal(sa, sbb)
+        assert not (qa == 0xA5).all() and not (sa == 0x5A).all()
