@@ -783,6 +783,49 @@ SVT_B200_API int svt_b200_inter_predict(const SvtB200Frame *refs, int32_t n_ref_
                                         const SvtB200InterJob *jobs, int32_t n_jobs, void *scratch, size_t scratch_bytes,
                                         void *stream);
 
+/* =============================================================================================== */
+/* Sub-pel motion refinement                                                  */
+/* =============================================================================================== */
+
+/* svt_av1_find_best_sub_pixel_tree (Encoder/Codec/mcomp.c:350-418) as md_subpel_search sets it up
+ * (EbProductCodingLoop.c:2063-2155: 8-bit luma, no second predictor / mask / OBMC, last_mv_search_list == NULL), for a
+ * batch of independent (block, reference) searches.  The search is the reference's: centre error, then per round
+ * (1/2, 1/4, 1/8 sample) left / right / up / down, the diagonal they point to, and with iters_per_step > 1 the
+ * second-level check; an evaluation = svt_aom_upsampled_pred (Encoder/C_DEFAULT/variance.c:212-269: 8-tap / 4-tap /
+ * bilinear kernels, two passes each rounded to 8 bits) + svt_aom_varianceWxH (EbComputeVariance_C.c:14-61) +
+ * svt_mv_err_cost (mcomp.c:44-64). */
+typedef struct SvtB200SubpelJob {
+    int16_t blk_x, blk_y; /* context_ptr->blk_origin_x / _y */
+    uint8_t bw, bh;       /* block_size_wide / _high [bsize] */
+    uint8_t ref;          /* index into refs[] */
+    uint8_t reserved;
+    int16_t start_mv_row, start_mv_col; /* subpel_start_mv: the full-pel MV in 1/8 sample */
+    int16_t ref_mv_row, ref_mv_col;     /* context_ptr->ref_mv (the MV the rate is measured from) */
+    int16_t col_min, col_max, row_min, row_max; /* ms_params->mv_limits (svt_av1_set_subpel_mv_search_range, mcomp.h:124-138) */
+} SvtB200SubpelJob;
+typedef struct SvtB200SubpelParams {
+    int32_t allow_hp;           /* eight_pel_search_enabled && frm_hdr.allow_high_precision_mv */
+    int32_t forced_stop;        /* SUBPEL_FORCE_STOP: 0 EIGHTH_PEL .. 3 FULL_PEL */
+    int32_t iters_per_step;     /* md_subpel_ctrls.subpel_iters_per_step */
+    int32_t subpel_search_type; /* SUBPEL_SEARCH_TYPE: 1 USE_2_TAPS, 2 USE_4_TAPS, 3 USE_8_TAPS */
+    int32_t mv_cost_type;       /* MV_COST_TYPE: 0 ENTROPY, 1 L1_LOWRES, 2 L1_MIDRES, 3 L1_HDRES, 4 NONE */
+    int32_t error_per_bit;      /* AOMMAX(rdmult >> RD_EPB_SHIFT, 1) */
+    int32_t mvjcost[4];         /* md_rate_estimation_ptr->nmv_vec_cost */
+    const int32_t *mvcost[2];   /* DEVICE, nmvcoststack[0 / 1]: centred tables, indices -16383 .. 16383 (MV_COST_ENTROPY only) */
+} SvtB200SubpelParams;
+typedef struct SvtB200SubpelResult {
+    int16_t mv_row, mv_col; /* *bestmv */
+    int32_t besterr;        /* the return value */
+    int32_t distortion;     /* *distortion */
+    uint32_t sse;           /* *sse1 */
+} SvtB200SubpelResult;
+/* src: the source picture, refs[]: the reference pictures (8-bit; only the luma planes are read; references padded as
+ * the reference pads them: the limits keep a block within AOM_INTERP_EXTEND of the picture and 4 taps reach beyond);
+ * jobs / results: DEVICE arrays.  Asynchronous on `stream`. */
+SVT_B200_API int svt_b200_subpel_search(const SvtB200SubpelParams *p, const SvtB200Frame *src, const SvtB200Frame *refs,
+                                        int32_t n_ref_frames, const SvtB200SubpelJob *jobs, int32_t n_jobs,
+                                        SvtB200SubpelResult *results, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -864,3 +864,82 @@ REFH_API void refh_me_downsample(const SvtB200Plane *full, const SvtB200Plane *q
     else
         downsample_decimation_input_picture_ime(&f, &q, &s);
 }
+
+/* ------------------------------------------------------------------------------------------------------------------ */
+/* Sub-pel refinement: svt_av1_find_best_sub_pixel_tree per job, parameters set as md_subpel_search does               */
+/* (EbProductCodingLoop.c:2063-2155).                                                                                 */
+/* ------------------------------------------------------------------------------------------------------------------ */
+#include "mcomp.h"
+#include "av1me.h"
+void init_fn_ptr(void);
+extern AomVarianceFnPtr mefn_ptr[BlockSizeS_ALL];
+
+REFH_API int refh_subpel_search(const SvtB200SubpelParams *p, const int32_t *mvcost0, const int32_t *mvcost1, const SvtB200Frame *src,
+                                const SvtB200Frame *refs, int n_ref_frames, const SvtB200SubpelJob *jobs, int n_jobs,
+                                SvtB200SubpelResult *results) {
+    refh_init();
+    init_fn_ptr();
+    (void)n_ref_frames;
+    for (int i = 0; i < n_jobs; i++) {
+        const SvtB200SubpelJob *j = &jobs[i];
+        int bsize = -1;
+        for (int b = 0; b < BlockSizeS_ALL; b++)
+            if (block_size_wide[b] == j->bw && block_size_high[b] == j->bh) bsize = b;
+        if (bsize < 0) return -1;
+        MacroBlockD xd;
+        memset(&xd, 0, sizeof(xd));
+        xd.mi_row = j->blk_y >> 2;
+        xd.mi_col = j->blk_x >> 2;
+        MV ref_mv = {j->ref_mv_row, j->ref_mv_col};
+        SUBPEL_MOTION_SEARCH_PARAMS ms;
+        memset(&ms, 0, sizeof(ms));
+        ms.allow_hp = p->allow_hp;
+        ms.forced_stop = (SUBPEL_FORCE_STOP)p->forced_stop;
+        ms.iters_per_step = p->iters_per_step;
+        ms.mv_limits.col_min = j->col_min, ms.mv_limits.col_max = j->col_max;
+        ms.mv_limits.row_min = j->row_min, ms.mv_limits.row_max = j->row_max;
+        ms.mv_cost_params.ref_mv = &ref_mv;
+        ms.mv_cost_params.mv_cost_type = (MV_COST_TYPE)p->mv_cost_type;
+        ms.mv_cost_params.error_per_bit = p->error_per_bit;
+        ms.mv_cost_params.mvjcost = p->mvjcost;
+        ms.mv_cost_params.mvcost[0] = mvcost0;
+        ms.mv_cost_params.mvcost[1] = mvcost1;
+        ms.var_params.vfp = &mefn_ptr[bsize];
+        ms.var_params.subpel_search_type = (SUBPEL_SEARCH_TYPE)p->subpel_search_type;
+        ms.var_params.w = j->bw;
+        ms.var_params.h = j->bh;
+        const SvtB200Frame *rf = &refs[j->ref];
+        struct svt_buf_2d rb, sb2;
+        memset(&rb, 0, sizeof(rb));
+        memset(&sb2, 0, sizeof(sb2));
+        rb.buf = (uint8_t *)rf->y + (ptrdiff_t)j->blk_y * rf->stride_y + j->blk_x;
+        rb.stride = rf->stride_y, rb.width = rf->width, rb.height = rf->height;
+        sb2.buf = (uint8_t *)src->y + (ptrdiff_t)j->blk_y * src->stride_y + j->blk_x;
+        sb2.stride = src->stride_y, sb2.width = src->width, sb2.height = src->height;
+        ms.var_params.ms_buffers.ref = &rb;
+        ms.var_params.ms_buffers.src = &sb2;
+        MV start = {j->start_mv_row, j->start_mv_col}, best;
+        int dist = 0;
+        unsigned int sse = 0;
+        const int err = svt_av1_find_best_sub_pixel_tree(&xd, NULL, &ms, start, &best, &dist, &sse, NULL);
+        results[i].mv_row = best.row, results[i].mv_col = best.col;
+        results[i].besterr = err, results[i].distortion = dist, results[i].sse = sse;
+    }
+    return 0;
+}
+
+/* the limits md_subpel_search derives for a block (EbProductCodingLoop.c:2090-2101) */
+REFH_API void refh_subpel_limits(int mi_rows, int mi_cols, int blk_x, int blk_y, int bw, int bh, int ref_mv_row, int ref_mv_col,
+                                 int16_t out[4]) {
+    MV ref_mv = {(int16_t)ref_mv_row, (int16_t)ref_mv_col};
+    MvLimits lim;
+    const int mi_row = blk_y >> 2, mi_col = blk_x >> 2;
+    lim.row_min = -(((mi_row + (bh >> 2)) * MI_SIZE) + AOM_INTERP_EXTEND);
+    lim.col_min = -(((mi_col + (bw >> 2)) * MI_SIZE) + AOM_INTERP_EXTEND);
+    lim.row_max = (mi_rows - mi_row) * MI_SIZE + AOM_INTERP_EXTEND;
+    lim.col_max = (mi_cols - mi_col) * MI_SIZE + AOM_INTERP_EXTEND;
+    svt_av1_set_mv_search_range(&lim, &ref_mv);
+    SubpelMvLimits sl;
+    svt_av1_set_subpel_mv_search_range(&sl, (FullMvLimits *)&lim, &ref_mv);
+    out[0] = (int16_t)sl.col_min, out[1] = (int16_t)sl.col_max, out[2] = (int16_t)sl.row_min, out[3] = (int16_t)sl.row_max;
+}

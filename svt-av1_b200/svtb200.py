@@ -160,6 +160,17 @@ INTER_JOB_DTYPE = [("plane", "u1"), ("n_refs", "u1"), ("bw", "u1"), ("bh", "u1")
                    ("mb_to_bottom_edge", "<i4")]
 
 
+class SubpelParams(C.Structure):
+    _fields_ = [("allow_hp", C.c_int32), ("forced_stop", C.c_int32), ("iters_per_step", C.c_int32), ("subpel_search_type", C.c_int32),
+                ("mv_cost_type", C.c_int32), ("error_per_bit", C.c_int32), ("mvjcost", C.c_int32 * 4), ("mvcost", C.c_void_p * 2)]
+
+
+SUBPEL_JOB_DTYPE = [("blk_x", "<i2"), ("blk_y", "<i2"), ("bw", "u1"), ("bh", "u1"), ("ref", "u1"), ("reserved", "u1"),
+                    ("start_mv_row", "<i2"), ("start_mv_col", "<i2"), ("ref_mv_row", "<i2"), ("ref_mv_col", "<i2"),
+                    ("col_min", "<i2"), ("col_max", "<i2"), ("row_min", "<i2"), ("row_max", "<i2")]
+SUBPEL_RESULT_DTYPE = [("mv_row", "<i2"), ("mv_col", "<i2"), ("besterr", "<i4"), ("distortion", "<i4"), ("sse", "<u4")]
+
+
 def preset8_me_params(width, height, n_l0=1, n_l1=1, dist=((1, 2, 3, 4), (1, 2, 3, 4)), temporal_layer=1,
                       is_ref=1):
     """ME parameters of preset 8 (ENC_M8) at >=720p, 30 fps, as set_me_hme_params_oq /
