@@ -162,7 +162,8 @@ INTER_JOB_DTYPE = [("plane", "u1"), ("n_refs", "u1"), ("bw", "u1"), ("bh", "u1")
 
 class SubpelParams(C.Structure):
     _fields_ = [("allow_hp", C.c_int32), ("forced_stop", C.c_int32), ("iters_per_step", C.c_int32), ("subpel_search_type", C.c_int32),
-                ("mv_cost_type", C.c_int32), ("error_per_bit", C.c_int32), ("mvjcost", C.c_int32 * 4), ("mvcost", C.c_void_p * 2)]
+                ("mv_cost_type", C.c_int32), ("error_per_bit", C.c_int32), ("mvjcost", C.c_int32 * 4), ("max_block_w", C.c_int32),
+                ("max_block_h", C.c_int32), ("mvcost", C.c_void_p * 2)]
 
 
 SUBPEL_JOB_DTYPE = [("blk_x", "<i2"), ("blk_y", "<i2"), ("bw", "u1"), ("bh", "u1"), ("ref", "u1"), ("reserved", "u1"),

@@ -130,6 +130,43 @@ for what, ijobs in (("every AV1 block shape down to 4x4 / 2x2 chroma", ic.make_j
                         "gpu_ms": ms, "algorithmic_bytes": alg, "achieved_gbs": alg / ms / 1e6, "hbm_frac": alg / ms / 1e6 / peak,
                         "reference_c_ms_1thread": ref_ms})
 
+# ---- svt_b200_subpel_search: one search per 16x16 block of the picture and 2 references (md_subpel_search's set-up) ----
+import subpel_cases as sc  # noqa: E402
+from test_subpel_gpu import run_gpu as _subpel_run  # noqa: E402,F401
+ssrc, srefs = sc.pictures(W, H, 77, n_refs=2)
+sp, stabs = sc.params(seed=5, search_type=3, iters=2, allow_hp=1)
+mi_cols, mi_rows = 2 * ((W + 7) >> 3), 2 * ((H + 7) >> 3)
+sj = []
+srng = np.random.default_rng(9)
+for by in range(0, H - 15, 16):
+    for bx in range(0, W - 15, 16):
+        for r in range(2):
+            j = np.zeros((), sb.SUBPEL_JOB_DTYPE)
+            fr, fc = int(srng.integers(-8, 9)), int(srng.integers(-8, 9))
+            j["blk_x"], j["blk_y"], j["bw"], j["bh"], j["ref"] = bx, by, 16, 16, r
+            j["start_mv_row"], j["start_mv_col"], j["ref_mv_row"], j["ref_mv_col"] = fr * 8, fc * 8, fr * 8 + 3, fc * 8 - 5
+            j["col_min"], j["col_max"], j["row_min"], j["row_max"] = sc.limits(mi_rows, mi_cols, bx, by, 16, 16, fr * 8 + 3, fc * 8 - 5)
+            sj.append(j)
+sj = np.array(sj, dtype=sb.SUBPEL_JOB_DTYPE)
+d_ssrc, d_srefs = gr.DevYuv(ssrc), [gr.DevYuv(x) for x in srefs]
+d_stabs = [torch.from_numpy(t).cuda() for t in stabs]
+sq = sb.SubpelParams.from_buffer_copy(sp)
+for i in range(2):
+    sq.mvcost[i] = d_stabs[i].data_ptr() + 4 * sc.MV_MAX
+sq.max_block_w = sq.max_block_h = 16
+d_sj = torch.from_numpy(sj.view(np.uint8)).cuda()
+d_sr = torch.zeros(len(sj) * 16, dtype=torch.uint8, device="cuda")
+sss = d_ssrc.struct()
+sarr = (sb.Frame * 2)(*[x.struct() for x in d_srefs])
+ms = gpu_ms(lambda: sb.check(lib.svt_b200_subpel_search(C.byref(sq), C.byref(sss), sarr, 2, C.c_void_p(d_sj.data_ptr()), len(sj),
+                                                       C.c_void_p(d_sr.data_ptr()), None), lib), n=5)
+cm.refh().refh_subpel_search.restype = C.c_int
+t0 = time.perf_counter()
+sc.run_cpu(cm.refh().refh_subpel_search, sp, stabs, ssrc, srefs, sj[::16])
+ref_ms = (time.perf_counter() - t0) * 1e3 * 16
+out["rows"].append({"entry": "svt_b200_subpel_search (%d searches: every 16x16 block x 2 references, 8-tap, 1/8 sample, 2 iterations per step)" % len(sj),
+                    "gpu_ms": ms, "searches_per_s": len(sj) / ms * 1e3, "reference_c_ms_1thread": ref_ms})
+
 # ---- svt_av1_pick_filter_level (full-image search) -------------------------------------------------------------------
 mi_rows, mi_cols, part, psrc, prec = pick_case(W, H, BD, 6)
 last = (24, 20, 14, 10)
