@@ -73,6 +73,7 @@ __device__ __forceinline__ int clip8(int v) { return min(max(v, 0), 255); }
 
 struct Geo {
     int w, h, wp, tp; // window pitch (bytes), transposed-intermediate pitch (bytes)
+    uint32_t inv_h7, inv_w; // ceil(2^32 / (h + 7)), ceil(2^32 / w): exact quotients by __umulhi for the item counts here
     uint8_t *win, *tmp, *src;
 };
 
@@ -89,7 +90,7 @@ __device__ unsigned eval_error(const Geo &g, const SvtB200SubpelParams &p, Mv2 s
     const int ngx = g.w >> 2;
     // pass 1: rows 0 .. h + 6 (3 above, 4 below the block), 4 columns per thread, transposed 8-bit output
     for (int it = threadIdx.x; it < (g.h + 7) * ngx; it += SP_NT) {
-        const int xg = it / (g.h + 7), r = it - xg * (g.h + 7); // r fastest: the transposed stores of a warp are contiguous
+        const int xg = (int)__umulhi((uint32_t)it, g.inv_h7), r = it - xg * (g.h + 7); // r fastest: the transposed stores of a warp are contiguous
         const uint32_t *wr = reinterpret_cast<const uint32_t *>(g.win + (r0 + r) * g.wp) + xg;
         const uint32_t a0 = wr[0], a1 = wr[1], a2 = wr[2], a3 = wr[3];
         const uint32_t W0 = __funnelshift_r(a0, a1, 8 * c0), W1 = __funnelshift_r(a1, a2, 8 * c0), W2 = __funnelshift_r(a2, a3, 8 * c0);
@@ -105,7 +106,7 @@ __device__ unsigned eval_error(const Geo &g, const SvtB200SubpelParams &p, Mv2 s
     int sum = 0;
     unsigned sse = 0;
     for (int it = threadIdx.x; it < g.w * (g.h >> 2); it += SP_NT) {
-        const int yg = it / g.w, x = it - yg * g.w;
+        const int yg = (int)__umulhi((uint32_t)it, g.inv_w), x = it - yg * g.w;
         const uint32_t *tc = reinterpret_cast<const uint32_t *>(g.tmp + x * g.tp) + yg;
         const uint32_t W0 = tc[0], W1 = tc[1], W2 = tc[2];
 #pragma unroll
@@ -183,6 +184,8 @@ __global__ void __launch_bounds__(SP_NT) subpel_kernel(const __grid_constant__ S
     g.w = j.bw, g.h = j.bh;
     g.wp = ((g.w + 2 * REACH + 7 + 4 + 3) & ~3) | 4;  // >= w + 11 + the realignment over-read, pitch / 4 odd
     g.tp = ((g.h + 8 + 3) & ~3) | 4;                   // >= h + 8, pitch / 4 odd
+    g.inv_h7 = (uint32_t)(((1ull << 32) + g.h + 6) / (uint32_t)(g.h + 7));
+    g.inv_w = (uint32_t)(((1ull << 32) + g.w - 1) / (uint32_t)g.w);
     g.win = smem;
     g.tmp = g.win + (g.h + 2 * REACH + 7) * g.wp;
     g.src = g.tmp + g.w * g.tp;
