@@ -811,7 +811,8 @@ typedef struct SvtB200SubpelParams {
     int32_t mv_cost_type;       /* MV_COST_TYPE: 0 ENTROPY, 1 L1_LOWRES, 2 L1_MIDRES, 3 L1_HDRES, 4 NONE */
     int32_t error_per_bit;      /* AOMMAX(rdmult >> RD_EPB_SHIFT, 1) */
     int32_t mvjcost[4];         /* md_rate_estimation_ptr->nmv_vec_cost */
-    int32_t max_block_w, max_block_h; /* largest bw / bh among the jobs (sizes the shared-memory window); 0 = 128 */
+    int32_t max_block_w, max_block_h; /* largest bw / bh among the jobs (sizes the shared-memory window and the CTA); 0 = 128.
+                                       * A job that exceeds it is not searched: besterr = distortion = -1, mv = start_mv */
     const int32_t *mvcost[2];   /* DEVICE, nmvcoststack[0 / 1]: centred tables, indices -16383 .. 16383 (MV_COST_ENTROPY only) */
 } SvtB200SubpelParams;
 typedef struct SvtB200SubpelResult {

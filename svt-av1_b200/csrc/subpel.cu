@@ -53,10 +53,10 @@ struct SubpelDev {
     int ref_stride[8];
     const SvtB200SubpelJob *jobs;
     SvtB200SubpelResult *results;
-    int n_jobs;
+    int n_jobs, max_w, max_h;
 };
 
-constexpr int SP_NT = 128;
+constexpr int SP_NT_MAX = 128; // CTA size is a template parameter: 32 / 64 / 128 threads by the largest block of the batch
 constexpr int REACH = 2; // whole samples the search can move up/left of the start position (14/8 -> -2 .. +1)
 
 __device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c) {
@@ -82,6 +82,7 @@ struct Mv2 {
 };
 
 // svt_upsampled_pref_error for one candidate, by the whole CTA; returns the variance, *sse_out the sum of squares
+template <int SP_NT>
 __device__ unsigned eval_error(const Geo &g, const SvtB200SubpelParams &p, Mv2 start, Mv2 mv, unsigned *sse_out, int *s_red) {
     const int drow = (mv.row >> 3) - (start.row >> 3), dcol = (mv.col >> 3) - (start.col >> 3); // -REACH .. REACH - 1
     const uint2 tx = sub_taps(p.subpel_search_type, mv.col & 7), ty = sub_taps(p.subpel_search_type, mv.row & 7);
@@ -159,11 +160,12 @@ struct Best {
     int distortion;
 };
 
+template <int SP_NT>
 __device__ unsigned check_better(const Geo &g, const SvtB200SubpelParams &p, const SvtB200SubpelJob &j, Mv2 start, Mv2 mv, Best &b,
                                  int &is_better, int *s_red) {
     if (mv.col < j.col_min || mv.col > j.col_max || mv.row < j.row_min || mv.row > j.row_max) return 0x7fffffffu; // INT_MAX
     unsigned sse;
-    const int thismse = (int)eval_error(g, p, start, mv, &sse, s_red);
+    const int thismse = (int)eval_error<SP_NT>(g, p, start, mv, &sse, s_red);
     const unsigned cost = (unsigned)mv_err_cost(p, j, mv) + (unsigned)thismse;
     if (cost < b.besterr) {
         b.besterr = cost;
@@ -175,11 +177,16 @@ __device__ unsigned check_better(const Geo &g, const SvtB200SubpelParams &p, con
     return cost;
 }
 
+template <int SP_NT>
 __global__ void __launch_bounds__(SP_NT) subpel_kernel(const __grid_constant__ SubpelDev d) {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int s_red[2 * SP_NT / 32];
+    __shared__ int s_red[2 * SP_NT_MAX / 32];
     const SvtB200SubpelJob j = d.jobs[blockIdx.x];
     const SvtB200SubpelParams &p = d.p;
+    if (j.bw > d.max_w || j.bh > d.max_h || j.bw < 4 || j.bh < 4 || ((j.bw | j.bh) & 3)) { // does not fit the window of this launch
+        if (threadIdx.x == 0) d.results[blockIdx.x] = SvtB200SubpelResult{j.start_mv_row, j.start_mv_col, -1, -1, 0u};
+        return;
+    }
     Geo g;
     g.w = j.bw, g.h = j.bh;
     g.wp = ((g.w + 2 * REACH + 7 + 4 + 3) & ~3) | 4;  // >= w + 11 + the realignment over-read, pitch / 4 odd
@@ -209,19 +216,19 @@ __global__ void __launch_bounds__(SP_NT) subpel_kernel(const __grid_constant__ S
     const int round = min(3 - p.forced_stop, 3 - (p.allow_hp ? 0 : 1));
     Best b;
     b.mv = start;
-    b.besterr = eval_error(g, p, start, start, &b.sse, s_red);
+    b.besterr = eval_error<SP_NT>(g, p, start, start, &b.sse, s_red);
     b.distortion = (int)b.besterr;
     b.besterr += (unsigned)mv_err_cost(p, j, start);
     int hstep = 4;
     for (int iter = 0; iter < round; iter++) {
         const Mv2 ctr = b.mv;
         int dummy = 0;
-        const unsigned left = check_better(g, p, j, start, Mv2{ctr.row, ctr.col - hstep}, b, dummy, s_red);
-        const unsigned right = check_better(g, p, j, start, Mv2{ctr.row, ctr.col + hstep}, b, dummy, s_red);
-        const unsigned up = check_better(g, p, j, start, Mv2{ctr.row - hstep, ctr.col}, b, dummy, s_red);
-        const unsigned down = check_better(g, p, j, start, Mv2{ctr.row + hstep, ctr.col}, b, dummy, s_red);
+        const unsigned left = check_better<SP_NT>(g, p, j, start, Mv2{ctr.row, ctr.col - hstep}, b, dummy, s_red);
+        const unsigned right = check_better<SP_NT>(g, p, j, start, Mv2{ctr.row, ctr.col + hstep}, b, dummy, s_red);
+        const unsigned up = check_better<SP_NT>(g, p, j, start, Mv2{ctr.row - hstep, ctr.col}, b, dummy, s_red);
+        const unsigned down = check_better<SP_NT>(g, p, j, start, Mv2{ctr.row + hstep, ctr.col}, b, dummy, s_red);
         Mv2 diag{up <= down ? -hstep : hstep, left <= right ? -hstep : hstep};
-        check_better(g, p, j, start, Mv2{ctr.row + diag.row, ctr.col + diag.col}, b, dummy, s_red);
+        check_better<SP_NT>(g, p, j, start, Mv2{ctr.row + diag.row, ctr.col + diag.col}, b, dummy, s_red);
         if (!(ctr.row == b.mv.row && ctr.col == b.mv.col) && p.iters_per_step > 1) { // svt_second_level_check_v2
             if (ctr.row == b.mv.row)
                 diag.row = -diag.row;
@@ -229,9 +236,9 @@ __global__ void __launch_bounds__(SP_NT) subpel_kernel(const __grid_constant__ S
                 diag.col = -diag.col;
             const Mv2 rb{b.mv.row + diag.row, b.mv.col}, cb{b.mv.row, b.mv.col + diag.col}, db{b.mv.row + diag.row, b.mv.col + diag.col};
             int has_better = 0;
-            check_better(g, p, j, start, rb, b, has_better, s_red);
-            check_better(g, p, j, start, cb, b, has_better, s_red);
-            if (has_better) check_better(g, p, j, start, db, b, has_better, s_red);
+            check_better<SP_NT>(g, p, j, start, rb, b, has_better, s_red);
+            check_better<SP_NT>(g, p, j, start, cb, b, has_better, s_red);
+            if (has_better) check_better<SP_NT>(g, p, j, start, db, b, has_better, s_red);
         }
         hstep >>= 1;
     }
@@ -269,7 +276,7 @@ extern "C" int svt_b200_subpel_search(const SvtB200SubpelParams *p, const SvtB20
     SVTB_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 64 && !tables_done[dev].load()) {
         SVTB_CUDA_TRY(cudaMemcpyToSymbol(c_sub_taps, h_sub_taps, sizeof(h_sub_taps)));
-        SVTB_CUDA_TRY(cudaFuncSetAttribute(subpel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(128, 128)));
+        SVTB_CUDA_TRY(cudaFuncSetAttribute(subpel_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(128, 128)));
         tables_done[dev].store(1);
     }
     SubpelDev d;
@@ -286,8 +293,16 @@ extern "C" int svt_b200_subpel_search(const SvtB200SubpelParams *p, const SvtB20
         d.ref_stride[i] = refs[i].stride_y;
     }
     d.jobs = jobs, d.results = results, d.n_jobs = n_jobs;
-    const size_t smem = smem_bytes(p->max_block_w ? p->max_block_w : 128, p->max_block_h ? p->max_block_h : 128);
-    SVTB_LAUNCH(subpel_kernel, n_jobs, SP_NT, smem, (cudaStream_t)stream, d);
+    const int mw = p->max_block_w ? p->max_block_w : 128, mh = p->max_block_h ? p->max_block_h : 128;
+    const size_t smem = smem_bytes(mw, mh);
+    d.max_w = mw, d.max_h = mh;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (mw * mh <= 64) // a pass is (h + 7) x w / 4 resp. w x h / 4 work items: one warp covers an 8x8 block
+        SVTB_LAUNCH(subpel_kernel<32>, n_jobs, 32, smem, st, d);
+    else if (mw * mh <= 1024)
+        SVTB_LAUNCH(subpel_kernel<64>, n_jobs, 64, smem, st, d);
+    else
+        SVTB_LAUNCH(subpel_kernel<128>, n_jobs, 128, smem, st, d);
     SVTB_CUDA_TRY(cudaGetLastError());
     return SVT_B200_OK;
 }

@@ -60,3 +60,17 @@ def test_subpel_search_1080p_batch():
     again = run_gpu(p, tabs, src, refs, jobs)  # default window size (128x128): same answers
     for f in ("mv_row", "mv_col", "besterr"):
         np.testing.assert_array_equal(again[f], want[f], f)
+
+
+@pytest.mark.parametrize("mx", [8, 16, 32])
+def test_subpel_search_small_block_launches(mx):
+    """max_block_w / _h select the CTA size (32 / 64 threads for small blocks): same answers."""
+    w, h = 256, 128
+    src, refs = sc.pictures(w, h, 90 + mx)
+    blocks = [b for b in sc.BLOCKS if max(b) <= mx]
+    jobs = sc.make_jobs(w, h, len(refs), 150, 91 + mx, blocks=blocks)
+    p, tabs = sc.params(seed=mx, search_type=3, iters=2, allow_hp=1)
+    want = sc.run_cpu(cm.oracle().orc_subpel_search, p, tabs, src, refs, jobs)
+    got = run_gpu(p, tabs, src, refs, jobs, max_block=(mx, mx))
+    for f in ("mv_row", "mv_col", "besterr", "distortion", "sse"):
+        np.testing.assert_array_equal(got[f], want[f], f)
