@@ -1,0 +1,164 @@
+"""Golden digests: outputs of the UNMODIFIED reference (oracle/_ref) on seeded inputs, reduced to SHA-256 and committed in
+tests/golden/reference_digests.json by tests/golden/make_golden.py; test_golden.py checks that the oracle reproduces every
+digest, so the oracle stays pinned to the reference even on a machine where oracle/_ref cannot be built.
+Each case is a function(which) -> bytes with which in {"ref", "oracle"}."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+
+import common as cm
+import svtb200 as sb
+
+
+def _frame_bytes(f):
+    return b"".join(np.ascontiguousarray(f.plane(i)).tobytes() for i in range(3))
+
+
+def case_me(which):
+    w, h, n0, n1, tl, isref, dist = 320, 192, 2, 1, 1, 1, ((1, 2, 3, 4), (1, 2, 3, 4))
+    geos, src, refs = cm.make_me_case(w, h, n0, n1, seed=321)
+    if which == "ref":
+        params, out = cm.run_ref_me(w, h, 8, n0, n1, dist, tl, isref, geos, src, refs)
+    else:
+        params = sb.preset8_me_params(w, h, n0, n1, dist, tl, isref)
+        out = cm.run_oracle_me(params, src, refs)
+    f = out.fields()
+    used = [f["best_sad"][:, l, r].tobytes() + f["best_mv"][:, l, r].tobytes() + f["hme"][:, l, r].tobytes()
+            for l in range(params.num_lists) for r in range(params.num_refs[l])]
+    return b"".join(used) + f["me_mv"].tobytes() + f["me_cand"].tobytes() + f["total_cand"].tobytes() + f["rc"].tobytes()
+
+
+def case_encode(which):
+    from test_txfm_gpu import make_tus, oracle_encode_tus, quant_plane
+    out = b""
+    for ts, bd, use_fp in ((2, 8, 0), (3, 10, 1), (12, 8, 0), (18, 10, 0)):
+        rng = np.random.default_rng(1000 + ts)
+        W, H = 192, 128
+        src = cm.synth_yuv(W, H, 1, 7, bd)
+        pred = cm.degrade(src, 11, amp=14)
+        p = sb.EncodeParams()
+        p.tx_size, p.use_fp = ts, use_fp
+        for i in range(3):
+            p.q[i] = quant_plane(rng, bd)
+        tus = make_tus(rng, ts, W, H, limit=60)
+        if which == "oracle":
+            rec, q, eob = oracle_encode_tus(p, src, pred, tus, use_fp)
+        else:
+            rec = pred.copy()
+            n = min(sb.TX_W[ts], 32) * min(sb.TX_H[ts], 32)
+            q, eob = np.zeros((len(tus), n), np.int32), np.zeros(len(tus), np.uint16)
+            arr = (sb.Tu * len(tus))(*tus)
+            ss, ps, rs = src.struct(), pred.struct(), rec.struct()
+            cm.refh().refh_encode_tus(C.byref(p), C.byref(ss), C.byref(ps), C.byref(rs), arr, len(tus), cm.ptr(q), cm.ptr(eob))
+        out += np.ascontiguousarray(q).tobytes() + np.ascontiguousarray(eob).astype(np.uint16).tobytes() + _frame_bytes(rec)
+    return out
+
+
+def case_dlf(which):
+    from test_oracle_dlf import dlf_case, dlf_params, run_ref_dlf
+    from test_dlf_gpu import flat_mi
+    out = b""
+    for (w, h, bd, seed, levels, sharp) in ((192, 136, 8, 1, (20, 24, 12, 9), 0), (192, 136, 10, 2, (33, 17, 40, 25), 3)):
+        mi_rows, mi_cols, part, frame = dlf_case(w, h, bd, seed, levels, sharp)
+        if which == "ref":
+            got, _ = run_ref_dlf(mi_rows, mi_cols, part, frame, levels, sharp)
+        else:
+            flat = flat_mi(mi_rows, mi_cols, part, levels)
+            p = dlf_params(mi_rows, mi_cols, levels, sharp)
+            got = frame.copy()
+            st = got.struct()
+            cm.oracle().orc_dlf_frame(C.byref(p), C.byref(st), flat)
+        out += _frame_bytes(got)
+    return out
+
+
+def case_cdef(which):
+    from test_oracle_cdef import cdef_picture_case
+    out = b""
+    for (w, h, bd, pick) in ((192, 136, 8, 3), (136, 128, 10, 1)):
+        src, rec, mi_rows, mi_cols, skip = cdef_picture_case(w, h, bd)
+        nfb = ((mi_rows + 15) // 16) * ((mi_cols + 15) // 16)
+        mse = np.zeros((2, nfb, 64), np.uint64)
+        rs, ss = rec.struct(), src.struct()
+        if which == "ref":
+            cm.refh().refh_cdef_search(mi_rows, mi_cols, 172, {0: 1, 1: 2, 2: 3, 3: 4}[pick], C.byref(rs), C.byref(ss), cm.ptr(skip),
+                                       skip.shape[1], cm.ptr(mse))
+        else:
+            p = sb.CdefSearchParams()
+            p.mi_rows, p.mi_cols, p.pri_damping = mi_rows, mi_cols, 3 + (172 >> 6)
+            cm.oracle().orc_cdef_strength_table(pick, C.byref(p))
+            cm.oracle().orc_cdef_search(C.byref(p), C.byref(rs), C.byref(ss), cm.ptr(skip), skip.shape[1], cm.ptr(mse))
+        out += mse.tobytes()
+        idx = np.random.default_rng(4).integers(0, 8, nfb).astype(np.int8)
+        ys, uvs = (C.c_int32 * 8)(0, 5, 17, 63, 40, 2, 12, 33), (C.c_int32 * 8)(0, 0, 9, 62, 4, 1, 60, 3)
+        if which == "ref":
+            got = rec.copy()
+            st = got.struct()
+            cm.refh().refh_cdef_apply(mi_rows, mi_cols, 5, ys, uvs, C.byref(st), cm.ptr(skip), skip.shape[1], cm.ptr(idx))
+        else:
+            p = sb.CdefApplyParams()
+            p.mi_rows, p.mi_cols, p.damping = mi_rows, mi_cols, 5
+            for i in range(8):
+                p.y_strength[i], p.uv_strength[i] = ys[i], uvs[i]
+            got = rec.copy()
+            os_ = got.struct()
+            cm.oracle().orc_cdef_apply(C.byref(p), C.byref(rs), C.byref(os_), cm.ptr(skip), skip.shape[1], cm.ptr(idx))
+        out += _frame_bytes(got)
+    return out
+
+
+def case_lr(which):
+    from test_oracle_lr_frame import lr_case, run_oracle_lr, run_ref_lr
+    out = b""
+    for (w, h, bd, seed, unit_sizes, modes, opt) in ((200, 136, 8, 3, (64, 32, 32), ("mix", "mix", "mix"), 0),
+                                                     (192, 144, 10, 4, (128, 64, 64), ("wiener", "sgr", "mix"), 1)):
+        cdef, dblk, units = lr_case(w, h, bd, seed, unit_sizes, modes)
+        got = (run_ref_lr if which == "ref" else run_oracle_lr)(cdef, dblk, units, unit_sizes, (3, 3, 3), opt)
+        out += _frame_bytes(got)
+    return out
+
+
+def case_inter(which):
+    import interp_cases as ic
+    out = b""
+    for (w, h, bd, sb_size, seed) in ((176, 144, 8, 64, 11), (128, 96, 12, 64, 15)):
+        refs = [ic.ref_picture(w, h, bd, seed * 10 + i, "texture" if i else "rand") for i in range(3)]
+        jobs = ic.make_jobs(w, h, len(refs), seed, sb_size=sb_size)
+        fn = cm.refh().refh_inter_predict if which == "ref" else cm.oracle().orc_inter_predict
+        got = ic.run_cpu(fn, refs, cm.Yuv(w, h, bd, pad=ic.REF_PAD), jobs)
+        out += _frame_bytes(got)
+    return out
+
+
+def case_subpel(which):
+    import subpel_cases as sc
+    out = b""
+    for cfg in (dict(search_type=3, iters=2, allow_hp=1), dict(search_type=2, iters=1, allow_hp=0), dict(search_type=1, iters=2, allow_hp=1, cost_type=1)):
+        src, refs = sc.pictures(320, 192, 40)
+        jobs = sc.make_jobs(320, 192, len(refs), 88, 50)
+        p, tabs = sc.params(seed=1, **cfg)
+        if which == "ref":
+            cm.refh().refh_subpel_search.restype = C.c_int
+        fn = cm.refh().refh_subpel_search if which == "ref" else cm.oracle().orc_subpel_search
+        out += sc.run_cpu(fn, p, tabs, src, refs, jobs).tobytes()
+    return out
+
+
+def case_downsample(which):
+    from test_oracle_me import downsample_case, run_downsample
+    out = b""
+    for (w, h, filt) in ((322, 182, 1), (176, 144, 0)):
+        geos, full, q, s = downsample_case(w, h, 5)
+        fn = cm.refh().refh_me_downsample if which == "ref" else cm.oracle().orc_me_downsample
+        q, s = run_downsample(fn, geos, full, q, s, filt)
+        out += q.tobytes() + s.tobytes()
+    return out
+
+
+CASES = {"me_picture": case_me, "encode_tus": case_encode, "dlf_frame": case_dlf, "cdef_search_apply": case_cdef, "lr_frame": case_lr,
+         "inter_predict": case_inter, "subpel_search": case_subpel, "me_downsample": case_downsample}
+
+
+def digest(name, which):
+    return hashlib.sha256(CASES[name](which)).hexdigest()
