@@ -787,6 +787,24 @@ SVT_B200_API int svt_b200_inter_predict(const SvtB200Frame *refs, int32_t n_ref_
 /* Sub-pel motion refinement                                                  */
 /* =============================================================================================== */
 
+/* replace svt_aom_varianceWxH (22 sizes, aom_dsp_rtcd.h:488-530; EbComputeVariance_C.c:14-61) and svt_aom_mse16x16 (:249;
+ * EbPsnr.c:84-89, which returns the variance too) */
+#define SVT_B200_VAR_DECL(W, H)                                                                                      \
+    SVT_B200_API unsigned int svt_aom_variance##W##x##H##_cuda(const uint8_t *src_ptr, int source_stride,             \
+                                                               const uint8_t *ref_ptr, int ref_stride, unsigned int *sse);
+SVT_B200_VAR_DECL(4, 4) SVT_B200_VAR_DECL(4, 8) SVT_B200_VAR_DECL(4, 16) SVT_B200_VAR_DECL(8, 4) SVT_B200_VAR_DECL(8, 8)
+SVT_B200_VAR_DECL(8, 16) SVT_B200_VAR_DECL(8, 32) SVT_B200_VAR_DECL(16, 4) SVT_B200_VAR_DECL(16, 8) SVT_B200_VAR_DECL(16, 16)
+SVT_B200_VAR_DECL(16, 32) SVT_B200_VAR_DECL(16, 64) SVT_B200_VAR_DECL(32, 8) SVT_B200_VAR_DECL(32, 16) SVT_B200_VAR_DECL(32, 32)
+SVT_B200_VAR_DECL(32, 64) SVT_B200_VAR_DECL(64, 16) SVT_B200_VAR_DECL(64, 32) SVT_B200_VAR_DECL(64, 64) SVT_B200_VAR_DECL(64, 128)
+SVT_B200_VAR_DECL(128, 64) SVT_B200_VAR_DECL(128, 128)
+SVT_B200_API uint32_t svt_aom_mse16x16_cuda(const uint8_t *src_ptr, int32_t source_stride, const uint8_t *ref_ptr,
+                                            int32_t recon_stride, uint32_t *sse);
+/* replaces svt_aom_upsampled_pred (aom_dsp_rtcd.h:354; Encoder/C_DEFAULT/variance.c:212-269). xd, cm, mi_row, mi_col, mv are
+ * unused by the C code as well; subpel_search: 1 USE_2_TAPS, 2 USE_4_TAPS, 3 USE_8_TAPS. */
+SVT_B200_API void svt_aom_upsampled_pred_cuda(void *xd, const void *cm, int mi_row, int mi_col, const void *mv, uint8_t *comp_pred,
+                                              int width, int height, int subpel_x_q3, int subpel_y_q3, const uint8_t *ref,
+                                              int ref_stride, int subpel_search);
+
 /* svt_av1_find_best_sub_pixel_tree (Encoder/Codec/mcomp.c:350-418) as md_subpel_search sets it up
  * (EbProductCodingLoop.c:2063-2155: 8-bit luma, no second predictor / mask / OBMC, last_mv_search_list == NULL), for a
  * batch of independent (block, reference) searches.  The search is the reference's: centre error, then per round

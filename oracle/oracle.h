@@ -103,6 +103,8 @@ ORC_API void orc_convolve8(const uint8_t *src, ptrdiff_t src_stride, uint8_t *ds
 ORC_API void orc_inter_predict(const SvtB200Frame *refs, int n_ref_frames, const SvtB200Frame *pred, const SvtB200InterJob *jobs,
                                int n_jobs);
 /* ---- subpel_oracle.c ---- */
+ORC_API void orc_upsampled_pred(uint8_t *comp_pred, int width, int height, int subpel_x_q3, int subpel_y_q3, const uint8_t *ref,
+                                int ref_stride, int subpel_search);
 ORC_API void orc_subpel_search(const SvtB200SubpelParams *p, const int32_t *mvcost0, const int32_t *mvcost1, const SvtB200Frame *src,
                                const SvtB200Frame *refs, int n_ref_frames, const SvtB200SubpelJob *jobs, int n_jobs,
                                SvtB200SubpelResult *results);

@@ -83,6 +83,36 @@ static unsigned eval_error(const Ctx *c, Mv mv, unsigned *sse_out) {
     return sse - (unsigned)(((int64_t)sum * sum) / (w * h));
 }
 
+/* svt_aom_upsampled_pred_c (variance.c:212-269) on its own: comp_pred is width x height, packed */
+ORC_API void orc_upsampled_pred(uint8_t *comp_pred, int width, int height, int subpel_x_q3, int subpel_y_q3, const uint8_t *ref,
+                                int ref_stride, int subpel_search) {
+    int16_t kx[8], ky[8];
+    orc_interp_kernel(subpel_search == 1 ? 3 : 0, subpel_search == 3 ? 8 : 4, subpel_x_q3 << 1, kx);
+    orc_interp_kernel(subpel_search == 1 ? 3 : 0, subpel_search == 3 ? 8 : 4, subpel_y_q3 << 1, ky);
+    uint8_t *temp = (uint8_t *)malloc((size_t)(height + 7) * width);
+    if (subpel_x_q3 && subpel_y_q3)
+        for (int y = 0; y < height + 7; y++)
+            for (int x = 0; x < width; x++) {
+                int s = 0;
+                for (int k = 0; k < 8; k++) s += kx[k] * ref[(y - 3) * ref_stride + x - 3 + k];
+                temp[y * width + x] = (uint8_t)clip8((s + 64) >> 7);
+            }
+    for (int y = 0; y < height; y++)
+        for (int x = 0; x < width; x++) {
+            int s = 0, pr;
+            if (!subpel_x_q3 && !subpel_y_q3)
+                pr = ref[y * ref_stride + x];
+            else {
+                for (int k = 0; k < 8; k++)
+                    s += !subpel_y_q3 ? kx[k] * ref[y * ref_stride + x - 3 + k]
+                                      : !subpel_x_q3 ? ky[k] * ref[(y - 3 + k) * ref_stride + x] : ky[k] * temp[(y + k) * width + x];
+                pr = clip8((s + 64) >> 7);
+            }
+            comp_pred[y * width + x] = (uint8_t)pr;
+        }
+    free(temp);
+}
+
 static int mv_err_cost(const Ctx *c, Mv mv) {
     const int16_t dr = (int16_t)(mv.row - c->j->ref_mv_row), dc = (int16_t)(mv.col - c->j->ref_mv_col);
     const int ar = abs(dr), ac = abs(dc);

@@ -520,7 +520,7 @@ __global__ void convolve8_kernel(const __grid_constant__ Conv8Args a) {
 
 void convolve8_run(const uint8_t *src, ptrdiff_t src_stride, uint8_t *dst, ptrdiff_t dst_stride, const int16_t *filter, int step,
                    int w, int h, int vert) {
-    if (w <= 0 || h <= 0 || w > 128 || h > 128 || step <= 0 || step > 64 || !filter || !src || !dst) {
+    if (w <= 0 || h <= 0 || w > 128 || h > 136 || step <= 0 || step > 64 || !filter || !src || !dst) {
         fprintf(stderr, "svt_aom_convolve8_%s_cuda: bad argument\n", vert ? "vert" : "horiz");
         abort();
     }
@@ -591,6 +591,33 @@ void svt_aom_convolve8_vert_cuda(const uint8_t *src, ptrdiff_t src_stride, uint8
                                  int x_step_q4, const int16_t *filter_y, int y_step_q4, int w, int h) {
     (void)filter_x, (void)x_step_q4;
     convolve8_run(src, src_stride, dst, dst_stride, filter_y, y_step_q4, w, h, 1);
+}
+
+void svt_aom_upsampled_pred_cuda(void *xd, const void *cm, int mi_row, int mi_col, const void *mv, uint8_t *comp_pred, int width,
+                                 int height, int subpel_x_q3, int subpel_y_q3, const uint8_t *ref, int ref_stride, int subpel_search) {
+    (void)xd, (void)cm, (void)mi_row, (void)mi_col, (void)mv;
+    if (subpel_search < 1 || subpel_search > 3 || width <= 0 || height <= 0 || width > 128 || height > 128 || !comp_pred || !ref) {
+        fprintf(stderr, "svt_aom_upsampled_pred_cuda: bad argument\n");
+        abort();
+    }
+    if (!subpel_x_q3 && !subpel_y_q3) {
+        for (int i = 0; i < height; i++) memcpy(comp_pred + (size_t)i * width, ref + (ptrdiff_t)i * ref_stride, (size_t)width);
+        return;
+    }
+    // av1_get_filter (variance.c:200-210): bilinear / the regular 4-tap / the regular 8-tap kernels, as a 256-byte aligned
+    // [16][8] table the way svt_aom_convolve8_* locate it (get_filter_base)
+    alignas(256) int16_t table[16][8];
+    for (int sp = 0; sp < 16; sp++) svt_b200_get_interp_kernel(subpel_search == 1 ? 3 : 0, subpel_search == 3 ? 8 : 4, sp, table[sp]);
+    if (!subpel_y_q3) {
+        convolve8_run(ref, ref_stride, comp_pred, width, table[subpel_x_q3 << 1], 16, width, height, 0);
+    } else if (!subpel_x_q3) {
+        convolve8_run(ref, ref_stride, comp_pred, width, table[subpel_y_q3 << 1], 16, width, height, 1);
+    } else { // both: the first pass over height + 7 rows is rounded to 8 bits before the second
+        static thread_local uint8_t temp[(128 + 8) * 128];
+        const int ih = height + 7;
+        convolve8_run(ref - 3 * (ptrdiff_t)ref_stride, ref_stride, temp, width, table[subpel_x_q3 << 1], 16, width, ih, 0);
+        convolve8_run(temp + 3 * width, width, comp_pred, width, table[subpel_y_q3 << 1], 16, width, height, 1);
+    }
 }
 
 int svt_b200_get_interp_kernel(int32_t interp_filter, int32_t w, int32_t subpel, int16_t out[8]) {

@@ -14,7 +14,7 @@ using namespace svtb200;
 
 namespace {
 
-enum { M_SAD8 = 0, M_SAD16, M_SSE8, M_SSE16, M_DIST32, M_SQ32, M_SATD, M_BLKERR };
+enum { M_SAD8 = 0, M_SAD16, M_SSE8, M_SSE16, M_DIST32, M_SQ32, M_SATD, M_BLKERR, M_VAR8 };
 
 // a, b: packed w x h arrays (element size by mode). out[0], out[1]: 64-bit results.
 __global__ void __launch_bounds__(256) reduce2_kernel(const void *a, const void *b, int n, int mode, unsigned long long *out) {
@@ -45,6 +45,12 @@ __global__ void __launch_bounds__(256) reduce2_kernel(const void *a, const void 
             break;
         }
         case M_SATD: r0 += (unsigned long long)(long long)abs(((const int32_t *)a)[i]); break;
+        case M_VAR8: { // variance_c: sum of differences (two's complement in r0) and of their squares
+            const long long d = (long long)((const uint8_t *)a)[i] - ((const uint8_t *)b)[i];
+            r0 += (unsigned long long)d;
+            r1 += (unsigned long long)(d * d);
+            break;
+        }
         default: { // svt_av1_block_error_c: int products (32-bit), 64-bit sums
             const int c = ((const int32_t *)a)[i], d = c - ((const int32_t *)b)[i];
             r0 += (unsigned long long)(long long)(int)((unsigned)d * (unsigned)d);
@@ -181,6 +187,26 @@ uint32_t sad_16b_kernel_cuda(uint16_t *src, uint32_t src_stride, uint16_t *ref, 
 SAD_MXN(128, 128) SAD_MXN(128, 64) SAD_MXN(64, 128) SAD_MXN(64, 64) SAD_MXN(64, 32) SAD_MXN(64, 16) SAD_MXN(32, 64)
 SAD_MXN(32, 32) SAD_MXN(32, 16) SAD_MXN(32, 8) SAD_MXN(16, 64) SAD_MXN(16, 32) SAD_MXN(16, 16) SAD_MXN(16, 8)
 SAD_MXN(16, 4) SAD_MXN(8, 32) SAD_MXN(8, 16) SAD_MXN(8, 8) SAD_MXN(8, 4) SAD_MXN(4, 16) SAD_MXN(4, 8) SAD_MXN(4, 4)
+
+// svt_aom_varianceWxH (aom_dsp_rtcd.h:488-530; C impl Encoder/C_DEFAULT/EbComputeVariance_C.c:14-61) and svt_aom_mse16x16
+// (:249; Encoder/Codec/EbPsnr.c:84-89 — despite its name it also returns sse - sum^2 / 256): the reference's 32-bit wrap kept
+static uint32_t variance_run(const void *a, int sa, const void *b, int sb, int w, int h, uint32_t *sse) {
+    uint64_t r[2];
+    reduce2(a, (size_t)sa, b, (size_t)sb, w, h, 1, M_VAR8, r);
+    const int64_t sum = (int64_t)r[0];
+    *sse = (uint32_t)r[1];
+    return *sse - (uint32_t)((sum * sum) / (w * h));
+}
+#define VAR_WXH(W, H)                                                                                                          \
+    unsigned int svt_aom_variance##W##x##H##_cuda(const uint8_t *a, int a_stride, const uint8_t *b, int b_stride, unsigned int *sse) { \
+        return variance_run(a, a_stride, b, b_stride, W, H, sse);                                                        \
+    }
+VAR_WXH(4, 4) VAR_WXH(4, 8) VAR_WXH(4, 16) VAR_WXH(8, 4) VAR_WXH(8, 8) VAR_WXH(8, 16) VAR_WXH(8, 32) VAR_WXH(16, 4) VAR_WXH(16, 8)
+VAR_WXH(16, 16) VAR_WXH(16, 32) VAR_WXH(16, 64) VAR_WXH(32, 8) VAR_WXH(32, 16) VAR_WXH(32, 32) VAR_WXH(32, 64) VAR_WXH(64, 16)
+VAR_WXH(64, 32) VAR_WXH(64, 64) VAR_WXH(64, 128) VAR_WXH(128, 64) VAR_WXH(128, 128)
+uint32_t svt_aom_mse16x16_cuda(const uint8_t *src_ptr, int32_t source_stride, const uint8_t *ref_ptr, int32_t recon_stride, uint32_t *sse) {
+    return variance_run(src_ptr, source_stride, ref_ptr, recon_stride, 16, 16, sse);
+}
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

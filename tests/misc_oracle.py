@@ -119,3 +119,12 @@ def get_proj_subspace(src, dat, flt0, flt1, r):
     if det < 1e-8:
         return [0, 0]
     return [rint((h11 * c0 - h01 * c1) / det * 128), rint((h00 * c1 - h01 * c0) / det * 128)]
+
+
+def variance(a, b):
+    """svt_aom_varianceWxH_c / svt_aom_mse16x16_c (EbComputeVariance_C.c:14-61, EbPsnr.c:84): (variance, sse), 32-bit wrap."""
+    d = a.astype(np.int64) - b.astype(np.int64)
+    sse = int((d * d).sum()) & 0xFFFFFFFF
+    s = int(d.sum())
+    q = abs(s * s) // a.size  # C division of a non-negative value
+    return (sse - (q & 0xFFFFFFFF)) & 0xFFFFFFFF, sse

@@ -45,3 +45,47 @@ def test_subpel_search_matches_reference(cfg):
         np.testing.assert_array_equal(a[f], b[f], f)
     moved = (a["mv_row"] != jobs["start_mv_row"]) | (a["mv_col"] != jobs["start_mv_col"])
     assert moved.any() == (CONFIGS[cfg].get("forced_stop", 0) != 3)
+
+
+VAR_SIZES = [(4, 4), (4, 8), (4, 16), (8, 4), (8, 8), (8, 16), (8, 32), (16, 4), (16, 8), (16, 16), (16, 32), (16, 64), (32, 8), (32, 16),
+             (32, 32), (32, 64), (64, 16), (64, 32), (64, 64), (64, 128), (128, 64), (128, 128)]
+
+
+@needs_ref
+def test_variance_restatement_matches_reference():
+    """misc_oracle.variance vs svt_aom_varianceWxH_c (all 22 sizes) and svt_aom_mse16x16_c, random and extreme blocks."""
+    import misc_oracle as mo
+    lib = cm.ref()
+    rng = np.random.default_rng(8)
+    for (w, h) in VAR_SIZES:
+        fn = getattr(lib, f"svt_aom_variance{w}x{h}_c")
+        fn.restype = C.c_uint32
+        for kind in ("rand", "extreme", "flat"):
+            a = rng.integers(0, 256, (h, w + 7)).astype(np.uint8) if kind == "rand" else np.full((h, w + 7), 255, np.uint8)
+            b = rng.integers(0, 256, (h, w + 3)).astype(np.uint8) if kind == "rand" else np.zeros((h, w + 3), np.uint8)
+            if kind == "flat":
+                b[...] = 250
+            sse = C.c_uint32(0)
+            want = fn(cm.ptr(a), a.shape[1], cm.ptr(b), b.shape[1], C.byref(sse))
+            got = mo.variance(a[:, :w], b[:, :w])
+            assert got == (want, sse.value), (w, h, kind)
+    lib.svt_aom_mse16x16_c.restype = C.c_uint32
+    a, b = rng.integers(0, 256, (16, 16)).astype(np.uint8), rng.integers(0, 256, (16, 16)).astype(np.uint8)
+    sse = C.c_uint32(0)
+    assert mo.variance(a, b) == (lib.svt_aom_mse16x16_c(cm.ptr(a), 16, cm.ptr(b), 16, C.byref(sse)), sse.value)
+
+
+@needs_ref
+@pytest.mark.parametrize("search", [1, 2, 3])
+def test_upsampled_pred_matches_reference(search):
+    lib = cm.ref()
+    rng = np.random.default_rng(20 + search)
+    for (w, h) in [(4, 4), (8, 8), (16, 32), (64, 64), (128, 128), (32, 8)]:
+        ref = rng.integers(0, 256, (h + 16, w + 16)).astype(np.uint8)
+        for sx in range(8):
+            for sy in (0, 3, 7) if sx % 2 else (0, 1, 4):
+                a, b = np.zeros((h, w), np.uint8), np.ones((h, w), np.uint8)
+                r0 = C.c_void_p(ref.ctypes.data + 8 * ref.shape[1] + 8)
+                cm.oracle().orc_upsampled_pred(cm.ptr(a), w, h, sx, sy, r0, ref.shape[1], search)
+                lib.svt_aom_upsampled_pred_c(None, None, 0, 0, None, cm.ptr(b), w, h, sx, sy, r0, ref.shape[1], search)
+                np.testing.assert_array_equal(a, b, f"{w}x{h} {sx},{sy}")

@@ -74,3 +74,38 @@ def test_subpel_search_small_block_launches(mx):
     got = run_gpu(p, tabs, src, refs, jobs, max_block=(mx, mx))
     for f in ("mv_row", "mv_col", "besterr", "distortion", "sse"):
         np.testing.assert_array_equal(got[f], want[f], f)
+
+
+def test_variance_and_mse_dropins():
+    import misc_oracle as mo
+    from test_oracle_subpel import VAR_SIZES
+    lib = sb.load()
+    rng = np.random.default_rng(18)
+    for (w, h) in VAR_SIZES:
+        fn = getattr(lib, f"svt_aom_variance{w}x{h}_cuda")
+        fn.restype = C.c_uint32
+        for kind in ("rand", "extreme"):
+            a = rng.integers(0, 256, (h, w + 7)).astype(np.uint8) if kind == "rand" else np.full((h, w + 7), 255, np.uint8)
+            b = rng.integers(0, 256, (h, w + 3)).astype(np.uint8) if kind == "rand" else np.zeros((h, w + 3), np.uint8)
+            sse = C.c_uint32(0)
+            got = fn(cm.ptr(a), a.shape[1], cm.ptr(b), b.shape[1], C.byref(sse))
+            assert (got, sse.value) == mo.variance(a[:, :w], b[:, :w]), (w, h, kind)
+    lib.svt_aom_mse16x16_cuda.restype = C.c_uint32
+    a, b = rng.integers(0, 256, (16, 20)).astype(np.uint8), rng.integers(0, 256, (16, 16)).astype(np.uint8)
+    sse = C.c_uint32(0)
+    got = lib.svt_aom_mse16x16_cuda(cm.ptr(a), 20, cm.ptr(b), 16, C.byref(sse))
+    assert (got, sse.value) == mo.variance(a[:, :16], b)
+
+
+@pytest.mark.parametrize("search", [1, 2, 3])
+def test_upsampled_pred_dropin(search):
+    lib = sb.load()
+    rng = np.random.default_rng(30 + search)
+    for (w, h) in [(4, 4), (8, 8), (16, 32), (64, 64), (128, 128), (32, 8)]:
+        ref = rng.integers(0, 256, (h + 16, w + 16)).astype(np.uint8)
+        for sx, sy in ((0, 0), (3, 0), (0, 5), (1, 1), (7, 4), (4, 7)):
+            want, got = np.zeros((h, w), np.uint8), np.ones((h, w), np.uint8)
+            r0 = C.c_void_p(ref.ctypes.data + 8 * ref.shape[1] + 8)
+            cm.oracle().orc_upsampled_pred(cm.ptr(want), w, h, sx, sy, r0, ref.shape[1], search)
+            lib.svt_aom_upsampled_pred_cuda(None, None, 0, 0, None, cm.ptr(got), w, h, sx, sy, r0, ref.shape[1], search)
+            np.testing.assert_array_equal(got, want, f"{w}x{h} {sx},{sy}")
