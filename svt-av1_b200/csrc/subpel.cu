@@ -165,8 +165,9 @@ __device__ unsigned check_better(const Geo &g, const SvtB200SubpelParams &p, con
                                  int &is_better, int *s_red) {
     if (mv.col < j.col_min || mv.col > j.col_max || mv.row < j.row_min || mv.row > j.row_max) return 0x7fffffffu; // INT_MAX
     unsigned sse;
+    const unsigned rate = (unsigned)mv_err_cost(p, j, mv); // issued first: the two table reads overlap the filtering
     const int thismse = (int)eval_error<SP_NT>(g, p, start, mv, &sse, s_red);
-    const unsigned cost = (unsigned)mv_err_cost(p, j, mv) + (unsigned)thismse;
+    const unsigned cost = rate + (unsigned)thismse;
     if (cost < b.besterr) {
         b.besterr = cost;
         b.mv = mv;
@@ -216,9 +217,10 @@ __global__ void __launch_bounds__(SP_NT) subpel_kernel(const __grid_constant__ S
     const int round = min(3 - p.forced_stop, 3 - (p.allow_hp ? 0 : 1));
     Best b;
     b.mv = start;
+    const unsigned rate0 = (unsigned)mv_err_cost(p, j, start);
     b.besterr = eval_error<SP_NT>(g, p, start, start, &b.sse, s_red);
     b.distortion = (int)b.besterr;
-    b.besterr += (unsigned)mv_err_cost(p, j, start);
+    b.besterr += rate0;
     int hstep = 4;
     for (int iter = 0; iter < round; iter++) {
         const Mv2 ctr = b.mv;
