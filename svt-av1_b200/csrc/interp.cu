@@ -8,11 +8,13 @@
 //   into whole-sample position + 1/16 phase, dispatch on (phase_x != 0, phase_y != 0, compound), and for compound blocks
 //   the second reference averaged (plain or distance weighted) into the first without the CONV_BUF round trip.
 //
-// Work decomposition: one warp filters one tile of <= 16x16 output samples. The (tw+7)x(th+7) source window is staged
-// once in shared memory (16-bit), the horizontal pass writes the int16 intermediate the reference keeps in im_block,
-// the vertical pass produces 8 outputs per lane. The sixteen reference functions differ only in which pass runs and in
-// the rounding, so all of them are one device routine (conv_tile) + one finishing step.
-// Bound: HBM/L2 traffic (read ~(1 + 7/16)^2 x, write 1 x per sample; ~20 multiply-adds per sample).
+// Work decomposition: a HALF warp filters one tile of <= 16x8 output samples (two unrelated tiles per warp). Lane r reads
+// row r of the (th+7)x(tw+7) source window into registers (aligned 32-bit loads + funnel shifts) and runs the horizontal
+// pass there (dp4a / dp2a on the AV1 kernels halved into int8), leaving the int16 intermediate the reference keeps in
+// im_block in shared memory; then each lane slides the vertical 8 taps down a column strip of <= 8 rows. The sixteen
+// reference functions differ only in which pass runs and in the rounding, so all of them are one device routine
+// (conv_tile) + one finishing step. Bound: instruction issue (per-tile set-up is comparable to the filtering for small
+// blocks); HBM traffic is ~(1 + n_refs) B per predicted sample.
 #include <algorithm>
 #include <mutex>
 
