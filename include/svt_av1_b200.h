@@ -314,17 +314,18 @@ SVT_B200_API void svt_residual_kernel16bit_cuda(uint16_t *input, uint32_t input_
                                                 uint32_t area_height);
 
 /* replace svt_av1_fwd_txfm2d_{WxH} (aom_dsp_rtcd.h:105-216; C impl EbTransforms.c:2301-3053).
- * tx_type is the reference's TxType enum value (DCT_DCT=0 ... H_FLIPADST=15). */
+ * tx_type is the reference's TxType (a 1-byte packed enum, DCT_DCT=0 ... H_FLIPADST=15): uint8_t keeps the by-value
+ * argument ABI identical; likewise TxSize below. */
 #define SVT_B200_DECL_FWD(W, H)                                                                      \
     SVT_B200_API void svt_av1_fwd_txfm2d_##W##x##H##_cuda(int16_t *input, int32_t *output,           \
-                                                          uint32_t input_stride, int32_t tx_type,    \
+                                                          uint32_t input_stride, uint8_t tx_type,    \
                                                           uint8_t bit_depth);                        \
     /* partial-frequency shapes svt_av1_fwd_txfm2d_WxH_N2 / _N4 (aom_dsp_rtcd.h:150-216) */           \
     SVT_B200_API void svt_av1_fwd_txfm2d_##W##x##H##_N2_cuda(int16_t *input, int32_t *output,        \
-                                                             uint32_t input_stride, int32_t tx_type, \
+                                                             uint32_t input_stride, uint8_t tx_type, \
                                                              uint8_t bit_depth);                     \
     SVT_B200_API void svt_av1_fwd_txfm2d_##W##x##H##_N4_cuda(int16_t *input, int32_t *output,        \
-                                                             uint32_t input_stride, int32_t tx_type, \
+                                                             uint32_t input_stride, uint8_t tx_type, \
                                                              uint8_t bit_depth);
 SVT_B200_DECL_FWD(4, 4) SVT_B200_DECL_FWD(8, 8) SVT_B200_DECL_FWD(16, 16) SVT_B200_DECL_FWD(32, 32)
 SVT_B200_DECL_FWD(64, 64) SVT_B200_DECL_FWD(4, 8) SVT_B200_DECL_FWD(8, 4) SVT_B200_DECL_FWD(8, 16)
@@ -345,15 +346,15 @@ SVT_B200_API uint64_t svt_b200_handle_transform64(int32_t *output, int tx_size);
 #define SVT_B200_DECL_INV_SQ(W)                                                                        \
     SVT_B200_API void svt_av1_inv_txfm2d_add_##W##x##W##_cuda(                                         \
         const int32_t *input, uint16_t *output_r, int32_t stride_r, uint16_t *output_w, int32_t stride_w, \
-        int32_t tx_type, int32_t bd);
+        uint8_t tx_type, int32_t bd);
 #define SVT_B200_DECL_INV_RECT(W, H)                                                                   \
     SVT_B200_API void svt_av1_inv_txfm2d_add_##W##x##H##_cuda(                                         \
         const int32_t *input, uint16_t *output_r, int32_t stride_r, uint16_t *output_w, int32_t stride_w, \
-        int32_t tx_type, int32_t tx_size, int32_t eob, int32_t bd);
+        uint8_t tx_type, uint8_t tx_size, int32_t eob, int32_t bd);
 #define SVT_B200_DECL_INV_RECT_NOEOB(W, H)                                                             \
     SVT_B200_API void svt_av1_inv_txfm2d_add_##W##x##H##_cuda(                                         \
         const int32_t *input, uint16_t *output_r, int32_t stride_r, uint16_t *output_w, int32_t stride_w, \
-        int32_t tx_type, int32_t tx_size, int32_t bd);
+        uint8_t tx_type, uint8_t tx_size, int32_t bd);
 SVT_B200_DECL_INV_SQ(4) SVT_B200_DECL_INV_SQ(8) SVT_B200_DECL_INV_SQ(16) SVT_B200_DECL_INV_SQ(32)
 SVT_B200_DECL_INV_SQ(64) SVT_B200_DECL_INV_RECT_NOEOB(4, 8) SVT_B200_DECL_INV_RECT_NOEOB(8, 4)
 SVT_B200_DECL_INV_RECT(8, 16) SVT_B200_DECL_INV_RECT(16, 8) SVT_B200_DECL_INV_RECT(16, 32)

@@ -650,18 +650,18 @@ extern "C" {
 
 // --- forward transforms: one exported symbol per RTCD pointer (aom_dsp_rtcd.h:105-216) ---
 #define FWD_DROPIN(W, H, TXS)                                                                                     \
-    void svt_av1_fwd_txfm2d_##W##x##H##_cuda(int16_t *input, int32_t *output, uint32_t input_stride, int32_t tx_type, \
+    void svt_av1_fwd_txfm2d_##W##x##H##_cuda(int16_t *input, int32_t *output, uint32_t input_stride, uint8_t tx_type, \
                                              uint8_t bit_depth) {                                                 \
         (void)bit_depth;                                                                                          \
         fwd_dropin(input, output, input_stride, tx_type, TXS, 0, nullptr);                                        \
     }                                                                                                             \
     void svt_av1_fwd_txfm2d_##W##x##H##_N2_cuda(int16_t *input, int32_t *output, uint32_t input_stride,           \
-                                                int32_t tx_type, uint8_t bit_depth) {                             \
+                                                uint8_t tx_type, uint8_t bit_depth) {                             \
         (void)bit_depth;                                                                                          \
         fwd_dropin(input, output, input_stride, tx_type, TXS, 0, nullptr, 1);                                     \
     }                                                                                                             \
     void svt_av1_fwd_txfm2d_##W##x##H##_N4_cuda(int16_t *input, int32_t *output, uint32_t input_stride,           \
-                                                int32_t tx_type, uint8_t bit_depth) {                             \
+                                                uint8_t tx_type, uint8_t bit_depth) {                             \
         (void)bit_depth;                                                                                          \
         fwd_dropin(input, output, input_stride, tx_type, TXS, 0, nullptr, 2);                                     \
     }
@@ -688,21 +688,21 @@ FWD_DROPIN(64, 16, 18)
 // --- inverse transforms (common_dsp_rtcd.h:105-156); rectangular ones carry tx_size (+eob) like the reference ---
 #define INV_SQ(W, TXS)                                                                                            \
     void svt_av1_inv_txfm2d_add_##W##x##W##_cuda(const int32_t *input, uint16_t *output_r, int32_t stride_r,      \
-                                                 uint16_t *output_w, int32_t stride_w, int32_t tx_type, int32_t bd) { \
+                                                 uint16_t *output_w, int32_t stride_w, uint8_t tx_type, int32_t bd) { \
         inv_dropin(input, output_r, stride_r, output_w, stride_w, tx_type, TXS, bd);                              \
     }
 #define INV_RECT(W, H, TXS)                                                                                       \
     void svt_av1_inv_txfm2d_add_##W##x##H##_cuda(const int32_t *input, uint16_t *output_r, int32_t stride_r,      \
-                                                 uint16_t *output_w, int32_t stride_w, int32_t tx_type,           \
-                                                 int32_t tx_size, int32_t eob, int32_t bd) {                      \
+                                                 uint16_t *output_w, int32_t stride_w, uint8_t tx_type,           \
+                                                 uint8_t tx_size, int32_t eob, int32_t bd) {                      \
         (void)tx_size;                                                                                            \
         (void)eob;                                                                                                \
         inv_dropin(input, output_r, stride_r, output_w, stride_w, tx_type, TXS, bd);                              \
     }
 #define INV_RECT_NOEOB(W, H, TXS)                                                                                 \
     void svt_av1_inv_txfm2d_add_##W##x##H##_cuda(const int32_t *input, uint16_t *output_r, int32_t stride_r,      \
-                                                 uint16_t *output_w, int32_t stride_w, int32_t tx_type,           \
-                                                 int32_t tx_size, int32_t bd) {                                   \
+                                                 uint16_t *output_w, int32_t stride_w, uint8_t tx_type,           \
+                                                 uint8_t tx_size, int32_t bd) {                                   \
         (void)tx_size;                                                                                            \
         inv_dropin(input, output_r, stride_r, output_w, stride_w, tx_type, TXS, bd);                              \
     }
