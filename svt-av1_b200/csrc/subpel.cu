@@ -81,11 +81,9 @@ struct Mv2 {
     int row, col;
 };
 
-// svt_upsampled_pref_error for one candidate, by the whole CTA: {variance, sum of squares}
-// (one out-of-line copy: the tree search calls it from nine places, and inlining them all overflows the instruction cache —
-// ncu showed `no_instruction` as the top stall)
+// svt_upsampled_pref_error for one candidate, by the whole CTA; returns the variance, *sse_out the sum of squares
 template <int SP_NT>
-__device__ __noinline__ uint2 eval_error(const Geo g, const SvtB200SubpelParams &p, Mv2 start, Mv2 mv, int *s_red) { // {variance, sse}
+__device__ unsigned eval_error(const Geo &g, const SvtB200SubpelParams &p, Mv2 start, Mv2 mv, unsigned *sse_out, int *s_red) {
     const int drow = (mv.row >> 3) - (start.row >> 3), dcol = (mv.col >> 3) - (start.col >> 3); // -REACH .. REACH - 1
     const uint2 tx = sub_taps(p.subpel_search_type, mv.col & 7), ty = sub_taps(p.subpel_search_type, mv.row & 7);
     const int c0 = dcol + REACH; // byte offset of tap 0 of output column 0 in a window row (0..3)
@@ -138,7 +136,8 @@ __device__ __noinline__ uint2 eval_error(const Geo g, const SvtB200SubpelParams 
         sse += (unsigned)s_red[2 * wq + 1];
     }
     __syncthreads(); // s_red and tmp are free again
-    return make_uint2(sse - (unsigned)(((long long)sum * sum) / (g.w * g.h)), sse);
+    *sse_out = sse;
+    return sse - (unsigned)(((long long)sum * sum) / (g.w * g.h));
 }
 
 __device__ int mv_err_cost(const SvtB200SubpelParams &p, const SvtB200SubpelJob &j, Mv2 mv) {
@@ -165,10 +164,9 @@ template <int SP_NT>
 __device__ unsigned check_better(const Geo &g, const SvtB200SubpelParams &p, const SvtB200SubpelJob &j, Mv2 start, Mv2 mv, Best &b,
                                  int &is_better, int *s_red) {
     if (mv.col < j.col_min || mv.col > j.col_max || mv.row < j.row_min || mv.row > j.row_max) return 0x7fffffffu; // INT_MAX
+    unsigned sse;
     const unsigned rate = (unsigned)mv_err_cost(p, j, mv); // issued first: the two table reads overlap the filtering
-    const uint2 ev = eval_error<SP_NT>(g, p, start, mv, s_red);
-    const int thismse = (int)ev.x;
-    const unsigned sse = ev.y;
+    const int thismse = (int)eval_error<SP_NT>(g, p, start, mv, &sse, s_red);
     const unsigned cost = rate + (unsigned)thismse;
     if (cost < b.besterr) {
         b.besterr = cost;
@@ -220,8 +218,7 @@ __global__ void __launch_bounds__(SP_NT) subpel_kernel(const __grid_constant__ S
     Best b;
     b.mv = start;
     const unsigned rate0 = (unsigned)mv_err_cost(p, j, start);
-    const uint2 ev0 = eval_error<SP_NT>(g, p, start, start, s_red);
-    b.besterr = ev0.x, b.sse = ev0.y;
+    b.besterr = eval_error<SP_NT>(g, p, start, start, &b.sse, s_red);
     b.distortion = (int)b.besterr;
     b.besterr += rate0;
     int hstep = 4;
