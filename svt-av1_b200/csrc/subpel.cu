@@ -6,7 +6,8 @@
 //   svt_mv_err_cost :44, svt_aom_upsampled_pred_c (Encoder/C_DEFAULT/variance.c:212-269: two passes of
 //   svt_aom_convolve8_horiz/vert, each rounded and clipped to 8 bits), svt_aom_varianceWxH_c (EbComputeVariance_C.c:14-61).
 //
-// One CTA per job. The search never leaves start_mv +- 14/8 sample (each of the three rounds moves at most twice its
+// One CTA per job; the candidates of a round that do not depend on each other are filtered as one batch (eval_batch).
+// The search never leaves start_mv +- 14/8 sample (each of the three rounds moves at most twice its
 // step per axis), so the (h + 10) x (w + 10) reference window and the source block are staged in shared memory ONCE and
 // every one of the <= 25 candidate evaluations runs out of shared memory:
 //   pass 1  (row, 4 columns) per thread: 4 aligned LDS.32, funnel-shift realignment, 2 dp4a per output with the AV1
@@ -81,63 +82,88 @@ struct Mv2 {
     int row, col;
 };
 
-// svt_upsampled_pref_error for one candidate, by the whole CTA; returns the variance, *sse_out the sum of squares
-template <int SP_NT>
-__device__ unsigned eval_error(const Geo &g, const SvtB200SubpelParams &p, Mv2 start, Mv2 mv, unsigned *sse_out, int *s_red) {
-    const int drow = (mv.row >> 3) - (start.row >> 3), dcol = (mv.col >> 3) - (start.col >> 3); // -REACH .. REACH - 1
-    const uint2 tx = sub_taps(p.subpel_search_type, mv.col & 7), ty = sub_taps(p.subpel_search_type, mv.row & 7);
-    const int c0 = dcol + REACH; // byte offset of tap 0 of output column 0 in a window row (0..3)
-    const int r0 = drow + REACH; // window row of tap 0 of output row 0
+constexpr int MAX_BATCH = 4; // candidates evaluated between two barriers (left, right, up, down of a round)
+
+// svt_upsampled_pref_error for up to N candidates at once, by the whole CTA: the candidates of a round are independent of
+// each other (they depend on the round's centre only), so their first passes run back to back into N intermediate
+// buffers, one barrier, then their second passes, ONE reduction of the 2 N sums — 3 barriers per batch instead of 3 per
+// candidate. out[c] = {variance, sum of squares}; inactive candidates (outside the MV limits) are skipped.
+template <int SP_NT, int N>
+__device__ __forceinline__ void eval_batch(const Geo &g, const SvtB200SubpelParams &p, Mv2 start, const Mv2 (&mv)[N], const bool (&act)[N],
+                                           uint2 (&out)[N], int *s_red) {
     const int ngx = g.w >> 2;
+    const int tmp_bytes = g.w * g.tp;
     // pass 1: rows 0 .. h + 6 (3 above, 4 below the block), 4 columns per thread, transposed 8-bit output
-    for (int it = threadIdx.x; it < (g.h + 7) * ngx; it += SP_NT) {
-        const int xg = (int)__umulhi((uint32_t)it, g.inv_h7), r = it - xg * (g.h + 7); // r fastest: the transposed stores of a warp are contiguous
-        const uint32_t *wr = reinterpret_cast<const uint32_t *>(g.win + (r0 + r) * g.wp) + xg;
-        const uint32_t a0 = wr[0], a1 = wr[1], a2 = wr[2], a3 = wr[3];
-        const uint32_t W0 = __funnelshift_r(a0, a1, 8 * c0), W1 = __funnelshift_r(a1, a2, 8 * c0), W2 = __funnelshift_r(a2, a3, 8 * c0);
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const uint32_t q0 = e ? __funnelshift_r(W0, W1, 8 * e) : W0, q1 = e ? __funnelshift_r(W1, W2, 8 * e) : W1;
-            const int s = dp4a_us(q1, tx.y, dp4a_us(q0, tx.x, 0));
-            g.tmp[(4 * xg + e) * g.tp + r] = (uint8_t)clip8((s + 32) >> 6);
+    for (int c = 0; c < N; c++) {
+        if (!act[c]) continue;
+        const int drow = (mv[c].row >> 3) - (start.row >> 3), dcol = (mv[c].col >> 3) - (start.col >> 3); // -REACH .. REACH - 1
+        const uint2 tx = sub_taps(p.subpel_search_type, mv[c].col & 7);
+        const int c0 = dcol + REACH; // byte offset of tap 0 of output column 0 in a window row (0..3)
+        const int r0 = drow + REACH; // window row of tap 0 of output row 0
+        uint8_t *tmp = g.tmp + c * tmp_bytes;
+        for (int it = threadIdx.x; it < (g.h + 7) * ngx; it += SP_NT) {
+            const int xg = (int)__umulhi((uint32_t)it, g.inv_h7), r = it - xg * (g.h + 7); // r fastest: contiguous transposed stores
+            const uint32_t *wr = reinterpret_cast<const uint32_t *>(g.win + (r0 + r) * g.wp) + xg;
+            const uint32_t a0 = wr[0], a1 = wr[1], a2 = wr[2], a3 = wr[3];
+            const uint32_t W0 = __funnelshift_r(a0, a1, 8 * c0), W1 = __funnelshift_r(a1, a2, 8 * c0), W2 = __funnelshift_r(a2, a3, 8 * c0);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const uint32_t q0 = e ? __funnelshift_r(W0, W1, 8 * e) : W0, q1 = e ? __funnelshift_r(W1, W2, 8 * e) : W1;
+                const int s = dp4a_us(q1, tx.y, dp4a_us(q0, tx.x, 0));
+                tmp[(4 * xg + e) * g.tp + r] = (uint8_t)clip8((s + 32) >> 6);
+            }
         }
     }
     __syncthreads();
     // pass 2 + the variance terms: column x, rows 4 yg .. 4 yg + 3
-    int sum = 0;
-    unsigned sse = 0;
-    for (int it = threadIdx.x; it < g.w * (g.h >> 2); it += SP_NT) {
-        const int yg = (int)__umulhi((uint32_t)it, g.inv_w), x = it - yg * g.w;
-        const uint32_t *tc = reinterpret_cast<const uint32_t *>(g.tmp + x * g.tp) + yg;
-        const uint32_t W0 = tc[0], W1 = tc[1], W2 = tc[2];
+    int sum[N];
+    unsigned sse[N];
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const uint32_t q0 = e ? __funnelshift_r(W0, W1, 8 * e) : W0, q1 = e ? __funnelshift_r(W1, W2, 8 * e) : W1;
-            const int pr = clip8((dp4a_us(q1, ty.y, dp4a_us(q0, ty.x, 0)) + 32) >> 6);
-            const int diff = pr - (int)g.src[(4 * yg + e) * g.w + x];
-            sum += diff;
-            sse += (unsigned)(diff * diff);
+    for (int c = 0; c < N; c++) {
+        sum[c] = 0, sse[c] = 0;
+        if (!act[c]) continue;
+        const uint2 ty = sub_taps(p.subpel_search_type, mv[c].row & 7);
+        const uint8_t *tmp = g.tmp + c * tmp_bytes;
+        for (int it = threadIdx.x; it < g.w * (g.h >> 2); it += SP_NT) {
+            const int yg = (int)__umulhi((uint32_t)it, g.inv_w), x = it - yg * g.w;
+            const uint32_t *tc = reinterpret_cast<const uint32_t *>(tmp + x * g.tp) + yg;
+            const uint32_t W0 = tc[0], W1 = tc[1], W2 = tc[2];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const uint32_t q0 = e ? __funnelshift_r(W0, W1, 8 * e) : W0, q1 = e ? __funnelshift_r(W1, W2, 8 * e) : W1;
+                const int pr = clip8((dp4a_us(q1, ty.y, dp4a_us(q0, ty.x, 0)) + 32) >> 6);
+                const int diff = pr - (int)g.src[(4 * yg + e) * g.w + x];
+                sum[c] += diff;
+                sse[c] += (unsigned)(diff * diff);
+            }
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        sse += __shfl_xor_sync(0xffffffffu, sse, o);
-    }
-    if ((threadIdx.x & 31) == 0) {
-        s_red[(threadIdx.x >> 5) * 2] = sum;
-        s_red[(threadIdx.x >> 5) * 2 + 1] = (int)sse;
+    for (int c = 0; c < N; c++) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sum[c] += __shfl_xor_sync(0xffffffffu, sum[c], o);
+            sse[c] += __shfl_xor_sync(0xffffffffu, sse[c], o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            s_red[((threadIdx.x >> 5) * MAX_BATCH + c) * 2] = sum[c];
+            s_red[((threadIdx.x >> 5) * MAX_BATCH + c) * 2 + 1] = (int)sse[c];
+        }
     }
     __syncthreads();
-    sum = 0, sse = 0;
 #pragma unroll
-    for (int wq = 0; wq < SP_NT / 32; wq++) {
-        sum += s_red[2 * wq];
-        sse += (unsigned)s_red[2 * wq + 1];
+    for (int c = 0; c < N; c++) {
+        int sm = 0;
+        unsigned sq = 0;
+#pragma unroll
+        for (int wq = 0; wq < SP_NT / 32; wq++) {
+            sm += s_red[(wq * MAX_BATCH + c) * 2];
+            sq += (unsigned)s_red[(wq * MAX_BATCH + c) * 2 + 1];
+        }
+        out[c] = make_uint2(sq - (unsigned)(((long long)sm * sm) / (g.w * g.h)), sq);
     }
-    __syncthreads(); // s_red and tmp are free again
-    *sse_out = sse;
-    return sse - (unsigned)(((long long)sum * sum) / (g.w * g.h));
+    __syncthreads(); // s_red and the intermediates are free again
 }
 
 __device__ int mv_err_cost(const SvtB200SubpelParams &p, const SvtB200SubpelJob &j, Mv2 mv) {
@@ -160,28 +186,46 @@ struct Best {
     int distortion;
 };
 
-template <int SP_NT>
-__device__ unsigned check_better(const Geo &g, const SvtB200SubpelParams &p, const SvtB200SubpelJob &j, Mv2 start, Mv2 mv, Best &b,
-                                 int &is_better, int *s_red) {
-    if (mv.col < j.col_min || mv.col > j.col_max || mv.row < j.row_min || mv.row > j.row_max) return 0x7fffffffu; // INT_MAX
-    unsigned sse;
-    const unsigned rate = (unsigned)mv_err_cost(p, j, mv); // issued first: the two table reads overlap the filtering
-    const int thismse = (int)eval_error<SP_NT>(g, p, start, mv, &sse, s_red);
-    const unsigned cost = rate + (unsigned)thismse;
-    if (cost < b.besterr) {
-        b.besterr = cost;
-        b.mv = mv;
-        b.distortion = thismse;
-        b.sse = sse;
-        is_better |= 1;
+__device__ __forceinline__ bool in_limits(const SvtB200SubpelJob &j, Mv2 mv) { // svt_av1_is_subpelmv_in_range
+    return mv.col >= j.col_min && mv.col <= j.col_max && mv.row >= j.row_min && mv.row <= j.row_max;
+}
+
+// svt_check_better for N candidates whose errors do not depend on each other: evaluated together, then the reference's
+// updates of (besterr, best_mv, distortion, sse) applied in its order. cost[c] = what svt_check_better returns.
+template <int SP_NT, int N>
+__device__ __forceinline__ void check_better_batch(const Geo &g, const SvtB200SubpelParams &p, const SvtB200SubpelJob &j, Mv2 start,
+                                                   const Mv2 (&mv)[N], Best &b, int &is_better, unsigned (&cost)[N], int *s_red) {
+    bool act[N];
+    unsigned rate[N];
+    uint2 ev[N];
+#pragma unroll
+    for (int c = 0; c < N; c++) {
+        act[c] = in_limits(j, mv[c]);
+        rate[c] = act[c] ? (unsigned)mv_err_cost(p, j, mv[c]) : 0u; // issued first: the table reads overlap the filtering
     }
-    return cost;
+    eval_batch<SP_NT, N>(g, p, start, mv, act, ev, s_red);
+#pragma unroll
+    for (int c = 0; c < N; c++) {
+        if (!act[c]) {
+            cost[c] = 0x7fffffffu; // INT_MAX
+            continue;
+        }
+        const int thismse = (int)ev[c].x;
+        cost[c] = rate[c] + (unsigned)thismse;
+        if (cost[c] < b.besterr) {
+            b.besterr = cost[c];
+            b.mv = mv[c];
+            b.distortion = thismse;
+            b.sse = ev[c].y;
+            is_better |= 1;
+        }
+    }
 }
 
 template <int SP_NT>
 __global__ void __launch_bounds__(SP_NT) subpel_kernel(const __grid_constant__ SubpelDev d) {
     extern __shared__ __align__(16) uint8_t smem[];
-    __shared__ int s_red[2 * SP_NT_MAX / 32];
+    __shared__ int s_red[2 * MAX_BATCH * SP_NT_MAX / 32];
     const SvtB200SubpelJob j = d.jobs[blockIdx.x];
     const SvtB200SubpelParams &p = d.p;
     if (j.bw > d.max_w || j.bh > d.max_h || j.bw < 4 || j.bh < 4 || ((j.bw | j.bh) & 3)) { // does not fit the window of this launch
@@ -196,7 +240,7 @@ __global__ void __launch_bounds__(SP_NT) subpel_kernel(const __grid_constant__ S
     g.inv_w = (uint32_t)(((1ull << 32) + g.w - 1) / (uint32_t)g.w);
     g.win = smem;
     g.tmp = g.win + (g.h + 2 * REACH + 7) * g.wp;
-    g.src = g.tmp + g.w * g.tp;
+    g.src = g.tmp + MAX_BATCH * g.w * g.tp;
     const Mv2 start{j.start_mv_row, j.start_mv_col};
     // stage the window (rows / columns -REACH - 3 .. of the start position) and the source block
     const uint8_t *ref = d.ref[j.ref & 7] + (ptrdiff_t)(j.blk_y + (start.row >> 3) - REACH - 3) * d.ref_stride[j.ref & 7] + j.blk_x +
@@ -217,30 +261,39 @@ __global__ void __launch_bounds__(SP_NT) subpel_kernel(const __grid_constant__ S
     const int round = min(3 - p.forced_stop, 3 - (p.allow_hp ? 0 : 1));
     Best b;
     b.mv = start;
-    const unsigned rate0 = (unsigned)mv_err_cost(p, j, start);
-    b.besterr = eval_error<SP_NT>(g, p, start, start, &b.sse, s_red);
-    b.distortion = (int)b.besterr;
-    b.besterr += rate0;
+    {
+        const unsigned rate0 = (unsigned)mv_err_cost(p, j, start);
+        const Mv2 m1[1] = {start};
+        const bool a1[1] = {true};
+        uint2 e1[1];
+        eval_batch<SP_NT, 1>(g, p, start, m1, a1, e1, s_red);
+        b.besterr = e1[0].x, b.sse = e1[0].y;
+        b.distortion = (int)b.besterr;
+        b.besterr += rate0;
+    }
     int hstep = 4;
     for (int iter = 0; iter < round; iter++) {
         const Mv2 ctr = b.mv;
         int dummy = 0;
-        const unsigned left = check_better<SP_NT>(g, p, j, start, Mv2{ctr.row, ctr.col - hstep}, b, dummy, s_red);
-        const unsigned right = check_better<SP_NT>(g, p, j, start, Mv2{ctr.row, ctr.col + hstep}, b, dummy, s_red);
-        const unsigned up = check_better<SP_NT>(g, p, j, start, Mv2{ctr.row - hstep, ctr.col}, b, dummy, s_red);
-        const unsigned down = check_better<SP_NT>(g, p, j, start, Mv2{ctr.row + hstep, ctr.col}, b, dummy, s_red);
-        Mv2 diag{up <= down ? -hstep : hstep, left <= right ? -hstep : hstep};
-        check_better<SP_NT>(g, p, j, start, Mv2{ctr.row + diag.row, ctr.col + diag.col}, b, dummy, s_red);
+        // svt_first_level_check: left, right, up, down (one batch), then the diagonal they point to
+        const Mv2 m4[4] = {{ctr.row, ctr.col - hstep}, {ctr.row, ctr.col + hstep}, {ctr.row - hstep, ctr.col}, {ctr.row + hstep, ctr.col}};
+        unsigned c4[4];
+        check_better_batch<SP_NT, 4>(g, p, j, start, m4, b, dummy, c4, s_red);
+        Mv2 diag{c4[2] <= c4[3] ? -hstep : hstep, c4[0] <= c4[1] ? -hstep : hstep};
+        const Mv2 md[1] = {{ctr.row + diag.row, ctr.col + diag.col}};
+        unsigned cd[1];
+        check_better_batch<SP_NT, 1>(g, p, j, start, md, b, dummy, cd, s_red);
         if (!(ctr.row == b.mv.row && ctr.col == b.mv.col) && p.iters_per_step > 1) { // svt_second_level_check_v2
             if (ctr.row == b.mv.row)
                 diag.row = -diag.row;
             else if (ctr.col == b.mv.col)
                 diag.col = -diag.col;
-            const Mv2 rb{b.mv.row + diag.row, b.mv.col}, cb{b.mv.row, b.mv.col + diag.col}, db{b.mv.row + diag.row, b.mv.col + diag.col};
+            const Mv2 m2[2] = {{b.mv.row + diag.row, b.mv.col}, {b.mv.row, b.mv.col + diag.col}};
+            const Mv2 mb[1] = {{b.mv.row + diag.row, b.mv.col + diag.col}};
             int has_better = 0;
-            check_better<SP_NT>(g, p, j, start, rb, b, has_better, s_red);
-            check_better<SP_NT>(g, p, j, start, cb, b, has_better, s_red);
-            if (has_better) check_better<SP_NT>(g, p, j, start, db, b, has_better, s_red);
+            unsigned c2[2];
+            check_better_batch<SP_NT, 2>(g, p, j, start, m2, b, has_better, c2, s_red);
+            if (has_better) check_better_batch<SP_NT, 1>(g, p, j, start, mb, b, has_better, cd, s_red);
         }
         hstep >>= 1;
     }
@@ -254,7 +307,7 @@ __global__ void __launch_bounds__(SP_NT) subpel_kernel(const __grid_constant__ S
 
 size_t smem_bytes(int w, int h) {
     const int wp = ((w + 2 * REACH + 7 + 4 + 3) & ~3) | 4, tp = ((h + 8 + 3) & ~3) | 4;
-    return (size_t)(h + 2 * REACH + 7) * wp + (size_t)w * tp + (size_t)w * h + 16;
+    return (size_t)(h + 2 * REACH + 7) * wp + (size_t)MAX_BATCH * w * tp + (size_t)w * h + 16;
 }
 
 } // namespace
