@@ -156,8 +156,49 @@ def case_downsample(which):
     return out
 
 
+def case_pick_filter_level(which):
+    from test_dlf_gpu import flat_mi
+    from test_oracle_dlf import PICK_CASES, pick_case, pick_params, run_ref_pick
+    out = []
+    for (w, h, bd, seed, method, mode, last, only4, deltas) in PICK_CASES[:4]:
+        mi_rows, mi_cols, part, src, rec = pick_case(w, h, bd, seed)
+        if which == "ref":
+            lv, _ = run_ref_pick(mi_rows, mi_cols, part, src, rec, method, mode, last, only4, deltas=deltas)
+        else:
+            flat = flat_mi(mi_rows, mi_cols, part, last)
+            p = pick_params(mi_rows, mi_cols, method, mode, last, only4, deltas=deltas)
+            r, t = rec.copy(), rec.copy()
+            rs, ss, ts = r.struct(), src.struct(), t.struct()
+            got = (C.c_int32 * 4)()
+            cm.oracle().orc_pick_filter_level(C.byref(p), C.byref(rs), C.byref(ss), C.byref(ts), flat, got)
+            lv = list(got)
+        out += [int(x) for x in lv]
+    return np.array(out, np.int32).tobytes()
+
+
+def case_convolve_forms(which):
+    """The eight convolve forms x bd 8 / 10 on one block each (the sixteen reference functions by index)."""
+    import interp_cases as ic
+    from test_oracle_interp import _block, run_oracle_convolve, run_ref_convolve
+    rng = np.random.default_rng(77)
+    out = b""
+    for bd in (8, 10):
+        for form in range(8):
+            sx, sy, comp = form >> 2 & 1, form >> 1 & 1, form & 1
+            r0, r1 = ic.conv_rounds(bd, comp)
+            w, h = 16, 8
+            src = _block(rng, w, h, bd, "rand")
+            conv = rng.integers(0, 1 << (bd + 5), (h, w)).astype(np.uint16)
+            dst = np.zeros((h, w), np.uint16 if bd > 8 else np.uint8)
+            fn = run_ref_convolve if which == "ref" else run_oracle_convolve
+            fn(form, src, w, h, 2, 1, 5 if sx else 0, 11 if sy else 0, bd, r0, r1, comp, 1, 9, 7, conv, dst)
+            out += dst.tobytes() + conv.tobytes()
+    return out
+
+
 CASES = {"me_picture": case_me, "encode_tus": case_encode, "dlf_frame": case_dlf, "cdef_search_apply": case_cdef, "lr_frame": case_lr,
-         "inter_predict": case_inter, "subpel_search": case_subpel, "me_downsample": case_downsample}
+         "inter_predict": case_inter, "subpel_search": case_subpel, "me_downsample": case_downsample,
+         "pick_filter_level": case_pick_filter_level, "convolve_forms": case_convolve_forms}
 
 
 def digest(name, which):
