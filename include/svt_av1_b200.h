@@ -847,6 +847,63 @@ SVT_B200_API int svt_b200_subpel_search(const SvtB200SubpelParams *p, const SvtB
                                         int32_t n_ref_frames, const SvtB200SubpelJob *jobs, int32_t n_jobs,
                                         SvtB200SubpelResult *results, void *stream);
 
+/* =============================================================================================== */
+/* (3) Picture engine: the picture-level entries with HOST buffers, as the reference's process     */
+/*     loops own them (SURVEY.md 8b "Batched entry", "Memory ownership", "Threading").             */
+/*     One engine per encoder handle and GPU.  Every call is synchronous for its caller and        */
+/*     re-entrant: the reference calls from N pipeline threads for N pictures at once.             */
+/* =============================================================================================== */
+typedef struct SvtB200Engine SvtB200Engine;
+
+typedef struct SvtB200EngineStats {
+    uint64_t me_pictures, dlf_frames, cdef_frames;
+    uint64_t me_plane_uploads, me_plane_hits; /* ME plane residency cache: pictures uploaded / found resident */
+    uint64_t h2d_bytes, d2h_bytes, pinned_bytes;
+} SvtB200EngineStats;
+
+/* device: CUDA ordinal (the integration reads SVT_CUDA_DEVICE).  Fails (no CPU fallback) when it does not exist.
+ * Host buffers handed to the engine are page-locked on first use (SVT_B200_PIN_HOST=0 disables) and released in
+ * svt_b200_engine_destroy, which must therefore run before the caller frees them (svt_av1_enc_deinit hook). */
+SVT_B200_API int svt_b200_engine_create(int device, SvtB200Engine **out);
+SVT_B200_API void svt_b200_engine_destroy(SvtB200Engine *e);
+SVT_B200_API int svt_b200_engine_get_stats(SvtB200Engine *e, SvtB200EngineStats *out);
+
+/* The three padded 8-bit luma planes of one picture in HOST memory (EbPaReferenceObject: input_padded_picture_ptr,
+ * quarter_/sixteenth_{filtered,decimated}_picture_ptr; pointers address element (0,0) of the padded buffer_y).
+ * (key, tag) identify the content - the integration passes the EbPaReferenceObject pointer and the picture number -
+ * so a picture uploaded once (as ME source) is found resident when later pictures use it as reference.
+ * quarter / sixteenth may be NULL: they are then derived on the device (svt_b200_me_downsample). */
+typedef struct SvtB200HostMePicture {
+    const void *key;
+    uint64_t tag;
+    const uint8_t *full, *quarter, *sixteenth;
+} SvtB200HostMePicture;
+
+/* Replaces the SB loop of motion_estimation_kernel (EbMotionEstimationProcess.c:831-965) for one picture with host
+ * planes and host results: me_mv [n_sb][85*7][2] int16, me_cand [n_sb][85*23], total_cand [n_sb][85],
+ * rc_me_distortion [n_sb] (layouts of SvtB200MeOutputs).  filtered_downsample: only read when a picture carries no
+ * quarter / sixteenth planes (scs->down_sampling_method_me_search == ME_FILTERED_DOWNSAMPLED). */
+SVT_B200_API int svt_b200_engine_me_picture(SvtB200Engine *e, const SvtB200MeParams *p, const SvtB200HostMePicture *src,
+                                            const SvtB200HostMePicture refs[SVT_B200_ME_LISTS][SVT_B200_ME_MAX_REFS],
+                                            int32_t filtered_downsample, int16_t *me_mv, uint8_t *me_cand,
+                                            uint8_t *total_cand, uint32_t *rc_me_distortion);
+
+/* svt_av1_loop_filter_frame (EbDeblockingFilter.c:711) on a HOST picture, in place; mi: host array. */
+SVT_B200_API int svt_b200_engine_dlf_frame(SvtB200Engine *e, const SvtB200DlfParams *p, const SvtB200Frame *frame,
+                                           const SvtB200DlfMi *mi);
+
+/* The CDEF stage of cdef_kernel (EbCdefProcess.c:510-534) for one HOST picture: strength search of every 64x64 filter
+ * block -> `mse` (host, [2][nfb][64], = pcs->mse_seg) -> `decide(user, mse, apply, fb_strength_idx)` on the calling
+ * thread, where the integration runs the reference's finish_cdef_search (EbEncCdef.c:1167) and fills the frame
+ * strengths (damping, y/uv strength tables) and mbmi.cdef_strength per filter block (preset to -1) -> frame apply,
+ * written back into `recon` (host) in place.  decide returns 1 to apply, 0 to skip the apply (the reference skips it for
+ * non-reference pictures without recon output), < 0 on error.  The reconstruction stays on the device between the
+ * search and the apply. */
+typedef int (*SvtB200CdefDecideFn)(void *user, const uint64_t *mse, SvtB200CdefApplyParams *apply, int8_t *fb_strength_idx);
+SVT_B200_API int svt_b200_engine_cdef_frame(SvtB200Engine *e, const SvtB200CdefSearchParams *sp, const SvtB200Frame *recon,
+                                            const SvtB200Frame *source, const uint8_t *skip8, int32_t skip_stride,
+                                            uint64_t *mse, SvtB200CdefDecideFn decide, void *user);
+
 #ifdef __cplusplus
 }
 #endif
