@@ -859,6 +859,9 @@ typedef struct SvtB200EngineStats {
     uint64_t me_pictures, dlf_frames, cdef_frames;
     uint64_t me_plane_uploads, me_plane_hits; /* ME plane residency cache: pictures uploaded / found resident */
     uint64_t h2d_bytes, d2h_bytes, pinned_bytes;
+    /* wall time summed over calling threads: waiting for a slot, page-locking host buffers, waiting for another
+     * thread's upload of a shared reference, issuing copies + launches, waiting for the GPU, copying results out */
+    uint64_t ns_slot_wait, ns_pin, ns_plane_wait, ns_issue, ns_sync, ns_host_copy, pin_calls;
 } SvtB200EngineStats;
 
 /* device: CUDA ordinal (the integration reads SVT_CUDA_DEVICE).  Fails (no CPU fallback) when it does not exist.

@@ -112,10 +112,12 @@ void svt_cuda_backend_deinit(void) {
             svt_b200_engine_get_stats(g_engine, &st);
             fprintf(stderr,
                     "SVT [CUDA profile]: engine: %llu ME pictures (%llu plane uploads, %llu resident hits), %llu dlf, %llu cdef, "
-                    "H2D %.1f MB, D2H %.1f MB, pinned %.1f MB, %llu kernel launches\n",
+                    "H2D %.1f MB, D2H %.1f MB, pinned %.1f MB, %llu kernel launches; thread-ms: slot wait %.1f, issue %.1f "
+                    "(of which wait for another thread's upload %.1f), wait for GPU %.1f, host staging copies %.1f\n",
                     (unsigned long long)st.me_pictures, (unsigned long long)st.me_plane_uploads,
                     (unsigned long long)st.me_plane_hits, (unsigned long long)st.dlf_frames, (unsigned long long)st.cdef_frames,
-                    st.h2d_bytes / 1e6, st.d2h_bytes / 1e6, st.pinned_bytes / 1e6, (unsigned long long)svt_b200_launch_count());
+                    st.h2d_bytes / 1e6, st.d2h_bytes / 1e6, st.pinned_bytes / 1e6, (unsigned long long)svt_b200_launch_count(),
+                    st.ns_slot_wait / 1e6, st.ns_issue / 1e6, st.ns_plane_wait / 1e6, st.ns_sync / 1e6, st.ns_host_copy / 1e6);
         }
         svt_b200_engine_destroy(g_engine);
         g_engine = NULL;

@@ -7,16 +7,21 @@
 //   * a residency cache of the three padded luma planes of every picture that ME touches (as source or as reference),
 //     keyed by (host object, picture number): a picture is uploaded once and then serves as reference for the pictures
 //     that follow it (EbPaReferenceObject lifetime, EbPictureBufferDesc.c:65-78 layout);
-//   * per-call slots (stream + device scratch/outputs + pinned result staging) so N threads run N pictures at once;
-//   * lazily page-locking (cudaHostRegister) the host planes it is handed, so uploads / read-backs are real DMA;
+//   * per-call slots (stream + device scratch/outputs + pinned staging) so N threads run N pictures at once;
 //   * the deblock -> CDEF search -> (host strength decision) -> CDEF apply chain of one picture with the
 //     reconstruction resident on the device across the stages.
+// Measured on the 128-thread host of the B200 box (profiles/r2_engine_*.txt): what costs in this setting is not the GPU
+// (0.3 ms per 1080p picture) but CUDA calls that take process-wide locks while ~20 pipeline threads are inside the
+// library — cudaHostRegister of the caller's buffers (4 ms each and it stalls every other thread), cudaMalloc (device
+// synchronisation) and pageable cudaMemcpy (holds the context lock for the whole host copy).  So every buffer is
+// allocated ONCE, when the first picture fixes the geometry (one device arena, one pinned arena), host pictures are
+// packed into the slot's pinned staging with plain memcpy outside any CUDA lock, and each call makes ~10 short
+// asynchronous CUDA calls and one stream wait.
 // Every entry is synchronous for its caller (the reference's stage returns when its picture is done) and re-entrant.
 // There is no CPU fallback: a CUDA failure is returned as SVT_B200_ERR_CUDA and the integration aborts the encode.
 #include <algorithm>
 #include <condition_variable>
 #include <mutex>
-#include <unordered_map>
 #include <vector>
 
 #include "common.cuh"
@@ -25,16 +30,17 @@ using namespace svtb200;
 
 namespace {
 
-constexpr int kMeSlots = 8;      // concurrent ME pictures
-constexpr int kFiltSlots = 6;    // concurrent deblock / CDEF pictures
+constexpr int kMeSlots = 8;       // concurrent ME pictures
+constexpr int kFiltSlots = 8;     // concurrent deblock / CDEF pictures
 constexpr int kPlaneEntries = 96; // resident ME pictures (3.3 MB each at 1080p, 13 MB at 2160p); >= kMeSlots * 9 so that
                                   // every in-flight picture can hold its source + 8 references at once (no deadlock)
+
+inline size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 struct PlaneEntry {
     const void *key = nullptr;
     uint64_t tag = 0;
     uint8_t *d[3] = {nullptr, nullptr, nullptr};
-    size_t cap[3] = {0, 0, 0};
     cudaEvent_t ready = nullptr;
     int state = 0; // 0 free, 1 loading, 2 ready
     int users = 0;
@@ -44,50 +50,73 @@ struct PlaneEntry {
 struct MeSlot {
     bool busy = false;
     cudaStream_t st = nullptr;
-    void *scratch = nullptr;
-    size_t scratch_cap = 0;
-    uint8_t *dev = nullptr; // best_sad | best_mv | hme | me_mv | me_cand | total | rc
-    size_t dev_cap = 0;
-    uint8_t *pin = nullptr; // me_mv | me_cand | total | rc
-    size_t pin_cap = 0;
-};
-
-struct DevFrame {
-    uint8_t *base = nullptr;
-    size_t cap = 0;
-    SvtB200Frame f;
+    cudaEvent_t up_done = nullptr; // the staging buffer has been consumed by its upload
+    bool up_pending = false;
+    uint8_t *scratch = nullptr;
+    uint8_t *dev = nullptr;     // best_sad | best_mv | hme | me_mv | me_cand | total | rc
+    uint8_t *pin_up = nullptr;  // full | quarter | sixteenth of one picture
+    uint8_t *pin_out = nullptr; // me_mv | me_cand | total | rc
 };
 
 struct FiltSlot {
     bool busy = false;
     cudaStream_t st = nullptr;
-    DevFrame recon, out, source;
-    uint8_t *misc = nullptr; // mi array | skip8 | mse | fb idx
-    size_t misc_cap = 0;
-    uint8_t *pin = nullptr;
-    size_t pin_cap = 0;
+    SvtB200Frame recon, out, source; // device pictures
+    uint8_t *misc = nullptr;         // mi array | skip8 | mse | fb idx
+    uint8_t *pin_a = nullptr;        // packed picture (reconstruction up / down)
+    uint8_t *pin_b = nullptr;        // packed picture (source); the mode-info array for deblocking
+    uint8_t *pin_small = nullptr;    // skip map | mse | fb idx
+};
+
+struct MeGeom {
+    size_t nb[3] = {0, 0, 0}, entry = 0, n_sb = 0, scratch = 0;
+    size_t b_sad = 0, b_hme = 0, b_mv = 0, b_cand = 0, b_tot = 0, b_rc = 0, o_mv = 0, o_cand = 0, o_tot = 0, o_rc = 0, dev = 0, out = 0;
+    bool operator==(const MeGeom &o) const { return nb[0] == o.nb[0] && nb[1] == o.nb[1] && nb[2] == o.nb[2] && n_sb == o.n_sb; }
+};
+
+struct FiltGeom {
+    int w = 0, h = 0, bd = 0, mi_rows = 0, mi_cols = 0;
+    int sy = 0, sc = 0; // device strides (samples)
+    size_t by = 0, bc = 0, frame = 0, packed = 0, mi = 0, skip = 0, mse = 0, nfb = 0, misc = 0, small = 0;
+    bool same(int w_, int h_, int bd_) const { return w == w_ && h == h_ && bd == bd_; }
 };
 
 } // namespace
 
 struct SvtB200Engine {
     int device = 0;
-    bool pin_host = true;
     std::mutex mu;
     std::condition_variable cv;
     uint64_t clock = 0;
     PlaneEntry planes[kPlaneEntries];
     MeSlot me[kMeSlots];
     FiltSlot filt[kFiltSlots];
-    std::mutex pin_mu;
-    std::unordered_map<const void *, size_t> pinned; // base -> bytes (0: registration failed, do not retry)
+    // geometry-bound memory, allocated once by the first picture of each kind
+    std::mutex init_mu;
+    bool me_ready = false, filt_ready = false;
+    MeGeom mg;
+    FiltGeom fg;
+    uint8_t *me_dev = nullptr, *me_pin = nullptr, *filt_dev = nullptr, *filt_pin = nullptr;
     struct {
         std::atomic<uint64_t> me_pictures{0}, dlf_frames{0}, cdef_frames{0}, me_plane_uploads{0}, me_plane_hits{0}, h2d_bytes{0},
-            d2h_bytes{0}, pinned_bytes{0};
+            d2h_bytes{0}, pinned_bytes{0}, ns_slot_wait{0}, ns_pin{0}, ns_plane_wait{0}, ns_issue{0}, ns_sync{0}, ns_host_copy{0},
+            pin_calls{0};
     } stats;
 };
 
 namespace {
+
+inline uint64_t now_ns() {
+    timespec t;
+    clock_gettime(CLOCK_MONOTONIC, &t);
+    return (uint64_t)t.tv_sec * 1000000000ull + (uint64_t)t.tv_nsec;
+}
+struct Lap { // accumulates wall time into an engine counter
+    std::atomic<uint64_t> &acc;
+    uint64_t t0;
+    explicit Lap(std::atomic<uint64_t> &a) : acc(a), t0(now_ns()) {}
+    ~Lap() { acc += now_ns() - t0; }
+};
 
 #define ENG_TRY(expr)                                                                                              \
     do {                                                                                                           \
@@ -98,46 +127,9 @@ namespace {
         }                                                                                                          \
     } while (0)
 
-int grow_dev(uint8_t **p, size_t *cap, size_t need) {
-    if (need <= *cap) return SVT_B200_OK;
-    if (*p) cudaFree(*p);
-    *p = nullptr;
-    *cap = 0;
-    const size_t n = (need + 0xffff) & ~(size_t)0xffff;
-    ENG_TRY(cudaMalloc((void **)p, n));
-    *cap = n;
-    return SVT_B200_OK;
-}
-int grow_pin(uint8_t **p, size_t *cap, size_t need) {
-    if (need <= *cap) return SVT_B200_OK;
-    if (*p) cudaFreeHost(*p);
-    *p = nullptr;
-    *cap = 0;
-    const size_t n = (need + 0xffff) & ~(size_t)0xffff;
-    ENG_TRY(cudaMallocHost((void **)p, n));
-    *cap = n;
-    return SVT_B200_OK;
-}
-
-// Page-lock a host range once (the reference allocates its picture buffers once per encoder and recycles them).
-void pin_range(SvtB200Engine *e, const void *base, size_t bytes) {
-    if (!e->pin_host || !base || !bytes) return;
-    std::lock_guard<std::mutex> g(e->pin_mu);
-    auto it = e->pinned.find(base);
-    if (it != e->pinned.end() && (it->second == 0 || it->second >= bytes)) return;
-    if (it != e->pinned.end()) cudaHostUnregister((void *)base);
-    cudaError_t r = cudaHostRegister((void *)base, bytes, cudaHostRegisterDefault);
-    if (r != cudaSuccess) {
-        cudaGetLastError(); // pageable copies still work; remember not to retry
-        e->pinned[base] = 0;
-        return;
-    }
-    e->pinned[base] = bytes;
-    e->stats.pinned_bytes += bytes;
-}
-
 template <typename Slot, int N>
 Slot *acquire(SvtB200Engine *e, Slot (&pool)[N]) {
+    Lap lap(e->stats.ns_slot_wait);
     std::unique_lock<std::mutex> lk(e->mu);
     for (;;) {
         for (int i = 0; i < N; i++)
@@ -157,12 +149,124 @@ void release(SvtB200Engine *e, Slot *s) {
     e->cv.notify_all();
 }
 
+cudaError_t timed_sync(SvtB200Engine *e, cudaStream_t st) {
+    Lap lap(e->stats.ns_sync);
+    return cudaStreamSynchronize(st);
+}
+
 size_t plane_bytes(const SvtB200Plane &g) { return (size_t)g.stride * (size_t)(g.height + 2 * g.origin_y); }
 
-// Make the three planes of `pic` resident and ordered before later work on `st`.  Returns the entry with users++.
-int plane_acquire(SvtB200Engine *e, const SvtB200MeParams *p, const SvtB200HostMePicture *pic, int filtered_ds,
-                  cudaStream_t st, PlaneEntry **out) {
-    const size_t nb[3] = {plane_bytes(p->full), plane_bytes(p->quarter), plane_bytes(p->sixteenth)};
+// ---- one-time allocation for the ME side --------------------------------------------------------------------------
+int ensure_me(SvtB200Engine *e, const SvtB200MeParams *p) {
+    MeGeom g;
+    g.nb[0] = plane_bytes(p->full);
+    g.nb[1] = plane_bytes(p->quarter);
+    g.nb[2] = plane_bytes(p->sixteenth);
+    g.n_sb = (size_t)((p->full.width + 63) / 64) * ((p->full.height + 63) / 64);
+    std::lock_guard<std::mutex> lk(e->init_mu);
+    if (e->me_ready) {
+        if (e->mg == g) return SVT_B200_OK;
+        set_error("engine: the ME picture geometry changed (one engine serves one sequence geometry)");
+        return SVT_B200_ERR_UNSUPPORTED;
+    }
+    g.entry = al256(g.nb[0]) + al256(g.nb[1]) + al256(g.nb[2]);
+    g.scratch = al256(svt_b200_me_scratch_bytes(p));
+    g.b_sad = g.n_sb * 8 * 85 * 4;
+    g.b_hme = g.n_sb * 8 * sizeof(SvtB200HmeResult);
+    g.b_mv = g.n_sb * 85 * 7 * 4;
+    g.b_cand = g.n_sb * 85 * 23;
+    g.b_tot = g.n_sb * 85;
+    g.b_rc = g.n_sb * 4;
+    g.o_mv = 2 * al256(g.b_sad) + al256(g.b_hme);
+    g.o_cand = g.o_mv + al256(g.b_mv);
+    g.o_tot = g.o_cand + al256(g.b_cand);
+    g.o_rc = g.o_tot + al256(g.b_tot);
+    g.dev = g.o_rc + al256(g.b_rc);
+    g.out = g.dev - g.o_mv;
+    const size_t dev_total = (size_t)kPlaneEntries * g.entry + (size_t)kMeSlots * (g.scratch + g.dev);
+    const size_t pin_total = (size_t)kMeSlots * (g.entry + al256(g.out));
+    ENG_TRY(cudaMalloc((void **)&e->me_dev, dev_total));
+    ENG_TRY(cudaMallocHost((void **)&e->me_pin, pin_total));
+    e->stats.pinned_bytes += pin_total;
+    uint8_t *d = e->me_dev, *h = e->me_pin;
+    for (auto &c : e->planes) {
+        c.d[0] = d;
+        c.d[1] = d + al256(g.nb[0]);
+        c.d[2] = c.d[1] + al256(g.nb[1]);
+        d += g.entry;
+    }
+    for (auto &s : e->me) {
+        s.scratch = d;
+        s.dev = d + g.scratch;
+        d += g.scratch + g.dev;
+        s.pin_up = h;
+        s.pin_out = h + g.entry;
+        h += g.entry + al256(g.out);
+    }
+    e->mg = g;
+    e->me_ready = true;
+    return SVT_B200_OK;
+}
+
+// ---- one-time allocation for the deblock / CDEF side ---------------------------------------------------------------
+int ensure_filt(SvtB200Engine *e, int w, int h, int bd, int mi_rows, int mi_cols) {
+    std::lock_guard<std::mutex> lk(e->init_mu);
+    if (e->filt_ready) {
+        if (e->fg.same(w, h, bd)) return SVT_B200_OK;
+        set_error("engine: the picture geometry changed (one engine serves one sequence geometry)");
+        return SVT_B200_ERR_UNSUPPORTED;
+    }
+    FiltGeom g;
+    g.w = w, g.h = h, g.bd = bd, g.mi_rows = mi_rows, g.mi_cols = mi_cols;
+    const int bps = bd > 8 ? 2 : 1, cw = (w + 1) >> 1, ch = (h + 1) >> 1;
+    g.sy = (w + 63) & ~63; // rows start 64-byte (8-bit) / 128-byte (16-bit) aligned: 128-bit vector access on every row
+    g.sc = (cw + 63) & ~63;
+    g.by = al256((size_t)g.sy * h * bps) + 256; // + slack between planes
+    g.bc = al256((size_t)g.sc * ch * bps) + 256;
+    g.frame = g.by + 2 * g.bc + 1024;
+    g.packed = al256(((size_t)w * h + 2 * (size_t)cw * ch) * bps);
+    g.mi = al256((size_t)mi_rows * mi_cols * sizeof(SvtB200DlfMi));
+    g.nfb = (size_t)((mi_rows + 15) / 16) * ((mi_cols + 15) / 16);
+    g.skip = al256((size_t)((mi_rows + 1) / 2) * ((((mi_cols + 1) / 2) + 15) & ~15));
+    g.mse = al256(g.nfb * 2 * 64 * 8);
+    g.small = g.skip + g.mse + al256(g.nfb);
+    g.misc = std::max(g.mi, g.small);
+    const size_t dev_total = (size_t)kFiltSlots * (3 * g.frame + g.misc);
+    const size_t pin_b = std::max(g.packed, g.mi);
+    const size_t pin_total = (size_t)kFiltSlots * (g.packed + pin_b + g.small);
+    ENG_TRY(cudaMalloc((void **)&e->filt_dev, dev_total));
+    ENG_TRY(cudaMallocHost((void **)&e->filt_pin, pin_total));
+    e->stats.pinned_bytes += pin_total;
+    uint8_t *d = e->filt_dev, *hp = e->filt_pin;
+    for (auto &s : e->filt) {
+        SvtB200Frame *fr[3] = {&s.recon, &s.out, &s.source};
+        for (SvtB200Frame *f : fr) {
+            f->y = d + 512; // margin: the filters' vector loads may touch a few bytes before sample (0,0)
+            f->cb = d + 512 + g.by;
+            f->cr = d + 512 + g.by + g.bc;
+            f->stride_y = g.sy;
+            f->stride_c = g.sc;
+            f->width = w;
+            f->height = h;
+            f->bit_depth = bd;
+            d += g.frame;
+        }
+        s.misc = d;
+        d += g.misc;
+        s.pin_a = hp;
+        s.pin_b = hp + g.packed;
+        s.pin_small = s.pin_b + pin_b;
+        hp += g.packed + pin_b + g.small;
+    }
+    e->fg = g;
+    e->filt_ready = true;
+    return SVT_B200_OK;
+}
+
+// Make the three planes of `pic` resident and ordered before later work on the slot's stream.  users++ on return.
+int plane_acquire(SvtB200Engine *e, MeSlot *s, const SvtB200MeParams *p, const SvtB200HostMePicture *pic, int filtered_ds,
+                  PlaneEntry **out) {
+    const MeGeom &g = e->mg;
     PlaneEntry *en = nullptr;
     bool loader = false;
     {
@@ -174,13 +278,16 @@ int plane_acquire(SvtB200Engine *e, const SvtB200MeParams *p, const SvtB200HostM
                     en = &c;
                     break;
                 }
-                if (c.users == 0 && c.state != 1 && (!victim || c.state < victim->state ||
-                                                     (c.state == victim->state && c.stamp < victim->stamp)))
+                if (c.users == 0 && c.state != 1 &&
+                    (!victim || c.state < victim->state || (c.state == victim->state && c.stamp < victim->stamp)))
                     victim = &c;
             }
             if (en) {
                 en->users++;
-                while (en->state == 1) e->cv.wait(lk);
+                {
+                    Lap lap(e->stats.ns_plane_wait);
+                    while (en->state == 1) e->cv.wait(lk);
+                }
                 if (en->state != 2) { // the loader failed
                     en->users--;
                     set_error("engine: upload of a reference picture failed in another thread");
@@ -205,23 +312,34 @@ int plane_acquire(SvtB200Engine *e, const SvtB200MeParams *p, const SvtB200HostM
     }
     if (loader) {
         int rc = SVT_B200_OK;
-        const uint8_t *host[3] = {pic->full, pic->quarter, pic->sixteenth};
-        for (int i = 0; i < 3 && rc == SVT_B200_OK; i++) rc = grow_dev(&en->d[i], &en->cap[i], nb[i]);
-        if (rc == SVT_B200_OK && !en->ready && cudaEventCreateWithFlags(&en->ready, cudaEventDisableTiming) != cudaSuccess)
-            rc = SVT_B200_ERR_CUDA;
         const bool gen = !pic->quarter || !pic->sixteenth; // decimations derived on the device
-        for (int i = 0; i < (gen ? 1 : 3) && rc == SVT_B200_OK; i++) {
-            pin_range(e, host[i], nb[i]);
-            if (cudaMemcpyAsync(en->d[i], host[i], nb[i], cudaMemcpyHostToDevice, st) != cudaSuccess) rc = SVT_B200_ERR_CUDA;
-            e->stats.h2d_bytes += nb[i];
+        if (s->up_pending) { // the staging buffer still feeds the previous upload of this call
+            if (cudaEventSynchronize(s->up_done) != cudaSuccess) rc = SVT_B200_ERR_CUDA;
+            s->up_pending = false;
         }
+        size_t bytes = 0;
+        if (rc == SVT_B200_OK) {
+            Lap lap(e->stats.ns_host_copy);
+            memcpy(s->pin_up, pic->full, g.nb[0]);
+            bytes = g.nb[0];
+            if (!gen) {
+                memcpy(s->pin_up + al256(g.nb[0]), pic->quarter, g.nb[1]);
+                memcpy(s->pin_up + al256(g.nb[0]) + al256(g.nb[1]), pic->sixteenth, g.nb[2]);
+                bytes = al256(g.nb[0]) + al256(g.nb[1]) + g.nb[2]; // the three planes are laid out alike on both sides
+            }
+        }
+        if (rc == SVT_B200_OK && cudaMemcpyAsync(en->d[0], s->pin_up, bytes, cudaMemcpyHostToDevice, s->st) != cudaSuccess)
+            rc = SVT_B200_ERR_CUDA;
+        if (rc == SVT_B200_OK && cudaEventRecord(s->up_done, s->st) != cudaSuccess) rc = SVT_B200_ERR_CUDA;
+        s->up_pending = rc == SVT_B200_OK;
+        e->stats.h2d_bytes += bytes;
         if (rc == SVT_B200_OK && gen) {
             SvtB200MePlanes dp = {en->d[0], en->d[1], en->d[2]};
-            rc = svt_b200_me_downsample(&p->full, &p->quarter, &p->sixteenth, &dp, filtered_ds, st);
+            rc = svt_b200_me_downsample(&p->full, &p->quarter, &p->sixteenth, &dp, filtered_ds, s->st);
         }
-        if (rc == SVT_B200_OK && cudaEventRecord(en->ready, st) != cudaSuccess) rc = SVT_B200_ERR_CUDA;
+        if (rc == SVT_B200_OK && cudaEventRecord(en->ready, s->st) != cudaSuccess) rc = SVT_B200_ERR_CUDA;
         {
-            std::lock_guard<std::mutex> g(e->mu);
+            std::lock_guard<std::mutex> gl(e->mu);
             en->state = rc == SVT_B200_OK ? 2 : 0;
             if (rc != SVT_B200_OK) en->users--;
         }
@@ -231,7 +349,7 @@ int plane_acquire(SvtB200Engine *e, const SvtB200MeParams *p, const SvtB200HostM
             return rc;
         }
     } else {
-        ENG_TRY(cudaStreamWaitEvent(st, en->ready, 0));
+        ENG_TRY(cudaStreamWaitEvent(s->st, en->ready, 0));
     }
     *out = en;
     return SVT_B200_OK;
@@ -246,46 +364,43 @@ void plane_release(SvtB200Engine *e, PlaneEntry **ents, int n) {
     e->cv.notify_all();
 }
 
-size_t frame_plane_bytes(int w, int h, int bd, int *stride) {
-    const int bps = bd > 8 ? 2 : 1;
-    *stride = (w + 63) & ~63; // samples; 64-sample multiple keeps every row 64-byte (8-bit) / 128-byte aligned
-    return (size_t)*stride * h * bps;
+// host picture <-> packed (tight rows: y, cb, cr) pinned staging
+void pack_frame(SvtB200Engine *e, uint8_t *pin, const SvtB200Frame *h) {
+    Lap lap(e->stats.ns_host_copy);
+    const int bps = h->bit_depth > 8 ? 2 : 1, cw = (h->width + 1) >> 1, ch = (h->height + 1) >> 1;
+    const size_t rw = (size_t)h->width * bps, rc = (size_t)cw * bps;
+    for (int y = 0; y < h->height; y++) memcpy(pin + y * rw, (const uint8_t *)h->y + (size_t)y * h->stride_y * bps, rw);
+    pin += rw * h->height;
+    for (int y = 0; y < ch; y++) memcpy(pin + y * rc, (const uint8_t *)h->cb + (size_t)y * h->stride_c * bps, rc);
+    pin += rc * ch;
+    for (int y = 0; y < ch; y++) memcpy(pin + y * rc, (const uint8_t *)h->cr + (size_t)y * h->stride_c * bps, rc);
 }
-
-// Device picture of the geometry of `h` (luma w x h, 4:2:0).
-int dev_frame(DevFrame *d, const SvtB200Frame *h) {
-    int sy, sc;
-    const int cw = (h->width + 1) >> 1, ch = (h->height + 1) >> 1;
-    const size_t by = frame_plane_bytes(h->width, h->height, h->bit_depth, &sy);
-    const size_t bc = frame_plane_bytes(cw, ch, h->bit_depth, &sc);
-    const size_t pad = 256;
-    int rc = grow_dev(&d->base, &d->cap, by + 2 * bc + 4 * pad);
-    if (rc != SVT_B200_OK) return rc;
-    d->f = *h;
-    d->f.y = d->base + pad;
-    d->f.cb = d->base + 2 * pad + by;
-    d->f.cr = d->base + 3 * pad + by + bc;
-    d->f.stride_y = sy;
-    d->f.stride_c = sc;
-    return SVT_B200_OK;
+void unpack_frame(SvtB200Engine *e, const SvtB200Frame *h, const uint8_t *pin) {
+    Lap lap(e->stats.ns_host_copy);
+    const int bps = h->bit_depth > 8 ? 2 : 1, cw = (h->width + 1) >> 1, ch = (h->height + 1) >> 1;
+    const size_t rw = (size_t)h->width * bps, rc = (size_t)cw * bps;
+    for (int y = 0; y < h->height; y++) memcpy((uint8_t *)h->y + (size_t)y * h->stride_y * bps, pin + y * rw, rw);
+    pin += rw * h->height;
+    for (int y = 0; y < ch; y++) memcpy((uint8_t *)h->cb + (size_t)y * h->stride_c * bps, pin + y * rc, rc);
+    pin += rc * ch;
+    for (int y = 0; y < ch; y++) memcpy((uint8_t *)h->cr + (size_t)y * h->stride_c * bps, pin + y * rc, rc);
 }
-
-int copy_frame(SvtB200Engine *e, const SvtB200Frame *dst, const SvtB200Frame *src, cudaMemcpyKind kind, cudaStream_t st) {
-    const int bps = src->bit_depth > 8 ? 2 : 1;
-    const int cw = (src->width + 1) >> 1, ch = (src->height + 1) >> 1;
-    const SvtB200Frame *host = kind == cudaMemcpyHostToDevice ? src : dst;
-    pin_range(e, host->y, ((size_t)host->stride_y * (host->height - 1) + host->width) * bps);
-    pin_range(e, host->cb, ((size_t)host->stride_c * (ch - 1) + cw) * bps);
-    pin_range(e, host->cr, ((size_t)host->stride_c * (ch - 1) + cw) * bps);
-    ENG_TRY(cudaMemcpy2DAsync(dst->y, (size_t)dst->stride_y * bps, src->y, (size_t)src->stride_y * bps, (size_t)src->width * bps,
-                              src->height, kind, st));
-    ENG_TRY(cudaMemcpy2DAsync(dst->cb, (size_t)dst->stride_c * bps, src->cb, (size_t)src->stride_c * bps, (size_t)cw * bps, ch, kind, st));
-    ENG_TRY(cudaMemcpy2DAsync(dst->cr, (size_t)dst->stride_c * bps, src->cr, (size_t)src->stride_c * bps, (size_t)cw * bps, ch, kind, st));
-    const size_t n = ((size_t)src->width * src->height + 2 * (size_t)cw * ch) * bps;
-    if (kind == cudaMemcpyHostToDevice)
-        e->stats.h2d_bytes += n;
-    else
-        e->stats.d2h_bytes += n;
+// packed pinned staging <-> device picture (three 2-D copies; both sides page-locked / device: pure DMA, asynchronous)
+int copy_packed(SvtB200Engine *e, const SvtB200Frame *dev, uint8_t *pin, cudaMemcpyKind kind, cudaStream_t st) {
+    const int bps = dev->bit_depth > 8 ? 2 : 1, cw = (dev->width + 1) >> 1, ch = (dev->height + 1) >> 1;
+    const size_t rw = (size_t)dev->width * bps, rc = (size_t)cw * bps;
+    uint8_t *py = pin, *pcb = pin + rw * dev->height, *pcr = pcb + rc * ch;
+    if (kind == cudaMemcpyHostToDevice) {
+        ENG_TRY(cudaMemcpy2DAsync(dev->y, (size_t)dev->stride_y * bps, py, rw, rw, dev->height, kind, st));
+        ENG_TRY(cudaMemcpy2DAsync(dev->cb, (size_t)dev->stride_c * bps, pcb, rc, rc, ch, kind, st));
+        ENG_TRY(cudaMemcpy2DAsync(dev->cr, (size_t)dev->stride_c * bps, pcr, rc, rc, ch, kind, st));
+        e->stats.h2d_bytes += rw * dev->height + 2 * rc * ch;
+    } else {
+        ENG_TRY(cudaMemcpy2DAsync(py, rw, dev->y, (size_t)dev->stride_y * bps, rw, dev->height, kind, st));
+        ENG_TRY(cudaMemcpy2DAsync(pcb, rc, dev->cb, (size_t)dev->stride_c * bps, rc, ch, kind, st));
+        ENG_TRY(cudaMemcpy2DAsync(pcr, rc, dev->cr, (size_t)dev->stride_c * bps, rc, ch, kind, st));
+        e->stats.d2h_bytes += rw * dev->height + 2 * rc * ch;
+    }
     return SVT_B200_OK;
 }
 
@@ -293,8 +408,10 @@ struct DeviceGuard { // engine calls come from arbitrary pipeline threads: bind 
     int prev = -1;
     explicit DeviceGuard(int dev) {
         cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
+        if (prev != dev)
+            cudaSetDevice(dev);
+        else
+            prev = -1;
     }
     ~DeviceGuard() {
         if (prev >= 0) cudaSetDevice(prev);
@@ -314,11 +431,13 @@ int svt_b200_engine_create(int device, SvtB200Engine **out) {
     }
     SvtB200Engine *e = new SvtB200Engine();
     e->device = device;
-    const char *pin = getenv("SVT_B200_PIN_HOST");
-    e->pin_host = !(pin && pin[0] == '0');
     DeviceGuard g(device);
-    for (auto &s : e->me) ENG_TRY(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    for (auto &s : e->me) {
+        ENG_TRY(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+        ENG_TRY(cudaEventCreateWithFlags(&s.up_done, cudaEventDisableTiming));
+    }
     for (auto &s : e->filt) ENG_TRY(cudaStreamCreateWithFlags(&s.st, cudaStreamNonBlocking));
+    for (auto &c : e->planes) ENG_TRY(cudaEventCreateWithFlags(&c.ready, cudaEventDisableTiming));
     *out = e;
     return SVT_B200_OK;
 }
@@ -329,24 +448,16 @@ void svt_b200_engine_destroy(SvtB200Engine *e) {
     cudaDeviceSynchronize();
     for (auto &s : e->me) {
         if (s.st) cudaStreamDestroy(s.st);
-        if (s.scratch) cudaFree(s.scratch);
-        if (s.dev) cudaFree(s.dev);
-        if (s.pin) cudaFreeHost(s.pin);
+        if (s.up_done) cudaEventDestroy(s.up_done);
     }
-    for (auto &s : e->filt) {
+    for (auto &s : e->filt)
         if (s.st) cudaStreamDestroy(s.st);
-        for (DevFrame *d : {&s.recon, &s.out, &s.source})
-            if (d->base) cudaFree(d->base);
-        if (s.misc) cudaFree(s.misc);
-        if (s.pin) cudaFreeHost(s.pin);
-    }
-    for (auto &c : e->planes) {
-        for (int i = 0; i < 3; i++)
-            if (c.d[i]) cudaFree(c.d[i]);
+    for (auto &c : e->planes)
         if (c.ready) cudaEventDestroy(c.ready);
-    }
-    for (auto &kv : e->pinned)
-        if (kv.second) cudaHostUnregister((void *)kv.first);
+    if (e->me_dev) cudaFree(e->me_dev);
+    if (e->filt_dev) cudaFree(e->filt_dev);
+    if (e->me_pin) cudaFreeHost(e->me_pin);
+    if (e->filt_pin) cudaFreeHost(e->filt_pin);
     cudaGetLastError();
     delete e;
 }
@@ -361,6 +472,13 @@ int svt_b200_engine_get_stats(SvtB200Engine *e, SvtB200EngineStats *out) {
     out->h2d_bytes = e->stats.h2d_bytes;
     out->d2h_bytes = e->stats.d2h_bytes;
     out->pinned_bytes = e->stats.pinned_bytes;
+    out->ns_slot_wait = e->stats.ns_slot_wait;
+    out->ns_pin = e->stats.ns_pin;
+    out->ns_plane_wait = e->stats.ns_plane_wait;
+    out->ns_issue = e->stats.ns_issue;
+    out->ns_sync = e->stats.ns_sync;
+    out->ns_host_copy = e->stats.ns_host_copy;
+    out->pin_calls = e->stats.pin_calls;
     return SVT_B200_OK;
 }
 
@@ -373,93 +491,109 @@ int svt_b200_engine_me_picture(SvtB200Engine *e, const SvtB200MeParams *p, const
         return SVT_B200_ERR_ARG;
     }
     DeviceGuard dg(e->device);
-    const size_t n_sb = (size_t)((p->full.width + 63) / 64) * ((p->full.height + 63) / 64);
-    const size_t b_sad = n_sb * 8 * 85 * 4, b_hme = n_sb * 8 * sizeof(SvtB200HmeResult);
-    const size_t b_mv = n_sb * 85 * 7 * 4, b_cand = n_sb * 85 * 23, b_tot = n_sb * 85, b_rc = n_sb * 4;
-    auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    int rc = ensure_me(e, p);
+    if (rc != SVT_B200_OK) return rc;
+    const MeGeom &g = e->mg;
     MeSlot *s = acquire(e, e->me);
-    int rc = SVT_B200_OK;
     PlaneEntry *ents[1 + SVT_B200_ME_LISTS * SVT_B200_ME_MAX_REFS] = {nullptr};
     int n_ent = 0;
     do {
-        const size_t need_scratch = svt_b200_me_scratch_bytes(p);
-        if ((rc = grow_dev((uint8_t **)&s->scratch, &s->scratch_cap, need_scratch)) != SVT_B200_OK) break;
-        const size_t o_mv = 2 * al(b_sad) + al(b_hme), o_cand = o_mv + al(b_mv), o_tot = o_cand + al(b_cand), o_rc = o_tot + al(b_tot);
-        if ((rc = grow_dev(&s->dev, &s->dev_cap, o_rc + al(b_rc))) != SVT_B200_OK) break;
-        const size_t out_bytes = al(b_mv) + al(b_cand) + al(b_tot) + al(b_rc);
-        if ((rc = grow_pin(&s->pin, &s->pin_cap, out_bytes)) != SVT_B200_OK) break;
         SvtB200MePlanes dsrc, drefs[SVT_B200_ME_LISTS][SVT_B200_ME_MAX_REFS];
         memset(drefs, 0, sizeof(drefs));
-        if ((rc = plane_acquire(e, p, src, filtered_downsample, s->st, &ents[n_ent])) != SVT_B200_OK) break;
-        dsrc = {ents[n_ent]->d[0], ents[n_ent]->d[1], ents[n_ent]->d[2]};
-        n_ent++;
-        for (int l = 0; l < p->num_lists && rc == SVT_B200_OK; l++)
-            for (int r = 0; r < p->num_refs[l] && rc == SVT_B200_OK; r++) {
-                if (!refs[l][r].full) {
-                    set_error("svt_b200_engine_me_picture: reference [%d][%d] has no planes", l, r);
-                    rc = SVT_B200_ERR_ARG;
-                    break;
+        {
+            Lap lap(e->stats.ns_issue);
+            if ((rc = plane_acquire(e, s, p, src, filtered_downsample, &ents[n_ent])) != SVT_B200_OK) break;
+            dsrc = {ents[n_ent]->d[0], ents[n_ent]->d[1], ents[n_ent]->d[2]};
+            n_ent++;
+            for (int l = 0; l < p->num_lists && rc == SVT_B200_OK; l++)
+                for (int r = 0; r < p->num_refs[l] && rc == SVT_B200_OK; r++) {
+                    if (!refs[l][r].full) {
+                        set_error("svt_b200_engine_me_picture: reference [%d][%d] has no planes", l, r);
+                        rc = SVT_B200_ERR_ARG;
+                        break;
+                    }
+                    if ((rc = plane_acquire(e, s, p, &refs[l][r], filtered_downsample, &ents[n_ent])) != SVT_B200_OK) break;
+                    drefs[l][r] = {ents[n_ent]->d[0], ents[n_ent]->d[1], ents[n_ent]->d[2]};
+                    n_ent++;
                 }
-                if ((rc = plane_acquire(e, p, &refs[l][r], filtered_downsample, s->st, &ents[n_ent])) != SVT_B200_OK) break;
-                drefs[l][r] = {ents[n_ent]->d[0], ents[n_ent]->d[1], ents[n_ent]->d[2]};
-                n_ent++;
+            if (rc != SVT_B200_OK) break;
+            SvtB200MeOutputs o;
+            o.best_sad = (uint32_t *)s->dev;
+            o.best_mv = (uint32_t *)(s->dev + al256(g.b_sad));
+            o.hme = (SvtB200HmeResult *)(s->dev + 2 * al256(g.b_sad));
+            o.me_mv = (int16_t *)(s->dev + g.o_mv);
+            o.me_cand = s->dev + g.o_cand;
+            o.total_cand = s->dev + g.o_tot;
+            o.rc_me_distortion = (uint32_t *)(s->dev + g.o_rc);
+            if ((rc = svt_b200_me_picture(p, &dsrc, drefs, &o, s->scratch, s->st)) != SVT_B200_OK) break;
+            // the four result arrays are contiguous on the device: one read-back
+            if (cudaMemcpyAsync(s->pin_out, s->dev + g.o_mv, g.out, cudaMemcpyDeviceToHost, s->st) != cudaSuccess) {
+                set_error("engine: ME read-back failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = SVT_B200_ERR_CUDA;
+                break;
             }
-        if (rc != SVT_B200_OK) break;
-        SvtB200MeOutputs o;
-        o.best_sad = (uint32_t *)s->dev;
-        o.best_mv = (uint32_t *)(s->dev + al(b_sad));
-        o.hme = (SvtB200HmeResult *)(s->dev + 2 * al(b_sad));
-        o.me_mv = (int16_t *)(s->dev + o_mv);
-        o.me_cand = s->dev + o_cand;
-        o.total_cand = s->dev + o_tot;
-        o.rc_me_distortion = (uint32_t *)(s->dev + o_rc);
-        if ((rc = svt_b200_me_picture(p, &dsrc, drefs, &o, s->scratch, s->st)) != SVT_B200_OK) break;
-        // the four result arrays are contiguous on the device: one read-back
-        if (cudaMemcpyAsync(s->pin, s->dev + o_mv, out_bytes, cudaMemcpyDeviceToHost, s->st) != cudaSuccess ||
-            cudaStreamSynchronize(s->st) != cudaSuccess) {
-            set_error("engine: ME read-back failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        if (timed_sync(e, s->st) != cudaSuccess) {
+            set_error("engine: ME failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc = SVT_B200_ERR_CUDA;
             break;
         }
-        memcpy(me_mv, s->pin, b_mv);
-        memcpy(me_cand, s->pin + al(b_mv), b_cand);
-        memcpy(total_cand, s->pin + al(b_mv) + al(b_cand), b_tot);
-        memcpy(rc_me_distortion, s->pin + al(b_mv) + al(b_cand) + al(b_tot), b_rc);
+        s->up_pending = false;
+        Lap lap(e->stats.ns_host_copy);
+        memcpy(me_mv, s->pin_out, g.b_mv);
+        memcpy(me_cand, s->pin_out + (g.o_cand - g.o_mv), g.b_cand);
+        memcpy(total_cand, s->pin_out + (g.o_tot - g.o_mv), g.b_tot);
+        memcpy(rc_me_distortion, s->pin_out + (g.o_rc - g.o_mv), g.b_rc);
         e->stats.me_pictures++;
-        e->stats.d2h_bytes += out_bytes;
+        e->stats.d2h_bytes += g.out;
     } while (0);
-    if (rc != SVT_B200_OK) cudaStreamSynchronize(s->st); // nothing of this picture may still read the planes
+    if (rc != SVT_B200_OK) {
+        cudaStreamSynchronize(s->st); // nothing of this picture may still read the planes
+        s->up_pending = false;
+    }
     plane_release(e, ents, n_ent);
     release(e, s);
     return rc;
 }
 
 int svt_b200_engine_dlf_frame(SvtB200Engine *e, const SvtB200DlfParams *p, const SvtB200Frame *frame, const SvtB200DlfMi *mi) {
-    if (!e || !p || !frame || !mi) {
-        set_error("svt_b200_engine_dlf_frame: null argument");
+    if (!e || !p || !frame || !mi || p->mi_stride != p->mi_cols) {
+        set_error("svt_b200_engine_dlf_frame: bad argument (mi_stride must equal mi_cols)");
         return SVT_B200_ERR_ARG;
     }
     DeviceGuard dg(e->device);
+    int rc = ensure_filt(e, frame->width, frame->height, frame->bit_depth, p->mi_rows, p->mi_cols);
+    if (rc != SVT_B200_OK) return rc;
+    const FiltGeom &g = e->fg;
+    const size_t b_mi = (size_t)p->mi_rows * p->mi_cols * sizeof(SvtB200DlfMi);
+    if (b_mi > g.mi) {
+        set_error("svt_b200_engine_dlf_frame: mode-info array larger than the sequence geometry");
+        return SVT_B200_ERR_ARG;
+    }
     FiltSlot *s = acquire(e, e->filt);
-    int rc;
     do {
-        const size_t b_mi = (size_t)p->mi_rows * p->mi_stride * sizeof(SvtB200DlfMi);
-        if ((rc = dev_frame(&s->recon, frame)) != SVT_B200_OK) break;
-        if ((rc = grow_dev(&s->misc, &s->misc_cap, b_mi)) != SVT_B200_OK) break;
-        pin_range(e, mi, b_mi);
-        if (cudaMemcpyAsync(s->misc, mi, b_mi, cudaMemcpyHostToDevice, s->st) != cudaSuccess) {
-            set_error("engine: mode-info upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-            rc = SVT_B200_ERR_CUDA;
-            break;
+        pack_frame(e, s->pin_a, frame);
+        {
+            Lap lap(e->stats.ns_host_copy);
+            memcpy(s->pin_b, mi, b_mi);
         }
-        if ((rc = copy_frame(e, &s->recon.f, frame, cudaMemcpyHostToDevice, s->st)) != SVT_B200_OK) break;
-        if ((rc = svt_b200_dlf_frame(p, &s->recon.f, (const SvtB200DlfMi *)s->misc, s->st)) != SVT_B200_OK) break;
-        if ((rc = copy_frame(e, frame, &s->recon.f, cudaMemcpyDeviceToHost, s->st)) != SVT_B200_OK) break;
-        if (cudaStreamSynchronize(s->st) != cudaSuccess) {
+        {
+            Lap lap(e->stats.ns_issue);
+            if (cudaMemcpyAsync(s->misc, s->pin_b, b_mi, cudaMemcpyHostToDevice, s->st) != cudaSuccess) {
+                set_error("engine: mode-info upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = SVT_B200_ERR_CUDA;
+                break;
+            }
+            if ((rc = copy_packed(e, &s->recon, s->pin_a, cudaMemcpyHostToDevice, s->st)) != SVT_B200_OK) break;
+            if ((rc = svt_b200_dlf_frame(p, &s->recon, (const SvtB200DlfMi *)s->misc, s->st)) != SVT_B200_OK) break;
+            if ((rc = copy_packed(e, &s->recon, s->pin_a, cudaMemcpyDeviceToHost, s->st)) != SVT_B200_OK) break;
+        }
+        if (timed_sync(e, s->st) != cudaSuccess) {
             set_error("engine: deblocking failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc = SVT_B200_ERR_CUDA;
             break;
         }
+        unpack_frame(e, frame, s->pin_a);
         e->stats.dlf_frames++;
         e->stats.h2d_bytes += b_mi;
     } while (0);
@@ -471,68 +605,84 @@ int svt_b200_engine_dlf_frame(SvtB200Engine *e, const SvtB200DlfParams *p, const
 int svt_b200_engine_cdef_frame(SvtB200Engine *e, const SvtB200CdefSearchParams *sp, const SvtB200Frame *recon,
                                const SvtB200Frame *source, const uint8_t *skip8, int32_t skip_stride, uint64_t *mse,
                                SvtB200CdefDecideFn decide, void *user) {
-    if (!e || !sp || !recon || !source || !skip8 || !mse || !decide) {
-        set_error("svt_b200_engine_cdef_frame: null argument");
+    if (!e || !sp || !recon || !source || !skip8 || !mse || !decide || recon->width != source->width ||
+        recon->height != source->height || recon->bit_depth != source->bit_depth) {
+        set_error("svt_b200_engine_cdef_frame: bad argument");
         return SVT_B200_ERR_ARG;
     }
     DeviceGuard dg(e->device);
+    int rc = ensure_filt(e, recon->width, recon->height, recon->bit_depth, sp->mi_rows, sp->mi_cols);
+    if (rc != SVT_B200_OK) return rc;
+    const FiltGeom &g = e->fg;
+    const int nvfb = (sp->mi_rows + 15) / 16, nhfb = (sp->mi_cols + 15) / 16, nfb = nvfb * nhfb;
+    const size_t b_skip = (size_t)((sp->mi_rows + 1) / 2) * skip_stride, b_mse = (size_t)2 * nfb * 64 * 8;
+    if (al256(b_skip) > g.skip || (size_t)nfb > g.nfb) {
+        set_error("svt_b200_engine_cdef_frame: skip map / filter-block count larger than the sequence geometry");
+        return SVT_B200_ERR_ARG;
+    }
     FiltSlot *s = acquire(e, e->filt);
-    int rc;
     do {
-        const int nvfb = (sp->mi_rows + 15) / 16, nhfb = (sp->mi_cols + 15) / 16, nfb = nvfb * nhfb;
-        const size_t b_skip = (size_t)((sp->mi_rows + 1) / 2) * skip_stride, b_mse = (size_t)2 * nfb * 64 * 8;
-        auto al = [](size_t v) { return (v + 255) & ~(size_t)255; };
-        const size_t o_mse = al(b_skip), o_idx = o_mse + al(b_mse);
-        if ((rc = dev_frame(&s->recon, recon)) != SVT_B200_OK) break;
-        if ((rc = dev_frame(&s->out, recon)) != SVT_B200_OK) break;
-        if ((rc = dev_frame(&s->source, source)) != SVT_B200_OK) break;
-        if ((rc = grow_dev(&s->misc, &s->misc_cap, o_idx + al((size_t)nfb))) != SVT_B200_OK) break;
-        if ((rc = grow_pin(&s->pin, &s->pin_cap, al(b_mse) + al((size_t)nfb))) != SVT_B200_OK) break;
-        if (cudaMemcpyAsync(s->misc, skip8, b_skip, cudaMemcpyHostToDevice, s->st) != cudaSuccess) {
-            set_error("engine: skip-map upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-            rc = SVT_B200_ERR_CUDA;
-            break;
+        uint8_t *d_skip = s->misc, *d_mse = s->misc + g.skip, *d_idx = d_mse + g.mse;
+        uint8_t *h_skip = s->pin_small, *h_mse = h_skip + g.skip, *h_idx = h_mse + g.mse;
+        pack_frame(e, s->pin_a, recon);
+        pack_frame(e, s->pin_b, source);
+        memcpy(h_skip, skip8, b_skip);
+        {
+            Lap lap(e->stats.ns_issue);
+            if (cudaMemcpyAsync(d_skip, h_skip, b_skip, cudaMemcpyHostToDevice, s->st) != cudaSuccess) {
+                set_error("engine: skip-map upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = SVT_B200_ERR_CUDA;
+                break;
+            }
+            if ((rc = copy_packed(e, &s->recon, s->pin_a, cudaMemcpyHostToDevice, s->st)) != SVT_B200_OK) break;
+            if ((rc = copy_packed(e, &s->source, s->pin_b, cudaMemcpyHostToDevice, s->st)) != SVT_B200_OK) break;
+            if ((rc = svt_b200_cdef_search(sp, &s->recon, &s->source, d_skip, skip_stride, (uint64_t *)d_mse, s->st)) != SVT_B200_OK)
+                break;
+            if (cudaMemcpyAsync(h_mse, d_mse, b_mse, cudaMemcpyDeviceToHost, s->st) != cudaSuccess) {
+                rc = SVT_B200_ERR_CUDA;
+                break;
+            }
         }
-        if ((rc = copy_frame(e, &s->recon.f, recon, cudaMemcpyHostToDevice, s->st)) != SVT_B200_OK) break;
-        if ((rc = copy_frame(e, &s->source.f, source, cudaMemcpyHostToDevice, s->st)) != SVT_B200_OK) break;
-        if ((rc = svt_b200_cdef_search(sp, &s->recon.f, &s->source.f, s->misc, skip_stride, (uint64_t *)(s->misc + o_mse), s->st)) !=
-            SVT_B200_OK)
-            break;
-        if (cudaMemcpyAsync(s->pin, s->misc + o_mse, b_mse, cudaMemcpyDeviceToHost, s->st) != cudaSuccess ||
-            cudaStreamSynchronize(s->st) != cudaSuccess) {
+        if (timed_sync(e, s->st) != cudaSuccess) {
             set_error("engine: CDEF search failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc = SVT_B200_ERR_CUDA;
             break;
         }
-        memcpy(mse, s->pin, b_mse);
+        memcpy(mse, h_mse, b_mse);
         // the strength decision (finish_cdef_search, EbEncCdef.c:1167) is the host's: it reads mse and fills the apply set
         SvtB200CdefApplyParams ap;
         memset(&ap, 0, sizeof(ap));
         ap.mi_rows = sp->mi_rows;
         ap.mi_cols = sp->mi_cols;
-        int8_t *idx = (int8_t *)(s->pin + al(b_mse));
+        int8_t *idx = (int8_t *)h_idx;
         memset(idx, -1, (size_t)nfb);
         const int apply = decide(user, mse, &ap, idx);
         e->stats.cdef_frames++;
         e->stats.h2d_bytes += b_skip;
         e->stats.d2h_bytes += b_mse;
         if (apply <= 0) {
-            rc = apply < 0 ? SVT_B200_ERR_ARG : SVT_B200_OK;
+            if (apply < 0) {
+                set_error("svt_b200_engine_cdef_frame: the strength-decision callback failed");
+                rc = SVT_B200_ERR_ARG;
+            }
             break;
         }
-        if (cudaMemcpyAsync(s->misc + o_idx, idx, (size_t)nfb, cudaMemcpyHostToDevice, s->st) != cudaSuccess) {
-            rc = SVT_B200_ERR_CUDA;
-            break;
+        {
+            Lap lap(e->stats.ns_issue);
+            if (cudaMemcpyAsync(d_idx, idx, (size_t)nfb, cudaMemcpyHostToDevice, s->st) != cudaSuccess) {
+                rc = SVT_B200_ERR_CUDA;
+                break;
+            }
+            if ((rc = svt_b200_cdef_apply(&ap, &s->recon, &s->out, d_skip, skip_stride, (const int8_t *)d_idx, s->st)) != SVT_B200_OK)
+                break;
+            if ((rc = copy_packed(e, &s->out, s->pin_a, cudaMemcpyDeviceToHost, s->st)) != SVT_B200_OK) break;
         }
-        if ((rc = svt_b200_cdef_apply(&ap, &s->recon.f, &s->out.f, s->misc, skip_stride, (const int8_t *)(s->misc + o_idx), s->st)) !=
-            SVT_B200_OK)
-            break;
-        if ((rc = copy_frame(e, recon, &s->out.f, cudaMemcpyDeviceToHost, s->st)) != SVT_B200_OK) break;
-        if (cudaStreamSynchronize(s->st) != cudaSuccess) {
+        if (timed_sync(e, s->st) != cudaSuccess) {
             set_error("engine: CDEF apply failed: %s", cudaGetErrorString(cudaGetLastError()));
             rc = SVT_B200_ERR_CUDA;
             break;
         }
+        unpack_frame(e, recon, s->pin_a);
     } while (0);
     if (rc != SVT_B200_OK) cudaStreamSynchronize(s->st);
     release(e, s);
