@@ -818,7 +818,10 @@ typedef struct SvtB200SubpelJob {
     uint8_t bw, bh;       /* block_size_wide / _high [bsize] */
     uint8_t ref;          /* index into refs[] */
     uint8_t reserved;
-    int16_t start_mv_row, start_mv_col; /* subpel_start_mv: the full-pel MV in 1/8 sample */
+    int16_t start_mv_row, start_mv_col; /* subpel_start_mv: the full-pel MV in 1/8 sample (multiples of 8; anything else is
+                                           rejected with besterr = -1, like a block that does not fit or ref >= n_ref_frames).
+                                           The reference's last_mv_search_list early-out (mcomp.c) is not modelled: pass jobs
+                                           as md_subpel_search does, with last_mv_search_list == NULL */
     int16_t ref_mv_row, ref_mv_col;     /* context_ptr->ref_mv (the MV the rate is measured from) */
     int16_t col_min, col_max, row_min, row_max; /* ms_params->mv_limits (svt_av1_set_subpel_mv_search_range, mcomp.h:124-138) */
 } SvtB200SubpelJob;

@@ -18,6 +18,16 @@
 
 #include "../include/svt_av1_b200.h"
 
+/* svt_av1_inv_txfm_add_cuda reads the reference's TxfmParam through a layout view (txfm.cu TxfmParamView: packed 1-byte
+ * TxType / TxSize enums, then int32 lossless, bd, is_hbd, a 1-byte TxSetType, int32 eob).  This file sees both headers:
+ * pin the layout at compile time so a build of the reference with other enum packing cannot be misread silently. */
+#include <stddef.h>
+_Static_assert(sizeof(((TxfmParam *)0)->tx_type) == 1 && sizeof(((TxfmParam *)0)->tx_size) == 1, "TxType / TxSize must be packed 1-byte enums");
+_Static_assert(offsetof(TxfmParam, tx_type) == 0 && offsetof(TxfmParam, tx_size) == 1, "TxfmParam: tx_type, tx_size first");
+_Static_assert(offsetof(TxfmParam, lossless) == 4 && offsetof(TxfmParam, bd) == 8 && offsetof(TxfmParam, is_hbd) == 12,
+               "TxfmParam: lossless / bd / is_hbd at 4 / 8 / 12");
+_Static_assert(offsetof(TxfmParam, eob) == 20 && sizeof(TxfmParam) == 24, "TxfmParam: eob at 20, 24 bytes");
+
 #define REFH_API __attribute__((visibility("default")))
 typedef void (*AnyFn)(void);
 #define MAX_SLOTS 256

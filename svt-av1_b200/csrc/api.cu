@@ -17,7 +17,25 @@ void set_error(const char *fmt, ...) {
     fprintf(stderr, "libsvtav1_b200: fatal CUDA error in %s: %s (no CPU fallback)\n", what, cudaGetErrorString(e));
     abort();
 }
+void ThreadCtx::drop() {
+    if (h) cudaFreeHost(h);
+    if (d) cudaFree(d);
+    if (stream) cudaStreamDestroy(stream);
+    h = d = nullptr;
+    stream = nullptr;
+    cap = 0;
+}
 void ThreadCtx::reserve(size_t bytes) {
+    int dev = 0;
+    SVTB_CUDA_FATAL(cudaGetDevice(&dev));
+    if (dev != device) { // this thread now serves another GPU: its stream and staging belong to the old one
+        if (device >= 0) {
+            cudaSetDevice(device);
+            drop();
+            cudaSetDevice(dev);
+        }
+        device = dev;
+    }
     if (!stream) SVTB_CUDA_FATAL(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
     if (bytes <= cap) return;
     size_t ncap = cap ? cap : (1u << 20);
@@ -30,9 +48,7 @@ void ThreadCtx::reserve(size_t bytes) {
 }
 ThreadCtx::~ThreadCtx() {
     // the CUDA context may already be gone at thread/process exit; ignore errors
-    if (h) cudaFreeHost(h);
-    if (d) cudaFree(d);
-    if (stream) cudaStreamDestroy(stream);
+    drop();
 }
 ThreadCtx &tls() {
     static thread_local ThreadCtx ctx;

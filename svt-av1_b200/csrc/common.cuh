@@ -50,9 +50,37 @@ struct ThreadCtx {
     uint8_t *h = nullptr; // pinned
     uint8_t *d = nullptr; // device
     size_t cap = 0;
+    int device = -1; // the device stream / d belong to: rebuilt when the calling thread's current device changes
     void reserve(size_t bytes);
+    void drop();
     ~ThreadCtx();
 };
+
+// Per-DEVICE one-time set-up (cudaFuncSetAttribute, occupancy queries and table uploads are per device, a process may
+// use several - svt_b200_set_device): `fn` runs once for the calling thread's current device, under a lock, and its
+// CUDA errors are fatal (no CPU fallback).  Usage: static PerDeviceOnce once; once.run([]{ ... });
+struct PerDeviceOnce {
+    std::atomic<int> done[64];
+    PerDeviceOnce() {
+        for (auto &d : done) d.store(0);
+    }
+    template <typename F>
+    void run(F fn) {
+        int dev = 0;
+        SVTB_CUDA_FATAL(cudaGetDevice(&dev));
+        dev &= 63;
+        if (done[dev].load(std::memory_order_acquire) == 2) return;
+        int expect = 0;
+        if (done[dev].compare_exchange_strong(expect, 1)) {
+            fn();
+            done[dev].store(2, std::memory_order_release);
+        } else {
+            while (done[dev].load(std::memory_order_acquire) != 2) {
+            } // another pipeline thread is setting this device up
+        }
+    }
+};
+#define SVTB_ATTR(kernel, bytes) SVTB_CUDA_FATAL(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes))
 ThreadCtx &tls();
 
 // ---- device helpers -------------------------------------------------------------------------------

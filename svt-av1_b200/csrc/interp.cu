@@ -670,22 +670,27 @@ int svt_b200_inter_predict(const SvtB200Frame *refs, int32_t n_ref_frames, const
     d.items = (uint32_t *)scratch + 64;
     d.cap = (int)std::min<size_t>((scratch_bytes - 256) / 4, (size_t)1 << 30);
     cudaStream_t st = (cudaStream_t)stream;
-    static int n_sm = 0;
+    // SM count and occupancy are per device (a process may drive several GPUs): cached per device ordinal
+    int dev = 0;
+    SVTB_CUDA_TRY(cudaGetDevice(&dev));
+    dev &= 63;
+    static std::atomic<int> n_sm_dev[64], occ_dev[64][2];
+    int n_sm = n_sm_dev[dev].load();
     if (!n_sm) {
-        int dev = 0;
-        SVTB_CUDA_TRY(cudaGetDevice(&dev));
         SVTB_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+        n_sm_dev[dev].store(n_sm);
     }
     SVTB_CUDA_TRY(cudaMemsetAsync(d.count, 0, 4, st));
-    static int occ[2] = {0, 0}; // resident CTAs per SM of the persistent kernel
     const int hb = d.bd > 8;
-    if (!occ[hb]) {
+    int occ = occ_dev[dev][hb].load(); // resident CTAs per SM of the persistent kernel
+    if (!occ) {
         if (hb)
-            SVTB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], inter_tiles_kernel<uint16_t>, INTER_NT, 0));
+            SVTB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, inter_tiles_kernel<uint16_t>, INTER_NT, 0));
         else
-            SVTB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], inter_tiles_kernel<uint8_t>, INTER_NT, 0));
+            SVTB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, inter_tiles_kernel<uint8_t>, INTER_NT, 0));
+        occ_dev[dev][hb].store(occ);
     }
-    const int g1 = (n_jobs + INTER_NT - 1) / INTER_NT, g2 = n_sm * std::max(occ[hb], 1);
+    const int g1 = (n_jobs + INTER_NT - 1) / INTER_NT, g2 = n_sm * std::max(occ, 1);
     if (d.bd == 8) {
         SVTB_LAUNCH(inter_expand_kernel<uint8_t>, g1, INTER_NT, 0, st, d);
         SVTB_LAUNCH(inter_tiles_kernel<uint8_t>, g2, INTER_NT, 0, st, d);

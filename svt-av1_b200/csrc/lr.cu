@@ -407,16 +407,16 @@ __global__ void __launch_bounds__(256) sgr_search_error_kernel(const __grid_cons
     if ((threadIdx.x & 31) == 0 && acc) atomicAdd(reinterpret_cast<unsigned long long *>(d.err + (size_t)unit * d.n_eps + ei), (unsigned long long)acc);
 }
 
-static bool g_lr_attr = false;
 static void lr_attrs() {
-    if (g_lr_attr) return;
-    cudaFuncSetAttribute(sgr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(wiener_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    cudaFuncSetAttribute(lr_frame_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, LR_SMEM);
-    cudaFuncSetAttribute(lr_frame_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, LR_SMEM);
-    cudaFuncSetAttribute(sgr_search_filter_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, LR_SMEM);
-    cudaFuncSetAttribute(sgr_search_filter_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, LR_SMEM);
-    g_lr_attr = true;
+    static PerDeviceOnce once;
+    once.run([] {
+        SVTB_ATTR(sgr_kernel, 96 * 1024);
+        SVTB_ATTR(wiener_kernel, 96 * 1024);
+        SVTB_ATTR(lr_frame_kernel<uint8_t>, LR_SMEM);
+        SVTB_ATTR(lr_frame_kernel<uint16_t>, LR_SMEM);
+        SVTB_ATTR(sgr_search_filter_kernel<uint8_t>, LR_SMEM);
+        SVTB_ATTR(sgr_search_filter_kernel<uint16_t>, LR_SMEM);
+    });
 }
 
 // The reference passes high-bit-depth planes as CONVERT_TO_BYTEPTR(ptr) (= ptr >> 1): undo it like CONVERT_TO_SHORTPTR

@@ -1375,15 +1375,15 @@ __global__ void fill32_kernel(uint32_t *p, int n, uint32_t v) {
     if (i < n) p[i] = v;
 }
 
-static bool g_attr_done = false;
 static void set_attrs() {
-    if (g_attr_done) return;
-    cudaFuncSetAttribute(hme_kernel_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, HME_SMEM_BYTES);
-    cudaFuncSetAttribute(hme_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HME_FAST_SMEM);
-    cudaFuncSetAttribute(fullpel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, FP_SMEM_BYTES);
-    cudaFuncSetAttribute(fullpel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, FP_SMEM_BYTES);
-    cudaFuncSetAttribute(sad_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    g_attr_done = true;
+    static PerDeviceOnce once;
+    once.run([] {
+        SVTB_ATTR(hme_kernel_generic, HME_SMEM_BYTES);
+        SVTB_ATTR(hme_kernel, HME_FAST_SMEM);
+        SVTB_ATTR(fullpel_kernel<true>, FP_SMEM_BYTES);
+        SVTB_ATTR(fullpel_kernel<false>, FP_SMEM_BYTES);
+        SVTB_ATTR(sad_loop_kernel, 200 * 1024);
+    });
 }
 
 // copy a w x h byte rectangle (row stride `stride`) into a tight buffer
@@ -1416,7 +1416,8 @@ int svt_b200_me_picture(const SvtB200MeParams *p, const SvtB200MePlanes *src,
     }
     // window sizes the staging budget was sized for (every preset of v0.8.6 at non-screen content fits)
     if (p->max_me_search_width > 256 || p->max_me_search_height > 256 ||
-        p->hme_level0_max_search_area_in_width_array[0] > 240 || p->hme_level0_max_search_area_in_height_array[0] > 240) {
+        std::max(p->hme_level0_max_search_area_in_width_array[0], p->hme_level0_max_search_area_in_width_array[1]) > 240 ||
+        std::max(p->hme_level0_max_search_area_in_height_array[0], p->hme_level0_max_search_area_in_height_array[1]) > 240) {
         set_error("svt_b200_me_picture: search area larger than the kernels are sized for");
         return SVT_B200_ERR_UNSUPPORTED;
     }
@@ -1465,12 +1466,16 @@ int svt_b200_me_picture(const SvtB200MeParams *p, const SvtB200MePlanes *src,
             const size_t win = (size_t)wpw * 4 * (sah - 1 + (bhh - 1) * k + 1);
             return 4 * win + (size_t)((bw + 3) / 4) * 4 * bhh;
         };
-        int w0 = p->hme_level0_search_area_in_width_array[0] * maxd, h0 = p->hme_level0_search_area_in_height_array[0] * maxd;
-        if (w0 > p->hme_level0_max_search_area_in_width_array[0]) w0 = p->hme_level0_max_search_area_in_width_array[0];
-        if (h0 > p->hme_level0_max_search_area_in_height_array[0]) h0 = p->hme_level0_max_search_area_in_height_array[0];
+        // the kernel indexes the per-region arrays with [rx] / [ry]: size for the largest region that is used
+        const int nrx = p->number_hme_search_region_in_width, nry = p->number_hme_search_region_in_height;
+        auto amax = [](const int32_t *a, int n) { return n > 1 ? std::max(a[0], a[1]) : a[0]; };
+        int w0 = amax(p->hme_level0_search_area_in_width_array, nrx) * maxd, h0 = amax(p->hme_level0_search_area_in_height_array, nry) * maxd;
+        const int w0m = amax(p->hme_level0_max_search_area_in_width_array, nrx), h0m = amax(p->hme_level0_max_search_area_in_height_array, nry);
+        if (w0 > w0m) w0 = w0m;
+        if (h0 > h0m) h0 = h0m;
         size_t a = level_bytes((w0 + 15) & ~15, h0, 16, 16);
-        size_t b = level_bytes((p->hme_level1_search_area_in_width_array[0] + 7) & ~7, p->hme_level1_search_area_in_height_array[0], 32, 32);
-        size_t c = level_bytes((p->hme_level2_search_area_in_width_array[0] + 7) & ~7, p->hme_level2_search_area_in_height_array[0], 64, 64);
+        size_t b = level_bytes((amax(p->hme_level1_search_area_in_width_array, nrx) + 7) & ~7, amax(p->hme_level1_search_area_in_height_array, nry), 32, 32);
+        size_t c = level_bytes((amax(p->hme_level2_search_area_in_width_array, nrx) + 7) & ~7, amax(p->hme_level2_search_area_in_height_array, nry), 64, 64);
         hme_need = a > b ? a : b;
         hme_need = hme_need > c ? hme_need : c;
         hme_need += 256;

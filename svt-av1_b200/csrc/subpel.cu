@@ -54,7 +54,7 @@ struct SubpelDev {
     int ref_stride[8];
     const SvtB200SubpelJob *jobs;
     SvtB200SubpelResult *results;
-    int n_jobs, max_w, max_h;
+    int n_jobs, max_w, max_h, n_refs;
 };
 
 constexpr int SP_NT_MAX = 128; // CTA size is a template parameter: 32 / 64 / 128 threads by the largest block of the batch
@@ -228,7 +228,11 @@ __global__ void __launch_bounds__(SP_NT) subpel_kernel(const __grid_constant__ S
     __shared__ int s_red[2 * MAX_BATCH * SP_NT_MAX / 32];
     const SvtB200SubpelJob j = d.jobs[blockIdx.x];
     const SvtB200SubpelParams &p = d.p;
-    if (j.bw > d.max_w || j.bh > d.max_h || j.bw < 4 || j.bh < 4 || ((j.bw | j.bh) & 3)) { // does not fit the window of this launch
+    // rejected (besterr = -1): blocks that do not fit the window of this launch, a start MV that is not full-pel (the staged
+    // window and the REACH arithmetic assume md_subpel_search's full-pel start, EbProductCodingLoop.c:2094) and a reference
+    // index outside the pictures that were passed
+    if (j.bw > d.max_w || j.bh > d.max_h || j.bw < 4 || j.bh < 4 || ((j.bw | j.bh) & 3) || ((j.start_mv_row | j.start_mv_col) & 7) ||
+        j.ref >= d.n_refs) {
         if (threadIdx.x == 0) d.results[blockIdx.x] = SvtB200SubpelResult{j.start_mv_row, j.start_mv_col, -1, -1, 0u};
         return;
     }
@@ -339,6 +343,7 @@ extern "C" int svt_b200_subpel_search(const SvtB200SubpelParams *p, const SvtB20
     d.p = *p;
     d.src = (const uint8_t *)src->y;
     d.src_stride = src->stride_y;
+    d.n_refs = n_ref_frames;
     for (int i = 0; i < n_ref_frames; i++) {
         if (refs[i].bit_depth != 8) {
             set_error("svt_b200_subpel_search: reference %d is not 8-bit", i);

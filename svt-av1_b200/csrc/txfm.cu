@@ -534,14 +534,14 @@ static int tx_grid(int tx_size, int n) {
     const int T = w > h ? w : h, bpc = TX_NT / T;
     return (n + bpc - 1) / bpc;
 }
-static bool g_tx_attr = false;
 static void tx_attrs() {
-    if (g_tx_attr) return;
-    cudaFuncSetAttribute(fwd_txfm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(inv_txfm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(encode_tu_kernel<uint8_t, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    cudaFuncSetAttribute(encode_tu_kernel<uint16_t, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-    g_tx_attr = true;
+    static PerDeviceOnce once;
+    once.run([] {
+        SVTB_ATTR(fwd_txfm_kernel, 64 * 1024);
+        SVTB_ATTR(inv_txfm_kernel, 64 * 1024);
+        SVTB_ATTR((encode_tu_kernel<uint8_t, -1>), 64 * 1024);
+        SVTB_ATTR((encode_tu_kernel<uint16_t, -1>), 64 * 1024);
+    });
 }
 
 // ---- host side of the drop-ins --------------------------------------------------------------------------------
