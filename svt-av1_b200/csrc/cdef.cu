@@ -463,8 +463,17 @@ struct CdefSearchGridDev {
 };
 
 constexpr int CDEF_COMPACT_NG = 20; // strength tables up to this size park the per-block sums for a compact distortion pass
+// Build variants measured in profiles/r2_cdef_search_build_variants.json: (256,3) / (256,2) launch bounds and a
+// force-inlined plane_search_grid remove most of the 304-456 B stack frame and are all SLOWER (1080p: 0.106 ms product,
+// 0.112-0.130 ms variants) - the kernel lives on 4 resident CTAs per SM hiding the constrain() ALU chains.
+#ifndef CDEF_SEARCH_MINB
+#define CDEF_SEARCH_MINB 4 // resident CTAs per SM the search kernel is compiled for (register cap 65536 / (256 * MINB))
+#endif
+#ifndef CDEF_SEARCH_INLINE
+#define CDEF_SEARCH_INLINE __noinline__
+#endif
 template <typename T, int BS, int NSEC, bool LUMA, bool kBorder>
-__device__ __noinline__ void plane_search_grid(const CdefSearchDev &d, const CdefGrid &g, const int16_t *in, int count,
+__device__ CDEF_SEARCH_INLINE void plane_search_grid(const CdefSearchDev &d, const CdefGrid &g, const int16_t *in, int count,
                                                   const uint8_t *s_by, const uint8_t *s_bx, const int8_t *s_dir, const int *s_var,
                                                   unsigned long long *s_mse, uint32_t *s_sums, int pli, int y0, int x0, int damping) {
     const int tid = threadIdx.x, lane = tid & 31;
@@ -633,7 +642,7 @@ __device__ __noinline__ void plane_search_grid(const CdefSearchDev &d, const Cde
 }
 
 template <typename T, int NSEC>
-__global__ void __launch_bounds__(NT, 4) cdef_search_grid_kernel(const __grid_constant__ CdefSearchGridDev gd) {
+__global__ void __launch_bounds__(NT, CDEF_SEARCH_MINB) cdef_search_grid_kernel(const __grid_constant__ CdefSearchGridDev gd) {
     __shared__ int16_t tile[68 * TS];
     __shared__ uint8_t s_by[64], s_bx[64];
     __shared__ int8_t s_dir[64];
@@ -724,6 +733,10 @@ struct CdefApplyDev {
     int nvfb, nhfb, coeff_shift;
 };
 
+// Tried: one CTA per 32x32 QUADRANT of the filter block (4x the CTAs, a quarter of the serial chain each): bit-exact but
+// slower (1080p 0.0428 vs 0.0409 ms, 2160p 10-bit 0.151 vs 0.110 ms; profiles/r2b_kernel_bench_filters.json vs
+// r2c_*): the rim samples and the per-quadrant set-up cost more than the shorter chain saves - the kernel is throughput
+// bound (12 taps x constrain() per sample), not latency bound.  One CTA per filter block kept.
 template <typename T>
 __global__ void __launch_bounds__(NT) cdef_apply_kernel(const __grid_constant__ CdefApplyDev d) {
     __shared__ int16_t tile[68 * TS];

@@ -177,6 +177,145 @@ __global__ void __launch_bounds__(256) dlf_pass_kernel(const __grid_constant__ D
         }
 }
 
+// ---- block-edge kernels (the fast path) ----------------------------------------------------------------------------
+// One thread per 4x4 unit's leading edge = its FOUR sample lines: the edge parameters are derived once per edge instead of
+// once per line, and the samples move as 32/64-bit words.
+//  * vertical edges : thread (unit column, unit row); per line one aligned 4-sample word either side of the edge (two
+//    for the 14-tap filter).  Only the samples a filter may change are stored, in the widest aligned pieces that do not
+//    touch a neighbouring edge's samples (a 4-tap edge 4 samples away owns x-4, x-3).
+//  * horizontal edges: thread = the unit's 4 columns, one 4-sample word per row, 128 B per warp and row; the rows a
+//    filter of this length may change are stored as whole words (no other edge of the pass writes them).
+// Needs 4-sample-aligned planes (base and stride multiples of 4 samples): every picture the engine allocates, and the
+// reference's EbPictureBufferDesc planes.  Anything else takes dlf_pass_kernel.
+template <typename T> struct Word4; // four samples
+template <> struct Word4<uint8_t> {
+    using W = uint32_t;
+    static __device__ __forceinline__ void unpack(W w, int *v) {
+        v[0] = w & 0xff, v[1] = (w >> 8) & 0xff, v[2] = (w >> 16) & 0xff, v[3] = w >> 24;
+    }
+    static __device__ __forceinline__ W pack(const int *v) { return (W)v[0] | ((W)v[1] << 8) | ((W)v[2] << 16) | ((W)v[3] << 24); }
+};
+template <> struct Word4<uint16_t> {
+    using W = uint2;
+    static __device__ __forceinline__ void unpack(W w, int *v) {
+        v[0] = w.x & 0xffff, v[1] = w.x >> 16, v[2] = w.y & 0xffff, v[3] = w.y >> 16;
+    }
+    static __device__ __forceinline__ W pack(const int *v) {
+        return make_uint2((uint32_t)v[0] | ((uint32_t)v[1] << 16), (uint32_t)v[2] | ((uint32_t)v[3] << 16));
+    }
+};
+template <typename T> __device__ __forceinline__ int lane_get(uint32_t w, int c) { return (w >> (8 * c)) & 0xff; }
+template <typename T> __device__ __forceinline__ int lane_get(uint2 w, int c) { return ((c < 2 ? w.x : w.y) >> (16 * (c & 1))) & 0xffff; }
+template <typename T> __device__ __forceinline__ void lane_set(uint32_t &w, int c, int v) {
+    w = (w & ~(0xffu << (8 * c))) | ((uint32_t)v << (8 * c));
+}
+template <typename T> __device__ __forceinline__ void lane_set(uint2 &w, int c, int v) {
+    uint32_t &h = c < 2 ? w.x : w.y;
+    h = (h & ~(0xffffu << (16 * (c & 1)))) | ((uint32_t)v << (16 * (c & 1)));
+}
+// samples a filter of this length may change on each side (filter4 / filter6: 2, filter8: 3, filter14: 6)
+__device__ __forceinline__ int mod_of(int len) { return len == 14 ? 6 : len == 8 ? 3 : 2; }
+
+template <typename T>
+__global__ void __launch_bounds__(256) dlf_vert_kernel(const __grid_constant__ DlfDev d, int planes) {
+    using WT = typename Word4<T>::W;
+    const int plane = (planes >> (2 * blockIdx.z)) & 3;
+    const int ss = plane ? 1 : 0;
+    const int pw = (d.p.mi_cols * 4) >> ss, ph = (d.p.mi_rows * 4) >> ss;
+    const int ux = blockIdx.x * 32 + (threadIdx.x & 31), uy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int x = ux * 4, y = uy * 4;
+    if (x >= pw || y >= ph || ux == 0) return;
+    int level = 0;
+    const int len = edge_params(d, plane, 1, x, y, level);
+    if (!len) return;
+    int bl, li, th;
+    thresholds(level, d.p.sharpness, bl, li, th);
+    T *row0 = reinterpret_cast<T *>(d.plane[plane]) + (size_t)y * d.stride[plane] + x;
+    const int rows = min(4, ph - y);
+    const bool wide = len == 14;
+    // all loads of the edge's four lines are issued before the first line is filtered (one memory round trip, not four)
+    WT w[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const T *row = row0 + (size_t)min(r, rows - 1) * d.stride[plane];
+        w[r][1] = *reinterpret_cast<const WT *>(row - 4);
+        w[r][2] = *reinterpret_cast<const WT *>(row);
+        if (wide) {
+            w[r][0] = *reinterpret_cast<const WT *>(row - 8);
+            w[r][3] = *reinterpret_cast<const WT *>(row + 4);
+        } else {
+            w[r][0] = w[r][3] = WT{};
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        if (r >= rows) break;
+        T *row = row0 + (size_t)r * d.stride[plane];
+        int px[16]; // samples x-8 .. x+7; lpf_sample works on px+1 (p6 = x-7 .. q6 = x+6)
+        Word4<T>::unpack(w[r][0], px);
+        Word4<T>::unpack(w[r][1], px + 4);
+        Word4<T>::unpack(w[r][2], px + 8);
+        Word4<T>::unpack(w[r][3], px + 12);
+        const int changed = lpf_sample(px + 1, len, bl, li, th, d.bd);
+        if (!changed) continue;
+        if (changed == 6) { // x-6 .. x+5: two samples, two words, two samples
+            row[-6] = (T)px[2], row[-5] = (T)px[3];
+            *reinterpret_cast<WT *>(row - 4) = Word4<T>::pack(px + 4);
+            *reinterpret_cast<WT *>(row) = Word4<T>::pack(px + 8);
+            row[4] = (T)px[12], row[5] = (T)px[13];
+        } else { // 2 or 3 samples each side: never the word's far samples (they may belong to the next edge)
+            if (changed == 3) row[-3] = (T)px[5], row[2] = (T)px[10];
+            row[-2] = (T)px[6], row[-1] = (T)px[7], row[0] = (T)px[8], row[1] = (T)px[9];
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dlf_horz_kernel(const __grid_constant__ DlfDev d, int planes) {
+    using WT = typename Word4<T>::W;
+    const int plane = (planes >> (2 * blockIdx.z)) & 3;
+    const int ss = plane ? 1 : 0;
+    const int pw = (d.p.mi_cols * 4) >> ss, ph = (d.p.mi_rows * 4) >> ss;
+    const int ux = blockIdx.x * 32 + (threadIdx.x & 31), uy = blockIdx.y * 8 + (threadIdx.x >> 5);
+    const int x = ux * 4, y = uy * 4;
+    if (x >= pw || y >= ph || uy == 0) return;
+    int level = 0;
+    const int len = edge_params(d, plane, 0, x, y, level);
+    if (!len) return;
+    int bl, li, th;
+    thresholds(level, d.p.sharpness, bl, li, th);
+    const ptrdiff_t st = d.stride[plane];
+    T *s = reinterpret_cast<T *>(d.plane[plane]) + (size_t)y * st + x;
+    const int n = taps_of(len), m = mod_of(len);
+    // the 14 rows stay packed (one word of 4 columns per row); a column is unpacked, filtered and its changed samples
+    // merged back into the words - 28 live registers instead of a 4 x 14 sample array (occupancy: ncu, profiles/)
+    WT up[7], dn[7]; // up[t] = row y-1-t, dn[t] = row y+t
+#pragma unroll
+    for (int t = 0; t < 7; t++) {
+        up[t] = t < n ? *reinterpret_cast<const WT *>(s - (ptrdiff_t)(t + 1) * st) : WT{};
+        dn[t] = t < n ? *reinterpret_cast<const WT *>(s + (ptrdiff_t)t * st) : WT{};
+    }
+    int any = 0;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        int px[14];
+#pragma unroll
+        for (int t = 0; t < 7; t++) px[6 - t] = lane_get<T>(up[t], c), px[7 + t] = lane_get<T>(dn[t], c);
+        const int changed = lpf_sample(px, len, bl, li, th, d.bd);
+        any |= changed;
+#pragma unroll
+        for (int t = 0; t < 6; t++)
+            if (t < changed) lane_set<T>(up[t], c, px[6 - t]), lane_set<T>(dn[t], c, px[7 + t]);
+    }
+    if (!any) return;
+#pragma unroll
+    for (int t = 0; t < 6; t++)
+        if (t < m) {
+            *reinterpret_cast<WT *>(s - (ptrdiff_t)(t + 1) * st) = up[t];
+            *reinterpret_cast<WT *>(s + (ptrdiff_t)t * st) = dn[t];
+        }
+}
+
 // drop-in: one 4-line edge segment staged as a 16 x 4 window (p7..q7 across, 4 lines)
 __global__ void lpf_edge_kernel(uint16_t *win, int len, int blimit, int limit, int thresh, int bd) {
     const int i = threadIdx.x;
@@ -288,7 +427,27 @@ static int dlf_frame_impl(const SvtB200DlfParams *p, const SvtB200Frame *frame, 
         max_w = std::max(max_w, (p->mi_cols * 4) >> ss);
         max_h = std::max(max_h, (p->mi_rows * 4) >> ss);
     }
+    // the block-edge kernels move 4-sample words: planes whose base / stride are 4-sample aligned (every EbPictureBufferDesc
+    // and every engine picture); other layouts take the line-per-thread kernel
+    const size_t wbytes = hbd ? 8 : 4;
+    const bool aligned = !getenv("SVT_B200_DLF_LINE_KERNEL") && ((uintptr_t)frame->y % wbytes) == 0 && ((uintptr_t)frame->cb % wbytes) == 0 &&
+        ((uintptr_t)frame->cr % wbytes) == 0 && frame->stride_y % 4 == 0 && frame->stride_c % 4 == 0;
     for (int vert = 1; vert >= 0 && n_planes; vert--) {
+        if (aligned) {
+            dim3 grid((max_w / 4 + 31) / 32, (max_h / 4 + 7) / 8, n_planes); // CTA = 32 x 8 units = 128 x 32 samples
+            if (vert) {
+                if (hbd)
+                    SVTB_LAUNCH(dlf_vert_kernel<uint16_t>, grid, 256, 0, st, d, planes);
+                else
+                    SVTB_LAUNCH(dlf_vert_kernel<uint8_t>, grid, 256, 0, st, d, planes);
+            } else {
+                if (hbd)
+                    SVTB_LAUNCH(dlf_horz_kernel<uint16_t>, grid, 256, 0, st, d, planes);
+                else
+                    SVTB_LAUNCH(dlf_horz_kernel<uint8_t>, grid, 256, 0, st, d, planes);
+            }
+            continue;
+        }
         const int nx = vert ? max_w / 4 : max_w, ny = vert ? max_h : max_h / 4;
         dim3 grid((nx + 255) / 256, ny, n_planes);
         if (hbd)

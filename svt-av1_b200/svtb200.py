@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsvtav1_b200.so")
+# SVTB200_LIB: an experimental build of the same library (kernel variants for tools/kernel_bench.py); default = the product
+LIB_PATH = os.environ.get("SVTB200_LIB") or os.path.join(_HERE, "libsvtav1_b200.so")
 
 ME_MAX_REFS, ME_LISTS, ME_PU, ME_MAX_MV, ME_MAX_CAND = 4, 2, 85, 7, 23
 
