@@ -494,6 +494,11 @@ typedef struct SvtB200DlfParams {
 SVT_B200_API int svt_b200_dlf_frame(const SvtB200DlfParams *p, const SvtB200Frame *frame,
                                     const SvtB200DlfMi *mi, void *stream);
 
+/* The same with the block levels taken from a level table instead of the lvl_* fields of the summary:
+ * lut = DEVICE uint8 [3][2][128] as svt_b200_lf_level_lut fills it (lfi_n->lvl[plane][seg][dir][ref][mode] indexed by lvl_class). */
+SVT_B200_API int svt_b200_dlf_frame_lut(const SvtB200DlfParams *p, const SvtB200Frame *frame, const SvtB200DlfMi *mi,
+                                        const uint8_t *lut, void *stream);
+
 /* What svt_av1_loop_filter_frame_init (EbDeblockingCommon.c:78-145) reads besides the four frame levels. */
 typedef struct SvtB200LfFrameInit {
     int32_t mode_ref_delta_enabled; /* lf->mode_ref_delta_enabled */
@@ -897,6 +902,14 @@ SVT_B200_API int svt_b200_engine_me_picture(SvtB200Engine *e, const SvtB200MePar
 /* svt_av1_loop_filter_frame (EbDeblockingFilter.c:711) on a HOST picture, in place; mi: host array. */
 SVT_B200_API int svt_b200_engine_dlf_frame(SvtB200Engine *e, const SvtB200DlfParams *p, const SvtB200Frame *frame,
                                            const SvtB200DlfMi *mi);
+
+/* dlf_kernel for loop_filter_mode >= 2 (presets <= 6; EbDlfProcess.c:186-216): svt_av1_pick_filter_level(FROM_FULL_IMAGE)
+ * followed by svt_av1_loop_filter_frame with the picked levels, on a HOST picture in place.  recon / source are uploaded
+ * once, every trial of the level search (one plane pass + SSE + plane restore) runs on the device, then the frame is
+ * deblocked with the result and read back.  levels_out: {filter_level[0], [1], u, v} for the frame header.
+ * mi: host array [mi_rows][mi_cols] (lvl_class is what is read).  pp->dlf.sharpness is ignored (the reference forces 0). */
+SVT_B200_API int svt_b200_engine_dlf_pick_frame(SvtB200Engine *e, const SvtB200LpfPickParams *pp, const SvtB200Frame *recon,
+                                                const SvtB200Frame *source, const SvtB200DlfMi *mi, int32_t levels_out[4]);
 
 /* The CDEF stage of cdef_kernel (EbCdefProcess.c:510-534) for one HOST picture: strength search of every 64x64 filter
  * block -> `mse` (host, [2][nfb][64], = pcs->mse_seg) -> `decide(user, mse, apply, fb_strength_idx)` on the calling

@@ -12,7 +12,8 @@ The hooks (all behind `#if SVT_CUDA`, all inert unless the environment sets SVT_
   EbMotionEstimationProcess.c   the SB loop (:831-965) becomes the else-branch of svt_cuda_me_segment(...)
   EbCodingLoop.c                the per-SB deblocking of loop_filter_mode 1 (:3785-3795) is skipped when the frame is
                                 deblocked on the GPU in dlf_kernel instead
-  EbDlfProcess.c                svt_av1_loop_filter_frame (:216) -> svt_cuda_dlf_frame; loop_filter_mode 1 pictures are
+  EbDlfProcess.c                svt_av1_pick_filter_level(FULL_IMAGE) + svt_av1_loop_filter_frame (:203-216) ->
+                                svt_cuda_dlf_pick_frame / svt_cuda_dlf_frame; loop_filter_mode 1 pictures are
                                 deblocked here, frame level, before the pre-CDEF preparation (:220)
   EbCdefProcess.c               cdef_seg_search of each segment (:510-515) skipped, and finish_cdef_search +
                                 svt_av1_cdef_frame (:521-534) replaced by svt_cuda_cdef_picture for the whole picture
@@ -68,6 +69,16 @@ HOOKS = [
               "            else\n"
               "#endif\n"
               "            svt_av1_loop_filter_frame(recon_buffer, pcs_ptr, 0, 3);\n"),
+    dict(file="Source/Lib/Encoder/Codec/EbDlfProcess.c",
+         anchor="            svt_av1_pick_filter_level(\n                context_ptr,\n"
+                "                (EbPictureBufferDesc *)pcs_ptr->parent_pcs_ptr->enhanced_picture_ptr,\n"
+                "                pcs_ptr,\n                LPF_PICK_FROM_FULL_IMAGE);\n",
+         after=None, action="insert_before",
+         text="#if SVT_CUDA\n"
+              "            /* level search + deblocking as one GPU call (the svt_av1_loop_filter_frame hook below then returns) */\n"
+              "            if (svt_cuda_dlf_applies(pcs_ptr, scs_ptr) && svt_cuda_dlf_pick_frame(pcs_ptr, scs_ptr, recon_buffer)) {\n"
+              "            } else\n"
+              "#endif\n"),
     dict(file="Source/Lib/Encoder/Codec/EbDlfProcess.c",
          anchor="        //pre-cdef prep\n", after=None, action="insert_before",
          text="#if SVT_CUDA\n"

@@ -327,25 +327,10 @@ static void flatten_mi(SvtB200DlfMi *f, const MbModeInfo *mbmi, const LoopFilter
     f->pad[0] = f->pad[1] = 0;
 }
 
-/* Deblocks the reconstruction of pcs in place on the GPU (only called when svt_cuda_dlf_applies).  The caller has run
- * svt_av1_loop_filter_init, svt_av1_pick_filter_level and - as svt_av1_loop_filter_frame does first (:724) -
- * svt_av1_loop_filter_frame_init(frm_hdr, lf_info, 0, 3) is run here. */
-void svt_cuda_dlf_frame(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr, EbPictureBufferDesc *recon_buffer) {
+static SvtB200DlfMi *flatten_picture(PictureControlSet *pcs_ptr) {
     PictureParentControlSet *ppcs    = pcs_ptr->parent_pcs_ptr;
-    FrameHeader *            frm_hdr = &ppcs->frm_hdr;
-    const int is_16bit = scs_ptr->static_config.encoder_bit_depth > EB_8BIT || scs_ptr->static_config.is_16bit_pipeline;
-    if (!frm_hdr->loop_filter_params.filter_level[0] && !frm_hdr->loop_filter_params.filter_level[1]) return;
-    if (!recon_buffer) { /* the selection of dlf_kernel (EbDlfProcess.c:180-193) */
-        if (ppcs->is_used_as_reference_flag == EB_TRUE)
-            recon_buffer = is_16bit ? ((EbReferenceObject *)ppcs->reference_picture_wrapper_ptr->object_ptr)->reference_picture16bit
-                                    : ((EbReferenceObject *)ppcs->reference_picture_wrapper_ptr->object_ptr)->reference_picture;
-        else
-            recon_buffer = is_16bit ? pcs_ptr->recon_picture16bit_ptr : pcs_ptr->recon_picture_ptr;
-    }
-    svt_av1_loop_filter_frame_init(frm_hdr, &ppcs->lf_info, 0, 3);
-    const int64_t  t0      = g_prof ? now_ns() : 0;
-    const int      mi_rows = ppcs->av1_cm->mi_rows, mi_cols = ppcs->av1_cm->mi_cols;
-    const size_t   n       = (size_t)mi_rows * mi_cols;
+    const int                mi_rows = ppcs->av1_cm->mi_rows, mi_cols = ppcs->av1_cm->mi_cols;
+    const size_t             n       = (size_t)mi_rows * mi_cols;
     if (t_mi_cap < n) {
         free(t_mi);
         t_mi     = (SvtB200DlfMi *)malloc(n * sizeof(SvtB200DlfMi));
@@ -354,8 +339,8 @@ void svt_cuda_dlf_frame(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr,
     }
     const LoopFilterInfoN *lfi_n = &ppcs->lf_info;
     for (int r = 0; r < mi_rows; r++) {
-        ModeInfo **   row  = pcs_ptr->mi_grid_base + (size_t)r * pcs_ptr->mi_stride;
-        SvtB200DlfMi *out  = t_mi + (size_t)r * mi_cols;
+        ModeInfo **       row  = pcs_ptr->mi_grid_base + (size_t)r * pcs_ptr->mi_stride;
+        SvtB200DlfMi *    out  = t_mi + (size_t)r * mi_cols;
         const MbModeInfo *prev = NULL;
         for (int c = 0; c < mi_cols; c++) {
             const MbModeInfo *m = &row[c]->mbmi;
@@ -369,6 +354,36 @@ void svt_cuda_dlf_frame(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr,
             prev = m;
         }
     }
+    return t_mi;
+}
+
+static EbPictureBufferDesc *recon_of(PictureControlSet *pcs_ptr, int is_16bit) { /* the selection of dlf_kernel (EbDlfProcess.c:180-193) */
+    PictureParentControlSet *ppcs = pcs_ptr->parent_pcs_ptr;
+    if (ppcs->is_used_as_reference_flag == EB_TRUE)
+        return is_16bit ? ((EbReferenceObject *)ppcs->reference_picture_wrapper_ptr->object_ptr)->reference_picture16bit
+                        : ((EbReferenceObject *)ppcs->reference_picture_wrapper_ptr->object_ptr)->reference_picture;
+    return is_16bit ? pcs_ptr->recon_picture16bit_ptr : pcs_ptr->recon_picture_ptr;
+}
+
+static __thread const PictureControlSet *t_filtered = NULL; /* svt_cuda_dlf_pick_frame already deblocked this picture */
+
+/* Deblocks the reconstruction of pcs in place on the GPU (only called when svt_cuda_dlf_applies).  The caller has run
+ * svt_av1_loop_filter_init, svt_av1_pick_filter_level and - as svt_av1_loop_filter_frame does first (:724) -
+ * svt_av1_loop_filter_frame_init(frm_hdr, lf_info, 0, 3) is run here. */
+void svt_cuda_dlf_frame(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr, EbPictureBufferDesc *recon_buffer) {
+    PictureParentControlSet *ppcs    = pcs_ptr->parent_pcs_ptr;
+    FrameHeader *            frm_hdr = &ppcs->frm_hdr;
+    const int is_16bit = scs_ptr->static_config.encoder_bit_depth > EB_8BIT || scs_ptr->static_config.is_16bit_pipeline;
+    if (t_filtered == pcs_ptr) { /* level search and filtering were one GPU call */
+        t_filtered = NULL;
+        return;
+    }
+    if (!frm_hdr->loop_filter_params.filter_level[0] && !frm_hdr->loop_filter_params.filter_level[1]) return;
+    if (!recon_buffer) recon_buffer = recon_of(pcs_ptr, is_16bit);
+    svt_av1_loop_filter_frame_init(frm_hdr, &ppcs->lf_info, 0, 3);
+    const int64_t t0      = g_prof ? now_ns() : 0;
+    const int     mi_rows = ppcs->av1_cm->mi_rows, mi_cols = ppcs->av1_cm->mi_cols;
+    SvtB200DlfMi *mi      = flatten_picture(pcs_ptr);
     SvtB200DlfParams p;
     memset(&p, 0, sizeof(p));
     p.mi_rows         = mi_rows;
@@ -383,9 +398,58 @@ void svt_cuda_dlf_frame(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr,
     p.plane_end       = 3;
     SvtB200Frame f;
     host_frame(&f, recon_buffer, is_16bit, mi_cols * 4, mi_rows * 4);
-    int rc = svt_b200_engine_dlf_frame(g_engine, &p, &f, t_mi);
+    int rc = svt_b200_engine_dlf_frame(g_engine, &p, &f, mi);
     if (rc) die("svt_b200_engine_dlf_frame", rc);
     if (g_prof) stat_add(1, ST_DLF, t0);
+}
+
+/* svt_av1_pick_filter_level(LPF_PICK_FROM_FULL_IMAGE) + svt_av1_loop_filter_frame of dlf_kernel (loop_filter_mode >= 2,
+ * EbDlfProcess.c:186-216) as ONE GPU call: the level search (search_filter_level x3: luma, U, V; every trial = filter a
+ * plane + SSE against the source + restore) and the final deblocking share one upload of the picture.  Returns 0 when the
+ * C path has to run (picture size not a multiple of 8: the SSE and the filter then cover different areas). */
+int svt_cuda_dlf_pick_frame(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr, EbPictureBufferDesc *recon_buffer) {
+    PictureParentControlSet *ppcs    = pcs_ptr->parent_pcs_ptr;
+    FrameHeader *            frm_hdr = &ppcs->frm_hdr;
+    struct LoopFilter *      lf      = &frm_hdr->loop_filter_params;
+    const int is_16bit = scs_ptr->static_config.encoder_bit_depth > EB_8BIT || scs_ptr->static_config.is_16bit_pipeline;
+    const int mi_rows = ppcs->av1_cm->mi_rows, mi_cols = ppcs->av1_cm->mi_cols;
+    EbPictureBufferDesc *input = is_16bit ? pcs_ptr->input_frame16bit : (EbPictureBufferDesc *)ppcs->enhanced_picture_ptr;
+    if (input->width != mi_cols * 4 || input->height != mi_rows * 4) return 0;
+    const int64_t t0 = g_prof ? now_ns() : 0;
+    if (!recon_buffer) recon_buffer = recon_of(pcs_ptr, is_16bit);
+    lf->sharpness_level = 0; /* :1202 */
+    SvtB200LpfPickParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.dlf.mi_rows = mi_rows, pp.dlf.mi_cols = mi_cols, pp.dlf.mi_stride = mi_cols;
+    pp.dlf.plane_start = 0, pp.dlf.plane_end = 3;
+    pp.init.mode_ref_delta_enabled = lf->mode_ref_delta_enabled;
+    for (int i = 0; i < 8; i++) pp.init.ref_deltas[i] = lf->ref_deltas[i];
+    for (int i = 0; i < 2; i++) pp.init.mode_deltas[i] = lf->mode_deltas[i];
+    pp.init.segmentation_enabled = frm_hdr->segmentation_params.segmentation_enabled;
+    for (int sg = 0; sg < 8; sg++) {
+        pp.init.seg_feature_mask[sg] = 0;
+        for (int f = 0; f < 8; f++) {
+            if (frm_hdr->segmentation_params.feature_enabled[sg][f]) pp.init.seg_feature_mask[sg] |= (uint8_t)(1u << f);
+            pp.init.seg_feature_data[sg][f] = frm_hdr->segmentation_params.feature_data[sg][f];
+        }
+    }
+    pp.method           = 0; /* LPF_PICK_FROM_FULL_IMAGE */
+    pp.loop_filter_mode = ppcs->loop_filter_mode;
+    pp.tx_mode_only_4x4 = frm_hdr->tx_mode == ONLY_4X4;
+    pp.last_level[0] = lf->filter_level[0], pp.last_level[1] = lf->filter_level[1];
+    pp.last_level[2] = lf->filter_level_u, pp.last_level[3] = lf->filter_level_v;
+    SvtB200DlfMi *mi = flatten_picture(pcs_ptr); /* only lvl_class is read on this path */
+    SvtB200Frame  rec, src;
+    host_frame(&rec, recon_buffer, is_16bit, mi_cols * 4, mi_rows * 4);
+    host_frame(&src, input, is_16bit, mi_cols * 4, mi_rows * 4);
+    int32_t lv[4];
+    int     rc = svt_b200_engine_dlf_pick_frame(g_engine, &pp, &rec, &src, mi, lv);
+    if (rc) die("svt_b200_engine_dlf_pick_frame", rc);
+    lf->filter_level[0] = lv[0], lf->filter_level[1] = lv[1], lf->filter_level_u = lv[2], lf->filter_level_v = lv[3];
+    svt_av1_loop_filter_frame_init(frm_hdr, &ppcs->lf_info, 0, 3); /* what svt_av1_loop_filter_frame leaves behind */
+    t_filtered = pcs_ptr;
+    if (g_prof) stat_add(1, ST_DLF, t0);
+    return 1;
 }
 
 /* ===================================================================================================================

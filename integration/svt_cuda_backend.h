@@ -22,6 +22,7 @@ int svt_cuda_me_segment(MotionEstimationContext_t *context_ptr, PictureParentCon
                         EbPictureBufferDesc *input_picture_ptr, uint32_t segment_index, uint32_t x_sb_start_index,
                         uint32_t x_sb_end_index, uint32_t y_sb_start_index, uint32_t y_sb_end_index);
 void svt_cuda_dlf_frame(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr, EbPictureBufferDesc *recon_buffer);
+int  svt_cuda_dlf_pick_frame(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr, EbPictureBufferDesc *recon_buffer);
 void svt_cuda_cdef_picture(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr);
 
 /* SVT_CUDA_PROFILE=1: wall time the stage threads spend in each stage, CPU path included (stage: 0 me, 1 dlf, 2 cdef) */

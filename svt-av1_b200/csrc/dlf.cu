@@ -462,6 +462,14 @@ static int dlf_frame_impl(const SvtB200DlfParams *p, const SvtB200Frame *frame, 
 int svt_b200_dlf_frame(const SvtB200DlfParams *p, const SvtB200Frame *frame, const SvtB200DlfMi *mi, void *stream) {
     return dlf_frame_impl(p, frame, mi, nullptr, stream);
 }
+int svt_b200_dlf_frame_lut(const SvtB200DlfParams *p, const SvtB200Frame *frame, const SvtB200DlfMi *mi, const uint8_t *lut,
+                           void *stream) {
+    if (!lut) {
+        set_error("svt_b200_dlf_frame_lut: null level table");
+        return SVT_B200_ERR_ARG;
+    }
+    return dlf_frame_impl(p, frame, mi, lut, stream);
+}
 
 // svt_av1_loop_filter_frame_init (EbDeblockingCommon.c:78-145): lvl[plane][seg][dir][ref][mode] as lut[plane][dir][class]
 int svt_b200_lf_level_lut(const SvtB200LfFrameInit *init, const int32_t levels[4], uint8_t lut[3][2][128]) {

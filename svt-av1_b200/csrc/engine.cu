@@ -22,6 +22,7 @@
 #include <algorithm>
 #include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "common.cuh"
@@ -230,7 +231,7 @@ int ensure_filt(SvtB200Engine *e, int w, int h, int bd, int mi_rows, int mi_cols
     g.skip = al256((size_t)((mi_rows + 1) / 2) * ((((mi_cols + 1) / 2) + 15) & ~15));
     g.mse = al256(g.nfb * 2 * 64 * 8);
     g.small = g.skip + g.mse + al256(g.nfb);
-    g.misc = std::max(g.mi, g.small);
+    g.misc = std::max(g.mi + 4096, g.small); // + the level search's scratch (level table, SSE accumulator)
     const size_t dev_total = (size_t)kFiltSlots * (3 * g.frame + g.misc);
     const size_t pin_b = std::max(g.packed, g.mi);
     const size_t pin_total = (size_t)kFiltSlots * (g.packed + pin_b + g.small);
@@ -261,6 +262,24 @@ int ensure_filt(SvtB200Engine *e, int w, int h, int bd, int mi_rows, int mi_cols
     e->fg = g;
     e->filt_ready = true;
     return SVT_B200_OK;
+}
+
+// memcpy split over four threads above 4 MB (see run_copies below)
+void par_memcpy(void *dst, const void *src, size_t n) {
+    if (n <= (4u << 20)) {
+        memcpy(dst, src, n);
+        return;
+    }
+    const size_t q = ((n / 4) + 4095) & ~(size_t)4095;
+    std::thread th[3];
+    for (int t = 1; t < 4; t++) {
+        const size_t o = q * t, len = o >= n ? 0 : std::min(q, n - o);
+        th[t - 1] = std::thread([=] {
+            if (len) memcpy((uint8_t *)dst + o, (const uint8_t *)src + o, len);
+        });
+    }
+    memcpy(dst, src, std::min(q, n));
+    for (auto &t : th) t.join();
 }
 
 // Make the three planes of `pic` resident and ordered before later work on the slot's stream.  users++ on return.
@@ -320,7 +339,7 @@ int plane_acquire(SvtB200Engine *e, MeSlot *s, const SvtB200MeParams *p, const S
         size_t bytes = 0;
         if (rc == SVT_B200_OK) {
             Lap lap(e->stats.ns_host_copy);
-            memcpy(s->pin_up, pic->full, g.nb[0]);
+            par_memcpy(s->pin_up, pic->full, g.nb[0]);
             bytes = g.nb[0];
             if (!gen) {
                 memcpy(s->pin_up + al256(g.nb[0]), pic->quarter, g.nb[1]);
@@ -364,26 +383,50 @@ void plane_release(SvtB200Engine *e, PlaneEntry **ents, int n) {
     e->cv.notify_all();
 }
 
-// host picture <-> packed (tight rows: y, cb, cr) pinned staging
-void pack_frame(SvtB200Engine *e, uint8_t *pin, const SvtB200Frame *h) {
+// host picture <-> packed (tight rows: y, cb, cr) pinned staging.  A 2160p 10-bit picture is 25 MB and one pipeline
+// thread copies it at 2-3 GB/s (the picture pools of the encoder are spread over both sockets: profiles/r2_encoder_2160p_*),
+// so pictures above 4 MB are split by rows over four threads (the host has 128 hardware threads and ~10 busy ones).
+struct RowCopy {
+    uint8_t *dst;
+    const uint8_t *src;
+    size_t dst_pitch, src_pitch, bytes;
+    int rows;
+};
+void copy_rows(const RowCopy &c, int r0, int r1) {
+    for (int y = r0; y < r1; y++) memcpy(c.dst + (size_t)y * c.dst_pitch, c.src + (size_t)y * c.src_pitch, c.bytes);
+}
+void run_copies(SvtB200Engine *e, const RowCopy (&c)[3]) {
     Lap lap(e->stats.ns_host_copy);
+    size_t total = 0;
+    for (const RowCopy &k : c) total += k.bytes * k.rows;
+    const int nt = total > (4u << 20) ? 4 : 1;
+    auto part = [&c, nt](int t) {
+        for (const RowCopy &k : c) copy_rows(k, (int)((int64_t)k.rows * t / nt), (int)((int64_t)k.rows * (t + 1) / nt));
+    };
+    if (nt == 1) {
+        part(0);
+        return;
+    }
+    std::thread th[3];
+    for (int t = 1; t < nt; t++) th[t - 1] = std::thread(part, t);
+    part(0);
+    for (int t = 1; t < nt; t++) th[t - 1].join();
+}
+void pack_frame(SvtB200Engine *e, uint8_t *pin, const SvtB200Frame *h) {
     const int bps = h->bit_depth > 8 ? 2 : 1, cw = (h->width + 1) >> 1, ch = (h->height + 1) >> 1;
     const size_t rw = (size_t)h->width * bps, rc = (size_t)cw * bps;
-    for (int y = 0; y < h->height; y++) memcpy(pin + y * rw, (const uint8_t *)h->y + (size_t)y * h->stride_y * bps, rw);
-    pin += rw * h->height;
-    for (int y = 0; y < ch; y++) memcpy(pin + y * rc, (const uint8_t *)h->cb + (size_t)y * h->stride_c * bps, rc);
-    pin += rc * ch;
-    for (int y = 0; y < ch; y++) memcpy(pin + y * rc, (const uint8_t *)h->cr + (size_t)y * h->stride_c * bps, rc);
+    const RowCopy c[3] = {{pin, (const uint8_t *)h->y, rw, (size_t)h->stride_y * bps, rw, h->height},
+                          {pin + rw * h->height, (const uint8_t *)h->cb, rc, (size_t)h->stride_c * bps, rc, ch},
+                          {pin + rw * h->height + rc * ch, (const uint8_t *)h->cr, rc, (size_t)h->stride_c * bps, rc, ch}};
+    run_copies(e, c);
 }
 void unpack_frame(SvtB200Engine *e, const SvtB200Frame *h, const uint8_t *pin) {
-    Lap lap(e->stats.ns_host_copy);
     const int bps = h->bit_depth > 8 ? 2 : 1, cw = (h->width + 1) >> 1, ch = (h->height + 1) >> 1;
     const size_t rw = (size_t)h->width * bps, rc = (size_t)cw * bps;
-    for (int y = 0; y < h->height; y++) memcpy((uint8_t *)h->y + (size_t)y * h->stride_y * bps, pin + y * rw, rw);
-    pin += rw * h->height;
-    for (int y = 0; y < ch; y++) memcpy((uint8_t *)h->cb + (size_t)y * h->stride_c * bps, pin + y * rc, rc);
-    pin += rc * ch;
-    for (int y = 0; y < ch; y++) memcpy((uint8_t *)h->cr + (size_t)y * h->stride_c * bps, pin + y * rc, rc);
+    const RowCopy c[3] = {{(uint8_t *)h->y, pin, (size_t)h->stride_y * bps, rw, rw, h->height},
+                          {(uint8_t *)h->cb, pin + rw * h->height, (size_t)h->stride_c * bps, rc, rc, ch},
+                          {(uint8_t *)h->cr, pin + rw * h->height + rc * ch, (size_t)h->stride_c * bps, rc, rc, ch}};
+    run_copies(e, c);
 }
 // packed pinned staging <-> device picture (three 2-D copies; both sides page-locked / device: pure DMA, asynchronous)
 int copy_packed(SvtB200Engine *e, const SvtB200Frame *dev, uint8_t *pin, cudaMemcpyKind kind, cudaStream_t st) {
@@ -575,7 +618,7 @@ int svt_b200_engine_dlf_frame(SvtB200Engine *e, const SvtB200DlfParams *p, const
         pack_frame(e, s->pin_a, frame);
         {
             Lap lap(e->stats.ns_host_copy);
-            memcpy(s->pin_b, mi, b_mi);
+            par_memcpy(s->pin_b, mi, b_mi);
         }
         {
             Lap lap(e->stats.ns_issue);
@@ -594,6 +637,76 @@ int svt_b200_engine_dlf_frame(SvtB200Engine *e, const SvtB200DlfParams *p, const
             break;
         }
         unpack_frame(e, frame, s->pin_a);
+        e->stats.dlf_frames++;
+        e->stats.h2d_bytes += b_mi;
+    } while (0);
+    if (rc != SVT_B200_OK) cudaStreamSynchronize(s->st);
+    release(e, s);
+    return rc;
+}
+
+int svt_b200_engine_dlf_pick_frame(SvtB200Engine *e, const SvtB200LpfPickParams *pp, const SvtB200Frame *recon,
+                                   const SvtB200Frame *source, const SvtB200DlfMi *mi, int32_t levels_out[4]) {
+    if (!e || !pp || !recon || !source || !mi || !levels_out || pp->dlf.mi_stride != pp->dlf.mi_cols || recon->width != source->width ||
+        recon->height != source->height || recon->bit_depth != source->bit_depth) {
+        set_error("svt_b200_engine_dlf_pick_frame: bad argument");
+        return SVT_B200_ERR_ARG;
+    }
+    DeviceGuard dg(e->device);
+    int rc = ensure_filt(e, recon->width, recon->height, recon->bit_depth, pp->dlf.mi_rows, pp->dlf.mi_cols);
+    if (rc != SVT_B200_OK) return rc;
+    const FiltGeom &g = e->fg;
+    const size_t b_mi = (size_t)pp->dlf.mi_rows * pp->dlf.mi_cols * sizeof(SvtB200DlfMi);
+    if (b_mi > g.mi) {
+        set_error("svt_b200_engine_dlf_pick_frame: mode-info array larger than the sequence geometry");
+        return SVT_B200_ERR_ARG;
+    }
+    FiltSlot *s = acquire(e, e->filt);
+    do {
+        uint8_t *d_scratch = s->misc + g.mi; // 768 B level table + the SSE accumulator of the search, then the final table
+        pack_frame(e, s->pin_a, recon);
+        {
+            Lap lap(e->stats.ns_issue);
+            if ((rc = copy_packed(e, &s->recon, s->pin_a, cudaMemcpyHostToDevice, s->st)) != SVT_B200_OK) break;
+        }
+        // pin_b holds the mode-info array first, then (after its upload completed) the packed source picture
+        {
+            Lap lap(e->stats.ns_host_copy);
+            par_memcpy(s->pin_b, mi, b_mi);
+        }
+        if (cudaMemcpyAsync(s->misc, s->pin_b, b_mi, cudaMemcpyHostToDevice, s->st) != cudaSuccess || timed_sync(e, s->st) != cudaSuccess) {
+            set_error("engine: mode-info upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = SVT_B200_ERR_CUDA;
+            break;
+        }
+        pack_frame(e, s->pin_b, source);
+        if ((rc = copy_packed(e, &s->source, s->pin_b, cudaMemcpyHostToDevice, s->st)) != SVT_B200_OK) break;
+        // every trial: one plane pass + SSE + plane restore on the device, one 8-byte read-back (the bisection is host logic)
+        if ((rc = svt_b200_pick_filter_level(pp, &s->recon, &s->source, &s->out, (const SvtB200DlfMi *)s->misc, d_scratch, levels_out,
+                                             s->st)) != SVT_B200_OK)
+            break;
+        SvtB200DlfParams dp = pp->dlf;
+        dp.sharpness = 0; // svt_av1_pick_filter_level sets lf->sharpness_level = 0 (EbDeblockingFilter.c:1202)
+        dp.filter_level[0] = levels_out[0], dp.filter_level[1] = levels_out[1];
+        dp.filter_level_u = levels_out[2], dp.filter_level_v = levels_out[3];
+        dp.plane_start = 0, dp.plane_end = 3;
+        uint8_t(*lut)[2][128] = reinterpret_cast<uint8_t(*)[2][128]>(s->pin_small);
+        svt_b200_lf_level_lut(&pp->init, levels_out, lut);
+        {
+            Lap lap(e->stats.ns_issue);
+            if (cudaMemcpyAsync(d_scratch + 1024, s->pin_small, 768, cudaMemcpyHostToDevice, s->st) != cudaSuccess) {
+                rc = SVT_B200_ERR_CUDA;
+                break;
+            }
+            if ((rc = svt_b200_dlf_frame_lut(&dp, &s->recon, (const SvtB200DlfMi *)s->misc, d_scratch + 1024, s->st)) != SVT_B200_OK) break;
+            if ((rc = copy_packed(e, &s->recon, s->pin_a, cudaMemcpyDeviceToHost, s->st)) != SVT_B200_OK) break;
+        }
+        if (timed_sync(e, s->st) != cudaSuccess) {
+            set_error("engine: deblocking (picked levels) failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = SVT_B200_ERR_CUDA;
+            break;
+        }
+        unpack_frame(e, recon, s->pin_a);
         e->stats.dlf_frames++;
         e->stats.h2d_bytes += b_mi;
     } while (0);
