@@ -399,7 +399,17 @@ void run_copies(SvtB200Engine *e, const RowCopy (&c)[3]) {
     Lap lap(e->stats.ns_host_copy);
     size_t total = 0;
     for (const RowCopy &k : c) total += k.bytes * k.rows;
-    const int nt = total > (4u << 20) ? 4 : 1;
+    static const int trace = getenv("SVT_B200_ENGINE_TRACE") ? atoi(getenv("SVT_B200_ENGINE_TRACE")) : 0;
+    static const int max_threads = getenv("SVT_B200_COPY_THREADS") ? atoi(getenv("SVT_B200_COPY_THREADS")) : 4;
+    const uint64_t t0 = trace ? now_ns() : 0;
+    struct Tr {
+        uint64_t t0;
+        size_t n;
+        ~Tr() {
+            if (t0) fprintf(stderr, "engine trace: picture copy %.1f MB in %.3f ms\n", n / 1e6, (now_ns() - t0) / 1e6);
+        }
+    } tr{t0, total};
+    const int nt = total > (4u << 20) ? std::max(1, std::min(4, max_threads)) : 1;
     auto part = [&c, nt](int t) {
         for (const RowCopy &k : c) copy_rows(k, (int)((int64_t)k.rows * t / nt), (int)((int64_t)k.rows * (t + 1) / nt));
     };
