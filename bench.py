@@ -34,9 +34,22 @@ for p in (os.path.join(ROOT, "svt-av1_b200"), os.path.join(ROOT, "tools"), ROOT)
     if p not in sys.path:
         sys.path.insert(0, p)
 
+# --config: "1080p" = BASELINE configs[1] (the headline, default); "2160p10" = configs[2] (3840x2160 10-bit preset 6: the
+# deblocking level search, CDEF on 16-bit planes and - still on the CPU - loop restoration are on)
+CONFIGS = {"1080p": dict(W=1920, H=1080, BITS=8, PRESET=8, QP=43, METRIC="1080p30 8-bit preset-8 encode fps",
+                         NAME="BASELINE configs[1]: 1920x1080 8-bit yuv420p, preset 8, CQP qp=43"),
+           "2160p10": dict(W=3840, H=2160, BITS=10, PRESET=6, QP=43, METRIC="2160p 10-bit preset-6 encode fps",
+                           NAME="BASELINE configs[2]: 3840x2160 10-bit yuv420p10le, preset 6, CQP qp=43")}
 W, H, BITS, PRESET, QP = 1920, 1080, 8, 8, 43
-FRAMES_PER_STEP = 16  # one mini-GOP of the 4-level hierarchical structure preset 8 uses
+CONFIG_NAME = CONFIGS["1080p"]["NAME"]
+FRAMES_PER_STEP = 16  # one mini-GOP of the 4-level hierarchical structure presets 6-8 use
 METRIC = "1080p30 8-bit preset-8 encode fps"
+
+
+def select_config(name):
+    global W, H, BITS, PRESET, QP, METRIC, CONFIG_NAME
+    c = CONFIGS[name]
+    W, H, BITS, PRESET, QP, METRIC, CONFIG_NAME = c["W"], c["H"], c["BITS"], c["PRESET"], c["QP"], c["METRIC"], c["NAME"]
 B = os.path.join(ROOT, "integration", "_build")
 BIN = {"cuda": os.path.join(B, "enc_bench_cuda_simd"), "ref": os.path.join(B, "enc_bench_ref_simd"),
        "app_cuda": os.path.join(B, "SvtAv1EncAppCudaSimd")}
@@ -63,7 +76,7 @@ def make_clip(stream, frames):
     """Synthetic 1080p clip of stream `stream` (SURVEY 8d generator, per-stream seed), cached on tmpfs."""
     import make_yuv
     path = clip_path(stream, frames)
-    want = frames * (W * H + 2 * (W // 2) * (H // 2))
+    want = frames * (W * H + 2 * (W // 2) * (H // 2)) * (2 if BITS > 8 else 1)
     if not (os.path.exists(path) and os.path.getsize(path) == want):
         tmp = path + ".tmp%d" % os.getpid()
         make_yuv.write_clip(tmp, W, H, frames, BITS, seed=1234 + 1000 * stream)
@@ -95,12 +108,43 @@ def gpu_numa_cpus(idx):
         return None
 
 
+def cpu_partition(n, r):
+    """CPUs of stream r when n streams share the host: the physical cores (with their hyper-thread siblings) are split
+    into n disjoint, equal groups in (socket, core) order - the reference's documented way to run several jobs on one
+    server is `--lp <cpus per job>` with unpinned threads (EbAppConfig.c:887-894); the affinity keeps the jobs apart.
+    n == 1: None (no restriction beyond the caller's)."""
+    if n <= 1:
+        return None
+    try:
+        cores = {}
+        base = "/sys/devices/system/cpu"
+        for d in os.listdir(base):
+            if not re.fullmatch(r"cpu\d+", d):
+                continue
+            t = os.path.join(base, d, "topology")
+            if not os.path.exists(os.path.join(t, "core_id")):
+                continue
+            key = (int(open(os.path.join(t, "physical_package_id")).read()), int(open(os.path.join(t, "core_id")).read()))
+            cores.setdefault(key, []).append(int(d[3:]))
+        allowed = os.sched_getaffinity(0)
+        groups = [sorted(c for c in v if c in allowed) for _, v in sorted(cores.items())]
+        groups = [g for g in groups if g]
+        per = max(1, len(groups) // n)
+        mine = groups[r * per:(r + 1) * per]
+        cpus = sorted(c for g in mine for c in g)
+        return cpus or None
+    except Exception:
+        return None
+
+
 def start_enc(kind, clip, frames, warm_frames, out=None, env_extra=None, cpus=None):
     env = dict(os.environ)
     for k in list(env):
         if k.startswith("SVT_CUDA"):
             del env[k]
     env.update(env_extra or {})
+    if cpus and "ENC_BENCH_LP" not in env and env.get("SVTB200_STREAMS", "1") != "1":
+        env["ENC_BENCH_LP"] = str(len(cpus))  # thread / segment counts sized for this stream's share of the host
     cmd = [BIN[kind], clip, str(W), str(H), str(frames), str(BITS), str(PRESET), str(QP), str(warm_frames)] + ([out] if out else [])
 
     def pre():
@@ -137,7 +181,9 @@ def app_average_speed(clip, frames, env_extra, cpus):
     env = dict(os.environ)
     env.update(env_extra)
     cmd = [BIN["app_cuda"], "-i", clip, "-w", str(W), "-h", str(H), "--fps", "30", "--preset", str(PRESET), "--rc", "0", "-q", str(QP),
-           "-n", str(frames), "-b", ivf]
+           "-n", str(frames), "-b", ivf] + (["--input-depth", str(BITS)] if BITS != 8 else [])
+    if cpus and env.get("SVTB200_STREAMS", "1") != "1":
+        cmd += ["--lp", str(len(cpus))]
 
     def pre():
         if cpus:
@@ -167,13 +213,16 @@ def ivf_payload_md5(path):
 
 
 def workload(frames, world):
-    return {"workload": "BASELINE configs[1]: 1920x1080 8-bit yuv420p, preset 8, CQP qp=43, %d synthetic frames per stream "
-                        "(configs[1] is a 300-frame clip), %d stream(s) one per GPU" % (frames, world),
+    return {"workload": "%s, %d synthetic frames per stream (the BASELINE clip has 300), %d stream(s) one per GPU"
+                        % (CONFIG_NAME, frames, world),
             "frames_per_step": FRAMES_PER_STEP, "streams": world,
-            "stages_on_gpu": ["open-loop ME (HME + full-pel + candidate construction)", "deblocking (frame level)",
+            "stages_on_gpu": ["open-loop ME (HME + full-pel + candidate construction)",
+                              "deblocking (frame level" + (", with the level search svt_av1_pick_filter_level)" if PRESET <= 6 else ")"),
                               "CDEF strength search", "CDEF frame apply"],
-            "stages_on_cpu": "mode decision / EncDec, TPL, temporal filtering, global motion, entropy coding (reference AVX2/AVX-512 code)",
-            "l2": "every picture is new data: 3.1 MB per picture streamed from a 1.1 GB clip (>> 126 MB L2)",
+            "stages_on_cpu": "mode decision / EncDec, TPL, temporal filtering, global motion, entropy coding" +
+                             (", loop restoration (search + apply)" if PRESET <= 6 else "") + " (reference AVX2/AVX-512 code)",
+            "l2": "every picture is new data: %.1f MB per picture streamed from the clip (the ring of pictures in flight >> 126 MB L2)"
+                  % ((W * H * 3 // 2) * (2 if BITS > 8 else 1) / 1e6),
             "timing": "host monotonic clock between output packets (the encoder pipeline is host-driven); kernel-level times in "
                       "roofline / extra.hot_path are CUDA events on the launch stream"}
 
@@ -186,7 +235,9 @@ def run_reference(args):
     with ThreadPoolExecutor(max_workers=min(n, 8)) as ex:
         clips = list(ex.map(lambda s: make_clip(s, frames), range(n)))
     out0 = os.path.join(shm_dir(), "ref_%d.obu" % os.getpid())
-    procs = [start_enc("ref", clips[s], frames, warm, out=out0 if s == 0 else None) for s in range(n)]
+    parts = [cpu_partition(n, s) for s in range(n)]
+    procs = [start_enc("ref", clips[s], frames, warm, out=out0 if s == 0 else None, cpus=parts[s],
+                       env_extra={"SVTB200_STREAMS": str(n)}) for s in range(n)]
     res = [finish_enc(p, "reference encoder (stream %d)" % s) for s, p in enumerate(procs)]
     secs = max(r["seconds_timed"] for r in res)
     timed_frames = (frames - warm) * n
@@ -194,11 +245,13 @@ def run_reference(args):
     val = timed_frames / secs
     sample = ("%d concurrent stream(s) x %d frames (%d warm-up + %d timed) of the configs[1] workload through the reference "
               "encoder's own SSE2..AVX2/AVX-512 code paths (asm level picked by its cpuid dispatch), default threading on all "
-              "%d logical CPUs; built without the 13 nasm files (36 non-hot-path symbols forwarded to C, oracle/simd_asm_shim.c)"
-              % (n, frames, warm, frames - warm, cores))
+              "%d logical CPUs%s; built without the 13 nasm files (36 non-hot-path symbols forwarded to C, oracle/simd_asm_shim.c)"
+              % (n, frames, warm, frames - warm, cores,
+                 "" if n == 1 else " split into %d disjoint core groups of %d CPUs, one per stream, --lp %d unpinned"
+                 % (n, len(parts[0] or []), len(parts[0] or []))))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": n, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": secs * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload(frames, n),
+            "vs_baseline": None, "dtype": "u8" if BITS == 8 else "u16", "data": "synthetic", "config": workload(frames, n),
             "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "reference-avx2-minus-asm", "sample": sample},
             "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "bitstream_md5_stream0": md5_file(out0),
@@ -219,9 +272,27 @@ def hot_path(args_steps=6):
     return json.loads(lines[-1])
 
 
+def kernel_roofline():
+    """configs[2] geometry: tools/kernel_bench.py (CUDA-graph ring, device ms per picture of every filter entry)."""
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "kernel_bench.py")], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
+    if p.returncode != 0:
+        sys.stderr.write(p.stderr.decode(errors="replace")[-2000:])
+        raise RuntimeError("tools/kernel_bench.py failed")
+    kb = json.loads(p.stdout.decode())
+    g = [x for x in kb["geometries"] if x["geometry"].startswith("%dx%d" % (W, H))][0]
+    rows = [r for r in g["rows"] if not r["entry"].startswith("  ")]
+    dom = max(rows, key=lambda r: r["ms"])
+    return {"kernel": dom["entry"] + " (dominant picture-level entry at this geometry)", "bound": "hbm", "achieved": dom["achieved_gbs"],
+            "peak": kb["hbm_peak_gbs"], "unit": "GB/s", "frac": dom["frac_of_hbm_peak"], "traffic": None,
+            "same_size_copy": g["same_size_copy"], "stages": rows,
+            "note": "CDEF search is integer-ALU bound (10 filter evaluations per sample); deblocking and the CDEF apply are the streaming "
+                    "entries; `same_size_copy` is a plain device copy of one picture through the same launch path (the ceiling for a "
+                    "launch of this size)"}
+
+
 def cpu_baseline_sample():
-    """Bounded sample of the same workload on the host cores: the reference's SIMD encoder, 128 frames of stream 0."""
-    frames, warm = 8 * FRAMES_PER_STEP, 2 * FRAMES_PER_STEP
+    """Bounded sample of the same workload on the host cores: the reference's SIMD encoder on a prefix of stream 0."""
+    frames, warm = (8 * FRAMES_PER_STEP, 2 * FRAMES_PER_STEP) if W <= 1920 else (3 * FRAMES_PER_STEP, FRAMES_PER_STEP)
     clip = make_clip(0, frames)
     r = finish_enc(start_enc("ref", clip, frames, warm), "reference encoder (cpu_baseline)")
     cores = os.cpu_count() or 1
@@ -243,8 +314,9 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     frames, warm = (args.steps + args.warmup) * FRAMES_PER_STEP, args.warmup * FRAMES_PER_STEP
     clip = make_clip(rank, frames)
-    cpus = gpu_numa_cpus(local)
-    env = {"SVT_CUDA": "1", "SVT_CUDA_DEVICE": str(local), "SVT_CUDA_PROFILE": "1"}
+    # one stream: the CPUs local to the GPU; several streams: disjoint core groups (the same split the reference arm uses)
+    cpus = gpu_numa_cpus(local) if world == 1 else cpu_partition(world, rank)
+    env = {"SVT_CUDA": "1", "SVT_CUDA_DEVICE": str(local), "SVT_CUDA_PROFILE": "1", "SVTB200_STREAMS": str(world)}
     from bench_hotpath import ClockSampler
     sampler = ClockSampler(local)
     sampler.start()
@@ -281,7 +353,8 @@ def run_b200(args):
         timed_frames = (frames - warm) * world
         line = {"metric": METRIC, "value": timed_frames / secs_max, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": secs_max * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
-                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": workload(frames, world), "clocks": sampler.summary(),
+                "vs_baseline": None, "dtype": "u8" if BITS == 8 else "u16", "data": "synthetic", "config": workload(frames, world),
+                "clocks": sampler.summary(),
                 "e2e": {"value": frames * world / app_secs_max, "unit": "frames/s",
                         "h2d_bytes_per_step": int(h2d / (args.steps + args.warmup)) if h2d else None,
                         "d2h_bytes_per_step": int(d2h / (args.steps + args.warmup)) if d2h else None,
@@ -292,10 +365,13 @@ def run_b200(args):
                 "encoder": {"fps_whole_run_api": r["fps_all"], "init_s": r["init_s"], "numa_cpus": len(cpus) if cpus else None,
                             "engine": eng_line}}
         if world == 1 and not args.no_hotpath:
-            hp = hot_path()
-            line["roofline"] = hp["roofline"]
-            line["extra"] = {"hot_path": {k: hp[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "gpu_launches",
-                                                           "stage_ms_per_frame", "config") if k in hp}}
+            if args.config == "1080p":
+                hp = hot_path()
+                line["roofline"] = hp["roofline"]
+                line["extra"] = {"hot_path": {k: hp[k] for k in ("metric", "value", "unit", "ms_per_step", "e2e", "gpu_launches",
+                                                               "stage_ms_per_frame", "config") if k in hp}}
+            else:
+                line["roofline"] = kernel_roofline()
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_sample()
         emit(line)
@@ -312,7 +388,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-hotpath", action="store_true", help="skip the device-resident kernel chain (roofline)")
+    ap.add_argument("--config", default="1080p", choices=sorted(CONFIGS), help="1080p = BASELINE configs[1] (default), 2160p10 = configs[2]")
     args = ap.parse_args()
+    select_config(args.config)
     # stdout carries exactly ONE line (the JSON result): anything libraries print to fd 1 is routed to stderr
     global _REAL_STDOUT
     sys.stdout.flush()
