@@ -77,3 +77,38 @@ def test_simd_build_with_cuda_backend_matches_simd_reference(tmp_path):
     ref = ec.run_variant("ref_simd", clip, 720, 400, 24, 8, 43, 8, str(tmp_path))
     gpu = ec.run_variant("cuda_simd", clip, 720, 400, 24, 8, 43, 8, str(tmp_path))
     _same(ref, gpu)
+
+
+@skip_if_unbuilt
+def test_gop_sharded_encode_matches_cpu_per_substream(tmp_path):
+    """BASELINE configs[4] sharding (one stream, closed GOPs round-robin over encoder instances): every rank's CUDA-backed
+    sub-stream is bit-identical to the CPU reference encode of the same sub-clip; the splice holds every packet once."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "shard_encode.py"), "--width", "640", "--height", "360", "--frames", "96",
+                        "--gop", "32", "--gpus", "2", "--sequential", "--variant", "cuda_simd", "--verify", "--decode", "--preset", "8", "--qp", "50",
+                        "--workdir", str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=1800)
+    assert r.returncode == 0, (r.stdout.decode()[-1500:], r.stderr.decode()[-1500:])
+    d = json.loads(r.stdout.decode().strip().splitlines()[-1])
+    assert d["parity"] is True and d["packets"] == 96
+    assert d["decode_matches_recon"] is True  # the GOP-spliced stream decodes (reference decoder) to the spliced reconstructions
+
+
+DEC = os.path.join(ROOT, "oracle", "_ref", "app", "SvtAv1DecApp")
+
+
+@skip_if_unbuilt
+@pytest.mark.skipif(not os.path.exists(DEC), reason="oracle/_ref/app/SvtAv1DecApp not built")
+@pytest.mark.parametrize("bits,preset", [(8, 8), (10, 6)])
+def test_conformance_decoder_output_equals_cuda_encoder_recon(tmp_path, bits, preset):
+    """SURVEY 8c(3) conformance, independent of the C-only encoder: the bitstream of the CUDA-backed encoder, decoded by the
+    reference's own AV1 decoder, equals the encoder's reconstruction (which the GPU deblocking / CDEF produced)."""
+    import subprocess
+    clip = _clip(tmp_path, 640, 360, 16, bits)
+    gpu = ec.run_variant("cuda_c", clip, 640, 360, 16, preset, 50, bits, str(tmp_path))
+    assert gpu["rc"] == 0 and gpu["rec_md5"]
+    dec = str(tmp_path / "dec.yuv")
+    p = subprocess.run([DEC, "-i", str(tmp_path / "cuda_c.ivf"), "-o", dec] + (["-bit-depth", str(bits)] if bits != 8 else []),
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+    assert p.returncode == 0, p.stdout.decode(errors="replace")[-1500:]
+    assert ec.md5(dec) == gpu["rec_md5"]

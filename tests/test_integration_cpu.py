@@ -97,3 +97,15 @@ def test_bench_reference_arm_line():
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["cpu_baseline"]["kind"] == "reference-avx2-minus-asm" and d["cpu_baseline"]["cores"] == os.cpu_count()
     assert "configs[1]" in d["config"]["workload"]
+
+
+@need_build
+def test_gop_sharded_encode_splices_to_a_full_stream(tmp_path):
+    """tools/shard_encode.py with the CPU reference encoder as the worker (no GPU): 3 GOPs over 2 ranks, every packet of the
+    clip present once in the spliced stream."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "shard_encode.py"), "--width", "352", "--height", "288", "--frames", "40",
+                        "--gop", "16", "--gpus", "2", "--sequential", "--variant", "ref_simd", "--preset", "8", "--qp", "50",
+                        "--workdir", str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, timeout=900)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    d = json.loads(r.stdout.decode().strip().splitlines()[-1])
+    assert d["packets"] == 40 and d["gops_per_rank"] == [2, 1]

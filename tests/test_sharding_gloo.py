@@ -48,3 +48,24 @@ def test_two_rank_sharding_and_max_reduce():
     assert res[0][3] == [1] * 8
     assert res[0][4] != res[1][4]
     assert sharding.aggregate_fps(80, 15.0, 2) == 160 / 0.015
+
+
+def test_gop_sharding_round_robin_and_splice(tmp_path):
+    """One stream over N encoder instances: every GOP owned once, round-robin; splitting a clip and splicing
+    the per-rank packet lists back restores stream order (ragged last GOP included)."""
+    import sharding
+    assert sharding.assign_gops(7, 3) == [[0, 3, 6], [1, 4], [2, 5]]
+    for world in (1, 2, 3, 8):
+        owners = sharding.assign_gops(11, world)
+        assert sorted(g for o in owners for g in o) == list(range(11))
+    fb, gop, frames = 16, 4, 18  # 18 "frames" of 16 bytes, GOPs of 4 (the last one has 2)
+    clip = tmp_path / "clip.bin"
+    clip.write_bytes(b"".join(bytes([i]) * fb for i in range(frames)))
+    for world in (1, 2, 3):
+        paths, owners = sharding.split_clip(str(clip), fb, gop, world, str(tmp_path), tag="t%d" % world)
+        per_rank = []
+        for p in paths:
+            d = open(p, "rb").read()
+            per_rank.append([d[i:i + fb] for i in range(0, len(d), fb)])  # one "packet" per frame
+        whole = sharding.splice_gops(per_rank, owners, gop, frames)
+        assert whole == [bytes([i]) * fb for i in range(frames)]
