@@ -864,7 +864,7 @@ SVT_B200_API int svt_b200_subpel_search(const SvtB200SubpelParams *p, const SvtB
 typedef struct SvtB200Engine SvtB200Engine;
 
 typedef struct SvtB200EngineStats {
-    uint64_t me_pictures, dlf_frames, cdef_frames;
+    uint64_t me_pictures, dlf_frames, cdef_frames, lr_frames;
     uint64_t me_plane_uploads, me_plane_hits; /* ME plane residency cache: pictures uploaded / found resident */
     uint64_t h2d_bytes, d2h_bytes, pinned_bytes;
     /* wall time summed over calling threads: waiting for a slot, page-locking host buffers, waiting for another
@@ -910,6 +910,19 @@ SVT_B200_API int svt_b200_engine_dlf_frame(SvtB200Engine *e, const SvtB200DlfPar
  * mi: host array [mi_rows][mi_cols] (lvl_class is what is read).  pp->dlf.sharpness is ignored (the reference forces 0). */
 SVT_B200_API int svt_b200_engine_dlf_pick_frame(SvtB200Engine *e, const SvtB200LpfPickParams *pp, const SvtB200Frame *recon,
                                                 const SvtB200Frame *source, const SvtB200DlfMi *mi, int32_t levels_out[4]);
+
+/* svt_av1_loop_restoration_filter_frame of rest_kernel (EbRestProcess.c:530-534; presets <= 6) on a HOST picture in place.
+ * frame: the picture after CDEF (cm->frame_to_show).  The stripe context comes from the boundary lines the reference saved
+ * with svt_av1_loop_restoration_save_boundary_lines(after_cdef = 0) - RestorationStripeBoundaries of each plane: `above` /
+ * `below` address sample 0 of line 0 of stripe 0 (stripe_boundary_above/below + RESTORATION_EXTRA_HORZ), two lines per
+ * stripe, `stride` samples apart.  p->plane[i].units are HOST arrays here (n_units[i] entries); planes whose
+ * frame_restoration_type is 0 are left untouched. */
+typedef struct SvtB200HostLrLines {
+    const void *above, *below;
+    int32_t stride;
+} SvtB200HostLrLines;
+SVT_B200_API int svt_b200_engine_lr_frame(SvtB200Engine *e, const SvtB200LrFrameParams *p, const int32_t n_units[3],
+                                          const SvtB200Frame *frame, const SvtB200HostLrLines lines[3]);
 
 /* The CDEF stage of cdef_kernel (EbCdefProcess.c:510-534) for one HOST picture: strength search of every 64x64 filter
  * block -> `mse` (host, [2][nfb][64], = pcs->mse_seg) -> `decide(user, mse, apply, fb_strength_idx)` on the calling

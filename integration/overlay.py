@@ -17,6 +17,7 @@ The hooks (all behind `#if SVT_CUDA`, all inert unless the environment sets SVT_
                                 deblocked here, frame level, before the pre-CDEF preparation (:220)
   EbCdefProcess.c               cdef_seg_search of each segment (:510-515) skipped, and finish_cdef_search +
                                 svt_av1_cdef_frame (:521-534) replaced by svt_cuda_cdef_picture for the whole picture
+  EbRestProcess.c               svt_av1_loop_restoration_filter_frame (:533) -> svt_cuda_lr_frame (presets <= 6)
 """
 import difflib
 import os
@@ -108,6 +109,15 @@ HOOKS = [
     dict(file="Source/Lib/Encoder/Codec/EbCdefProcess.c",
          anchor="            } else {\n                frm_hdr->cdef_params.cdef_bits             = 0;\n",
          after="void *cdef_kernel(void *input_ptr) {", action="insert_before", text="                }\n"),
+    # -------------------------------------------------------------------------------------------------- EbRestProcess.c
+    dict(file="Source/Lib/Encoder/Codec/EbRestProcess.c",
+         anchor="                    svt_av1_loop_restoration_filter_frame(cm->frame_to_show, cm, 0);\n",
+         after="void *rest_kernel(void *input_ptr) {", action="insert_before",
+         text="#if SVT_CUDA\n"
+              "                    if (svt_cuda_lr_applies(pcs_ptr, scs_ptr))\n"
+              "                        svt_cuda_lr_frame(pcs_ptr, scs_ptr); /* the frame apply; the search above stays the reference's */\n"
+              "                    else\n"
+              "#endif\n"),
 ]
 
 

@@ -10,7 +10,7 @@
  * Switches (environment, read once):
  *   SVT_CUDA=1            turn the CUDA backend on (default: off -> the build behaves exactly like the reference)
  *   SVT_CUDA_DEVICE=n     CUDA ordinal (default 0)
- *   SVT_CUDA_ME / SVT_CUDA_DLF / SVT_CUDA_CDEF = 0 to leave one stage on the CPU (default 1 when SVT_CUDA=1)
+ *   SVT_CUDA_ME / SVT_CUDA_DLF / SVT_CUDA_CDEF / SVT_CUDA_LR = 0 to leave one stage on the CPU (default 1 when SVT_CUDA=1)
  *   SVT_CUDA_ME_DS=1      derive the 1/4 and 1/16 ME planes on the device instead of uploading the host's
  *   SVT_CUDA_PROFILE=1    print per-stage wall time / call counts at deinit (also for the CPU path, for comparison)
  * There is NO CPU fallback once a stage is on: a failing GPU call prints the library's message and aborts.
@@ -41,13 +41,13 @@
 #include "svt_av1_b200.h"
 #include "svt_cuda_backend.h"
 
-static int            g_on = -1, g_me = 0, g_dlf = 0, g_cdef = 0, g_me_ds = 0, g_prof = 0;
+static int            g_on = -1, g_me = 0, g_dlf = 0, g_cdef = 0, g_lr = 0, g_me_ds = 0, g_prof = 0;
 static SvtB200Engine *g_engine = NULL;
 static int            g_users  = 0;
 
-enum { ST_ME, ST_DLF, ST_CDEF, ST_N };
+enum { ST_ME, ST_DLF, ST_CDEF, ST_LR, ST_N };
 static struct { volatile int64_t ns, calls; } g_stat[2][ST_N]; /* [gpu?][stage] */
-static const char *g_stage_name[ST_N] = {"me", "dlf", "cdef"};
+static const char *g_stage_name[ST_N] = {"me", "dlf", "cdef", "lr"};
 
 static int64_t now_ns(void) {
     struct timespec t;
@@ -82,6 +82,7 @@ void svt_cuda_backend_init(void) {
             g_me    = env_flag("SVT_CUDA_ME", 1);
             g_dlf   = env_flag("SVT_CUDA_DLF", 1);
             g_cdef  = env_flag("SVT_CUDA_CDEF", 1);
+            g_lr    = env_flag("SVT_CUDA_LR", 1);
             g_me_ds = env_flag("SVT_CUDA_ME_DS", 0);
         }
     }
@@ -90,8 +91,8 @@ void svt_cuda_backend_init(void) {
         const char *d  = getenv("SVT_CUDA_DEVICE");
         int         rc = svt_b200_engine_create(d ? atoi(d) : 0, &g_engine);
         if (rc) die("svt_b200_engine_create", rc);
-        SVT_LOG("SVT [CUDA backend]: libsvtav1_b200 v%d on device %d (me %d, dlf %d, cdef %d)\n", svt_b200_version(),
-                d ? atoi(d) : 0, g_me, g_dlf, g_cdef);
+        SVT_LOG("SVT [CUDA backend]: libsvtav1_b200 v%d on device %d (me %d, dlf %d, cdef %d, lr %d)\n", svt_b200_version(),
+                d ? atoi(d) : 0, g_me, g_dlf, g_cdef, g_lr);
     }
 }
 
@@ -111,12 +112,12 @@ void svt_cuda_backend_deinit(void) {
             SvtB200EngineStats st;
             svt_b200_engine_get_stats(g_engine, &st);
             fprintf(stderr,
-                    "SVT [CUDA profile]: engine: %llu ME pictures (%llu plane uploads, %llu resident hits), %llu dlf, %llu cdef, "
+                    "SVT [CUDA profile]: engine: %llu ME pictures (%llu plane uploads, %llu resident hits), %llu dlf, %llu cdef, %llu lr, "
                     "H2D %.1f MB, D2H %.1f MB, pinned %.1f MB, %llu kernel launches; thread-ms: slot wait %.1f, issue %.1f "
                     "(of which wait for another thread's upload %.1f), wait for GPU %.1f, host staging copies %.1f\n",
                     (unsigned long long)st.me_pictures, (unsigned long long)st.me_plane_uploads,
                     (unsigned long long)st.me_plane_hits, (unsigned long long)st.dlf_frames, (unsigned long long)st.cdef_frames,
-                    st.h2d_bytes / 1e6, st.d2h_bytes / 1e6, st.pinned_bytes / 1e6, (unsigned long long)svt_b200_launch_count(),
+                    (unsigned long long)st.lr_frames, st.h2d_bytes / 1e6, st.d2h_bytes / 1e6, st.pinned_bytes / 1e6, (unsigned long long)svt_b200_launch_count(),
                     st.ns_slot_wait / 1e6, st.ns_issue / 1e6, st.ns_plane_wait / 1e6, st.ns_sync / 1e6, st.ns_host_copy / 1e6);
         }
         svt_b200_engine_destroy(g_engine);
@@ -134,6 +135,11 @@ static int containers_ok(const SequenceControlSet *scs_ptr) {
 int svt_cuda_dlf_applies(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr) {
     PictureParentControlSet *ppcs = pcs_ptr->parent_pcs_ptr;
     return g_on > 0 && g_dlf && containers_ok(scs_ptr) && !ppcs->frm_hdr.delta_lf_params.delta_lf_present &&
+        ppcs->av1_cm->tiles_info.tile_cols * ppcs->av1_cm->tiles_info.tile_rows == 1;
+}
+int svt_cuda_lr_applies(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr) {
+    PictureParentControlSet *ppcs = pcs_ptr->parent_pcs_ptr;
+    return g_on > 0 && g_lr && containers_ok(scs_ptr) && av1_superres_unscaled(&ppcs->av1_cm->frm_size) &&
         ppcs->av1_cm->tiles_info.tile_cols * ppcs->av1_cm->tiles_info.tile_rows == 1;
 }
 int svt_cuda_cdef_applies(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr) {
@@ -572,4 +578,66 @@ void svt_cuda_cdef_picture(PictureControlSet *pcs_ptr, SequenceControlSet *scs_p
     int rc = svt_b200_engine_cdef_frame(g_engine, &sp, &recon, &source, t_skip, skip_stride, t_mse, cdef_decide, &d);
     if (rc) die("svt_b200_engine_cdef_frame", rc);
     if (g_prof) stat_add(1, ST_CDEF, t0);
+}
+
+/* ===================================================================================================================
+ * Loop restoration, apply side: svt_av1_loop_restoration_filter_frame(cm->frame_to_show, cm, 0) of rest_kernel
+ * (EbRestProcess.c:530-534).  The search (restoration_seg_search, rest_finish_search) stays the reference's.
+ * ================================================================================================================= */
+#include "EbRestoration.h"
+static __thread SvtB200LrUnit *t_units[3]     = {NULL, NULL, NULL};
+static __thread int            t_units_cap[3] = {0, 0, 0};
+
+void svt_cuda_lr_frame(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr) {
+    (void)scs_ptr;
+    const int64_t     t0    = g_prof ? now_ns() : 0;
+    Av1Common *       cm    = pcs_ptr->parent_pcs_ptr->av1_cm;
+    Yv12BufferConfig *frame = cm->frame_to_show;
+    const int         hbd   = cm->use_highbitdepth;
+    SvtB200LrFrameParams p;
+    SvtB200HostLrLines   lines[3];
+    int32_t              n_units[3];
+    memset(&p, 0, sizeof(p));
+    p.optimized_lr = 0;
+    for (int pl = 0; pl < 3; pl++) {
+        RestorationInfo *rsi = &cm->rst_info[pl];
+        rsi->optimized_lr    = 0; /* what svt_av1_loop_restoration_filter_frame(frame, cm, 0) sets (:1324) */
+        p.plane[pl].frame_restoration_type = rsi->frame_restoration_type;
+        p.plane[pl].restoration_unit_size  = rsi->restoration_unit_size;
+        const int n = rsi->units_per_tile;
+        if (t_units_cap[pl] < n) {
+            free(t_units[pl]);
+            t_units[pl]     = (SvtB200LrUnit *)malloc((size_t)n * sizeof(SvtB200LrUnit));
+            t_units_cap[pl] = n;
+            if (!t_units[pl]) die("malloc", -1);
+        }
+        for (int u = 0; u < n; u++) {
+            const RestorationUnitInfo *ri = &rsi->unit_info[u];
+            SvtB200LrUnit *            o  = &t_units[pl][u];
+            o->restoration_type = ri->restoration_type;
+            memcpy(o->vfilter, ri->wiener_info.vfilter, sizeof(o->vfilter));
+            memcpy(o->hfilter, ri->wiener_info.hfilter, sizeof(o->hfilter));
+            o->sgr_ep     = ri->sgrproj_info.ep;
+            o->sgr_xqd[0] = ri->sgrproj_info.xqd[0];
+            o->sgr_xqd[1] = ri->sgrproj_info.xqd[1];
+        }
+        n_units[pl]        = n;
+        p.plane[pl].units  = t_units[pl];
+        lines[pl].above    = rsi->boundaries.stripe_boundary_above + (RESTORATION_EXTRA_HORZ << hbd);
+        lines[pl].below    = rsi->boundaries.stripe_boundary_below + (RESTORATION_EXTRA_HORZ << hbd);
+        lines[pl].stride   = rsi->boundaries.stripe_boundary_stride;
+    }
+    SvtB200Frame f;
+    memset(&f, 0, sizeof(f));
+    f.y         = REAL_PTR(hbd, frame->buffers[0]);
+    f.cb        = REAL_PTR(hbd, frame->buffers[1]);
+    f.cr        = REAL_PTR(hbd, frame->buffers[2]);
+    f.stride_y  = frame->strides[0];
+    f.stride_c  = frame->strides[1];
+    f.width     = frame->crop_widths[0];
+    f.height    = frame->crop_heights[0];
+    f.bit_depth = hbd ? (int)cm->bit_depth : 8;
+    int rc      = svt_b200_engine_lr_frame(g_engine, &p, n_units, &f, lines);
+    if (rc) die("svt_b200_engine_lr_frame", rc);
+    if (g_prof) stat_add(1, ST_LR, t0);
 }

@@ -15,6 +15,7 @@ void svt_cuda_backend_deinit(void); /* svt_av1_enc_deinit (EbEncHandle.c:1879) *
 int svt_cuda_me_active(void);
 int svt_cuda_dlf_applies(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr);
 int svt_cuda_cdef_applies(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr);
+int svt_cuda_lr_applies(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr);
 
 int svt_cuda_me_segment(MotionEstimationContext_t *context_ptr, PictureParentControlSet *pcs_ptr, SequenceControlSet *scs_ptr,
                         EbPaReferenceObject *pa_ref_obj, EbPictureBufferDesc *input_padded_picture_ptr,
@@ -24,6 +25,7 @@ int svt_cuda_me_segment(MotionEstimationContext_t *context_ptr, PictureParentCon
 void svt_cuda_dlf_frame(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr, EbPictureBufferDesc *recon_buffer);
 int  svt_cuda_dlf_pick_frame(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr, EbPictureBufferDesc *recon_buffer);
 void svt_cuda_cdef_picture(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr);
+void svt_cuda_lr_frame(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr);
 
 /* SVT_CUDA_PROFILE=1: wall time the stage threads spend in each stage, CPU path included (stage: 0 me, 1 dlf, 2 cdef) */
 int64_t svt_cuda_prof_begin(void);

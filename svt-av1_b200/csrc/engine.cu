@@ -99,7 +99,7 @@ struct SvtB200Engine {
     FiltGeom fg;
     uint8_t *me_dev = nullptr, *me_pin = nullptr, *filt_dev = nullptr, *filt_pin = nullptr;
     struct {
-        std::atomic<uint64_t> me_pictures{0}, dlf_frames{0}, cdef_frames{0}, me_plane_uploads{0}, me_plane_hits{0}, h2d_bytes{0},
+        std::atomic<uint64_t> me_pictures{0}, dlf_frames{0}, cdef_frames{0}, lr_frames{0}, me_plane_uploads{0}, me_plane_hits{0}, h2d_bytes{0},
             d2h_bytes{0}, pinned_bytes{0}, ns_slot_wait{0}, ns_pin{0}, ns_plane_wait{0}, ns_issue{0}, ns_sync{0}, ns_host_copy{0},
             pin_calls{0};
     } stats;
@@ -520,6 +520,7 @@ int svt_b200_engine_get_stats(SvtB200Engine *e, SvtB200EngineStats *out) {
     out->me_pictures = e->stats.me_pictures;
     out->dlf_frames = e->stats.dlf_frames;
     out->cdef_frames = e->stats.cdef_frames;
+    out->lr_frames = e->stats.lr_frames;
     out->me_plane_uploads = e->stats.me_plane_uploads;
     out->me_plane_hits = e->stats.me_plane_hits;
     out->h2d_bytes = e->stats.h2d_bytes;
@@ -719,6 +720,132 @@ int svt_b200_engine_dlf_pick_frame(SvtB200Engine *e, const SvtB200LpfPickParams 
         unpack_frame(e, recon, s->pin_a);
         e->stats.dlf_frames++;
         e->stats.h2d_bytes += b_mi;
+    } while (0);
+    if (rc != SVT_B200_OK) cudaStreamSynchronize(s->st);
+    release(e, s);
+    return rc;
+}
+
+int svt_b200_engine_lr_frame(SvtB200Engine *e, const SvtB200LrFrameParams *p, const int32_t n_units[3], const SvtB200Frame *frame,
+                             const SvtB200HostLrLines lines[3]) {
+    if (!e || !p || !n_units || !frame || !lines) {
+        set_error("svt_b200_engine_lr_frame: null argument");
+        return SVT_B200_ERR_ARG;
+    }
+    DeviceGuard dg(e->device);
+    int rc = ensure_filt(e, frame->width, frame->height, frame->bit_depth, (frame->height + 3) / 4, (frame->width + 3) / 4);
+    if (rc != SVT_B200_OK) return rc;
+    const FiltGeom &g = e->fg;
+    const int bps = frame->bit_depth > 8 ? 2 : 1;
+    size_t b_units = 0;
+    for (int i = 0; i < 3; i++) b_units += al256((size_t)std::max(n_units[i], 0) * sizeof(SvtB200LrUnit));
+    // staging of the boundary lines: 4 rows per stripe boundary and plane
+    size_t b_lines = 0;
+    int nb[3], pw[3], ph[3], SH[3], off[3];
+    for (int i = 0; i < 3; i++) {
+        const int ss = i ? 1 : 0;
+        pw[i] = i ? (frame->width + 1) >> 1 : frame->width;
+        ph[i] = i ? (frame->height + 1) >> 1 : frame->height;
+        SH[i] = 64 >> ss, off[i] = 8 >> ss;
+        const int n_stripes = (ph[i] + off[i] + SH[i] - 1) / SH[i];
+        nb[i] = p->plane[i].frame_restoration_type ? n_stripes - 1 : 0;
+        b_lines += al256((size_t)nb[i] * 4 * pw[i] * bps);
+    }
+    if (b_units + 256 > g.misc || b_lines > g.packed) {
+        set_error("svt_b200_engine_lr_frame: unit / boundary-line arrays larger than the sequence geometry");
+        return SVT_B200_ERR_ARG;
+    }
+    FiltSlot *s = acquire(e, e->filt);
+    do {
+        pack_frame(e, s->pin_a, frame);
+        // units -> pin_small (host) -> misc (device)
+        SvtB200LrFrameParams dp = *p;
+        {
+            size_t o = 0;
+            if (b_units > g.small) {
+                set_error("svt_b200_engine_lr_frame: too many restoration units");
+                rc = SVT_B200_ERR_ARG;
+                break;
+            }
+            for (int i = 0; i < 3; i++) {
+                const size_t n = (size_t)std::max(n_units[i], 0) * sizeof(SvtB200LrUnit);
+                if (n) memcpy(s->pin_small + o, p->plane[i].units, n);
+                dp.plane[i].units = (const SvtB200LrUnit *)(s->misc + o);
+                o += al256(n);
+            }
+        }
+        // boundary lines: [boundary][row -2, -1, 0, +1 around the stripe edge][width], packed per plane in pin_b
+        {
+            Lap lap(e->stats.ns_host_copy);
+            size_t o = 0;
+            for (int i = 0; i < 3; i++) {
+                const size_t rb = (size_t)pw[i] * bps, ls = (size_t)lines[i].stride * bps;
+                for (int b = 0; b < nb[i]; b++) {
+                    uint8_t *d = s->pin_b + o + (size_t)b * 4 * rb;
+                    const uint8_t *ab = (const uint8_t *)lines[i].above + (size_t)(2 * (b + 1)) * ls; // stripe b+1: rows y0-2, y0-1
+                    const uint8_t *be = (const uint8_t *)lines[i].below + (size_t)(2 * b) * ls;       // stripe b: rows y1, y1+1
+                    memcpy(d, ab, rb);
+                    memcpy(d + rb, ab + ls, rb);
+                    memcpy(d + 2 * rb, be, rb);
+                    memcpy(d + 3 * rb, be + ls, rb);
+                }
+                o += al256((size_t)nb[i] * 4 * rb);
+            }
+        }
+        {
+            Lap lap(e->stats.ns_issue);
+            if (b_units && cudaMemcpyAsync(s->misc, s->pin_small, b_units, cudaMemcpyHostToDevice, s->st) != cudaSuccess) {
+                rc = SVT_B200_ERR_CUDA;
+                break;
+            }
+            if ((rc = copy_packed(e, &s->recon, s->pin_a, cudaMemcpyHostToDevice, s->st)) != SVT_B200_OK) break;
+            // scatter the boundary rows into a device picture that is only read at those rows (the deblocked context)
+            size_t o = 0;
+            bool ok = true;
+            for (int i = 0; i < 3 && ok; i++) {
+                if (!nb[i]) continue;
+                const size_t rb = (size_t)pw[i] * bps;
+                uint8_t *plane = (uint8_t *)(i == 0 ? s->source.y : i == 1 ? s->source.cb : s->source.cr);
+                const size_t dpitch = (size_t)(i ? s->source.stride_c : s->source.stride_y) * bps;
+                for (int k = 0; k < 4 && ok; k++) { // row B - 2 + k of every boundary B = (b + 1) * SH - off
+                    int rows = nb[i];
+                    if ((nb[i]) * SH[i] - off[i] - 2 + k >= ph[i]) rows--; // the last boundary's row lies below the plane
+                    if (rows <= 0) continue;
+                    ok = cudaMemcpy2DAsync(plane + (size_t)(SH[i] - off[i] - 2 + k) * dpitch, dpitch * SH[i], s->pin_b + o + (size_t)k * rb,
+                                           4 * rb, rb, rows, cudaMemcpyHostToDevice, s->st) == cudaSuccess;
+                }
+                o += al256((size_t)nb[i] * 4 * rb);
+            }
+            if (!ok) {
+                set_error("engine: boundary-line upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = SVT_B200_ERR_CUDA;
+                break;
+            }
+            if ((rc = svt_b200_lr_frame(&dp, &s->recon, &s->source, &s->out, s->st)) != SVT_B200_OK) break;
+            if ((rc = copy_packed(e, &s->out, s->pin_a, cudaMemcpyDeviceToHost, s->st)) != SVT_B200_OK) break;
+        }
+        if (timed_sync(e, s->st) != cudaSuccess) {
+            set_error("engine: loop restoration failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = SVT_B200_ERR_CUDA;
+            break;
+        }
+        // planes without restoration stay as they are on the host (the reference copies back only filtered planes)
+        SvtB200Frame fr = *frame;
+        {
+            Lap lap(e->stats.ns_host_copy);
+            const int cw = pw[1], ch = ph[1];
+            const size_t rw = (size_t)frame->width * bps, rcb = (size_t)cw * bps;
+            const uint8_t *py = s->pin_a, *pcb = py + rw * frame->height, *pcr = pcb + rcb * ch;
+            if (p->plane[0].frame_restoration_type) {
+                const RowCopy c[3] = {{(uint8_t *)fr.y, py, (size_t)fr.stride_y * bps, rw, rw, fr.height}, {nullptr, nullptr, 0, 0, 0, 0}, {nullptr, nullptr, 0, 0, 0, 0}};
+                run_copies(e, c);
+            }
+            if (p->plane[1].frame_restoration_type)
+                for (int y = 0; y < ch; y++) memcpy((uint8_t *)fr.cb + (size_t)y * fr.stride_c * bps, pcb + y * rcb, rcb);
+            if (p->plane[2].frame_restoration_type)
+                for (int y = 0; y < ch; y++) memcpy((uint8_t *)fr.cr + (size_t)y * fr.stride_c * bps, pcr + y * rcb, rcb);
+        }
+        e->stats.lr_frames++;
     } while (0);
     if (rc != SVT_B200_OK) cudaStreamSynchronize(s->st);
     release(e, s);

@@ -86,3 +86,14 @@ def test_encode_tus_4k_10bit():
         assert got_eob[i] == want_eob[j]
         np.testing.assert_array_equal(got_q[i], want_q[j])
         np.testing.assert_array_equal(got_rec.plane(0)[t.y:t.y + 32, t.x:t.x + 32], want_rec.plane(0)[t.y:t.y + 32, t.x:t.x + 32])
+
+
+def test_me_picture_4k_geometry():
+    """Open-loop ME at the configs[2] / [4] geometry (3840x2160: 2040 superblocks; ME always runs on the 8-bit luma planes):
+    every MeSbResults field vs the oracle."""
+    import gpu_runner as gr
+    dist = ((1, 2, 3, 4), (1, 2, 3, 4))
+    geos, src, refs = cm.make_me_case(W, H, 2, 2, seed=41)
+    params = sb.preset8_me_params(W, H, 2, 2, dist, 1, 1)
+    got = gr.run_gpu_me(params, src, refs)
+    cm.assert_me_equal(got, cm.run_oracle_me(params, src, refs), params, "2160p gpu-vs-oracle")

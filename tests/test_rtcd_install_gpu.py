@@ -133,3 +133,21 @@ def test_reference_subpel_search_on_cuda_pointers(installed):
     want, got, launches = installed(lambda: sc.run_cpu(cm.refh().refh_subpel_search, p, tabs, src, refs, jobs))
     assert launches > 10 * len(jobs)
     np.testing.assert_array_equal(got, want)
+
+
+def test_reference_motion_estimate_sb_on_cuda_pointers(installed):
+    """The reference's own motion_estimate_sb (HME levels 0-2, integer search, pruning, candidate construction) over every SB
+    of a small picture with the SAD pointers (svt_sad_loop_kernel, svt_ext_all_sad_calculation_8x8_16x16,
+    svt_ext_eight_sad_calculation_32x32_64x64, svt_ext_sad_calculation_*, svt_nxm_sad_kernel, svt_initialize_buffer_32bits)
+    replaced by the CUDA drop-ins: identical MeSbResults (ME was only checked oracle-side)."""
+    w, h = 192, 128
+    dist = ((1, 2, 3, 4), (1, 2, 3, 4))
+    geos, src, refs = cm.make_me_case(w, h, 2, 1, seed=11)
+
+    def run():
+        _, out = cm.run_ref_me(w, h, 8, 2, 1, dist, 2, 1, geos, src, refs)
+        return out
+    want, got, launches = installed(run)
+    assert launches > 100
+    params = sb.preset8_me_params(w, h, 2, 1, dist, 2, 1)
+    cm.assert_me_equal(got, want, params, "reference motion_estimate_sb: CUDA pointers vs C pointers")

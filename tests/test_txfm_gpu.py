@@ -157,7 +157,13 @@ def oracle_encode_tus(params, src, pred, tus, use_fp):
         if max(w, h) == 64:
             orc.orc_handle_transform64(cm.ptr(coeff), ts)
         scan = np.zeros(1024, np.int16)
-        assert lib.svt_b200_get_scan(ts, tu.tx_type, cm.ptr(scan)) == n
+        if cm.have_ref():  # the oracle side takes its scan order from the REFERENCE's av1_scan_orders, not from the product
+            assert cm.refh().refh_get_scan(ts, tu.tx_type, cm.ptr(scan)) == n
+            mine = np.zeros(1024, np.int16)
+            assert lib.svt_b200_get_scan(ts, tu.tx_type, cm.ptr(mine)) == n
+            np.testing.assert_array_equal(mine[:n], scan[:n], err_msg="svt_b200_get_scan differs from av1_scan_orders")
+        else:
+            assert lib.svt_b200_get_scan(ts, tu.tx_type, cm.ptr(scan)) == n
         q, dq, eob = np.zeros(n, np.int32), np.zeros(n, np.int32), C.c_uint16(0)
         qp = params.q[tu.plane]
         if use_fp:
