@@ -344,20 +344,24 @@ static SvtB200DlfMi *flatten_picture(PictureControlSet *pcs_ptr) {
         if (!t_mi) die("malloc", -1);
     }
     const LoopFilterInfoN *lfi_n = &ppcs->lf_info;
+    /* Every 4x4 cell owns a ModeInfo (EbAdaptiveMotionVectorPrediction.c update_mi_map fills all cells of a block alike), and
+     * dereferencing each one is a cache miss: 518k of them at 2160p.  A block's entry is computed at its first cell of a
+     * row and replicated over the block's width; rows below the block's first row copy the row above (same block: the
+     * cell's sb_type says how many rows the block spans and AV1 blocks are aligned to their size). */
     for (int r = 0; r < mi_rows; r++) {
-        ModeInfo **       row  = pcs_ptr->mi_grid_base + (size_t)r * pcs_ptr->mi_stride;
-        SvtB200DlfMi *    out  = t_mi + (size_t)r * mi_cols;
-        const MbModeInfo *prev = NULL;
-        for (int c = 0; c < mi_cols; c++) {
-            const MbModeInfo *m = &row[c]->mbmi;
-            /* cells of one block carry the same fields: reuse the left neighbour's entry when they match */
-            if (prev && m->block_mi.sb_type == prev->block_mi.sb_type && m->tx_depth == prev->tx_depth &&
-                m->block_mi.ref_frame[0] == prev->block_mi.ref_frame[0] && m->block_mi.skip == prev->block_mi.skip &&
-                m->block_mi.mode == prev->block_mi.mode)
-                out[c] = out[c - 1];
-            else
+        ModeInfo **   row = pcs_ptr->mi_grid_base + (size_t)r * pcs_ptr->mi_stride;
+        SvtB200DlfMi *out = t_mi + (size_t)r * mi_cols;
+        for (int c = 0; c < mi_cols;) {
+            const MbModeInfo *m   = &row[c]->mbmi;
+            const int         bw4 = mi_size_wide[m->block_mi.sb_type], bh4 = mi_size_high[m->block_mi.sb_type];
+            const int         n   = AOMMIN(bw4 - (c & (bw4 - 1)), mi_cols - c);
+            if ((r & (bh4 - 1)) && r > 0)
+                memcpy(&out[c], &out[c - mi_cols], (size_t)n * sizeof(SvtB200DlfMi)); /* not the block's first row */
+            else {
                 flatten_mi(&out[c], m, lfi_n);
-            prev = m;
+                for (int k = 1; k < n; k++) out[c + k] = out[c];
+            }
+            c += n;
         }
     }
     return t_mi;
@@ -466,6 +470,8 @@ typedef struct CdefDecide {
     PictureControlSet * pcs;
     SequenceControlSet *scs;
     int                 nvfb, nhfb;
+    const uint8_t *     skip8; /* [ceil(mi_rows/2)][skip_stride] */
+    int                 skip_stride, rows8, cols8;
 } CdefDecide;
 
 void finish_cdef_search(EncDecContext *context_ptr, PictureControlSet *pcs_ptr, int32_t selected_strength_cnt[64]);
@@ -492,8 +498,15 @@ static int cdef_decide(void *user, const uint64_t *mse, SvtB200CdefApplyParams *
     for (int fbr = 0; fbr < d->nvfb; fbr++)
         for (int fbc = 0; fbc < d->nhfb; fbc++) {
             const ModeInfo *mi = pcs->mi_grid_base[MI_SIZE_64X64 * fbr * cm->mi_stride + MI_SIZE_64X64 * fbc];
-            fb_strength_idx[fbr * d->nhfb + fbc] =
-                (!mi || svt_sb_all_skip(pcs, cm, fbr * MI_SIZE_64X64, fbc * MI_SIZE_64X64)) ? -1 : mi->mbmi.cdef_strength;
+            /* svt_sb_all_skip == every 8x8 of the filter block is skip (the map the search used) */
+            int all_skip = 1;
+            for (int r8 = 8 * fbr; r8 < AOMMIN(8 * fbr + 8, d->rows8) && all_skip; r8++)
+                for (int c8 = 8 * fbc; c8 < AOMMIN(8 * fbc + 8, d->cols8); c8++)
+                    if (!d->skip8[(size_t)r8 * d->skip_stride + c8]) {
+                        all_skip = 0;
+                        break;
+                    }
+            fb_strength_idx[fbr * d->nhfb + fbc] = (!mi || all_skip) ? -1 : mi->mbmi.cdef_strength;
         }
     return 1;
 }
@@ -540,14 +553,27 @@ void svt_cuda_cdef_picture(PictureControlSet *pcs_ptr, SequenceControlSet *scs_p
     memset(t_skip, 1, b_skip);
     ModeInfo **grid = pcs_ptr->mi_grid_base;
     const int  ms   = pcs_ptr->mi_stride;
-    for (int r = 0; r < mi_rows; r += 2)
-        for (int c = 0; c < mi_cols; c += 2) {
-            int s = 1;
-            for (int dr = 0; dr < 2; dr++)
-                for (int dc = 0; dc < 2; dc++)
-                    if (r + dr < mi_rows && c + dc < mi_cols) s &= (int)grid[(r + dr) * ms + c + dc]->mbmi.block_mi.skip;
-            t_skip[(size_t)(r >> 1) * skip_stride + (c >> 1)] = (uint8_t)s;
+    /* is_8x8_block_skip = AND of the four cells' skip flags; a block of 8x8 or more has one flag for all its cells, so one
+     * dereference serves the block's whole width (only sub-8x8 partitions need all four cells) */
+    for (int r = 0; r < mi_rows; r += 2) {
+        uint8_t *out = t_skip + (size_t)(r >> 1) * skip_stride;
+        for (int c = 0; c < mi_cols;) {
+            const MbModeInfo *m   = &grid[r * ms + c]->mbmi;
+            const int         bw4 = mi_size_wide[m->block_mi.sb_type], bh4 = mi_size_high[m->block_mi.sb_type];
+            if (bw4 >= 2 && bh4 >= 2) {
+                const int n = AOMMIN(bw4 - (c & (bw4 - 1)), mi_cols - c);
+                memset(out + (c >> 1), m->block_mi.skip ? 1 : 0, (size_t)(n + 1) >> 1);
+                c += n;
+            } else {
+                int sk = 1;
+                for (int dr = 0; dr < 2; dr++)
+                    for (int dc = 0; dc < 2; dc++)
+                        if (r + dr < mi_rows && c + dc < mi_cols) sk &= (int)grid[(r + dr) * ms + c + dc]->mbmi.block_mi.skip;
+                out[c >> 1] = (uint8_t)sk;
+                c += 2;
+            }
         }
+    }
 
     /* pcs->src[] / ref_coeff[] were set by dlf_kernel's pre-cdef prep (EbDlfProcess.c:254-300): sample (0,0) of each plane */
     EbPictureBufferDesc *recon_desc;
@@ -574,7 +600,7 @@ void svt_cuda_cdef_picture(PictureControlSet *pcs_ptr, SequenceControlSet *scs_p
     recon.height = source.height = mi_rows * 4;
     recon.bit_depth = source.bit_depth = is_16bit ? 10 : 8;
 
-    CdefDecide d = {pcs_ptr, scs_ptr, nvfb, nhfb};
+    CdefDecide d = {pcs_ptr, scs_ptr, nvfb, nhfb, t_skip, skip_stride, rows8, (mi_cols + 1) / 2};
     int rc = svt_b200_engine_cdef_frame(g_engine, &sp, &recon, &source, t_skip, skip_stride, t_mse, cdef_decide, &d);
     if (rc) die("svt_b200_engine_cdef_frame", rc);
     if (g_prof) stat_add(1, ST_CDEF, t0);
