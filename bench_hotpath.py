@@ -777,18 +777,33 @@ def roofline(stage_ms, pk, pk_kind, n_sb):
              "dlf": "hbm", "cdef_search": "integer ALU (10 filters per sample)", "cdef_apply": "hbm"}
     # DRAM bytes per frame from the committed `ncu --set full` capture of one frame (profiles/ncu_traffic.json, written
     # by tools/ncu_summary.py): sums over the launches of the stage's kernels
-    kernels = {"me": ("hme_kernel", "fullpel_kernel"), "encdec": ("encode_tu_kernel",), "dlf": ("dlf_pass_kernel",),
+    kernels = {"me": ("hme_kernel", "fullpel_kernel"), "encdec": ("encode_tu_kernel",), "dlf": ("dlf_vert_kernel", "dlf_horz_kernel"),
                "cdef_search": ("cdef_search_grid_kernel",), "cdef_apply": ("cdef_apply_kernel",)}
-    try:
-        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-    except Exception:
-        ncu = {}
+    launches_per_frame = {"encode_tu_kernel": 3}
+    ncu = {}
+    for f in ("ncu_traffic.json", "r2_ncu_kernels.json"):  # round-2 capture first choice, round-1 for kernels it does not hold
+        try:
+            for k, v in json.load(open(os.path.join(ROOT, "profiles", f))).items():
+                n = max(1, v.get("launches", 1))
+                per = launches_per_frame.get(k, 1)
+                ncu[k] = {"dram_bytes": v["dram_bytes"] / n * per if f.startswith("r2") else v["dram_bytes"],
+                          "time_us": v["time_us"] / n * per if f.startswith("r2") else v["time_us"],
+                          "alu_pipe_pct": v.get("alu_pipe_pct"), "issue_active_pct": v.get("issue_active_pct")}
+        except Exception:
+            pass
     stages = []
     for k, b in alg.items():
         ach = b / (stage_ms[k] / 1e3) / 1e9
-        tr = sum(ncu[n]["dram_bytes"] for n in kernels[k]) if all(n in ncu for n in kernels[k]) else None
+        have = all(n in ncu for n in kernels[k])
+        tr = sum(ncu[n]["dram_bytes"] for n in kernels[k]) if have else None
+        alu = None
+        if have and all(ncu[n]["alu_pipe_pct"] is not None for n in kernels[k]):
+            tt = sum(ncu[n]["time_us"] for n in kernels[k])
+            alu = {"pipe_alu_pct_of_peak": round(sum(ncu[n]["alu_pipe_pct"] * ncu[n]["time_us"] for n in kernels[k]) / tt, 1),
+                   "issue_slots_busy_pct": round(sum(ncu[n]["issue_active_pct"] * ncu[n]["time_us"] for n in kernels[k]) / tt, 1),
+                   "source": "ncu --set full, profiles/r2_ncu_full_summary.txt (sm__inst_executed_pipe_alu / smsp__issue_active, time-weighted)"}
         stages.append({"stage": k, "kernels": list(kernels[k]), "ms_per_frame": stage_ms[k], "algorithmic_bytes": int(b), "achieved": ach,
-                       "frac": ach / pk["hbm_gbs"], "traffic": tr, "binding": bound[k]})
+                       "frac": ach / pk["hbm_gbs"], "traffic": tr, "alu": alu, "binding": bound[k]})
     dom = max(stages, key=lambda x: x["ms_per_frame"])
     return {"kernel": "stage '%s' = %s (dominant; per-kernel ncu data in profiles/)" % (dom["stage"], " + ".join(dom["kernels"])), "bound": "hbm",
             "achieved": dom["achieved"], "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": dom["frac"], "traffic": dom["traffic"],

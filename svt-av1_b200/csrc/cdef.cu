@@ -652,7 +652,11 @@ __global__ void __launch_bounds__(NT, CDEF_SEARCH_MINB) cdef_search_grid_kernel(
     __shared__ uint32_t s_sums[64 * CDEF_COMPACT_NG * 3 + 128]; // parked (sum f, sum f^2, sum f*o) per (block, strength) + (sum o, sum o^2)
     const CdefSearchDev &d = gd.d;
     const int tid = threadIdx.x;
+    // grid.y = 2: CTA (fb, 0) searches the luma plane, CTA (fb, 1) both chroma planes (it stages the luma tile once more for
+    // the block directions).  One CTA per filter block was 510 CTAs = 0.86 waves at 1080p (ncu launch__waves_per_multiprocessor)
+    // with every CTA a serial chain over three planes; split, the grid is 1020 CTAs of 2/3 and 1/3 of that chain.
     const int fb = blockIdx.x, fbr = fb / d.nhfb, fbc = fb - fbr * d.nhfb;
+    const bool chroma_cta = blockIdx.y != 0;
     const SvtB200CdefSearchParams &p = d.p;
     const int nvb = min(16, p.mi_rows - 16 * fbr), nhb = min(16, p.mi_cols - 16 * fbc);
     const int cs = d.coeff_shift;
@@ -679,13 +683,11 @@ __global__ void __launch_bounds__(NT, CDEF_SEARCH_MINB) cdef_search_grid_kernel(
     __syncthreads();
     const int count = s_count;
     if (count == 0) { // svt_sb_all_skip: not searched; entries defined as 0
-        for (int i = tid; i < 64; i += NT) {
-            out_y[i] = 0;
-            out_c[i] = 0;
-        }
+        for (int i = tid; i < 64; i += NT) (chroma_cta ? out_c : out_y)[i] = 0;
         return;
     }
     for (int pli = 0; pli < 3; pli++) {
+        if (!chroma_cta && pli) break; // the luma CTA is done after plane 0
         const int sh = pli ? 1 : 0;
         const int pw = (p.mi_cols * 4) >> sh, ph = (p.mi_rows * 4) >> sh;
         const int bh = (nvb * 4) >> sh, bw = (nhb * 4) >> sh;
@@ -698,6 +700,7 @@ __global__ void __launch_bounds__(NT, CDEF_SEARCH_MINB) cdef_search_grid_kernel(
         if (pli == 0) {
             find_dirs(in, s_by, s_bx, count, cs, s_dir, s_var);
             __syncthreads();
+            if (chroma_cta) continue; // directions only
         }
         const int damping = p.pri_damping + cs - (pli != 0);
         if (pli == 0) {
@@ -975,14 +978,14 @@ int svt_b200_cdef_search(const SvtB200CdefSearchParams *p, const SvtB200Frame *r
         for (int i = 0; i < nsec; i++) gd.g.sec[i] = p->sec_strength[i];
         if (d.recon.hbd) {
             if (nsec == 2)
-                SVTB_LAUNCH((cdef_search_grid_kernel<uint16_t, 2>), d.nvfb * d.nhfb, NT, 0, st, gd);
+                SVTB_LAUNCH((cdef_search_grid_kernel<uint16_t, 2>), dim3(d.nvfb * d.nhfb, 2), NT, 0, st, gd);
             else
-                SVTB_LAUNCH((cdef_search_grid_kernel<uint16_t, 4>), d.nvfb * d.nhfb, NT, 0, st, gd);
+                SVTB_LAUNCH((cdef_search_grid_kernel<uint16_t, 4>), dim3(d.nvfb * d.nhfb, 2), NT, 0, st, gd);
         } else {
             if (nsec == 2)
-                SVTB_LAUNCH((cdef_search_grid_kernel<uint8_t, 2>), d.nvfb * d.nhfb, NT, 0, st, gd);
+                SVTB_LAUNCH((cdef_search_grid_kernel<uint8_t, 2>), dim3(d.nvfb * d.nhfb, 2), NT, 0, st, gd);
             else
-                SVTB_LAUNCH((cdef_search_grid_kernel<uint8_t, 4>), d.nvfb * d.nhfb, NT, 0, st, gd);
+                SVTB_LAUNCH((cdef_search_grid_kernel<uint8_t, 4>), dim3(d.nvfb * d.nhfb, 2), NT, 0, st, gd);
         }
     } else if (d.recon.hbd)
         SVTB_LAUNCH(cdef_search_kernel<uint16_t>, d.nvfb * d.nhfb, NT, 0, st, d);

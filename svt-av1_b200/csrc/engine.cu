@@ -23,6 +23,7 @@
 #include <condition_variable>
 #include <mutex>
 #include <thread>
+#include <sys/resource.h>
 #include <vector>
 
 #include "common.cuh"
@@ -405,10 +406,23 @@ void run_copies(SvtB200Engine *e, const RowCopy (&c)[3]) {
     struct Tr {
         uint64_t t0;
         size_t n;
+        int to_host;
+        rusage r0;
         ~Tr() {
-            if (t0) fprintf(stderr, "engine trace: picture copy %.1f MB in %.3f ms\n", n / 1e6, (now_ns() - t0) / 1e6);
+            if (!t0) return;
+            rusage r1;
+            getrusage(RUSAGE_THREAD, &r1);
+            fprintf(stderr, "engine trace: picture copy %s %.1f MB in %.3f ms (minflt %ld majflt %ld nvcsw %ld nivcsw %ld cpu %.3f ms)\n",
+                    to_host ? "pinned->host" : "host->pinned", n / 1e6, (now_ns() - t0) / 1e6, r1.ru_minflt - r0.ru_minflt,
+                    r1.ru_majflt - r0.ru_majflt, r1.ru_nvcsw - r0.ru_nvcsw, r1.ru_nivcsw - r0.ru_nivcsw,
+                    ((r1.ru_utime.tv_sec - r0.ru_utime.tv_sec) + (r1.ru_stime.tv_sec - r0.ru_stime.tv_sec)) * 1e3 +
+                        ((r1.ru_utime.tv_usec - r0.ru_utime.tv_usec) + (r1.ru_stime.tv_usec - r0.ru_stime.tv_usec)) / 1e3);
         }
-    } tr{t0, total};
+    } tr{t0, total, 0, {}};
+    if (trace) {
+        getrusage(RUSAGE_THREAD, &tr.r0);
+        tr.to_host = c[0].dst_pitch != c[0].bytes; // unpack writes strided host rows
+    }
     const int nt = total > (4u << 20) ? std::max(1, std::min(4, max_threads)) : 1;
     auto part = [&c, nt](int t) {
         for (const RowCopy &k : c) copy_rows(k, (int)((int64_t)k.rows * t / nt), (int)((int64_t)k.rows * (t + 1) / nt));

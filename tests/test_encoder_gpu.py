@@ -61,12 +61,18 @@ def test_360p_preset8_device_side_me_downsample(tmp_path):
 
 @skip_if_unbuilt
 def test_10bit_preset6_bitstream_and_recon_md5(tmp_path):
-    """A 10-bit preset-6 clip (the configs[2] stage set at a small size): 16-bit pipeline, loop_filter_mode 3 (the frame is
-    deblocked in dlf_kernel), CDEF on 16-bit planes, restoration on the CPU."""
-    clip = _clip(tmp_path, 640, 360, 12, 10)
-    ref = ec.run_variant("ref_c", clip, 640, 360, 12, 6, 50, 10, str(tmp_path))
-    gpu = ec.run_variant("cuda_c", clip, 640, 360, 12, 6, 50, 10, str(tmp_path))
+    """A 10-bit preset-6 clip (the configs[2] stage set at a small size): 16-bit pipeline, loop_filter_mode 3 (level search +
+    deblocking in dlf_kernel as one GPU call), CDEF on 16-bit planes, restoration search on the CPU and apply on the GPU."""
+    clip = _clip(tmp_path, 640, 360, 24, 10)
+    ref = ec.run_variant("ref_c", clip, 640, 360, 24, 6, 50, 10, str(tmp_path))
+    gpu = ec.run_variant("cuda_c", clip, 640, 360, 24, 6, 50, 10, str(tmp_path), extra_env={"SVT_CUDA_PROFILE": "1"})
     _same(ref, gpu)
+    import re
+    m = re.search(r"engine: (\d+) ME pictures .*?, (\d+) dlf, (\d+) cdef, (\d+) lr", " ".join(gpu.get("log", [])))
+    n_me, n_dlf, n_cdef, n_lr = (int(x) for x in m.groups())
+    # every picture is deblocked (level search included) and CDEF-filtered on the GPU; the pictures whose restoration search
+    # (CPU) picked Wiener / self-guided units are restored on the GPU from the saved boundary lines
+    assert n_dlf == 24 and n_cdef == 24 and n_me >= 22 and n_lr >= 1, gpu.get("log")
 
 
 @skip_if_unbuilt

@@ -36,8 +36,14 @@ def main():
                 u = units[hdr.index(metric)] if metric in hdr else ""
                 return v * {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0, "msecond": 1e3, "usecond": 1.0, "nsecond": 1e-3}.get(u, 1.0)
             short = name.split("(")[0].split("::")[-1].split("<")[0].strip()
-            t = traffic.setdefault(short, {"launches": 0, "dram_bytes": 0.0, "time_us": 0.0})
+            t = traffic.setdefault(short, {"launches": 0, "dram_bytes": 0.0, "time_us": 0.0, "alu_pipe_pct": 0.0, "issue_active_pct": 0.0,
+                                           "warps_active_pct": 0.0})
             t["launches"] += 1
+            # pipe / issue utilisation: mean over the captured launches of the kernel (the ALU roofline of VERDICT r1 item 5)
+            for key, metric in (("alu_pipe_pct", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                                ("issue_active_pct", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                                ("warps_active_pct", "sm__warps_active.avg.pct_of_peak_sustained_active")):
+                t[key] += (val(metric) - t[key]) / t["launches"]
             t["dram_bytes"] += val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
             t["time_us"] += val("gpu__time_duration.sum")
         if name in seen:
