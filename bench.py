@@ -54,6 +54,10 @@ B = os.path.join(ROOT, "integration", "_build")
 BIN = {"cuda": os.path.join(B, "enc_bench_cuda_simd"), "ref": os.path.join(B, "enc_bench_ref_simd"),
        "app_cuda": os.path.join(B, "SvtAv1EncAppCudaSimd")}
 _REAL_STDOUT = None
+# N > 1 streams: each stream is confined to its own group of cores (cpu_partition).  SVTB200_BENCH_LP=1 additionally passes
+# `--lp <group size>` (the encoder then sizes its thread / picture pools for the group); the default leaves the encoder's own
+# sizing (for the whole host) in place, which measured faster for both arms (profiles/r2_scaling_lp_experiment.txt)
+USE_LP = os.environ.get("SVTB200_BENCH_LP", "0") == "1"
 
 
 def emit(obj):
@@ -143,7 +147,7 @@ def start_enc(kind, clip, frames, warm_frames, out=None, env_extra=None, cpus=No
         if k.startswith("SVT_CUDA"):
             del env[k]
     env.update(env_extra or {})
-    if cpus and "ENC_BENCH_LP" not in env and env.get("SVTB200_STREAMS", "1") != "1":
+    if cpus and "ENC_BENCH_LP" not in env and env.get("SVTB200_STREAMS", "1") != "1" and USE_LP:
         env["ENC_BENCH_LP"] = str(len(cpus))  # thread / segment counts sized for this stream's share of the host
     cmd = [BIN[kind], clip, str(W), str(H), str(frames), str(BITS), str(PRESET), str(QP), str(warm_frames)] + ([out] if out else [])
 
@@ -182,7 +186,7 @@ def app_average_speed(clip, frames, env_extra, cpus):
     env.update(env_extra)
     cmd = [BIN["app_cuda"], "-i", clip, "-w", str(W), "-h", str(H), "--fps", "30", "--preset", str(PRESET), "--rc", "0", "-q", str(QP),
            "-n", str(frames), "-b", ivf] + (["--input-depth", str(BITS)] if BITS != 8 else [])
-    if cpus and env.get("SVTB200_STREAMS", "1") != "1":
+    if cpus and env.get("SVTB200_STREAMS", "1") != "1" and USE_LP:
         cmd += ["--lp", str(len(cpus))]
 
     def pre():
