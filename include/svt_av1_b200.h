@@ -935,6 +935,15 @@ typedef int (*SvtB200CdefDecideFn)(void *user, const uint64_t *mse, SvtB200CdefA
 SVT_B200_API int svt_b200_engine_cdef_frame(SvtB200Engine *e, const SvtB200CdefSearchParams *sp, const SvtB200Frame *recon,
                                             const SvtB200Frame *source, const uint8_t *skip8, int32_t skip_stride,
                                             uint64_t *mse, SvtB200CdefDecideFn decide, void *user);
+/* The same preceded by the deblocking of the picture (dlf != NULL; mi: host array [mi_rows][mi_cols]): the reconstruction
+ * is uploaded ONCE, deblocked on the device and handed to the CDEF stages there - for pictures whose deblocked version
+ * nobody needs on the host (no loop restoration: svt_av1_loop_restoration_save_boundary_lines would read it).  When
+ * `decide` returns 0 (no apply) the host reconstruction is left as it was: the reference does not filter a picture nobody
+ * reads. */
+SVT_B200_API int svt_b200_engine_dlf_cdef_frame(SvtB200Engine *e, const SvtB200DlfParams *dlf, const SvtB200DlfMi *mi,
+                                                const SvtB200CdefSearchParams *sp, const SvtB200Frame *recon,
+                                                const SvtB200Frame *source, const uint8_t *skip8, int32_t skip_stride,
+                                                uint64_t *mse, SvtB200CdefDecideFn decide, void *user);
 
 #ifdef __cplusplus
 }

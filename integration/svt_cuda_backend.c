@@ -11,6 +11,7 @@
  *   SVT_CUDA=1            turn the CUDA backend on (default: off -> the build behaves exactly like the reference)
  *   SVT_CUDA_DEVICE=n     CUDA ordinal (default 0)
  *   SVT_CUDA_ME / SVT_CUDA_DLF / SVT_CUDA_CDEF / SVT_CUDA_LR = 0 to leave one stage on the CPU (default 1 when SVT_CUDA=1)
+ *   SVT_CUDA_FUSE=0       deblock in the DLF stage's own GPU call instead of deferring it into the CDEF stage's call
  *   SVT_CUDA_ME_DS=1      derive the 1/4 and 1/16 ME planes on the device instead of uploading the host's
  *   SVT_CUDA_PROFILE=1    print per-stage wall time / call counts at deinit (also for the CPU path, for comparison)
  * There is NO CPU fallback once a stage is on: a failing GPU call prints the library's message and aborts.
@@ -41,7 +42,7 @@
 #include "svt_av1_b200.h"
 #include "svt_cuda_backend.h"
 
-static int            g_on = -1, g_me = 0, g_dlf = 0, g_cdef = 0, g_lr = 0, g_me_ds = 0, g_prof = 0;
+static int            g_on = -1, g_me = 0, g_dlf = 0, g_cdef = 0, g_lr = 0, g_fuse = 0, g_me_ds = 0, g_prof = 0;
 static SvtB200Engine *g_engine = NULL;
 static int            g_users  = 0;
 
@@ -83,6 +84,7 @@ void svt_cuda_backend_init(void) {
             g_dlf   = env_flag("SVT_CUDA_DLF", 1);
             g_cdef  = env_flag("SVT_CUDA_CDEF", 1);
             g_lr    = env_flag("SVT_CUDA_LR", 1);
+            g_fuse  = env_flag("SVT_CUDA_FUSE", 1);
             g_me_ds = env_flag("SVT_CUDA_ME_DS", 0);
         }
     }
@@ -333,16 +335,21 @@ static void flatten_mi(SvtB200DlfMi *f, const MbModeInfo *mbmi, const LoopFilter
     f->pad[0] = f->pad[1] = 0;
 }
 
+static SvtB200DlfMi *flatten_picture_into(PictureControlSet *pcs_ptr, SvtB200DlfMi *dst);
 static SvtB200DlfMi *flatten_picture(PictureControlSet *pcs_ptr) {
-    PictureParentControlSet *ppcs    = pcs_ptr->parent_pcs_ptr;
-    const int                mi_rows = ppcs->av1_cm->mi_rows, mi_cols = ppcs->av1_cm->mi_cols;
-    const size_t             n       = (size_t)mi_rows * mi_cols;
+    PictureParentControlSet *ppcs = pcs_ptr->parent_pcs_ptr;
+    const size_t             n    = (size_t)ppcs->av1_cm->mi_rows * ppcs->av1_cm->mi_cols;
     if (t_mi_cap < n) {
         free(t_mi);
         t_mi     = (SvtB200DlfMi *)malloc(n * sizeof(SvtB200DlfMi));
         t_mi_cap = n;
         if (!t_mi) die("malloc", -1);
     }
+    return flatten_picture_into(pcs_ptr, t_mi);
+}
+static SvtB200DlfMi *flatten_picture_into(PictureControlSet *pcs_ptr, SvtB200DlfMi *t_mi) {
+    PictureParentControlSet *ppcs    = pcs_ptr->parent_pcs_ptr;
+    const int                mi_rows = ppcs->av1_cm->mi_rows, mi_cols = ppcs->av1_cm->mi_cols;
     const LoopFilterInfoN *lfi_n = &ppcs->lf_info;
     /* Every 4x4 cell owns a ModeInfo (EbAdaptiveMotionVectorPrediction.c update_mi_map fills all cells of a block alike), and
      * dereferencing each one is a cache miss: 518k of them at 2160p.  A block's entry is computed at its first cell of a
@@ -377,6 +384,47 @@ static EbPictureBufferDesc *recon_of(PictureControlSet *pcs_ptr, int is_16bit) {
 
 static __thread const PictureControlSet *t_filtered = NULL; /* svt_cuda_dlf_pick_frame already deblocked this picture */
 
+/* Deblocking deferred into the CDEF stage's GPU call (svt_b200_engine_dlf_cdef_frame): the DLF stage only derives the
+ * parameters; the reconstruction is then uploaded once for both filters.  Only when nobody needs the deblocked picture on the
+ * host: no loop restoration (its boundary lines are saved from the deblocked host picture in dlf_kernel), no statistics. */
+#include <pthread.h>
+typedef struct PendingDlf {
+    const PictureControlSet *pcs;
+    SvtB200DlfParams         p;
+    SvtB200DlfMi *           mi;
+    size_t                   cap;
+    int                      used;
+} PendingDlf;
+#define N_PENDING 64
+static PendingDlf      g_pend[N_PENDING];
+static pthread_mutex_t g_pend_mu = PTHREAD_MUTEX_INITIALIZER;
+
+static int fuse_ok(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr) {
+    return g_fuse && svt_cuda_cdef_applies(pcs_ptr, scs_ptr) && scs_ptr->seq_header.cdef_level && pcs_ptr->parent_pcs_ptr->cdef_level &&
+        !scs_ptr->seq_header.enable_restoration && !scs_ptr->static_config.stat_report;
+}
+static PendingDlf *pending_take(const PictureControlSet *pcs_ptr, int create) {
+    PendingDlf *e = NULL;
+    pthread_mutex_lock(&g_pend_mu);
+    for (int i = 0; i < N_PENDING && !e; i++)
+        if (g_pend[i].used && g_pend[i].pcs == pcs_ptr) e = &g_pend[i];
+    if (!e && create)
+        for (int i = 0; i < N_PENDING && !e; i++)
+            if (!g_pend[i].used) {
+                e       = &g_pend[i];
+                e->used = 1;
+                e->pcs  = pcs_ptr;
+            }
+    pthread_mutex_unlock(&g_pend_mu);
+    return e;
+}
+static void pending_release(PendingDlf *e) {
+    pthread_mutex_lock(&g_pend_mu);
+    e->used = 0;
+    e->pcs  = NULL;
+    pthread_mutex_unlock(&g_pend_mu);
+}
+
 /* Deblocks the reconstruction of pcs in place on the GPU (only called when svt_cuda_dlf_applies).  The caller has run
  * svt_av1_loop_filter_init, svt_av1_pick_filter_level and - as svt_av1_loop_filter_frame does first (:724) -
  * svt_av1_loop_filter_frame_init(frm_hdr, lf_info, 0, 3) is run here. */
@@ -393,7 +441,19 @@ void svt_cuda_dlf_frame(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr,
     svt_av1_loop_filter_frame_init(frm_hdr, &ppcs->lf_info, 0, 3);
     const int64_t t0      = g_prof ? now_ns() : 0;
     const int     mi_rows = ppcs->av1_cm->mi_rows, mi_cols = ppcs->av1_cm->mi_cols;
-    SvtB200DlfMi *mi      = flatten_picture(pcs_ptr);
+    PendingDlf *  pend    = fuse_ok(pcs_ptr, scs_ptr) ? pending_take(pcs_ptr, 1) : NULL;
+    SvtB200DlfMi *mi;
+    if (pend) {
+        const size_t n = (size_t)mi_rows * mi_cols;
+        if (pend->cap < n) {
+            free(pend->mi);
+            pend->mi  = (SvtB200DlfMi *)malloc(n * sizeof(SvtB200DlfMi));
+            pend->cap = n;
+            if (!pend->mi) die("malloc", -1);
+        }
+        mi = flatten_picture_into(pcs_ptr, pend->mi);
+    } else
+        mi = flatten_picture(pcs_ptr);
     SvtB200DlfParams p;
     memset(&p, 0, sizeof(p));
     p.mi_rows         = mi_rows;
@@ -406,6 +466,11 @@ void svt_cuda_dlf_frame(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr,
     p.filter_level_v  = frm_hdr->loop_filter_params.filter_level_v;
     p.plane_start     = 0;
     p.plane_end       = 3;
+    if (pend) { /* the CDEF stage's call deblocks first (svt_cuda_cdef_picture) */
+        pend->p = p;
+        if (g_prof) stat_add(1, ST_DLF, t0);
+        return;
+    }
     SvtB200Frame f;
     host_frame(&f, recon_buffer, is_16bit, mi_cols * 4, mi_rows * 4);
     int rc = svt_b200_engine_dlf_frame(g_engine, &p, &f, mi);
@@ -600,9 +665,12 @@ void svt_cuda_cdef_picture(PictureControlSet *pcs_ptr, SequenceControlSet *scs_p
     recon.height = source.height = mi_rows * 4;
     recon.bit_depth = source.bit_depth = is_16bit ? 10 : 8;
 
-    CdefDecide d = {pcs_ptr, scs_ptr, nvfb, nhfb, t_skip, skip_stride, rows8, (mi_cols + 1) / 2};
-    int rc = svt_b200_engine_cdef_frame(g_engine, &sp, &recon, &source, t_skip, skip_stride, t_mse, cdef_decide, &d);
-    if (rc) die("svt_b200_engine_cdef_frame", rc);
+    CdefDecide  d    = {pcs_ptr, scs_ptr, nvfb, nhfb, t_skip, skip_stride, rows8, (mi_cols + 1) / 2};
+    PendingDlf *pend = pending_take(pcs_ptr, 0); /* deblocking deferred by the DLF stage: same upload, deblock, then CDEF */
+    int rc = svt_b200_engine_dlf_cdef_frame(g_engine, pend ? &pend->p : NULL, pend ? pend->mi : NULL, &sp, &recon, &source, t_skip,
+                                            skip_stride, t_mse, cdef_decide, &d);
+    if (pend) pending_release(pend);
+    if (rc) die("svt_b200_engine_dlf_cdef_frame", rc);
     if (g_prof) stat_add(1, ST_CDEF, t0);
 }
 

@@ -232,7 +232,7 @@ int ensure_filt(SvtB200Engine *e, int w, int h, int bd, int mi_rows, int mi_cols
     g.skip = al256((size_t)((mi_rows + 1) / 2) * ((((mi_cols + 1) / 2) + 15) & ~15));
     g.mse = al256(g.nfb * 2 * 64 * 8);
     g.small = g.skip + g.mse + al256(g.nfb);
-    g.misc = std::max(g.mi + 4096, g.small); // + the level search's scratch (level table, SSE accumulator)
+    g.misc = g.mi + 4096 + g.small; // mode-info summary | the level search's scratch | skip map, mse, filter-block indices
     const size_t dev_total = (size_t)kFiltSlots * (3 * g.frame + g.misc);
     const size_t pin_b = std::max(g.packed, g.mi);
     const size_t pin_total = (size_t)kFiltSlots * (g.packed + pin_b + g.small);
@@ -869,9 +869,15 @@ int svt_b200_engine_lr_frame(SvtB200Engine *e, const SvtB200LrFrameParams *p, co
 int svt_b200_engine_cdef_frame(SvtB200Engine *e, const SvtB200CdefSearchParams *sp, const SvtB200Frame *recon,
                                const SvtB200Frame *source, const uint8_t *skip8, int32_t skip_stride, uint64_t *mse,
                                SvtB200CdefDecideFn decide, void *user) {
+    return svt_b200_engine_dlf_cdef_frame(e, nullptr, nullptr, sp, recon, source, skip8, skip_stride, mse, decide, user);
+}
+
+int svt_b200_engine_dlf_cdef_frame(SvtB200Engine *e, const SvtB200DlfParams *dlf, const SvtB200DlfMi *mi,
+                                   const SvtB200CdefSearchParams *sp, const SvtB200Frame *recon, const SvtB200Frame *source,
+                                   const uint8_t *skip8, int32_t skip_stride, uint64_t *mse, SvtB200CdefDecideFn decide, void *user) {
     if (!e || !sp || !recon || !source || !skip8 || !mse || !decide || recon->width != source->width ||
-        recon->height != source->height || recon->bit_depth != source->bit_depth) {
-        set_error("svt_b200_engine_cdef_frame: bad argument");
+        recon->height != source->height || recon->bit_depth != source->bit_depth || (dlf && (!mi || dlf->mi_stride != dlf->mi_cols))) {
+        set_error("svt_b200_engine_dlf_cdef_frame: bad argument");
         return SVT_B200_ERR_ARG;
     }
     DeviceGuard dg(e->device);
@@ -884,11 +890,36 @@ int svt_b200_engine_cdef_frame(SvtB200Engine *e, const SvtB200CdefSearchParams *
         set_error("svt_b200_engine_cdef_frame: skip map / filter-block count larger than the sequence geometry");
         return SVT_B200_ERR_ARG;
     }
+    const size_t b_mi = dlf ? (size_t)dlf->mi_rows * dlf->mi_cols * sizeof(SvtB200DlfMi) : 0;
+    if (b_mi > g.mi) {
+        set_error("svt_b200_engine_dlf_cdef_frame: mode-info array larger than the sequence geometry");
+        return SVT_B200_ERR_ARG;
+    }
     FiltSlot *s = acquire(e, e->filt);
     do {
-        uint8_t *d_skip = s->misc, *d_mse = s->misc + g.skip, *d_idx = d_mse + g.mse;
+        uint8_t *d_small = s->misc + g.mi + 4096; // the mode-info summary (deblocking) occupies the head of misc
+        uint8_t *d_skip = d_small, *d_mse = d_small + g.skip, *d_idx = d_mse + g.mse;
         uint8_t *h_skip = s->pin_small, *h_mse = h_skip + g.skip, *h_idx = h_mse + g.mse;
         pack_frame(e, s->pin_a, recon);
+        if (dlf) { // the deblocking the DLF stage deferred: same upload of the reconstruction serves both filters
+            {
+                Lap lap(e->stats.ns_host_copy);
+                par_memcpy(s->pin_b, mi, b_mi);
+            }
+            Lap lap(e->stats.ns_issue);
+            if (cudaMemcpyAsync(s->misc, s->pin_b, b_mi, cudaMemcpyHostToDevice, s->st) != cudaSuccess) {
+                rc = SVT_B200_ERR_CUDA;
+                break;
+            }
+            if ((rc = copy_packed(e, &s->recon, s->pin_a, cudaMemcpyHostToDevice, s->st)) != SVT_B200_OK) break;
+            if ((rc = svt_b200_dlf_frame(dlf, &s->recon, (const SvtB200DlfMi *)s->misc, s->st)) != SVT_B200_OK) break;
+            if (timed_sync(e, s->st) != cudaSuccess) { // pin_b is reused for the source picture below
+                rc = SVT_B200_ERR_CUDA;
+                break;
+            }
+            e->stats.dlf_frames++;
+            e->stats.h2d_bytes += b_mi;
+        }
         pack_frame(e, s->pin_b, source);
         memcpy(h_skip, skip8, b_skip);
         {
@@ -898,7 +929,7 @@ int svt_b200_engine_cdef_frame(SvtB200Engine *e, const SvtB200CdefSearchParams *
                 rc = SVT_B200_ERR_CUDA;
                 break;
             }
-            if ((rc = copy_packed(e, &s->recon, s->pin_a, cudaMemcpyHostToDevice, s->st)) != SVT_B200_OK) break;
+            if (!dlf && (rc = copy_packed(e, &s->recon, s->pin_a, cudaMemcpyHostToDevice, s->st)) != SVT_B200_OK) break;
             if ((rc = copy_packed(e, &s->source, s->pin_b, cudaMemcpyHostToDevice, s->st)) != SVT_B200_OK) break;
             if ((rc = svt_b200_cdef_search(sp, &s->recon, &s->source, d_skip, skip_stride, (uint64_t *)d_mse, s->st)) != SVT_B200_OK)
                 break;
