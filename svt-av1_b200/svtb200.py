@@ -173,6 +173,23 @@ SUBPEL_JOB_DTYPE = [("blk_x", "<i2"), ("blk_y", "<i2"), ("bw", "u1"), ("bh", "u1
 SUBPEL_RESULT_DTYPE = [("mv_row", "<i2"), ("mv_col", "<i2"), ("besterr", "<i4"), ("distortion", "<i4"), ("sse", "<u4")]
 
 
+class HostMePicture(C.Structure):  # SvtB200HostMePicture
+    _fields_ = [("key", C.c_void_p), ("tag", C.c_uint64), ("full", C.c_void_p), ("quarter", C.c_void_p), ("sixteenth", C.c_void_p)]
+
+
+class HostLrLines(C.Structure):  # SvtB200HostLrLines
+    _fields_ = [("above", C.c_void_p), ("below", C.c_void_p), ("stride", C.c_int32)]
+
+
+class EngineStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("me_pictures", "dlf_frames", "cdef_frames", "lr_frames", "me_plane_uploads", "me_plane_hits",
+                                          "h2d_bytes", "d2h_bytes", "pinned_bytes", "ns_slot_wait", "ns_pin", "ns_plane_wait", "ns_issue",
+                                          "ns_sync", "ns_host_copy", "pin_calls")]
+
+
+CDEF_DECIDE_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(CdefApplyParams), C.POINTER(C.c_int8))
+
+
 def preset8_me_params(width, height, n_l0=1, n_l1=1, dist=((1, 2, 3, 4), (1, 2, 3, 4)), temporal_layer=1,
                       is_ref=1):
     """ME parameters of preset 8 (ENC_M8) at >=720p, 30 fps, as set_me_hme_params_oq /
