@@ -428,6 +428,32 @@ SVT_B200_API int svt_b200_encode_tus(const SvtB200EncodeParams *p, const SvtB200
                                      const SvtB200Frame *pred, const SvtB200Frame *recon,
                                      const SvtB200Tu *tus, int32_t n_tus, int32_t *qcoeff, uint16_t *eob,
                                      void *scratch, void *stream);
+/* The dispatcher generality of av1_estimate_transform / av1_quantize_inv_quantize for the fused path (EbTransforms.c:3613-3670
+ * trans_coeff_shape; EbFullLoop.c:1400-1470 table set by q_index): transform units of MIXED sizes, partial-frequency shapes
+ * and quantiser sets in one call.  tus: HOST array, bucketed by (tx_size, pf_shape, qset) inside - one launch of the
+ * size-specialised kernel per bucket.  Outputs in INPUT order: eob[i], cul_level[i] (device; cul_level may be NULL) and the
+ * levels of unit i at qcoeff + qcoeff_offsets[i] (device; min(w,32)*min(h,32) int32 each); qcoeff_offsets: HOST array of
+ * n_tus + 1 entries filled by the call (qcoeff must hold qcoeff_offsets[n_tus] entries: <= 1024 per unit).
+ * scratch: device memory, >= 28 bytes per unit + 256.  Synchronous on `stream` (returns when the results are complete). */
+typedef struct SvtB200TuEx {
+    int32_t x, y;     /* top-left sample inside its plane */
+    uint8_t plane;    /* 0 Y, 1 Cb, 2 Cr */
+    uint8_t tx_type;  /* TxType */
+    uint8_t tx_size;  /* TxSize, TX_4X4 = 0 ... TX_64X16 = 18 */
+    uint8_t pf_shape; /* EB_TRANS_COEFF_SHAPE: 0 DEFAULT_SHAPE, 1 N2_SHAPE, 2 N4_SHAPE, 3 ONLY_DC_SHAPE (EbDefinitions.h:2611-2614) */
+    uint16_t qset;    /* index into SvtB200EncodeParamsEx::qsets (one per distinct q_index in the picture) */
+    uint16_t reserved;
+} SvtB200TuEx;
+typedef struct SvtB200EncodeParamsEx {
+    int32_t use_fp;                      /* as SvtB200EncodeParams::use_fp */
+    int32_t n_qsets;
+    const SvtB200QuantPlane (*qsets)[3]; /* HOST array [n_qsets][3 planes] */
+} SvtB200EncodeParamsEx;
+SVT_B200_API int svt_b200_encode_tus_ex(const SvtB200EncodeParamsEx *p, const SvtB200Frame *src, const SvtB200Frame *pred,
+                                        const SvtB200Frame *recon, const SvtB200TuEx *tus, int32_t n_tus, int32_t *qcoeff,
+                                        int64_t *qcoeff_offsets, uint16_t *eob, int32_t *cul_level, void *scratch,
+                                        size_t scratch_bytes, void *stream);
+
 /* Device -> host hand-over of the levels: the entropy coder reads a TU's levels in scan order up to eob
  * (av1_write_coeffs_txb_1d), so instead of n int32 per TU the host can fetch `packed` = the eob[b] levels of TU b in scan
  * order at packed[offsets[b] .. offsets[b+1]) (offsets: exclusive prefix sum of eob, n_tus + 1 entries; *total = the

@@ -65,6 +65,8 @@ ORC_API void orc_fwd_txfm2d(const int16_t *input, int32_t *output, uint32_t stri
 ORC_API void orc_fwd_txfm2d_pf(const int16_t *input, int32_t *output, uint32_t stride, int tx_type, int tx_size,
                                int bit_depth, int shift);
 ORC_API uint64_t orc_handle_transform64(int32_t *output, int tx_size);
+ORC_API uint64_t orc_estimate_transform(const int16_t *res, uint32_t stride, int32_t *coeff, int tx_size, int bit_depth,
+                                        int tx_type, int shape);
 ORC_API void orc_inv_txfm2d_add(const int32_t *input, const uint16_t *pred, int32_t stride_r, uint16_t *recon,
                                 int32_t stride_w, int tx_type, int tx_size, int bd);
 ORC_API void orc_residual(const void *src, uint32_t src_stride, const void *pred, uint32_t pred_stride, int16_t *res,

@@ -675,6 +675,17 @@ static void ref_inv(int tx_size, const int32_t *dq, uint16_t *pr, int sr, uint16
     }
 }
 
+/* The reference's own dispatcher (EbTransforms.c:3613): every shape, every size, through its RTCD pointers. */
+#include "EbTransforms.h"
+REFH_API uint64_t refh_estimate_transform(int16_t *res, uint32_t stride, int32_t *coeff, int tx_size, int bit_depth, int tx_type,
+                                          int shape) {
+    refh_init();
+    uint64_t energy = 0;
+    av1_estimate_transform(res, stride, coeff, 0, (TxSize)tx_size, &energy, (uint32_t)bit_depth, (TxType)tx_type, PLANE_TYPE_Y,
+                           (EB_TRANS_COEFF_SHAPE)shape);
+    return energy;
+}
+
 REFH_API int refh_encode_tus(const SvtB200EncodeParams *p, const SvtB200Frame *src, const SvtB200Frame *pred,
                              const SvtB200Frame *recon, const SvtB200Tu *tus, int n_tus, int32_t *qcoeff, uint16_t *eobs) {
     refh_init();

@@ -434,6 +434,30 @@ uint64_t orc_handle_transform64(int32_t *output, int tx_size) {
     return e;
 }
 
+/* av1_estimate_transform (EbTransforms.c:3613-3670): the trans_coeff_shape dispatcher of the encoder.
+ *   DEFAULT_SHAPE  (:3434-3600) forward transform, then for 64-sized units the discarded-area energy / zero / re-pack;
+ *   N2 / N4 SHAPE  (:3052-3405) the top-left (w>>s) x (h>>s) coefficients only; 64-sized units are re-packed 32 wide by
+ *                  handle_transform*_N2_N4 (:2933-2965), which report an energy of 0;
+ *   ONLY_DC_SHAPE  (:3407-3430) the N4 result with every entry but coefficient 0 cleared.
+ * coeff: w*h entries (the packed layout of 64-sized units occupies the first min(w,32)*min(h,32)). Returns the energy. */
+uint64_t orc_estimate_transform(const int16_t *res, uint32_t stride, int32_t *coeff, int tx_size, int bit_depth, int tx_type,
+                                int shape) {
+    const int w = k_txw[tx_size], h = k_txh[tx_size];
+    if (shape == 0) {
+        orc_fwd_txfm2d(res, coeff, stride, tx_type, tx_size, bit_depth);
+        return (w == 64 || h == 64) ? orc_handle_transform64(coeff, tx_size) : 0;
+    }
+    orc_fwd_txfm2d_pf(res, coeff, stride, tx_type, tx_size, bit_depth, shape == 1 ? 1 : 2);
+    if (w == 64 || h == 64) orc_handle_transform64(coeff, tx_size); /* the dropped area is already zero: re-pack only */
+    if (shape == 3) {
+        /* the clearing loop of :3424-3429 walks w-wide indices over the N4 result; every entry the N4 transform left
+         * non-zero satisfies its condition, so exactly coefficient 0 survives */
+        for (int i = 1; i < w * h; i++)
+            if (i % w < (w >> 2) || i / w < (h >> 2)) coeff[i] = 0;
+    }
+    return 0;
+}
+
 static void inv_1d(int32_t *x, int s, int n, int kind, int bit, int clamp_bit) {
     if (kind == 0) orc_idct(x, s, n, bit, clamp_bit);
     else if (kind == 3) { /* iidentity: same scaling as forward */

@@ -15,6 +15,9 @@
 // are packed several per CTA.  In the fused kernel HBM sees only src + pred in and qcoeff + recon out
 // (7 B/px for 8-bit) — the int32 coefficient planes of the reference's five separate calls never
 // leave the SM.
+#include <algorithm>
+#include <vector>
+
 #include "common.cuh"
 #include "txfm.cuh"
 
@@ -324,6 +327,9 @@ struct EncodeDev {
     int32_t *qcoeff; // [n_tus][iw*ih]
     uint16_t *eob; // [n_tus]
     int32_t *cul_level; // [n_tus] or null: av1_quantize_inv_quantize's return value (EbFullLoop.c:1596-1608)
+    int pf_shape; // EB_TRANS_COEFF_SHAPE of av1_estimate_transform: 0 default, 1 N2, 2 N4, 3 ONLY_DC (EbTransforms.c:3613-3670)
+    const long long *qoff; // null: TU b writes qcoeff + b * n, eob[b]; else qcoeff + qoff[b] and eob / cul_level [out_idx[b]]
+    const int32_t *out_idx;
 };
 // four horizontally adjacent samples at p (any alignment): aligned 32-bit loads + funnel shift for bytes
 template <typename T>
@@ -414,12 +420,16 @@ __global__ void __launch_bounds__(TX_NT) encode_tu_kernel(const __grid_constant_
         const int log_scale = (w * h > 256) + (w * h > 1024); // av1_get_tx_scale
         const int mode = d.quant_mode + (d.hbd ? 1 : 0);
         const int16_t *iscan = d.iscan[(t.vk != 3 && t.hk == 3) ? 1 : (t.vk == 3 && t.hk != 3) ? 2 : 0];
-        int32_t *qout = d.qcoeff + (size_t)b * n;
+        int32_t *qout = d.qoff ? d.qcoeff + d.qoff[b] : d.qcoeff + (size_t)b * n;
+        // partial-frequency shapes: the N2 / N4 transforms produce the top-left half / quarter (per dimension) of the
+        // default transform's coefficients and zeros elsewhere; ONLY_DC keeps coefficient 0 alone
+        const int kw = d.pf_shape == 3 ? 1 : min(iw, w >> d.pf_shape), kh = d.pf_shape == 3 ? 1 : min(ih, h >> d.pf_shape);
         int eob = 0, lvl = 0;
         for (int i = li; i < n; i += Tn) {
             const int r = i >> liw, c = i & (iw - 1);
             int32_t qc, dqc;
-            quant_one(mode, buf[r * pitch + c], i != 0, d.q[pl], log_scale, 32, 32, qc, dqc);
+            const int32_t coef = (r < kh && c < kw) ? buf[r * pitch + c] : 0;
+            quant_one(mode, coef, i != 0, d.q[pl], log_scale, 32, 32, qc, dqc);
             qout[i] = qc;
             buf[r * pitch + c] = dqc;
             if (qc) {
@@ -443,8 +453,9 @@ __global__ void __launch_bounds__(TX_NT) encode_tu_kernel(const __grid_constant_
     const int range_row = bd == 8 ? 16 : bd == 10 ? 18 : 20, range_col = bd == 8 ? 16 : bd == 10 ? 16 : 18;
     if (live) {
         if (li == 0) {
-            d.eob[b] = (uint16_t)s_eob[lb];
-            if (d.cul_level) d.cul_level[b] = min(63, s_cul[lb]) + (dc_sign == 1 ? 64 : dc_sign == 2 ? 128 : 0);
+            const int ob = d.out_idx ? d.out_idx[b] : b;
+            d.eob[ob] = (uint16_t)s_eob[lb];
+            if (d.cul_level) d.cul_level[ob] = min(63, s_cul[lb]) + (dc_sign == 1 ? 64 : dc_sign == 2 ? 128 : 0);
         }
         for (int r = li; r < t.h; r += Tn) {
             const int rect = t.rect, is0 = t.is0;
@@ -995,9 +1006,19 @@ int svt_b200_encode_tus(const SvtB200EncodeParams *p, const SvtB200Frame *src, c
     return svt_b200_encode_tus_cul(p, src, pred, recon, tus, n_tus, qcoeff, eob, nullptr, stream);
 }
 
+static int encode_launch(const SvtB200EncodeParams *p, int pf_shape, const long long *qoff, const int32_t *out_idx,
+                         const SvtB200Frame *src, const SvtB200Frame *pred, const SvtB200Frame *recon, const SvtB200Tu *tus,
+                         int32_t n_tus, int32_t *qcoeff, uint16_t *eob, int32_t *cul_level, void *stream);
+
 int svt_b200_encode_tus_cul(const SvtB200EncodeParams *p, const SvtB200Frame *src, const SvtB200Frame *pred,
                             const SvtB200Frame *recon, const SvtB200Tu *tus, int32_t n_tus, int32_t *qcoeff, uint16_t *eob,
                             int32_t *cul_level, void *stream) {
+    return encode_launch(p, 0, nullptr, nullptr, src, pred, recon, tus, n_tus, qcoeff, eob, cul_level, stream);
+}
+
+static int encode_launch(const SvtB200EncodeParams *p, int pf_shape, const long long *qoff, const int32_t *out_idx,
+                         const SvtB200Frame *src, const SvtB200Frame *pred, const SvtB200Frame *recon, const SvtB200Tu *tus,
+                         int32_t n_tus, int32_t *qcoeff, uint16_t *eob, int32_t *cul_level, void *stream) {
     if (!p || !src || !pred || !recon || !tus || !qcoeff || !eob || n_tus < 0 || p->tx_size < 0 || p->tx_size > 18 ||
         src->bit_depth != pred->bit_depth || src->bit_depth != recon->bit_depth) {
         set_error("svt_b200_encode_tus: bad argument");
@@ -1033,6 +1054,9 @@ int svt_b200_encode_tus_cul(const SvtB200EncodeParams *p, const SvtB200Frame *sr
     d.qcoeff = qcoeff;
     d.eob = eob;
     d.cul_level = cul_level;
+    d.pf_shape = pf_shape;
+    d.qoff = qoff;
+    d.out_idx = out_idx;
     // inverse scan tables of this size: built once per (device, tx_size) and kept resident (`scratch` is unused since
     // then; the parameter stays for ABI stability)
     const int16_t *tab = scan_tables(p->tx_size);
@@ -1058,5 +1082,78 @@ int svt_b200_encode_tus_cul(const SvtB200EncodeParams *p, const SvtB200Frame *sr
 #undef SVTB_ENC
     SVTB_CUDA_TRY(cudaGetLastError());
     return SVT_B200_OK;
+}
+
+// av1_estimate_transform's dispatcher generality for the fused path: a HOST list of transform units of MIXED
+// transform sizes, partial-frequency shapes and quantiser sets (per-block qindex / segment delta-q: av1_quantize_inv_quantize
+// picks the table by q_index, EbFullLoop.c:1400-1470).  The list is bucketed by (tx_size, pf_shape, qset) on the host, every
+// bucket is one launch of the size-specialised kernel, and the outputs land in INPUT order: eob[i] / cul_level[i], and the
+// levels of unit i at qcoeff + qcoeff_offsets[i] (min(w,32) * min(h,32) entries; offsets returned to the caller).
+int svt_b200_encode_tus_ex(const SvtB200EncodeParamsEx *p, const SvtB200Frame *src, const SvtB200Frame *pred,
+                           const SvtB200Frame *recon, const SvtB200TuEx *tus, int32_t n_tus, int32_t *qcoeff,
+                           int64_t *qcoeff_offsets, uint16_t *eob, int32_t *cul_level, void *scratch, size_t scratch_bytes,
+                           void *stream) {
+    if (!p || !tus || !qcoeff || !qcoeff_offsets || !eob || n_tus < 0 || !p->qsets || p->n_qsets < 1 || !scratch) {
+        set_error("svt_b200_encode_tus_ex: bad argument");
+        return SVT_B200_ERR_ARG;
+    }
+    const size_t per_tu = sizeof(TuDev) + sizeof(long long) + sizeof(int32_t);
+    if (scratch_bytes < (size_t)n_tus * per_tu + 256) {
+        set_error("svt_b200_encode_tus_ex: scratch too small (%zu bytes per unit + 256)", per_tu);
+        return SVT_B200_ERR_ARG;
+    }
+    // offsets in input order
+    long long off = 0;
+    for (int i = 0; i < n_tus; i++) {
+        const SvtB200TuEx &t = tus[i];
+        if (t.tx_size > 18 || t.pf_shape > 3 || t.plane > 2 || t.qset >= p->n_qsets) {
+            set_error("svt_b200_encode_tus_ex: unit %d out of range", i);
+            return SVT_B200_ERR_ARG;
+        }
+        qcoeff_offsets[i] = off;
+        off += (long long)std::min<int>(h_txw[t.tx_size], 32) * std::min<int>(h_txh[t.tx_size], 32);
+    }
+    qcoeff_offsets[n_tus] = off;
+    if (n_tus == 0) return SVT_B200_OK;
+    // bucket: stable sort of the indices by key
+    std::vector<int32_t> order(n_tus);
+    for (int i = 0; i < n_tus; i++) order[i] = i;
+    auto key = [&](int i) { return ((uint32_t)tus[i].tx_size << 24) | ((uint32_t)tus[i].pf_shape << 16) | tus[i].qset; };
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return key(a) < key(b); });
+    // staging: TuDev[n] | qoff[n] | out_idx[n] in pinned memory of the calling thread, one upload
+    ThreadCtx &c = tls();
+    c.reserve((size_t)n_tus * per_tu + 256);
+    TuDev *h_tu = reinterpret_cast<TuDev *>(c.h);
+    long long *h_qoff = reinterpret_cast<long long *>(c.h + (((size_t)n_tus * sizeof(TuDev) + 15) & ~(size_t)15));
+    int32_t *h_idx = reinterpret_cast<int32_t *>(reinterpret_cast<uint8_t *>(h_qoff) + (size_t)n_tus * sizeof(long long));
+    for (int k = 0; k < n_tus; k++) {
+        const SvtB200TuEx &t = tus[order[k]];
+        h_tu[k] = TuDev{t.x, t.y, t.plane, t.tx_type};
+        h_qoff[k] = qcoeff_offsets[order[k]];
+        h_idx[k] = order[k];
+    }
+    uint8_t *dsc = reinterpret_cast<uint8_t *>(scratch);
+    const size_t total = (size_t)(reinterpret_cast<uint8_t *>(h_idx + n_tus) - c.h);
+    cudaStream_t st = (cudaStream_t)stream;
+    SVTB_CUDA_TRY(cudaMemcpyAsync(dsc, c.h, total, cudaMemcpyHostToDevice, st));
+    const TuDev *d_tu = reinterpret_cast<const TuDev *>(dsc);
+    const long long *d_qoff = reinterpret_cast<const long long *>(dsc + (reinterpret_cast<uint8_t *>(h_qoff) - c.h));
+    const int32_t *d_idx = reinterpret_cast<const int32_t *>(dsc + (reinterpret_cast<uint8_t *>(h_idx) - c.h));
+    int rc = SVT_B200_OK;
+    for (int k0 = 0; k0 < n_tus && rc == SVT_B200_OK;) {
+        int k1 = k0;
+        while (k1 < n_tus && key(order[k1]) == key(order[k0])) k1++;
+        const SvtB200TuEx &t = tus[order[k0]];
+        SvtB200EncodeParams bp;
+        bp.tx_size = t.tx_size;
+        bp.use_fp = p->use_fp;
+        for (int pl = 0; pl < 3; pl++) bp.q[pl] = p->qsets[t.qset][pl];
+        rc = encode_launch(&bp, t.pf_shape, d_qoff + k0, d_idx + k0, src, pred, recon, reinterpret_cast<const SvtB200Tu *>(d_tu + k0),
+                           k1 - k0, qcoeff, eob, cul_level, stream);
+        k0 = k1;
+    }
+    // the pinned staging of this thread is reused by its next call
+    SVTB_CUDA_TRY(cudaStreamSynchronize(st));
+    return rc;
 }
 }

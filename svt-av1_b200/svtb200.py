@@ -94,6 +94,15 @@ class EncodeParams(C.Structure):
     _fields_ = [("tx_size", C.c_int32), ("use_fp", C.c_int32), ("q", QuantPlane * 3)]
 
 
+class TuEx(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("plane", C.c_uint8), ("tx_type", C.c_uint8), ("tx_size", C.c_uint8),
+                ("pf_shape", C.c_uint8), ("qset", C.c_uint16), ("reserved", C.c_uint16)]
+
+
+class EncodeParamsEx(C.Structure):
+    _fields_ = [("use_fp", C.c_int32), ("n_qsets", C.c_int32), ("qsets", C.POINTER(QuantPlane * 3))]
+
+
 TX_W = [4, 8, 16, 32, 64, 4, 8, 8, 16, 16, 32, 32, 64, 4, 16, 8, 32, 16, 64]
 TX_H = [4, 8, 16, 32, 64, 8, 4, 16, 8, 32, 16, 64, 32, 16, 4, 32, 8, 64, 16]
 
@@ -272,6 +281,9 @@ def load():
         getattr(lib, f"svt_handle_transform{n}_cuda").restype = C.c_uint64
     lib.svt_b200_encode_tus.argtypes = [C.POINTER(EncodeParams), C.POINTER(Frame), C.POINTER(Frame), C.POINTER(Frame),
                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.svt_b200_encode_tus_ex.argtypes = [C.POINTER(EncodeParamsEx), C.POINTER(Frame), C.POINTER(Frame), C.POINTER(Frame),
+                                           C.POINTER(TuEx), C.c_int32, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_size_t, C.c_void_p]
     lib.svt_b200_cdef_search.argtypes = [C.POINTER(CdefSearchParams), C.POINTER(Frame), C.POINTER(Frame), C.c_void_p,
                                          C.c_int32, C.c_void_p, C.c_void_p]
     lib.svt_b200_cdef_apply.argtypes = [C.POINTER(CdefApplyParams), C.POINTER(Frame), C.POINTER(Frame), C.c_void_p,

@@ -105,6 +105,31 @@ def run_gpu_encode_tus(p, src, pred, tus, with_cul=False):
     return out + (cul.cpu().numpy(),) if with_cul else out
 
 
+def run_gpu_encode_tus_ex(qsets, use_fp, src, pred, tus):
+    """svt_b200_encode_tus_ex on a HOST list of sb.TuEx; returns (recon, [levels per unit], eob, cul_level)."""
+    lib = sb.load()
+    ds, dp, dr = DevYuv(src), DevYuv(pred), DevYuv(pred.copy())
+    arr = (sb.TuEx * len(tus))(*tus)
+    qs = ((sb.QuantPlane * 3) * len(qsets))()
+    for i, three in enumerate(qsets):
+        for pl in range(3):
+            qs[i][pl] = three[pl]
+    p = sb.EncodeParamsEx(use_fp, len(qsets), qs)
+    q = torch.full((max(1, len(tus)) * 1024,), 77, dtype=torch.int32, device="cuda")
+    eob = torch.zeros(max(1, len(tus)), dtype=torch.int16, device="cuda")
+    cul = torch.full((max(1, len(tus)),), -1, dtype=torch.int32, device="cuda")
+    scratch = torch.zeros(len(tus) * 28 + 256, dtype=torch.uint8, device="cuda")
+    offs = (C.c_int64 * (len(tus) + 1))()
+    ss, ps, rs = ds.struct(), dp.struct(), dr.struct()
+    sb.check(lib.svt_b200_encode_tus_ex(C.byref(p), C.byref(ss), C.byref(ps), C.byref(rs), arr, len(tus), C.c_void_p(q.data_ptr()), offs,
+                                        C.c_void_p(eob.data_ptr()), C.c_void_p(cul.data_ptr()), C.c_void_p(scratch.data_ptr()),
+                                        scratch.numel(), None), lib)
+    torch.cuda.synchronize()
+    qh = q.cpu().numpy()
+    levels = [qh[offs[i]:offs[i + 1]] for i in range(len(tus))]
+    return dr.download(), levels, eob.cpu().numpy().view(np.uint16)[:len(tus)], cul.cpu().numpy()[:len(tus)], qh[offs[len(tus)]:]
+
+
 def run_gpu_dlf(p, frame, flat):
     lib = sb.load()
     df = DevYuv(frame.copy())

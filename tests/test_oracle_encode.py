@@ -37,3 +37,29 @@ def test_oracle_chain_matches_reference_chain(case):
     np.testing.assert_array_equal(q, want_q)
     for i in range(3):
         np.testing.assert_array_equal(rec.plane(i), want_rec.plane(i))
+
+
+@needs_ref
+@pytest.mark.parametrize("tx_size", range(19))
+def test_oracle_estimate_transform_matches_reference_dispatcher(tx_size):
+    """orc_estimate_transform (shape dispatcher restated) vs the reference's av1_estimate_transform for the four
+    EB_TRANS_COEFF_SHAPE values: the coefficients the quantiser reads (min(w,32) x min(h,32)) and the reported energy."""
+    from test_oracle_txfm import allowed_types, residual_block
+    orc, ref = cm.oracle(), cm.refh()
+    orc.orc_estimate_transform.restype = C.c_uint64
+    ref.refh_estimate_transform.restype = C.c_uint64
+    w, h = sb.TX_W[tx_size], sb.TX_H[tx_size]
+    n = min(w, 32) * min(h, 32)
+    rng = np.random.default_rng(900 + tx_size)
+    for bd in (8, 10):
+        for shape in range(4):
+            for tx_type in allowed_types(tx_size):
+                res = residual_block(rng, w, h, bd, "rand")
+                a, b = np.zeros(w * h, np.int32), np.zeros(w * h, np.int32)
+                stride = res.shape[1] if res.ndim == 2 else w
+                ea = orc.orc_estimate_transform(cm.ptr(res), C.c_uint32(stride), cm.ptr(a), tx_size, bd, tx_type, shape)
+                eb = ref.refh_estimate_transform(cm.ptr(res), C.c_uint32(stride), cm.ptr(b), tx_size, bd, tx_type, shape)
+                np.testing.assert_array_equal(a[:n], b[:n], err_msg=f"bd {bd} shape {shape} type {tx_type}")
+                assert ea == eb
+                if shape == 3:
+                    assert not a[1:n].any()

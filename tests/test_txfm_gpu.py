@@ -249,6 +249,117 @@ def test_encode_tus_1080p_16x16_and_roundtrip_property():
     np.testing.assert_array_equal(again_rec.plane(0), got_rec.plane(0))
 
 
+def oracle_encode_tus_ex(qsets, src, pred, tus, use_fp):
+    """The chain of oracle_encode_tus for units of mixed size / shape / quantiser set: orc_estimate_transform is the
+    restatement of the reference's shape dispatcher (pinned against av1_estimate_transform in test_oracle_encode.py)."""
+    orc = cm.oracle()
+    orc.orc_estimate_transform.restype = C.c_uint64
+    lib = sb.load()
+    hbd = 1 if src.bd > 8 else 0
+    recon = pred.copy()
+    levels, eobs = [], np.zeros(len(tus), np.uint16)
+    for i, tu in enumerate(tus):
+        ts = tu.tx_size
+        w, h = TX_W[ts], TX_H[ts]
+        n = min(w, 32) * min(h, 32)
+        log_scale = (1 if w * h > 256 else 0) + (1 if w * h > 1024 else 0)
+        sp, pp, rp = src.plane(tu.plane), pred.plane(tu.plane), recon.plane(tu.plane)
+        sblk = np.ascontiguousarray(sp[tu.y:tu.y + h, tu.x:tu.x + w])
+        pblk = np.ascontiguousarray(pp[tu.y:tu.y + h, tu.x:tu.x + w])
+        res = np.zeros((h, w), np.int16)
+        orc.orc_residual(cm.ptr(sblk), C.c_uint32(w), cm.ptr(pblk), C.c_uint32(w), cm.ptr(res), C.c_uint32(w), C.c_uint32(w), C.c_uint32(h), hbd)
+        coeff = np.zeros(w * h, np.int32)
+        orc.orc_estimate_transform(cm.ptr(res), C.c_uint32(w), cm.ptr(coeff), ts, src.bd, tu.tx_type, tu.pf_shape)
+        scan = np.zeros(1024, np.int16)
+        assert lib.svt_b200_get_scan(ts, tu.tx_type, cm.ptr(scan)) == n  # checked against av1_scan_orders in oracle_encode_tus
+        q, dq, eob = np.zeros(n, np.int32), np.zeros(n, np.int32), C.c_uint16(0)
+        qp = qsets[tu.qset][tu.plane]
+        if use_fp:
+            orc.orc_quantize_fp(cm.ptr(coeff), C.c_ssize_t(n), qp.round_fp, qp.quant_fp, cm.ptr(q), cm.ptr(dq), qp.dequant,
+                                C.byref(eob), cm.ptr(scan), log_scale, hbd)
+        else:
+            orc.orc_quantize_b(cm.ptr(coeff), C.c_ssize_t(n), qp.zbin, qp.round, qp.quant, qp.quant_shift, cm.ptr(q), cm.ptr(dq),
+                               qp.dequant, C.byref(eob), cm.ptr(scan), None, None, log_scale, hbd)
+        levels.append(q)
+        eobs[i] = eob.value
+        p16 = pblk.astype(np.uint16)
+        r16 = np.zeros((h, w), np.uint16)
+        orc.orc_inv_txfm2d_add(cm.ptr(dq), cm.ptr(p16), w, cm.ptr(r16), w, tu.tx_type, ts, src.bd)
+        rp[tu.y:tu.y + h, tu.x:tu.x + w] = r16.astype(rp.dtype)
+    return recon, levels, eobs
+
+
+def mixed_tus(rng, w_pic, h_pic, n_qsets, shapes=(0, 0, 1, 2, 3)):
+    """Non-overlapping units of mixed sizes: every 64x64 cell of a plane is tiled with one randomly chosen size."""
+    tus = []
+    for pl in range(3):
+        pw, ph = (w_pic, h_pic) if pl == 0 else ((w_pic + 1) // 2, (h_pic + 1) // 2)
+        for cy in range(0, ph - 63, 64):
+            for cx in range(0, pw - 63, 64):
+                ts = int(rng.integers(0, 19))
+                w, h = TX_W[ts], TX_H[ts]
+                types = allowed_types(ts)
+                cell = [(cx + x, cy + y) for y in range(0, 64, h) for x in range(0, 64, w)]
+                for k in rng.choice(len(cell), min(len(cell), 6), replace=False):
+                    x, y = cell[int(k)]
+                    tus.append(sb.TuEx(x, y, pl, int(rng.choice(types)), ts, int(rng.choice(shapes)), int(rng.integers(0, n_qsets)), 0))
+    order = rng.permutation(len(tus))  # the input order is NOT sorted by size: the entry buckets it
+    return [tus[int(i)] for i in order]
+
+
+@pytest.mark.parametrize("bd,use_fp", [(8, 0), (10, 1), (10, 0)])
+def test_encode_tus_ex_mixed_sizes_shapes_qsets_vs_oracle(bd, use_fp):
+    """the fused entry with the generality of the reference's dispatcher - units of all 19 sizes, the four
+    coefficient shapes and several quantiser sets in ONE call, results in input order."""
+    import gpu_runner as gr
+    rng = np.random.default_rng(4242 + bd + use_fp)
+    W, H = 320, 192
+    src = cm.synth_yuv(W, H, 1, 9, bd)
+    pred = cm.degrade(src, 13, amp=18)
+    qsets = [[quant_plane(rng, bd) for _ in range(3)] for _ in range(3)]
+    tus = mixed_tus(rng, W, H, len(qsets))
+    assert len({t.tx_size for t in tus}) >= 10 and {t.pf_shape for t in tus} == {0, 1, 2, 3}
+    want_rec, want_q, want_eob = oracle_encode_tus_ex(qsets, src, pred, tus, use_fp)
+    got_rec, got_q, got_eob, got_cul, tail = gr.run_gpu_encode_tus_ex(qsets, use_fp, src, pred, tus)
+    np.testing.assert_array_equal(got_eob, want_eob)
+    for i, (g, wq) in enumerate(zip(got_q, want_q)):
+        np.testing.assert_array_equal(g, wq, err_msg=f"unit {i}: size {tus[i].tx_size} shape {tus[i].pf_shape}")
+    assert (tail == 77).all()  # nothing written past qcoeff_offsets[n]
+    want_cul = np.array([min(63, int(np.abs(q.astype(np.int64)).sum())) + (64 if q[0] < 0 else 128 if q[0] > 0 else 0) for q in want_q])
+    np.testing.assert_array_equal(got_cul, want_cul)
+    for i in range(3):
+        np.testing.assert_array_equal(got_rec.plane(i), want_rec.plane(i), err_msg=f"plane {i}")
+
+
+def test_encode_tus_ex_default_shape_equals_the_single_size_entry():
+    """Consistency of the two entries: one size, default shape, one quantiser set -> the same levels / eob / recon as
+    svt_b200_encode_tus_cul; an empty list and out-of-range fields are handled (no launch / SVT_B200_ERR_ARG)."""
+    import gpu_runner as gr
+    rng = np.random.default_rng(5)
+    W, H = 192, 128
+    src = cm.synth_yuv(W, H, 1, 7, 8)
+    pred = cm.degrade(src, 11, amp=14)
+    p = sb.EncodeParams()
+    p.tx_size, p.use_fp = 7, 0
+    for i in range(3):
+        p.q[i] = quant_plane(rng, 8)
+    tus = make_tus(rng, 7, W, H, limit=100)
+    rec1, q1, eob1, cul1 = gr.run_gpu_encode_tus(p, src, pred, tus, with_cul=True)
+    ex = [sb.TuEx(t.x, t.y, t.plane, t.tx_type, 7, 0, 0, 0) for t in tus]
+    rec2, q2, eob2, cul2, _ = gr.run_gpu_encode_tus_ex([[p.q[0], p.q[1], p.q[2]]], 0, src, pred, ex)
+    np.testing.assert_array_equal(eob2, eob1)
+    np.testing.assert_array_equal(cul2, cul1)
+    np.testing.assert_array_equal(np.stack(q2), q1)
+    for i in range(3):
+        np.testing.assert_array_equal(rec2.plane(i), rec1.plane(i))
+    rec3, q3, eob3, _, _ = gr.run_gpu_encode_tus_ex([[p.q[0], p.q[1], p.q[2]]], 0, src, pred, [])
+    assert q3 == [] and all((rec3.plane(i) == pred.plane(i)).all() for i in range(3))
+    with pytest.raises(Exception):
+        gr.run_gpu_encode_tus_ex([[p.q[0], p.q[1], p.q[2]]], 0, src, pred, [sb.TuEx(0, 0, 0, 0, 19, 0, 0, 0)])
+    with pytest.raises(Exception):
+        gr.run_gpu_encode_tus_ex([[p.q[0], p.q[1], p.q[2]]], 0, src, pred, [sb.TuEx(0, 0, 0, 0, 2, 0, 1, 0)])
+
+
 @pytest.mark.parametrize("tx_size", range(19))
 def test_partial_frequency_dropins(tx_size):
     lib, orc = sb.load(), cm.oracle()
