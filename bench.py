@@ -54,10 +54,10 @@ B = os.path.join(ROOT, "integration", "_build")
 BIN = {"cuda": os.path.join(B, "enc_bench_cuda_simd"), "ref": os.path.join(B, "enc_bench_ref_simd"),
        "app_cuda": os.path.join(B, "SvtAv1EncAppCudaSimd")}
 _REAL_STDOUT = None
-# N > 1 streams: each stream is confined to its own group of cores (cpu_partition).  SVTB200_BENCH_LP=1 additionally passes
-# `--lp <group size>` (the encoder then sizes its thread / picture pools for the group); the default leaves the encoder's own
-# sizing (for the whole host) in place, which measured faster for both arms (profiles/r2_scaling_lp_experiment.txt)
-USE_LP = os.environ.get("SVTB200_BENCH_LP", "0") == "1"
+# N > 1 streams: each stream is confined to its own group of cores (cpu_partition) and is told so with `--lp <group size>`
+# (the reference's own switch: thread / picture pools sized for the group) - the configuration of the committed N = 2 / 4
+# lines (profiles/bench_r2c_*).  SVTB200_BENCH_LP=0 leaves the encoder's sizing for the whole host in place.
+USE_LP = os.environ.get("SVTB200_BENCH_LP", "1") == "1"
 
 
 def emit(obj):

@@ -138,6 +138,161 @@ __global__ void __launch_bounds__(ST_NT) stats_kernel(const StatsDev d, int tile
     }
 }
 
+// ---- the same normal equations on the INT8 tensor cores ---------------------------------------------------------
+// H and M together are the Gram matrix of z = [the win2 window differences, the source difference] over the samples of
+// a unit: G = Z^T Z (upper triangle; column win2 is M).  The differences need 9 (8-bit) to 13 (12-bit) bits, the tensor
+// cores multiply int8, so every difference is split once, at staging, into balanced limbs  v = 128 * hi + lo,
+// lo in [-64, 63], |hi| <= 32, and THREE int8 Gram matrices are accumulated, of hi, of lo and of (hi + lo) (which
+// still fits: |hi + lo| <= 96):   v_k v_l = 16256 * hi_k hi_l + 128 * (hi + lo)_k (hi + lo)_l - 127 * lo_k lo_l.
+// Every product sum is an exact int32 (4096 samples * 96^2 < 2^31) and the combination is done in int64, so the result
+// is the reference's integer sum bit for bit (EbRestorationPick.c:704-790), whatever the order.
+//
+// mma.sync.m16n8k32.s8: the K dimension are 32 samples of one tile row, the M / N dimensions rows of Z^T / columns of Z.
+// Both operands are the same data: lane (g, tig) holds, for row m = g + 8 j of Z^T, the 8 samples 8 tig .. 8 tig + 7 of
+// the K step as two registers, which are at once rows g / g + 8 of the A fragments of row tile j / 2 and column g of the B
+// fragment of column tile j (the K index -> sample map is ours to choose as long as A and B agree).  A register is 4
+// consecutive bytes of a staged int8 plane at an arbitrary byte offset (window column kc): three aligned LDS.32 and two
+// PRMT per row.  A CTA owns a 64x64 sample tile of one unit; warp = (limb, quarter of the tile rows); 16 (win 7) or 6
+// (win 5) accumulator tiles per warp stay in registers for the whole tile, are merged through int32 shared atomics,
+// combined to int64 and sent to the unit's M / H with one 64-bit global atomic per entry and CTA.
+constexpr int TC_TW = 64, TC_TH = 64, TC_NT = 384, TC_PITCH = 72, TC_SLICES = 4;
+
+__device__ __forceinline__ void mma_s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <typename T, int WIN>
+__global__ void __launch_bounds__(TC_NT) stats_mma_kernel(const StatsDev d, int tiles_x_max) {
+    constexpr int HW = WIN / 2, WIN2 = WIN * WIN, NROW = WIN2 + 1, NJ = (NROW + 7) / 8, MT = (NJ + 1) / 2;
+    constexpr int RH = TC_TH + 2 * HW, YB = RH * TC_PITCH, XB = TC_TH * TC_PITCH;
+    constexpr int NTILE = MT * NJ - MT * (MT - 1); // sum over mt of (NJ - 2 mt): column tiles nt >= 2 mt
+    static_assert(3 * NTILE * 128 * 4 <= 3 * (YB + XB), "the merge buffer aliases the staged planes");
+    static_assert(TC_TW + 2 * HW <= TC_PITCH - 2, "a row read ends inside the pitch");
+    __shared__ __align__(16) uint8_t s_raw[3 * (YB + XB)]; // [limb] window planes, then [limb] source planes
+    const StatsUnit u = d.units[blockIdx.y];
+    const int uw = u.h_end - u.h_start, uh = u.v_end - u.v_start;
+    const int tx = blockIdx.x % tiles_x_max, ty = blockIdx.x / tiles_x_max;
+    const int x0 = u.h_start + tx * TC_TW, y0 = u.v_start + ty * TC_TH;
+    if (x0 >= u.h_end || y0 >= u.v_end) return;
+    const int tw = min(TC_TW, u.h_end - x0), th = min(TC_TH, u.v_end - y0);
+    const int avg = (int)(d.sum[blockIdx.y] / (unsigned long long)(uw * uh)); // find_average: truncating division
+    const T *dg = reinterpret_cast<const T *>(d.dgd);
+    const T *sr = reinterpret_cast<const T *>(d.src);
+    const int tid = threadIdx.x;
+    // staging: 4 samples -> one word of each limb plane
+    for (int i = tid; i < (RH + TC_TH) * (TC_PITCH / 4); i += TC_NT) {
+        const int r = i / (TC_PITCH / 4), wc = i - r * (TC_PITCH / 4);
+        const bool win_row = r < RH;
+        const int rr = win_row ? r : r - RH;
+        uint32_t ph = 0, pl = 0, ps = 0;
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+            const int c = wc * 4 + b;
+            int v = 0;
+            if (win_row) {
+                if (rr < th + 2 * HW && c < tw + 2 * HW) {
+                    int yy = y0 + rr - HW, xx = x0 + c - HW;
+                    if (d.clamp) {
+                        yy = min(max(yy, 0), d.ph - 1);
+                        xx = min(max(xx, 0), d.pw - 1);
+                    }
+                    v = (int)dg[(size_t)yy * d.dgd_stride + xx] - avg;
+                }
+            } else if (rr < th && c < tw) {
+                v = (int)sr[(size_t)(y0 + rr) * d.src_stride + x0 + c] - avg;
+            }
+            const int lo = ((v + 64) & 127) - 64, hi = (v - lo) >> 7;
+            ph |= (uint32_t)(uint8_t)hi << (8 * b);
+            pl |= (uint32_t)(uint8_t)lo << (8 * b);
+            ps |= (uint32_t)(uint8_t)(hi + lo) << (8 * b);
+        }
+        const int o = (win_row ? rr * TC_PITCH : 3 * YB + rr * TC_PITCH) + wc * 4, lstride = win_row ? YB : XB;
+        *reinterpret_cast<uint32_t *>(s_raw + o) = ph;
+        *reinterpret_cast<uint32_t *>(s_raw + o + lstride) = pl;
+        *reinterpret_cast<uint32_t *>(s_raw + o + 2 * lstride) = ps;
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, tig = lane & 3;
+    const int limb = warp % 3, slice = warp / 3;
+    // byte offset of row m = g + 8 j of Z^T at tile sample (0, 0): window element (kc, kr) -> kr rows down, kc bytes right
+    int off[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+        const int m = g + 8 * j;
+        if (m < WIN2) {
+            const int kc = m / WIN, kr = m - kc * WIN;
+            off[j] = limb * YB + kr * TC_PITCH + kc;
+        } else {
+            off[j] = 3 * YB + limb * XB; // the source row (m == WIN2); rows beyond it are masked to zero below
+        }
+    }
+    const uint32_t last_mask = (g + 8 * (NJ - 1) <= WIN2) ? 0xffffffffu : 0u;
+    int acc[NTILE][4];
+#pragma unroll
+    for (int t = 0; t < NTILE; t++)
+#pragma unroll
+        for (int q = 0; q < 4; q++) acc[t][q] = 0;
+    for (int pi = slice; pi < th; pi += TC_SLICES) {
+        for (int pj0 = 0; pj0 < tw; pj0 += 32) {
+            const int colb = pi * TC_PITCH + pj0 + 8 * tig;
+            uint32_t f[2 * MT][2];
+#pragma unroll
+            for (int j = 0; j < NJ; j++) {
+                const int a = off[j] + colb;
+                const uint32_t *wp = reinterpret_cast<const uint32_t *>(s_raw + (a & ~3));
+                const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], sel = 0x3210u + 0x1111u * (uint32_t)(a & 3);
+                f[j][0] = __byte_perm(w0, w1, sel);
+                f[j][1] = __byte_perm(w1, w2, sel);
+            }
+            f[NJ - 1][0] &= last_mask;
+            f[NJ - 1][1] &= last_mask;
+            if (2 * MT > NJ) f[2 * MT - 1][0] = f[2 * MT - 1][1] = 0;
+            if (pj0 + 32 > tw) { // ragged right edge: samples outside the unit contribute a zero vector
+                const int nv = min(max(tw - (pj0 + 8 * tig), 0), 8);
+                const uint32_t m0 = nv >= 4 ? 0xffffffffu : (1u << (8 * nv)) - 1u;
+                const uint32_t m1 = nv >= 8 ? 0xffffffffu : nv <= 4 ? 0u : (1u << (8 * (nv - 4))) - 1u;
+#pragma unroll
+                for (int j = 0; j < NJ; j++) {
+                    f[j][0] &= m0;
+                    f[j][1] &= m1;
+                }
+            }
+            int t = 0;
+#pragma unroll
+            for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+                for (int nt = 2 * mt; nt < NJ; nt++, t++)
+                    mma_s8(acc[t], f[2 * mt][0], f[2 * mt + 1][0], f[2 * mt][1], f[2 * mt + 1][1], f[nt][0], f[nt][1]);
+        }
+    }
+    __syncthreads(); // every warp is done with the planes: reuse them as the merge buffer
+    int *s_g = reinterpret_cast<int *>(s_raw);
+    for (int i = tid; i < 3 * NTILE * 128; i += TC_NT) s_g[i] = 0;
+    __syncthreads();
+#pragma unroll
+    for (int t = 0; t < NTILE; t++)
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (acc[t][q]) atomicAdd(&s_g[(limb * NTILE + t) * 128 + q * 32 + lane], acc[t][q]);
+    __syncthreads();
+    long long *out = d.out + (size_t)blockIdx.y * (WIN2 + WIN2 * WIN2);
+    for (int i = tid; i < NTILE * 128; i += TC_NT) {
+        const int t = i >> 7, q = (i >> 5) & 3, ln = i & 31;
+        int mt = 0, rem = t; // tile index -> (mt, nt)
+        while (rem >= NJ - 2 * mt) {
+            rem -= NJ - 2 * mt;
+            mt++;
+        }
+        const int nt = 2 * mt + rem;
+        const int k = 16 * mt + (ln >> 2) + 8 * (q >> 1), l = 8 * nt + 2 * (ln & 3) + (q & 1);
+        if (k > l || l > WIN2 || k >= WIN2) continue;
+        const long long v = 16256ll * s_g[i] + 128ll * s_g[2 * NTILE * 128 + i] - 127ll * s_g[NTILE * 128 + i];
+        if (v) atomicAdd(reinterpret_cast<unsigned long long *>(out + (l == WIN2 ? k : WIN2 + k * WIN2 + l)), (unsigned long long)v);
+    }
+}
+
 // high-bit-depth divider (truncating, as C's `/=`) and the mirror of the upper triangle
 __global__ void stats_finish_kernel(long long *out, int n_units, int win2, int divider) {
     long long *o = out + (size_t)blockIdx.x * (win2 + win2 * win2);
@@ -159,8 +314,30 @@ int stats_launch(StatsDev &d, int win, int hbd, int max_uw, int max_uh, cudaStre
     const int win2 = win * win;
     if (cudaMemsetAsync(d.sum, 0, (size_t)d.n_units * 8, st) != cudaSuccess) return -1;
     if (cudaMemsetAsync(d.out, 0, (size_t)d.n_units * (win2 + win2 * win2) * 8, st) != cudaSuccess) return -1;
+    // SVT_B200_STATS_IMAD=1: the round-1 integer-pipe kernel (kept for the comparison in profiles/)
+    static const bool imad = getenv("SVT_B200_STATS_IMAD") != nullptr;
+    const dim3 gs(std::min(64, (max_uw * max_uh + 255) / 256), d.n_units);
+    if (!imad) {
+        const int tiles_x = (max_uw + TC_TW - 1) / TC_TW, tiles_y = (max_uh + TC_TH - 1) / TC_TH;
+        const dim3 gt(tiles_x * tiles_y, d.n_units);
+        if (hbd) {
+            SVTB_LAUNCH(stats_sum_kernel<uint16_t>, gs, 256, 0, st, d);
+            if (win == 7)
+                SVTB_LAUNCH((stats_mma_kernel<uint16_t, 7>), gt, TC_NT, 0, st, d, tiles_x);
+            else
+                SVTB_LAUNCH((stats_mma_kernel<uint16_t, 5>), gt, TC_NT, 0, st, d, tiles_x);
+        } else {
+            SVTB_LAUNCH(stats_sum_kernel<uint8_t>, gs, 256, 0, st, d);
+            if (win == 7)
+                SVTB_LAUNCH((stats_mma_kernel<uint8_t, 7>), gt, TC_NT, 0, st, d, tiles_x);
+            else
+                SVTB_LAUNCH((stats_mma_kernel<uint8_t, 5>), gt, TC_NT, 0, st, d, tiles_x);
+        }
+        SVTB_LAUNCH(stats_finish_kernel, d.n_units, 256, 0, st, d.out, d.n_units, win2, d.divider);
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    }
     const int tiles_x = (max_uw + ST_TW - 1) / ST_TW, tiles_y = (max_uh + ST_TH - 1) / ST_TH;
-    const dim3 gs(std::min(64, (max_uw * max_uh + 255) / 256), d.n_units), gt(tiles_x * tiles_y, d.n_units);
+    const dim3 gt(tiles_x * tiles_y, d.n_units);
     if (hbd) {
         SVTB_LAUNCH(stats_sum_kernel<uint16_t>, gs, 256, 0, st, d);
         if (win == 7)

@@ -111,6 +111,48 @@ def test_compute_stats_dropins(bd):
             np.testing.assert_array_equal(Hm, h2.reshape(-1))
 
 
+@pytest.mark.parametrize("bd", [8, 10, 12])
+def test_compute_stats_extreme_values(bd):
+    """The int8 limb split of the tensor-core kernel at its range limits: differences of +-(2^bd - 1) (a unit that is
+    almost all 0 with a few full-scale samples, and the reverse), a checkerboard (average in the middle), src != dgd."""
+    import ctypes as C
+    import misc_oracle as mo
+    lib = sb.load()
+    rng = np.random.default_rng(170 + bd)
+    dt = np.uint16 if bd > 8 else np.uint8
+    top = (1 << bd) - 1
+    w, h = 128, 96  # 2 x 2 tiles of 64 x 64, ragged bottom
+    for kind in ("sparse_hi", "sparse_lo", "checker", "rows"):
+        H, W = h + 16, w + 16
+        if kind == "sparse_hi":
+            dgd = np.where(rng.random((H, W)) < 0.002, top, 0)
+            src = np.where(rng.random((H, W)) < 0.5, top, 0)
+        elif kind == "sparse_lo":
+            dgd = np.where(rng.random((H, W)) < 0.002, 0, top)
+            src = np.where(rng.random((H, W)) < 0.5, 0, top)
+        elif kind == "checker":
+            yy, xx = np.mgrid[0:H, 0:W]
+            dgd = np.where((yy + xx) & 1, top, 0)
+            src = top - dgd
+        else:
+            yy, xx = np.mgrid[0:H, 0:W]
+            dgd = np.where(yy % 3 == 0, top, np.where(yy % 3 == 1, top // 2 + 1, 0))
+            src = np.where(xx % 5 < 2, top, 63)
+        dgd, src = dgd.astype(dt), src.astype(dt)
+        for win in (7, 5):
+            n = win * win
+            M, Hm = np.zeros(n, np.int64), np.zeros(n * n, np.int64)
+            hs, vs = 8, 8
+            if bd == 8:
+                lib.svt_av1_compute_stats_cuda(win, cm.ptr(dgd), cm.ptr(src), hs, hs + w, vs, vs + h, dgd.shape[1], src.shape[1], cm.ptr(M), cm.ptr(Hm))
+            else:
+                lib.svt_av1_compute_stats_highbd_cuda(win, C.c_void_p(dgd.ctypes.data >> 1), C.c_void_p(src.ctypes.data >> 1), hs, hs + w, vs,
+                                                      vs + h, dgd.shape[1], src.shape[1], cm.ptr(M), cm.ptr(Hm), bd)
+            m2, h2 = mo.compute_stats(win, dgd, src, hs, hs + w, vs, vs + h, bd)
+            np.testing.assert_array_equal(M, m2, err_msg=f"{kind} win {win}")
+            np.testing.assert_array_equal(Hm, h2.reshape(-1), err_msg=f"{kind} win {win}")
+
+
 @pytest.mark.parametrize("bd", [8, 10])
 def test_pixel_proj_error_dropins(bd):
     import ctypes as C
@@ -134,7 +176,7 @@ def test_pixel_proj_error_dropins(bd):
             assert got == mo.pixel_proj_error(src[:, :w], dat[:, :w], f0[:, :w], f1[:, :w], (xq[0], xq[1]), r, bd > 8)
 
 
-@pytest.mark.parametrize("case", [(192, 136, 8, 64), (264, 200, 10, 128), (1920, 1080, 8, 256), (640, 360, 12, 64)])
+@pytest.mark.parametrize("case", [(192, 136, 8, 64), (264, 200, 10, 128), (1920, 1080, 8, 256), (640, 360, 12, 64), (3840, 2160, 10, 256)])
 def test_lr_wiener_stats_picture(case):
     """svt_b200_lr_wiener_stats: every restoration unit of every plane in one call, pictures resident on the device,
     against compute_stats on the replicate-extended picture (the reference extends the picture by 3 before the search)."""
@@ -161,8 +203,8 @@ def test_lr_wiener_stats_picture(case):
                 rects.append((x0, x0 + uw, y0, y0 + uh))
                 x0 += uw
             y0 += uh
-        if len(rects) > 24:  # bound the numpy work at 1080p: a spread of units incl. the corners
-            idx = sorted(set([0, len(rects) - 1] + list(np.random.default_rng(3).choice(len(rects), 20, replace=False))))
+        if len(rects) > 24:  # bound the numpy work at 1080p / 2160p: a spread of units incl. the corners
+            idx = sorted(set([0, len(rects) - 1] + list(np.random.default_rng(3).choice(len(rects), 20 if w < 3000 else 8, replace=False))))
             rects = [rects[i] for i in idx]
         r = torch.tensor(rects, dtype=torch.int32, device="cuda")
         n2 = win * win
