@@ -971,6 +971,54 @@ SVT_B200_API int svt_b200_engine_dlf_cdef_frame(SvtB200Engine *e, const SvtB200D
                                                 const SvtB200Frame *source, const uint8_t *skip8, int32_t skip_stride,
                                                 uint64_t *mse, SvtB200CdefDecideFn decide, void *user);
 
+/* =============================================================================================== */
+/* Temporal filtering                                                      */
+/* =============================================================================================== */
+
+/* The planewise weighting of the temporal filter for many blocks of one (centre picture, motion-compensated reference)
+ * pair: replaces the per-32x32 calls of svt_av1_apply_temporal_filter_planewise[_hbd] (aom_dsp_rtcd.c:365-366; C
+ * EbTemporalFiltering.c:643-811, 829-1017) made by apply_filtering_block_plane_wise (:1025-1131).  Bit-exact, floating
+ * point chain included (see csrc/tf.cu).  src: the picture being filtered; pred: its motion-compensated prediction from
+ * one reference picture, same geometry; accum / count: picture-sized accumulators (device), same coordinates as pred.
+ * blocks: DEVICE array; x / y: luma position of the block (even); block_error[q] / d_factor[q] for the four quadrants
+ * q = (row >= h/2) * 2 + (col >= w/2), computed as the reference does (:696-734):
+ *   block_error = split ? tf_16x16_block_error[idx*4+q] / 256 : tf_32x32_block_error[idx] / 1024   (errors >> 4 at 10 bit)
+ *   d_factor    = max(sqrtf(powf(mv.row,2) + powf(mv.col,2)) / max(min_frame_size * 0.1, 1), 1)
+ * den[p] = 2 * n_decay^2, n_decay = decay_control * (0.7 + log1p(noise_levels[p])) (:712). */
+typedef struct SvtB200TfBlock {
+    int32_t x, y;
+    double block_error[4], d_factor[4];
+} SvtB200TfBlock;
+typedef struct SvtB200TfParams {
+    double den[3];
+    int32_t chroma;           /* MeContext::tf_chroma */
+    int32_t block_w, block_h; /* 32 x 32 in the reference (BW >> 1); even, <= 64 */
+} SvtB200TfParams;
+typedef struct SvtB200TfAccum {
+    uint32_t *accum[3];
+    uint16_t *count[3];
+    int32_t stride_y, stride_c; /* entries */
+} SvtB200TfAccum;
+SVT_B200_API int svt_b200_tf_planewise(const SvtB200TfParams *p, const SvtB200Frame *src, const SvtB200Frame *pred,
+                                       const SvtB200TfBlock *blocks, int32_t n_blocks, const SvtB200TfAccum *acc, void *stream);
+/* apply_filtering_central[_highbd] (:551-621) for the whole picture: accum += 1000 * sample, count += 1000 */
+SVT_B200_API int svt_b200_tf_central(const SvtB200Frame *center, const SvtB200TfAccum *acc, int32_t chroma, void *stream);
+/* get_final_filtered_pixels (:1943-2050) for the whole picture: dst = (accum + count / 2) / count in place;
+ * sse2: DEVICE uint64[2] or NULL: sum of (old - new)^2 for luma and for both chroma planes (filtered_sse / filtered_sse_uv) */
+SVT_B200_API int svt_b200_tf_normalize(const SvtB200Frame *dst, const SvtB200TfAccum *acc, int32_t chroma, uint64_t *sse2,
+                                       void *stream);
+/* One block, HOST pointers in the reference's layout: the body of the drop-ins for the two RTCD pointers (the
+ * MeContext-reading shim lives next to the reference's headers: oracle/rtcd_install.c, integration/). */
+SVT_B200_API int svt_b200_tf_planewise_block_host(int32_t bit_depth, int32_t chroma, const void *y_src, int32_t y_src_stride,
+                                                  const void *y_pre, int32_t y_pre_stride, const void *u_src, const void *v_src,
+                                                  int32_t uv_src_stride, const void *u_pre, const void *v_pre,
+                                                  int32_t uv_pre_stride, uint32_t bw, uint32_t bh, const double *den3,
+                                                  const double *block_error4, const double *d_factor4, uint32_t *y_accum,
+                                                  uint16_t *y_count, uint32_t *u_accum, uint16_t *u_count, uint32_t *v_accum,
+                                                  uint16_t *v_count);
+/* test hook: checksum of the library's expf over the floats with bit patterns lo..hi (see oracle orc_expf_checksum) */
+SVT_B200_API int svt_b200_tf_expf_checksum(uint32_t lo_bits, uint32_t hi_bits, uint64_t *out_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -113,4 +113,23 @@ ORC_API void orc_subpel_search(const SvtB200SubpelParams *p, const int32_t *mvco
 #ifdef __cplusplus
 }
 #endif
+/* ---- temporal filter, planewise weighting (tf_oracle.c; EbTemporalFiltering.c:525-811, 829-1017, 1943-2050) ---- */
+ORC_API const uint64_t *orc_exp2f_table(void);
+ORC_API float orc_expf(float x);
+ORC_API long orc_expf_mismatches(uint32_t lo_bits, uint32_t hi_bits, long *weight_mismatches);
+ORC_API uint64_t orc_expf_checksum(uint32_t lo_bits, uint32_t hi_bits);
+ORC_API int orc_tf_weight(uint64_t sum, int n, double block_error, double d_factor, double den);
+ORC_API void orc_tf_den(int decay_control, const double *noise_levels, double den[3]);
+ORC_API void orc_tf_block_factors(int split, const uint64_t err16[4], uint64_t err32, const int16_t mvx16[4], const int16_t mvy16[4],
+                                  int16_t mvx32, int16_t mvy32, int min_frame_size, int hbd, double block_error[4], double d_factor[4]);
+ORC_API void orc_tf_planewise(const void *y_src, int y_src_stride, const void *y_pre, int y_pre_stride, const void *u_src,
+                              const void *v_src, int uv_src_stride, const void *u_pre, const void *v_pre, int uv_pre_stride,
+                              unsigned bw, unsigned bh, int ss_x, int ss_y, const double den[3], const double block_error[4],
+                              const double d_factor[4], int chroma, int bit_depth, uint32_t *y_accum, uint16_t *y_count,
+                              uint32_t *u_accum, uint16_t *u_count, uint32_t *v_accum, uint16_t *v_count);
+ORC_API void orc_tf_central(const void *pre, int pre_stride, unsigned w, unsigned h, int hbd, uint32_t *accum, uint16_t *count,
+                            int acc_stride);
+ORC_API uint64_t orc_tf_normalize(void *dst, int dst_stride, unsigned w, unsigned h, int hbd, const uint32_t *accum,
+                                  const uint16_t *count, int acc_stride);
+
 #endif

@@ -954,3 +954,46 @@ REFH_API void refh_subpel_limits(int mi_rows, int mi_cols, int blk_x, int blk_y,
     svt_av1_set_subpel_mv_search_range(&sl, (FullMvLimits *)&lim, &ref_mv);
     out[0] = (int16_t)sl.col_min, out[1] = (int16_t)sl.col_max, out[2] = (int16_t)sl.row_min, out[3] = (int16_t)sl.row_max;
 }
+
+/* ====================================================================================================
+ * Temporal filter: the reference's svt_av1_apply_temporal_filter_planewise[_hbd] on one block, with the MeContext fields
+ * it reads (EbMotionEstimationContext.h:443-458) filled from plain arguments.  via_rtcd: 0 calls the _c functions, 1 the
+ * RTCD pointers (whatever is installed there).
+ * ================================================================================================== */
+#include "EbTemporalFiltering.h"
+REFH_API int refh_tf_planewise(int via_rtcd, int bit_depth, int chroma, int block_row, int block_col, const int32_t *split_flag4,
+                               const uint64_t *err16_16, const uint64_t *err32_4, const int16_t *mvx16_16, const int16_t *mvy16_16,
+                               const int16_t *mvx32_4, const int16_t *mvy32_4, int min_frame_size, const void *y_src,
+                               int y_src_stride, const void *y_pre, int y_pre_stride, const void *u_src, const void *v_src,
+                               int uv_src_stride, const void *u_pre, const void *v_pre, int uv_pre_stride, unsigned bw, unsigned bh,
+                               int ss_x, int ss_y, const double *noise_levels, int decay_control, uint32_t *y_accum,
+                               uint16_t *y_count, uint32_t *u_accum, uint16_t *u_count, uint32_t *v_accum, uint16_t *v_count) {
+    refh_init();
+    MeContext *c = (MeContext *)calloc(1, sizeof(MeContext));
+    if (!c) return -1;
+    c->tf_chroma = (uint8_t)chroma;
+    c->tf_block_row = block_row;
+    c->tf_block_col = block_col;
+    c->min_frame_size = (uint16_t)min_frame_size;
+    for (int i = 0; i < 4; i++) {
+        c->tf_32x32_block_split_flag[i] = split_flag4[i];
+        c->tf_32x32_block_error[i] = err32_4[i];
+        c->tf_32x32_mv_x[i] = mvx32_4[i];
+        c->tf_32x32_mv_y[i] = mvy32_4[i];
+    }
+    for (int i = 0; i < 16; i++) {
+        c->tf_16x16_block_error[i] = err16_16[i];
+        c->tf_16x16_mv_x[i] = mvx16_16[i];
+        c->tf_16x16_mv_y[i] = mvy16_16[i];
+    }
+    if (bit_depth == 8)
+        (via_rtcd ? svt_av1_apply_temporal_filter_planewise : svt_av1_apply_temporal_filter_planewise_c)(
+            c, y_src, y_src_stride, y_pre, y_pre_stride, u_src, v_src, uv_src_stride, u_pre, v_pre, uv_pre_stride, bw, bh, ss_x, ss_y,
+            noise_levels, decay_control, y_accum, y_count, u_accum, u_count, v_accum, v_count);
+    else
+        (via_rtcd ? svt_av1_apply_temporal_filter_planewise_hbd : svt_av1_apply_temporal_filter_planewise_hbd_c)(
+            c, y_src, y_src_stride, y_pre, y_pre_stride, u_src, v_src, uv_src_stride, u_pre, v_pre, uv_pre_stride, bw, bh, ss_x, ss_y,
+            noise_levels, decay_control, y_accum, y_count, u_accum, u_count, v_accum, v_count, (uint32_t)bit_depth);
+    free(c);
+    return 0;
+}

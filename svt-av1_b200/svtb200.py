@@ -94,6 +94,18 @@ class EncodeParams(C.Structure):
     _fields_ = [("tx_size", C.c_int32), ("use_fp", C.c_int32), ("q", QuantPlane * 3)]
 
 
+class TfBlock(C.Structure):
+    _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("block_error", C.c_double * 4), ("d_factor", C.c_double * 4)]
+
+
+class TfParams(C.Structure):
+    _fields_ = [("den", C.c_double * 3), ("chroma", C.c_int32), ("block_w", C.c_int32), ("block_h", C.c_int32)]
+
+
+class TfAccum(C.Structure):
+    _fields_ = [("accum", C.c_void_p * 3), ("count", C.c_void_p * 3), ("stride_y", C.c_int32), ("stride_c", C.c_int32)]
+
+
 class TuEx(C.Structure):
     _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("plane", C.c_uint8), ("tx_type", C.c_uint8), ("tx_size", C.c_uint8),
                 ("pf_shape", C.c_uint8), ("qset", C.c_uint16), ("reserved", C.c_uint16)]
@@ -281,6 +293,14 @@ def load():
         getattr(lib, f"svt_handle_transform{n}_cuda").restype = C.c_uint64
     lib.svt_b200_encode_tus.argtypes = [C.POINTER(EncodeParams), C.POINTER(Frame), C.POINTER(Frame), C.POINTER(Frame),
                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.svt_b200_tf_planewise.argtypes = [C.POINTER(TfParams), C.POINTER(Frame), C.POINTER(Frame), C.c_void_p, C.c_int32,
+                                          C.POINTER(TfAccum), C.c_void_p]
+    lib.svt_b200_tf_central.argtypes = [C.POINTER(Frame), C.POINTER(TfAccum), C.c_int32, C.c_void_p]
+    lib.svt_b200_tf_normalize.argtypes = [C.POINTER(Frame), C.POINTER(TfAccum), C.c_int32, C.c_void_p, C.c_void_p]
+    lib.svt_b200_tf_expf_checksum.argtypes = [C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]
+    lib.svt_b200_tf_planewise_block_host.argtypes = [C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                                     C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_uint32, C.c_uint32,
+                                                     C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)] + [C.c_void_p] * 6
     lib.svt_b200_encode_tus_ex.argtypes = [C.POINTER(EncodeParamsEx), C.POINTER(Frame), C.POINTER(Frame), C.POINTER(Frame),
                                            C.POINTER(TuEx), C.c_int32, C.c_void_p, C.POINTER(C.c_int64), C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_size_t, C.c_void_p]

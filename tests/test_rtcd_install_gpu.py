@@ -28,7 +28,7 @@ def installed():
         rc.svt_cuda_uninstall_rtcd()
         want = fn()
         n = rc.svt_cuda_install_rtcd()
-        assert n == 223, n
+        assert n == 225, n
         l0 = lib.svt_b200_launch_count()
         try:
             got = fn()
@@ -151,3 +151,15 @@ def test_reference_motion_estimate_sb_on_cuda_pointers(installed):
     assert launches > 100
     params = sb.preset8_me_params(w, h, 2, 1, dist, 2, 1)
     cm.assert_me_equal(got, want, params, "reference motion_estimate_sb: CUDA pointers vs C pointers")
+
+
+@pytest.mark.parametrize("k", [0, 1, 4, 5])
+def test_reference_temporal_filter_pointers_on_cuda(installed, k):
+    """svt_av1_apply_temporal_filter_planewise / _hbd: the reference's RTCD pointers with the CUDA drop-ins installed give
+    the accumulators of its own C functions (MeContext read by the shim in oracle/rtcd_install.c)."""
+    import tf_cases as tc
+    c = tc.make_case(**tc.CASES[k])
+    want, got, launches = installed(lambda: tc.run_reference(cm.refh(), c, via_rtcd=1))
+    assert launches >= 1
+    for a, b in zip(got, want):
+        np.testing.assert_array_equal(a, b)
