@@ -1016,6 +1016,19 @@ SVT_B200_API int svt_b200_tf_planewise_block_host(int32_t bit_depth, int32_t chr
                                                   const double *block_error4, const double *d_factor4, uint32_t *y_accum,
                                                   uint16_t *y_count, uint32_t *u_accum, uint16_t *u_count, uint32_t *v_accum,
                                                   uint16_t *v_count);
+/* Picture-analysis block statistics of a whole 8-bit picture: per 64x64 SB (raster order) the 85 luma means and
+ * variances of compute_block_mean_compute_variance (EbPictureAnalysisProcess.c:1005-2575; entries in EbMeTierZeroPu order,
+ * EbMotionEstimationContext.h:51-137 = pcs->y_mean[sb][] / pcs->variance[sb][]), the 21 chroma means per plane of
+ * compute_chroma_block_mean (:493-1003; entries 0..20 of pcs->cb_mean[sb][] / cr_mean[sb][]; zero for incomplete SBs as
+ * zero_out_chroma_block_mean :432) and pcs->pic_avg_variance (:2929-2974).  full_precision must be 0: the sub-sampled flavour
+ * (BLOCK_MEAN_PREC_SUB, EbSequenceControlSet.c:192) is the only one the reference can run - its FULL flavour calls the
+ * compute_mean_8x8 RTCD pointer, which no SET_* line of aom_dsp_rtcd.c assigns.  Samples right of / below the picture read as
+ * the replicated edge, which is what the reference's padded input picture holds there.  All outputs DEVICE:
+ * y_mean [n_sb][85] uint8, variance [n_sb][85] uint16, cb_mean / cr_mean [n_sb][21] uint8 or both NULL, pic_avg_variance
+ * one uint16 or NULL (then scratch, 8 bytes of device memory, may be NULL too). */
+SVT_B200_API int svt_b200_picture_mean_variance(const SvtB200Frame *pic, int32_t full_precision, uint8_t *y_mean, uint16_t *variance,
+                                                uint8_t *cb_mean, uint8_t *cr_mean, uint16_t *pic_avg_variance, void *scratch,
+                                                void *stream);
 /* test hook: checksum of the library's expf over the floats with bit patterns lo..hi (see oracle orc_expf_checksum) */
 SVT_B200_API int svt_b200_tf_expf_checksum(uint32_t lo_bits, uint32_t hi_bits, uint64_t *out_host);
 

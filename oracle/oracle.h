@@ -132,4 +132,11 @@ ORC_API void orc_tf_central(const void *pre, int pre_stride, unsigned w, unsigne
 ORC_API uint64_t orc_tf_normalize(void *dst, int dst_stride, unsigned w, unsigned h, int hbd, const uint32_t *accum,
                                   const uint16_t *count, int acc_stride);
 
+/* ---- picture-analysis block statistics (pa_oracle.c; EbPictureAnalysisProcess.c:287-378, 432-1003, 1005-2575, 2929-2974) ---- */
+ORC_API void orc_sb_mean_variance(const uint8_t *y, int stride, int full_precision, uint8_t mean_out[85], uint16_t var_out[85]);
+ORC_API void orc_sb_chroma_mean(const uint8_t *c, int stride, int full_precision, uint8_t mean_out[21]);
+ORC_API uint16_t orc_picture_mean_variance(const uint8_t *y, int stride_y, const uint8_t *cb, const uint8_t *cr, int stride_c, int width,
+                                           int height, int full_precision, uint8_t *y_mean, uint16_t *variance, uint8_t *cb_mean,
+                                           uint8_t *cr_mean);
+
 #endif

@@ -997,3 +997,38 @@ REFH_API int refh_tf_planewise(int via_rtcd, int bit_depth, int chroma, int bloc
     free(c);
     return 0;
 }
+
+/* ====================================================================================================
+ * Picture analysis: the reference's compute_block_mean_compute_variance / compute_chroma_block_mean on one SB
+ * (EbPictureAnalysisProcess.c:1005, :493) with the minimal control sets they touch.
+ * ================================================================================================== */
+EbErrorType compute_block_mean_compute_variance(SequenceControlSet *scs_ptr, PictureParentControlSet *pcs_ptr,
+                                                EbPictureBufferDesc *input_padded_picture_ptr, uint32_t sb_index,
+                                                uint32_t input_luma_origin_index);
+EbErrorType compute_chroma_block_mean(SequenceControlSet *scs_ptr, PictureParentControlSet *pcs_ptr,
+                                      EbPictureBufferDesc *input_padded_picture_ptr, uint32_t sb_coding_order,
+                                      uint32_t input_cb_origin_index, uint32_t input_cr_origin_index);
+REFH_API int refh_sb_mean_variance(uint8_t *y, int stride_y, uint32_t luma_index, uint8_t *cb, uint8_t *cr, int stride_c,
+                                   uint32_t chroma_index, int full_precision, uint8_t *y_mean85, uint16_t *var85, uint8_t *cb_mean85,
+                                   uint8_t *cr_mean85) {
+    refh_init();
+    SequenceControlSet *scs = (SequenceControlSet *)calloc(1, sizeof(SequenceControlSet));
+    PictureParentControlSet *pcs = (PictureParentControlSet *)calloc(1, sizeof(PictureParentControlSet));
+    EbPictureBufferDesc pic;
+    memset(&pic, 0, sizeof(pic));
+    if (!scs || !pcs) return -1;
+    scs->block_mean_calc_prec = full_precision ? BLOCK_MEAN_PREC_FULL : BLOCK_MEAN_PREC_SUB;
+    uint8_t *ym = y_mean85, *cbm = cb_mean85, *crm = cr_mean85;
+    uint16_t *vr = var85;
+    pcs->y_mean = &ym;
+    pcs->cb_mean = &cbm;
+    pcs->cr_mean = &crm;
+    pcs->variance = &vr;
+    pic.buffer_y = y, pic.buffer_cb = cb, pic.buffer_cr = cr;
+    pic.stride_y = (uint16_t)stride_y, pic.stride_cb = pic.stride_cr = (uint16_t)stride_c;
+    compute_block_mean_compute_variance(scs, pcs, &pic, 0, luma_index);
+    if (cb && cr) compute_chroma_block_mean(scs, pcs, &pic, 0, chroma_index, chroma_index);
+    free(scs);
+    free(pcs);
+    return 0;
+}
