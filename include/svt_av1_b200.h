@@ -1029,6 +1029,11 @@ SVT_B200_API int svt_b200_tf_planewise_block_host(int32_t bit_depth, int32_t chr
 SVT_B200_API int svt_b200_picture_mean_variance(const SvtB200Frame *pic, int32_t full_precision, uint8_t *y_mean, uint16_t *variance,
                                                 uint8_t *cb_mean, uint8_t *cr_mean, uint16_t *pic_avg_variance, void *scratch,
                                                 void *stream);
+/* the same with HOST planes (sample (0,0) pointers, strides in bytes) and host output arrays; synchronous */
+SVT_B200_API int svt_b200_picture_mean_variance_host(const uint8_t *y, int32_t stride_y, const uint8_t *cb, const uint8_t *cr,
+                                                     int32_t stride_c, int32_t width, int32_t height, uint8_t *y_mean,
+                                                     uint16_t *variance, uint8_t *cb_mean, uint8_t *cr_mean,
+                                                     uint16_t *pic_avg_variance);
 /* test hook: checksum of the library's expf over the floats with bit patterns lo..hi (see oracle orc_expf_checksum) */
 SVT_B200_API int svt_b200_tf_expf_checksum(uint32_t lo_bits, uint32_t hi_bits, uint64_t *out_host);
 

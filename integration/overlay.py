@@ -1,5 +1,5 @@
 #!/usr/bin/env python3
-"""Builds the overlay sources: copies of SIX reference files with the CUDA-backend hooks inserted, written to
+"""Builds the overlay sources: copies of SEVEN reference files with the CUDA-backend hooks inserted, written to
 integration/_build/src/ (git-ignored; nothing of the reference is committed to this repository).
 
 Each hook is (file, anchor text that must occur exactly once [after an optional `after` marker], action).  The script
@@ -18,6 +18,8 @@ The hooks (all behind `#if SVT_CUDA`, all inert unless the environment sets SVT_
   EbCdefProcess.c               cdef_seg_search of each segment (:510-515) skipped, and finish_cdef_search +
                                 svt_av1_cdef_frame (:521-534) replaced by svt_cuda_cdef_picture for the whole picture
   EbRestProcess.c               svt_av1_loop_restoration_filter_frame (:533) -> svt_cuda_lr_frame (presets <= 6)
+  EbPictureAnalysisProcess.c    compute_picture_spatial_statistics (:2929): the per-SB loop is skipped when
+                                svt_cuda_pa_statistics did the picture (SVT_CUDA_PA=1, a parity switch, off by default)
 """
 import difflib
 import os
@@ -117,6 +119,12 @@ HOOKS = [
               "                    if (svt_cuda_lr_applies(pcs_ptr, scs_ptr))\n"
               "                        svt_cuda_lr_frame(pcs_ptr, scs_ptr); /* the frame apply; the search above stays the reference's */\n"
               "                    else\n"
+              "#endif\n"),
+    # --------------------------------------------------------------------------------------- EbPictureAnalysisProcess.c
+    dict(file="Source/Lib/Encoder/Codec/EbPictureAnalysisProcess.c",
+         anchor="    uint64_t pic_tot_variance = 0;\n", after="void compute_picture_spatial_statistics(SequenceControlSet", action="insert_after",
+         text="#if SVT_CUDA\n"
+              "    if (svt_cuda_pa_statistics(pcs_ptr, input_picture_ptr, input_padded_picture_ptr, sb_total_count)) return;\n"
               "#endif\n"),
 ]
 

@@ -41,8 +41,14 @@
 
 #include "svt_av1_b200.h"
 #include "svt_cuda_backend.h"
+#include "aom_dsp_rtcd.h"
+static volatile long long g_tf_calls = 0;
+#define SVT_CUDA_TF_COUNT() __sync_fetch_and_add(&g_tf_calls, 1)
+#include "svt_cuda_tf_shim.h"
+static void (*g_tf_saved[2])(void);
 
-static int            g_on = -1, g_me = 0, g_dlf = 0, g_cdef = 0, g_lr = 0, g_fuse = 0, g_me_ds = 0, g_prof = 0;
+static int            g_on = -1, g_me = 0, g_dlf = 0, g_cdef = 0, g_lr = 0, g_fuse = 0, g_me_ds = 0, g_prof = 0, g_tf = 0, g_pa = 0;
+static volatile long long g_pa_calls = 0;
 static SvtB200Engine *g_engine = NULL;
 static int            g_users  = 0;
 
@@ -86,6 +92,9 @@ void svt_cuda_backend_init(void) {
             g_lr    = env_flag("SVT_CUDA_LR", 1);
             g_fuse  = env_flag("SVT_CUDA_FUSE", 1);
             g_me_ds = env_flag("SVT_CUDA_ME_DS", 0);
+            /* parity switches, off by default: bit-exact, but per-block / per-picture round trips that do not pay */
+            g_tf = env_flag("SVT_CUDA_TF", 0);
+            g_pa = env_flag("SVT_CUDA_PA", 0);
         }
     }
     if (!g_on) return;
@@ -93,8 +102,14 @@ void svt_cuda_backend_init(void) {
         const char *d  = getenv("SVT_CUDA_DEVICE");
         int         rc = svt_b200_engine_create(d ? atoi(d) : 0, &g_engine);
         if (rc) die("svt_b200_engine_create", rc);
-        SVT_LOG("SVT [CUDA backend]: libsvtav1_b200 v%d on device %d (me %d, dlf %d, cdef %d, lr %d)\n", svt_b200_version(),
-                d ? atoi(d) : 0, g_me, g_dlf, g_cdef, g_lr);
+        SVT_LOG("SVT [CUDA backend]: libsvtav1_b200 v%d on device %d (me %d, dlf %d, cdef %d, lr %d, tf %d, pa %d)\n", svt_b200_version(),
+                d ? atoi(d) : 0, g_me, g_dlf, g_cdef, g_lr, g_tf, g_pa);
+        if (g_tf) { /* the temporal filter's weighting through the GPU drop-ins (svt_cuda_tf_shim.h) */
+            g_tf_saved[0] = (void (*)(void))svt_av1_apply_temporal_filter_planewise;
+            g_tf_saved[1] = (void (*)(void))svt_av1_apply_temporal_filter_planewise_hbd;
+            svt_av1_apply_temporal_filter_planewise     = svt_av1_apply_temporal_filter_planewise_cuda;
+            svt_av1_apply_temporal_filter_planewise_hbd = svt_av1_apply_temporal_filter_planewise_hbd_cuda;
+        }
     }
 }
 
@@ -121,6 +136,13 @@ void svt_cuda_backend_deinit(void) {
                     (unsigned long long)st.me_plane_hits, (unsigned long long)st.dlf_frames, (unsigned long long)st.cdef_frames,
                     (unsigned long long)st.lr_frames, st.h2d_bytes / 1e6, st.d2h_bytes / 1e6, st.pinned_bytes / 1e6, (unsigned long long)svt_b200_launch_count(),
                     st.ns_slot_wait / 1e6, st.ns_issue / 1e6, st.ns_plane_wait / 1e6, st.ns_sync / 1e6, st.ns_host_copy / 1e6);
+        }
+        if (g_prof && (g_tf || g_pa))
+            fprintf(stderr, "SVT [CUDA profile]: tf blocks on the GPU %lld, picture-analysis pictures on the GPU %lld\n", (long long)g_tf_calls,
+                    (long long)g_pa_calls);
+        if (g_tf && g_tf_saved[0]) {
+            svt_av1_apply_temporal_filter_planewise     = (__typeof__(svt_av1_apply_temporal_filter_planewise))g_tf_saved[0];
+            svt_av1_apply_temporal_filter_planewise_hbd = (__typeof__(svt_av1_apply_temporal_filter_planewise_hbd))g_tf_saved[1];
         }
         svt_b200_engine_destroy(g_engine);
         g_engine = NULL;
@@ -734,4 +756,39 @@ void svt_cuda_lr_frame(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr) 
     int rc      = svt_b200_engine_lr_frame(g_engine, &p, n_units, &f, lines);
     if (rc) die("svt_b200_engine_lr_frame", rc);
     if (g_prof) stat_add(1, ST_LR, t0);
+}
+
+/* compute_picture_spatial_statistics (EbPictureAnalysisProcess.c:2929-2974): SVT_CUDA_PA=1 computes pcs->y_mean / variance /
+ * cb_mean / cr_mean of every SB and pic_avg_variance in one GPU call.  Returns 0 when the C loop must run. */
+int svt_cuda_pa_statistics(PictureParentControlSet *pcs_ptr, EbPictureBufferDesc *input_picture_ptr,
+                           EbPictureBufferDesc *input_padded_picture_ptr, uint32_t sb_total_count) {
+    if (g_on <= 0 || !g_pa || input_picture_ptr->bit_depth != EB_8BIT) return 0;
+    const int w = input_picture_ptr->width, h = input_picture_ptr->height;
+    const int sbw = (w + 63) / 64, sbh = (h + 63) / 64;
+    if ((uint32_t)(sbw * sbh) != sb_total_count || sb_total_count != pcs_ptr->sb_total_count) return 0;
+    /* the SBs must be in raster order (sb_params_array is), checked on the last one */
+    if (pcs_ptr->sb_params_array[sb_total_count - 1].origin_x != (sbw - 1) * 64 || pcs_ptr->sb_params_array[sb_total_count - 1].origin_y != (sbh - 1) * 64)
+        return 0;
+    const size_t n  = sb_total_count;
+    uint8_t *    ym = (uint8_t *)malloc(n * (85 + 21 + 21) + n * 85 * 2 + 2);
+    if (!ym) return 0;
+    uint16_t *vr = (uint16_t *)(ym + n * (85 + 21 + 21) + ((n * (85 + 21 + 21)) & 1)) ;
+    uint8_t * cbm = ym + n * 85, *crm = cbm + n * 21;
+    uint16_t  avg = 0;
+    /* luma from the padded picture (same samples inside the picture), chroma from the input picture, as the reference */
+    const uint8_t *y  = input_padded_picture_ptr->buffer_y + input_padded_picture_ptr->origin_y * input_padded_picture_ptr->stride_y + input_padded_picture_ptr->origin_x;
+    const uint8_t *cb = input_picture_ptr->buffer_cb + (input_picture_ptr->origin_y >> 1) * input_picture_ptr->stride_cb + (input_picture_ptr->origin_x >> 1);
+    const uint8_t *cr = input_picture_ptr->buffer_cr + (input_picture_ptr->origin_y >> 1) * input_picture_ptr->stride_cr + (input_picture_ptr->origin_x >> 1);
+    int rc = svt_b200_picture_mean_variance_host(y, input_padded_picture_ptr->stride_y, cb, cr, input_picture_ptr->stride_cb, w, h, ym, vr, cbm, crm, &avg);
+    if (rc) die("svt_b200_picture_mean_variance_host", rc);
+    for (uint32_t sb = 0; sb < sb_total_count; sb++) {
+        memcpy(pcs_ptr->y_mean[sb], ym + (size_t)sb * 85, 85);
+        memcpy(pcs_ptr->variance[sb], vr + (size_t)sb * 85, 85 * sizeof(uint16_t));
+        memcpy(pcs_ptr->cb_mean[sb], cbm + (size_t)sb * 21, 21); /* the reference writes entries 0..20 only */
+        memcpy(pcs_ptr->cr_mean[sb], crm + (size_t)sb * 21, 21);
+    }
+    pcs_ptr->pic_avg_variance = avg;
+    free(ym);
+    __sync_fetch_and_add(&g_pa_calls, 1);
+    return 1;
 }

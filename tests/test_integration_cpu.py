@@ -33,10 +33,10 @@ def test_overlay_hooks_apply_to_the_reference_tree(tmp_path):
     replaces one condition line."""
     subprocess.check_call([sys.executable, os.path.join(ROOT, "integration", "overlay.py")])
     patch = open(os.path.join(B, "overlay.patch")).read()
-    assert patch.count("--- a/") == 6
+    assert patch.count("--- a/") == 7
     removed = [l for l in patch.splitlines() if l.startswith("-") and not l.startswith("---")]
     assert len(removed) == 1 and "loop_filter_mode == 1" in removed[0], removed
-    for name in ("svt_cuda_backend_init", "svt_cuda_backend_deinit", "svt_cuda_me_segment", "svt_cuda_dlf_frame", "svt_cuda_cdef_picture", "svt_cuda_lr_frame"):
+    for name in ("svt_cuda_backend_init", "svt_cuda_backend_deinit", "svt_cuda_me_segment", "svt_cuda_dlf_frame", "svt_cuda_cdef_picture", "svt_cuda_lr_frame", "svt_cuda_pa_statistics"):
         assert name in patch
 
 
