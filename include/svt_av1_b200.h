@@ -1034,6 +1034,14 @@ SVT_B200_API int svt_b200_picture_mean_variance_host(const uint8_t *y, int32_t s
                                                      int32_t stride_c, int32_t width, int32_t height, uint8_t *y_mean,
                                                      uint16_t *variance, uint8_t *cb_mean, uint8_t *cr_mean,
                                                      uint16_t *pic_avg_variance);
+/* Open-loop intra search of the TPL path for every 16x16 macroblock of an 8-bit picture: replaces
+ * the open_loop_intra_search_mb calls of the ME process (EbMotionEstimationProcess.c:965-975; C EbMotionEstimation.c:3043-3155)
+ * for the TPL controls of presets >= 5 (tpl_ctrls.tpl_opt_flag = 1, EbPictureDecisionProcess.c:3899-3935), where the mode loop
+ * is DC_PRED only.  cost: DEVICE int64 [mb rows][mb cols] with mb cols = (width + 15) / 16 (the reference's mb_stride):
+ * OisMbResults::intra_cost; intra_mode is DC_PRED (0) for every macroblock.  The multi-mode search of presets < 5
+ * (directional / smooth / Paeth predictors) is not built. */
+SVT_B200_API int svt_b200_ois_dc_picture(const SvtB200Frame *pic, int64_t *cost, void *stream);
+SVT_B200_API int svt_b200_ois_dc_picture_host(const uint8_t *y, int32_t stride, int32_t width, int32_t height, int64_t *cost);
 /* test hook: checksum of the library's expf over the floats with bit patterns lo..hi (see oracle orc_expf_checksum) */
 SVT_B200_API int svt_b200_tf_expf_checksum(uint32_t lo_bits, uint32_t hi_bits, uint64_t *out_host);
 

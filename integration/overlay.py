@@ -9,7 +9,9 @@ also writes the result as a unified diff (integration/_build/overlay.patch) - th
 The hooks (all behind `#if SVT_CUDA`, all inert unless the environment sets SVT_CUDA=1):
   EbEncHandle.c                 svt_av1_enc_init: svt_cuda_backend_init() after setup_rtcd_internal (:1144-1145);
                                 svt_av1_enc_deinit: svt_cuda_backend_deinit() (:1879)
-  EbMotionEstimationProcess.c   the SB loop (:831-965) becomes the else-branch of svt_cuda_me_segment(...)
+  EbMotionEstimationProcess.c   the SB loop (:831-965) becomes the else-branch of svt_cuda_me_segment(...); the open-loop
+                                intra search loop (:965-975) the else-branch of svt_cuda_ois_segment (SVT_CUDA_OIS=1, a
+                                parity switch, off by default)
   EbCodingLoop.c                the per-SB deblocking of loop_filter_mode 1 (:3785-3795) is skipped when the frame is
                                 deblocked on the GPU in dlf_kernel instead
   EbDlfProcess.c                svt_av1_pick_filter_level(FULL_IMAGE) + svt_av1_loop_filter_frame (:203-216) ->
@@ -54,6 +56,14 @@ HOOKS = [
     dict(file="Source/Lib/Encoder/Codec/EbMotionEstimationProcess.c",
          anchor="                for (uint32_t y_sb_index = y_sb_start_index; y_sb_index < y_sb_end_index;\n",
          after="                use_scaled_source_refs_if_needed(pcs_ptr,\n", action="insert_before", text=ME_CALL),
+    dict(file="Source/Lib/Encoder/Codec/EbMotionEstimationProcess.c",
+         anchor="                for (uint32_t y_sb_index = y_sb_start_index; y_sb_index < y_sb_end_index;\n",
+         after="                scs_ptr->static_config.enable_tpl_la)\n", action="insert_before",
+         text="#if SVT_CUDA\n"
+              "                if (svt_cuda_ois_segment(pcs_ptr, scs_ptr, input_picture_ptr, segment_index)) {\n"
+              "                    /* every macroblock of the picture was searched on the GPU by the thread that got segment 0 */\n"
+              "                } else\n"
+              "#endif\n"),
     # --------------------------------------------------------------------------------------------------- EbCodingLoop.c
     dict(file="Source/Lib/Encoder/Codec/EbCodingLoop.c",
          anchor="    if (dlf_enable_flag && pcs_ptr->parent_pcs_ptr->loop_filter_mode == 1 && total_tile_cnt == 1) {\n",

@@ -47,8 +47,8 @@ static volatile long long g_tf_calls = 0;
 #include "svt_cuda_tf_shim.h"
 static void (*g_tf_saved[2])(void);
 
-static int            g_on = -1, g_me = 0, g_dlf = 0, g_cdef = 0, g_lr = 0, g_fuse = 0, g_me_ds = 0, g_prof = 0, g_tf = 0, g_pa = 0;
-static volatile long long g_pa_calls = 0;
+static int            g_on = -1, g_me = 0, g_dlf = 0, g_cdef = 0, g_lr = 0, g_fuse = 0, g_me_ds = 0, g_prof = 0, g_tf = 0, g_pa = 0, g_ois = 0;
+static volatile long long g_pa_calls = 0, g_ois_calls = 0;
 static SvtB200Engine *g_engine = NULL;
 static int            g_users  = 0;
 
@@ -95,6 +95,7 @@ void svt_cuda_backend_init(void) {
             /* parity switches, off by default: bit-exact, but per-block / per-picture round trips that do not pay */
             g_tf = env_flag("SVT_CUDA_TF", 0);
             g_pa = env_flag("SVT_CUDA_PA", 0);
+            g_ois = env_flag("SVT_CUDA_OIS", 0);
         }
     }
     if (!g_on) return;
@@ -137,9 +138,9 @@ void svt_cuda_backend_deinit(void) {
                     (unsigned long long)st.lr_frames, st.h2d_bytes / 1e6, st.d2h_bytes / 1e6, st.pinned_bytes / 1e6, (unsigned long long)svt_b200_launch_count(),
                     st.ns_slot_wait / 1e6, st.ns_issue / 1e6, st.ns_plane_wait / 1e6, st.ns_sync / 1e6, st.ns_host_copy / 1e6);
         }
-        if (g_prof && (g_tf || g_pa))
-            fprintf(stderr, "SVT [CUDA profile]: tf blocks on the GPU %lld, picture-analysis pictures on the GPU %lld\n", (long long)g_tf_calls,
-                    (long long)g_pa_calls);
+        if (g_prof && (g_tf || g_pa || g_ois))
+            fprintf(stderr, "SVT [CUDA profile]: tf blocks on the GPU %lld, picture-analysis pictures on the GPU %lld, open-loop intra pictures on the GPU %lld\n",
+                    (long long)g_tf_calls, (long long)g_pa_calls, (long long)g_ois_calls);
         if (g_tf && g_tf_saved[0]) {
             svt_av1_apply_temporal_filter_planewise     = (__typeof__(svt_av1_apply_temporal_filter_planewise))g_tf_saved[0];
             svt_av1_apply_temporal_filter_planewise_hbd = (__typeof__(svt_av1_apply_temporal_filter_planewise_hbd))g_tf_saved[1];
@@ -790,5 +791,33 @@ int svt_cuda_pa_statistics(PictureParentControlSet *pcs_ptr, EbPictureBufferDesc
     pcs_ptr->pic_avg_variance = avg;
     free(ym);
     __sync_fetch_and_add(&g_pa_calls, 1);
+    return 1;
+}
+
+/* The open-loop intra search loop of the ME process (EbMotionEstimationProcess.c:965-975): SVT_CUDA_OIS=1 and the TPL
+ * controls of presets >= 5 (DC_PRED only) -> the thread that owns segment 0 searches every macroblock of the picture in one
+ * GPU call and fills pcs->ois_mb_results; the other segments' threads skip their loop.  Returns 0 when the C loop must run. */
+int svt_cuda_ois_segment(PictureParentControlSet *pcs_ptr, SequenceControlSet *scs_ptr, EbPictureBufferDesc *input_picture_ptr,
+                         uint32_t segment_index) {
+    if (g_on <= 0 || !g_ois) return 0;
+    EbPictureBufferDesc *enh = pcs_ptr->enhanced_picture_ptr;
+    if (!pcs_ptr->tpl_data.tpl_ctrls.tpl_opt_flag || input_picture_ptr->bit_depth != EB_8BIT || !enh) return 0;
+    const int w = enh->width, h = enh->height;
+    if (w != scs_ptr->seq_header.max_frame_width || h != scs_ptr->seq_header.max_frame_height || (w & 7) || (h & 7)) return 0;
+    if (segment_index != 0) return 1;
+    const int mbw = (w + 15) / 16, mbh = (h + 15) / 16;
+    int64_t * cost = (int64_t *)malloc((size_t)mbw * mbh * sizeof(int64_t));
+    if (!cost) die("svt_cuda_ois_segment: out of memory", -1);
+    const uint8_t *y = input_picture_ptr->buffer_y + enh->origin_x + (size_t)enh->origin_y * input_picture_ptr->stride_y;
+    int rc = svt_b200_ois_dc_picture_host(y, input_picture_ptr->stride_y, w, h, cost);
+    if (rc) die("svt_b200_ois_dc_picture_host", rc);
+    for (int i = 0; i < mbw * mbh; i++) {
+        OisMbResults *r = pcs_ptr->ois_mb_results[i];
+        memset(r, 0, sizeof(*r));
+        r->intra_mode = DC_PRED;
+        r->intra_cost = cost[i];
+    }
+    free(cost);
+    __sync_fetch_and_add(&g_ois_calls, 1);
     return 1;
 }

@@ -30,6 +30,9 @@ void svt_cuda_lr_frame(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr);
 int  svt_cuda_pa_statistics(PictureParentControlSet *pcs_ptr, EbPictureBufferDesc *input_picture_ptr,
                             EbPictureBufferDesc *input_padded_picture_ptr, uint32_t sb_total_count); /* SVT_CUDA_PA=1 */
 
+int  svt_cuda_ois_segment(PictureParentControlSet *pcs_ptr, SequenceControlSet *scs_ptr, EbPictureBufferDesc *input_picture_ptr,
+                          uint32_t segment_index); /* SVT_CUDA_OIS=1 */
+
 /* SVT_CUDA_PROFILE=1: wall time the stage threads spend in each stage, CPU path included (stage: 0 me, 1 dlf, 2 cdef) */
 int64_t svt_cuda_prof_begin(void);
 void    svt_cuda_prof_end_cpu(int stage, int64_t t0);

@@ -139,4 +139,6 @@ ORC_API uint16_t orc_picture_mean_variance(const uint8_t *y, int stride_y, const
                                            int height, int full_precision, uint8_t *y_mean, uint16_t *variance, uint8_t *cb_mean,
                                            uint8_t *cr_mean);
 
+ORC_API void orc_ois_dc_picture(const uint8_t *y, int stride, int width, int height, int64_t *cost);
+
 #endif

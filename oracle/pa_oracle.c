@@ -90,3 +90,40 @@ uint16_t orc_picture_mean_variance(const uint8_t *y, int stride_y, const uint8_t
         }
     return (uint16_t)(tot / (uint64_t)(sbw * sbh));
 }
+
+/* ---- open-loop intra search, the flavour of presets >= 5 (TPL "opt" controls) -------------------------------------
+ * open_loop_intra_search_mb (EbMotionEstimation.c:3043-3155) with tpl_ctrls.tpl_opt_flag = 1 (set_tpl_controls,
+ * EbPictureDecisionProcess.c:3899-3935: levels 5 and up): the mode loop runs DC_PRED only.  Per 16x16 macroblock whose
+ * origin is inside the picture: neighbours from the SOURCE (update_neighbor_samples_array_open_loop_mb,
+ * EbEncIntraPrediction.c:1201-1280: above = the row over the block, at most min(32, width - x) samples, the rest 127;
+ * left = the column left of it, at most min(32, height - y) samples, the rest 129), dc_pred[x > 0][y > 0][TX_16X16]
+ * (EbIntraPrediction.c:2606-2631), residual, svt_av1_wht_fwd_txfm = the forward 16x16 DCT_DCT (EbTransforms.c:3827),
+ * intra_cost = svt_aom_satd = sum of |coefficient|.  y points at sample (0,0) of a plane that is readable (padded, as the
+ * reference's input picture is) up to the next multiple of 16 in both directions.  cost: [mb rows][mb cols]. */
+void orc_ois_dc_picture(const uint8_t *y, int stride, int width, int height, int64_t *cost) {
+    const int mbw = (width + 15) / 16, mbh = (height + 15) / 16;
+    for (int my = 0; my < mbh; my++)
+        for (int mx = 0; mx < mbw; mx++) {
+            const int x = mx * 16, yy = my * 16;
+            int above[16], left[16];
+            const int na = width - x < 32 ? width - x : 32, nl = height - yy < 32 ? height - yy : 32;
+            for (int i = 0; i < 16; i++) {
+                above[i] = (yy > 0 && i < na) ? y[(size_t)(yy - 1) * stride + x + i] : 127;
+                left[i] = (x > 0 && i < nl) ? y[(size_t)(yy + i) * stride + x - 1] : 129;
+            }
+            int sa = 0, sl = 0, dc;
+            for (int i = 0; i < 16; i++) sa += above[i], sl += left[i];
+            if (x > 0 && yy > 0) dc = (sa + sl + 16) >> 5;
+            else if (yy > 0) dc = (sa + 8) >> 4;
+            else if (x > 0) dc = (sl + 8) >> 4;
+            else dc = 128;
+            int16_t res[256];
+            int32_t coeff[256];
+            for (int r = 0; r < 16; r++)
+                for (int c = 0; c < 16; c++) res[r * 16 + c] = (int16_t)(y[(size_t)(yy + r) * stride + x + c] - dc);
+            orc_fwd_txfm2d(res, coeff, 16, 0 /* DCT_DCT */, 2 /* TX_16X16 */, 8);
+            int64_t s = 0;
+            for (int i = 0; i < 256; i++) s += coeff[i] < 0 ? -(int64_t)coeff[i] : coeff[i];
+            cost[my * mbw + mx] = s;
+        }
+}

@@ -1032,3 +1032,56 @@ REFH_API int refh_sb_mean_variance(uint8_t *y, int stride_y, uint32_t luma_index
     free(pcs);
     return 0;
 }
+
+/* ====================================================================================================
+ * Open-loop intra search: the reference's open_loop_intra_search_mb (EbMotionEstimation.c:3043) over every SB of a
+ * picture with the TPL controls of `tpl_level` (set_tpl_controls: >= 5 -> DC_PRED only).  buf: padded luma buffer,
+ * (origin_x, origin_y) its first picture sample.  cost / mode: [mb rows][mb cols].
+ * ================================================================================================== */
+EbErrorType open_loop_intra_search_mb(PictureParentControlSet *pcs_ptr, uint32_t sb_index, EbPictureBufferDesc *input_ptr);
+EbErrorType sb_params_init(SequenceControlSet *scs_ptr);
+void set_tpl_controls(PictureParentControlSet *pcs_ptr, uint8_t tpl_level);
+void init_intra_dc_predictors_c_internal(void);
+void init_intra_predictors_internal(void);
+REFH_API int refh_ois_picture(uint8_t *buf, int stride, int origin_x, int origin_y, int width, int height, int tpl_level,
+                              int64_t *cost, int32_t *mode) {
+    refh_init();
+    static int intra_tables = 0;
+    if (!intra_tables) { /* as svt_av1_enc_init does (EbEncHandle.c:1149-1153) */
+        init_intra_dc_predictors_c_internal();
+        init_intra_predictors_internal();
+        intra_tables = 1;
+    }
+    SequenceControlSet *scs = (SequenceControlSet *)calloc(1, sizeof(SequenceControlSet));
+    PictureParentControlSet *pcs = (PictureParentControlSet *)calloc(1, sizeof(PictureParentControlSet));
+    EbObjectWrapper wrap;
+    EbPictureBufferDesc pic;
+    memset(&wrap, 0, sizeof(wrap));
+    memset(&pic, 0, sizeof(pic));
+    if (!scs || !pcs) return -1;
+    wrap.object_ptr = scs;
+    pcs->scs_wrapper_ptr = &wrap;
+    pcs->scs_ptr = scs;
+    scs->sb_sz = 64;
+    scs->seq_header.max_frame_width = (uint16_t)width;
+    scs->seq_header.max_frame_height = (uint16_t)height;
+    scs->static_config.enable_paeth = DEFAULT;
+    scs->static_config.enable_smooth = DEFAULT;
+    if (sb_params_init(scs) != EB_ErrorNone) return -2;
+    pic.buffer_y = buf, pic.stride_y = (uint16_t)stride, pic.origin_x = (uint16_t)origin_x, pic.origin_y = (uint16_t)origin_y;
+    pic.width = (uint16_t)width, pic.height = (uint16_t)height;
+    pcs->enhanced_picture_ptr = &pic;
+    set_tpl_controls(pcs, (uint8_t)tpl_level);
+    const int mbw = (width + 15) / 16, mbh = (height + 15) / 16;
+    OisMbResults *res = (OisMbResults *)calloc((size_t)mbw * mbh, sizeof(OisMbResults));
+    OisMbResults **ptrs = (OisMbResults **)calloc((size_t)mbw * mbh, sizeof(OisMbResults *));
+    for (int i = 0; i < mbw * mbh; i++) {
+        ptrs[i] = &res[i];
+        res[i].intra_cost = -1, res[i].intra_mode = -1;
+    }
+    pcs->ois_mb_results = ptrs;
+    for (uint32_t sb = 0; sb < scs->sb_total_count; sb++) open_loop_intra_search_mb(pcs, sb, &pic);
+    for (int i = 0; i < mbw * mbh; i++) cost[i] = res[i].intra_cost, mode[i] = res[i].intra_mode;
+    free(res), free(ptrs), free(scs), free(pcs); /* sb_params_array belongs to the reference's allocation tracker */
+    return 0;
+}

@@ -1156,4 +1156,109 @@ int svt_b200_encode_tus_ex(const SvtB200EncodeParamsEx *p, const SvtB200Frame *s
     SVTB_CUDA_TRY(cudaStreamSynchronize(st));
     return rc;
 }
+} // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Open-loop intra search of the TPL path, the flavour of presets >= 5 (tpl_opt_flag: DC_PRED only):
+// open_loop_intra_search_mb (EbMotionEstimation.c:3043-3155) for every 16x16 macroblock of a picture in one launch.
+// 16 threads per macroblock (one row / one column of the 16x16 DCT each), 8 macroblocks per CTA.  Neighbours come from
+// the source picture (update_neighbor_samples_array_open_loop_mb, EbEncIntraPrediction.c:1201: above = at most
+// min(32, width - x) samples of the row over the block, the rest 127; left = at most min(32, height - y) samples, the rest
+// 129), the predictor is dc_pred[x > 0][y > 0][TX_16X16], the cost svt_aom_satd of svt_av1_fwd_txfm2d_16x16(DCT_DCT) of the
+// residual.  Samples right of / below the picture are read as the replicated edge (the reference reads its padded input
+// picture there).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+struct OisDev {
+    const uint8_t *y;
+    int stride, w, h, mbw, n_mb;
+    long long *cost;
+};
+__global__ void __launch_bounds__(TX_NT) ois_dc_kernel(const OisDev d) {
+    extern __shared__ int32_t sm[];
+    constexpr int W = 16, T = 16, BPC = TX_NT / T;
+    const int pitch = tx_pitch(W);
+    const int lb = threadIdx.x / T, li = threadIdx.x % T;
+    const int mb = blockIdx.x * BPC + lb;
+    const bool live = mb < d.n_mb;
+    int32_t *buf = sm + lb * (pitch * W);
+    const TxCfg t = make_txcfg(2 /* TX_16X16 */, 0 /* DCT_DCT */);
+    const int mx = live ? mb % d.mbw : 0, my = live ? mb / d.mbw : 0, x = mx * 16, y = my * 16;
+    // DC: lane li holds above[li] and left[li]; the 16 lanes of a macroblock are one half-warp
+    int a = 0, l = 0;
+    if (y > 0) a = li < min(32, d.w - x) ? d.y[(size_t)(y - 1) * d.stride + x + li] : 127;
+    if (x > 0) l = li < min(32, d.h - y) ? d.y[(size_t)(y + li) * d.stride + x - 1] : 129;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        l += __shfl_xor_sync(0xffffffffu, l, o);
+    }
+    const int dc = (x > 0 && y > 0) ? (a + l + 16) >> 5 : y > 0 ? (a + 8) >> 4 : x > 0 ? (l + 8) >> 4 : 128;
+    if (live) {
+        const uint8_t *row = d.y + (size_t)min(y + li, d.h - 1) * d.stride;
+#pragma unroll
+        for (int c = 0; c < W; c++) buf[li * pitch + c] = (int)row[min(x + c, d.w - 1)] - dc;
+    }
+    __syncthreads();
+    if (live) {
+        const int fs0 = t.fs0, fs1 = t.fs1;
+        fwd_1d_pass(buf + li, pitch, t.h, t.vk, t.cbc, [=](int32_t v) { return (int32_t)((uint32_t)v << fs0); },
+                    [=](int32_t v) { return fs1 ? round_shift64((long long)v, -fs1) : v; });
+    }
+    __syncthreads();
+    long long s = 0;
+    if (live) {
+        const int fs2 = t.fs2;
+        fwd_1d_pass(buf + li * pitch, 1, t.w, t.hk, t.cbr, [](int32_t v) { return v; },
+                    [=](int32_t v) { return fs2 ? round_shift64((long long)v, -fs2) : v; });
+#pragma unroll
+        for (int c = 0; c < W; c++) s += abs(buf[li * pitch + c]);
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (live && li == 0) d.cost[mb] = s;
+}
+} // namespace
+
+extern "C" {
+
+// pic: 8-bit picture (the luma plane is read); cost: DEVICE int64 [mb rows][mb cols], mb cols = (width + 15) / 16 =
+// the reference's mb_stride; every entry is OisMbResults::intra_cost of that macroblock, its intra_mode is DC_PRED.
+int svt_b200_ois_dc_picture(const SvtB200Frame *pic, int64_t *cost, void *stream) {
+    if (!pic || !pic->y || pic->bit_depth != 8 || !cost || pic->width <= 0 || pic->height <= 0) {
+        set_error("svt_b200_ois_dc_picture: bad argument (8-bit pictures)");
+        return SVT_B200_ERR_ARG;
+    }
+    txfm_tables_init();
+    OisDev d;
+    d.y = (const uint8_t *)pic->y, d.stride = pic->stride_y, d.w = pic->width, d.h = pic->height;
+    d.mbw = (pic->width + 15) / 16;
+    d.n_mb = d.mbw * ((pic->height + 15) / 16);
+    d.cost = (long long *)cost;
+    const int bpc = TX_NT / 16;
+    SVTB_LAUNCH(ois_dc_kernel, (d.n_mb + bpc - 1) / bpc, TX_NT, (size_t)bpc * tx_pitch(16) * 16 * sizeof(int32_t), (cudaStream_t)stream, d);
+    SVTB_CUDA_TRY(cudaGetLastError());
+    return SVT_B200_OK;
+}
+
+// the same with a HOST luma plane in and a host cost array out (the encoder binding: integration/svt_cuda_backend.c)
+int svt_b200_ois_dc_picture_host(const uint8_t *y, int32_t stride, int32_t width, int32_t height, int64_t *cost) {
+    if (!y || !cost || width <= 0 || height <= 0) {
+        set_error("svt_b200_ois_dc_picture_host: bad argument");
+        return SVT_B200_ERR_ARG;
+    }
+    const int n_mb = ((width + 15) / 16) * ((height + 15) / 16);
+    const size_t o_cost = ((size_t)width * height + 255) & ~(size_t)255, total = o_cost + (size_t)n_mb * 8;
+    ThreadCtx &c = tls();
+    c.reserve(total);
+    for (int r = 0; r < height; r++) memcpy(c.h + (size_t)r * width, y + (size_t)r * stride, width);
+    SVTB_CUDA_TRY(cudaMemcpyAsync(c.d, c.h, (size_t)width * height, cudaMemcpyHostToDevice, c.stream));
+    SvtB200Frame f = {c.d, nullptr, nullptr, width, 0, width, height, 8};
+    const int rc = svt_b200_ois_dc_picture(&f, (int64_t *)(c.d + o_cost), c.stream);
+    if (rc) return rc;
+    SVTB_CUDA_TRY(cudaMemcpyAsync(c.h + o_cost, c.d + o_cost, (size_t)n_mb * 8, cudaMemcpyDeviceToHost, c.stream));
+    SVTB_CUDA_TRY(cudaStreamSynchronize(c.stream));
+    memcpy(cost, c.h + o_cost, (size_t)n_mb * 8);
+    return SVT_B200_OK;
+}
 }

@@ -294,6 +294,8 @@ def load():
     lib.svt_b200_encode_tus.argtypes = [C.POINTER(EncodeParams), C.POINTER(Frame), C.POINTER(Frame), C.POINTER(Frame),
                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.svt_b200_picture_mean_variance.argtypes = [C.POINTER(Frame), C.c_int32] + [C.c_void_p] * 7
+    lib.svt_b200_ois_dc_picture.argtypes = [C.POINTER(Frame), C.c_void_p, C.c_void_p]
+    lib.svt_b200_ois_dc_picture_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.svt_b200_tf_planewise.argtypes = [C.POINTER(TfParams), C.POINTER(Frame), C.POINTER(Frame), C.c_void_p, C.c_int32,
                                           C.POINTER(TfAccum), C.c_void_p]
     lib.svt_b200_tf_central.argtypes = [C.POINTER(Frame), C.POINTER(TfAccum), C.c_int32, C.c_void_p]

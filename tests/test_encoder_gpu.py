@@ -101,9 +101,10 @@ def test_gop_sharded_encode_matches_cpu_per_substream(tmp_path):
 
 
 @skip_if_unbuilt
-@pytest.mark.parametrize("switch,bits,preset", [("SVT_CUDA_TF", 8, 8), ("SVT_CUDA_TF", 10, 6), ("SVT_CUDA_PA", 8, 8)])
-def test_parity_switches_temporal_filter_and_picture_analysis(tmp_path, switch, bits, preset):
-    """The two rank-4 stages inside the real encoder (off by default: they are bit-exact but do not pay - one GPU round trip
+@pytest.mark.parametrize("switch,bits,preset", [("SVT_CUDA_TF", 8, 8), ("SVT_CUDA_TF", 10, 6), ("SVT_CUDA_PA", 8, 8), ("SVT_CUDA_OIS", 8, 8)])
+def test_parity_switches_temporal_filter_picture_analysis_open_loop_intra(tmp_path, switch, bits, preset):
+    """SVT_CUDA_OIS=1: the open-loop intra search of the TPL path (rank 3, presets >= 5: DC_PRED) for a whole picture in one GPU
+    call.  The two rank-4 stages inside the real encoder (off by default: they are bit-exact but do not pay - one GPU round trip
     per 32x32 block / per picture): SVT_CUDA_TF=1 points the reference's temporal-filter RTCD pointers at the GPU drop-ins
     (every filtered sample of the key / base pictures goes through the reproduced double / expf chain), SVT_CUDA_PA=1 takes
     pcs->y_mean / variance / cb_mean / cr_mean / pic_avg_variance from svt_b200_picture_mean_variance.  The stream and the
@@ -113,10 +114,16 @@ def test_parity_switches_temporal_filter_and_picture_analysis(tmp_path, switch, 
     ref = ec.run_variant("ref_c", clip, 640, 360, 18, preset, 50, bits, str(tmp_path))
     gpu = ec.run_variant("cuda_c", clip, 640, 360, 18, preset, 50, bits, str(tmp_path), extra_env={switch: "1", "SVT_CUDA_PROFILE": "1"})
     _same(ref, gpu)
-    m = re.search(r"tf blocks on the GPU (\d+), picture-analysis pictures on the GPU (\d+)", " ".join(gpu.get("log", [])))
+    m = re.search(r"tf blocks on the GPU (\d+), picture-analysis pictures on the GPU (\d+), open-loop intra pictures on the GPU (\d+)",
+                  " ".join(gpu.get("log", [])))
     assert m, gpu.get("log")
-    n_tf, n_pa = int(m.group(1)), int(m.group(2))
-    assert (n_tf > 100 and n_pa == 0) if switch == "SVT_CUDA_TF" else (n_pa == 18 and n_tf == 0), (n_tf, n_pa)
+    n_tf, n_pa, n_ois = (int(x) for x in m.groups())
+    if switch == "SVT_CUDA_TF":
+        assert n_tf > 100 and n_pa == 0 and n_ois == 0, (n_tf, n_pa, n_ois)
+    elif switch == "SVT_CUDA_PA":
+        assert n_pa == 18 and n_tf == 0 and n_ois == 0, (n_tf, n_pa, n_ois)
+    else:
+        assert n_ois >= 1 and n_tf == 0 and n_pa == 0, (n_tf, n_pa, n_ois)
 
 
 DEC = os.path.join(ROOT, "oracle", "_ref", "app", "SvtAv1DecApp")
