@@ -155,7 +155,10 @@ __global__ void __launch_bounds__(ST_NT) stats_kernel(const StatsDev d, int tile
 // PRMT per row.  A CTA owns a 64x64 sample tile of one unit; warp = (limb, quarter of the tile rows); 16 (win 7) or 6
 // (win 5) accumulator tiles per warp stay in registers for the whole tile, are merged through int32 shared atomics,
 // combined to int64 and sent to the unit's M / H with one 64-bit global atomic per entry and CTA.
-constexpr int TC_TW = 64, TC_TH = 64, TC_NT = 384, TC_PITCH = 72, TC_SLICES = 4;
+// row pitch of the staged window planes: 37 words - the 7 window rows a quarter-warp group reads in one LDS land 5 banks
+// apart (bank = 5 kr + 2 tig: conflict-free but for one pair), against 2-way conflicts on most banks with the dense 18-word
+// pitch (ncu: 42 % of the shared wavefronts were conflicts); the source planes (one reader per group) stay dense
+constexpr int TC_TW = 64, TC_TH = 64, TC_NT = 384, TC_PITCH = 148, TC_XPITCH = 72, TC_SLICES = 4;
 
 __device__ __forceinline__ void mma_s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
@@ -166,10 +169,10 @@ __device__ __forceinline__ void mma_s8(int (&c)[4], uint32_t a0, uint32_t a1, ui
 template <typename T, int WIN>
 __global__ void __launch_bounds__(TC_NT) stats_mma_kernel(const StatsDev d, int tiles_x_max) {
     constexpr int HW = WIN / 2, WIN2 = WIN * WIN, NROW = WIN2 + 1, NJ = (NROW + 7) / 8, MT = (NJ + 1) / 2;
-    constexpr int RH = TC_TH + 2 * HW, YB = RH * TC_PITCH, XB = TC_TH * TC_PITCH;
+    constexpr int RH = TC_TH + 2 * HW, YB = RH * TC_PITCH, XB = TC_TH * TC_XPITCH, SW = TC_XPITCH / 4; // SW: staged words per row
     constexpr int NTILE = MT * NJ - MT * (MT - 1); // sum over mt of (NJ - 2 mt): column tiles nt >= 2 mt
     static_assert(3 * NTILE * 128 * 4 <= 3 * (YB + XB), "the merge buffer aliases the staged planes");
-    static_assert(TC_TW + 2 * HW <= TC_PITCH - 2, "a row read ends inside the pitch");
+    static_assert(TC_TW + 2 * HW <= TC_XPITCH - 2 && TC_XPITCH <= TC_PITCH, "a row read ends inside the staged words");
     __shared__ __align__(16) uint8_t s_raw[3 * (YB + XB)]; // [limb] window planes, then [limb] source planes
     const StatsUnit u = d.units[blockIdx.y];
     const int uw = u.h_end - u.h_start, uh = u.v_end - u.v_start;
@@ -182,8 +185,8 @@ __global__ void __launch_bounds__(TC_NT) stats_mma_kernel(const StatsDev d, int 
     const T *sr = reinterpret_cast<const T *>(d.src);
     const int tid = threadIdx.x;
     // staging: 4 samples -> one word of each limb plane
-    for (int i = tid; i < (RH + TC_TH) * (TC_PITCH / 4); i += TC_NT) {
-        const int r = i / (TC_PITCH / 4), wc = i - r * (TC_PITCH / 4);
+    for (int i = tid; i < (RH + TC_TH) * SW; i += TC_NT) {
+        const int r = i / SW, wc = i - r * SW;
         const bool win_row = r < RH;
         const int rr = win_row ? r : r - RH;
         uint32_t ph = 0, pl = 0, ps = 0;
@@ -208,7 +211,7 @@ __global__ void __launch_bounds__(TC_NT) stats_mma_kernel(const StatsDev d, int 
             pl |= (uint32_t)(uint8_t)lo << (8 * b);
             ps |= (uint32_t)(uint8_t)(hi + lo) << (8 * b);
         }
-        const int o = (win_row ? rr * TC_PITCH : 3 * YB + rr * TC_PITCH) + wc * 4, lstride = win_row ? YB : XB;
+        const int o = (win_row ? rr * TC_PITCH : 3 * YB + rr * TC_XPITCH) + wc * 4, lstride = win_row ? YB : XB;
         *reinterpret_cast<uint32_t *>(s_raw + o) = ph;
         *reinterpret_cast<uint32_t *>(s_raw + o + lstride) = pl;
         *reinterpret_cast<uint32_t *>(s_raw + o + 2 * lstride) = ps;
@@ -228,6 +231,7 @@ __global__ void __launch_bounds__(TC_NT) stats_mma_kernel(const StatsDev d, int 
             off[j] = 3 * YB + limb * XB; // the source row (m == WIN2); rows beyond it are masked to zero below
         }
     }
+    const int last_pitch = (g + 8 * (NJ - 1) >= WIN2) ? TC_XPITCH : TC_PITCH; // only row group NJ - 1 can be the source row
     const uint32_t last_mask = (g + 8 * (NJ - 1) <= WIN2) ? 0xffffffffu : 0u;
     int acc[NTILE][4];
 #pragma unroll
@@ -236,11 +240,11 @@ __global__ void __launch_bounds__(TC_NT) stats_mma_kernel(const StatsDev d, int 
         for (int q = 0; q < 4; q++) acc[t][q] = 0;
     for (int pi = slice; pi < th; pi += TC_SLICES) {
         for (int pj0 = 0; pj0 < tw; pj0 += 32) {
-            const int colb = pi * TC_PITCH + pj0 + 8 * tig;
+            const int colb = pi * TC_PITCH + pj0 + 8 * tig, colb_last = pi * last_pitch + pj0 + 8 * tig;
             uint32_t f[2 * MT][2];
 #pragma unroll
             for (int j = 0; j < NJ; j++) {
-                const int a = off[j] + colb;
+                const int a = off[j] + (j == NJ - 1 ? colb_last : colb);
                 const uint32_t *wp = reinterpret_cast<const uint32_t *>(s_raw + (a & ~3));
                 const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2], sel = 0x3210u + 0x1111u * (uint32_t)(a & 3);
                 f[j][0] = __byte_perm(w0, w1, sel);
