@@ -133,6 +133,66 @@ def geometry(w, h, bd):
     ms = ring_ms(lambda i: sb.check(lib.svt_b200_cdef_apply(C.byref(pa), C.byref(rss[i]), C.byref(oss[i]), C.c_void_p(dskip.data_ptr()),
                                                             skip.shape[1], C.c_void_p(didx.data_ptr()), SP), lib), ring)
     out["rows"].append(row("svt_b200_cdef_apply (8 strength pairs cycled over the filter blocks)", ms, 2 * pic_bytes, copy_ms))
+    del drs, dss, dos
+
+    # ---- pre-analysis entries (round 2): temporal filter, picture statistics, open-loop intra search ----------------
+    if bd == 8 or True:
+        n_acc = w * h * 3 // 2
+        xs, ys = range(0, w - 31, 32), range(0, h - 31, 32)
+        blocks = [(x, y) for y in ys for x in xs]
+        arr = (sb.TfBlock * len(blocks))()
+        rng = np.random.default_rng(7)
+        for i, (x, y) in enumerate(blocks):
+            arr[i].x, arr[i].y = x, y
+            for q in range(4):
+                arr[i].block_error[q], arr[i].d_factor[q] = float(rng.integers(0, 2000) / 256.0), 1.0 + float(rng.integers(0, 100)) / 100.0
+        dblk = torch.from_numpy(np.frombuffer(arr, dtype=np.uint8).copy()).cuda()
+        pred = cm.degrade(src, 32, amp=6)
+        small = max(4, ring // 2)  # accumulators add 6 bytes per sample: a shorter ring still exceeds L2
+        srcs, preds = [gr.DevYuv(src) for _ in range(small)], [gr.DevYuv(pred) for _ in range(small)]
+        cw, ch = (w + 1) // 2, (h + 1) // 2
+        accs = [[torch.zeros(h * w, dtype=torch.int32, device="cuda"), torch.zeros(ch * cw, dtype=torch.int32, device="cuda"),
+                 torch.zeros(ch * cw, dtype=torch.int32, device="cuda")] for _ in range(small)]
+        cnts = [[torch.zeros(h * w, dtype=torch.int16, device="cuda"), torch.zeros(ch * cw, dtype=torch.int16, device="cuda"),
+                 torch.zeros(ch * cw, dtype=torch.int16, device="cuda")] for _ in range(small)]
+        tas = []
+        for a, c_ in zip(accs, cnts):
+            ta = sb.TfAccum()
+            for i in range(3):
+                ta.accum[i], ta.count[i] = a[i].data_ptr(), c_[i].data_ptr()
+            ta.stride_y, ta.stride_c = w, cw
+            tas.append(ta)
+        tp = sb.TfParams()
+        for i in range(3):
+            tp.den[i] = 2.0 * (4 * 1.9) ** 2
+        tp.chroma, tp.block_w, tp.block_h = 1, 32, 32
+        s_s, p_s = [d.struct() for d in srcs], [d.struct() for d in preds]
+        ms_copy_small = copy_ms  # same-size copy measured above on the full ring
+        ms = ring_ms(lambda i: sb.check(lib.svt_b200_tf_planewise(C.byref(tp), C.byref(s_s[i]), C.byref(p_s[i]), C.c_void_p(dblk.data_ptr()),
+                                                                  len(blocks), C.byref(tas[i]), SP), lib), small)
+        alg_tf = 2 * pic_bytes + 2 * n_acc * 6  # source + prediction read, accumulators (4 B) and counters (2 B) read + written
+        out["rows"].append(row("svt_b200_tf_planewise (every 32x32 block of one reference picture, chroma on)", ms, alg_tf, ms_copy_small,
+                               "double-precision weight chain per sample (IEEE div x3, expf restated)"))
+        ms = ring_ms(lambda i: sb.check(lib.svt_b200_tf_central(C.byref(s_s[i]), C.byref(tas[i]), 1, SP), lib), small)
+        out["rows"].append(row("svt_b200_tf_central", ms, pic_bytes + 2 * n_acc * 6, ms_copy_small))
+        dsse = torch.zeros(2, dtype=torch.int64, device="cuda")
+        ms = ring_ms(lambda i: sb.check(lib.svt_b200_tf_normalize(C.byref(s_s[i]), C.byref(tas[i]), 1, C.c_void_p(dsse.data_ptr()), SP), lib), small)
+        out["rows"].append(row("svt_b200_tf_normalize", ms, 2 * pic_bytes + n_acc * 6, ms_copy_small))
+        del accs, cnts, preds
+        if bd == 8:
+            n_sb = ((w + 63) // 64) * ((h + 63) // 64)
+            o1 = torch.zeros(n_sb * 85, dtype=torch.uint8, device="cuda")
+            o2 = torch.zeros(n_sb * 85, dtype=torch.int16, device="cuda")
+            o3, o4 = torch.zeros(n_sb * 21, dtype=torch.uint8, device="cuda"), torch.zeros(n_sb * 21, dtype=torch.uint8, device="cuda")
+            ms = ring_ms(lambda i: sb.check(lib.svt_b200_picture_mean_variance(C.byref(s_s[i]), 0, o1.data_ptr(), o2.data_ptr(), o3.data_ptr(),
+                                                                                 o4.data_ptr(), None, None, SP), lib), small)
+            out["rows"].append(row("svt_b200_picture_mean_variance (sub-sampled flavour: every other row)", ms, pic_bytes // 2, ms_copy_small,
+                                   "reads half the rows; 32-byte sectors make the DRAM traffic ~ the whole picture"))
+            mbn = ((w + 15) // 16) * ((h + 15) // 16)
+            oc = torch.zeros(mbn, dtype=torch.int64, device="cuda")
+            ms = ring_ms(lambda i: sb.check(lib.svt_b200_ois_dc_picture(C.byref(s_s[i]), oc.data_ptr(), SP), lib), small)
+            out["rows"].append(row("svt_b200_ois_dc_picture (DC predictor + 16x16 DCT + SATD per macroblock)", ms, w * h + mbn * 8, ms_copy_small,
+                                   "transform bound: 2 x 16-point DCT passes per macroblock on 16 threads"))
     return out
 
 
