@@ -179,12 +179,12 @@ def parse_engine(log):
     return None, None, None, None
 
 
-def app_average_speed(clip, frames, env_extra, cpus):
+def app_average_speed(clip, frames, env_extra, cpus, app=None):
     """The reference's own application on the same clip: file on tmpfs -> .ivf; returns ("Average Speed" fps, ivf path)."""
     ivf = os.path.join(shm_dir(), "out_%d.ivf" % os.getpid())
     env = dict(os.environ)
     env.update(env_extra)
-    cmd = [BIN["app_cuda"], "-i", clip, "-w", str(W), "-h", str(H), "--fps", "30", "--preset", str(PRESET), "--rc", "0", "-q", str(QP),
+    cmd = [app or BIN["app_cuda"], "-i", clip, "-w", str(W), "-h", str(H), "--fps", "30", "--preset", str(PRESET), "--rc", "0", "-q", str(QP),
            "-n", str(frames), "-b", ivf] + (["--input-depth", str(BITS)] if BITS != 8 else [])
     if cpus and env.get("SVTB200_STREAMS", "1") != "1" and USE_LP:
         cmd += ["--lp", str(len(cpus))]
@@ -247,7 +247,7 @@ def run_reference(args):
     timed_frames = (frames - warm) * n
     cores = os.cpu_count() or 1
     val = timed_frames / secs
-    sample = ("%d concurrent stream(s) x %d frames (%d warm-up + %d timed) of the configs[1] workload through the reference "
+    sample = ("%d concurrent stream(s) x %d frames (%d warm-up + %d timed) of this line's config.workload through the reference "
               "encoder's own SSE2..AVX2/AVX-512 code paths (asm level picked by its cpuid dispatch), default threading on all "
               "%d logical CPUs%s; built without the 13 nasm files (36 non-hot-path symbols forwarded to C, oracle/simd_asm_shim.c)"
               % (n, frames, warm, frames - warm, cores,
@@ -262,6 +262,17 @@ def run_reference(args):
             "per_stream_fps": [round((frames - warm) / r["seconds_timed"], 3) for r in res],
             "fps_whole_run": [r["fps_all"] for r in res]}
     os.remove(out0)
+    # the like-for-like partner of the CUDA arm's `e2e` (the application's whole-run "Average Speed": initialisation, file
+    # input, pipeline fill and drain included), measured with the reference's own SIMD application on stream 0's clip
+    ref_app = os.path.join(ROOT, "oracle", "_ref", "app", "SvtAv1EncAppSimd")
+    if n == 1 and os.path.exists(ref_app):
+        try:
+            fps, ivf = app_average_speed(clips[0], frames, {}, None, app=ref_app)
+            os.remove(ivf)
+            line["app_average_speed_fps"] = fps
+        except Exception as e:  # noqa: BLE001
+            line["app_average_speed_fps"] = None
+            sys.stderr.write("reference application run failed: %s\n" % e)
     emit(line)
 
 
@@ -394,7 +405,9 @@ def run_b200(args):
                         "h2d_bytes_per_step": int(h2d / (args.steps + args.warmup)) if h2d else None,
                         "d2h_bytes_per_step": int(d2h / (args.steps + args.warmup)) if d2h else None,
                         "what": "SvtAv1EncApp (reference application, CUDA-backed library): clip file on tmpfs -> .ivf, 'Average Speed' "
-                                "over the whole run incl. pipeline fill; value above = the K timed steps through the API"},
+                                "over the whole run incl. initialisation, pipeline fill and drain; value above = the K timed steps through the API "
+                                "(the measurement the reference arm's value / e2e is).  Like for like with this number: the reference "
+                                "arm's `app_average_speed_fps` (the reference's own SIMD application, same clip)"},
                 "gpu_launches": int(launches * args.steps / (args.steps + args.warmup)) if launches else 0,
                 "bitstream_md5_stream0": md5, "bitstream_md5_matches_app": md5 == app_md5,
                 "encoder": {"fps_whole_run_api": r["fps_all"], "init_s": r["init_s"], "numa_cpus": len(cpus) if cpus else None,

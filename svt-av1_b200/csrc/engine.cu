@@ -266,8 +266,14 @@ int ensure_filt(SvtB200Engine *e, int w, int h, int bd, int mi_rows, int mi_cols
 }
 
 // memcpy split over four threads above 4 MB (see run_copies below)
+// copies at or below this size stay on the calling thread (SVT_B200_COPY_MIN_KB; thread creation costs ~50 us)
+size_t copy_split_bytes() {
+    static const size_t v = getenv("SVT_B200_COPY_MIN_KB") ? (size_t)atol(getenv("SVT_B200_COPY_MIN_KB")) << 10 : (size_t)4 << 20;
+    return v;
+}
+
 void par_memcpy(void *dst, const void *src, size_t n) {
-    if (n <= (4u << 20)) {
+    if (n <= copy_split_bytes()) {
         memcpy(dst, src, n);
         return;
     }
@@ -423,7 +429,7 @@ void run_copies(SvtB200Engine *e, const RowCopy (&c)[3]) {
         getrusage(RUSAGE_THREAD, &tr.r0);
         tr.to_host = c[0].dst_pitch != c[0].bytes; // unpack writes strided host rows
     }
-    const int nt = total > (4u << 20) ? std::max(1, std::min(4, max_threads)) : 1;
+    const int nt = total > copy_split_bytes() ? std::max(1, std::min(8, max_threads)) : 1;
     auto part = [&c, nt](int t) {
         for (const RowCopy &k : c) copy_rows(k, (int)((int64_t)k.rows * t / nt), (int)((int64_t)k.rows * (t + 1) / nt));
     };
@@ -431,7 +437,7 @@ void run_copies(SvtB200Engine *e, const RowCopy (&c)[3]) {
         part(0);
         return;
     }
-    std::thread th[3];
+    std::thread th[7];
     for (int t = 1; t < nt; t++) th[t - 1] = std::thread(part, t);
     part(0);
     for (int t = 1; t < nt; t++) th[t - 1].join();
