@@ -299,6 +299,39 @@ SVT_B200_API int svt_b200_cdef_apply(const SvtB200CdefApplyParams *p, const SvtB
                                      const SvtB200Frame *out, const uint8_t *skip8, int32_t skip_stride,
                                      const int8_t *fb_strength_idx, void *stream);
 
+/* The strength decision of the CDEF search on the device: replaces finish_cdef_search (EbEncCdef.c:1167-1340;
+ * joint_strength_search_dual :1136, svt_search_one_dual_c :1070) between svt_b200_cdef_search and svt_b200_cdef_apply, so
+ * the picture does not visit the host in between.  All integer (uint64 sums, RDCOST with the picture's lambda): exact.
+ * lambda: full_lambda of av1_lambda_assignment_function_table[pred_structure](pcs, ..., bit_depth, base_q_idx, EB_FALSE)
+ * (:1209); filter_strength[gi]: what STORE_CDEF_FILTER_STRENGTH writes for index gi (:1165; pri * CDEF_SEC_STRENGTHS + sec of
+ * get_cdef_filter_strengths, the identity for the full 64-entry table) - svt_b200_cdef_decide_table() fills it.
+ * mse / skip8: DEVICE, as svt_b200_cdef_search wrote / read them.  out: DEVICE SvtB200CdefDecision; fb_strength_idx: DEVICE
+ * int8 [nvfb*nhfb] (mbmi.cdef_strength of each filter block, -1 for the all-skip ones): the input of
+ * svt_b200_cdef_apply_dev.  scratch: DEVICE, >= 16 bytes per filter block + 64. */
+typedef struct SvtB200CdefDecideParams {
+    int32_t mi_rows, mi_cols;
+    int32_t n_strengths; /* nb_cdef_strengths[pick_method] (start_gi = 0) */
+    int32_t reserved;
+    uint64_t lambda;
+    int32_t filter_strength[SVT_B200_CDEF_MAX_STRENGTHS];
+} SvtB200CdefDecideParams;
+typedef struct SvtB200CdefDecision {
+    int32_t cdef_bits;                      /* frm_hdr->cdef_params.cdef_bits */
+    int32_t nb_cdef_strengths;              /* ppcs->nb_cdef_strengths = 1 << cdef_bits */
+    int32_t y_strength[8], uv_strength[8];  /* frm_hdr->cdef_params.cdef_y_strength / cdef_uv_strength (after STORE_...) */
+    int32_t y_index[8], uv_index[8];        /* the same as indices into the searched strength table */
+    int32_t sb_count;                       /* filter blocks that took part */
+    int32_t reserved;
+} SvtB200CdefDecision;
+SVT_B200_API int svt_b200_cdef_decide_table(int pick_method, SvtB200CdefDecideParams *p); /* n_strengths + filter_strength */
+SVT_B200_API int svt_b200_cdef_decide(const SvtB200CdefDecideParams *p, const uint64_t *mse, const uint8_t *skip8,
+                                      int32_t skip_stride, SvtB200CdefDecision *out, int8_t *fb_strength_idx, void *scratch,
+                                      void *stream);
+/* svt_b200_cdef_apply with the strengths taken from a DEVICE SvtB200CdefDecision (the output of svt_b200_cdef_decide) */
+SVT_B200_API int svt_b200_cdef_apply_dev(int32_t mi_rows, int32_t mi_cols, int32_t damping, const SvtB200CdefDecision *decision,
+                                         const SvtB200Frame *recon, const SvtB200Frame *out, const uint8_t *skip8,
+                                         int32_t skip_stride, const int8_t *fb_strength_idx, void *stream);
+
 /* =============================================================================================== */
 /* Residual / forward + inverse transform / quantisation                                           */
 /* =============================================================================================== */
@@ -970,6 +1003,14 @@ SVT_B200_API int svt_b200_engine_dlf_cdef_frame(SvtB200Engine *e, const SvtB200D
                                                 const SvtB200CdefSearchParams *sp, const SvtB200Frame *recon,
                                                 const SvtB200Frame *source, const uint8_t *skip8, int32_t skip_stride,
                                                 uint64_t *mse, SvtB200CdefDecideFn decide, void *user);
+/* The same with the strength decision on the device (svt_b200_cdef_decide instead of the callback): one upload, deblocking
+ * (dlf / mi may be NULL), CDEF search, decision, CDEF apply (apply != 0), one download, ONE synchronisation.  decision /
+ * fb_strength_idx: HOST outputs (frame header fields and mbmi.cdef_strength per filter block, -1 = all-skip block). */
+SVT_B200_API int svt_b200_engine_dlf_cdef_frame_dev(SvtB200Engine *e, const SvtB200DlfParams *dlf, const SvtB200DlfMi *mi,
+                                                    const SvtB200CdefSearchParams *sp, const SvtB200CdefDecideParams *dp,
+                                                    int32_t damping, int32_t apply, const SvtB200Frame *recon,
+                                                    const SvtB200Frame *source, const uint8_t *skip8, int32_t skip_stride,
+                                                    SvtB200CdefDecision *decision, int8_t *fb_strength_idx);
 
 /* =============================================================================================== */
 /* Temporal filtering                                                      */

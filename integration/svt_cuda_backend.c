@@ -47,8 +47,12 @@ static volatile long long g_tf_calls = 0;
 #include "svt_cuda_tf_shim.h"
 static void (*g_tf_saved[2])(void);
 
-static int            g_on = -1, g_me = 0, g_dlf = 0, g_cdef = 0, g_lr = 0, g_fuse = 0, g_me_ds = 0, g_prof = 0, g_tf = 0, g_pa = 0, g_ois = 0;
+static int            g_on = -1, g_me = 0, g_dlf = 0, g_cdef = 0, g_lr = 0, g_fuse = 0, g_me_ds = 0, g_prof = 0, g_tf = 0, g_pa = 0, g_ois = 0, g_cdef_dev = 1;
 static volatile long long g_pa_calls = 0, g_ois_calls = 0;
+/* SVT_CUDA_PROFILE: host-side pieces of the deblocking / CDEF hooks (thread-ns): mode-info flattening, skip8 map, the
+ * reference's finish_cdef_search inside the engine's callback, the engine call as a whole */
+static volatile long long g_ns_flatten = 0, g_ns_skip8 = 0, g_ns_decide = 0, g_ns_engine_cdef = 0;
+#define PROF_ADD(var, t_start) do { if (g_prof) __sync_fetch_and_add(&(var), now_ns() - (t_start)); } while (0)
 static SvtB200Engine *g_engine = NULL;
 static int            g_users  = 0;
 
@@ -92,6 +96,7 @@ void svt_cuda_backend_init(void) {
             g_lr    = env_flag("SVT_CUDA_LR", 1);
             g_fuse  = env_flag("SVT_CUDA_FUSE", 1);
             g_me_ds = env_flag("SVT_CUDA_ME_DS", 0);
+            g_cdef_dev = env_flag("SVT_CUDA_CDEF_DECIDE", 1); /* 0: finish_cdef_search on the host (engine callback) */
             /* parity switches, off by default: bit-exact, but per-block / per-picture round trips that do not pay */
             g_tf = env_flag("SVT_CUDA_TF", 0);
             g_pa = env_flag("SVT_CUDA_PA", 0);
@@ -138,6 +143,9 @@ void svt_cuda_backend_deinit(void) {
                     (unsigned long long)st.lr_frames, st.h2d_bytes / 1e6, st.d2h_bytes / 1e6, st.pinned_bytes / 1e6, (unsigned long long)svt_b200_launch_count(),
                     st.ns_slot_wait / 1e6, st.ns_issue / 1e6, st.ns_plane_wait / 1e6, st.ns_sync / 1e6, st.ns_host_copy / 1e6);
         }
+        if (g_prof)
+            fprintf(stderr, "SVT [CUDA profile]: host side of the filter hooks, thread-ms: flatten mode info %.1f, skip8 map %.1f, finish_cdef_search %.1f, CDEF engine calls %.1f\n",
+                    g_ns_flatten / 1e6, g_ns_skip8 / 1e6, g_ns_decide / 1e6, g_ns_engine_cdef / 1e6);
         if (g_prof && (g_tf || g_pa || g_ois))
             fprintf(stderr, "SVT [CUDA profile]: tf blocks on the GPU %lld, picture-analysis pictures on the GPU %lld, open-loop intra pictures on the GPU %lld\n",
                     (long long)g_tf_calls, (long long)g_pa_calls, (long long)g_ois_calls);
@@ -476,7 +484,7 @@ void svt_cuda_dlf_frame(PictureControlSet *pcs_ptr, SequenceControlSet *scs_ptr,
         }
         mi = flatten_picture_into(pcs_ptr, pend->mi);
     } else
-        mi = flatten_picture(pcs_ptr);
+        { const int64_t tf0 = g_prof ? now_ns() : 0; mi = flatten_picture(pcs_ptr); PROF_ADD(g_ns_flatten, tf0); }
     SvtB200DlfParams p;
     memset(&p, 0, sizeof(p));
     p.mi_rows         = mi_rows;
@@ -574,7 +582,9 @@ static int cdef_decide(void *user, const uint64_t *mse, SvtB200CdefApplyParams *
     memcpy(pcs->mse_seg[0], mse, sizeof(uint64_t) * (size_t)nfb * TOTAL_STRENGTHS);
     memcpy(pcs->mse_seg[1], mse + (size_t)nfb * TOTAL_STRENGTHS, sizeof(uint64_t) * (size_t)nfb * TOTAL_STRENGTHS);
     int32_t selected_strength_cnt[64] = {0};
+    const int64_t td0 = g_prof ? now_ns() : 0;
     finish_cdef_search(0, pcs, selected_strength_cnt);
+    PROF_ADD(g_ns_decide, td0);
     if (!(d->scs->seq_header.enable_restoration != 0 || ppcs->is_used_as_reference_flag || d->scs->static_config.recon_enabled))
         return 0; /* EbCdefProcess.c:527-529: the frame is not filtered when nobody reads it */
     ap->damping = fh->cdef_params.cdef_damping;
@@ -638,6 +648,7 @@ void svt_cuda_cdef_picture(PictureControlSet *pcs_ptr, SequenceControlSet *scs_p
         t_mse_cap = n_mse;
     }
     if (!t_skip || !t_mse) die("malloc", -1);
+    const int64_t ts0 = g_prof ? now_ns() : 0;
     memset(t_skip, 1, b_skip);
     ModeInfo **grid = pcs_ptr->mi_grid_base;
     const int  ms   = pcs_ptr->mi_stride;
@@ -663,6 +674,7 @@ void svt_cuda_cdef_picture(PictureControlSet *pcs_ptr, SequenceControlSet *scs_p
         }
     }
 
+    PROF_ADD(g_ns_skip8, ts0);
     /* pcs->src[] / ref_coeff[] were set by dlf_kernel's pre-cdef prep (EbDlfProcess.c:254-300): sample (0,0) of each plane */
     EbPictureBufferDesc *recon_desc;
     if (ppcs->is_used_as_reference_flag == EB_TRUE)
@@ -690,8 +702,51 @@ void svt_cuda_cdef_picture(PictureControlSet *pcs_ptr, SequenceControlSet *scs_p
 
     CdefDecide  d    = {pcs_ptr, scs_ptr, nvfb, nhfb, t_skip, skip_stride, rows8, (mi_cols + 1) / 2};
     PendingDlf *pend = pending_take(pcs_ptr, 0); /* deblocking deferred by the DLF stage: same upload, deblock, then CDEF */
-    int rc = svt_b200_engine_dlf_cdef_frame(g_engine, pend ? &pend->p : NULL, pend ? pend->mi : NULL, &sp, &recon, &source, t_skip,
-                                            skip_stride, t_mse, cdef_decide, &d);
+    const int64_t te0 = g_prof ? now_ns() : 0;
+    int           rc;
+    if (g_cdef_dev && scs_ptr->seq_header.sb_size != BLOCK_128X128) {
+        /* finish_cdef_search on the device (svt_b200_cdef_decide): the picture makes one round trip.  Inputs the reference
+         * derives on the host: the picture's lambda (EbEncCdef.c:1209) and the strength table of the pick method */
+        SvtB200CdefDecideParams dp;
+        memset(&dp, 0, sizeof(dp));
+        svt_b200_cdef_decide_table(pick_method, &dp);
+        dp.mi_rows = mi_rows;
+        dp.mi_cols = mi_cols;
+        uint32_t fast_lambda = 0, full_lambda = 0;
+        (*av1_lambda_assignment_function_table[ppcs->pred_structure])(pcs_ptr, &fast_lambda, &full_lambda,
+                                                                     (uint8_t)ppcs->enhanced_picture_ptr->bit_depth,
+                                                                     (uint16_t)(uint8_t)ppcs->frm_hdr.quantization_params.base_q_idx, EB_FALSE);
+        dp.lambda = full_lambda;
+        const int apply = scs_ptr->seq_header.enable_restoration != 0 || ppcs->is_used_as_reference_flag || scs_ptr->static_config.recon_enabled;
+        SvtB200CdefDecision dec;
+        int8_t *            fb_idx = (int8_t *)malloc((size_t)nvfb * nhfb);
+        if (!fb_idx) die("malloc", -1);
+        rc = svt_b200_engine_dlf_cdef_frame_dev(g_engine, pend ? &pend->p : NULL, pend ? pend->mi : NULL, &sp, &dp, sp.pri_damping, apply,
+                                                &recon, &source, t_skip, skip_stride, &dec, fb_idx);
+        PROF_ADD(g_ns_engine_cdef, te0);
+        if (pend) pending_release(pend);
+        if (rc) die("svt_b200_engine_dlf_cdef_frame_dev", rc);
+        /* what finish_cdef_search leaves behind (EbEncCdef.c:1276-1336) */
+        FrameHeader *fh            = &ppcs->frm_hdr;
+        fh->cdef_params.cdef_bits  = (uint8_t)dec.cdef_bits;
+        ppcs->nb_cdef_strengths    = dec.nb_cdef_strengths;
+        for (int j = 0; j < dec.nb_cdef_strengths; j++) {
+            fh->cdef_params.cdef_y_strength[j]  = dec.y_strength[j];
+            fh->cdef_params.cdef_uv_strength[j] = dec.uv_strength[j];
+        }
+        fh->cdef_params.cdef_damping = sp.pri_damping;
+        for (int fbr = 0; fbr < nvfb; fbr++)
+            for (int fbc = 0; fbc < nhfb; fbc++) {
+                const int8_t v = fb_idx[fbr * nhfb + fbc];
+                if (v >= 0) pcs_ptr->mi_grid_base[MI_SIZE_64X64 * fbr * pcs_ptr->mi_stride + MI_SIZE_64X64 * fbc]->mbmi.cdef_strength = v;
+            }
+        free(fb_idx);
+        if (g_prof) stat_add(1, ST_CDEF, t0);
+        return;
+    }
+    rc = svt_b200_engine_dlf_cdef_frame(g_engine, pend ? &pend->p : NULL, pend ? pend->mi : NULL, &sp, &recon, &source, t_skip,
+                                        skip_stride, t_mse, cdef_decide, &d);
+    PROF_ADD(g_ns_engine_cdef, te0);
     if (pend) pending_release(pend);
     if (rc) die("svt_b200_engine_dlf_cdef_frame", rc);
     if (g_prof) stat_add(1, ST_CDEF, t0);

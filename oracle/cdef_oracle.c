@@ -340,3 +340,101 @@ int orc_cdef_strength_table(int pick_method, SvtB200CdefSearchParams *p) {
     }
     return p->n_strengths;
 }
+
+/* ---- the strength decision: finish_cdef_search (EbEncCdef.c:1167-1340) ------------------------------------------------
+ * sb list = the filter blocks that are not all-skip (svt_sb_all_skip, :1243), in raster order; mse[0] luma, mse[1] chroma
+ * sums per strength index.  svt_search_one_dual_c (:1070-1114): given nb already chosen (luma, chroma) pairs, add the pair
+ * (j, k) that minimises sum over blocks of min(best so far, mse0[j] + mse1[k]); first minimum in (j outer, k inner) order.
+ * joint_strength_search_dual (:1136-1160): greedy for nb = 1..n, then 4 n refinement rounds that drop the oldest pair and
+ * re-add.  The number of signalled sets (1, 2, 4, 8) minimises RDCOST(lambda, cost_literal(sb_count * bits + n * 12), 16 * mse)
+ * with strict improvement (:1263-1283); every block then takes its best set (:1287-1298). */
+static uint64_t one_dual(int *lev0, int *lev1, int nb, const uint64_t *mse0, const uint64_t *mse1, const int *sb, int sb_count, int n) {
+    static uint64_t tot[64][64];
+    uint64_t best_tot = (uint64_t)1 << 63;
+    int b0 = 0, b1 = 0;
+    memset(tot, 0, sizeof(tot));
+    for (int i = 0; i < sb_count; i++) {
+        const uint64_t *m0 = mse0 + (size_t)sb[i] * 64, *m1 = mse1 + (size_t)sb[i] * 64;
+        uint64_t best = (uint64_t)1 << 63;
+        for (int g = 0; g < nb; g++) {
+            const uint64_t c = m0[lev0[g]] + m1[lev1[g]];
+            if (c < best) best = c;
+        }
+        for (int j = 0; j < n; j++)
+            for (int k = 0; k < n; k++) {
+                const uint64_t c = m0[j] + m1[k];
+                tot[j][k] += c < best ? c : best;
+            }
+    }
+    for (int j = 0; j < n; j++)
+        for (int k = 0; k < n; k++)
+            if (tot[j][k] < best_tot) best_tot = tot[j][k], b0 = j, b1 = k;
+    lev0[nb] = b0, lev1[nb] = b1;
+    return best_tot;
+}
+
+void orc_cdef_decide(const SvtB200CdefDecideParams *p, const uint64_t *mse, const uint8_t *skip8, int skip_stride,
+                     SvtB200CdefDecision *out, int8_t *fb_strength_idx) {
+    const int nvfb = (p->mi_rows + 15) / 16, nhfb = (p->mi_cols + 15) / 16, nfb = nvfb * nhfb;
+    const int rows8 = (p->mi_rows + 1) / 2, cols8 = (p->mi_cols + 1) / 2;
+    const uint64_t *mse0 = mse, *mse1 = mse + (size_t)nfb * 64;
+    int *sb = malloc(sizeof(int) * (size_t)nfb), sb_count = 0;
+    for (int fb = 0; fb < nfb; fb++) {
+        const int fbr = fb / nhfb, fbc = fb % nhfb;
+        int all_skip = 1;
+        for (int r = 8 * fbr; r < 8 * fbr + 8 && r < rows8; r++)
+            for (int c = 8 * fbc; c < 8 * fbc + 8 && c < cols8; c++) all_skip &= skip8[(size_t)r * skip_stride + c] != 0;
+        fb_strength_idx[fb] = -1;
+        if (!all_skip) sb[sb_count++] = fb;
+    }
+    memset(out, 0, sizeof(*out));
+    uint64_t best_cost = (uint64_t)1 << 63;
+    for (int bits = 0; bits <= 3; bits++) {
+        int lev0[8], lev1[8] = {0};
+        const int n = 1 << bits;
+        uint64_t tot = (uint64_t)1 << 63;
+        for (int i = 0; i < n; i++) tot = one_dual(lev0, lev1, i, mse0, mse1, sb, sb_count, p->n_strengths);
+        for (int i = 0; i < 4 * n; i++) {
+            for (int j = 0; j < n - 1; j++) lev0[j] = lev0[j + 1], lev1[j] = lev1[j + 1];
+            tot = one_dual(lev0, lev1, n - 1, mse0, mse1, sb, sb_count, p->n_strengths);
+        }
+        const int total_bits = sb_count * bits + n * 6 * 2;
+        const uint64_t rate = (uint64_t)((int64_t)total_bits * 512), dist = tot * 16;
+        const uint64_t cost = ((rate * p->lambda + 256) >> 9) + dist * 128;
+        if (cost < best_cost) {
+            best_cost = cost;
+            out->cdef_bits = bits;
+            for (int j = 0; j < n; j++) out->y_index[j] = lev0[j], out->uv_index[j] = lev1[j];
+        }
+    }
+    out->nb_cdef_strengths = 1 << out->cdef_bits;
+    out->sb_count = sb_count;
+    for (int i = 0; i < sb_count; i++) {
+        const uint64_t *m0 = mse0 + (size_t)sb[i] * 64, *m1 = mse1 + (size_t)sb[i] * 64;
+        uint64_t best = (uint64_t)1 << 63;
+        int bg = 0;
+        for (int g = 0; g < out->nb_cdef_strengths; g++) {
+            const uint64_t c = m0[out->y_index[g]] + m1[out->uv_index[g]];
+            if (c < best) best = c, bg = g;
+        }
+        fb_strength_idx[sb[i]] = (int8_t)bg;
+    }
+    for (int j = 0; j < out->nb_cdef_strengths; j++) {
+        out->y_strength[j] = p->filter_strength[out->y_index[j]];
+        out->uv_strength[j] = p->filter_strength[out->uv_index[j]];
+    }
+    free(sb);
+}
+
+/* nb_cdef_strengths[pick_method] and STORE_CDEF_FILTER_STRENGTH per index (get_cdef_filter_strengths, EbDefinitions.h:1696) */
+int orc_cdef_decide_table(int pick_method, SvtB200CdefDecideParams *p) {
+    SvtB200CdefSearchParams sp;
+    const int n = orc_cdef_strength_table(pick_method, &sp);
+    if (n <= 0) return n;
+    p->n_strengths = n;
+    for (int g = 0; g < n; g++) {
+        const int sec = sp.sec_strength[g] == 4 ? 3 : sp.sec_strength[g]; /* the table stores sec + (sec == 3) */
+        p->filter_strength[g] = pick_method == 0 ? g : sp.pri_strength[g] * 4 + sec;
+    }
+    return n;
+}

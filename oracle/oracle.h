@@ -53,6 +53,9 @@ ORC_API void orc_cdef_search(const SvtB200CdefSearchParams *p, const SvtB200Fram
 ORC_API void orc_cdef_apply(const SvtB200CdefApplyParams *p, const SvtB200Frame *recon, const SvtB200Frame *out,
                             const uint8_t *skip8, int32_t skip_stride, const int8_t *fb_strength_idx);
 ORC_API int orc_cdef_strength_table(int pick_method, SvtB200CdefSearchParams *p);
+ORC_API void orc_cdef_decide(const SvtB200CdefDecideParams *p, const uint64_t *mse, const uint8_t *skip8, int skip_stride,
+                             SvtB200CdefDecision *out, int8_t *fb_strength_idx);
+ORC_API int orc_cdef_decide_table(int pick_method, SvtB200CdefDecideParams *p);
 /* ---- txfm_oracle.c ---- */
 ORC_API const int32_t *orc_cospi_table(int bit);
 ORC_API const int32_t *orc_sinpi_table(int bit);

@@ -384,6 +384,44 @@ REFH_API int refh_cdef_search(int mi_rows, int mi_cols, int base_q_idx, int cdef
 }
 
 /* in place on `recon` (the reference's behaviour) */
+/* finish_cdef_search (EbEncCdef.c:1167) on a given mse table: frame header fields, per-filter-block choice, and the lambda the
+ * reference derived for the picture (the oracle takes it as an input). */
+#include "EbEncDecProcess.h"
+#include "EbModeDecisionProcess.h"
+void finish_cdef_search(EncDecContext *context_ptr, PictureControlSet *pcs_ptr, int32_t selected_strength_cnt[64]);
+REFH_API int refh_cdef_finish(int mi_rows, int mi_cols, int base_q_idx, int cdef_level, int bit_depth, const uint8_t *skip8,
+                              int skip_stride, const uint64_t *mse, int32_t *cdef_bits, int32_t *nb_strengths, int32_t *y_strength8,
+                              int32_t *uv_strength8, int8_t *fb_strength, uint64_t *lambda_out) {
+    SvtB200Frame dummy;
+    memset(&dummy, 0, sizeof(dummy));
+    dummy.bit_depth = bit_depth;
+    FiltCtx *c = filt_ctx_new(mi_rows, mi_cols, bit_depth, &dummy, &dummy, skip8, skip_stride, NULL);
+    const int nfb = ((mi_rows + 15) / 16) * ((mi_cols + 15) / 16), nhfb = (mi_cols + 15) / 16;
+    c->ppcs->frm_hdr.quantization_params.base_q_idx = (uint8_t)base_q_idx;
+    c->ppcs->cdef_level = (int8_t)cdef_level;
+    c->ppcs->pred_structure = 0;
+    uint64_t *copy = (uint64_t *)malloc(sizeof(uint64_t) * 2 * nfb * 64);
+    memcpy(copy, mse, sizeof(uint64_t) * 2 * nfb * 64);
+    c->pcs->mse_seg[0] = (uint64_t(*)[TOTAL_STRENGTHS])copy;
+    c->pcs->mse_seg[1] = (uint64_t(*)[TOTAL_STRENGTHS])(copy + (size_t)nfb * 64);
+    for (int i = 0; i < mi_rows * mi_cols; i++) c->mi[i].mbmi.cdef_strength = -1;
+    uint32_t fast_lambda = 0, full_lambda = 0;
+    (*av1_lambda_assignment_function_table[0])(c->pcs, &fast_lambda, &full_lambda, (uint8_t)c->input.bit_depth, (uint16_t)(uint8_t)base_q_idx, EB_FALSE);
+    *lambda_out = full_lambda;
+    int32_t cnt[64] = {0};
+    finish_cdef_search(0, c->pcs, cnt);
+    *cdef_bits = c->ppcs->frm_hdr.cdef_params.cdef_bits;
+    *nb_strengths = c->ppcs->nb_cdef_strengths;
+    for (int i = 0; i < 8; i++) {
+        y_strength8[i] = c->ppcs->frm_hdr.cdef_params.cdef_y_strength[i];
+        uv_strength8[i] = c->ppcs->frm_hdr.cdef_params.cdef_uv_strength[i];
+    }
+    for (int fb = 0; fb < nfb; fb++) fb_strength[fb] = c->mi[(size_t)(16 * (fb / nhfb)) * mi_cols + 16 * (fb % nhfb)].mbmi.cdef_strength;
+    free(copy);
+    filt_ctx_free(c);
+    return 0;
+}
+
 REFH_API int refh_cdef_apply(int mi_rows, int mi_cols, int damping, const int32_t *y_strength,
                              const int32_t *uv_strength, SvtB200Frame *recon, const uint8_t *skip8, int skip_stride,
                              const int8_t *fb_strength_idx) {

@@ -728,6 +728,7 @@ __global__ void __launch_bounds__(NT, CDEF_SEARCH_MINB) cdef_search_grid_kernel(
 }
 
 struct CdefApplyDev {
+    const SvtB200CdefDecision *dec; // null: strengths from p (host); else from the device decision of cdef_decide_kernel
     SvtB200CdefApplyParams p;
     FrameDev recon, out;
     const uint8_t *skip8;
@@ -757,11 +758,12 @@ __global__ void __launch_bounds__(NT) cdef_apply_kernel(const __grid_constant__ 
     const int idx = d.fb_idx[fb];
     int level = 0, sec = 0, uv_level = 0, uv_sec = 0;
     if (idx >= 0) {
-        level = p.y_strength[idx] / 4;
-        sec = p.y_strength[idx] % 4;
+        const int ys = d.dec ? d.dec->y_strength[idx] : p.y_strength[idx], uvs = d.dec ? d.dec->uv_strength[idx] : p.uv_strength[idx];
+        level = ys / 4;
+        sec = ys % 4;
         sec += sec == 3;
-        uv_level = p.uv_strength[idx] / 4;
-        uv_sec = p.uv_strength[idx] % 4;
+        uv_level = uvs / 4;
+        uv_sec = uvs % 4;
         uv_sec += uv_sec == 3;
     }
     const bool fb_on = idx >= 0 && !(level == 0 && sec == 0 && uv_level == 0 && uv_sec == 0);
@@ -926,6 +928,143 @@ __global__ void copy_rect8_kernel(uint16_t *dst, const uint8_t *src, int n) {
 }
 } // namespace
 
+// ---- the strength decision on the device: finish_cdef_search (EbEncCdef.c:1167-1340) --------------------------------
+// One CTA of 1024 threads.  svt_search_one_dual_c adds, to the nb already chosen (luma, chroma) pairs, the pair (j, k) that
+// minimises the sum over filter blocks of min(best so far, mse0[j] + mse1[k]); the n x n candidate pairs are the threads
+// (pairs x block slices when n^2 < 1024), the per-block "best so far" is one pass over the blocks, the argmin is the first
+// minimum in (j outer, k inner) order = the smallest (sum, j * n + k).  joint_strength_search_dual calls it 5 n times per
+// number of sets n = 1, 2, 4, 8.  uint64 sums only: exact whatever the order.
+struct DecideDev {
+    SvtB200CdefDecideParams p;
+    const unsigned long long *mse0, *mse1;
+    const uint8_t *skip8;
+    int skip_stride, nvfb, nhfb, rows8, cols8;
+    SvtB200CdefDecision *out;
+    int8_t *fb_idx;
+    int *sb_list;               // [nfb]
+    unsigned long long *best_sb; // [nfb]
+};
+
+__device__ __forceinline__ void lex_min(unsigned long long &v, int &i, unsigned long long ov, int oi) {
+    if (ov < v || (ov == v && oi < i)) v = ov, i = oi;
+}
+
+__global__ void __launch_bounds__(1024) cdef_decide_kernel(const DecideDev d) {
+    __shared__ int s_count, s_lev0[8], s_lev1[8], s_best_idx;
+    __shared__ unsigned long long s_part[1024], s_best_val, s_rv[32];
+    __shared__ int s_ri[32];
+    const int tid = threadIdx.x, nfb = d.nvfb * d.nhfb, n = d.p.n_strengths, P = n * n;
+    if (tid == 0) s_count = 0;
+    __syncthreads();
+    for (int fb = tid; fb < nfb; fb += 1024) {
+        const int fbr = fb / d.nhfb, fbc = fb - fbr * d.nhfb;
+        int all_skip = 1;
+        for (int r = 8 * fbr; r < min(8 * fbr + 8, d.rows8) && all_skip; r++)
+            for (int c = 8 * fbc; c < min(8 * fbc + 8, d.cols8); c++)
+                if (!d.skip8[(size_t)r * d.skip_stride + c]) {
+                    all_skip = 0;
+                    break;
+                }
+        d.fb_idx[fb] = -1;
+        if (!all_skip) d.sb_list[atomicAdd(&s_count, 1)] = fb;
+    }
+    __syncthreads();
+    const int sb_count = s_count;
+    // pairs per pass and block slices: PP pair slots (a multiple of 32), G = 1024 / PP slices of the block list
+    const int PP = min(1024, (P + 31) & ~31), G = 1024 / PP;
+    const int slot = tid % PP, slice = tid / PP;
+
+    auto search_one = [&](int nb) -> unsigned long long {
+        for (int i = tid; i < sb_count; i += 1024) {
+            const unsigned long long *m0 = d.mse0 + (size_t)d.sb_list[i] * 64, *m1 = d.mse1 + (size_t)d.sb_list[i] * 64;
+            unsigned long long best = 1ull << 63;
+            for (int g = 0; g < nb; g++) best = min(best, m0[s_lev0[g]] + m1[s_lev1[g]]);
+            d.best_sb[i] = best;
+        }
+        __syncthreads();
+        unsigned long long bv = ~0ull;
+        int bi = 0x7fffffff;
+        for (int p0 = 0; p0 < P; p0 += PP) { // one pass unless n^2 > 1024 (the 64-entry table)
+            const int pr = p0 + slot;
+            unsigned long long acc = 0;
+            if (pr < P && slice < G) {
+                const int j = pr / n, k = pr - j * n;
+                for (int i = slice; i < sb_count; i += G) {
+                    const size_t o = (size_t)d.sb_list[i] * 64;
+                    acc += min(d.best_sb[i], d.mse0[o + j] + d.mse1[o + k]);
+                }
+            }
+            s_part[tid] = acc;
+            __syncthreads();
+            if (tid < PP && p0 + tid < P) {
+                unsigned long long t = 0;
+                for (int g = 0; g < G; g++) t += s_part[g * PP + tid];
+                lex_min(bv, bi, t, p0 + tid);
+            }
+            __syncthreads();
+        }
+        for (int o = 16; o > 0; o >>= 1) lex_min(bv, bi, __shfl_xor_sync(0xffffffffu, bv, o), __shfl_xor_sync(0xffffffffu, bi, o));
+        if ((tid & 31) == 0) s_rv[tid >> 5] = bv, s_ri[tid >> 5] = bi;
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < 32; w++) lex_min(bv, bi, s_rv[w], s_ri[w]);
+            s_lev0[nb] = bi / n;
+            s_lev1[nb] = bi - (bi / n) * n;
+            s_best_val = bv;
+            s_best_idx = bi;
+        }
+        __syncthreads();
+        return s_best_val;
+    };
+
+    unsigned long long best_cost = 1ull << 63;
+    for (int bits = 0; bits <= 3; bits++) {
+        const int ns = 1 << bits;
+        unsigned long long tot = 1ull << 63;
+        for (int i = 0; i < ns; i++) tot = search_one(i);
+        for (int i = 0; i < 4 * ns; i++) {
+            if (tid == 0)
+                for (int j = 0; j < ns - 1; j++) s_lev0[j] = s_lev0[j + 1], s_lev1[j] = s_lev1[j + 1];
+            __syncthreads();
+            tot = search_one(ns - 1);
+        }
+        const long long total_bits = (long long)sb_count * bits + ns * 6 * 2; // CDEF_STRENGTH_BITS = 6
+        const unsigned long long rate = (unsigned long long)(total_bits * 512), dist = tot * 16; // av1_cost_literal
+        const unsigned long long cost = ((rate * d.p.lambda + 256) >> 9) + dist * 128;          // RDCOST
+        if (cost < best_cost) { // the same value in every thread
+            best_cost = cost;
+            if (tid == 0) {
+                d.out->cdef_bits = bits;
+                for (int j = 0; j < ns; j++) d.out->y_index[j] = s_lev0[j], d.out->uv_index[j] = s_lev1[j];
+            }
+        }
+        __syncthreads();
+    }
+    __threadfence_block();
+    __syncthreads();
+    const int nb = 1 << d.out->cdef_bits;
+    for (int i = tid; i < sb_count; i += 1024) {
+        const size_t o = (size_t)d.sb_list[i] * 64;
+        unsigned long long best = 1ull << 63;
+        int bg = 0;
+        for (int g = 0; g < nb; g++) {
+            const unsigned long long c = d.mse0[o + d.out->y_index[g]] + d.mse1[o + d.out->uv_index[g]];
+            if (c < best) best = c, bg = g;
+        }
+        d.fb_idx[d.sb_list[i]] = (int8_t)bg;
+    }
+    if (tid == 0) {
+        d.out->nb_cdef_strengths = nb;
+        d.out->sb_count = sb_count;
+        d.out->reserved = 0;
+        for (int j = 0; j < 8; j++) {
+            if (j >= nb) d.out->y_index[j] = d.out->uv_index[j] = 0;
+            d.out->y_strength[j] = j < nb ? d.p.filter_strength[d.out->y_index[j]] : 0;
+            d.out->uv_strength[j] = j < nb ? d.p.filter_strength[d.out->uv_index[j]] : 0;
+        }
+    }
+}
+
 extern "C" {
 
 int svt_b200_cdef_strength_table(int pick_method, SvtB200CdefSearchParams *p) {
@@ -1004,11 +1143,80 @@ int svt_b200_cdef_apply(const SvtB200CdefApplyParams *p, const SvtB200Frame *rec
         return SVT_B200_ERR_ARG;
     }
     d.p = *p;
+    d.dec = nullptr;
     d.skip8 = skip8;
     d.skip_stride = skip_stride;
     d.fb_idx = fb_strength_idx;
     d.nvfb = (p->mi_rows + 15) / 16;
     d.nhfb = (p->mi_cols + 15) / 16;
+    d.coeff_shift = recon->bit_depth - 8;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d.recon.hbd)
+        SVTB_LAUNCH(cdef_apply_kernel<uint16_t>, d.nvfb * d.nhfb, NT, 0, st, d);
+    else
+        SVTB_LAUNCH(cdef_apply_kernel<uint8_t>, d.nvfb * d.nhfb, NT, 0, st, d);
+    SVTB_CUDA_TRY(cudaGetLastError());
+    return SVT_B200_OK;
+}
+
+int svt_b200_cdef_decide_table(int pick_method, SvtB200CdefDecideParams *p) {
+    SvtB200CdefSearchParams sp;
+    if (!p) return SVT_B200_ERR_ARG;
+    const int n = svt_b200_cdef_strength_table(pick_method, &sp);
+    if (n <= 0) return n;
+    p->n_strengths = n;
+    for (int g = 0; g < n; g++) {
+        // STORE_CDEF_FILTER_STRENGTH (EbEncCdef.c:1165): pri * CDEF_SEC_STRENGTHS + sec; the search table stores sec + (sec == 3)
+        const int sec = sp.sec_strength[g] == 4 ? 3 : sp.sec_strength[g];
+        p->filter_strength[g] = pick_method == 0 ? g : sp.pri_strength[g] * 4 + sec;
+    }
+    return n;
+}
+
+int svt_b200_cdef_decide(const SvtB200CdefDecideParams *p, const uint64_t *mse, const uint8_t *skip8, int32_t skip_stride,
+                         SvtB200CdefDecision *out, int8_t *fb_strength_idx, void *scratch, void *stream) {
+    if (!p || !mse || !skip8 || !out || !fb_strength_idx || !scratch || p->n_strengths < 1 || p->n_strengths > 64 || p->mi_rows <= 0 ||
+        p->mi_cols <= 0) {
+        set_error("svt_b200_cdef_decide: bad argument");
+        return SVT_B200_ERR_ARG;
+    }
+    DecideDev d;
+    d.p = *p;
+    d.nvfb = (p->mi_rows + 15) / 16;
+    d.nhfb = (p->mi_cols + 15) / 16;
+    const size_t nfb = (size_t)d.nvfb * d.nhfb;
+    d.mse0 = reinterpret_cast<const unsigned long long *>(mse);
+    d.mse1 = d.mse0 + nfb * 64;
+    d.skip8 = skip8;
+    d.skip_stride = skip_stride;
+    d.rows8 = (p->mi_rows + 1) / 2;
+    d.cols8 = (p->mi_cols + 1) / 2;
+    d.out = out;
+    d.fb_idx = fb_strength_idx;
+    d.best_sb = reinterpret_cast<unsigned long long *>(scratch);
+    d.sb_list = reinterpret_cast<int *>(d.best_sb + nfb);
+    SVTB_LAUNCH(cdef_decide_kernel, 1, 1024, 0, (cudaStream_t)stream, d);
+    SVTB_CUDA_TRY(cudaGetLastError());
+    return SVT_B200_OK;
+}
+
+int svt_b200_cdef_apply_dev(int32_t mi_rows, int32_t mi_cols, int32_t damping, const SvtB200CdefDecision *decision,
+                            const SvtB200Frame *recon, const SvtB200Frame *out, const uint8_t *skip8, int32_t skip_stride,
+                            const int8_t *fb_strength_idx, void *stream) {
+    CdefApplyDev d;
+    if (!decision || !skip8 || !fb_strength_idx || frame_dev(recon, &d.recon) || frame_dev(out, &d.out) ||
+        recon->bit_depth != out->bit_depth || recon->y == out->y) {
+        set_error("svt_b200_cdef_apply_dev: bad argument (out must not alias recon)");
+        return SVT_B200_ERR_ARG;
+    }
+    memset(&d.p, 0, sizeof(d.p));
+    d.p.mi_rows = mi_rows, d.p.mi_cols = mi_cols, d.p.damping = damping;
+    d.dec = decision;
+    d.skip8 = skip8;
+    d.skip_stride = skip_stride;
+    d.fb_idx = fb_strength_idx;
+    d.nvfb = (mi_rows + 15) / 16;
+    d.nhfb = (mi_cols + 15) / 16;
     d.coeff_shift = recon->bit_depth - 8;
     cudaStream_t st = (cudaStream_t)stream;
     if (d.recon.hbd)

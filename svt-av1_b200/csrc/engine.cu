@@ -67,7 +67,8 @@ struct FiltSlot {
     uint8_t *misc = nullptr;         // mi array | skip8 | mse | fb idx
     uint8_t *pin_a = nullptr;        // packed picture (reconstruction up / down)
     uint8_t *pin_b = nullptr;        // packed picture (source); the mode-info array for deblocking
-    uint8_t *pin_small = nullptr;    // skip map | mse | fb idx
+    uint8_t *pin_small = nullptr;    // skip map | mse | fb idx | decision
+    uint8_t *pin_mi = nullptr;       // the mode-info array when the call must not reuse pin_b (single-sync path)
 };
 
 struct MeGeom {
@@ -79,7 +80,7 @@ struct MeGeom {
 struct FiltGeom {
     int w = 0, h = 0, bd = 0, mi_rows = 0, mi_cols = 0;
     int sy = 0, sc = 0; // device strides (samples)
-    size_t by = 0, bc = 0, frame = 0, packed = 0, mi = 0, skip = 0, mse = 0, nfb = 0, misc = 0, small = 0;
+    size_t by = 0, bc = 0, frame = 0, packed = 0, mi = 0, skip = 0, mse = 0, nfb = 0, misc = 0, small = 0, idx = 0, dec = 0;
     bool same(int w_, int h_, int bd_) const { return w == w_ && h == h_ && bd == bd_; }
 };
 
@@ -231,11 +232,13 @@ int ensure_filt(SvtB200Engine *e, int w, int h, int bd, int mi_rows, int mi_cols
     g.nfb = (size_t)((mi_rows + 15) / 16) * ((mi_cols + 15) / 16);
     g.skip = al256((size_t)((mi_rows + 1) / 2) * ((((mi_cols + 1) / 2) + 15) & ~15));
     g.mse = al256(g.nfb * 2 * 64 * 8);
-    g.small = g.skip + g.mse + al256(g.nfb);
+    g.idx = al256(g.nfb);
+    g.dec = al256(sizeof(SvtB200CdefDecision)) + al256(g.nfb * 16 + 64); // the device decision + cdef_decide's scratch
+    g.small = g.skip + g.mse + g.idx + g.dec;
     g.misc = g.mi + 4096 + g.small; // mode-info summary | the level search's scratch | skip map, mse, filter-block indices
     const size_t dev_total = (size_t)kFiltSlots * (3 * g.frame + g.misc);
     const size_t pin_b = std::max(g.packed, g.mi);
-    const size_t pin_total = (size_t)kFiltSlots * (g.packed + pin_b + g.small);
+    const size_t pin_total = (size_t)kFiltSlots * (g.packed + pin_b + g.small + g.mi);
     ENG_TRY(cudaMalloc((void **)&e->filt_dev, dev_total));
     ENG_TRY(cudaMallocHost((void **)&e->filt_pin, pin_total));
     e->stats.pinned_bytes += pin_total;
@@ -258,7 +261,8 @@ int ensure_filt(SvtB200Engine *e, int w, int h, int bd, int mi_rows, int mi_cols
         s.pin_a = hp;
         s.pin_b = hp + g.packed;
         s.pin_small = s.pin_b + pin_b;
-        hp += g.packed + pin_b + g.small;
+        s.pin_mi = s.pin_small + g.small;
+        hp += g.packed + pin_b + g.small + g.mi;
     }
     e->fg = g;
     e->filt_ready = true;
@@ -984,6 +988,91 @@ int svt_b200_engine_dlf_cdef_frame(SvtB200Engine *e, const SvtB200DlfParams *dlf
             break;
         }
         unpack_frame(e, recon, s->pin_a);
+    } while (0);
+    if (rc != SVT_B200_OK) cudaStreamSynchronize(s->st);
+    release(e, s);
+    return rc;
+}
+
+// The same picture pass with the strength decision on the DEVICE (svt_b200_cdef_decide replaces the host callback): one
+// upload, deblocking, CDEF search, decision, CDEF apply, one download, ONE synchronisation - the reconstruction and the
+// decision arrive together.  apply: 0 = search + decision only (EbCdefProcess.c:527-529: nobody reads the filtered picture).
+int svt_b200_engine_dlf_cdef_frame_dev(SvtB200Engine *e, const SvtB200DlfParams *dlf, const SvtB200DlfMi *mi,
+                                       const SvtB200CdefSearchParams *sp, const SvtB200CdefDecideParams *dp, int32_t damping,
+                                       int32_t apply, const SvtB200Frame *recon, const SvtB200Frame *source, const uint8_t *skip8,
+                                       int32_t skip_stride, SvtB200CdefDecision *decision, int8_t *fb_strength_idx) {
+    if (!e || !sp || !dp || !recon || !source || !skip8 || !decision || !fb_strength_idx || recon->width != source->width ||
+        recon->height != source->height || recon->bit_depth != source->bit_depth || (dlf && (!mi || dlf->mi_stride != dlf->mi_cols)) ||
+        dp->mi_rows != sp->mi_rows || dp->mi_cols != sp->mi_cols || dp->n_strengths != sp->n_strengths) {
+        set_error("svt_b200_engine_dlf_cdef_frame_dev: bad argument");
+        return SVT_B200_ERR_ARG;
+    }
+    DeviceGuard dg(e->device);
+    int rc = ensure_filt(e, recon->width, recon->height, recon->bit_depth, sp->mi_rows, sp->mi_cols);
+    if (rc != SVT_B200_OK) return rc;
+    const FiltGeom &g = e->fg;
+    const int nvfb = (sp->mi_rows + 15) / 16, nhfb = (sp->mi_cols + 15) / 16, nfb = nvfb * nhfb;
+    const size_t b_skip = (size_t)((sp->mi_rows + 1) / 2) * skip_stride;
+    const size_t b_mi = dlf ? (size_t)dlf->mi_rows * dlf->mi_cols * sizeof(SvtB200DlfMi) : 0;
+    if (al256(b_skip) > g.skip || (size_t)nfb > g.nfb || b_mi > g.mi) {
+        set_error("svt_b200_engine_dlf_cdef_frame_dev: picture larger than the sequence geometry");
+        return SVT_B200_ERR_ARG;
+    }
+    FiltSlot *s = acquire(e, e->filt);
+    do {
+        uint8_t *d_small = s->misc + g.mi + 4096;
+        uint8_t *d_skip = d_small, *d_mse = d_small + g.skip, *d_idx = d_mse + g.mse, *d_dec = d_idx + g.idx;
+        uint8_t *d_scr = d_dec + al256(sizeof(SvtB200CdefDecision));
+        uint8_t *h_skip = s->pin_small, *h_idx = h_skip + g.skip + g.mse;
+        pack_frame(e, s->pin_a, recon);
+        pack_frame(e, s->pin_b, source);
+        {
+            Lap lap(e->stats.ns_host_copy);
+            if (dlf) par_memcpy(s->pin_mi, mi, b_mi);
+            memcpy(h_skip, skip8, b_skip);
+        }
+        {
+            Lap lap(e->stats.ns_issue);
+            if (dlf && cudaMemcpyAsync(s->misc, s->pin_mi, b_mi, cudaMemcpyHostToDevice, s->st) != cudaSuccess) {
+                rc = SVT_B200_ERR_CUDA;
+                break;
+            }
+            if ((rc = copy_packed(e, &s->recon, s->pin_a, cudaMemcpyHostToDevice, s->st)) != SVT_B200_OK) break;
+            if (dlf && (rc = svt_b200_dlf_frame(dlf, &s->recon, (const SvtB200DlfMi *)s->misc, s->st)) != SVT_B200_OK) break;
+            if (cudaMemcpyAsync(d_skip, h_skip, b_skip, cudaMemcpyHostToDevice, s->st) != cudaSuccess) {
+                rc = SVT_B200_ERR_CUDA;
+                break;
+            }
+            if ((rc = copy_packed(e, &s->source, s->pin_b, cudaMemcpyHostToDevice, s->st)) != SVT_B200_OK) break;
+            if ((rc = svt_b200_cdef_search(sp, &s->recon, &s->source, d_skip, skip_stride, (uint64_t *)d_mse, s->st)) != SVT_B200_OK)
+                break;
+            if ((rc = svt_b200_cdef_decide(dp, (const uint64_t *)d_mse, d_skip, skip_stride, (SvtB200CdefDecision *)d_dec, (int8_t *)d_idx,
+                                           d_scr, s->st)) != SVT_B200_OK)
+                break;
+            if (apply) {
+                if ((rc = svt_b200_cdef_apply_dev(sp->mi_rows, sp->mi_cols, damping, (const SvtB200CdefDecision *)d_dec, &s->recon, &s->out,
+                                                  d_skip, skip_stride, (const int8_t *)d_idx, s->st)) != SVT_B200_OK)
+                    break;
+                if ((rc = copy_packed(e, &s->out, s->pin_a, cudaMemcpyDeviceToHost, s->st)) != SVT_B200_OK) break;
+            }
+            // filter-block indices and the decision are adjacent on both sides: one copy
+            if (cudaMemcpyAsync(h_idx, d_idx, g.idx + sizeof(SvtB200CdefDecision), cudaMemcpyDeviceToHost, s->st) != cudaSuccess) {
+                rc = SVT_B200_ERR_CUDA;
+                break;
+            }
+        }
+        if (timed_sync(e, s->st) != cudaSuccess) {
+            set_error("engine: deblocking + CDEF failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = SVT_B200_ERR_CUDA;
+            break;
+        }
+        memcpy(fb_strength_idx, h_idx, (size_t)nfb);
+        memcpy(decision, h_idx + g.idx, sizeof(SvtB200CdefDecision));
+        if (apply) unpack_frame(e, recon, s->pin_a);
+        if (dlf) e->stats.dlf_frames++;
+        e->stats.cdef_frames++;
+        e->stats.h2d_bytes += b_skip + b_mi;
+        e->stats.d2h_bytes += g.idx + sizeof(SvtB200CdefDecision);
     } while (0);
     if (rc != SVT_B200_OK) cudaStreamSynchronize(s->st);
     release(e, s);

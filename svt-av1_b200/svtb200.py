@@ -94,6 +94,16 @@ class EncodeParams(C.Structure):
     _fields_ = [("tx_size", C.c_int32), ("use_fp", C.c_int32), ("q", QuantPlane * 3)]
 
 
+class CdefDecideParams(C.Structure):
+    _fields_ = [("mi_rows", C.c_int32), ("mi_cols", C.c_int32), ("n_strengths", C.c_int32), ("reserved", C.c_int32), ("lambda_", C.c_uint64),
+                ("filter_strength", C.c_int32 * 64)]
+
+
+class CdefDecision(C.Structure):
+    _fields_ = [("cdef_bits", C.c_int32), ("nb_cdef_strengths", C.c_int32), ("y_strength", C.c_int32 * 8), ("uv_strength", C.c_int32 * 8),
+                ("y_index", C.c_int32 * 8), ("uv_index", C.c_int32 * 8), ("sb_count", C.c_int32), ("reserved", C.c_int32)]
+
+
 class TfBlock(C.Structure):
     _fields_ = [("x", C.c_int32), ("y", C.c_int32), ("block_error", C.c_double * 4), ("d_factor", C.c_double * 4)]
 
@@ -294,6 +304,10 @@ def load():
     lib.svt_b200_encode_tus.argtypes = [C.POINTER(EncodeParams), C.POINTER(Frame), C.POINTER(Frame), C.POINTER(Frame),
                                         C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.svt_b200_picture_mean_variance.argtypes = [C.POINTER(Frame), C.c_int32] + [C.c_void_p] * 7
+    lib.svt_b200_cdef_decide_table.argtypes = [C.c_int, C.POINTER(CdefDecideParams)]
+    lib.svt_b200_engine_dlf_cdef_frame_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(CdefSearchParams), C.POINTER(CdefDecideParams),
+                                                       C.c_int32, C.c_int32, C.POINTER(Frame), C.POINTER(Frame), C.c_void_p, C.c_int32,
+                                                       C.POINTER(CdefDecision), C.c_void_p]
     lib.svt_b200_ois_dc_picture.argtypes = [C.POINTER(Frame), C.c_void_p, C.c_void_p]
     lib.svt_b200_ois_dc_picture_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
     lib.svt_b200_tf_planewise.argtypes = [C.POINTER(TfParams), C.POINTER(Frame), C.POINTER(Frame), C.c_void_p, C.c_int32,

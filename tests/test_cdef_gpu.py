@@ -108,3 +108,36 @@ def test_cdef_apply_vs_oracle(case):
     same = gr.run_gpu_cdef_apply(p0, rec, skip, np.zeros(nfb, np.int8))
     for i in range(3):
         np.testing.assert_array_equal(same.plane(i), rec.plane(i))
+
+
+@pytest.mark.parametrize("case", [(0, 3, 68, 120, "smooth"), (1, 3, 68, 120, "rand"), (2, 2, 45, 80, "smooth"), (3, 1, 45, 80, "ties"),
+                                  (4, 0, 34, 46, "smooth"), (5, 3, 16, 16, "rand"), (6, 3, 90, 160, "ties"), (7, 3, 270, 480, "smooth"),
+                                  (8, 2, 540, 960, "rand")])
+def test_cdef_decide_vs_oracle(case):
+    """svt_b200_cdef_decide (finish_cdef_search on the device) on synthetic mse tables: all four strength tables (10 / 20 /
+    32 / 64 entries: 100 to 4096 candidate pairs per search step), ties, skipped filter blocks, up to 2160p geometry."""
+    import ctypes as C
+    import torch
+    from test_oracle_cdef_decide import decide_case
+    seed, pick, mi_rows, mi_cols, kind = case
+    lib, orc = sb.load(), cm.oracle()
+    p = sb.CdefDecideParams()
+    n = lib.svt_b200_cdef_decide_table(pick, C.byref(p))
+    p.mi_rows, p.mi_cols, p.lambda_ = mi_rows, mi_cols, 1000 + 977 * seed
+    skip, stride, mse = decide_case(seed, mi_rows, mi_cols, n, kind)
+    nfb = mse.shape[1]
+    want, want_idx = sb.CdefDecision(), np.zeros(nfb, np.int8)
+    orc.orc_cdef_decide(C.byref(p), cm.ptr(mse), cm.ptr(skip), stride, C.byref(want), cm.ptr(want_idx))
+    dm, dsk = torch.from_numpy(mse.view(np.int64)).cuda(), torch.from_numpy(skip).cuda()
+    dout = torch.zeros(C.sizeof(sb.CdefDecision), dtype=torch.uint8, device="cuda")
+    didx = torch.full((nfb,), 77, dtype=torch.int8, device="cuda")
+    scr = torch.zeros(nfb * 16 + 64, dtype=torch.uint8, device="cuda")
+    lib.svt_b200_cdef_decide.argtypes = [C.POINTER(sb.CdefDecideParams)] + [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    sb.check(lib.svt_b200_cdef_decide(C.byref(p), dm.data_ptr(), dsk.data_ptr(), stride, dout.data_ptr(), didx.data_ptr(), scr.data_ptr(), None), lib)
+    torch.cuda.synchronize()
+    got = sb.CdefDecision.from_buffer_copy(dout.cpu().numpy().tobytes())
+    assert (got.cdef_bits, got.nb_cdef_strengths, got.sb_count) == (want.cdef_bits, want.nb_cdef_strengths, want.sb_count)
+    k = want.nb_cdef_strengths
+    assert list(got.y_index)[:k] == list(want.y_index)[:k] and list(got.uv_index)[:k] == list(want.uv_index)[:k]
+    assert list(got.y_strength)[:k] == list(want.y_strength)[:k] and list(got.uv_strength)[:k] == list(want.uv_strength)[:k]
+    np.testing.assert_array_equal(didx.cpu().numpy(), want_idx)

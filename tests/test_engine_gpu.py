@@ -191,6 +191,75 @@ def test_engine_cdef_frame_with_host_decision(bd, with_dlf):
         lib.svt_b200_engine_destroy(e)
 
 
+
+@pytest.mark.parametrize("bd,with_dlf,pick", [(8, False, 3), (10, True, 2), (8, True, 3)])
+def test_engine_cdef_frame_with_device_decision(bd, with_dlf, pick):
+    """deblocking -> search -> svt_b200_cdef_decide (finish_cdef_search on the device) -> apply in ONE engine call: the
+    decision, the per-filter-block choice and the filtered picture against the oracle chain."""
+    from test_dlf_gpu import flat_mi
+    from test_oracle_cdef import cdef_picture_case
+    from test_oracle_dlf import dlf_params
+    lib, orc = sb.load(), cm.oracle()
+    e = C.c_void_p()
+    sb.check(lib.svt_b200_engine_create(0, C.byref(e)), lib)
+    try:
+        w, h = 320, 200
+        src, rec, mi_rows, mi_cols, skip = cdef_picture_case(w, h, bd)
+        skip[0:8, 0:8] = 1  # one filter block entirely skipped
+        levels = (20, 24, 12, 9)
+        pre = rec.copy()
+        dp, flat = None, None
+        if with_dlf:
+            part = cm.random_partition(mi_rows, mi_cols, 5)
+            flat = flat_mi(mi_rows, mi_cols, part, levels)
+            dp = dlf_params(mi_rows, mi_cols, levels, 1)
+            ps = pre.struct()
+            orc.orc_dlf_frame(C.byref(dp), C.byref(ps), flat)
+        sp = sb.CdefSearchParams()
+        sp.mi_rows, sp.mi_cols, sp.pri_damping = mi_rows, mi_cols, 5
+        orc.orc_cdef_strength_table(pick, C.byref(sp))
+        dcp = sb.CdefDecideParams()
+        assert lib.svt_b200_cdef_decide_table(pick, C.byref(dcp)) == sp.n_strengths
+        ref_tab = sb.CdefDecideParams()
+        orc.orc_cdef_decide_table(pick, C.byref(ref_tab))
+        assert list(dcp.filter_strength) == list(ref_tab.filter_strength)
+        dcp.mi_rows, dcp.mi_cols, dcp.lambda_ = mi_rows, mi_cols, 3500
+        nfb = ((mi_rows + 15) // 16) * ((mi_cols + 15) // 16)
+        want_mse = np.zeros((2, nfb, 64), np.uint64)
+        pres, ss = pre.struct(), src.struct()
+        orc.orc_cdef_search(C.byref(sp), C.byref(pres), C.byref(ss), cm.ptr(skip), skip.shape[1], cm.ptr(want_mse))
+        want_dec, want_idx = sb.CdefDecision(), np.zeros(nfb, np.int8)
+        orc.orc_cdef_decide(C.byref(dcp), cm.ptr(want_mse), cm.ptr(skip), skip.shape[1], C.byref(want_dec), cm.ptr(want_idx))
+        pa = sb.CdefApplyParams()
+        pa.mi_rows, pa.mi_cols, pa.damping = mi_rows, mi_cols, 5
+        for i in range(8):
+            pa.y_strength[i], pa.uv_strength[i] = want_dec.y_strength[i], want_dec.uv_strength[i]
+        want = pre.copy()
+        ws = want.struct()
+        orc.orc_cdef_apply(C.byref(pa), C.byref(pres), C.byref(ws), cm.ptr(skip), skip.shape[1], cm.ptr(want_idx))
+        got, gs_dec, g_idx = rec.copy(), sb.CdefDecision(), np.full(nfb, 99, np.int8)
+        gs = got.struct()
+        sb.check(lib.svt_b200_engine_dlf_cdef_frame_dev(e, C.byref(dp) if dp else None, flat, C.byref(sp), C.byref(dcp), 5, 1, C.byref(gs), C.byref(ss),
+                                                        cm.ptr(skip), skip.shape[1], C.byref(gs_dec), cm.ptr(g_idx)), lib)
+        assert (gs_dec.cdef_bits, gs_dec.nb_cdef_strengths, gs_dec.sb_count) == (want_dec.cdef_bits, want_dec.nb_cdef_strengths, want_dec.sb_count)
+        n = want_dec.nb_cdef_strengths
+        assert list(gs_dec.y_strength)[:n] == list(want_dec.y_strength)[:n] and list(gs_dec.uv_strength)[:n] == list(want_dec.uv_strength)[:n]
+        np.testing.assert_array_equal(g_idx, want_idx)
+        assert want_idx[0] == -1 and (want_idx >= 0).any()
+        for i in range(3):
+            np.testing.assert_array_equal(got.plane(i), want.plane(i), err_msg=f"plane {i}")
+        # apply = 0: decision only, the host picture untouched
+        again, d2, i2 = rec.copy(), sb.CdefDecision(), np.zeros(nfb, np.int8)
+        ags = again.struct()
+        sb.check(lib.svt_b200_engine_dlf_cdef_frame_dev(e, C.byref(dp) if dp else None, flat, C.byref(sp), C.byref(dcp), 5, 0, C.byref(ags), C.byref(ss),
+                                                        cm.ptr(skip), skip.shape[1], C.byref(d2), cm.ptr(i2)), lib)
+        np.testing.assert_array_equal(i2, want_idx)
+        for i in range(3):
+            np.testing.assert_array_equal(again.plane(i), rec.plane(i))
+    finally:
+        lib.svt_b200_engine_destroy(e)
+
+
 @pytest.mark.parametrize("case", [(192, 136, 8, 1, 0, 3, (20, 24, 12, 9)), (128, 128, 10, 3, 0, 3, (40, 40, 33, 20))])
 def test_engine_dlf_pick_frame(case):
     """Level search + deblocking as one call: the levels equal the oracle's svt_av1_pick_filter_level, the picture equals the
