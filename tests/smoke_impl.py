@@ -36,4 +36,20 @@ def run():
     test_interp_gpu.test_inter_predict_vs_oracle(176, 144, 8, 64, 21, "texture")
     test_me_gpu.test_me_downsample_vs_oracle(176, 144, 1)
     done += ["subpel", "inter_predict", "me_downsample"]
+    # round 2: the tensor-core Wiener statistics, the temporal filter, picture statistics, open-loop intra search and the CDEF
+    # strength decision - the -m gpu tests themselves, one small case each
+    import test_misc_gpu
+    import test_ois_gpu
+    import test_pa_gpu
+    import test_tf_gpu
+    test_misc_gpu.test_compute_stats_extreme_values(8)
+    done.append("wiener_stats(imma)")
+    import tf_cases
+    test_tf_gpu.test_planewise_block_dropin_vs_oracle(tf_cases.CASES[0])
+    done.append("temporal_filter")
+    test_pa_gpu.test_picture_mean_variance_vs_oracle((200, 120, 0))
+    test_ois_gpu.test_ois_dc_picture_vs_oracle((200, 120))
+    done.append("picture_stats, open_loop_intra")
+    test_cdef_gpu.test_cdef_decide_vs_oracle((0, 3, 68, 120, "smooth"))
+    done.append("cdef_decide")
     print("smoke OK: %s bit-exact vs oracle, launches=%d" % (", ".join(done), lib.svt_b200_launch_count()))
