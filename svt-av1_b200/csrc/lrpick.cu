@@ -166,8 +166,8 @@ __device__ __forceinline__ void mma_s8(int (&c)[4], uint32_t a0, uint32_t a1, ui
                  : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <typename T, int WIN>
-__global__ void __launch_bounds__(TC_NT) stats_mma_kernel(const StatsDev d, int tiles_x_max) {
+template <typename T, int WIN, int MINB>
+__global__ void __launch_bounds__(TC_NT, MINB) stats_mma_kernel(const StatsDev d, int tiles_x_max) {
     constexpr int HW = WIN / 2, WIN2 = WIN * WIN, NROW = WIN2 + 1, NJ = (NROW + 7) / 8, MT = (NJ + 1) / 2;
     constexpr int RH = TC_TH + 2 * HW, YB = RH * TC_PITCH, XB = TC_TH * TC_XPITCH, SW = TC_XPITCH / 4; // SW: staged words per row
     constexpr int NTILE = MT * NJ - MT * (MT - 1); // sum over mt of (NJ - 2 mt): column tiles nt >= 2 mt
@@ -322,21 +322,31 @@ int stats_launch(StatsDev &d, int win, int hbd, int max_uw, int max_uh, cudaStre
     static const bool imad = getenv("SVT_B200_STATS_IMAD") != nullptr;
     const dim3 gs(std::min(64, (max_uw * max_uh + 255) / 256), d.n_units);
     if (!imad) {
+        // SVT_B200_STATS_MINB=2: the register-capped build of the same kernel (80 registers, 2 CTAs / SM, some spills)
+        static const bool two = getenv("SVT_B200_STATS_MINB") && atoi(getenv("SVT_B200_STATS_MINB")) == 2;
         const int tiles_x = (max_uw + TC_TW - 1) / TC_TW, tiles_y = (max_uh + TC_TH - 1) / TC_TH;
         const dim3 gt(tiles_x * tiles_y, d.n_units);
+#define SVTB_STATS_MMA(T, W)                                                                  \
+    do {                                                                                      \
+        if (two)                                                                              \
+            SVTB_LAUNCH((stats_mma_kernel<T, W, 2>), gt, TC_NT, 0, st, d, tiles_x);           \
+        else                                                                                  \
+            SVTB_LAUNCH((stats_mma_kernel<T, W, 1>), gt, TC_NT, 0, st, d, tiles_x);           \
+    } while (0)
         if (hbd) {
             SVTB_LAUNCH(stats_sum_kernel<uint16_t>, gs, 256, 0, st, d);
             if (win == 7)
-                SVTB_LAUNCH((stats_mma_kernel<uint16_t, 7>), gt, TC_NT, 0, st, d, tiles_x);
+                SVTB_STATS_MMA(uint16_t, 7);
             else
-                SVTB_LAUNCH((stats_mma_kernel<uint16_t, 5>), gt, TC_NT, 0, st, d, tiles_x);
+                SVTB_STATS_MMA(uint16_t, 5);
         } else {
             SVTB_LAUNCH(stats_sum_kernel<uint8_t>, gs, 256, 0, st, d);
             if (win == 7)
-                SVTB_LAUNCH((stats_mma_kernel<uint8_t, 7>), gt, TC_NT, 0, st, d, tiles_x);
+                SVTB_STATS_MMA(uint8_t, 7);
             else
-                SVTB_LAUNCH((stats_mma_kernel<uint8_t, 5>), gt, TC_NT, 0, st, d, tiles_x);
+                SVTB_STATS_MMA(uint8_t, 5);
         }
+#undef SVTB_STATS_MMA
         SVTB_LAUNCH(stats_finish_kernel, d.n_units, 256, 0, st, d.out, d.n_units, win2, d.divider);
         return cudaGetLastError() == cudaSuccess ? 0 : -1;
     }
