@@ -1025,7 +1025,6 @@ int svt_b200_engine_dlf_cdef_frame_dev(SvtB200Engine *e, const SvtB200DlfParams 
         uint8_t *d_scr = d_dec + al256(sizeof(SvtB200CdefDecision));
         uint8_t *h_skip = s->pin_small, *h_idx = h_skip + g.skip + g.mse;
         pack_frame(e, s->pin_a, recon);
-        pack_frame(e, s->pin_b, source);
         {
             Lap lap(e->stats.ns_host_copy);
             if (dlf) par_memcpy(s->pin_mi, mi, b_mi);
@@ -1039,6 +1038,10 @@ int svt_b200_engine_dlf_cdef_frame_dev(SvtB200Engine *e, const SvtB200DlfParams 
             }
             if ((rc = copy_packed(e, &s->recon, s->pin_a, cudaMemcpyHostToDevice, s->st)) != SVT_B200_OK) break;
             if (dlf && (rc = svt_b200_dlf_frame(dlf, &s->recon, (const SvtB200DlfMi *)s->misc, s->st)) != SVT_B200_OK) break;
+        }
+        pack_frame(e, s->pin_b, source); // the host packs the source while the device receives and deblocks the reconstruction
+        {
+            Lap lap(e->stats.ns_issue);
             if (cudaMemcpyAsync(d_skip, h_skip, b_skip, cudaMemcpyHostToDevice, s->st) != cudaSuccess) {
                 rc = SVT_B200_ERR_CUDA;
                 break;
