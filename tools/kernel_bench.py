@@ -133,6 +133,18 @@ def geometry(w, h, bd):
     ms = ring_ms(lambda i: sb.check(lib.svt_b200_cdef_apply(C.byref(pa), C.byref(rss[i]), C.byref(oss[i]), C.c_void_p(dskip.data_ptr()),
                                                             skip.shape[1], C.c_void_p(didx.data_ptr()), SP), lib), ring)
     out["rows"].append(row("svt_b200_cdef_apply (8 strength pairs cycled over the filter blocks)", ms, 2 * pic_bytes, copy_ms))
+    # the strength decision between the two (finish_cdef_search on the device): a single CTA, latency not bandwidth
+    dcp = sb.CdefDecideParams()
+    lib.svt_b200_cdef_decide_table(3, C.byref(dcp))
+    dcp.mi_rows, dcp.mi_cols, dcp.lambda_ = mi_rows, mi_cols, 3500
+    ddec = torch.zeros(C.sizeof(sb.CdefDecision), dtype=torch.uint8, device="cuda")
+    didx2 = torch.zeros(nfb, dtype=torch.int8, device="cuda")
+    dscr = torch.zeros(nfb * 16 + 64, dtype=torch.uint8, device="cuda")
+    lib.svt_b200_cdef_decide.argtypes = [C.POINTER(sb.CdefDecideParams)] + [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    ms = ring_ms(lambda i: sb.check(lib.svt_b200_cdef_decide(C.byref(dcp), dmse.data_ptr(), dskip.data_ptr(), skip.shape[1], ddec.data_ptr(),
+                                                             didx2.data_ptr(), dscr.data_ptr(), SP), lib), 8)
+    out["rows"].append(row("svt_b200_cdef_decide (finish_cdef_search: 75 search steps over %d filter blocks x 100 strength pairs)" % nfb, ms,
+                           nfb * 2 * 10 * 8, copy_ms, "one CTA: a latency chain of 75 dependent reductions, not a bandwidth kernel"))
     del drs, dss, dos
 
     # ---- pre-analysis entries (round 2): temporal filter, picture statistics, open-loop intra search ----------------
