@@ -85,6 +85,7 @@ def main():
     ap.add_argument("--no-recon", action="store_true")
     ap.add_argument("--profile", action="store_true")
     ap.add_argument("--workdir", default=None)
+    ap.add_argument("--env", action="append", default=[], help="KEY=VALUE passed to the encoders (e.g. SVT_CUDA_CDEF_DECIDE=0)")
     a = ap.parse_args()
     wd = a.workdir or tempfile.mkdtemp(prefix="svtenc_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     os.makedirs(wd, exist_ok=True)
@@ -94,7 +95,7 @@ def main():
     first = None
     for v in a.variants.split(","):
         r = run_variant(v, clip, a.width, a.height, a.frames, a.preset, a.qp, a.bits, wd, recon=not a.no_recon,
-                        extra_env={"SVT_CUDA_PROFILE": "1"} if a.profile else None)
+                        extra_env=dict([kv.split("=", 1) for kv in a.env], **({"SVT_CUDA_PROFILE": "1"} if a.profile else {})))
         if first is None:
             first = r
         r["same_as_first"] = (r["ivf_md5"] == first["ivf_md5"] and r["rec_md5"] == first["rec_md5"]) if r["ivf_md5"] else False
