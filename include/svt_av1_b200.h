@@ -307,7 +307,7 @@ SVT_B200_API int svt_b200_cdef_apply(const SvtB200CdefApplyParams *p, const SvtB
  * get_cdef_filter_strengths, the identity for the full 64-entry table) - svt_b200_cdef_decide_table() fills it.
  * mse / skip8: DEVICE, as svt_b200_cdef_search wrote / read them.  out: DEVICE SvtB200CdefDecision; fb_strength_idx: DEVICE
  * int8 [nvfb*nhfb] (mbmi.cdef_strength of each filter block, -1 for the all-skip ones): the input of
- * svt_b200_cdef_apply_dev.  scratch: DEVICE, >= 16 bytes per filter block + 64. */
+ * svt_b200_cdef_apply_dev.  scratch: DEVICE, >= (16 + 16 * n_strengths) bytes per filter block + 64. */
 typedef struct SvtB200CdefDecideParams {
     int32_t mi_rows, mi_cols;
     int32_t n_strengths; /* nb_cdef_strengths[pick_method] (start_gi = 0) */

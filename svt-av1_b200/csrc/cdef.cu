@@ -943,6 +943,7 @@ struct DecideDev {
     int8_t *fb_idx;
     int *sb_list;               // [nfb]
     unsigned long long *best_sb; // [nfb]
+    unsigned long long *c0, *c1; // [sb_count][n]: the searched strengths of the participating blocks, dense (L1-resident at 1080p)
 };
 
 __device__ __forceinline__ void lex_min(unsigned long long &v, int &i, unsigned long long ov, int oi) {
@@ -970,13 +971,21 @@ __global__ void __launch_bounds__(1024) cdef_decide_kernel(const DecideDev d) {
     }
     __syncthreads();
     const int sb_count = s_count;
+    // the 64-entry rows of the search output hold n <= 64 used entries: copy them densely once (the 75 search steps below
+    // re-read the table; 82 KB instead of 522 KB at 1080p with the 10-strength table)
+    for (int idx = tid; idx < sb_count * n; idx += 1024) {
+        const int i = idx / n, st = idx - i * n;
+        d.c0[idx] = d.mse0[(size_t)d.sb_list[i] * 64 + st];
+        d.c1[idx] = d.mse1[(size_t)d.sb_list[i] * 64 + st];
+    }
+    __syncthreads();
     // pairs per pass and block slices: PP pair slots (a multiple of 32), G = 1024 / PP slices of the block list
     const int PP = min(1024, (P + 31) & ~31), G = 1024 / PP;
     const int slot = tid % PP, slice = tid / PP;
 
     auto search_one = [&](int nb) -> unsigned long long {
         for (int i = tid; i < sb_count; i += 1024) {
-            const unsigned long long *m0 = d.mse0 + (size_t)d.sb_list[i] * 64, *m1 = d.mse1 + (size_t)d.sb_list[i] * 64;
+            const unsigned long long *m0 = d.c0 + (size_t)i * n, *m1 = d.c1 + (size_t)i * n;
             unsigned long long best = 1ull << 63;
             for (int g = 0; g < nb; g++) best = min(best, m0[s_lev0[g]] + m1[s_lev1[g]]);
             d.best_sb[i] = best;
@@ -989,10 +998,18 @@ __global__ void __launch_bounds__(1024) cdef_decide_kernel(const DecideDev d) {
             unsigned long long acc = 0;
             if (pr < P && slice < G) {
                 const int j = pr / n, k = pr - j * n;
-                for (int i = slice; i < sb_count; i += G) {
-                    const size_t o = (size_t)d.sb_list[i] * 64;
-                    acc += min(d.best_sb[i], d.mse0[o + j] + d.mse1[o + k]);
+                const unsigned long long *q0 = d.c0 + j, *q1 = d.c1 + k;
+                int i = slice;
+                unsigned long long a0 = 0, a1 = 0, a2 = 0, a3 = 0; // four independent chains: the loop is latency bound
+                for (; i + 3 * G < sb_count; i += 4 * G) {
+                    const size_t o0 = (size_t)i * n, o1 = (size_t)(i + G) * n, o2 = (size_t)(i + 2 * G) * n, o3 = (size_t)(i + 3 * G) * n;
+                    a0 += min(d.best_sb[i], q0[o0] + q1[o0]);
+                    a1 += min(d.best_sb[i + G], q0[o1] + q1[o1]);
+                    a2 += min(d.best_sb[i + 2 * G], q0[o2] + q1[o2]);
+                    a3 += min(d.best_sb[i + 3 * G], q0[o3] + q1[o3]);
                 }
+                for (; i < sb_count; i += G) a0 += min(d.best_sb[i], q0[(size_t)i * n] + q1[(size_t)i * n]);
+                acc = a0 + a1 + a2 + a3;
             }
             s_part[tid] = acc;
             __syncthreads();
@@ -1044,11 +1061,11 @@ __global__ void __launch_bounds__(1024) cdef_decide_kernel(const DecideDev d) {
     __syncthreads();
     const int nb = 1 << d.out->cdef_bits;
     for (int i = tid; i < sb_count; i += 1024) {
-        const size_t o = (size_t)d.sb_list[i] * 64;
+        const size_t o = (size_t)i * n;
         unsigned long long best = 1ull << 63;
         int bg = 0;
         for (int g = 0; g < nb; g++) {
-            const unsigned long long c = d.mse0[o + d.out->y_index[g]] + d.mse1[o + d.out->uv_index[g]];
+            const unsigned long long c = d.c0[o + d.out->y_index[g]] + d.c1[o + d.out->uv_index[g]];
             if (c < best) best = c, bg = g;
         }
         d.fb_idx[d.sb_list[i]] = (int8_t)bg;
@@ -1194,7 +1211,9 @@ int svt_b200_cdef_decide(const SvtB200CdefDecideParams *p, const uint64_t *mse, 
     d.out = out;
     d.fb_idx = fb_strength_idx;
     d.best_sb = reinterpret_cast<unsigned long long *>(scratch);
-    d.sb_list = reinterpret_cast<int *>(d.best_sb + nfb);
+    d.c0 = d.best_sb + nfb;
+    d.c1 = d.c0 + nfb * p->n_strengths;
+    d.sb_list = reinterpret_cast<int *>(d.c1 + nfb * p->n_strengths);
     SVTB_LAUNCH(cdef_decide_kernel, 1, 1024, 0, (cudaStream_t)stream, d);
     SVTB_CUDA_TRY(cudaGetLastError());
     return SVT_B200_OK;

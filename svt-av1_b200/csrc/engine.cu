@@ -233,7 +233,7 @@ int ensure_filt(SvtB200Engine *e, int w, int h, int bd, int mi_rows, int mi_cols
     g.skip = al256((size_t)((mi_rows + 1) / 2) * ((((mi_cols + 1) / 2) + 15) & ~15));
     g.mse = al256(g.nfb * 2 * 64 * 8);
     g.idx = al256(g.nfb);
-    g.dec = al256(sizeof(SvtB200CdefDecision)) + al256(g.nfb * 16 + 64); // the device decision + cdef_decide's scratch
+    g.dec = al256(sizeof(SvtB200CdefDecision)) + al256(g.nfb * (16 + 16 * 64) + 64); // the device decision + cdef_decide's scratch (any table size)
     g.small = g.skip + g.mse + g.idx + g.dec;
     g.misc = g.mi + 4096 + g.small; // mode-info summary | the level search's scratch | skip map, mse, filter-block indices
     const size_t dev_total = (size_t)kFiltSlots * (3 * g.frame + g.misc);

@@ -131,7 +131,7 @@ def test_cdef_decide_vs_oracle(case):
     dm, dsk = torch.from_numpy(mse.view(np.int64)).cuda(), torch.from_numpy(skip).cuda()
     dout = torch.zeros(C.sizeof(sb.CdefDecision), dtype=torch.uint8, device="cuda")
     didx = torch.full((nfb,), 77, dtype=torch.int8, device="cuda")
-    scr = torch.zeros(nfb * 16 + 64, dtype=torch.uint8, device="cuda")
+    scr = torch.zeros(nfb * (16 + 16 * 64) + 64, dtype=torch.uint8, device="cuda")
     lib.svt_b200_cdef_decide.argtypes = [C.POINTER(sb.CdefDecideParams)] + [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     sb.check(lib.svt_b200_cdef_decide(C.byref(p), dm.data_ptr(), dsk.data_ptr(), stride, dout.data_ptr(), didx.data_ptr(), scr.data_ptr(), None), lib)
     torch.cuda.synchronize()

@@ -139,7 +139,7 @@ def geometry(w, h, bd):
     dcp.mi_rows, dcp.mi_cols, dcp.lambda_ = mi_rows, mi_cols, 3500
     ddec = torch.zeros(C.sizeof(sb.CdefDecision), dtype=torch.uint8, device="cuda")
     didx2 = torch.zeros(nfb, dtype=torch.int8, device="cuda")
-    dscr = torch.zeros(nfb * 16 + 64, dtype=torch.uint8, device="cuda")
+    dscr = torch.zeros(nfb * (16 + 16 * 64) + 64, dtype=torch.uint8, device="cuda")
     lib.svt_b200_cdef_decide.argtypes = [C.POINTER(sb.CdefDecideParams)] + [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     ms = ring_ms(lambda i: sb.check(lib.svt_b200_cdef_decide(C.byref(dcp), dmse.data_ptr(), dskip.data_ptr(), skip.shape[1], ddec.data_ptr(),
                                                              didx2.data_ptr(), dscr.data_ptr(), SP), lib), 8)
