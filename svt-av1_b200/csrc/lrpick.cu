@@ -157,7 +157,9 @@ __global__ void __launch_bounds__(ST_NT) stats_kernel(const StatsDev d, int tile
 // combined to int64 and sent to the unit's M / H with one 64-bit global atomic per entry and CTA.
 // row pitch of the staged window planes: 37 words - the 7 window rows a quarter-warp group reads in one LDS land 5 banks
 // apart (bank = 5 kr + 2 tig: conflict-free but for one pair), against 2-way conflicts on most banks with the dense 18-word
-// pitch (ncu: 42 % of the shared wavefronts were conflicts); the source planes (one reader per group) stay dense
+// pitch (ncu: 42 % of the shared wavefronts were conflicts) - which changed the run time by nothing measurable (0.107 ms
+// either way): the kernel is bound by its 12 warps / SM (116 registers), not by the shared-memory pipe; the source planes
+// (one reader per group) stay dense
 constexpr int TC_TW = 64, TC_TH = 64, TC_NT = 384, TC_PITCH = 148, TC_XPITCH = 72, TC_SLICES = 4;
 
 __device__ __forceinline__ void mma_s8(int (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
@@ -322,7 +324,9 @@ int stats_launch(StatsDev &d, int win, int hbd, int max_uw, int max_uh, cudaStre
     static const bool imad = getenv("SVT_B200_STATS_IMAD") != nullptr;
     const dim3 gs(std::min(64, (max_uw * max_uh + 255) / 256), d.n_units);
     if (!imad) {
-        // SVT_B200_STATS_MINB=2: the register-capped build of the same kernel (80 registers, 2 CTAs / SM, some spills)
+        // SVT_B200_STATS_MINB=2: the register-capped build of the same kernel (80 registers, 2 CTAs / SM, some spills).
+        // Measured slower (1080p 0.134 vs 0.105 ms, 2160p 10-bit 0.423 vs 0.344 ms): the spilled accumulators cost more than
+        // the second resident CTA hides - kept selectable for that comparison only.
         static const bool two = getenv("SVT_B200_STATS_MINB") && atoi(getenv("SVT_B200_STATS_MINB")) == 2;
         const int tiles_x = (max_uw + TC_TW - 1) / TC_TW, tiles_y = (max_uh + TC_TH - 1) / TC_TH;
         const dim3 gt(tiles_x * tiles_y, d.n_units);
