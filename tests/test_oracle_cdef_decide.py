@@ -58,3 +58,31 @@ def test_decide_restatement_matches_finish_cdef_search(case):
     assert list(out.y_strength)[:nb.value] == list(ys)[:nb.value] and list(out.uv_strength)[:nb.value] == list(uvs)[:nb.value]
     np.testing.assert_array_equal(got_fb, fbs)
     assert lam.value > 0
+
+
+@needs_ref
+def test_decide_restatement_all_blocks_skipped_and_single_block():
+    """Edge cases of finish_cdef_search: no filter block takes part (every 8x8 skipped) and a one-block picture."""
+    orc, refh = cm.oracle(), cm.refh()
+    for (mi_rows, mi_cols, all_skip) in ((34, 46, True), (16, 16, False), (9, 13, False)):
+        p = sb.CdefDecideParams()
+        n = orc.orc_cdef_decide_table(3, C.byref(p))
+        p.mi_rows, p.mi_cols = mi_rows, mi_cols
+        skip, stride, mse = decide_case(77, mi_rows, mi_cols, n, "rand")
+        if all_skip:
+            skip[...] = 1
+        else:
+            skip[...] = 0
+        nfb = mse.shape[1]
+        bits, nb, lam = C.c_int32(), C.c_int32(), C.c_uint64()
+        ys, uvs, fbs = (C.c_int32 * 8)(), (C.c_int32 * 8)(), np.zeros(nfb, np.int8)
+        assert refh.refh_cdef_finish(mi_rows, mi_cols, 120, 4, 8, cm.ptr(skip), stride, cm.ptr(mse), C.byref(bits), C.byref(nb), ys, uvs,
+                                     cm.ptr(fbs), C.byref(lam)) == 0
+        p.lambda_ = lam.value
+        out, got_fb = sb.CdefDecision(), np.zeros(nfb, np.int8)
+        orc.orc_cdef_decide(C.byref(p), cm.ptr(mse), cm.ptr(skip), stride, C.byref(out), cm.ptr(got_fb))
+        assert (out.cdef_bits, out.nb_cdef_strengths) == (bits.value, nb.value)
+        k = nb.value
+        assert list(out.y_strength)[:k] == list(ys)[:k] and list(out.uv_strength)[:k] == list(uvs)[:k]
+        np.testing.assert_array_equal(got_fb, fbs)
+        assert out.sb_count == (0 if all_skip else nfb)

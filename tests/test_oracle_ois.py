@@ -14,7 +14,7 @@ def padded_luma(w, h, seed, pad=80):
 
 
 @needs_ref
-@pytest.mark.parametrize("geom", [(128, 64), (200, 120), (352, 288), (72, 88), (640, 360)])
+@pytest.mark.parametrize("geom", [(128, 64), (200, 120), (352, 288), (72, 88), (640, 360), (16, 16), (24, 40), (1920, 1080)])
 def test_ois_dc_restatement_matches_reference(geom):
     w, h = geom
     orc, refh = cm.oracle(), cm.refh()

@@ -61,3 +61,19 @@ def test_central_and_normalize():
         want = (acc[:, :32].astype(np.int64) + (cnt[:, :32] >> 1)) // cnt[:, :32]
         np.testing.assert_array_equal(dst[:, :32], want.astype(dt))
         assert sse == int(((pre[:, :32].astype(np.int64) - want) ** 2).sum())
+
+
+@needs_ref
+def test_planewise_restatement_random_sweep():
+    """40 more random blocks (both bit depths, chroma on / off, split and unsplit, small and large motion, noise levels,
+    decay controls): every accumulator and counter equal to the reference's."""
+    orc, refh = _orc(), cm.refh()
+    rng = np.random.default_rng(2024)
+    for k in range(40):
+        kw = dict(seed=100 + k, bd=int(rng.choice([8, 10])), chroma=int(rng.integers(0, 2)), split=[None, 0, 1][int(rng.integers(0, 3))],
+                  big_motion=bool(rng.integers(0, 2)), noise=tuple(float(x) for x in rng.uniform(0, 8, 3)), decay=int(rng.integers(2, 5)),
+                  amp=int(rng.choice([1, 3, 8, 20, 50])))
+        c = tc.make_case(**kw)
+        want, got = tc.run_reference(refh, c), tc.run_oracle(orc, c)
+        for name, a, b in zip(("y_accum", "y_count", "u_accum", "u_count", "v_accum", "v_count"), got, want):
+            np.testing.assert_array_equal(a, b, err_msg="%s case %r" % (name, kw))
