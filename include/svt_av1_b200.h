@@ -9,13 +9,17 @@
  *      (Source/Lib/Encoder/Codec/aom_dsp_rtcd.h, Source/Lib/Common/Codec/common_dsp_rtcd.h).
  *      They take HOST pointers, stage through a thread-local pinned buffer + stream, run the sm_100a
  *      kernel and copy the result back.  They exist for API fidelity and parity tests; a launch per
- *      8x8 block can never be fast.  `svt_b200_install_rtcd()` hands their addresses to the patched
- *      `setup_rtcd_internal`.
+ *      8x8 block can never be fast.  The installer that assigns them to the reference's pointers is compiled next
+ *      to the reference's headers (oracle/rtcd_install.c: svt_cuda_install_rtcd(), 225 pointers, type-checked at compile
+ *      time; INTEGRATION.md section 1 shows the setup_rtcd_internal hook).
  *
  *  (2) `svt_b200_*` picture-level ("batched") entries, which are where throughput comes from.  They
  *      replace the L2 segment loops of the reference (motion_estimation_kernel, EncDec final pass,
  *      dlf_kernel, cdef_kernel, rest_kernel).  All pointers are DEVICE pointers unless the name ends
  *      in `_host`; `stream` is a `cudaStream_t` passed as `void*` (NULL = default stream).
+ *
+ *  (3) `svt_b200_engine_*`: the picture engine - HOST pictures in, host results out, synchronous and re-entrant -
+ *      which is what the reference's process loops call (integration/svt_cuda_backend.c).
  *
  * No torch / C++ types cross this boundary.  Every function returns 0 on success or a negative
  * SvtB200Status; there is NO CPU fallback — a missing GPU is an error.
