@@ -196,9 +196,112 @@ def case_convolve_forms(which):
     return out
 
 
+def case_estimate_transform(which):
+    """av1_estimate_transform's shape dispatcher: 19 sizes x 4 shapes x a few types (the coefficients the quantiser reads)."""
+    from test_oracle_txfm import allowed_types, residual_block
+    orc = cm.oracle()
+    out = b""
+    for ts in range(19):
+        w, h = sb.TX_W[ts], sb.TX_H[ts]
+        n = min(w, 32) * min(h, 32)
+        rng = np.random.default_rng(900 + ts)
+        for shape in range(4):
+            for tx_type in allowed_types(ts)[:4]:
+                res = residual_block(rng, w, h, 10, "rand")
+                a = np.zeros(w * h, np.int32)
+                if which == "oracle":
+                    orc.orc_estimate_transform(cm.ptr(res), C.c_uint32(res.shape[1]), cm.ptr(a), ts, 10, tx_type, shape)
+                else:
+                    cm.refh().refh_estimate_transform(cm.ptr(res), C.c_uint32(res.shape[1]), cm.ptr(a), ts, 10, tx_type, shape)
+                out += a[:n].tobytes()
+    return out
+
+
+def case_temporal_filter(which):
+    import tf_cases as tc
+    out = b""
+    for kw in tc.CASES:
+        c = tc.make_case(**kw)
+        res = tc.run_oracle(cm.oracle(), c) if which == "oracle" else tc.run_reference(cm.refh(), c)
+        out += b"".join(np.ascontiguousarray(a).tobytes() for a in res)
+    return out
+
+
+def case_picture_statistics(which):
+    from test_oracle_pa import sb_planes
+    orc = cm.oracle()
+    out = b""
+    rng = np.random.default_rng(40)
+    for kind in ("rand", "flat", "extreme", "smooth", "rand"):
+        y, cb, cr = sb_planes(rng, kind)
+        oy, ox = int(rng.integers(0, 24)), int(rng.integers(0, 60))
+        li, ci = oy * y.shape[1] + ox, (oy // 2) * cb.shape[1] + ox // 2
+        ym, var, cbm, crm = np.zeros(85, np.uint8), np.zeros(85, np.uint16), np.zeros(85, np.uint8), np.zeros(85, np.uint8)
+        if which == "oracle":
+            orc.orc_sb_mean_variance(C.c_void_p(y.ctypes.data + li), y.shape[1], 0, cm.ptr(ym), cm.ptr(var))
+            orc.orc_sb_chroma_mean(C.c_void_p(cb.ctypes.data + ci), cb.shape[1], 0, cm.ptr(cbm))
+            orc.orc_sb_chroma_mean(C.c_void_p(cr.ctypes.data + ci), cr.shape[1], 0, cm.ptr(crm))
+        else:
+            cm.refh().refh_sb_mean_variance(cm.ptr(y), y.shape[1], li, cm.ptr(cb), cm.ptr(cr), cb.shape[1], ci, 0, cm.ptr(ym), cm.ptr(var), cm.ptr(cbm),
+                                            cm.ptr(crm))
+        out += ym.tobytes() + var.tobytes() + cbm[:21].tobytes() + crm[:21].tobytes()
+    return out
+
+
+def case_open_loop_intra(which):
+    from test_oracle_ois import padded_luma
+    out = b""
+    for (w, h) in ((200, 120), (352, 288), (72, 88)):
+        buf, pad = padded_luma(w, h, 60 + w)
+        mbw, mbh = (w + 15) // 16, (h + 15) // 16
+        cost, mode = np.zeros(mbw * mbh, np.int64), np.zeros(mbw * mbh, np.int32)
+        if which == "oracle":
+            cm.oracle().orc_ois_dc_picture(C.c_void_p(buf.ctypes.data + pad * buf.shape[1] + pad), buf.shape[1], w, h, cm.ptr(cost))
+        else:
+            cm.refh().refh_ois_picture(cm.ptr(buf), buf.shape[1], pad, pad, w, h, 8, cm.ptr(cost), cm.ptr(mode))
+        out += cost.tobytes()
+    return out
+
+
+# full_lambda the reference derives (compute_rdmult_sse) for the harness's picture control set at qindex = 4 * key, 8 bit
+GOLDEN_LAMBDAS = {43: 257491, 20: 20078, 50: 554843, 30: 55473, 35: 101038}
+
+
+def case_cdef_decide(which):
+    """finish_cdef_search on synthetic mse tables; the lambda of each case is a fixed number recorded with the reference run
+    (it only depends on qindex / bit depth for the zeroed picture control set of the harness)."""
+    from test_oracle_cdef_decide import decide_case
+    LAMBDAS = GOLDEN_LAMBDAS
+    out = b""
+    for seed, pick, mi_rows, mi_cols, qidx, kind in ((0, 3, 68, 120, 43, "smooth"), (1, 3, 68, 120, 20, "rand"), (2, 2, 45, 80, 50, "smooth"),
+                                                      (3, 1, 45, 80, 30, "ties"), (4, 0, 34, 46, 35, "smooth")):
+        p = sb.CdefDecideParams()
+        n = cm.oracle().orc_cdef_decide_table(pick, C.byref(p))
+        p.mi_rows, p.mi_cols = mi_rows, mi_cols
+        skip, stride, mse = decide_case(seed, mi_rows, mi_cols, n, kind)
+        nfb = mse.shape[1]
+        fbs = np.zeros(nfb, np.int8)
+        if which == "oracle":
+            p.lambda_ = LAMBDAS[qidx]
+            o = sb.CdefDecision()
+            cm.oracle().orc_cdef_decide(C.byref(p), cm.ptr(mse), cm.ptr(skip), stride, C.byref(o), cm.ptr(fbs))
+            bits, nb, ys, uvs = o.cdef_bits, o.nb_cdef_strengths, list(o.y_strength), list(o.uv_strength)
+        else:
+            b_, n_, lam = C.c_int32(), C.c_int32(), C.c_uint64()
+            y8, uv8 = (C.c_int32 * 8)(), (C.c_int32 * 8)()
+            cm.refh().refh_cdef_finish(mi_rows, mi_cols, qidx * 4, {0: 1, 1: 2, 2: 3, 3: 4}[pick], 8, cm.ptr(skip), stride, cm.ptr(mse), C.byref(b_),
+                                       C.byref(n_), y8, uv8, cm.ptr(fbs), C.byref(lam))
+            assert lam.value == LAMBDAS[qidx], (qidx, lam.value)
+            bits, nb, ys, uvs = b_.value, n_.value, list(y8), list(uv8)
+        out += bytes([bits, nb]) + np.array(ys[:nb] + uvs[:nb], np.int32).tobytes() + fbs.tobytes()
+    return out
+
+
 CASES = {"me_picture": case_me, "encode_tus": case_encode, "dlf_frame": case_dlf, "cdef_search_apply": case_cdef, "lr_frame": case_lr,
          "inter_predict": case_inter, "subpel_search": case_subpel, "me_downsample": case_downsample,
-         "pick_filter_level": case_pick_filter_level, "convolve_forms": case_convolve_forms}
+         "pick_filter_level": case_pick_filter_level, "convolve_forms": case_convolve_forms, "estimate_transform_shapes": case_estimate_transform,
+         "temporal_filter_planewise": case_temporal_filter, "picture_statistics": case_picture_statistics, "open_loop_intra_dc": case_open_loop_intra,
+         "cdef_decide": case_cdef_decide}
 
 
 def digest(name, which):
