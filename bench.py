@@ -314,7 +314,10 @@ def encoder_roofline(hp_roof):
                 "note": "the dominant kernels of this path (CDEF strength search, ME) are integer-ALU bound by their arithmetic (SURVEY 8d): "
                         "`alu` is the meaningful fraction for them, the HBM fraction is reported because the contract asks for it; the "
                         "streaming stage is deblocking (tools/kernel_bench.py: 12 % of HBM peak at 1080p where a plain copy of the same "
-                        "picture reaches 26 %, 28 % at 2160p 10-bit where the copy reaches 74 %)"})
+                        "picture reaches 26 %, 28 % at 2160p 10-bit where the copy reaches 74 %).  The shares come from the launch list "
+                        "committed before the CDEF strength decision moved to the device: cdef_decide_kernel adds one single-CTA launch "
+                        "per picture (0.9 ms at 1080p on 1 of 148 SMs, profiles/r2g_kernel_bench.json) - a latency chain, not a "
+                        "throughput kernel, so it is not the kernel a roofline describes"})
     return out
 
 
